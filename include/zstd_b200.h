@@ -1,0 +1,103 @@
+/*
+ * zstd_b200.h -- C ABI of libzstdb200.so, the B200-native drop-in for the ZstdSharp hot path
+ * (many independent zstd frames: decompress any level, compress levels 1..3).
+ *
+ * The first block mirrors, name for name and argument for argument, the native zstd entry points the
+ * reference already binds through P/Invoke (reference: src/Zstd.Extern/ExternMethods.cs:8-37,
+ * DllImport("libzstd", CallingConvention.Cdecl)); binding ZstdSharp to this library is a DllName change
+ * (see INTEGRATION.md).  The functions replace the managed implementations
+ *     ZSTD_compress2        src/ZstdSharp/Unsafe/ZstdCompress.cs:7138   (called by Compressor.Wrap, Compressor.cs:78-96)
+ *     ZSTD_compressCCtx     src/ZstdSharp/Unsafe/ZstdCompress.cs:5772   (called by Benchmark.cs:62-70)
+ *     ZSTD_decompressDCtx   src/ZstdSharp/Unsafe/ZstdDecompress.cs:1365 (called by Decompressor.Unwrap, Decompressor.cs:62-88)
+ *     ZSTD_decompressBound  src/ZstdSharp/Unsafe/ZstdDecompress.cs:971  (called by Decompressor.GetDecompressedSize, :50-54)
+ *     ZSTD_compressBound    src/ZstdSharp/Unsafe/ZstdCompress.cs:19
+ *     ZSTD_CCtx_setParameter src/ZstdSharp/Unsafe/ZstdCompress.cs:784   (Compressor.Level setter, Compressor.cs:16-33)
+ *     ZSTD_isError / ZSTD_getErrorName  src/ZstdSharp/Unsafe/ZstdCommon.cs:26,33 (ThrowHelper.cs:10-16)
+ * Conventions kept from the reference: size_t results, error <=> result > (size_t)-120 with code = 0 - result
+ * (Unsafe/ErrorPrivate.cs:10-13, Unsafe/ZSTD_ErrorCode.cs:5-35); caller owns src/dst and the library never
+ * retains them after a call; a context is single-threaded, distinct contexts may run concurrently
+ * (ZstdNetTests.cs:498-522).
+ *
+ * All compute runs on the GPU (CUDA, sm_100a).  There is no CPU fallback: without a usable device every
+ * compress/decompress entry point returns ZSTD_error_GENERIC and ZSTDB200_lastErrorString() says why.
+ *
+ * The second block (ZSTDB200_*) is new: the batch frame scheduler the reference does not have.
+ */
+#ifndef ZSTD_B200_H
+#define ZSTD_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#  define ZSTDB200_API __attribute__((visibility("default")))
+#else
+#  define ZSTDB200_API
+#endif
+
+typedef struct ZSTD_CCtx_s ZSTD_CCtx;
+typedef struct ZSTD_DCtx_s ZSTD_DCtx;
+
+/* ---- zstd-named surface (ExternMethods.cs:10-37) ---- */
+ZSTDB200_API ZSTD_CCtx* ZSTD_createCCtx(void);                                                   /* ExternMethods.cs:11 */
+ZSTDB200_API size_t     ZSTD_freeCCtx(ZSTD_CCtx* cctx);                                           /* :14 */
+ZSTDB200_API size_t     ZSTD_compressCCtx(ZSTD_CCtx* cctx, void* dst, size_t dstCapacity,
+                                          const void* src, size_t srcSize, int compressionLevel);  /* :17 */
+ZSTDB200_API size_t     ZSTD_compress2(ZSTD_CCtx* cctx, void* dst, size_t dstCapacity,
+                                       const void* src, size_t srcSize);                           /* :21 */
+ZSTDB200_API ZSTD_DCtx* ZSTD_createDCtx(void);                                                   /* :24 */
+ZSTDB200_API size_t     ZSTD_freeDCtx(ZSTD_DCtx* dctx);                                           /* :27 */
+ZSTDB200_API size_t     ZSTD_decompressDCtx(ZSTD_DCtx* dctx, void* dst, size_t dstCapacity,
+                                            const void* src, size_t srcSize);                      /* :30 */
+ZSTDB200_API size_t     ZSTD_compressBound(size_t srcSize);                                        /* :34 */
+/* param: ZSTD_c_compressionLevel = 100 (levels 0..3; 0 means 3), ZSTD_c_checksumFlag = 201 (0 only in this round);
+ * anything else -> ZSTD_error_parameter_unsupported. */
+ZSTDB200_API size_t     ZSTD_CCtx_setParameter(ZSTD_CCtx* cctx, int param, int value);             /* :37 */
+/* needed by the safe wrappers in addition (Decompressor.cs:53, ThrowHelper.cs:12-13) */
+ZSTDB200_API unsigned long long ZSTD_decompressBound(const void* src, size_t srcSize);
+ZSTDB200_API unsigned    ZSTD_isError(size_t code);
+ZSTDB200_API const char* ZSTD_getErrorName(size_t code);
+ZSTDB200_API unsigned    ZSTD_versionNumber(void);
+ZSTDB200_API const char* ZSTD_versionString(void);
+
+/* ---- batch frame scheduler (new; no reference counterpart) ----
+ * n independent items; item i is decompressed/compressed exactly as the single-call API would, and result[i]
+ * receives what that call would have returned (size or error code): a bad item never poisons the batch.
+ * The function's own return value is 0, or an error code when the batch as a whole could not run
+ * (no device, out of memory).  src/dst are HOST pointers; adjacent buffers (src[i]+srcSize[i]==src[i+1]) are
+ * moved with one DMA per run, so callers that keep a batch contiguous in pinned memory get full PCIe rate. */
+ZSTDB200_API size_t ZSTDB200_decompressBatch(ZSTD_DCtx* dctx, size_t n,
+                                             const void* const* src, const size_t* srcSize,
+                                             void* const* dst, const size_t* dstCapacity, size_t* result);
+ZSTDB200_API size_t ZSTDB200_compressBatch(ZSTD_CCtx* cctx, size_t n, int compressionLevel,
+                                           const void* const* src, const size_t* srcSize,
+                                           void* const* dst, const size_t* dstCapacity, size_t* result);
+
+/* Device-resident variants: d_src / d_dst are DEVICE pointers on the context's GPU; offsets, sizes and results are
+ * host arrays.  Used when frames already live in HBM (and by bench.py's kernel-only timing). */
+ZSTDB200_API size_t ZSTDB200_decompressBatchDevice(ZSTD_DCtx* dctx, size_t n,
+                                                   const void* d_src, const uint64_t* srcOffset, const size_t* srcSize,
+                                                   void* d_dst, const uint64_t* dstOffset, const size_t* dstCapacity,
+                                                   size_t* result);
+ZSTDB200_API size_t ZSTDB200_compressBatchDevice(ZSTD_CCtx* cctx, size_t n, int compressionLevel,
+                                                 const void* d_src, const uint64_t* srcOffset, const size_t* srcSize,
+                                                 void* d_dst, const uint64_t* dstOffset, const size_t* dstCapacity,
+                                                 size_t* result);
+
+/* ---- instrumentation ---- */
+/* Milliseconds (CUDA events on the context's stream) of the last batch call: [0] host->device, [1] all kernels,
+ * [2] device->host, [3..] per-kernel slots (decode: scan, setup, huf, seq, exec; encode: match, entropy). */
+#define ZSTDB200_TIMING_SLOTS 12
+ZSTDB200_API void     ZSTDB200_getLastTimings(const void* ctx, float* msOut /* [ZSTDB200_TIMING_SLOTS] */);
+ZSTDB200_API unsigned ZSTDB200_getLastLaunchCount(const void* ctx);   /* kernels launched by the last batch call */
+ZSTDB200_API const char* ZSTDB200_lastErrorString(void);              /* thread-local description of the last library-level failure */
+ZSTDB200_API int      ZSTDB200_deviceCount(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ZSTD_B200_H */

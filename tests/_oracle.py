@@ -1,0 +1,180 @@
+"""Test-side access to the CPU oracle (oracle/) and to system libzstd 1.5.5 (second, independent checker).
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may use these.
+"""
+from __future__ import annotations
+
+import ctypes
+import ctypes.util
+import os
+import subprocess
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ORACLE_DIR = os.path.join(ROOT, "oracle")
+ORACLE_LIB = os.path.join(ORACLE_DIR, "_build", "libzo.so")
+
+
+def build_oracle(force: bool = False) -> str:
+    srcs = [os.path.join(ORACLE_DIR, f) for f in ("zo_decode.c", "zo_encode.c", "zo_common.h", "zo.h")]
+    if force or not os.path.exists(ORACLE_LIB) or any(os.path.getmtime(s) > os.path.getmtime(ORACLE_LIB) for s in srcs):
+        os.makedirs(os.path.dirname(ORACLE_LIB), exist_ok=True)
+        subprocess.check_call(["gcc", "-O2", "-g", "-fPIC", "-std=gnu11", "-shared", "-o", ORACLE_LIB,
+                               os.path.join(ORACLE_DIR, "zo_decode.c"), os.path.join(ORACLE_DIR, "zo_encode.c")])
+    return ORACLE_LIB
+
+
+def _sig(fn, res, args):
+    fn.restype = res
+    fn.argtypes = args
+
+
+class Oracle:
+    def __init__(self):
+        self.lib = ctypes.CDLL(build_oracle())
+        L = self.lib
+        vp, st, ci = ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int
+        _sig(L.zo_compress, st, [vp, st, vp, st, ci])
+        _sig(L.zo_compress_advanced, st, [vp, st, vp, st, ci, ci])
+        _sig(L.zo_decompress, st, [vp, st, vp, st])
+        _sig(L.zo_compressBound, st, [st])
+        _sig(L.zo_decompressBound, ctypes.c_ulonglong, [vp, st])
+        _sig(L.zo_isError, ctypes.c_uint, [st])
+        _sig(L.zo_getErrorCode, ci, [st])
+        _sig(L.zo_getErrorName, ctypes.c_char_p, [st])
+        _sig(L.zo_getCParams, None, [ci, st, ctypes.POINTER(ctypes.c_uint)])
+        _sig(L.zo_matchfinder_block, st, [ci, vp, st, vp, vp, ctypes.POINTER(st), ctypes.POINTER(ctypes.c_uint32), ctypes.POINTER(ctypes.c_uint32)])
+        _sig(L.zo_decode_first_block_stages, st, [vp, st, vp, st, ctypes.POINTER(st), vp, st])
+
+    @staticmethod
+    def _buf(data):
+        a = np.frombuffer(data, dtype=np.uint8) if not isinstance(data, np.ndarray) else np.ascontiguousarray(data, dtype=np.uint8)
+        return a, (a.ctypes.data if a.size else 0)
+
+    def compress_raw(self, data, level: int, cap: int | None = None, checksum: int = 0):
+        a, p = self._buf(data)
+        cap = self.lib.zo_compressBound(a.size) if cap is None else cap
+        out = np.empty(max(cap, 1), dtype=np.uint8)
+        r = self.lib.zo_compress_advanced(out.ctypes.data, cap, p, a.size, level, checksum)
+        return r, out
+
+    def compress(self, data, level: int, checksum: int = 0) -> bytes:
+        r, out = self.compress_raw(data, level, checksum=checksum)
+        assert not self.lib.zo_isError(r), self.lib.zo_getErrorName(r)
+        return out[:r].tobytes()
+
+    def decompress_raw(self, frame, cap: int):
+        a, p = self._buf(frame)
+        out = np.empty(max(cap, 1), dtype=np.uint8)
+        r = self.lib.zo_decompress(out.ctypes.data, cap, p, a.size)
+        return r, out
+
+    def decompress(self, frame, cap: int) -> bytes:
+        r, out = self.decompress_raw(frame, cap)
+        assert not self.lib.zo_isError(r), self.lib.zo_getErrorName(r)
+        return out[:r].tobytes()
+
+    def error_code(self, rv: int) -> int:
+        return self.lib.zo_getErrorCode(rv)
+
+    def decompress_bound(self, frame) -> int:
+        a, p = self._buf(frame)
+        return int(self.lib.zo_decompressBound(p, a.size))
+
+    def cparams(self, level: int, n: int):
+        out = (ctypes.c_uint * 7)()
+        self.lib.zo_getCParams(level, n, out)
+        return tuple(out)
+
+    def matchfinder(self, data, level: int):
+        a, p = self._buf(data)
+        seqs = np.zeros((a.size // 3 + 2, 2), dtype=np.uint32)   # zo_seqDef = {u32 offset; u16 ll; u16 ml}
+        lits = np.zeros(a.size + 32, dtype=np.uint8)
+        litSize = ctypes.c_size_t(0)
+        ll = (ctypes.c_uint32 * 2)()
+        rep = (ctypes.c_uint32 * 3)()
+        n = self.lib.zo_matchfinder_block(level, p, a.size, seqs.ctypes.data, lits.ctypes.data, ctypes.byref(litSize), ll, rep)
+        assert not self.lib.zo_isError(n)
+        s = seqs[:n]
+        off = s[:, 0].copy()
+        llv = (s[:, 1] & 0xFFFF).astype(np.uint32)
+        mlv = (s[:, 1] >> 16).astype(np.uint32)
+        return off, llv, mlv, lits[:litSize.value].copy(), (ll[0], ll[1]), tuple(rep)
+
+    def decode_stages(self, frame):
+        a, p = self._buf(frame)
+        lits = np.zeros(131072 + 64, dtype=np.uint8)
+        litSize = ctypes.c_size_t(0)
+        triples = np.zeros((65536, 3), dtype=np.uint32)
+        n = self.lib.zo_decode_first_block_stages(p, a.size, lits.ctypes.data, lits.size, ctypes.byref(litSize), triples.ctypes.data, 65536)
+        assert not self.lib.zo_isError(n), self.lib.zo_getErrorName(n)
+        return lits[:litSize.value].copy(), triples[:n].copy()
+
+
+class LibZstd:
+    """System libzstd 1.5.5: the upstream C the reference is a translation of (at v1.5.1)."""
+
+    def __init__(self):
+        name = ctypes.util.find_library("zstd") or "libzstd.so.1"
+        self.lib = ctypes.CDLL(name)
+        L = self.lib
+        vp, st, ci = ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int
+        _sig(L.ZSTD_compress, st, [vp, st, vp, st, ci])
+        _sig(L.ZSTD_decompress, st, [vp, st, vp, st])
+        _sig(L.ZSTD_compressBound, st, [st])
+        _sig(L.ZSTD_isError, ctypes.c_uint, [st])
+        _sig(L.ZSTD_getErrorCode, ci, [st])
+        _sig(L.ZSTD_versionNumber, ctypes.c_uint, [])
+        _sig(L.ZSTD_decompressBound, ctypes.c_ulonglong, [vp, st])
+        _sig(L.ZSTD_createCCtx, vp, [])
+        _sig(L.ZSTD_freeCCtx, st, [vp])
+        _sig(L.ZSTD_CCtx_setParameter, st, [vp, ci, ci])
+        _sig(L.ZSTD_compress2, st, [vp, vp, st, vp, st])
+
+    def compress(self, data, level: int, checksum: int = 0) -> bytes:
+        a, p = Oracle._buf(data)
+        cap = self.lib.ZSTD_compressBound(a.size)
+        out = np.empty(max(cap, 1), dtype=np.uint8)
+        if checksum:
+            c = self.lib.ZSTD_createCCtx()
+            self.lib.ZSTD_CCtx_setParameter(c, 100, level)
+            self.lib.ZSTD_CCtx_setParameter(c, 201, 1)
+            r = self.lib.ZSTD_compress2(c, out.ctypes.data, cap, p, a.size)
+            self.lib.ZSTD_freeCCtx(c)
+        else:
+            r = self.lib.ZSTD_compress(out.ctypes.data, cap, p, a.size, level)
+        assert not self.lib.ZSTD_isError(r)
+        return out[:r].tobytes()
+
+    def decompress_raw(self, frame, cap: int):
+        a, p = Oracle._buf(frame)
+        out = np.empty(max(cap, 1), dtype=np.uint8)
+        r = self.lib.ZSTD_decompress(out.ctypes.data, cap, p, a.size)
+        return r, out
+
+    def decompress(self, frame, cap: int) -> bytes:
+        r, out = self.decompress_raw(frame, cap)
+        assert not self.lib.ZSTD_isError(r)
+        return out[:r].tobytes()
+
+    def error_code(self, rv: int) -> int:
+        return self.lib.ZSTD_getErrorCode(rv)
+
+
+_ORACLE = None
+_LIBZSTD = None
+
+
+def oracle() -> Oracle:
+    global _ORACLE
+    if _ORACLE is None:
+        _ORACLE = Oracle()
+    return _ORACLE
+
+
+def libzstd() -> LibZstd:
+    global _LIBZSTD
+    if _LIBZSTD is None:
+        _LIBZSTD = LibZstd()
+    return _LIBZSTD

@@ -1,0 +1,147 @@
+"""GPU parity: batch decompression through the C ABI must be bit-exact with the oracle (and libzstd 1.5.5).
+
+Mirrors the reference's differential strategy (src/ZstdSharp.Test/ZstdTest.cs:69-90) with the oracle in the role
+of the native library, and the behavioural set of ZstdNetTests.cs (sizes sweep :478-496, empty/1-byte :456-476,
+dst too small :214-258, invalid data :166-177, malformed content size :179-212).
+"""
+import numpy as np
+import pytest
+
+from zstdsharp_b200 import datagen as dg
+
+from _oracle import oracle, libzstd
+
+pytestmark = pytest.mark.gpu
+
+FRAME = dg.FRAME
+
+
+@pytest.fixture(scope="module")
+def dec():
+    from zstdsharp_b200 import Decompressor
+    d = Decompressor()
+    yield d
+    d.Dispose()
+
+
+def _chunks(data: np.ndarray, size: int = FRAME):
+    return [data[i:i + size] for i in range(0, data.size, size)]
+
+
+@pytest.mark.parametrize("workload", ["text", "silesia", "incompressible", "literal_heavy", "literal_mix"])
+@pytest.mark.parametrize("level", [1, 3])
+def test_batch_bit_exact_vs_oracle(dec, workload, level):
+    o = oracle()
+    data = dg.WORKLOADS[workload](16 * FRAME)
+    chunks = _chunks(data)
+    frames = [o.compress(c, level) for c in chunks]
+    outs = dec.UnwrapBatch(frames)
+    assert dec.launch_count() > 0
+    for c, f, out in zip(chunks, frames, outs):
+        assert out == o.decompress(f, FRAME)          # bit-exact with the oracle's Unwrap
+        assert out == c.tobytes()
+
+
+def test_size_sweep_byte_ramp(dec):
+    """ZstdNetTests.cs:478-496: sizes 2..100000 step 3000 of (byte)i data, plus empty and 1-byte inputs."""
+    o = oracle()
+    sizes = [0, 1] + list(range(2, 100000, 3000))
+    srcs = [dg.byte_ramp(n) for n in sizes]
+    for level in (1, 3):
+        frames = [o.compress(s, level) for s in srcs]
+        outs = dec.UnwrapBatch(frames)
+        for s, out in zip(srcs, outs):
+            assert out == s.tobytes()
+
+
+def test_single_call_api(dec):
+    o = oracle()
+    src = dg.text_like(FRAME)
+    f = o.compress(src, 1)
+    assert dec.Unwrap(f) == src.tobytes()
+    assert dec.GetDecompressedSize(f) == FRAME
+
+
+def test_multiblock_and_multiframe(dec):
+    """Frames larger than one block (cross-block repcodes / repeat tables / window) and concatenated frames."""
+    o = oracle()
+    z = libzstd()
+    big = dg.text_like(8 * FRAME)[: 5 * FRAME + 12345]
+    for comp in (lambda d: o.compress(d, 1), lambda d: z.compress(d, 3), lambda d: z.compress(d, 9), lambda d: z.compress(d, 19)):
+        f = comp(big)
+        assert dec.Unwrap(f) == big.tobytes()
+    a, b = dg.text_like(FRAME), dg.literal_heavy(FRAME)
+    skippable = (0x184D2A53).to_bytes(4, "little") + (7).to_bytes(4, "little") + b"skipme!"
+    cat = o.compress(a, 1) + skippable + o.compress(b, 3) + skippable
+    assert dec.Unwrap(cat) == a.tobytes() + b.tobytes()
+
+
+def test_higher_levels_and_checksum_frames_from_libzstd(dec):
+    """Decode side must accept any conformant frame (any level); checksum frames carry a 4-byte trailer."""
+    z = libzstd()
+    data = dg.silesia_mix(8 * FRAME)
+    frames, want = [], []
+    for i, c in enumerate(_chunks(data)):
+        lvl = [1, 2, 3, 5, 7, 12, 16, 19][i % 8]
+        frames.append(z.compress(c, lvl, checksum=i & 1))
+        want.append(c.tobytes())
+    assert dec.UnwrapBatch(frames) == want
+
+
+def test_error_parity(dec):
+    from zstdsharp_b200 import ZstdException, ZSTD_ErrorCode
+    o = oracle()
+    src = dg.text_like(FRAME)
+    f = bytearray(o.compress(src, 1))
+    # dst too small -> code 70 and TryUnwrap false (ZstdNetTests.cs:214-258, 399-454)
+    small = np.empty(20, dtype=np.uint8)
+    with pytest.raises(ZstdException) as e:
+        dec.Unwrap(bytes(f), small)
+    assert e.value.Code == ZSTD_ErrorCode.dstSize_tooSmall
+    assert dec.TryUnwrap(bytes(f), small) == (False, 0)
+    assert o.error_code(o.decompress_raw(bytes(f), 20)[0]) == 70
+    # not zstd data (ZstdNetTests.cs:166-177)
+    junk = bytes(range(1, 200))
+    with pytest.raises(ZstdException):
+        dec.Unwrap(junk)
+    r = dec.UnwrapBatch([junk, bytes(f)], raise_on_error=False)
+    assert isinstance(r[0], ZstdException) and r[1] == src.tobytes()      # a bad frame must not poison the batch
+    # malformed frame content size (ZstdNetTests.cs:179-212): descriptor byte then corrupt the FCS
+    small_src = bytes(range(100)) * 2
+    g = bytearray(o.compress(small_src, 1))
+    assert g[4] == 0x60 or g[4] == 0x20      # single segment, fcs code by size
+    g[5] ^= 0x01
+    out = np.empty(4096, dtype=np.uint8)
+    with pytest.raises(ZstdException) as e:
+        dec.Unwrap(bytes(g), out)
+    assert e.value.Code == o.error_code(o.decompress_raw(bytes(g), 4096)[0])
+    # truncated frame
+    t = bytes(f[: len(f) // 2])
+    rv, _ = o.decompress_raw(t, FRAME)
+    with pytest.raises(ZstdException) as e:
+        dec.Unwrap(t, np.empty(FRAME, dtype=np.uint8))
+    assert e.value.Code == o.error_code(rv)
+
+
+def test_corrupted_payload_never_crashes(dec):
+    """Bit flips inside the block payload: the GPU decoder must return either the oracle's bytes or an error."""
+    from zstdsharp_b200 import ZstdException
+    o = oracle()
+    rng = np.random.default_rng(7)
+    src = dg.text_like(FRAME)
+    f = o.compress(src, 1)
+    frames = []
+    for _ in range(64):
+        g = bytearray(f)
+        pos = int(rng.integers(12, len(g)))
+        g[pos] ^= 1 << int(rng.integers(0, 8))
+        frames.append(bytes(g))
+    res = dec.UnwrapBatch(frames, raise_on_error=False)
+    for g, r in zip(frames, res):
+        rv, out = o.decompress_raw(g, FRAME)
+        if not o.lib.zo_isError(rv):
+            # the oracle (= reference semantics) accepted the damaged frame: if we accept too, bytes must agree
+            if not isinstance(r, ZstdException):
+                assert r == out[:rv].tobytes()
+        else:
+            assert isinstance(r, ZstdException)

@@ -1,0 +1,1011 @@
+// zb_decode.cu -- batch Zstandard frame decoder for sm_100a (product code; no CPU fallback).
+//
+// Replaces, for batches of independent frames, the reference's
+//   ZSTD_decompressDCtx -> ZSTD_decompressMultiFrame -> ZSTD_decompressFrame        (ZstdDecompress.cs:1365,1216,1062)
+//     -> ZSTD_decompressBlock_internal                                             (ZstdDecompressBlock.cs:3090)
+//        -> ZSTD_decodeLiteralsBlock / HUF_decompress{1,4}X1_usingDTable           (:88, HufDecompress.cs:312,342)
+//        -> ZSTD_decodeSeqHeaders / ZSTD_buildFSETable                             (:1845, :1571)
+//        -> ZSTD_decompressSequences_body = ZSTD_decodeSequence + ZSTD_execSequence (:2668, :2360, :2187)
+// Kernels (one wave = the k-th block of every item):
+//   dec_scan_kernel      thread / item   counts blocks (number of waves), initialises cursors
+//   dec_setup_kernel     warp   / item   frame+block+literal+sequence headers, Huffman and FSE table construction
+//   dec_huf_kernel       lane   / stream HUF 4-stream (or single) literal decoding, tables staged in shared memory
+//   dec_seq_kernel       lane   / item   3-state FSE sequence decoding (serial chain), tables staged in shared memory
+//   dec_exec_kernel      CTA    / item   literal + match copies through a shared-memory output tile, raw/RLE blocks
+#include "zb_decode.cuh"
+
+namespace zb {
+
+// =====================================================================================================
+//  Exact little restatement of BIT_DStream_t for the tiny FSE-compressed Huffman weight stream
+//  (Bitstream.cs:172-425).  Only used on <= 128-byte streams by one lane; speed is irrelevant, the
+//  end-of-stream semantics (FSE_decompress_usingDTable_generic, FseDecompress.cs:230) are what matters.
+// =====================================================================================================
+struct SmallDStream {
+    uint64_t container; uint32_t consumed; int32_t ptr; int32_t size; const uint8_t* base;
+    __device__ uint64_t load64(int32_t at) const {   // MEM_readLEST at base+at; bytes outside the stream read as 0
+        uint64_t v = 0;
+        for (int i = 0; i < 8; i++) { int32_t a = at + i; uint32_t b = (a >= 0 && a < size) ? base[a] : 0u; v |= (uint64_t)b << (8 * i); }
+        return v;
+    }
+    __device__ bool init(const uint8_t* b, int32_t n) {
+        base = b; size = n;
+        if (n < 1) return false;
+        uint32_t last = b[n - 1];
+        if (last == 0) return false;
+        if (n >= 8) { ptr = n - 8; container = load64(ptr); consumed = 8 - highbit32(last); }
+        else { ptr = 0; container = load64(0); consumed = 8 - highbit32(last) + (uint32_t)(8 - n) * 8; }
+        return true;
+    }
+    __device__ uint32_t read(uint32_t nb) {   // BIT_readBits (masked shift, as in BIT_getMiddleBits)
+        uint32_t start = 64u - consumed - nb;
+        uint64_t v = (container >> (start & 63)) & ((1ull << nb) - 1);
+        consumed += nb;
+        return (uint32_t)v;
+    }
+    // BIT_reloadDStream: 0 unfinished, 1 endOfBuffer, 2 completed, 3 overflow
+    __device__ int reload() {
+        if (consumed > 64) return 3;
+        if (ptr >= 8) { ptr -= (int32_t)(consumed >> 3); consumed &= 7; container = load64(ptr); return 0; }
+        if (ptr == 0) return consumed < 64 ? 1 : 2;
+        uint32_t nbBytes = consumed >> 3; int res = 0;
+        if ((int32_t)nbBytes > ptr) { nbBytes = (uint32_t)ptr; res = 1; }
+        ptr -= (int32_t)nbBytes; consumed -= nbBytes * 8; container = load64(ptr);
+        return res;
+    }
+};
+
+// FSE_readNCount_body (EntropyCommon.cs:52).  Clean forward bit reader; bits past the end read as zero and
+// make the header invalid (the reference reaches the same verdict through its bitCount > 32 test).
+// Returns bytes consumed, or 0 on error.
+__device__ uint32_t fse_read_ncount(int16_t* norm, uint32_t* maxSVPtr, uint32_t* tableLogPtr, const uint8_t* src, uint32_t hbSize)
+{
+    uint32_t const maxSV1 = *maxSVPtr + 1;
+    uint64_t acc = 0; uint32_t accBits = 0; uint32_t bytePos = 0; uint32_t bitsUsed = 0;
+    auto fill = [&]() { while (accBits <= 56) { uint64_t b = bytePos < hbSize ? src[bytePos] : 0u; acc |= b << accBits; accBits += 8; bytePos++; } };
+    auto take = [&](uint32_t nb) { acc >>= nb; accBits -= nb; bitsUsed += nb; };
+    for (uint32_t s = 0; s < maxSV1; s++) norm[s] = 0;
+    fill();
+    int nbBits = (int)(acc & 0xF) + 5;
+    if (nbBits > 15) return 0;
+    take(4);
+    *tableLogPtr = (uint32_t)nbBits;
+    int remaining = (1 << nbBits) + 1;
+    int threshold = 1 << nbBits;
+    nbBits++;
+    uint32_t charnum = 0; bool previous0 = false;
+    for (;;) {
+        if (previous0) {
+            fill();
+            while ((acc & 3) == 3) { charnum += 3; take(2); fill(); if (charnum >= maxSV1 + 64) return 0; }
+            charnum += (uint32_t)(acc & 3); take(2);
+            if (charnum >= maxSV1) break;
+        }
+        fill();
+        {   int const max = (2 * threshold - 1) - remaining;
+            int count;
+            if ((int)(acc & (uint32_t)(threshold - 1)) < max) { count = (int)(acc & (uint32_t)(threshold - 1)); take((uint32_t)nbBits - 1); }
+            else { count = (int)(acc & (uint32_t)(2 * threshold - 1)); if (count >= threshold) count -= max; take((uint32_t)nbBits); }
+            count--;
+            if (count >= 0) remaining -= count; else remaining += count;
+            norm[charnum++] = (int16_t)count;
+            previous0 = (count == 0);
+            if (remaining < threshold) {
+                if (remaining <= 1) break;
+                nbBits = (int)highbit32((uint32_t)remaining) + 1;
+                threshold = 1 << (nbBits - 1);
+            }
+            if (charnum >= maxSV1) break;
+        }
+    }
+    if (remaining != 1) return 0;
+    if (charnum > maxSV1) return 0;
+    if (bitsUsed > 8 * hbSize) return 0;
+    *maxSVPtr = charnum - 1;
+    return (bitsUsed + 7) >> 3;
+}
+
+// Symbol spread shared by FSE_buildDTable_internal (FseDecompress.cs:25) and ZSTD_buildFSETable_body
+// (ZstdDecompressBlock.cs:1571).  cell[] receives the symbol of every state, symNext[] the first "next" value.
+__device__ bool fse_spread(uint8_t* cell, uint16_t* symNext, const int16_t* norm, uint32_t maxSV, uint32_t tableLog)
+{
+    uint32_t const tableSize = 1u << tableLog, tableMask = tableSize - 1;
+    uint32_t const step = (tableSize >> 1) + (tableSize >> 3) + 3;
+    uint32_t high = tableSize - 1, position = 0;
+    for (uint32_t s = 0; s <= maxSV; s++) {
+        if (norm[s] == -1) { cell[high--] = (uint8_t)s; symNext[s] = 1; } else symNext[s] = (uint16_t)norm[s];
+    }
+    for (uint32_t s = 0; s <= maxSV; s++) {
+        for (int i = 0; i < norm[s]; i++) {
+            cell[position] = (uint8_t)s;
+            position = (position + step) & tableMask;
+            while (position > high) position = (position + step) & tableMask;
+        }
+    }
+    return position == 0;
+}
+
+// Per-warp scratch of the setup kernel
+struct SetupScratch {
+    uint8_t weights[260];
+    uint8_t cell[512];
+    uint16_t symNext[64];
+    uint16_t start[260];
+    int16_t norm[64];
+    uint32_t rankStart[16];
+};
+
+// HUF_readStats_body (EntropyCommon.cs:292) executed by one lane. Returns header size (iSize+1) or 0 on error.
+__device__ uint32_t huf_read_stats(SetupScratch& sc, uint32_t* nbSymbolsPtr, uint32_t* tableLogPtr, const uint8_t* src, uint32_t srcSize)
+{
+    if (srcSize == 0) return 0;
+    uint32_t iSize = src[0], oSize;
+    if (iSize >= 128) {
+        oSize = iSize - 127; iSize = (oSize + 1) / 2;
+        if (iSize + 1 > srcSize) return 0;
+        if (oSize >= 256) return 0;
+        for (uint32_t n = 0; n < oSize; n += 2) { sc.weights[n] = src[1 + n / 2] >> 4; sc.weights[n + 1] = src[1 + n / 2] & 15; }
+    } else {
+        if (iSize + 1 > srcSize) return 0;
+        // FSE_decompress_wksp_body (FseDecompress.cs:334), maxLog 6, dst capacity 255
+        uint32_t tableLog, maxSV = 255;
+        // norm for up to 256 symbols would not fit sc.norm; weights are <= 12 so any symbol > 12 is invalid anyway,
+        // but the header may legally *mention* zero-probability symbols up to 255: parse into a local array.
+        int16_t normW[256];
+        uint32_t const hs = fse_read_ncount(normW, &maxSV, &tableLog, src + 1, iSize);
+        if (hs == 0) return 0;
+        if (tableLog > 6) return 0;
+        // FSE_buildDTable_internal: <= 64 cells
+        uint8_t cellS[64]; uint16_t next[256]; uint8_t cellBits[64]; uint16_t cellNew[64];
+        {
+            uint32_t const tableSize = 1u << tableLog, tableMask = tableSize - 1;
+            uint32_t const step = (tableSize >> 1) + (tableSize >> 3) + 3;
+            uint32_t high = tableSize - 1, position = 0;
+            for (uint32_t s = 0; s <= maxSV; s++) { if (normW[s] == -1) { cellS[high--] = (uint8_t)s; next[s] = 1; } else next[s] = (uint16_t)normW[s]; }
+            for (uint32_t s = 0; s <= maxSV; s++)
+                for (int i = 0; i < normW[s]; i++) {
+                    cellS[position] = (uint8_t)s; position = (position + step) & tableMask;
+                    while (position > high) position = (position + step) & tableMask;
+                }
+            if (position != 0) return 0;
+            for (uint32_t u = 0; u < tableSize; u++) {
+                uint32_t const sym = cellS[u]; uint32_t const ns = next[sym]++;
+                cellBits[u] = (uint8_t)(tableLog - highbit32(ns));
+                cellNew[u] = (uint16_t)((ns << cellBits[u]) - tableSize);
+            }
+        }
+        // FSE_decompress_usingDTable_generic (FseDecompress.cs:230), 64-bit variant
+        SmallDStream bd;
+        if (!bd.init(src + 1 + hs, (int32_t)(iSize - hs))) return 0;
+        uint32_t s1 = bd.read(tableLog); bd.reload();
+        uint32_t s2 = bd.read(tableLog); bd.reload();
+        uint32_t const omax = 255; uint32_t op = 0;
+        auto dec = [&](uint32_t& st) -> uint8_t { uint8_t sym = cellS[st]; uint32_t nb = cellBits[st]; uint32_t low = bd.read(nb); st = cellNew[st] + low; return sym; };
+        for (; (bd.reload() == 0) && (op + 3 < omax); op += 4) {
+            sc.weights[op] = dec(s1); sc.weights[op + 1] = dec(s2); sc.weights[op + 2] = dec(s1); sc.weights[op + 3] = dec(s2);
+        }
+        for (;;) {
+            if (op + 2 > omax) return 0;
+            sc.weights[op++] = dec(s1);
+            if (bd.reload() == 3) { sc.weights[op++] = dec(s2); break; }
+            if (op + 2 > omax) return 0;
+            sc.weights[op++] = dec(s2);
+            if (bd.reload() == 3) { sc.weights[op++] = dec(s1); break; }
+        }
+        oSize = op;
+    }
+    uint32_t rankStats[13]; for (int i = 0; i < 13; i++) rankStats[i] = 0;
+    uint32_t weightTotal = 0;
+    for (uint32_t n = 0; n < oSize; n++) {
+        if (sc.weights[n] > kHufTableLogMax) return 0;
+        rankStats[sc.weights[n]]++;
+        weightTotal += (1u << sc.weights[n]) >> 1;
+    }
+    if (weightTotal == 0) return 0;
+    uint32_t const tableLog = highbit32(weightTotal) + 1;
+    if (tableLog > kHufTableLogMax) return 0;
+    {
+        uint32_t const total = 1u << tableLog, rest = total - weightTotal;
+        uint32_t const verif = 1u << highbit32(rest), lastWeight = highbit32(rest) + 1;
+        if (verif != rest) return 0;
+        sc.weights[oSize] = (uint8_t)lastWeight;
+        rankStats[lastWeight]++;
+    }
+    if ((rankStats[1] < 2) || (rankStats[1] & 1)) return 0;
+    *nbSymbolsPtr = oSize + 1; *tableLogPtr = tableLog;
+    // start index of every symbol in the decode table: symbols sorted by (weight, symbol) (HufDecompress.cs:131-252)
+    uint32_t acc = 0;
+    for (uint32_t w = 1; w <= tableLog; w++) { sc.rankStart[w] = acc; acc += rankStats[w] * ((1u << w) >> 1); }
+    for (uint32_t s = 0; s < oSize + 1; s++) {
+        uint32_t const w = sc.weights[s];
+        if (w) { sc.start[s] = (uint16_t)sc.rankStart[w]; sc.rankStart[w] += (1u << w) >> 1; }
+    }
+    return iSize + 1;
+}
+
+// ZSTD_buildFSETable_body (ZstdDecompressBlock.cs:1571) into the compact entry format, one lane.
+__device__ void build_seq_table(uint32_t* out, SetupScratch& sc, uint32_t maxSV, uint32_t tableLog, int kind /*0 LL 1 ML 2 OF*/)
+{
+    uint32_t const tableSize = 1u << tableLog;
+    fse_spread(sc.cell, sc.symNext, sc.norm, maxSV, tableLog);
+    for (uint32_t u = 0; u < tableSize; u++) {
+        uint32_t const sym = sc.cell[u];
+        uint32_t const ns = sc.symNext[sym]++;
+        uint32_t const nbBits = tableLog - highbit32(ns);
+        uint32_t const next = (ns << nbBits) - tableSize;
+        uint32_t const add = kind == 0 ? c_LL_bits[sym] : (kind == 1 ? c_ML_bits[sym] : sym);
+        out[u] = fse_pack(nbBits, add, sym, next);
+    }
+}
+
+__global__ void dec_default_tables_kernel(uint32_t* out)
+{
+    __shared__ SetupScratch sc;
+    if (threadIdx.x != 0) return;
+    for (int i = 0; i <= kMaxLL; i++) sc.norm[i] = c_LL_defaultNorm[i];
+    build_seq_table(out + kFseLLOff, sc, kMaxLL, kLLDefaultNormLog, 0);
+    for (int i = 0; i <= kMaxML; i++) sc.norm[i] = c_ML_defaultNorm[i];
+    build_seq_table(out + kFseMLOff, sc, kMaxML, kMLDefaultNormLog, 1);
+    for (int i = 0; i <= kDefaultMaxOff; i++) sc.norm[i] = c_OF_defaultNorm[i];
+    build_seq_table(out + kFseOFOff, sc, kDefaultMaxOff, kOFDefaultNormLog, 2);
+}
+void dec_build_default_tables(uint32_t* d, cudaStream_t s) { dec_default_tables_kernel<<<1, 32, 0, s>>>(d); }
+
+// =====================================================================================================
+//  Frame walking helpers
+// =====================================================================================================
+__device__ __forceinline__ uint32_t frame_header_size(uint32_t fhd)   // ZSTD_frameHeaderSize_internal, ZstdDecompress.cs:427
+{
+    uint32_t const dictID = fhd & 3, single = (fhd >> 5) & 1, fcsId = fhd >> 6;
+    uint32_t const did[4] = {0, 1, 2, 4}; uint32_t const fcs[4] = {0, 2, 4, 8};
+    return 5 + !single + did[dictID] + fcs[fcsId] + (single && !fcsId);
+}
+
+// Skips skippable frames; decides whether the item is finished (ZSTD_decompressMultiFrame loop, ZstdDecompress.cs:1216-1321).
+// Returns true when a regular frame (or garbage to be diagnosed) starts at *pos.
+__device__ bool advance_frames(DecItem& it, const uint8_t* src, uint32_t* posIo)
+{
+    uint32_t pos = *posIo;
+    for (;;) {
+        uint32_t const rem = it.srcSize - pos;
+        if (rem < 5) {
+            if (rem != 0) { it.status = kStError; it.errCode = kSrcSizeWrong; } else it.status = kStDone;
+            *posIo = pos; return false;
+        }
+        uint32_t const magic = ld_le32(src + pos);
+        if ((magic & kMagicSkippableMask) == kMagicSkippableStart) {   // readSkippableFrameSize, :674
+            if (rem < 8) { it.status = kStError; it.errCode = kSrcSizeWrong; *posIo = pos; return false; }
+            uint32_t const sz = ld_le32(src + pos + 4);
+            if ((uint32_t)(sz + 8) < sz) { it.status = kStError; it.errCode = kFrameParameterUnsupported; *posIo = pos; return false; }
+            if ((uint64_t)sz + 8 > rem) { it.status = kStError; it.errCode = kSrcSizeWrong; *posIo = pos; return false; }
+            pos += sz + 8;
+            continue;
+        }
+        *posIo = pos; return true;
+    }
+}
+
+// Thread per item: initialise the cursor and count blocks = number of waves this item needs (walks like
+// ZSTD_findFrameSizeInfo, ZstdDecompress.cs:877; errors are diagnosed later by the setup kernel).
+__global__ void dec_scan_kernel(DecPass p, const DecItemInit* init)
+{
+    uint32_t const i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= p.nItems) return;
+    DecItem& it = p.items[i];
+    DecItemInit const in = init[i];
+    it.srcOff = in.srcOff; it.dstOff = in.dstOff; it.srcSize = in.srcSize; it.dstCap = in.dstCap;
+    it.srcPos = 0; it.outPos = 0; it.frameStart = 0; it.status = kStRunning; it.errCode = 0; it.inFrame = 0;
+    it.moreThan1Frame = 0; it.checksumFlag = 0; it.hasFcs = 0; it.fcs = 0; it.litEntropy = 0; it.fseEntropy = 0;
+    it.blkType = kBlkNone;
+    const uint8_t* src = p.src + in.srcOff; uint32_t const size = in.srcSize;
+    uint32_t pos = 0, blocks = 0;
+    for (;;) {
+        uint32_t rem = size - pos;
+        if (rem < 5) break;
+        uint32_t const magic = ld_le32(src + pos);
+        if ((magic & kMagicSkippableMask) == kMagicSkippableStart) {
+            if (rem < 8) break;
+            uint32_t const sz = ld_le32(src + pos + 4);
+            if ((uint64_t)sz + 8 > rem) break;
+            pos += sz + 8; continue;
+        }
+        if (magic != kMagic) break;
+        uint32_t const fhd = src[pos + 4];
+        uint32_t const hs = frame_header_size(fhd);
+        if (rem < hs + 3) break;
+        pos += hs;
+        bool bad = false;
+        for (;;) {
+            if (size - pos < 3) { bad = true; break; }
+            uint32_t const h = ld_le24(src + pos);
+            uint32_t const type = (h >> 1) & 3, cs = h >> 3;
+            uint32_t const csz = type == kBlkRle ? 1 : cs;
+            blocks++;
+            pos += 3;
+            if (type == 3 || csz > size - pos) { bad = true; break; }
+            pos += csz;
+            if (h & 1) break;
+        }
+        if (bad) break;
+        if (fhd & 4) { if (size - pos < 4) break; pos += 4; }
+    }
+    if (blocks == 0) blocks = 1;
+    atomicMax(&p.counters[3], blocks);
+}
+
+// =====================================================================================================
+//  Setup kernel: one warp per item; lane 0 parses, the warp fills the Huffman table.
+// =====================================================================================================
+constexpr int kSetupWarps = 4;
+
+__device__ void setup_fail(DecItem& it, uint32_t code) { it.status = kStError; it.errCode = code; it.blkType = kBlkNone; }
+
+// Parses the sequences section header and builds/keeps the three tables. Returns header bytes or 0xFFFFFFFF on error
+// (error code in *err).  ZSTD_decodeSeqHeaders, ZstdDecompressBlock.cs:1845; ZSTD_buildSeqTable :1746.
+__device__ uint32_t setup_seq_headers(DecItem& it, const DecPass& p, uint32_t item, SetupScratch& sc, const uint8_t* src, uint32_t srcSize, uint32_t* err)
+{
+    uint32_t ip = 0;
+    if (srcSize < 1) { *err = kSrcSizeWrong; return 0xFFFFFFFFu; }
+    uint32_t nbSeq = src[ip++];
+    if (nbSeq == 0) { it.nbSeq = 0; if (srcSize != 1) { *err = kSrcSizeWrong; return 0xFFFFFFFFu; } return 1; }
+    if (nbSeq > 0x7F) {
+        if (nbSeq == 0xFF) { if (ip + 2 > srcSize) { *err = kSrcSizeWrong; return 0xFFFFFFFFu; } nbSeq = ld_le16(src + ip) + kLongNbSeq; ip += 2; }
+        else { if (ip >= srcSize) { *err = kSrcSizeWrong; return 0xFFFFFFFFu; } nbSeq = ((nbSeq - 0x80) << 8) + src[ip++]; }
+    }
+    it.nbSeq = nbSeq;
+    if (ip + 1 > srcSize) { *err = kSrcSizeWrong; return 0xFFFFFFFFu; }
+    uint32_t const modes = src[ip++];
+    uint32_t* const tbl = p.fseTable + (size_t)item * kFseTableEntries;
+    *err = kCorruptionDetected;
+    for (int k = 0; k < 3; k++) {   // order: LL, OF, ML
+        uint32_t const type = k == 0 ? (modes >> 6) : (k == 1 ? ((modes >> 4) & 3) : ((modes >> 2) & 3));
+        int const kind = k == 0 ? 0 : (k == 1 ? 2 : 1);
+        uint32_t const maxSym = kind == 0 ? kMaxLL : (kind == 1 ? kMaxML : kMaxOff);
+        uint32_t const maxLog = kind == 2 ? kOffFSELog : kLLFSELog;
+        uint32_t const off = kind == 0 ? kFseLLOff : (kind == 1 ? kFseMLOff : kFseOFOff);
+        uint32_t* const logPtr = kind == 0 ? &it.llLog : (kind == 1 ? &it.mlLog : &it.ofLog);
+        switch (type) {
+        case 1: {   // set_rle
+            if (ip >= srcSize) return 0xFFFFFFFFu;
+            uint32_t const sym = src[ip++];
+            if (sym > maxSym) return 0xFFFFFFFFu;
+            uint32_t const add = kind == 0 ? c_LL_bits[sym] : (kind == 1 ? c_ML_bits[sym] : sym);
+            tbl[off] = fse_pack(0, add, sym, 0);
+            *logPtr = 0;
+            break; }
+        case 0: {   // set_basic: predefined table
+            uint32_t const n = kind == 2 ? (1u << kOFDefaultNormLog) : (1u << kLLDefaultNormLog);
+            for (uint32_t u = 0; u < n; u++) tbl[off + u] = p.defaultFse[off + u];
+            *logPtr = kind == 2 ? kOFDefaultNormLog : kLLDefaultNormLog;
+            break; }
+        case 3:     // set_repeat
+            if (!it.fseEntropy) return 0xFFFFFFFFu;
+            break;
+        default: {  // set_compressed
+            uint32_t maxSV = maxSym, tableLog;
+            uint32_t const hs = fse_read_ncount(sc.norm, &maxSV, &tableLog, src + ip, srcSize - ip);
+            if (hs == 0) return 0xFFFFFFFFu;
+            if (tableLog > maxLog) return 0xFFFFFFFFu;
+            build_seq_table(tbl + off, sc, maxSV, tableLog, kind);
+            *logPtr = tableLog;
+            ip += hs;
+            break; }
+        }
+    }
+    *err = 0;
+    return ip;
+}
+
+__global__ void __launch_bounds__(kSetupWarps * 32) dec_setup_kernel(DecPass p)
+{
+    __shared__ SetupScratch scratch[kSetupWarps];
+    __shared__ uint32_t s_huf[kSetupWarps][3];   // [0] fill table? [1] nbSymbols [2] tableLog
+    uint32_t const warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    uint32_t const item = blockIdx.x * kSetupWarps + warp;
+    if (item >= p.nItems) return;
+    DecItem& it = p.items[item];
+    SetupScratch& sc = scratch[warp];
+    const uint8_t* const src = p.src + it.srcOff;
+    if (lane == 0) {
+        s_huf[warp][0] = 0;
+        do {
+            if (it.status != kStRunning) { it.blkType = kBlkNone; break; }
+            uint32_t pos = it.srcPos; uint32_t const size = it.srcSize;
+            if (!it.inFrame) {
+                if (!advance_frames(it, src, &pos)) { it.srcPos = pos; it.blkType = kBlkNone; break; }
+                // ---- ZSTD_decompressFrame entry, ZstdDecompress.cs:1062 ----
+                uint32_t const rem = size - pos; uint32_t err = 0;
+                if (rem < 9) err = kSrcSizeWrong;
+                uint32_t fhsize = 0, fhd = 0;
+                if (!err) { fhd = src[pos + 4]; fhsize = frame_header_size(fhd); if (rem < fhsize + 3) err = kSrcSizeWrong; }
+                if (!err && ld_le32(src + pos) != kMagic) err = kPrefixUnknown;                 // ZSTD_getFrameHeader_advanced :462
+                if (!err && (fhd & 0x08)) err = kFrameParameterUnsupported;
+                if (!err) {
+                    uint32_t q = pos + 5; uint32_t const single = (fhd >> 5) & 1, fcsId = fhd >> 6, didCode = fhd & 3;
+                    if (!single) { uint32_t const wl = (src[q++] >> 3) + 10; if (wl > 31) err = kWindowTooLarge; }
+                    uint32_t dictID = 0;
+                    if (didCode == 1) { dictID = src[q]; q += 1; } else if (didCode == 2) { dictID = ld_le16(src + q); q += 2; } else if (didCode == 3) { dictID = ld_le32(src + q); q += 4; }
+                    uint64_t fcs = 0; uint32_t has = 1;
+                    if (fcsId == 0) { if (single) fcs = src[q]; else has = 0; }
+                    else if (fcsId == 1) fcs = ld_le16(src + q) + 256; else if (fcsId == 2) fcs = ld_le32(src + q); else fcs = ld_le64(src + q);
+                    if (!err && dictID != 0) err = kDictionaryWrong;                              // ZSTD_decodeFrameHeader :834
+                    it.fcs = fcs; it.hasFcs = has; it.checksumFlag = (fhd >> 2) & 1;
+                }
+                if (err) {
+                    if (err == kPrefixUnknown && it.moreThan1Frame) err = kSrcSizeWrong;          // :1282
+                    setup_fail(it, err); break;
+                }
+                pos += fhsize;
+                it.rep[0] = 1; it.rep[1] = 4; it.rep[2] = 8; it.litEntropy = 0; it.fseEntropy = 0;   // ZSTD_decompressBegin :1933
+                it.frameStart = it.outPos; it.inFrame = 1;
+            }
+            // ---- block header: ZSTD_getcBlockSize, ZstdDecompressBlock.cs:19 ----
+            uint32_t rem = size - pos;
+            if (rem < 3) { setup_fail(it, kSrcSizeWrong); break; }
+            uint32_t const h = ld_le24(src + pos);
+            uint32_t const type = (h >> 1) & 3, cs = h >> 3;
+            it.lastBlock = h & 1;
+            if (type == 3) { setup_fail(it, kCorruptionDetected); break; }
+            uint32_t const cBlockSize = type == kBlkRle ? 1 : cs;
+            pos += 3; rem -= 3;
+            if (cBlockSize > rem) { setup_fail(it, kSrcSizeWrong); break; }
+            uint32_t const capLeft = it.dstCap - it.outPos;
+            it.blkType = type; it.blkSrcOff = pos; it.blkSize = cs; it.srcPos = pos + cBlockSize;
+            it.nbSeq = 0; it.blockOut = 0; it.seqLitEnd = 0;
+            if (type != kBlkCompressed) {
+                if (cs > capLeft) setup_fail(it, kDstSizeTooSmall);     // ZSTD_copyRawBlock :1004 / ZSTD_setRleBlock :1029
+                break;
+            }
+            // ---- compressed block: ZSTD_decompressBlock_internal, ZstdDecompressBlock.cs:3090 ----
+            if (cBlockSize >= kBlockSizeMax) { setup_fail(it, kSrcSizeWrong); break; }
+            const uint8_t* const b = src + pos; uint32_t const bsize = cBlockSize;
+            // literals header: ZSTD_decodeLiteralsBlock :88
+            if (bsize < 3) { setup_fail(it, kCorruptionDetected); break; }
+            uint32_t const litEncType = b[0] & 3, lhlCode = (b[0] >> 2) & 3;
+            uint32_t const expectedWrite = capLeft < kBlockSizeMax ? capLeft : kBlockSizeMax;
+            uint32_t litSectionSize = 0; uint32_t err = 0;
+            if (litEncType == 2 || litEncType == 3) {
+                if (litEncType == 3 && !it.litEntropy) { setup_fail(it, kDictionaryCorrupted); break; }
+                if (bsize < 5) { setup_fail(it, kCorruptionDetected); break; }
+                uint32_t lhSize, litSize, litCSize, single = 0;
+                uint32_t const lhc = ld_le32(b);
+                if (lhlCode <= 1) { single = !lhlCode; lhSize = 3; litSize = (lhc >> 4) & 0x3FF; litCSize = (lhc >> 14) & 0x3FF; }
+                else if (lhlCode == 2) { lhSize = 4; litSize = (lhc >> 4) & 0x3FFF; litCSize = lhc >> 18; }
+                else { lhSize = 5; litSize = (lhc >> 4) & 0x3FFFF; litCSize = (lhc >> 22) + ((uint32_t)b[4] << 10); }
+                if (litSize > kBlockSizeMax) err = kCorruptionDetected;
+                else if (litCSize + lhSize > bsize) err = kCorruptionDetected;
+                else if (expectedWrite < litSize) err = kDstSizeTooSmall;
+                if (err) { setup_fail(it, err); break; }
+                uint32_t hSize = 0;
+                const uint8_t* const hsrc = b + lhSize;
+                if (litEncType == 2) {
+                    // HUF_decompress4X_hufOnly_wksp (HufDecompress.cs:1793) / HUF_decompress1X1_DCtx_wksp (:1766)
+                    if (!single && (litSize == 0 || litCSize == 0)) { setup_fail(it, kCorruptionDetected); break; }
+                    uint32_t nbSym = 0, tlog = 0;
+                    hSize = huf_read_stats(sc, &nbSym, &tlog, hsrc, litCSize);
+                    if (hSize == 0 || hSize >= litCSize) { setup_fail(it, kCorruptionDetected); break; }
+                    it.hufLog = tlog; s_huf[warp][0] = 1; s_huf[warp][1] = nbSym; s_huf[warp][2] = tlog;
+                }
+                uint32_t const cOff = lhSize + hSize, cLen = litCSize - hSize;
+                it.litType = kLitHuf; it.litSize = litSize;
+                if (single) {
+                    it.nStreams = 1; it.streamOff[0] = pos + cOff; it.streamLen[0] = cLen;
+                    if (cLen < 1) { setup_fail(it, kCorruptionDetected); break; }
+                } else {
+                    // HUF_decompress4X1_usingDTable_internal_body, HufDecompress.cs:342
+                    if (cLen < 10) { setup_fail(it, kCorruptionDetected); break; }
+                    uint32_t const l1 = ld_le16(b + cOff), l2 = ld_le16(b + cOff + 2), l3 = ld_le16(b + cOff + 4);
+                    if (l1 + l2 + l3 + 6 > cLen) { setup_fail(it, kCorruptionDetected); break; }
+                    uint32_t const l4 = cLen - (l1 + l2 + l3 + 6);
+                    uint32_t const seg = (litSize + 3) / 4;
+                    if (3 * seg > litSize) { setup_fail(it, kCorruptionDetected); break; }
+                    if (l1 < 1 || l2 < 1 || l3 < 1 || l4 < 1) { setup_fail(it, kCorruptionDetected); break; }   // BIT_initDStream: srcSize < 1
+                    it.nStreams = 4;
+                    it.streamOff[0] = pos + cOff + 6; it.streamLen[0] = l1;
+                    it.streamOff[1] = it.streamOff[0] + l1; it.streamLen[1] = l2;
+                    it.streamOff[2] = it.streamOff[1] + l2; it.streamLen[2] = l3;
+                    it.streamOff[3] = it.streamOff[2] + l3; it.streamLen[3] = l4;
+                }
+                it.litEntropy = 1;
+                litSectionSize = litCSize + lhSize;
+            } else {
+                uint32_t lhSize, litSize;
+                if (lhlCode == 1) { lhSize = 2; litSize = ld_le16(b) >> 4; }
+                else if (lhlCode == 3) { lhSize = 3; litSize = ld_le24(b) >> 4; }
+                else { lhSize = 1; litSize = b[0] >> 3; }
+                if (litEncType == 0) {          // set_basic (raw literals)
+                    if (expectedWrite < litSize) err = kDstSizeTooSmall;
+                    else if (litSize + lhSize > bsize) err = kCorruptionDetected;
+                    if (err) { setup_fail(it, err); break; }
+                    it.litType = kLitRaw; it.litSize = litSize; it.litOff = pos + lhSize;
+                    litSectionSize = lhSize + litSize;
+                } else {                        // set_rle
+                    if (lhlCode == 3 && bsize < 4) err = kCorruptionDetected;
+                    else if (litSize > kBlockSizeMax) err = kCorruptionDetected;
+                    else if (expectedWrite < litSize) err = kDstSizeTooSmall;
+                    if (err) { setup_fail(it, err); break; }
+                    it.litType = kLitRle; it.litSize = litSize; it.litOff = pos + lhSize;
+                    litSectionSize = lhSize + 1;
+                }
+            }
+            // sequences header
+            uint32_t serr = 0;
+            uint32_t const shs = setup_seq_headers(it, p, item, sc, b + litSectionSize, bsize - litSectionSize, &serr);
+            if (shs == 0xFFFFFFFFu) { setup_fail(it, serr); break; }
+            it.seqOff = pos + litSectionSize + shs; it.seqLen = bsize - litSectionSize - shs;
+            if (it.nbSeq) {
+                if (it.nbSeq > kSeqCap) { setup_fail(it, kCorruptionDetected); break; }
+                if (it.seqLen < 1) { setup_fail(it, kCorruptionDetected); break; }              // BIT_initDStream error -> corruption (:2697)
+                it.fseEntropy = 1;
+                uint32_t const slot = atomicAdd(&p.counters[1], 1u); p.seqList[slot] = item;
+            } else {
+                if (it.litSize > capLeft) { setup_fail(it, kDstSizeTooSmall); break; }           // last literals copy :2748
+            }
+            if (it.litType == kLitHuf) { uint32_t const slot = atomicAdd(&p.counters[0], 1u); p.hufList[slot] = item; }
+        } while (0);
+    }
+    __syncwarp();
+    // warp-cooperative fill of the single-symbol Huffman table at its native tableLog: every symbol of weight w
+    // owns (1<<w)>>1 consecutive cells, nbBits = tableLog+1-w (HUF_readDTableX1_wksp_bmi2, HufDecompress.cs:131-252)
+    if (s_huf[warp][0] && it.status == kStRunning) {
+        uint32_t const nbSym = s_huf[warp][1], tlog = s_huf[warp][2];
+        uint16_t* const tab = p.hufTable + (size_t)item * kHufTableEntries;
+        for (uint32_t s = 0; s < nbSym; s++) {
+            uint32_t const w = sc.weights[s];
+            if (!w) continue;
+            uint32_t const len = (1u << w) >> 1, st = sc.start[s];
+            uint16_t const e = (uint16_t)((s << 8) | (tlog + 1 - w));
+            for (uint32_t u = lane; u < len; u += 32) tab[st + u] = e;
+        }
+    }
+}
+
+// =====================================================================================================
+//  Backward bit reader over global memory (32-bit aligned word refills, one word prefetched).
+//  Semantics of BIT_DStream_t (Bitstream.cs:172-425) for well-formed streams; over-reads are tracked in `left`.
+// =====================================================================================================
+struct BitReader {
+    uint64_t w;            // unread bits, left aligned
+    int32_t cnt;           // valid bits in w
+    int32_t left;          // unread bits of the stream (negative = over-read)
+    const uint32_t* wp;    // next (lower) word to fetch
+    const uint32_t* lo;    // lowest word that may be read
+    uint32_t nxt;          // prefetched *wp
+
+    __device__ __forceinline__ bool init(const uint8_t* itemBase, uint32_t off, uint32_t len) {
+        const uint8_t* const last = itemBase + off + len - 1;
+        uint32_t const lastByte = *last;
+        if (lastByte == 0) return false;
+        uint32_t const hb = highbit32(lastByte);
+        left = (int32_t)((len - 1) * 8 + hb);
+        uintptr_t const a = (uintptr_t)last;
+        const uint32_t* const word = (const uint32_t*)(a & ~(uintptr_t)3);
+        lo = (const uint32_t*)((uintptr_t)itemBase & ~(uintptr_t)3);
+        uint32_t const bitsInWord = (uint32_t)(a & 3) * 8 + hb;
+        uint32_t const v = *word;
+        w = bitsInWord ? ((uint64_t)v << (64 - bitsInWord)) : 0ull;
+        cnt = (int32_t)bitsInWord;
+        wp = word - 1;
+        nxt = wp >= lo ? *wp : 0u;
+        refill();
+        return true;
+    }
+    __device__ __forceinline__ void refill() {
+        if (cnt <= 32) {
+            w |= (uint64_t)nxt << (32 - cnt);
+            cnt += 32;
+            wp--;
+            nxt = wp >= lo ? *wp : 0u;
+        }
+    }
+    __device__ __forceinline__ uint32_t peek(uint32_t nb) const { return (uint32_t)((w >> 1) >> (63 - nb)); }   // nb in [0,32]
+    __device__ __forceinline__ void skip(uint32_t nb) { w <<= nb; cnt -= (int32_t)nb; left -= (int32_t)nb; }
+    __device__ __forceinline__ uint32_t read(uint32_t nb) { uint32_t const v = peek(nb); skip(nb); return v; }
+};
+
+// =====================================================================================================
+//  Huffman literal decoding: one lane per stream, 16 items (64 streams) per CTA, tables in shared memory.
+//  HUF_decompress4X1_usingDTable_internal_body / HUF_decodeStreamX1 (HufDecompress.cs:342, :264)
+// =====================================================================================================
+constexpr int kHufItemsPerCta = 16;
+constexpr int kHufThreads = kHufItemsPerCta * 4;
+constexpr uint32_t kHufSmemEntries = 2048;     // tables with tableLog <= 11 are staged; log-12 tables are read from HBM/L2
+
+__device__ __forceinline__ uint32_t lit_segment_stride(uint32_t litSize) { uint32_t const seg = (litSize + 3) / 4; return (seg + 15) & ~15u; }
+
+__global__ void __launch_bounds__(kHufThreads) dec_huf_kernel(DecPass p)
+{
+    extern __shared__ uint16_t s_tab[];       // [kHufItemsPerCta][2048]
+    uint32_t const nWork = p.counters[0];
+    uint32_t const first = blockIdx.x * kHufItemsPerCta;
+    if (first >= nWork) return;
+    uint32_t const nHere = min((uint32_t)kHufItemsPerCta, nWork - first);
+    // stage tables (coalesced 16-byte copies)
+    for (uint32_t k = 0; k < nHere; k++) {
+        uint32_t const item = p.hufList[first + k];
+        uint32_t const log = p.items[item].hufLog;
+        if (log <= 11) {
+            const uint4* g = (const uint4*)(p.hufTable + (size_t)item * kHufTableEntries);
+            uint4* s = (uint4*)(s_tab + k * kHufSmemEntries);
+            uint32_t const n16 = ((1u << log) * 2 + 15) / 16;
+            for (uint32_t u = threadIdx.x; u < n16; u += kHufThreads) s[u] = g[u];
+        }
+    }
+    __syncthreads();
+    uint32_t const slot = threadIdx.x >> 2, stream = threadIdx.x & 3;
+    if (slot >= nHere) return;
+    uint32_t const item = p.hufList[first + slot];
+    DecItem& it = p.items[item];
+    if (it.status != kStRunning) return;
+    uint32_t const nStreams = it.nStreams;
+    if (stream >= nStreams) return;
+    uint32_t const litSize = it.litSize, log = it.hufLog;
+    uint32_t const seg = (litSize + 3) / 4;
+    uint32_t count, outOff;
+    if (nStreams == 1) { count = litSize; outOff = 0; }
+    else { count = stream < 3 ? seg : litSize - 3 * seg; outOff = stream * lit_segment_stride(litSize); }
+    uint8_t* out = p.litBuf + (size_t)item * kLitStride + outOff;
+    const uint8_t* const src = p.src + it.srcOff;
+    BitReader br;
+    bool ok = br.init(src, it.streamOff[stream], it.streamLen[stream]);
+    if (ok) {
+        const uint16_t* tab; bool const inSmem = log <= 11;
+        const uint16_t* const gtab = p.hufTable + (size_t)item * kHufTableEntries;
+        tab = s_tab + slot * kHufSmemEntries;
+        uint32_t i = 0;
+        // 16 symbols -> one 16-byte store (out is 16-byte aligned by construction)
+        for (; i + 16 <= count && br.left >= 0; i += 16) {
+            uint32_t v[4];
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                uint32_t acc = 0;
+#pragma unroll
+                for (int r = 0; r < 4; r++) {
+                    if ((r & 1) == 0) br.refill();
+                    uint32_t const idx = br.peek(log);
+                    uint32_t const e = inSmem ? tab[idx] : gtab[idx];
+                    br.skip(e & 0xFF);
+                    acc |= (e >> 8) << (8 * r);
+                }
+                v[q] = acc;
+            }
+            *(uint4*)(out + i) = make_uint4(v[0], v[1], v[2], v[3]);
+        }
+        for (; i < count && br.left >= 0; i++) {
+            br.refill();
+            uint32_t const idx = br.peek(log);
+            uint32_t const e = inSmem ? tab[idx] : gtab[idx];
+            br.skip(e & 0xFF);
+            out[i] = (uint8_t)(e >> 8);
+        }
+        ok = (br.left == 0) && (i == count);      // BIT_endOfDStream: the stream must be consumed exactly (:526-533)
+    }
+    if (!ok) { it.errCode = kCorruptionDetected; it.status = kStError; }
+}
+
+// =====================================================================================================
+//  Sequence decoding: one lane per item; LL/ML/OF tables staged in shared memory (5 KB per item).
+//  ZSTD_decompressSequences_body / ZSTD_decodeSequence (ZstdDecompressBlock.cs:2668, :2360) incl. the checks of
+//  ZSTD_execSequenceEnd (:2083-2103), so that the exec kernel can copy without re-validating.
+// =====================================================================================================
+constexpr int kSeqItemsPerCta = 11;
+
+__global__ void __launch_bounds__(32) dec_seq_kernel(DecPass p)
+{
+    extern __shared__ __align__(16) uint32_t s_seqTab[];   // [kSeqItemsPerCta][kFseTableEntries]
+    __shared__ uint32_t s_llBase[36], s_mlBase[53];
+    uint32_t const nWork = p.counters[1];
+    uint32_t const first = blockIdx.x * kSeqItemsPerCta;
+    if (first >= nWork) return;
+    uint32_t const nHere = min((uint32_t)kSeqItemsPerCta, nWork - first);
+    uint32_t const lane = threadIdx.x;
+    for (uint32_t k = 0; k < nHere; k++) {
+        uint32_t const item = p.seqList[first + k];
+        const uint4* g = (const uint4*)(p.fseTable + (size_t)item * kFseTableEntries);
+        uint4* s = (uint4*)(s_seqTab + k * kFseTableEntries);
+        for (uint32_t u = lane; u < kFseTableEntries / 4; u += 32) s[u] = g[u];
+    }
+    for (uint32_t u = lane; u < 36; u += 32) s_llBase[u] = c_LL_base[u];
+    for (uint32_t u = lane; u < 53; u += 32) s_mlBase[u] = c_ML_base[u];
+    __syncwarp();
+    if (lane >= nHere) return;
+    uint32_t const item = p.seqList[first + lane];
+    DecItem& it = p.items[item];
+    if (it.status != kStRunning) return;
+    const uint32_t* const tLL = s_seqTab + lane * kFseTableEntries + kFseLLOff;
+    const uint32_t* const tML = s_seqTab + lane * kFseTableEntries + kFseMLOff;
+    const uint32_t* const tOF = s_seqTab + lane * kFseTableEntries + kFseOFOff;
+    uint32_t* const oLL = p.seqLL + (size_t)item * kSeqCap;
+    uint32_t* const oML = p.seqML + (size_t)item * kSeqCap;
+    uint32_t* const oOF = p.seqOF + (size_t)item * kSeqCap;
+    const uint8_t* const src = p.src + it.srcOff;
+    uint32_t const nbSeq = it.nbSeq;
+    BitReader br;
+    uint32_t err = 0;
+    if (!br.init(src, it.seqOff, it.seqLen)) err = kCorruptionDetected;
+    uint32_t rep0 = it.rep[0], rep1 = it.rep[1], rep2 = it.rep[2];
+    uint32_t outPos = it.outPos; uint32_t const frameStart = it.frameStart, dstCap = it.dstCap;
+    uint32_t litPos = 0; uint32_t const litSize = it.litSize;
+    if (!err) {
+        uint32_t sL = br.read(it.llLog); br.refill();
+        uint32_t sO = br.read(it.ofLog); br.refill();
+        uint32_t sM = br.read(it.mlLog); br.refill();
+        if (br.left < 0) err = kCorruptionDetected;
+        for (uint32_t n = 0; n < nbSeq && !err; n++) {
+            uint32_t const eL = tLL[sL], eO = tOF[sO], eM = tML[sM];
+            uint32_t const llBits = (eL >> 4) & 31, mlBits = (eM >> 4) & 31, ofBits = (eO >> 4) & 31;
+            uint32_t const llSym = (eL >> 9) & 63, mlSym = (eM >> 9) & 63;
+            uint32_t ll = s_llBase[llSym], ml = s_mlBase[mlSym];
+            uint32_t offset;
+            if (ofBits > 1) {
+                offset = ((1u << ofBits) - 3u) + br.read(ofBits);           // OF_base[n] = (1<<n)-3 for n >= 2
+                rep2 = rep1; rep1 = rep0; rep0 = offset;
+                br.refill();
+            } else {
+                uint32_t const ll0 = (ll == 0);                              // baseValue == 0 <=> code 0
+                if (ofBits == 0) {
+                    offset = ll0 ? rep1 : rep0;
+                    rep1 = ll0 ? rep0 : rep1;
+                    rep0 = offset;
+                } else {
+                    uint32_t const ofv = 1u + ll0 + br.read(1);              // OF_base[1] = 1
+                    uint32_t temp = (ofv == 3) ? rep0 - 1 : (ofv == 1 ? rep1 : rep2);
+                    temp += !temp;
+                    if (ofv != 1) rep2 = rep1;
+                    rep1 = rep0; rep0 = offset = temp;
+                }
+            }
+            if (mlBits) ml += br.read(mlBits);
+            if (llBits) ll += br.read(llBits);
+            br.refill();
+            bool const overRead = br.left < 0;
+            // state updates in the reference's order LL, ML, OF (:2473-2480)
+            sL = (eL >> 16) + br.read(eL & 15);
+            sM = (eM >> 16) + br.read(eM & 15);
+            sO = (eO >> 16) + br.read(eO & 15);
+            br.refill();
+            // validity (ZSTD_execSequenceEnd order): output overflow, literal overrun, offset beyond frame start
+            uint32_t const seqLen = ll + ml;
+            if (seqLen > dstCap - outPos) err = kDstSizeTooSmall;
+            else if (ll > litSize - litPos) err = kCorruptionDetected;
+            else if (offset > (outPos + ll) - frameStart) err = kCorruptionDetected;
+            else if (overRead) err = kCorruptionDetected;
+            else if (n + 1 < nbSeq && br.left < 0) err = kCorruptionDetected;
+            oLL[n] = ll; oML[n] = ml; oOF[n] = offset;
+            outPos += seqLen; litPos += ll;
+        }
+        // the stream must not have unread bits left (BIT_reloadDStream >= completed, :2730)
+        if (!err && br.left > 0) err = kCorruptionDetected;
+        if (!err && (litSize - litPos) > dstCap - outPos) err = kDstSizeTooSmall;   // last literals, :2748
+    }
+    if (err) { it.status = kStError; it.errCode = err; return; }
+    it.rep[0] = rep0; it.rep[1] = rep1; it.rep[2] = rep2;
+    it.seqLitEnd = litPos;
+    it.blockOut = (outPos - it.outPos) + (litSize - litPos);
+}
+
+// =====================================================================================================
+//  Sequence execution + raw/RLE blocks: one CTA per item.
+//  Sequences are processed in batches whose regenerated bytes fit a shared-memory tile: literals and matches are
+//  assembled in the tile (matches that reach behind the tile read finished bytes from HBM/L2), dependent matches
+//  are resolved in rounds, then the tile is flushed with coalesced stores.  ZSTD_execSequence (:2187).
+// =====================================================================================================
+constexpr int kExecThreads = 256;
+constexpr uint32_t kTileBytes = 16384;
+
+__device__ __forceinline__ uint32_t lit_addr(uint32_t idx, uint32_t seg, uint32_t pad)   // padded 4-segment literal layout
+{ uint32_t const s = (idx >= seg) + (idx >= 2 * seg) + (idx >= 3 * seg); return idx + s * pad; }
+
+template <typename T> __device__ __forceinline__ T block_exclusive_scan(T v, T* warpSums, T* total)
+{
+    uint32_t const lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    T incl = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { T const o = __shfl_up_sync(0xFFFFFFFFu, incl, d); if (lane >= (uint32_t)d) incl += o; }
+    if (lane == 31) warpSums[warp] = incl;
+    __syncthreads();
+    T base = 0, tot = 0;
+#pragma unroll
+    for (int k = 0; k < kExecThreads / 32; k++) { T const s = warpSums[k]; if ((uint32_t)k < warp) base += s; tot += s; }
+    __syncthreads();
+    *total = tot;
+    return base + incl - v;
+}
+
+__device__ void cta_copy(uint8_t* dst, const uint8_t* src, uint32_t n)
+{
+    for (uint32_t i = threadIdx.x; i < n; i += kExecThreads) dst[i] = src[i];
+}
+
+__global__ void __launch_bounds__(kExecThreads) dec_exec_kernel(DecPass p)
+{
+    __shared__ __align__(16) uint8_t tile[kTileBytes];
+    __shared__ uint32_t s_scanA[kExecThreads / 32], s_scanB[kExecThreads / 32];
+    __shared__ uint32_t s_water, s_pending, s_count, s_span, s_litSpan, s_big[3];
+    uint32_t const item = blockIdx.x;
+    DecItem& it = p.items[item];
+    if (it.status != kStRunning || it.blkType == kBlkNone) return;
+    const uint8_t* const src = p.src + it.srcOff;
+    uint8_t* const dst = p.dst + it.dstOff;
+    uint32_t const outBase = it.outPos;
+    uint32_t blockOut = 0;
+    uint32_t const tid = threadIdx.x;
+
+    if (it.blkType == kBlkRaw) {
+        blockOut = it.blkSize;
+        cta_copy(dst + outBase, src + it.blkSrcOff, blockOut);
+    } else if (it.blkType == kBlkRle) {
+        blockOut = it.blkSize;
+        uint8_t const b = src[it.blkSrcOff];
+        for (uint32_t i = tid; i < blockOut; i += kExecThreads) dst[outBase + i] = b;
+    } else {
+        uint32_t const litType = it.litType, litSize = it.litSize;
+        uint32_t const seg = it.nStreams == 4 ? (litSize + 3) / 4 : 0xFFFFFFFFu;
+        uint32_t const pad = it.nStreams == 4 ? lit_segment_stride(litSize) - (litSize + 3) / 4 : 0;
+        const uint8_t* const litSrc = litType == kLitHuf ? p.litBuf + (size_t)item * kLitStride : src + it.litOff;
+        uint32_t const rleByte = litType == kLitRle ? src[it.litOff] : 0;
+        auto lit_at = [&](uint32_t idx) -> uint8_t {
+            if (litType == kLitRle) return (uint8_t)rleByte;
+            if (litType == kLitHuf) return litSrc[lit_addr(idx, seg, pad)];
+            return litSrc[idx];
+        };
+        uint32_t const nbSeq = it.nbSeq;
+        const uint32_t* const aLL = p.seqLL + (size_t)item * kSeqCap;
+        const uint32_t* const aML = p.seqML + (size_t)item * kSeqCap;
+        const uint32_t* const aOF = p.seqOF + (size_t)item * kSeqCap;
+        uint32_t seqBase = 0, outPos = outBase, litPos = 0;
+        while (seqBase < nbSeq) {
+            uint32_t const n = seqBase + tid;
+            uint32_t ll = 0, ml = 0, of = 0;
+            if (n < nbSeq) { ll = aLL[n]; ml = aML[n]; of = aOF[n]; }
+            uint32_t totOut, totLit;
+            uint32_t const oStart = block_exclusive_scan<uint32_t>(ll + ml, s_scanA, &totOut);   // tile-relative start of my literals
+            uint32_t const lStart = block_exclusive_scan<uint32_t>(ll, s_scanB, &totLit);
+            // how many sequences of this batch fit the tile?
+            if (tid == 0) s_count = 0;
+            __syncthreads();
+            bool const fits = (n < nbSeq) && (oStart + ll + ml <= kTileBytes);
+            if (fits) atomicMax(&s_count, tid + 1);
+            __syncthreads();
+            uint32_t const cnt = s_count;     // sequences [0, cnt) fit (prefix property: oStart is monotone)
+            if (cnt == 0) {
+                // a single sequence larger than the tile: copy it straight to HBM with the whole CTA
+                if (tid == 0) { s_big[0] = ll; s_big[1] = ml; s_big[2] = of; }
+                __syncthreads();
+                uint32_t const bl = s_big[0], bm = s_big[1], bo = s_big[2];
+                for (uint32_t i = tid; i < bl; i += kExecThreads) dst[outPos + i] = lit_at(litPos + i);
+                __syncthreads();
+                uint8_t* const md = dst + outPos + bl;
+                if (bo >= bm) { for (uint32_t i = tid; i < bm; i += kExecThreads) md[i] = md[(int64_t)i - bo]; }
+                else { for (uint32_t i = tid; i < bm; i += kExecThreads) md[i] = *(md - bo + (i % bo)); }   // periodic pattern
+                __syncthreads();
+                outPos += bl + bm; litPos += bl; seqBase += 1;
+                continue;
+            }
+            bool const mine = tid < cnt;
+            // tile span = end of sequence cnt-1
+            if (tid == cnt - 1) { s_span = oStart + ll + ml; s_litSpan = lStart + ll; }
+            // literals -> tile
+            if (mine) for (uint32_t k = 0; k < ll; k++) tile[oStart + k] = lit_at(litPos + lStart + k);
+            if (tid == 0) { s_pending = 0; s_water = 0xFFFFFFFFu; }
+            __syncthreads();
+            uint32_t const span = s_span;
+            // matches: rounds. A match is ready when the non-self part of its source lies below the watermark
+            // (= first byte of the earliest unfinished match).
+            uint32_t const mDst = oStart + ll;                  // tile-relative
+            bool pending = mine && ml > 0;
+            int64_t const srcRel = (int64_t)mDst - (int64_t)of; // tile-relative source start (may be negative: finished bytes in HBM)
+            uint32_t const nonSelf = of < ml ? of : ml;         // bytes of the source that are not produced by this match itself
+            for (;;) {
+                if (pending) atomicMin(&s_water, mDst);
+                __syncthreads();
+                uint32_t const water = s_water;
+                if (water == 0xFFFFFFFFu) break;
+                bool const ready = pending && (srcRel + (int64_t)nonSelf <= (int64_t)water || mDst == water);
+                if (ready) {
+                    const uint8_t* const gsrc = dst + outPos;   // tile origin in HBM
+                    for (uint32_t k = 0; k < ml; k++) {
+                        int64_t const sp = srcRel + (int64_t)(of < ml ? (k % of) : k);
+                        uint8_t const v = sp >= 0 ? tile[sp] : gsrc[sp];
+                        tile[mDst + k] = v;
+                    }
+                    pending = false;
+                }
+                __syncthreads();
+                if (tid == 0) s_water = 0xFFFFFFFFu;
+                __syncthreads();
+            }
+            // flush tile
+            for (uint32_t i = tid; i < span; i += kExecThreads) dst[outPos + i] = tile[i];
+            uint32_t const litSpan = s_litSpan;
+            __syncthreads();
+            outPos += span; litPos += litSpan; seqBase += cnt;
+        }
+        // last literals (ZstdDecompressBlock.cs:2748-2760)
+        uint32_t const lastLL = litSize - litPos;
+        for (uint32_t i = tid; i < lastLL; i += kExecThreads) dst[outPos + i] = lit_at(litPos + i);
+        outPos += lastLL;
+        blockOut = outPos - outBase;
+    }
+    __syncthreads();
+    // ---- end of block bookkeeping (ZSTD_decompressFrame loop tail, ZstdDecompress.cs:1156-1212) ----
+    if (tid == 0) {
+        it.outPos = outBase + blockOut;
+        if (it.lastBlock) {
+            uint32_t err = 0;
+            if (it.hasFcs && (uint64_t)(it.outPos - it.frameStart) != it.fcs) err = kCorruptionDetected;
+            uint32_t pos = it.srcPos;
+            if (!err && it.checksumFlag) {
+                if (it.srcSize - pos < 4) err = kChecksumWrong; else pos += 4;   // XXH64 content check: see DESIGN.md (next row f.1)
+            }
+            if (err) { it.status = kStError; it.errCode = err; }
+            else {
+                it.inFrame = 0; it.moreThan1Frame = 1;
+                advance_frames(it, src, &pos);
+                it.srcPos = pos;
+            }
+        }
+    }
+}
+
+__global__ void dec_finish_kernel(DecPass p)
+{
+    uint32_t const i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= p.nItems) return;
+    DecItem const& it = p.items[i];
+    uint64_t r;
+    if (it.status == kStDone) r = it.outPos;
+    else if (it.status == kStError) r = make_error(it.errCode);
+    else r = make_error(kGeneric);
+    p.results[i] = r;
+}
+
+__global__ void dec_reset_counters_kernel(uint32_t* counters) { if (threadIdx.x < 3) counters[threadIdx.x] = 0; }
+
+// opt-in shared memory sizes are a per-device function attribute: set them once per device
+static void dec_set_attrs()
+{
+    static bool done[64] = {};
+    int dev = 0; cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64 || done[dev]) return;
+    cudaFuncSetAttribute(dec_huf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kHufItemsPerCta * kHufSmemEntries * 2);
+    cudaFuncSetAttribute(dec_seq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSeqItemsPerCta * kFseTableEntries * 4);
+    done[dev] = true;
+}
+
+void dec_launch_wave(const DecPass& p, cudaStream_t s)
+{
+    dec_reset_counters_kernel<<<1, 32, 0, s>>>(p.counters);
+    dec_setup_kernel<<<(p.nItems + kSetupWarps - 1) / kSetupWarps, kSetupWarps * 32, 0, s>>>(p);
+    dec_set_attrs();
+    dec_huf_kernel<<<(p.nItems + kHufItemsPerCta - 1) / kHufItemsPerCta, kHufThreads, kHufItemsPerCta * kHufSmemEntries * 2, s>>>(p);
+    dec_seq_kernel<<<(p.nItems + kSeqItemsPerCta - 1) / kSeqItemsPerCta, 32, kSeqItemsPerCta * kFseTableEntries * 4, s>>>(p);
+    dec_exec_kernel<<<p.nItems, kExecThreads, 0, s>>>(p);
+}
+
+void dec_launch_wave_timed(const DecPass& p, cudaStream_t s, cudaEvent_t* ev)
+{
+    dec_reset_counters_kernel<<<1, 32, 0, s>>>(p.counters);
+    cudaEventRecord(ev[0], s);
+    dec_setup_kernel<<<(p.nItems + kSetupWarps - 1) / kSetupWarps, kSetupWarps * 32, 0, s>>>(p);
+    cudaEventRecord(ev[1], s);
+    dec_set_attrs();
+    dec_huf_kernel<<<(p.nItems + kHufItemsPerCta - 1) / kHufItemsPerCta, kHufThreads, kHufItemsPerCta * kHufSmemEntries * 2, s>>>(p);
+    cudaEventRecord(ev[2], s);
+    dec_seq_kernel<<<(p.nItems + kSeqItemsPerCta - 1) / kSeqItemsPerCta, 32, kSeqItemsPerCta * kFseTableEntries * 4, s>>>(p);
+    cudaEventRecord(ev[3], s);
+    dec_exec_kernel<<<p.nItems, kExecThreads, 0, s>>>(p);
+    cudaEventRecord(ev[4], s);
+}
+
+void dec_launch_finish(const DecPass& p, cudaStream_t s)
+{
+    dec_finish_kernel<<<(p.nItems + 255) / 256, 256, 0, s>>>(p);
+}
+
+void dec_launch_scan_init(const DecPass& p, const void* init, cudaStream_t s)
+{
+    dec_scan_kernel<<<(p.nItems + 127) / 128, 128, 0, s>>>(p, (const DecItemInit*)init);
+}
+
+}  // namespace zb

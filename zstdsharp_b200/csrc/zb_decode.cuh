@@ -1,0 +1,96 @@
+// zb_decode.cuh -- device-side data layout of the batch decoder (product code).
+//
+// HBM layout for one decode pass over `n` items (an item = one caller buffer holding >= 1 concatenated frames):
+//   DecItem      items[n]                  persistent per-item cursor + current-block descriptor
+//   uint16_t     hufTable[n][4096]         single-symbol Huffman table, entry = byte<<8 | nbBits (HufDecompress.cs:80)
+//   uint32_t     fseTable[n][1280]         compact LL(512) | ML(512) | OF(256) sequence tables (ZstdDecompressBlock.cs:1571)
+//   uint8_t      litBuf[n][kLitStride]     regenerated literals, 4 segments each padded to 16 B
+//   uint32_t     seqLL/ML/OF[n][kSeqCap]   decoded (litLength, matchLength, offset) triples, struct-of-arrays
+// Blocks of a frame are processed in "waves": wave k handles the k-th block of every item that still has one, so
+// repeat-mode tables, rep codes and the window carry over through the persistent per-item state.
+#pragma once
+#include "zb_common.cuh"
+
+namespace zb {
+
+constexpr uint32_t kHufTableEntries = 1u << kHufTableLogMax;       // 4096 x u16
+constexpr uint32_t kFseLLOff = 0, kFseMLOff = 512, kFseOFOff = 1024, kFseTableEntries = 1280;
+constexpr uint32_t kLitStride = kBlockSizeMax + 64;                // 4 x 15 B of segment padding fits
+
+enum : uint32_t { kStRunning = 0, kStDone = 1, kStError = 2 };
+enum : uint32_t { kBlkRaw = 0, kBlkRle = 1, kBlkCompressed = 2, kBlkNone = 3 };
+enum : uint32_t { kLitRaw = 0, kLitRle = 1, kLitHuf = 2 };
+
+// Compact FSE decode entry: [0,4) nbBits | [4,9) nbAdditionalBits | [9,15) symbol | [16,26) nextState base
+__host__ __device__ inline uint32_t fse_pack(uint32_t nbBits, uint32_t addBits, uint32_t sym, uint32_t next)
+{ return nbBits | (addBits << 4) | (sym << 9) | (next << 16); }
+
+struct __align__(16) DecItem {
+    // ---- static for the pass ----
+    uint64_t srcOff;        // byte offset of the item inside the packed source buffer
+    uint64_t dstOff;        // byte offset of the item's output inside the destination buffer
+    uint32_t srcSize;
+    uint32_t dstCap;
+    // ---- cursor (persists across waves) ----
+    uint32_t srcPos;        // next unread byte of the item
+    uint32_t outPos;        // bytes regenerated so far (all frames of the item)
+    uint32_t frameStart;    // outPos at which the current frame began (prefixStart)
+    uint32_t status;        // kStRunning / kStDone / kStError
+    uint32_t errCode;
+    uint32_t inFrame;
+    uint32_t moreThan1Frame;
+    uint32_t checksumFlag;
+    uint32_t hasFcs;
+    uint32_t _pad0;
+    uint64_t fcs;
+    uint32_t rep[3];
+    uint32_t litEntropy;    // a Huffman table from an earlier block of this frame is available
+    uint32_t fseEntropy;    // sequence tables from an earlier block of this frame are available
+    uint32_t hufLog;
+    uint32_t llLog, ofLog, mlLog;
+    // ---- descriptor of the block handled in the current wave ----
+    uint32_t blkType;
+    uint32_t blkSrcOff;     // offset (in item) of the block content
+    uint32_t blkSize;       // raw: byte count; rle: regenerated size; compressed: compressed size
+    uint32_t lastBlock;
+    uint32_t litType;
+    uint32_t litSize;
+    uint32_t litOff;        // raw: offset of literal bytes; rle: offset of the repeated byte
+    uint32_t nStreams;
+    uint32_t streamOff[4];
+    uint32_t streamLen[4];
+    uint32_t nbSeq;
+    uint32_t seqOff;
+    uint32_t seqLen;
+    uint32_t blockOut;      // regenerated size of this block (literals-only part added by exec)
+    uint32_t seqLitEnd;     // literals consumed by the sequences (set by seq_decode)
+    uint32_t _pad1[3];
+};
+
+struct DecPass {
+    DecItem* items;
+    uint32_t nItems;
+    const uint8_t* src;     // packed source bytes
+    uint8_t* dst;           // destination bytes
+    uint16_t* hufTable;
+    uint32_t* fseTable;
+    uint8_t* litBuf;
+    uint32_t* seqLL;
+    uint32_t* seqML;
+    uint32_t* seqOF;
+    const uint32_t* defaultFse;  // predefined LL|ML|OF tables (ZstdDecompressBlock.cs:398/:857/:1092)
+    uint32_t* hufList;      // item indices that need literal decoding this wave
+    uint32_t* seqList;      // item indices that need sequence decoding this wave
+    uint32_t* counters;     // [0] hufCount [1] seqCount [2] running items after this wave [3] max blocks (scan)
+    uint64_t* results;      // per item: regenerated size or error code
+};
+
+// host-callable launchers (zb_decode.cu)
+void dec_build_default_tables(uint32_t* d_defaultFse, cudaStream_t s);
+struct DecItemInit { uint64_t srcOff; uint64_t dstOff; uint32_t srcSize; uint32_t dstCap; };
+void dec_launch_scan_init(const DecPass& p, const void* d_init, cudaStream_t s);
+void dec_launch_wave(const DecPass& p, cudaStream_t s);
+void dec_launch_wave_timed(const DecPass& p, cudaStream_t s, cudaEvent_t* ev5);
+void dec_launch_finish(const DecPass& p, cudaStream_t s);
+
+}  // namespace zb

@@ -1,0 +1,29 @@
+// zb_encode.cuh -- host-visible interface of the batch encoder (product code).
+#pragma once
+#include "zb_common.cuh"
+
+namespace zb {
+
+struct EncArenaImpl;
+struct EncArena {
+    EncArenaImpl* impl = nullptr;
+    void release();
+    const uint8_t* compactBuf() const;
+};
+
+// ZSTD_compressBound, ZstdCompress.cs:19-22
+inline size_t enc_compress_bound(size_t srcSize)
+{ return srcSize + (srcSize >> 8) + ((srcSize < (128u << 10)) ? (((128u << 10) - srcSize) >> 11) : 0); }
+
+// Compresses n device-resident chunks (each one frame) at `level` (0..3). result[i] = frame size or error code.
+// timings: [1] all kernels, [8] match finder, [9] entropy stage.
+bool enc_compress_device(EncArena& A, cudaStream_t stream, cudaEvent_t* ev, size_t n, int level,
+                         const uint8_t* d_src, const uint64_t* srcOff, const size_t* srcSize,
+                         uint8_t* d_dst, const uint64_t* dstOff, const size_t* dstCap, size_t* result,
+                         float* timings, unsigned* launches);
+// Gathers the n variable-size frames into one dense device buffer (A.compactBuf()) at offsets cOff.
+bool enc_compact_device(EncArena& A, cudaStream_t stream, size_t n, const uint8_t* d_dst, const uint64_t* dstOff,
+                        const size_t* sizes, const uint64_t* cOff, size_t total, unsigned* launches);
+const char* enc_last_error();
+
+}  // namespace zb
