@@ -1,11 +1,1207 @@
-// zb_encode.cu -- placeholder until the encoder kernels land (next commit).
+// zb_encode.cu -- batch Zstandard frame encoder for sm_100a, levels 1..3 (product code; no CPU fallback).
+//
+// Replaces, for batches of independent chunks (one frame of one block each, srcSize <= 128 KiB), the reference's
+//   ZSTD_compress2 -> ZSTD_compressEnd -> ZSTD_compress_frameChunk -> ZSTD_compressBlock_internal   (ZstdCompress.cs:7138,5665,4690,4528)
+//     -> ZSTD_buildSeqStore -> ZSTD_compressBlock_fast / ZSTD_compressBlock_doubleFast               (:3432, ZstdFast.cs:96, ZstdDoubleFast.cs:51)
+//     -> ZSTD_entropyCompressSeqStore: ZSTD_compressLiterals (HIST_count, HUF_buildCTable, HUF_writeCTable,
+//        HUF_compress{1,4}X_usingCTable), ZSTD_buildSequencesStatistics (FSE_normalizeCount, FSE_writeNCount,
+//        FSE_buildCTable), ZSTD_encodeSequences                                                     (:3357; HufCompress.cs; FseCompress.cs; ZstdCompressSequences.cs)
+// The output of every chunk is byte-identical to what the reference's Compressor.Wrap produces for that chunk.
+// Kernels:
+//   enc_match_kernel     lane / chunk   exact restatement of the greedy hash-table parse (serial by construction)
+//   enc_entropy_kernel   CTA  / chunk   literal gather + histograms, Huffman/FSE table construction (one thread),
+//                                       parallel bit scatter of the 4 Huffman streams and of the sequence bitstream,
+//                                       block/frame assembly with the reference's accept/reject gates
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
 #include "zb_encode.cuh"
+
 namespace zb {
-struct EncArenaImpl {};
-void EncArena::release() {}
-const uint8_t* EncArena::compactBuf() const { return nullptr; }
-static const char* g_err = "encoder not built yet";
-bool enc_compress_device(EncArena&, cudaStream_t, cudaEvent_t*, size_t, int, const uint8_t*, const uint64_t*, const size_t*, uint8_t*, const uint64_t*, const size_t*, size_t*, float*, unsigned*) { return false; }
-bool enc_compact_device(EncArena&, cudaStream_t, size_t, const uint8_t*, const uint64_t*, const size_t*, const uint64_t*, size_t, unsigned*) { return false; }
-const char* enc_last_error() { return g_err; }
+
+// ------------------------------------------------------------------------------------------------------------
+//  Parameters: Clevels.cs:8 rows 0..3 of the four size tables, ZSTD_getCParams_internal (ZstdCompress.cs:7891),
+//  ZSTD_adjustCParams_internal (:2023).  Host-side integer logic, evaluated once per chunk.
+// ------------------------------------------------------------------------------------------------------------
+struct CParams { uint32_t windowLog, chainLog, hashLog, searchLog, minMatch, targetLength, strategy; };
+static const CParams kDefaultCParams[4][4] = {
+    {{19, 12, 13, 1, 6, 1, 1}, {19, 13, 14, 1, 7, 0, 1}, {20, 15, 16, 1, 6, 0, 1}, {21, 16, 17, 1, 5, 0, 2}},
+    {{18, 12, 13, 1, 5, 1, 1}, {18, 13, 14, 1, 6, 0, 1}, {18, 14, 14, 1, 5, 0, 2}, {18, 16, 16, 1, 4, 0, 2}},
+    {{17, 12, 12, 1, 5, 1, 1}, {17, 12, 13, 1, 6, 0, 1}, {17, 13, 15, 1, 5, 0, 1}, {17, 15, 16, 2, 5, 0, 2}},
+    {{14, 12, 13, 1, 5, 1, 1}, {14, 14, 15, 1, 5, 0, 1}, {14, 14, 15, 1, 4, 0, 1}, {14, 14, 15, 2, 4, 0, 2}},
+};
+static uint32_t h_highbit(uint32_t v) { return 31 - (uint32_t)__builtin_clz(v); }
+static CParams adjust_cparams(CParams c, uint64_t srcSize)
+{
+    if (srcSize < (1ull << 30)) {
+        uint32_t const t = (uint32_t)srcSize;
+        uint32_t const srcLog = t < 64 ? 6 : h_highbit(t - 1) + 1;
+        if (c.windowLog > srcLog) c.windowLog = srcLog;
+    }
+    if (c.hashLog > c.windowLog + 1) c.hashLog = c.windowLog + 1;
+    if (c.chainLog > c.windowLog) c.chainLog -= (c.chainLog - c.windowLog);
+    if (c.windowLog < 10) c.windowLog = 10;
+    return c;
 }
+static CParams get_cparams(int level, uint64_t srcSize)
+{
+    uint32_t const tableID = (srcSize <= 256 * 1024) + (srcSize <= 128 * 1024) + (srcSize <= 16 * 1024);
+    int const row = level == 0 ? 3 : level;
+    return adjust_cparams(adjust_cparams(kDefaultCParams[tableID][row], srcSize), srcSize);
+}
+
+// ------------------------------------------------------------------------------------------------------------
+//  Device-side layout
+// ------------------------------------------------------------------------------------------------------------
+constexpr uint32_t kEncSeqCap = kBlockSizeMax / 4 + 1;      // maxNbSeq = blockSize / 4 (minMatch != 3), ZstdCompress.cs:2570
+constexpr uint32_t kEncLitStride = kBlockSizeMax + 64;
+
+struct __align__(16) EncItem {
+    uint64_t srcOff, dstOff;
+    uint32_t srcSize, dstCap;
+    uint32_t windowLog, hashLog, chainLog, minMatch, strategy;
+    uint32_t tableOff;      // offset (in u32 entries) of this chunk's hash table(s) inside the table arena
+    uint32_t nbSeq, lastLL;
+    uint32_t _pad[2];
+};
+
+struct EncPass {
+    EncItem* items; uint32_t nItems;
+    const uint8_t* src; uint8_t* dst;
+    uint32_t* tables;       // zero-initialised hash tables (one region per chunk)
+    uint32_t* seqLL; uint32_t* seqML; uint32_t* seqOF;   // litLength, matchLength-3, offCode+1 (seqDef_s.cs)
+    uint8_t* litBuf;        // gathered literals
+    uint64_t* stateBits;    // per sequence: FSE state bits of OF | ML | LL (13 bits each: 9 value + 4 count)
+    uint64_t* results;
+};
+
+__device__ __forceinline__ uint32_t rd32(const uint8_t* p)
+{
+    uintptr_t const a = (uintptr_t)p; const uint32_t* w = (const uint32_t*)(a & ~(uintptr_t)3); uint32_t const sh = (uint32_t)(a & 3) * 8;
+    uint32_t const lo = w[0];
+    if (sh == 0) return lo;
+    return __funnelshift_r(lo, w[1], sh);
+}
+__device__ __forceinline__ uint64_t rd64(const uint8_t* p)
+{
+    uintptr_t const a = (uintptr_t)p; const uint32_t* w = (const uint32_t*)(a & ~(uintptr_t)3); uint32_t const sh = (uint32_t)(a & 3) * 8;
+    uint32_t const w0 = w[0], w1 = w[1];
+    if (sh == 0) return (uint64_t)w0 | ((uint64_t)w1 << 32);
+    uint32_t const w2 = w[2];
+    return (uint64_t)__funnelshift_r(w0, w1, sh) | ((uint64_t)__funnelshift_r(w1, w2, sh) << 32);
+}
+
+// ZSTD_hashPtr, ZstdCompressInternal.cs:340-437
+__device__ __forceinline__ uint32_t hash_ptr(const uint8_t* p, uint32_t hBits, uint32_t mls)
+{
+    switch (mls) {
+    default:
+    case 4: return (rd32(p) * 2654435761u) >> (32 - hBits);
+    case 5: return (uint32_t)(((rd64(p) << 24) * 889523592379ull) >> (64 - hBits));
+    case 6: return (uint32_t)(((rd64(p) << 16) * 227718039650203ull) >> (64 - hBits));
+    case 7: return (uint32_t)(((rd64(p) << 8) * 58295818150454627ull) >> (64 - hBits));
+    case 8: return (uint32_t)((rd64(p) * 0xCF1BBCDCB7A56463ull) >> (64 - hBits));
+    }
+}
+// ZSTD_count, ZstdCompressInternal.cs:264: common-prefix length bounded by pInLimit
+__device__ __forceinline__ uint32_t count_match(const uint8_t* pIn, const uint8_t* pMatch, const uint8_t* const pInLimit)
+{
+    const uint8_t* const pStart = pIn;
+    while (pIn + 4 <= pInLimit) {
+        uint32_t const diff = rd32(pIn) ^ rd32(pMatch);
+        if (diff) return (uint32_t)(pIn - pStart) + (__ffs((int)diff) - 1) / 8;
+        pIn += 4; pMatch += 4;
+    }
+    while (pIn < pInLimit && *pMatch == *pIn) { pIn++; pMatch++; }
+    return (uint32_t)(pIn - pStart);
+}
+
+struct SeqWriter {
+    uint32_t* ll; uint32_t* ml; uint32_t* of; uint32_t n;
+    __device__ __forceinline__ void store(uint32_t litLength, uint32_t offCode, uint32_t mlBase)   // ZSTD_storeSeq :204
+    { ll[n] = litLength; of[n] = offCode + 1; ml[n] = mlBase; n++; }
+};
+
+// ZSTD_compressBlock_fast_noDict_generic, ZstdFast.cs:96 (first block of a frame: base index 2, prefixStart = istart)
+__device__ uint32_t match_fast(uint32_t* hashTable, uint32_t hlog, uint32_t mls, const uint8_t* istart, uint32_t srcSize, SeqWriter& sw)
+{
+    const uint8_t* const base = istart - 2;
+    uint32_t const prefixStartIndex = 2;
+    const uint8_t* const prefixStart = istart;
+    const uint8_t* const iend = istart + srcSize; const uint8_t* const ilimit = iend - 8;
+    const uint8_t* anchor = istart; const uint8_t* ip0 = istart; const uint8_t* ip1; const uint8_t* ip2; const uint8_t* ip3;
+    uint32_t current0 = 0; uint32_t rep1 = 1, rep2 = 4;
+    uint32_t hash0, hash1, idx, mval, offcode; const uint8_t* match0; uint32_t mLength; uint32_t step; const uint8_t* nextStep;
+    ip0 += 1;                                           // ip0 == prefixStart (:129)
+    {   uint32_t const maxRep = 1;                      // curr - windowLow = 3 - 2 (:131-145)
+        if (rep2 > maxRep) rep2 = 0;
+        if (rep1 > maxRep) rep1 = 0;
+    }
+_start:
+    step = 2; nextStep = ip0 + 128;
+    ip1 = ip0 + 1; ip2 = ip0 + step; ip3 = ip2 + 1;
+    if (ip3 >= ilimit) goto _cleanup;
+    hash0 = hash_ptr(ip0, hlog, mls); hash1 = hash_ptr(ip1, hlog, mls);
+    idx = hashTable[hash0];
+    do {
+        uint32_t const rval = rep1 ? rd32(ip2 - rep1) : 0;
+        current0 = (uint32_t)(ip0 - base);
+        hashTable[hash0] = current0;
+        if ((rep1 > 0) && (rd32(ip2) == rval)) {
+            ip0 = ip2; match0 = ip0 - rep1;
+            mLength = ip0[-1] == match0[-1];
+            ip0 -= mLength; match0 -= mLength;
+            offcode = 0; mLength += 4;
+            goto _match;
+        }
+        mval = idx >= prefixStartIndex ? rd32(base + idx) : (rd32(ip0) ^ 1);
+        if (rd32(ip0) == mval) goto _offset;
+        idx = hashTable[hash1];
+        hash0 = hash1; hash1 = hash_ptr(ip2, hlog, mls);
+        ip0 = ip1; ip1 = ip2; ip2 = ip3;
+        current0 = (uint32_t)(ip0 - base);
+        hashTable[hash0] = current0;
+        mval = idx >= prefixStartIndex ? rd32(base + idx) : (rd32(ip0) ^ 1);
+        if (rd32(ip0) == mval) goto _offset;
+        idx = hashTable[hash1];
+        hash0 = hash1; hash1 = hash_ptr(ip2, hlog, mls);
+        ip0 = ip1; ip1 = ip2; ip2 = ip0 + step; ip3 = ip1 + step;
+        if (ip2 >= nextStep) { step++; nextStep += 128; }
+    } while (ip3 < ilimit);
+_cleanup:
+    return (uint32_t)(iend - anchor);
+_offset:
+    match0 = base + idx;
+    rep2 = rep1; rep1 = (uint32_t)(ip0 - match0);
+    offcode = rep1 + 2;
+    mLength = 4;
+    while (((ip0 > anchor) & (match0 > prefixStart)) && (ip0[-1] == match0[-1])) { ip0--; match0--; mLength++; }
+_match:
+    mLength += count_match(ip0 + mLength, match0 + mLength, iend);
+    sw.store((uint32_t)(ip0 - anchor), offcode, mLength - 3);
+    ip0 += mLength; anchor = ip0;
+    if (ip1 < ip0) hashTable[hash1] = (uint32_t)(ip1 - base);
+    if (ip0 <= ilimit) {
+        hashTable[hash_ptr(base + current0 + 2, hlog, mls)] = current0 + 2;
+        hashTable[hash_ptr(ip0 - 2, hlog, mls)] = (uint32_t)(ip0 - 2 - base);
+        if (rep2 > 0) {
+            while ((ip0 <= ilimit) && (rd32(ip0) == rd32(ip0 - rep2))) {
+                uint32_t const rLength = count_match(ip0 + 4, ip0 + 4 - rep2, iend) + 4;
+                { uint32_t const t = rep2; rep2 = rep1; rep1 = t; }
+                hashTable[hash_ptr(ip0, hlog, mls)] = (uint32_t)(ip0 - base);
+                ip0 += rLength;
+                sw.store(0, 0, rLength - 3);
+                anchor = ip0;
+            }
+        }
+    }
+    goto _start;
+}
+
+// ZSTD_compressBlock_doubleFast_noDict_generic, ZstdDoubleFast.cs:51
+__device__ uint32_t match_dfast(uint32_t* hashLong, uint32_t hBitsL, uint32_t* hashSmall, uint32_t hBitsS, uint32_t mls,
+                                const uint8_t* istart, uint32_t srcSize, SeqWriter& sw)
+{
+    const uint8_t* const base = istart - 2;
+    uint32_t const prefixLowestIndex = 2;
+    const uint8_t* const prefixLowest = istart;
+    const uint8_t* const iend = istart + srcSize; const uint8_t* const ilimit = iend - 8;
+    const uint8_t* anchor = istart;
+    uint32_t offset_1 = 1, offset_2 = 4;
+    uint32_t mLength, offset, curr = 0;
+    const uint8_t* nextStep; uint32_t step; uint32_t hl0, hl1 = 0; uint32_t idxl0, idxl1 = 0;
+    const uint8_t* matchl0; const uint8_t* matchs0; const uint8_t* matchl1 = istart;
+    const uint8_t* ip = istart; const uint8_t* ip1;
+    ip += 1;
+    {   uint32_t const maxRep = 1;
+        if (offset_2 > maxRep) offset_2 = 0;
+        if (offset_1 > maxRep) offset_1 = 0;
+    }
+    while (1) {
+        step = 1; nextStep = ip + 256; ip1 = ip + step;
+        if (ip1 > ilimit) goto _cleanup;
+        hl0 = hash_ptr(ip, hBitsL, 8);
+        idxl0 = hashLong[hl0]; matchl0 = base + idxl0;
+        do {
+            uint32_t const hs0 = hash_ptr(ip, hBitsS, mls);
+            uint32_t const idxs0 = hashSmall[hs0];
+            curr = (uint32_t)(ip - base);
+            matchs0 = base + idxs0;
+            hashLong[hl0] = hashSmall[hs0] = curr;
+            if ((offset_1 > 0) && (rd32(ip + 1 - offset_1) == rd32(ip + 1))) {
+                mLength = count_match(ip + 1 + 4, ip + 1 + 4 - offset_1, iend) + 4;
+                ip++;
+                sw.store((uint32_t)(ip - anchor), 0, mLength - 3);
+                goto _match_stored;
+            }
+            hl1 = hash_ptr(ip1, hBitsL, 8);
+            if (idxl0 > prefixLowestIndex) {
+                if (rd64(matchl0) == rd64(ip)) {
+                    mLength = count_match(ip + 8, matchl0 + 8, iend) + 8;
+                    offset = (uint32_t)(ip - matchl0);
+                    while (((ip > anchor) & (matchl0 > prefixLowest)) && (ip[-1] == matchl0[-1])) { ip--; matchl0--; mLength++; }
+                    goto _match_found;
+                }
+            }
+            idxl1 = hashLong[hl1]; matchl1 = base + idxl1;
+            if (idxs0 > prefixLowestIndex) {
+                if (rd32(matchs0) == rd32(ip)) goto _search_next_long;
+            }
+            if (ip1 >= nextStep) { step++; nextStep += 256; }
+            ip = ip1; ip1 += step;
+            hl0 = hl1; idxl0 = idxl1; matchl0 = matchl1;
+        } while (ip1 <= ilimit);
+_cleanup:
+        return (uint32_t)(iend - anchor);
+_search_next_long:
+        if (idxl1 > prefixLowestIndex) {
+            if (rd64(matchl1) == rd64(ip1)) {
+                ip = ip1;
+                mLength = count_match(ip + 8, matchl1 + 8, iend) + 8;
+                offset = (uint32_t)(ip - matchl1);
+                while (((ip > anchor) & (matchl1 > prefixLowest)) && (ip[-1] == matchl1[-1])) { ip--; matchl1--; mLength++; }
+                goto _match_found;
+            }
+        }
+        mLength = count_match(ip + 4, matchs0 + 4, iend) + 4;
+        offset = (uint32_t)(ip - matchs0);
+        while (((ip > anchor) & (matchs0 > prefixLowest)) && (ip[-1] == matchs0[-1])) { ip--; matchs0--; mLength++; }
+_match_found:
+        offset_2 = offset_1; offset_1 = offset;
+        if (step < 4) hashLong[hl1] = (uint32_t)(ip1 - base);
+        sw.store((uint32_t)(ip - anchor), offset + 2, mLength - 3);
+_match_stored:
+        ip += mLength; anchor = ip;
+        if (ip <= ilimit) {
+            {   uint32_t const indexToInsert = curr + 2;
+                hashLong[hash_ptr(base + indexToInsert, hBitsL, 8)] = indexToInsert;
+                hashLong[hash_ptr(ip - 2, hBitsL, 8)] = (uint32_t)(ip - 2 - base);
+                hashSmall[hash_ptr(base + indexToInsert, hBitsS, mls)] = indexToInsert;
+                hashSmall[hash_ptr(ip - 1, hBitsS, mls)] = (uint32_t)(ip - 1 - base);
+            }
+            while ((ip <= ilimit) && ((offset_2 > 0) && (rd32(ip) == rd32(ip - offset_2)))) {
+                uint32_t const rLength = count_match(ip + 4, ip + 4 - offset_2, iend) + 4;
+                uint32_t const t = offset_2; offset_2 = offset_1; offset_1 = t;
+                hashSmall[hash_ptr(ip, hBitsS, mls)] = (uint32_t)(ip - base);
+                hashLong[hash_ptr(ip, hBitsL, 8)] = (uint32_t)(ip - base);
+                sw.store(0, 0, rLength - 3);
+                ip += rLength; anchor = ip;
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(32) enc_match_kernel(EncPass p)
+{
+    uint32_t const i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= p.nItems) return;
+    EncItem& it = p.items[i];
+    it.nbSeq = 0; it.lastLL = it.srcSize;
+    if (it.srcSize < 7 || it.srcSize > kBlockSizeMax) return;      // ZSTD_buildSeqStore: srcSize < MIN_CBLOCK_SIZE+blockHeader+1 -> noCompress (:3438)
+    SeqWriter sw{p.seqLL + (size_t)i * kEncSeqCap, p.seqML + (size_t)i * kEncSeqCap, p.seqOF + (size_t)i * kEncSeqCap, 0};
+    const uint8_t* const src = p.src + it.srcOff;
+    uint32_t* const tab = p.tables + it.tableOff;
+    uint32_t lastLL;
+    if (it.strategy == 1) lastLL = match_fast(tab, it.hashLog, it.minMatch, src, it.srcSize, sw);
+    else lastLL = match_dfast(tab, it.hashLog, tab + (1u << it.hashLog), it.chainLog, it.minMatch, src, it.srcSize, sw);
+    it.nbSeq = sw.n; it.lastLL = lastLL;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+//  Entropy stage: one CTA per chunk
+// ------------------------------------------------------------------------------------------------------------
+constexpr int kEntThreads = 256;
+
+struct NodeElt { uint32_t count; uint16_t parent; uint8_t byte; uint8_t nbBits; };   // nodeElt_s.cs
+struct SymbolTT { int32_t deltaFindState; uint32_t deltaNbBits; };                   // FSE_symbolCompressionTransform.cs
+struct FseCTable { uint32_t tableLog; uint16_t stateTable[512]; SymbolTT tt[53]; };
+
+struct EntShared {
+    uint32_t hist[4][256];          // per-segment literal histograms
+    uint32_t count[256];            // total literal histogram / sequence-code histogram
+    uint8_t hufNbBits[256]; uint16_t hufValue[256];
+    NodeElt huffNode[513];
+    uint16_t rankBase[192], rankCurr[192];
+    uint8_t huffWeight[256];
+    FseCTable ct[3];                // 0 LL, 1 OF, 2 ML
+    FseCTable wct;                  // weights table (log <= 6)
+    int16_t norm[64];
+    uint16_t cumul[64];
+    uint8_t tableSymbol[512];
+    uint8_t hdr[192];               // Huffman tree description / NCount headers staging
+    uint32_t scanA[kEntThreads / 32], scanB[kEntThreads / 32];
+    uint32_t streamBits[4];
+    // scalars
+    uint32_t litSize, hufLog, maxSym, hSize, litMode /*0 raw 1 rle 2 huf*/, singleStream, cLitSize, litSectionSize;
+    uint32_t seqHdrSize, lastCountSize, llType, ofType, mlType, bitstreamBits;
+    uint32_t op;                    // write cursor inside the dst slot
+};
+
+__device__ __forceinline__ uint32_t ent_scan_excl(uint32_t v, uint32_t* warpSums, uint32_t* total)
+{
+    uint32_t const lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t incl = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { uint32_t const o = __shfl_up_sync(0xFFFFFFFFu, incl, d); if (lane >= (uint32_t)d) incl += o; }
+    if (lane == 31) warpSums[warp] = incl;
+    __syncthreads();
+    uint32_t base = 0, tot = 0;
+#pragma unroll
+    for (int k = 0; k < kEntThreads / 32; k++) { uint32_t const s = warpSums[k]; if ((uint32_t)k < warp) base += s; tot += s; }
+    __syncthreads();
+    *total = tot;
+    return base + incl - v;
+}
+
+// ---- serial helpers (thread 0) ----
+__device__ uint32_t fse_min_table_log(uint32_t srcSize, uint32_t maxSymbolValue)      // FseCompress.cs:384
+{ uint32_t const a = highbit32(srcSize) + 1, b = highbit32(maxSymbolValue) + 2; return a < b ? a : b; }
+__device__ uint32_t fse_optimal_table_log(uint32_t maxTableLog, uint32_t srcSize, uint32_t maxSymbolValue, uint32_t minus)   // :397
+{
+    uint32_t const maxBitsSrc = highbit32(srcSize - 1) - minus;
+    uint32_t tableLog = maxTableLog;
+    uint32_t const minBits = fse_min_table_log(srcSize, maxSymbolValue);
+    if (tableLog == 0) tableLog = 11;
+    if (maxBitsSrc < tableLog) tableLog = maxBitsSrc;
+    if (minBits > tableLog) tableLog = minBits;
+    if (tableLog < 5) tableLog = 5;
+    if (tableLog > 12) tableLog = 12;
+    return tableLog;
+}
+
+__device__ bool fse_normalize_m2(int16_t* norm, uint32_t tableLog, const uint32_t* count, uint32_t total, uint32_t maxSymbolValue, int16_t lowProbCount)   // :443
+{
+    int16_t const NOT_YET_ASSIGNED = -2;
+    uint32_t s, distributed = 0, ToDistribute;
+    uint32_t const lowThreshold = total >> tableLog;
+    uint32_t lowOne = (uint32_t)(((uint64_t)total * 3) >> (tableLog + 1));
+    for (s = 0; s <= maxSymbolValue; s++) {
+        if (count[s] == 0) { norm[s] = 0; continue; }
+        if (count[s] <= lowThreshold) { norm[s] = lowProbCount; distributed++; total -= count[s]; continue; }
+        if (count[s] <= lowOne) { norm[s] = 1; distributed++; total -= count[s]; continue; }
+        norm[s] = NOT_YET_ASSIGNED;
+    }
+    ToDistribute = (1u << tableLog) - distributed;
+    if (ToDistribute == 0) return true;
+    if ((total / ToDistribute) > lowOne) {
+        lowOne = (uint32_t)(((uint64_t)total * 3) / (ToDistribute * 2));
+        for (s = 0; s <= maxSymbolValue; s++)
+            if ((norm[s] == NOT_YET_ASSIGNED) && (count[s] <= lowOne)) { norm[s] = 1; distributed++; total -= count[s]; }
+        ToDistribute = (1u << tableLog) - distributed;
+    }
+    if (distributed == maxSymbolValue + 1) {
+        uint32_t maxV = 0, maxC = 0;
+        for (s = 0; s <= maxSymbolValue; s++) if (count[s] > maxC) { maxV = s; maxC = count[s]; }
+        norm[maxV] += (int16_t)ToDistribute;
+        return true;
+    }
+    if (total == 0) {
+        for (s = 0; ToDistribute > 0; s = (s + 1) % (maxSymbolValue + 1)) if (norm[s] > 0) { ToDistribute--; norm[s]++; }
+        return true;
+    }
+    {   uint64_t const vStepLog = 62 - tableLog;
+        uint64_t const mid = (1ull << (vStepLog - 1)) - 1;
+        uint64_t const rStep = ((((uint64_t)1 << vStepLog) * ToDistribute) + mid) / total;
+        uint64_t tmpTotal = mid;
+        for (s = 0; s <= maxSymbolValue; s++) {
+            if (norm[s] == NOT_YET_ASSIGNED) {
+                uint64_t const end = tmpTotal + ((uint64_t)count[s] * rStep);
+                uint32_t const sStart = (uint32_t)(tmpTotal >> vStepLog), sEnd = (uint32_t)(end >> vStepLog);
+                uint32_t const weight = sEnd - sStart;
+                if (weight < 1) return false;
+                norm[s] = (int16_t)weight;
+                tmpTotal = end;
+            }
+        }
+    }
+    return true;
+}
+
+// FSE_normalizeCount (:574). Returns 0 on error / rle special case, else tableLog.
+__device__ uint32_t fse_normalize_count(int16_t* norm, uint32_t tableLog, const uint32_t* count, uint32_t total, uint32_t maxSymbolValue, uint32_t useLowProbCount)
+{
+    if (tableLog < 5 || tableLog > 12) return 0;
+    if (tableLog < fse_min_table_log(total, maxSymbolValue)) return 0;
+    int16_t const lowProbCount = useLowProbCount ? -1 : 1;
+    uint64_t const scale = 62 - tableLog;
+    uint64_t const step = ((uint64_t)1 << 62) / total;
+    uint64_t const vStep = 1ull << (scale - 20);
+    int stillToDistribute = 1 << tableLog;
+    uint32_t s, largest = 0; int16_t largestP = 0;
+    uint32_t const lowThreshold = total >> tableLog;
+    for (s = 0; s <= maxSymbolValue; s++) {
+        if (count[s] == total) return 0;
+        if (count[s] == 0) { norm[s] = 0; continue; }
+        if (count[s] <= lowThreshold) { norm[s] = lowProbCount; stillToDistribute--; }
+        else {
+            int16_t proba = (int16_t)(((uint64_t)count[s] * step) >> scale);
+            if (proba < 8) {
+                uint64_t const restToBeat = vStep * c_rtbTable[proba];
+                proba += ((uint64_t)count[s] * step) - ((uint64_t)proba << scale) > restToBeat;
+            }
+            if (proba > largestP) { largestP = proba; largest = s; }
+            norm[s] = proba;
+            stillToDistribute -= proba;
+        }
+    }
+    if (-stillToDistribute >= (norm[largest] >> 1)) { if (!fse_normalize_m2(norm, tableLog, count, total, maxSymbolValue, lowProbCount)) return 0; }
+    else norm[largest] += (int16_t)stillToDistribute;
+    return tableLog;
+}
+
+// FSE_writeNCount_generic (:203), writeIsSafe: the staging buffer is always large enough. Returns size or 0 on error.
+__device__ uint32_t fse_write_ncount(uint8_t* out0, const int16_t* norm, uint32_t maxSymbolValue, uint32_t tableLog)
+{
+    uint8_t* out = out0;
+    int nbBits; int const tableSize = 1 << tableLog; int remaining, threshold;
+    uint32_t bitStream = 0; int bitCount = 0; uint32_t symbol = 0; uint32_t const alphabetSize = maxSymbolValue + 1; int previousIs0 = 0;
+    bitStream += (tableLog - 5) << bitCount; bitCount += 4;
+    remaining = tableSize + 1; threshold = tableSize; nbBits = (int)tableLog + 1;
+    while ((symbol < alphabetSize) && (remaining > 1)) {
+        if (previousIs0) {
+            uint32_t start = symbol;
+            while ((symbol < alphabetSize) && !norm[symbol]) symbol++;
+            if (symbol == alphabetSize) break;
+            while (symbol >= start + 24) { start += 24; bitStream += 0xFFFFu << bitCount; out[0] = (uint8_t)bitStream; out[1] = (uint8_t)(bitStream >> 8); out += 2; bitStream >>= 16; }
+            while (symbol >= start + 3) { start += 3; bitStream += 3u << bitCount; bitCount += 2; }
+            bitStream += (symbol - start) << bitCount; bitCount += 2;
+            if (bitCount > 16) { out[0] = (uint8_t)bitStream; out[1] = (uint8_t)(bitStream >> 8); out += 2; bitStream >>= 16; bitCount -= 16; }
+        }
+        {   int count = norm[symbol++];
+            int const max = (2 * threshold - 1) - remaining;
+            remaining -= count < 0 ? -count : count;
+            count++;
+            if (count >= threshold) count += max;
+            bitStream += (uint32_t)count << bitCount;
+            bitCount += nbBits;
+            bitCount -= (count < max);
+            previousIs0 = (count == 1);
+            if (remaining < 1) return 0;
+            while (remaining < threshold) { nbBits--; threshold >>= 1; }
+        }
+        if (bitCount > 16) { out[0] = (uint8_t)bitStream; out[1] = (uint8_t)(bitStream >> 8); out += 2; bitStream >>= 16; bitCount -= 16; }
+    }
+    if (remaining != 1) return 0;
+    out[0] = (uint8_t)bitStream; out[1] = (uint8_t)(bitStream >> 8);
+    out += (bitCount + 7) / 8;
+    return (uint32_t)(out - out0);
+}
+
+// FSE_buildCTable_wksp (:13)
+__device__ void fse_build_ctable(FseCTable& ct, EntShared& S, const int16_t* norm, uint32_t maxSymbolValue, uint32_t tableLog)
+{
+    uint32_t const tableSize = 1u << tableLog, tableMask = tableSize - 1;
+    uint32_t const step = (tableSize >> 1) + (tableSize >> 3) + 3;
+    uint32_t const maxSV1 = maxSymbolValue + 1;
+    uint32_t highThreshold = tableSize - 1;
+    ct.tableLog = tableLog;
+    S.cumul[0] = 0;
+    for (uint32_t u = 1; u <= maxSV1; u++) {
+        if (norm[u - 1] == -1) { S.cumul[u] = (uint16_t)(S.cumul[u - 1] + 1); S.tableSymbol[highThreshold--] = (uint8_t)(u - 1); }
+        else S.cumul[u] = (uint16_t)(S.cumul[u - 1] + (uint16_t)norm[u - 1]);
+    }
+    S.cumul[maxSV1] = (uint16_t)(tableSize + 1);
+    {   uint32_t position = 0;
+        for (uint32_t symbol = 0; symbol < maxSV1; symbol++) {
+            int const freq = norm[symbol];
+            for (int n = 0; n < freq; n++) {
+                S.tableSymbol[position] = (uint8_t)symbol;
+                position = (position + step) & tableMask;
+                while (position > highThreshold) position = (position + step) & tableMask;
+            }
+        }
+    }
+    for (uint32_t u = 0; u < tableSize; u++) { uint8_t const s = S.tableSymbol[u]; ct.stateTable[S.cumul[s]++] = (uint16_t)(tableSize + u); }
+    {   uint32_t total = 0;
+        for (uint32_t s = 0; s <= maxSymbolValue; s++) {
+            int const nc = norm[s];
+            if (nc == 0) { ct.tt[s].deltaNbBits = ((tableLog + 1) << 16) - (1u << tableLog); ct.tt[s].deltaFindState = 0; }
+            else if (nc == -1 || nc == 1) { ct.tt[s].deltaNbBits = (tableLog << 16) - (1u << tableLog); ct.tt[s].deltaFindState = (int32_t)(total - 1); total++; }
+            else {
+                uint32_t const maxBitsOut = tableLog - highbit32((uint32_t)nc - 1);
+                uint32_t const minStatePlus = (uint32_t)nc << maxBitsOut;
+                ct.tt[s].deltaNbBits = (maxBitsOut << 16) - minStatePlus;
+                ct.tt[s].deltaFindState = (int32_t)(total - (uint32_t)nc);
+                total += (uint32_t)nc;
+            }
+        }
+    }
+}
+
+// FSE state helpers (Fse.cs:10-96)
+__device__ __forceinline__ uint32_t fse_init_state(const FseCTable& ct, uint32_t symbol)
+{
+    SymbolTT const tt = ct.tt[symbol];
+    uint32_t const nbBitsOut = (tt.deltaNbBits + (1u << 15)) >> 16;
+    uint32_t const value = (nbBitsOut << 16) - tt.deltaNbBits;
+    return ct.stateTable[(int32_t)(value >> nbBitsOut) + tt.deltaFindState];
+}
+
+// simple serial LSB-first bit writer into shared/global bytes (used only for the <= 128-byte weight stream)
+struct TinyBW { uint64_t acc; uint32_t n; uint8_t* p; uint8_t* start;
+    __device__ void add(uint32_t v, uint32_t nb) { if (!nb) return; acc |= (uint64_t)(v & ((1u << nb) - 1)) << n; n += nb; while (n >= 8) { *p++ = (uint8_t)acc; acc >>= 8; n -= 8; } }
+    __device__ uint32_t close() { add(1, 1); if (n) { *p++ = (uint8_t)acc; } return (uint32_t)(p - start); } };
+
+// HUF_compressWeights (HufCompress.cs:40). Returns compressed size, 0 = not compressible, 1 = rle; 0xFFFFFFFF on error.
+__device__ uint32_t huf_compress_weights(uint8_t* dst, uint32_t dstSize, EntShared& S, uint32_t wtSize)
+{
+    uint32_t maxSymbolValue = 12, tableLog = 6;
+    uint32_t count[13];
+    if (wtSize <= 1) return 0;
+    for (int i = 0; i < 13; i++) count[i] = 0;
+    for (uint32_t i = 0; i < wtSize; i++) count[S.huffWeight[i]]++;
+    while (!count[maxSymbolValue]) maxSymbolValue--;
+    uint32_t maxCount = 0; for (uint32_t s = 0; s <= maxSymbolValue; s++) if (count[s] > maxCount) maxCount = count[s];
+    if (maxCount == wtSize) return 1;
+    if (maxCount == 1) return 0;
+    tableLog = fse_optimal_table_log(tableLog, wtSize, maxSymbolValue, 2);
+    if (!fse_normalize_count(S.norm, tableLog, count, wtSize, maxSymbolValue, 0)) return 0xFFFFFFFFu;
+    uint32_t const hSize = fse_write_ncount(dst, S.norm, maxSymbolValue, tableLog);
+    if (!hSize) return 0xFFFFFFFFu;
+    fse_build_ctable(S.wct, S, S.norm, maxSymbolValue, tableLog);
+    // FSE_compress_usingCTable_generic (FseCompress.cs:722), 64-bit variant
+    if (wtSize <= 2) return 0;
+    if (dstSize - hSize <= 8) return 0;
+    TinyBW bw{0, 0, dst + hSize, dst + hSize};
+    const uint8_t* ip = S.huffWeight + wtSize;
+    uint32_t s1, s2; uint32_t n = wtSize;
+    auto enc = [&](uint32_t& st, uint32_t sym) { SymbolTT const tt = S.wct.tt[sym]; uint32_t const nb = (st + tt.deltaNbBits) >> 16; bw.add(st, nb); st = S.wct.stateTable[(int32_t)(st >> nb) + tt.deltaFindState]; };
+    if (n & 1) { s1 = fse_init_state(S.wct, *--ip); s2 = fse_init_state(S.wct, *--ip); enc(s1, *--ip); }
+    else { s2 = fse_init_state(S.wct, *--ip); s1 = fse_init_state(S.wct, *--ip); }
+    n -= 2;
+    if (n & 2) { enc(s2, *--ip); enc(s1, *--ip); }
+    while (ip > S.huffWeight) { enc(s2, *--ip); enc(s1, *--ip); enc(s2, *--ip); enc(s1, *--ip); }
+    bw.add(s2, tableLog); bw.add(s1, tableLog);
+    uint32_t const cSize = bw.close();
+    return hSize + cSize;
+}
+
+// HUF_sort helpers (HufCompress.cs:520-687)
+__device__ __forceinline__ uint32_t huf_get_index(uint32_t count) { return count < 165 ? count : highbit32(count) + 158; }
+__device__ void huf_insertion_sort(NodeElt* a, int low, int high)
+{
+    int const size = high - low + 1; a += low;
+    for (int i = 1; i < size; ++i) { NodeElt const key = a[i]; int j = i - 1; while (j >= 0 && a[j].count < key.count) { a[j + 1] = a[j]; j--; } a[j + 1] = key; }
+}
+__device__ int huf_partition(NodeElt* arr, int low, int high)
+{
+    uint32_t const pivot = arr[high].count; int i = low - 1;
+    for (int j = low; j < high; j++) if (arr[j].count > pivot) { i++; NodeElt t = arr[i]; arr[i] = arr[j]; arr[j] = t; }
+    NodeElt t = arr[i + 1]; arr[i + 1] = arr[high]; arr[high] = t;
+    return i + 1;
+}
+// HUF_simpleQuickSort (:607-633) with an explicit stack.  The reference checks the insertion-sort threshold only on
+// entry to a (recursive) call; the part it keeps iterating on is partitioned down to single elements.  Both modes
+// are reproduced (mode 0 = call entry, mode 1 = loop continuation); sub-ranges are disjoint, so their order is free.
+__device__ void huf_quick_sort(NodeElt* arr, int low0, int high0)
+{
+    int stackLo[48], stackHi[48]; uint8_t stackMode[48]; int sp = 0;
+    stackLo[0] = low0; stackHi[0] = high0; stackMode[0] = 0; sp = 1;
+    while (sp) {
+        sp--; int const low = stackLo[sp], high = stackHi[sp]; int const mode = stackMode[sp];
+        if (mode == 0 && high - low < 8) { huf_insertion_sort(arr, low, high); continue; }
+        if (!(low < high)) continue;
+        int const idx = huf_partition(arr, low, high);
+        if (idx - low < high - idx) {
+            stackLo[sp] = idx + 1; stackHi[sp] = high; stackMode[sp] = 1; sp++;
+            stackLo[sp] = low; stackHi[sp] = idx - 1; stackMode[sp] = 0; sp++;
+        } else {
+            stackLo[sp] = low; stackHi[sp] = idx - 1; stackMode[sp] = 1; sp++;
+            stackLo[sp] = idx + 1; stackHi[sp] = high; stackMode[sp] = 0; sp++;
+        }
+    }
+}
+
+// HUF_buildCTable_wksp (HufCompress.cs:790): sort, tree, depth limit, canonical codes. Returns maxNbBits.
+__device__ uint32_t huf_build_ctable(EntShared& S, uint32_t maxSymbolValue, uint32_t maxNbBits)
+{
+    NodeElt* const huffNode0 = S.huffNode; NodeElt* const huffNode = huffNode0 + 1;
+    for (int i = 0; i < 513; i++) { huffNode0[i].count = 0; huffNode0[i].parent = 0; huffNode0[i].byte = 0; huffNode0[i].nbBits = 0; }
+    // HUF_sort :635
+    uint32_t const maxSymbolValue1 = maxSymbolValue + 1;
+    for (int i = 0; i < 192; i++) { S.rankBase[i] = 0; S.rankCurr[i] = 0; }
+    for (uint32_t n = 0; n < maxSymbolValue1; ++n) S.rankBase[huf_get_index(S.count[n])]++;
+    for (uint32_t n = 191; n > 0; --n) { S.rankBase[n - 1] += S.rankBase[n]; S.rankCurr[n - 1] = S.rankBase[n - 1]; }
+    for (uint32_t n = 0; n < maxSymbolValue1; ++n) {
+        uint32_t const c = S.count[n]; uint32_t const r = huf_get_index(c) + 1; uint32_t const pos = S.rankCurr[r]++;
+        huffNode[pos].count = c; huffNode[pos].byte = (uint8_t)n;
+    }
+    for (uint32_t n = 165; n < 191; ++n) {
+        uint32_t const bucketSize = S.rankCurr[n] - S.rankBase[n]; uint32_t const bucketStartIdx = S.rankBase[n];
+        if (bucketSize > 1) huf_quick_sort(huffNode + bucketStartIdx, 0, (int)bucketSize - 1);
+    }
+    // HUF_buildTree :689
+    int nonNullRank = (int)maxSymbolValue;
+    while (huffNode[nonNullRank].count == 0) nonNullRank--;
+    {
+        int lowS = nonNullRank, nodeNb = 256; int const nodeRoot = nodeNb + lowS - 1; int lowN = nodeNb;
+        huffNode[nodeNb].count = huffNode[lowS].count + huffNode[lowS - 1].count;
+        huffNode[lowS].parent = huffNode[lowS - 1].parent = (uint16_t)nodeNb;
+        nodeNb++; lowS -= 2;
+        for (int n = nodeNb; n <= nodeRoot; n++) huffNode[n].count = 1u << 30;
+        huffNode0[0].count = 1u << 31;
+        while (nodeNb <= nodeRoot) {
+            int const n1 = (huffNode[lowS].count < huffNode[lowN].count) ? lowS-- : lowN++;
+            int const n2 = (huffNode[lowS].count < huffNode[lowN].count) ? lowS-- : lowN++;
+            huffNode[nodeNb].count = huffNode[n1].count + huffNode[n2].count;
+            huffNode[n1].parent = huffNode[n2].parent = (uint16_t)nodeNb;
+            nodeNb++;
+        }
+        huffNode[nodeRoot].nbBits = 0;
+        for (int n = nodeRoot - 1; n >= 256; n--) huffNode[n].nbBits = (uint8_t)(huffNode[huffNode[n].parent].nbBits + 1);
+        for (int n = 0; n <= nonNullRank; n++) huffNode[n].nbBits = (uint8_t)(huffNode[huffNode[n].parent].nbBits + 1);
+    }
+    // HUF_setMaxHeight :377
+    {
+        uint32_t const largestBits = huffNode[nonNullRank].nbBits;
+        if (largestBits > maxNbBits) {
+            int totalCost = 0; uint32_t const baseCost = 1u << (largestBits - maxNbBits); int n = nonNullRank;
+            while (huffNode[n].nbBits > maxNbBits) { totalCost += (int)(baseCost - (1u << (largestBits - huffNode[n].nbBits))); huffNode[n].nbBits = (uint8_t)maxNbBits; n--; }
+            while (huffNode[n].nbBits == maxNbBits) --n;
+            totalCost >>= (largestBits - maxNbBits);
+            uint32_t const noSymbol = 0xF0F0F0F0u; uint32_t rankLast[14];
+            for (int i = 0; i < 14; i++) rankLast[i] = noSymbol;
+            {   uint32_t currentNbBits = maxNbBits;
+                for (int pos = n; pos >= 0; pos--) { if (huffNode[pos].nbBits >= currentNbBits) continue; currentNbBits = huffNode[pos].nbBits; rankLast[maxNbBits - currentNbBits] = (uint32_t)pos; } }
+            while (totalCost > 0) {
+                uint32_t nBitsToDecrease = highbit32((uint32_t)totalCost) + 1;
+                for (; nBitsToDecrease > 1; nBitsToDecrease--) {
+                    uint32_t const highPos = rankLast[nBitsToDecrease], lowPos = rankLast[nBitsToDecrease - 1];
+                    if (highPos == noSymbol) continue;
+                    if (lowPos == noSymbol) break;
+                    if (huffNode[highPos].count <= 2 * huffNode[lowPos].count) break;
+                }
+                while ((nBitsToDecrease <= 12) && (rankLast[nBitsToDecrease] == noSymbol)) nBitsToDecrease++;
+                totalCost -= 1 << (nBitsToDecrease - 1);
+                huffNode[rankLast[nBitsToDecrease]].nbBits++;
+                if (rankLast[nBitsToDecrease - 1] == noSymbol) rankLast[nBitsToDecrease - 1] = rankLast[nBitsToDecrease];
+                if (rankLast[nBitsToDecrease] == 0) rankLast[nBitsToDecrease] = noSymbol;
+                else { rankLast[nBitsToDecrease]--; if (huffNode[rankLast[nBitsToDecrease]].nbBits != maxNbBits - nBitsToDecrease) rankLast[nBitsToDecrease] = noSymbol; }
+            }
+            while (totalCost < 0) {
+                if (rankLast[1] == noSymbol) { while (huffNode[n].nbBits == maxNbBits) n--; huffNode[n + 1].nbBits--; rankLast[1] = (uint32_t)(n + 1); totalCost++; continue; }
+                huffNode[rankLast[1] + 1].nbBits--; rankLast[1]++; totalCost++;
+            }
+        } else maxNbBits = largestBits;
+    }
+    // HUF_buildCTableFromTree :750
+    {
+        uint16_t nbPerRank[13], valPerRank[13];
+        for (int i = 0; i < 13; i++) { nbPerRank[i] = 0; valPerRank[i] = 0; }
+        for (int n = 0; n <= nonNullRank; n++) nbPerRank[huffNode[n].nbBits]++;
+        {   uint16_t min = 0; for (int n = (int)maxNbBits; n > 0; n--) { valPerRank[n] = min; min += nbPerRank[n]; min >>= 1; } }
+        for (int i = 0; i < 256; i++) { S.hufNbBits[i] = 0; S.hufValue[i] = 0; }
+        for (uint32_t n = 0; n < maxSymbolValue1; n++) S.hufNbBits[huffNode[n].byte] = huffNode[n].nbBits;
+        for (uint32_t n = 0; n < maxSymbolValue1; n++) { uint32_t const nb = S.hufNbBits[n]; uint16_t const v = valPerRank[nb]++; S.hufValue[n] = nb ? v : 0; }
+    }
+    return maxNbBits;
+}
+
+// HUF_writeCTable_wksp (HufCompress.cs:168) into S.hdr. Returns header size, 0 on error.
+__device__ uint32_t huf_write_ctable(EntShared& S, uint32_t maxSymbolValue, uint32_t huffLog)
+{
+    uint8_t bitsToWeight[13];
+    bitsToWeight[0] = 0;
+    for (uint32_t n = 1; n < huffLog + 1; n++) bitsToWeight[n] = (uint8_t)(huffLog + 1 - n);
+    for (uint32_t n = 0; n < maxSymbolValue; n++) S.huffWeight[n] = bitsToWeight[S.hufNbBits[n]];
+    uint32_t const hSize = huf_compress_weights(S.hdr + 1, sizeof(S.hdr) - 1, S, maxSymbolValue);
+    if (hSize == 0xFFFFFFFFu) return 0;
+    if ((hSize > 1) && (hSize < maxSymbolValue / 2)) { S.hdr[0] = (uint8_t)hSize; return hSize + 1; }
+    if (maxSymbolValue > 128) return 0;
+    S.hdr[0] = (uint8_t)(128 + (maxSymbolValue - 1));
+    S.huffWeight[maxSymbolValue] = 0;
+    for (uint32_t n = 0; n < maxSymbolValue; n += 2) S.hdr[(n / 2) + 1] = (uint8_t)((S.huffWeight[n] << 4) + S.huffWeight[n + 1]);
+    return ((maxSymbolValue + 1) / 2) + 1;
+}
+
+// ZSTD_selectEncodingType (ZstdCompressSequences.cs:400), strategy < ZSTD_lazy, first block (no repeat mode)
+__device__ uint32_t select_encoding_type(uint32_t mostFrequent, uint32_t nbSeq, uint32_t defaultNormLog, bool isDefaultAllowed, uint32_t strategy)
+{
+    if (mostFrequent == nbSeq) { if (isDefaultAllowed && nbSeq <= 2) return 0; return 1; }
+    if (isDefaultAllowed) {
+        uint32_t const mult = 10 - strategy;
+        uint32_t const dynamicFse_nbSeq_min = ((1u << defaultNormLog) * mult) >> 3;
+        if ((nbSeq < dynamicFse_nbSeq_min) || (mostFrequent < (nbSeq >> (defaultNormLog - 1)))) return 0;
+    }
+    return 2;
+}
+
+__device__ __forceinline__ uint32_t ll_code(uint32_t ll) { return ll > 63 ? highbit32(ll) + 19 : c_LL_Code[ll]; }     // ZstdCompressInternal.cs:20
+__device__ __forceinline__ uint32_t ml_code(uint32_t ml) { return ml > 127 ? highbit32(ml) + 36 : c_ML_Code[ml]; }    // :32
+
+// scatter `nb` (<= 32) bits of v at absolute bit position `bit` of the zeroed word array w
+__device__ __forceinline__ void put_bits(uint32_t* w, uint64_t bit, uint32_t v, uint32_t nb)
+{
+    if (!nb) return;
+    uint32_t const sh = (uint32_t)(bit & 31); uint64_t const x = (uint64_t)(nb < 32 ? (v & ((1u << nb) - 1)) : v) << sh;
+    atomicOr(&w[bit >> 5], (uint32_t)x);
+    if (sh + nb > 32) atomicOr(&w[(bit >> 5) + 1], (uint32_t)(x >> 32));
+}
+
+__global__ void __launch_bounds__(kEntThreads) enc_entropy_kernel(EncPass p)
+{
+    __shared__ EntShared S;
+    uint32_t const item = blockIdx.x, tid = threadIdx.x;
+    EncItem& it = p.items[item];
+    const uint8_t* const src = p.src + it.srcOff;
+    uint8_t* const dst = p.dst + it.dstOff;                    // 16-byte aligned slot of compressBound(srcSize) bytes
+    uint32_t* const dstW = (uint32_t*)dst;
+    uint32_t const srcSize = it.srcSize;
+    if (srcSize > kBlockSizeMax) { if (tid == 0) p.results[item] = make_error(kSrcSizeWrong); return; }
+    // ---- frame header: ZSTD_writeFrameHeader (ZstdCompress.cs:4817), contentSizeFlag = 1, no dictID, no checksum ----
+    uint32_t fhSize;
+    {
+        uint32_t const fcsCode = (srcSize >= 256) + (srcSize >= 65536 + 256);
+        fhSize = 4 + 1 + (fcsCode == 0 ? 1 : (fcsCode == 1 ? 2 : 4));      // singleSegment always holds: windowSize >= srcSize
+        if (tid == 0) {
+            dst[0] = 0x28; dst[1] = 0xB5; dst[2] = 0x2F; dst[3] = 0xFD;
+            dst[4] = (uint8_t)((1u << 5) + (fcsCode << 6));
+            if (fcsCode == 0) dst[5] = (uint8_t)srcSize;
+            else if (fcsCode == 1) { uint32_t const v = srcSize - 256; dst[5] = (uint8_t)v; dst[6] = (uint8_t)(v >> 8); }
+            else { dst[5] = (uint8_t)srcSize; dst[6] = (uint8_t)(srcSize >> 8); dst[7] = (uint8_t)(srcSize >> 16); dst[8] = (uint8_t)(srcSize >> 24); }
+        }
+    }
+    uint8_t* const blk = dst + fhSize;                          // block header goes here
+    uint32_t const payload = fhSize + 3;                        // byte offset of the block content
+    bool raw = false;
+    uint32_t cSize = 0;
+    if (srcSize == 0) {                                         // ZSTD_writeEpilogue: one empty last raw block (:5621-5631)
+        if (tid == 0) { blk[0] = 1; blk[1] = 0; blk[2] = 0; p.results[item] = fhSize + 3; }
+        return;
+    }
+    uint32_t const nbSeq = it.nbSeq;
+    if (srcSize < 7) raw = true;
+    if (!raw) {
+        const uint32_t* const aLL = p.seqLL + (size_t)item * kEncSeqCap;
+        const uint32_t* const aML = p.seqML + (size_t)item * kEncSeqCap;
+        const uint32_t* const aOF = p.seqOF + (size_t)item * kEncSeqCap;
+        uint8_t* const lit = p.litBuf + (size_t)item * kEncLitStride;
+        // ---- 1. gather literals (ZSTD_storeSeq copies + ZSTD_storeLastLiterals) ----
+        uint32_t litSize;
+        {
+            uint32_t srcPos = 0, litPos = 0;
+            for (uint32_t base = 0; base < nbSeq; base += kEntThreads) {
+                uint32_t const n = base + tid;
+                uint32_t ll = 0, ml = 0;
+                if (n < nbSeq) { ll = aLL[n]; ml = aML[n] + 3; }
+                uint32_t totS, totL;
+                uint32_t const sOff = ent_scan_excl(ll + ml, S.scanA, &totS);
+                uint32_t const lOff = ent_scan_excl(ll, S.scanB, &totL);
+                const uint8_t* s = src + srcPos + sOff; uint8_t* d = lit + litPos + lOff;
+                for (uint32_t k = 0; k < ll; k++) d[k] = s[k];
+                srcPos += totS; litPos += totL;
+            }
+            uint32_t const lastLL = it.lastLL;
+            for (uint32_t k = tid; k < lastLL; k += kEntThreads) lit[litPos + k] = src[srcSize - lastLL + k];
+            litSize = litPos + lastLL;
+        }
+        for (uint32_t k = tid; k < 1024; k += kEntThreads) (&S.hist[0][0])[k] = 0;
+        __syncthreads();
+        // ---- 2. literals section: ZSTD_compressLiterals (ZstdCompressLiterals.cs:86) ----
+        uint32_t const minGainLit = (litSize >> 6) + 2;
+        uint32_t const lhSize = 3 + (litSize >= 1024) + (litSize >= 16384);
+        uint32_t const singleStream = litSize < 256;
+        uint32_t const seg = (litSize + 3) / 4;
+        uint32_t litMode = 0;   // 0 raw, 1 rle, 2 huffman
+        if (litSize > 63) {
+            bool const suspect = (nbSeq == 0) || (litSize / nbSeq >= 20);       // ZstdCompress.cs:3262
+            bool skip = false;
+            if (suspect && litSize >= 40960) {                                   // HufCompress.cs:1412-1446
+                for (uint32_t k = tid; k < 4096; k += kEntThreads) { atomicAdd(&S.hist[0][lit[k]], 1u); atomicAdd(&S.hist[1][lit[litSize - 4096 + k]], 1u); }
+                __syncthreads();
+                uint32_t m0 = max(S.hist[0][tid], 0u), m1 = S.hist[1][tid];
+                for (int d = 16; d; d >>= 1) { m0 = max(m0, __shfl_xor_sync(0xFFFFFFFFu, m0, d)); m1 = max(m1, __shfl_xor_sync(0xFFFFFFFFu, m1, d)); }
+                if ((tid & 31) == 0) { S.scanA[tid >> 5] = m0; S.scanB[tid >> 5] = m1; }
+                __syncthreads();
+                uint32_t lb = 0, le = 0;
+                for (int k = 0; k < kEntThreads / 32; k++) { lb = max(lb, S.scanA[k]); le = max(le, S.scanB[k]); }
+                skip = (lb + le) <= ((2 * 4096) >> 7) + 4;
+                __syncthreads();
+                for (uint32_t k = tid; k < 1024; k += kEntThreads) (&S.hist[0][0])[k] = 0;
+                __syncthreads();
+            }
+            if (!skip) {
+                // per-segment histograms (HIST_count_wksp, Hist.cs:196; the 4 stream totals need per-segment counts)
+                for (uint32_t k = tid; k < litSize; k += kEntThreads) atomicAdd(&S.hist[singleStream ? 0 : k / seg][lit[k]], 1u);
+                __syncthreads();
+                {
+                    uint32_t const c = S.hist[0][tid] + S.hist[1][tid] + S.hist[2][tid] + S.hist[3][tid];
+                    S.count[tid] = c;
+                    uint32_t m = c; uint32_t ms = c ? tid : 0;
+                    for (int d = 16; d; d >>= 1) { m = max(m, __shfl_xor_sync(0xFFFFFFFFu, m, d)); ms = max(ms, __shfl_xor_sync(0xFFFFFFFFu, ms, d)); }
+                    if ((tid & 31) == 0) { S.scanA[tid >> 5] = m; S.scanB[tid >> 5] = ms; }
+                }
+                __syncthreads();
+                uint32_t largest = 0, maxSym = 0;
+                for (int k = 0; k < kEntThreads / 32; k++) { largest = max(largest, S.scanA[k]); maxSym = max(maxSym, S.scanB[k]); }
+                __syncthreads();
+                if (largest == litSize) litMode = 1;                              // all same byte -> rle (HufCompress.cs:1458)
+                else if (largest <= (litSize >> 7) + 4) litMode = 0;              // not compressible enough (:1463)
+                else {
+                    if (tid == 0) {
+                        uint32_t huffLog = fse_optimal_table_log(11, litSize, maxSym, 1);       // HUF_optimalTableLog :12
+                        huffLog = huf_build_ctable(S, maxSym, huffLog);
+                        S.hufLog = huffLog;
+                        S.hSize = huffLog > 12 ? 0 : huf_write_ctable(S, maxSym, huffLog);
+                    }
+                    __syncthreads();
+                    uint32_t const hSize = S.hSize;
+                    if (hSize == 0 || hSize + 12 >= litSize) litMode = 0;          // (:1525-1528)
+                    else {
+                        // stream sizes from the per-segment histograms
+                        uint32_t const nStreams = singleStream ? 1 : 4;
+                        if (tid < 4) S.streamBits[tid] = 0;
+                        __syncthreads();
+                        for (uint32_t k = 0; k < nStreams; k++) {
+                            uint32_t v = S.hist[k][tid] * S.hufNbBits[tid];
+                            for (int d = 16; d; d >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, d);
+                            if ((tid & 31) == 0) atomicAdd(&S.streamBits[k], v);
+                        }
+                        __syncthreads();
+                        uint32_t total = hSize + (singleStream ? 0 : 6); bool bad = false;
+                        uint32_t sz[4] = {0, 0, 0, 0};
+                        for (uint32_t k = 0; k < nStreams; k++) { sz[k] = (S.streamBits[k] >> 3) + 1; if (sz[k] > 65535 && !singleStream) bad = true; total += sz[k]; }
+                        if (!singleStream && litSize < 12) bad = true;
+                        if (bad || total >= litSize - 1) litMode = 0;              // HUF_compressCTable_internal :1333-1356
+                        else if (total >= litSize - minGainLit) litMode = 0;       // ZstdCompressLiterals.cs:133
+                        else {
+                            litMode = 2;
+                            // zero the stream area, then scatter every symbol's code (symbols are appended last-to-first)
+                            uint32_t const strBase = payload + lhSize + hSize + (singleStream ? 0 : 6);
+                            for (uint32_t k = tid; k < total - hSize - (singleStream ? 0 : 6); k += kEntThreads) dst[strBase + k] = 0;
+                            __syncthreads();
+                            uint32_t strOff = strBase;
+                            for (uint32_t k = 0; k < nStreams; k++) {
+                                uint32_t const a = k * seg, b = singleStream ? litSize : min(litSize, (k + 1) * seg);
+                                uint64_t const bit0 = (uint64_t)strOff * 8;
+                                uint32_t carry = 0;           // bits already placed (from the end of the segment)
+                                // tiles from the end of the segment backwards; thread t takes 8 symbols
+                                for (uint32_t hi = b; hi > a; ) {
+                                    uint32_t const tile = min(hi - a, (uint32_t)kEntThreads * 8);
+                                    uint32_t const lo = hi - tile;
+                                    // thread t covers symbols [hi-8(t+1), hi-8t) clipped to >= lo, processed in descending order
+                                    int64_t const myHi = (int64_t)hi - 8 * (int64_t)tid, myLo = max((int64_t)lo, myHi - 8);
+                                    uint32_t bitsMine = 0;
+                                    for (int64_t q = myHi - 1; q >= myLo; q--) bitsMine += S.hufNbBits[lit[q]];
+                                    uint32_t tot;
+                                    uint32_t const off = ent_scan_excl(bitsMine, S.scanA, &tot);
+                                    uint64_t pos = bit0 + carry + off;
+                                    for (int64_t q = myHi - 1; q >= myLo; q--) { uint32_t const sym = lit[q]; uint32_t const nb = S.hufNbBits[sym]; put_bits(dstW, pos, S.hufValue[sym], nb); pos += nb; }
+                                    carry += tot; hi = lo;
+                                }
+                                if (tid == 0) put_bits(dstW, bit0 + carry, 1, 1);      // HUF_closeCStream end mark (:964)
+                                strOff += sz[k];
+                            }
+                            __syncthreads();
+                            if (tid == 0) {
+                                uint8_t* o = dst + payload;
+                                uint32_t const cLitSize = total;
+                                if (lhSize == 3) { uint32_t const lhc = 2 + ((!singleStream) << 2) + (litSize << 4) + (cLitSize << 14); o[0] = (uint8_t)lhc; o[1] = (uint8_t)(lhc >> 8); o[2] = (uint8_t)(lhc >> 16); }
+                                else if (lhSize == 4) { uint32_t const lhc = 2 + (2 << 2) + (litSize << 4) + (cLitSize << 18); o[0] = (uint8_t)lhc; o[1] = (uint8_t)(lhc >> 8); o[2] = (uint8_t)(lhc >> 16); o[3] = (uint8_t)(lhc >> 24); }
+                                else { uint32_t const lhc = 2 + (3 << 2) + (litSize << 4) + (cLitSize << 22); o[0] = (uint8_t)lhc; o[1] = (uint8_t)(lhc >> 8); o[2] = (uint8_t)(lhc >> 16); o[3] = (uint8_t)(lhc >> 24); o[4] = (uint8_t)(cLitSize >> 10); }
+                                for (uint32_t k = 0; k < hSize; k++) o[lhSize + k] = S.hdr[k];
+                                if (!singleStream) { uint8_t* j = o + lhSize + hSize; j[0] = (uint8_t)sz[0]; j[1] = (uint8_t)(sz[0] >> 8); j[2] = (uint8_t)sz[1]; j[3] = (uint8_t)(sz[1] >> 8); j[4] = (uint8_t)sz[2]; j[5] = (uint8_t)(sz[2] >> 8); }
+                                S.litSectionSize = lhSize + cLitSize;
+                            }
+                        }
+                    }
+                }
+            }
+        }
+        if (litMode == 0) {             // ZSTD_noCompressLiterals (:8)
+            uint32_t const flSize = 1 + (litSize > 31) + (litSize > 4095);
+            uint8_t* o = dst + payload;
+            if (tid == 0) {
+                if (flSize == 1) o[0] = (uint8_t)(0 + (litSize << 3));
+                else if (flSize == 2) { uint32_t const v = 0 + (1 << 2) + (litSize << 4); o[0] = (uint8_t)v; o[1] = (uint8_t)(v >> 8); }
+                else { uint32_t const v = 0 + (3 << 2) + (litSize << 4); o[0] = (uint8_t)v; o[1] = (uint8_t)(v >> 8); o[2] = (uint8_t)(v >> 16); }
+                S.litSectionSize = flSize + litSize;
+            }
+            for (uint32_t k = tid; k < litSize; k += kEntThreads) o[flSize + k] = lit[k];
+        } else if (litMode == 1) {      // ZSTD_compressRleLiteralsBlock (:49)
+            if (tid == 0) {
+                uint32_t const flSize = 1 + (litSize > 31) + (litSize > 4095);
+                uint8_t* o = dst + payload;
+                if (flSize == 1) o[0] = (uint8_t)(1 + (litSize << 3));
+                else if (flSize == 2) { uint32_t const v = 1 + (1 << 2) + (litSize << 4); o[0] = (uint8_t)v; o[1] = (uint8_t)(v >> 8); }
+                else { uint32_t const v = 1 + (3 << 2) + (litSize << 4); o[0] = (uint8_t)v; o[1] = (uint8_t)(v >> 8); o[2] = (uint8_t)(v >> 16); }
+                o[flSize] = lit[0];
+                S.litSectionSize = flSize + 1;
+            }
+        }
+        __syncthreads();
+        uint32_t op = payload + S.litSectionSize;
+        // ---- 3. sequences section (ZstdCompress.cs:3285-3352) ----
+        if (tid == 0) {
+            uint8_t* o = dst + op;
+            if (nbSeq < 128) { o[0] = (uint8_t)nbSeq; S.seqHdrSize = 1; }
+            else if (nbSeq < kLongNbSeq) { o[0] = (uint8_t)((nbSeq >> 8) + 0x80); o[1] = (uint8_t)nbSeq; S.seqHdrSize = 2; }
+            else { o[0] = 0xFF; uint32_t const v = nbSeq - kLongNbSeq; o[1] = (uint8_t)v; o[2] = (uint8_t)(v >> 8); S.seqHdrSize = 3; }
+        }
+        __syncthreads();
+        op += S.seqHdrSize;
+        bool zeroed = false;
+        if (nbSeq > 0) {
+            uint32_t const strategy = it.strategy;
+            uint32_t const seqHead = op; op += 1;
+            uint32_t lastCountSize = 0; uint32_t types[3];
+            // three statistics passes, in the reference's order LL, OF, ML (ZSTD_buildSequencesStatistics :3127)
+            for (int k = 0; k < 3; k++) {
+                uint32_t const maxCode = k == 0 ? kMaxLL : (k == 1 ? kMaxOff : kMaxML);
+                for (uint32_t q = tid; q < 64; q += kEntThreads) S.count[q] = 0;
+                __syncthreads();
+                for (uint32_t n = tid; n < nbSeq; n += kEntThreads) {
+                    uint32_t const code = k == 0 ? ll_code(aLL[n]) : (k == 1 ? highbit32(aOF[n]) : ml_code(aML[n]));
+                    atomicAdd(&S.count[code], 1u);
+                }
+                __syncthreads();
+                if (tid == 0) {
+                    uint32_t max = maxCode; while (!S.count[max]) max--;
+                    uint32_t mostFrequent = 0; for (uint32_t s = 0; s <= max; s++) if (S.count[s] > mostFrequent) mostFrequent = S.count[s];
+                    uint32_t const defLog = k == 1 ? kOFDefaultNormLog : kLLDefaultNormLog;
+                    bool const defAllowed = k == 1 ? (max <= (uint32_t)kDefaultMaxOff) : true;
+                    uint32_t const type = select_encoding_type(mostFrequent, nbSeq, defLog, defAllowed, strategy);
+                    uint32_t const lastCode = k == 0 ? ll_code(aLL[nbSeq - 1]) : (k == 1 ? highbit32(aOF[nbSeq - 1]) : ml_code(aML[nbSeq - 1]));
+                    uint32_t countSize = 0;
+                    FseCTable& ct = S.ct[k];
+                    uint8_t* o = dst + op;
+                    if (type == 1) {            // set_rle: FSE_buildCTable_rle (FseCompress.cs:706)
+                        ct.tableLog = 0; ct.stateTable[0] = 0; ct.stateTable[1] = 0; ct.tt[max].deltaNbBits = 0; ct.tt[max].deltaFindState = 0;
+                        // the reference writes codeTable[0], the code of the FIRST sequence (all codes are equal here)
+                        o[0] = (uint8_t)(k == 0 ? ll_code(aLL[0]) : (k == 1 ? highbit32(aOF[0]) : ml_code(aML[0])));
+                        countSize = 1;
+                    } else if (type == 0) {     // set_basic
+                        uint32_t const dmax = k == 0 ? kMaxLL : (k == 1 ? kDefaultMaxOff : kMaxML);
+                        for (uint32_t s = 0; s <= dmax; s++) S.norm[s] = k == 0 ? c_LL_defaultNorm[s] : (k == 1 ? c_OF_defaultNorm[s] : c_ML_defaultNorm[s]);
+                        fse_build_ctable(ct, S, S.norm, dmax, defLog);
+                    } else {                    // set_compressed: ZSTD_buildCTable (ZstdCompressSequences.cs:471)
+                        uint32_t const FSELog = k == 1 ? kOffFSELog : kLLFSELog;
+                        uint32_t nbSeq_1 = nbSeq;
+                        uint32_t const tableLog = fse_optimal_table_log(FSELog, nbSeq, max, 2);
+                        if (S.count[lastCode] > 1) { S.count[lastCode]--; nbSeq_1--; }
+                        fse_normalize_count(S.norm, tableLog, S.count, nbSeq_1, max, nbSeq_1 >= 2048);
+                        countSize = fse_write_ncount(S.hdr, S.norm, max, tableLog);
+                        for (uint32_t q = 0; q < countSize; q++) o[q] = S.hdr[q];
+                        fse_build_ctable(ct, S, S.norm, max, tableLog);
+                        lastCountSize = countSize;
+                    }
+                    S.scanA[0] = countSize; S.scanA[1] = type; S.scanA[2] = lastCountSize;
+                }
+                __syncthreads();
+                op += S.scanA[0]; types[k] = S.scanA[1]; if (S.scanA[1] == 2) lastCountSize = S.scanA[2];
+                __syncthreads();
+            }
+            if (tid == 0) dst[seqHead] = (uint8_t)((types[0] << 6) + (types[1] << 4) + (types[2] << 2));
+            // ---- 4. FSE state chains: three lanes walk the sequences last -> first (ZSTD_encodeSequences_body :585) ----
+            uint64_t* const sb = p.stateBits + (size_t)item * kEncSeqCap;
+            if (tid < 96 && (tid & 31) == 0) {
+                int const k = tid >> 5;    // 0 LL, 1 OF, 2 ML
+                const FseCTable& ct = S.ct[k];
+                auto code_at = [&](uint32_t n) { return k == 0 ? ll_code(aLL[n]) : (k == 1 ? highbit32(aOF[n]) : ml_code(aML[n])); };
+                uint32_t state = fse_init_state(ct, code_at(nbSeq - 1));
+                // stateBits layout per sequence: bits [13k, 13k+13) = value(9) | count(4)<<9 ; written with 3 separate arrays to avoid races
+                uint16_t* const out16 = (uint16_t*)sb + k;                          // 4 x u16 per sequence
+                out16[(size_t)(nbSeq - 1) * 4] = 0;
+                for (uint32_t n = nbSeq - 1; n-- > 0; ) {
+                    SymbolTT const tt = ct.tt[code_at(n)];
+                    uint32_t const nb = (state + tt.deltaNbBits) >> 16;
+                    out16[(size_t)n * 4] = (uint16_t)((state & ((1u << nb) - 1)) | (nb << 12));
+                    state = ct.stateTable[(int32_t)(state >> nb) + tt.deltaFindState];
+                }
+                S.scanB[k] = state;     // final states, flushed after the last packet
+            }
+            __syncthreads();
+            // ---- 5. bitstream scatter ----
+            // order inside sequence n's packet (low -> high): [OF state bits][ML state bits][LL state bits] (none for n = nbSeq-1),
+            // then LL extra, ML extra, OF extra.  Packets are laid out n = nbSeq-1 first.
+            uint32_t totalBits = 0;
+            {
+                // first pass: total length, so that the area can be zeroed before scattering
+                uint32_t mine = 0;
+                for (uint32_t n = tid; n < nbSeq; n += kEntThreads) {
+                    uint32_t const llc = ll_code(aLL[n]), mlc = ml_code(aML[n]), ofc = highbit32(aOF[n]);
+                    const uint16_t* s16 = (const uint16_t*)(sb + n);
+                    mine += c_LL_bits[llc] + c_ML_bits[mlc] + ofc + (s16[0] >> 12) + (s16[1] >> 12) + (s16[2] >> 12);
+                }
+                uint32_t tot; ent_scan_excl(mine, S.scanA, &tot);
+                totalBits = tot + S.ct[0].tableLog + S.ct[1].tableLog + S.ct[2].tableLog;
+            }
+            uint32_t const streamSize = (totalBits + 1 + 7) / 8;             // BIT_closeCStream: 1-bit end mark
+            for (uint32_t k = tid; k < streamSize; k += kEntThreads) dst[op + k] = 0;
+            __syncthreads();
+            zeroed = true;
+            {
+                uint64_t const bit0 = (uint64_t)op * 8;
+                uint32_t carry = 0;
+                for (uint32_t hi = nbSeq; hi > 0; ) {
+                    uint32_t const tile = min(hi, (uint32_t)kEntThreads);
+                    uint32_t const lo = hi - tile;
+                    bool const active = tid < tile;
+                    uint32_t const n = hi - 1 - tid;                           // descending
+                    uint32_t llv = 0, mlv = 0, ofv = 0, llb = 0, mlb = 0, ofb = 0, sL = 0, sM = 0, sO = 0;
+                    if (active) {
+                        llv = aLL[n]; mlv = aML[n]; ofv = aOF[n];
+                        llb = c_LL_bits[ll_code(llv)]; mlb = c_ML_bits[ml_code(mlv)]; ofb = highbit32(ofv);
+                        const uint16_t* s16 = (const uint16_t*)(sb + n);
+                        sL = s16[0]; sO = s16[1]; sM = s16[2];
+                    }
+                    uint32_t const len = active ? (llb + mlb + ofb + (sL >> 12) + (sM >> 12) + (sO >> 12)) : 0;
+                    uint32_t tot;
+                    uint32_t const off = ent_scan_excl(len, S.scanA, &tot);
+                    if (active) {
+                        uint64_t pos = bit0 + carry + off;
+                        put_bits(dstW, pos, sO & 0xFFF, sO >> 12); pos += sO >> 12;
+                        put_bits(dstW, pos, sM & 0xFFF, sM >> 12); pos += sM >> 12;
+                        put_bits(dstW, pos, sL & 0xFFF, sL >> 12); pos += sL >> 12;
+                        put_bits(dstW, pos, llv, llb); pos += llb;
+                        put_bits(dstW, pos, mlv, mlb); pos += mlb;
+                        put_bits(dstW, pos, ofv, ofb);
+                    }
+                    carry += tot; hi = lo;
+                }
+                if (tid == 0) {     // FSE_flushCState x3 in the order ML, OF, LL, then the end mark (:694-700)
+                    uint64_t pos = bit0 + carry;
+                    put_bits(dstW, pos, S.scanB[2], S.ct[2].tableLog); pos += S.ct[2].tableLog;
+                    put_bits(dstW, pos, S.scanB[1], S.ct[1].tableLog); pos += S.ct[1].tableLog;
+                    put_bits(dstW, pos, S.scanB[0], S.ct[0].tableLog); pos += S.ct[0].tableLog;
+                    put_bits(dstW, pos, 1, 1);
+                }
+            }
+            op += streamSize;
+            if (lastCountSize && (lastCountSize + streamSize) < 4) raw = true;          // ZstdCompress.cs:3346-3350
+        }
+        (void)zeroed;
+        __syncthreads();
+        cSize = op - payload;
+        // ZSTD_entropyCompressSeqStore gate (:3381-3389) and capacity of the slot
+        if (cSize >= srcSize - ((srcSize >> 6) + 2)) raw = true;
+    }
+    __syncthreads();
+    if (raw) {          // ZSTD_noCompressBlock (ZstdCompressInternal.cs:102)
+        for (uint32_t k = tid; k < srcSize; k += kEntThreads) dst[payload + k] = src[k];
+        if (tid == 0) {
+            uint32_t const h = 1 + (0u << 1) + (srcSize << 3);
+            blk[0] = (uint8_t)h; blk[1] = (uint8_t)(h >> 8); blk[2] = (uint8_t)(h >> 16);
+            p.results[item] = payload + srcSize;
+        }
+    } else if (tid == 0) {
+        uint32_t const h = 1 + (2u << 1) + (cSize << 3);
+        blk[0] = (uint8_t)h; blk[1] = (uint8_t)(h >> 8); blk[2] = (uint8_t)(h >> 16);
+        p.results[item] = payload + cSize;
+    }
+}
+
+__global__ void enc_compact_kernel(const uint8_t* src, const uint64_t* srcOff, const uint64_t* sizes, const uint64_t* dstOff, uint8_t* dst)
+{
+    uint32_t const i = blockIdx.x;
+    uint64_t const n = sizes[i];
+    const uint8_t* s = src + srcOff[i]; uint8_t* d = dst + dstOff[i];
+    for (uint64_t k = threadIdx.x; k < n; k += blockDim.x) d[k] = s[k];
+}
+
+// ------------------------------------------------------------------------------------------------------------
+//  Host driver
+// ------------------------------------------------------------------------------------------------------------
+struct DBuf { void* p = nullptr; size_t cap = 0;
+    bool ensure(size_t n) { if (n <= cap) return true; if (p) cudaFree(p); p = nullptr; cap = 0; size_t w = n + n / 8 + 256; if (cudaMalloc(&p, w) != cudaSuccess) { w = n + 256; if (cudaMalloc(&p, w) != cudaSuccess) { p = nullptr; return false; } } cap = w; return true; }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; } };
+struct HBuf { void* p = nullptr; size_t cap = 0;
+    bool ensure(size_t n) { if (n <= cap) return true; if (p) cudaFreeHost(p); p = nullptr; cap = 0; size_t w = n + n / 8 + 256; if (cudaHostAlloc(&p, w, cudaHostAllocDefault) != cudaSuccess) { p = nullptr; return false; } cap = w; return true; }
+    void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; } };
+
+struct EncArenaImpl {
+    DBuf items, tables, seqLL, seqML, seqOF, lit, stateBits, results, compact, cSrcOff, cSizes, cDstOff;
+    HBuf hItems, hResults, hC;
+};
+static thread_local std::string t_encErr;
+const char* enc_last_error() { return t_encErr.c_str(); }
+void EncArena::release()
+{
+    if (!impl) return;
+    DBuf* d[] = {&impl->items, &impl->tables, &impl->seqLL, &impl->seqML, &impl->seqOF, &impl->lit, &impl->stateBits, &impl->results, &impl->compact, &impl->cSrcOff, &impl->cSizes, &impl->cDstOff};
+    for (auto* b : d) b->release();
+    impl->hItems.release(); impl->hResults.release(); impl->hC.release();
+    delete impl; impl = nullptr;
+}
+const uint8_t* EncArena::compactBuf() const { return impl ? (const uint8_t*)impl->compact.p : nullptr; }
+
+#define ENC_CUDA(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { t_encErr = std::string(#call) + ": " + cudaGetErrorString(e_); fprintf(stderr, "[zstdb200] CUDA failure: %s\n", t_encErr.c_str()); return false; } } while (0)
+
+constexpr size_t kEncMaxItemsPerPass = 8192;
+
+bool enc_compress_device(EncArena& A, cudaStream_t stream, cudaEvent_t* ev, size_t n, int level,
+                         const uint8_t* d_src, const uint64_t* srcOff, const size_t* srcSize,
+                         uint8_t* d_dst, const uint64_t* dstOff, const size_t* dstCap, size_t* result,
+                         float* timings, unsigned* launches)
+{
+    if (!A.impl) A.impl = new EncArenaImpl();
+    EncArenaImpl& I = *A.impl;
+    float msAll = 0, msMatch = 0, msEnt = 0;
+    for (size_t base = 0; base < n; base += kEncMaxItemsPerPass) {
+        size_t const m = std::min(kEncMaxItemsPerPass, n - base);
+        if (!I.hItems.ensure(m * sizeof(EncItem)) || !I.items.ensure(m * sizeof(EncItem)) || !I.results.ensure(m * 8) || !I.hResults.ensure(m * 8)) { t_encErr = "out of memory (items)"; return false; }
+        EncItem* hi = (EncItem*)I.hItems.p;
+        size_t tableEntries = 0;
+        for (size_t i = 0; i < m; i++) {
+            size_t const ss = srcSize[base + i];
+            EncItem& e = hi[i];
+            memset(&e, 0, sizeof(e));
+            e.srcOff = srcOff[base + i]; e.dstOff = dstOff[base + i];
+            e.srcSize = (uint32_t)std::min<size_t>(ss, 0xFFFFFFF0u); e.dstCap = (uint32_t)std::min<size_t>(dstCap[base + i], 0xFFFFFFF0u);
+            CParams const c = get_cparams(level, std::min<size_t>(ss, kBlockSizeMax));
+            e.windowLog = c.windowLog; e.hashLog = c.hashLog; e.chainLog = c.chainLog; e.minMatch = c.minMatch; e.strategy = c.strategy;
+            e.tableOff = (uint32_t)tableEntries;
+            tableEntries += ((size_t)1 << c.hashLog) + (c.strategy == 2 ? ((size_t)1 << c.chainLog) : 0);
+        }
+        if (tableEntries >= 0xFFFFFFFFull) { t_encErr = "hash-table arena exceeds 32-bit indexing"; return false; }
+        if (!I.tables.ensure(tableEntries * 4) || !I.seqLL.ensure(m * (size_t)kEncSeqCap * 4) || !I.seqML.ensure(m * (size_t)kEncSeqCap * 4) ||
+            !I.seqOF.ensure(m * (size_t)kEncSeqCap * 4) || !I.lit.ensure(m * (size_t)kEncLitStride) || !I.stateBits.ensure(m * (size_t)kEncSeqCap * 8)) { t_encErr = "out of memory (arena)"; return false; }
+        ENC_CUDA(cudaMemcpyAsync(I.items.p, hi, m * sizeof(EncItem), cudaMemcpyHostToDevice, stream));
+        ENC_CUDA(cudaEventRecord(ev[14], stream));
+        ENC_CUDA(cudaMemsetAsync(I.tables.p, 0, tableEntries * 4, stream));      // tables are zeroed per frame (ZstdCompress.cs:2472,2481)
+        EncPass p;
+        p.items = (EncItem*)I.items.p; p.nItems = (uint32_t)m; p.src = d_src; p.dst = d_dst; p.tables = (uint32_t*)I.tables.p;
+        p.seqLL = (uint32_t*)I.seqLL.p; p.seqML = (uint32_t*)I.seqML.p; p.seqOF = (uint32_t*)I.seqOF.p; p.litBuf = (uint8_t*)I.lit.p;
+        p.stateBits = (uint64_t*)I.stateBits.p; p.results = (uint64_t*)I.results.p;
+        enc_match_kernel<<<(unsigned)((m + 31) / 32), 32, 0, stream>>>(p);
+        ENC_CUDA(cudaEventRecord(ev[15], stream));
+        enc_entropy_kernel<<<(unsigned)m, kEntThreads, 0, stream>>>(p);
+        ENC_CUDA(cudaEventRecord(ev[16], stream));
+        *launches += 3;
+        ENC_CUDA(cudaMemcpyAsync(I.hResults.p, I.results.p, m * 8, cudaMemcpyDeviceToHost, stream));
+        ENC_CUDA(cudaStreamSynchronize(stream));
+        ENC_CUDA(cudaGetLastError());
+        float t;
+        cudaEventElapsedTime(&t, ev[14], ev[16]); msAll += t;
+        cudaEventElapsedTime(&t, ev[14], ev[15]); msMatch += t;
+        cudaEventElapsedTime(&t, ev[15], ev[16]); msEnt += t;
+        const uint64_t* hr = (const uint64_t*)I.hResults.p;
+        for (size_t i = 0; i < m; i++) {
+            size_t const ss = srcSize[base + i];
+            if (ss > kBlockSizeMax) result[base + i] = (size_t)make_error(kSrcSizeWrong);   // multi-block frames: DESIGN.md "next" (f.2)
+            else result[base + i] = (size_t)hr[i];
+        }
+    }
+    timings[1] = msAll; timings[8] = msMatch; timings[9] = msEnt;
+    return true;
+}
+
+bool enc_compact_device(EncArena& A, cudaStream_t stream, size_t n, const uint8_t* d_dst, const uint64_t* dstOff,
+                        const size_t* sizes, const uint64_t* cOff, size_t total, unsigned* launches)
+{
+    if (!A.impl) A.impl = new EncArenaImpl();
+    EncArenaImpl& I = *A.impl;
+    if (!I.compact.ensure(total + 16) || !I.cSrcOff.ensure(n * 8) || !I.cSizes.ensure(n * 8) || !I.cDstOff.ensure(n * 8) || !I.hC.ensure(n * 24)) { t_encErr = "out of memory (compact)"; return false; }
+    uint64_t* h = (uint64_t*)I.hC.p;
+    for (size_t i = 0; i < n; i++) { h[i] = dstOff[i]; h[n + i] = is_error(sizes[i]) ? 0 : sizes[i]; h[2 * n + i] = cOff[i]; }
+    ENC_CUDA(cudaMemcpyAsync(I.cSrcOff.p, h, n * 8, cudaMemcpyHostToDevice, stream));
+    ENC_CUDA(cudaMemcpyAsync(I.cSizes.p, h + n, n * 8, cudaMemcpyHostToDevice, stream));
+    ENC_CUDA(cudaMemcpyAsync(I.cDstOff.p, h + 2 * n, n * 8, cudaMemcpyHostToDevice, stream));
+    enc_compact_kernel<<<(unsigned)n, 256, 0, stream>>>(d_dst, (const uint64_t*)I.cSrcOff.p, (const uint64_t*)I.cSizes.p, (const uint64_t*)I.cDstOff.p, (uint8_t*)I.compact.p);
+    *launches += 1;
+    return true;
+}
+
+}  // namespace zb
