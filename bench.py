@@ -1,0 +1,479 @@
+#!/usr/bin/env python
+"""Benchmark of the hot path: batch decompress (and level-1 compress) of independent 128 KiB zstd frames.
+
+  python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path (one rank per GPU under torchrun)
+  python bench.py --impl reference --steps K --warmup W    # the reference's CPU algorithm (oracle port) on the host cores
+
+One JSON line on stdout (rank 0).  `value` = decompress GB/s of uncompressed bytes, whole job, frames resident in HBM
+(configs[1] of BASELINE.json: 1 GiB of 128 KiB level-1 frames per GPU, weak scaling); `e2e` = the same through the
+host-pointer C ABI (ZSTDB200_decompressBatch) with pinned HOST buffers, H2D and D2H inside the timed region;
+`compress_l1` carries the level-1 compress numbers of configs[2] (1 GiB Silesia-mix-like in 128 KiB chunks).
+A step = one pass of the pipeline over the rank's whole batch.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from concurrent.futures import ThreadPoolExecutor
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+from zstdsharp_b200 import datagen as dg  # noqa: E402
+from zstdsharp_b200.sharding import shard_bounds  # noqa: E402
+
+FRAME = dg.FRAME
+METRIC = "decompress & level-1 compress GB/s (128KB frames) at 1/2/4/8 B200 vs CPU"
+UNIQUE_FRAMES = 512          # 64 MiB of generated corpus, tiled up to the batch size (every frame is a genuine sample)
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+def measured_hbm_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index: int):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc:
+            time.sleep(0.15)
+            self.proc.terminate()
+        sm, smax, reasons = [], [], set()
+        for ln in self.lines:
+            parts = [x.strip() for x in ln.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0])); smax.append(float(parts[1]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), parts[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        busy = [s for s in sm if s > 0]
+        return {"sm_mhz": float(np.median(busy)) if busy else None, "sm_max_mhz": max(smax) if smax else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------------------------------------------
+#  CPU side (oracle port of the reference algorithm): --impl reference and the cpu_baseline leg
+# ----------------------------------------------------------------------------------------------------------------
+def cpu_frames(level: int = 1, nframes: int = UNIQUE_FRAMES, workload: str = "text"):
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from _oracle import oracle
+    o = oracle()
+    data = dg.WORKLOADS[workload](nframes * FRAME)
+    chunks = [data[i * FRAME:(i + 1) * FRAME] for i in range(nframes)]
+    threads = os.cpu_count() or 1
+    with ThreadPoolExecutor(threads) as ex:
+        frames = list(ex.map(lambda c: o.compress(c, level), chunks))
+    return o, chunks, frames, threads
+
+
+def cpu_decode_pass(o, frames, threads, seconds_min=0.0):
+    """Decompresses every frame once with `threads` workers (one context per call, as ZstdNetTests.cs:498-522).
+    Returns (bytes, seconds)."""
+    outs = [np.empty(FRAME, dtype=np.uint8) for _ in range(threads)]
+    bufs = [np.frombuffer(f, dtype=np.uint8) for f in frames]
+    lib = o.lib
+
+    ctxs = [lib.zo_createDCtx() for _ in range(threads)]     # one Decompressor per thread
+
+    def work(tid):
+        out = outs[tid]
+        n = 0
+        for i in range(tid, len(bufs), threads):
+            r = lib.zo_decompressDCtx(ctxs[tid], out.ctypes.data, FRAME, bufs[i].ctypes.data, bufs[i].size)
+            assert r == FRAME
+            n += r
+        return n
+    total = 0
+    with ThreadPoolExecutor(threads) as ex:
+        t0 = time.perf_counter()
+        while True:
+            total += sum(ex.map(work, range(threads)))
+            if time.perf_counter() - t0 >= seconds_min:
+                break
+        dt = time.perf_counter() - t0
+    for c in ctxs:
+        lib.zo_freeDCtx(c)
+    return total, dt
+
+
+def cpu_compress_pass(o, chunks, threads, level=1):
+    lib = o.lib
+    cap = lib.zo_compressBound(FRAME)
+    outs = [np.empty(cap, dtype=np.uint8) for _ in range(threads)]
+
+    ctxs = [lib.zo_createCCtx() for _ in range(threads)]     # one Compressor per thread
+
+    def work(tid):
+        n = 0
+        for i in range(tid, len(chunks), threads):
+            c = chunks[i]
+            r = lib.zo_compressCCtx(ctxs[tid], outs[tid].ctypes.data, cap, c.ctypes.data, c.size, level, 0)
+            assert r < (1 << 62)
+            n += c.size
+        return n
+    with ThreadPoolExecutor(threads) as ex:
+        list(ex.map(work, range(threads)))                   # warm-up pass
+        t0 = time.perf_counter()
+        total = sum(ex.map(work, range(threads)))
+        dt = time.perf_counter() - t0
+    for c in ctxs:
+        lib.zo_freeCCtx(c)
+    return total, dt
+
+
+def native_libzstd_decode_rate(frames, threads):
+    """Context only: upstream libzstd 1.5.5 (faster than the managed reference, README.md:44-58) on the same frames."""
+    try:
+        from _oracle import libzstd
+        z = libzstd().lib
+    except Exception:
+        return None
+    bufs = [np.frombuffer(f, dtype=np.uint8) for f in frames]
+    outs = [np.empty(FRAME, dtype=np.uint8) for _ in range(threads)]
+
+    def work(tid):
+        n = 0
+        for _ in range(4):
+            for i in range(tid, len(bufs), threads):
+                n += z.ZSTD_decompress(outs[tid].ctypes.data, FRAME, bufs[i].ctypes.data, bufs[i].size)
+        return n
+    t0 = time.perf_counter()
+    with ThreadPoolExecutor(threads) as ex:
+        total = sum(ex.map(work, range(threads)))
+    return total / (time.perf_counter() - t0) / 1e9
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    o, chunks, frames, threads = cpu_frames(1, UNIQUE_FRAMES, "text")
+    for _ in range(args.warmup):
+        cpu_decode_pass(o, frames, threads)
+    t0 = time.perf_counter()
+    total = 0
+    for _ in range(args.steps):
+        b, _ = cpu_decode_pass(o, frames, threads)
+        total += b
+    dt = time.perf_counter() - t0
+    val = total / dt / 1e9
+    cb, ct = cpu_compress_pass(o, [c for c in dg.silesia_mix(128 * FRAME).reshape(-1, FRAME)], threads, 1)
+    sample = f"{UNIQUE_FRAMES} text-like 128 KiB level-1 frames ({UNIQUE_FRAMES * FRAME >> 20} MiB) per step, {threads} threads"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": round(val, 4), "unit": "GB/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": round(1e3 * dt / args.steps, 3), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+        "config": {"workload": "batch decompress of 128 KiB level-1 frames (configs[1]), bounded CPU sample", "frames_per_step": UNIQUE_FRAMES,
+                   "frame_bytes": FRAME, "note": "reference algorithm = C port of ZstdSharp's zstd 1.5.1 code (oracle/); .NET is not available in this image"},
+        "cpu_baseline": {"value": round(val, 4), "unit": "GB/s", "cores": threads, "kind": "port", "sample": sample},
+        "compress_l1": {"value": round(cb / ct / 1e9, 4), "unit": "GB/s", "sample": "128 Silesia-mix-like chunks, level 1"},
+        "native_libzstd_1_5_5_decompress_GBps": native_libzstd_decode_rate(frames, threads),
+        "e2e": {"value": round(val, 4), "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------------------------------
+#  GPU side
+# ----------------------------------------------------------------------------------------------------------------
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    from zstdsharp_b200 import api, _native
+    lib = _native.lib
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if lib.ZSTDB200_deviceCount() == 0:
+        raise SystemExit("bench.py: no CUDA device; zstdsharp_b200 has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+
+    def max_over_ranks(x: float) -> float:
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(x: float) -> float:
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    nframes = args.frames                                    # per GPU (weak scaling)
+    # host scatter: the global frame list (world * nframes frames, index g -> unique frame g % UNIQUE) is cut into
+    # contiguous ranges balanced by byte weight; this rank materialises its own range only.
+    uniq = min(UNIQUE_FRAMES, nframes)
+    lo, hi = shard_bounds([FRAME] * (world * nframes), world)[rank]
+    my_ids = np.arange(lo, hi) % uniq
+    n = len(my_ids)
+
+    stream = torch.cuda.Stream()
+    comp, dec = api.Compressor(1), api.Decompressor()
+    # contexts allocate lazily: give them the torch stream so that torch events bracket their work
+    def use_stream(ctx):
+        r = lib.ZSTDB200_setStream(ctx.handle, ctypes.c_void_p(stream.cuda_stream))
+        assert r == 0, lib.ZSTDB200_lastErrorString()
+    use_stream(comp); use_stream(dec)
+
+    def dev_call(fn, ctx, nitems, *a):
+        rc = fn(ctx.handle, nitems, *a)
+        if rc != 0:
+            raise SystemExit(f"bench.py: batch call failed: {lib.ZSTD_getErrorName(rc)} / {lib.ZSTDB200_lastErrorString()}")
+
+    u64, st = ctypes.c_uint64, ctypes.c_size_t
+    results = {}
+    sampler = ClockSampler(local)
+
+    def timed_steps(step_fn, warmup, steps):
+        for _ in range(warmup):
+            step_fn()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        launches, slots = 0, np.zeros(_native.TIMING_SLOTS)
+        t0 = time.perf_counter()
+        with torch.cuda.stream(stream):
+            e0.record(stream)
+            for _ in range(steps):
+                l, s = step_fn()
+                launches += l; slots += s
+            e1.record(stream)
+        barrier()
+        wall = time.perf_counter() - t0
+        dev_ms = e0.elapsed_time(e1)
+        return max_over_ranks(dev_ms), max_over_ranks(wall * 1e3), launches, slots / steps
+
+    # ------------------------------------------------------------------ corpus + compressed frames (made by the GPU encoder)
+    t_prep = time.perf_counter()
+    text = dg.text_like(uniq * FRAME)
+    sil = dg.silesia_mix(uniq * FRAME)
+    d_text_u = torch.from_numpy(text).cuda()
+    d_sil_u = torch.from_numpy(sil).cuda()
+    bound = comp.GetCompressBound(FRAME)
+    slot = (bound + 15) & ~15
+
+    def compress_unique(d_u):
+        d_out = torch.empty(uniq * slot, dtype=torch.uint8, device="cuda")
+        so = (u64 * uniq)(*[i * FRAME for i in range(uniq)]); ss = (st * uniq)(*([FRAME] * uniq))
+        do = (u64 * uniq)(*[i * slot for i in range(uniq)]); dc = (st * uniq)(*([bound] * uniq)); res = (st * uniq)()
+        dev_call(lib.ZSTDB200_compressBatchDevice, comp, uniq, 1, d_u.data_ptr(), so, ss, d_out.data_ptr(), do, dc, res)
+        sizes = np.array(list(res), dtype=np.int64)
+        assert (sizes > 0).all() and (sizes <= bound).all(), "GPU compressor reported an error"
+        host = d_out.cpu().numpy()
+        return [host[i * slot:i * slot + sizes[i]].copy() for i in range(uniq)]
+
+    frames_u = compress_unique(d_text_u)
+    csz_u = np.array([f.size for f in frames_u], dtype=np.int64)
+    # decode batch for this rank: compressed frames back to back (contiguous => one DMA in the e2e path)
+    csz = csz_u[my_ids]
+    coff = np.concatenate([[0], np.cumsum(csz)[:-1]]).astype(np.int64)
+    ctotal = int(csz.sum())
+    h_comp = torch.empty(ctotal + 64, dtype=torch.uint8).pin_memory()
+    hc = h_comp.numpy()
+    uoff = np.concatenate([[0], np.cumsum(csz_u)[:-1]])
+    ublob = np.concatenate(frames_u)
+    for k in range(0, n, uniq):                               # tile the unique blob
+        m = min(uniq, n - k)
+        if np.array_equal(my_ids[k:k + m], np.arange(m)):
+            e = int(uoff[m - 1] + csz_u[m - 1]); hc[int(coff[k]):int(coff[k]) + e] = ublob[:e]
+        else:
+            for j in range(m):
+                hc[int(coff[k + j]):int(coff[k + j]) + int(csz[k + j])] = frames_u[int(my_ids[k + j])]
+    d_comp = h_comp.cuda()
+    d_out = torch.empty(n * FRAME, dtype=torch.uint8, device="cuda")
+    log(f"[rank {rank}] prepared {n} frames, {ctotal / 1e6:.1f} MB compressed (ratio {n * FRAME / ctotal:.2f}) in {time.perf_counter() - t_prep:.1f}s")
+
+    so = (u64 * n)(*coff.tolist()); ss = (st * n)(*csz.tolist())
+    do = (u64 * n)(*[i * FRAME for i in range(n)]); dc = (st * n)(*([FRAME] * n)); res = (st * n)()
+
+    def dec_step():
+        dev_call(lib.ZSTDB200_decompressBatchDevice, dec, n, d_comp.data_ptr(), so, ss, d_out.data_ptr(), do, dc, res)
+        return dec.launch_count(), np.array(dec.timings())
+
+    sampler.start()
+    dev_ms, wall_ms, launches, slots = timed_steps(dec_step, args.warmup, args.steps)
+    clocks = sampler.stop()
+    assert all(r == FRAME for r in res), "a frame failed to decode"
+    # size-independent property at full size: every output frame equals the chunk it was made from
+    ref = d_text_u.view(uniq, FRAME)[torch.from_numpy(my_ids).cuda()]
+    assert torch.equal(d_out.view(n, FRAME), ref), "decoded batch differs from the source corpus"
+    del ref
+    total_u = sum_over_ranks(float(n * FRAME))
+    total_c = sum_over_ranks(float(ctotal))
+    dec_gbps = total_u * args.steps / (dev_ms * 1e-3) / 1e9
+
+    # dominant kernel and its roofline (algorithmic bytes per launch = sum(U_i + C_i))
+    names = {3: "dec_scan", 4: "dec_setup", 5: "dec_huf", 6: "dec_seq", 7: "dec_exec"}
+    kern_ms = {names[k]: float(slots[k]) for k in names}
+    top = max(kern_ms, key=kern_ms.get)
+    peak, peak_src = measured_hbm_peak()
+    algo_bytes = n * FRAME + ctotal
+    achieved = algo_bytes / (kern_ms[top] * 1e-3) / 1e9 if kern_ms[top] > 0 else 0.0
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tpath):
+        try:
+            traffic = json.load(open(tpath)).get(top)
+        except Exception:
+            traffic = None
+    roofline = {"kernel": top, "bound": "hbm", "achieved": round(achieved, 2), "peak": peak, "peak_source": peak_src, "unit": "GB/s",
+                "frac": round(achieved / peak, 5), "traffic": traffic, "algorithmic_bytes_per_launch": algo_bytes,
+                "kernel_ms": {k: round(v, 4) for k, v in kern_ms.items()},
+                "pipeline_frac": round((algo_bytes * world / (dev_ms * 1e-3 / args.steps) / 1e9) / (peak * world), 5)}
+
+    # ------------------------------------------------------------------ e2e decompress: host-pointer C ABI, pinned buffers
+    h_out = torch.empty(n * FRAME, dtype=torch.uint8).pin_memory()
+    vp = ctypes.c_void_p
+    base_c, base_o = h_comp.data_ptr(), h_out.data_ptr()
+    sp = (vp * n)(*[base_c + int(o) for o in coff]); dp = (vp * n)(*[base_o + i * FRAME for i in range(n)])
+
+    def e2e_dec_step():
+        dev_call(lib.ZSTDB200_decompressBatch, dec, n, sp, ss, dp, dc, res)
+        return dec.launch_count(), np.array(dec.timings())
+    e2e_steps = max(1, min(args.steps, 5))
+    _, e2e_wall_ms, _, e2e_slots = timed_steps(e2e_dec_step, min(args.warmup, 2), e2e_steps)
+    assert all(r == FRAME for r in res)
+    assert np.array_equal(h_out.numpy()[:FRAME], text[int(my_ids[0]) * FRAME:(int(my_ids[0]) + 1) * FRAME])
+    e2e_gbps = total_u * e2e_steps / (e2e_wall_ms * 1e-3) / 1e9
+    e2e = {"value": round(e2e_gbps, 3), "unit": "GB/s", "h2d_bytes_per_step": int(total_c), "d2h_bytes_per_step": int(total_u),
+           "ms_per_step": round(e2e_wall_ms / e2e_steps, 3), "api": "ZSTDB200_decompressBatch (host pointers, pinned, contiguous)",
+           "phase_ms": {"h2d": round(float(e2e_slots[0]), 3), "kernels": round(float(e2e_slots[1]), 3), "d2h": round(float(e2e_slots[2]), 3)}}
+    del h_out
+
+    # ------------------------------------------------------------------ level-1 compress (configs[2])
+    compress = None
+    if not args.skip_compress:
+        d_sil = d_sil_u.view(uniq, FRAME)[torch.from_numpy(my_ids).cuda()].contiguous().view(-1)
+        d_cout = torch.empty(n * slot, dtype=torch.uint8, device="cuda")
+        cso = (u64 * n)(*[i * FRAME for i in range(n)]); css = (st * n)(*([FRAME] * n))
+        cdo = (u64 * n)(*[i * slot for i in range(n)]); cdc = (st * n)(*([bound] * n)); cres = (st * n)()
+
+        def comp_step():
+            dev_call(lib.ZSTDB200_compressBatchDevice, comp, n, 1, d_sil.data_ptr(), cso, css, d_cout.data_ptr(), cdo, cdc, cres)
+            return comp.launch_count(), np.array(comp.timings())
+        csteps = max(1, min(args.steps, 3))
+        c_dev_ms, _, c_launch, c_slots = timed_steps(comp_step, min(args.warmup, 1), csteps)
+        csizes = np.array(list(cres), dtype=np.int64)
+        assert (csizes > 0).all() and (csizes <= bound).all()
+        # round trip of the compressed batch through the GPU decoder (encode -> decode property at full size)
+        rdo = (u64 * n)(*[i * FRAME for i in range(n)])
+        dev_call(lib.ZSTDB200_decompressBatchDevice, dec, n, d_cout.data_ptr(), cdo, (st * n)(*csizes.tolist()), d_out.data_ptr(), rdo, dc, res)
+        assert all(r == FRAME for r in res) and torch.equal(d_out, d_sil), "compress -> decompress round trip failed"
+        c_total_c = sum_over_ranks(float(csizes.sum()))
+        c_gbps = total_u * csteps / (c_dev_ms * 1e-3) / 1e9
+        c_algo = n * FRAME + int(csizes.sum())
+        compress = {"value": round(c_gbps, 3), "unit": "GB/s", "ms_per_step": round(c_dev_ms / csteps, 3), "steps": csteps,
+                    "workload": "batch compress 1 GiB Silesia-mix-like in 128 KiB chunks, level 1 (configs[2]), byte-identical per chunk (tests/test_encode_gpu.py)",
+                    "ratio": round(n * FRAME * world / c_total_c, 4),
+                    "kernel_ms": {"enc_match": round(float(c_slots[8]), 3), "enc_entropy": round(float(c_slots[9]), 3)},
+                    "roofline_frac_top_kernel": round(c_algo / (max(float(c_slots[8]), float(c_slots[9])) * 1e-3) / 1e9 / peak, 5),
+                    "gpu_launches": int(c_launch)}
+        # e2e compress through the host-pointer ABI
+        h_in = torch.from_numpy(np.ascontiguousarray(sil)).pin_memory() if n <= uniq else d_sil.cpu().pin_memory()
+        h_cout = torch.empty(n * slot, dtype=torch.uint8).pin_memory()
+        csp = (vp * n)(*[h_in.data_ptr() + i * FRAME for i in range(n)]); cdp = (vp * n)(*[h_cout.data_ptr() + i * slot for i in range(n)])
+
+        def e2e_comp_step():
+            dev_call(lib.ZSTDB200_compressBatch, comp, n, 1, csp, css, cdp, cdc, cres)
+            return comp.launch_count(), np.array(comp.timings())
+        _, ce_wall_ms, _, _ = timed_steps(e2e_comp_step, 1, 2)
+        compress["e2e"] = {"value": round(total_u * 2 / (ce_wall_ms * 1e-3) / 1e9, 3), "unit": "GB/s",
+                           "h2d_bytes_per_step": int(total_u), "d2h_bytes_per_step": int(c_total_c)}
+        del h_in, h_cout
+
+    # ------------------------------------------------------------------ CPU baseline (rank 0, N == 1 only)
+    cpu = None
+    if rank == 0 and world == 1 and not args.skip_cpu:
+        o, chunks, frames, threads = cpu_frames(1, 256, "text")
+        cpu_decode_pass(o, frames, threads)
+        b, t = cpu_decode_pass(o, frames, threads, seconds_min=2.0)
+        cpu = {"value": round(b / t / 1e9, 4), "unit": "GB/s", "cores": threads, "kind": "port",
+               "sample": f"256 text-like 128 KiB level-1 frames decoded repeatedly for {t:.1f} s on {threads} threads (oracle port of the reference's C# code)",
+               "native_libzstd_1_5_5_GBps": native_libzstd_decode_rate(frames, threads)}
+        cb, ct = cpu_compress_pass(o, [c for c in dg.silesia_mix(128 * FRAME).reshape(-1, FRAME)], threads, 1)
+        cpu["compress_l1_GBps"] = round(cb / ct / 1e9, 4)
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": round(dec_gbps, 3), "unit": "GB/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": round(dev_ms / args.steps, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u8", "data": "synthetic",
+            "config": {"workload": "batch decompress 1 GiB of 128 KiB level-1 frames, bit-exact (BASELINE.json configs[1]); value = decompress, compress_l1 = configs[2]",
+                       "frames_per_gpu": nframes, "frame_bytes": FRAME, "corpus": f"text_like seed 0x{dg.SEED_TEXT:X}: {uniq} unique frames tiled to {nframes}",
+                       "compressed_bytes_per_gpu": ctotal, "parallelism": f"host scatter, {world} rank(s), no collective",
+                       "l2": "inputs larger than L2 (compressed batch %.0f MB + 1 GiB output per step)" % (ctotal / 1e6)},
+            "wall_ms_per_step": round(wall_ms / args.steps, 4),
+            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
+            "cpu_baseline": cpu, "compress_l1": compress,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--frames", type=int, default=8192, help="frames per GPU (8192 x 128 KiB = 1 GiB)")
+    ap.add_argument("--skip-compress", action="store_true")
+    ap.add_argument("--skip-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

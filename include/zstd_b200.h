@@ -96,6 +96,9 @@ ZSTDB200_API void     ZSTDB200_getLastTimings(const void* ctx, float* msOut /* [
 ZSTDB200_API unsigned ZSTDB200_getLastLaunchCount(const void* ctx);   /* kernels launched by the last batch call */
 ZSTDB200_API const char* ZSTDB200_lastErrorString(void);              /* thread-local description of the last library-level failure */
 ZSTDB200_API int      ZSTDB200_deviceCount(void);
+/* Issue all work of this context on a caller-owned CUDA stream (e.g. torch.cuda.current_stream().cuda_stream), so that
+ * the caller's events bracket it; NULL restores the context's own stream. ctx is a ZSTD_CCtx* or ZSTD_DCtx*. */
+ZSTDB200_API size_t   ZSTDB200_setStream(void* ctx, void* cudaStream);
 
 #ifdef __cplusplus
 }

@@ -34,6 +34,14 @@ size_t zo_compress(void* dst, size_t dstCapacity, const void* src, size_t srcSiz
 size_t zo_compress_advanced(void* dst, size_t dstCapacity, const void* src, size_t srcSize,
                             int level, int checksumFlag);
 
+/* Context-reusing variants (one context per thread, as the reference's tests do: ZstdNetTests.cs:498-522). */
+void*  zo_createCCtx(void);
+void   zo_freeCCtx(void* cctx);
+size_t zo_compressCCtx(void* cctx, void* dst, size_t dstCapacity, const void* src, size_t srcSize, int level, int checksumFlag);
+void*  zo_createDCtx(void);
+void   zo_freeDCtx(void* dctx);
+size_t zo_decompressDCtx(void* dctx, void* dst, size_t dstCapacity, const void* src, size_t srcSize);
+
 /* Multi-frame decompression incl. skippable frames and checksum verification. */
 size_t             zo_decompress(void* dst, size_t dstCapacity, const void* src, size_t srcSize);
 unsigned long long zo_decompressBound(const void* src, size_t srcSize);

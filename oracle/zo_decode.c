@@ -697,7 +697,11 @@ static size_t zo_execSequence(BYTE* op, BYTE* const oend, seq_t sequence, const 
     memmove(op, *litPtr, sequence.litLength);
     *litPtr += sequence.litLength;
     if (sequence.offset > (size_t)(oLitEnd - prefixStart)) return ERROR(corruption_detected);   /* no dictionary: virtualStart == prefixStart */
-    {   size_t i; BYTE* o = oLitEnd; for (i = 0; i < sequence.matchLength; i++) o[i] = match[i]; }
+    {   BYTE* o = oLitEnd; size_t const ml = sequence.matchLength;
+        if (sequence.offset >= ml) memcpy(o, match, ml);               /* no overlap */
+        else if (sequence.offset >= 8) { size_t i = 0; for (; i + 8 <= ml; i += 8) memcpy(o + i, match + i, 8); for (; i < ml; i++) o[i] = match[i]; }
+        else { size_t i; for (i = 0; i < ml; i++) o[i] = match[i]; }    /* byte-forward copy = ZSTD_overlapCopy8 + wildcopy result */
+    }
     return sequenceLength;
 }
 
@@ -954,35 +958,44 @@ static void zo_initDCtx(zo_DCtx* d)
 
 #include <stdlib.h>
 
+void* zo_createDCtx(void) { zo_DCtx* const d = (zo_DCtx*)malloc(sizeof(zo_DCtx)); if (d) zo_initDCtx(d); return d; }
+void zo_freeDCtx(void* ctx) { free(ctx); }
+
 /* ZstdDecompress.cs:1216 ZSTD_decompressMultiFrame (no dictionary) */
-size_t zo_decompress(void* dst, size_t dstCapacity, const void* src, size_t srcSize)
+size_t zo_decompressDCtx(void* ctx, void* dst, size_t dstCapacity, const void* src, size_t srcSize)
 {
-    void* const dststart = dst; int moreThan1Frame = 0; size_t ret;
-    zo_DCtx* const dctx = (zo_DCtx*)malloc(sizeof(zo_DCtx));
+    void* const dststart = dst; int moreThan1Frame = 0;
+    zo_DCtx* const dctx = (zo_DCtx*)ctx;
     if (!dctx) return ERROR(memory_allocation);
-    zo_initDCtx(dctx);
     while (srcSize >= 5) {
         {   U32 const magicNumber = MEM_read32(src);
             if ((magicNumber & ZSTD_MAGIC_SKIPPABLE_MASK) == ZSTD_MAGIC_SKIPPABLE_START) {
                 size_t const skippableSize = zo_readSkippableFrameSize(src, srcSize);
-                if (ERR_isError(skippableSize)) { free(dctx); return skippableSize; }
+                if (ERR_isError(skippableSize)) return skippableSize;
                 src = (const BYTE*)src + skippableSize; srcSize -= skippableSize;
                 continue;
         }   }
         zo_decompressBegin(dctx);
         dctx->prefixStart = (const BYTE*)dst;      /* ZSTD_checkContinuity, ZstdDecompressBlock.cs:3166 */
         {   size_t const res = zo_decompressFrame(dctx, dst, dstCapacity, &src, &srcSize, NULL, 0);
-            if ((zo_getErrorCode(res) == ZO_error_prefix_unknown) && (moreThan1Frame == 1)) { free(dctx); return ERROR(srcSize_wrong); }
-            if (ERR_isError(res)) { free(dctx); return res; }
+            if ((zo_getErrorCode(res) == ZO_error_prefix_unknown) && (moreThan1Frame == 1)) return ERROR(srcSize_wrong);
+            if (ERR_isError(res)) return res;
             if (res != 0) dst = (BYTE*)dst + res;
             dstCapacity -= res;
         }
         moreThan1Frame = 1;
     }
-    free(dctx);
     if (srcSize) return ERROR(srcSize_wrong);
-    ret = (size_t)((BYTE*)dst - (BYTE*)dststart);
-    return ret;
+    return (size_t)((BYTE*)dst - (BYTE*)dststart);
+}
+
+size_t zo_decompress(void* dst, size_t dstCapacity, const void* src, size_t srcSize)
+{
+    void* const d = zo_createDCtx(); size_t r;
+    if (!d) return ERROR(memory_allocation);
+    r = zo_decompressDCtx(d, dst, dstCapacity, src, srcSize);
+    zo_freeDCtx(d);
+    return r;
 }
 
 size_t zo_decode_first_block_stages(const void* src, size_t srcSize, uint8_t* lits, size_t litCapacity, size_t* litSize,

@@ -983,6 +983,11 @@ static size_t ZSTD_hashPtr(const void* p, U32 hBits, U32 mls)   /* ZstdCompressI
 static size_t ZSTD_count(const BYTE* pIn, const BYTE* pMatch, const BYTE* const pInLimit)   /* :264 : common-prefix length bounded by pInLimit */
 {
     const BYTE* const pStart = pIn;
+    while (pIn + 8 <= pInLimit) {
+        U64 const diff = MEM_read64(pMatch) ^ MEM_read64(pIn);
+        if (diff) return (size_t)(pIn - pStart) + ((size_t)__builtin_ctzll(diff) >> 3);
+        pIn += 8; pMatch += 8;
+    }
     while (pIn < pInLimit && *pMatch == *pIn) { pIn++; pMatch++; }
     return (size_t)(pIn - pStart);
 }
@@ -1302,25 +1307,37 @@ static size_t ZSTD_writeFrameHeader(void* dst, size_t dstCapacity, U32 windowLog
     return pos;
 }
 
+/* Context buffers are sized once for the largest supported geometry (ZSTD_resetCCtx_internal :2548 reuses the
+ * workspace the same way); the match-finder tables are re-zeroed for every frame (:2472, :2481-2484). */
+#define ZO_MAX_HASHLOG 17
+#define ZO_MAX_CHAINLOG 16
+static size_t zo_ctx_buffers(zo_CCtx* c)
+{
+    size_t const maxNbSeq = ZSTD_BLOCKSIZE_MAX / 3;
+    if (c->seqStore.sequencesStart) return 0;
+    c->seqStore.sequencesStart = (zo_seqDef*)malloc((maxNbSeq + 1) * sizeof(zo_seqDef));
+    c->seqStore.litStart = (BYTE*)malloc(ZSTD_BLOCKSIZE_MAX + 32);
+    c->seqStore.llCode = (BYTE*)malloc(maxNbSeq + 1); c->seqStore.mlCode = (BYTE*)malloc(maxNbSeq + 1); c->seqStore.ofCode = (BYTE*)malloc(maxNbSeq + 1);
+    c->ms.hashTable = (U32*)malloc(((size_t)1 << ZO_MAX_HASHLOG) * sizeof(U32));
+    c->ms.chainTable = (U32*)malloc(((size_t)1 << ZO_MAX_CHAINLOG) * sizeof(U32));
+    if (!c->seqStore.sequencesStart || !c->seqStore.litStart || !c->seqStore.llCode || !c->seqStore.mlCode || !c->seqStore.ofCode || !c->ms.hashTable || !c->ms.chainTable)
+        return ERROR(memory_allocation);
+    return 0;
+}
 static size_t zo_ctx_alloc(zo_CCtx* c, size_t srcSize, int level)
 {
-    memset(c, 0, sizeof(*c));
     if (zo_getCParams_internal(&c->cParams, level, srcSize)) return ERROR(parameter_unsupported);
+    CHECK_F(zo_ctx_buffers(c));
     {   /* ZSTD_resetCCtx_internal :2548 : windowSize = max(1, min(1<<wlog, pledged)); blockSize = min(128K, windowSize) */
         size_t const windowSize = (size_t)1 << c->cParams.windowLog;
         size_t ws = windowSize < srcSize ? windowSize : srcSize; if (ws < 1) ws = 1;
         c->blockSize = ws < ZSTD_BLOCKSIZE_MAX ? ws : ZSTD_BLOCKSIZE_MAX;
     }
     {   size_t const divider = (c->cParams.minMatch == 3) ? 3 : 4;
-        size_t const maxNbSeq = c->blockSize / divider;
-        c->seqStore.maxNbSeq = maxNbSeq; c->seqStore.maxNbLit = c->blockSize;
-        c->seqStore.sequencesStart = (zo_seqDef*)malloc((maxNbSeq + 1) * sizeof(zo_seqDef));
-        c->seqStore.litStart = (BYTE*)malloc(c->blockSize + 32);
-        c->seqStore.llCode = (BYTE*)malloc(maxNbSeq + 1); c->seqStore.mlCode = (BYTE*)malloc(maxNbSeq + 1); c->seqStore.ofCode = (BYTE*)malloc(maxNbSeq + 1);
-    }
+        c->seqStore.maxNbSeq = c->blockSize / divider; c->seqStore.maxNbLit = c->blockSize; }
     c->ms.cParams = c->cParams;
-    c->ms.hashTable = (U32*)calloc((size_t)1 << c->cParams.hashLog, sizeof(U32));                        /* tables zeroed per frame: :2472,:2481 */
-    c->ms.chainTable = (c->cParams.strategy == ZSTD_fast) ? NULL : (U32*)calloc((size_t)1 << c->cParams.chainLog, sizeof(U32));
+    memset(c->ms.hashTable, 0, ((size_t)1 << c->cParams.hashLog) * sizeof(U32));                         /* tables zeroed per frame: :2472,:2481 */
+    if (c->cParams.strategy != ZSTD_fast) memset(c->ms.chainTable, 0, ((size_t)1 << c->cParams.chainLog) * sizeof(U32));
     c->prevCBlock = &c->blockStateA; c->nextCBlock = &c->blockStateB;
     ZSTD_reset_compressedBlockState(c->prevCBlock);
     c->isFirstBlock = 1;
@@ -1332,39 +1349,48 @@ static void zo_ctx_free(zo_CCtx* c)
     free(c->ms.hashTable); free(c->ms.chainTable);
 }
 
-size_t zo_compress_advanced(void* dst, size_t dstCapacity, const void* src, size_t srcSize, int level, int checksumFlag)
+void* zo_createCCtx(void) { return calloc(1, sizeof(zo_CCtx)); }
+void zo_freeCCtx(void* ctx) { if (ctx) { zo_ctx_free((zo_CCtx*)ctx); free(ctx); } }
+
+size_t zo_compressCCtx(void* ctx, void* dst, size_t dstCapacity, const void* src, size_t srcSize, int level, int checksumFlag)
 {
-    zo_CCtx* const c = (zo_CCtx*)malloc(sizeof(zo_CCtx));
+    zo_CCtx* const c = (zo_CCtx*)ctx;
     BYTE* const ostart = (BYTE*)dst; BYTE* op = ostart; size_t result;
     if (!c) return ERROR(memory_allocation);
     result = zo_ctx_alloc(c, srcSize, level);
-    if (ERR_isError(result)) { free(c); return result; }
+    if (ERR_isError(result)) return result;
     /* window: byte 0 of src gets index 2 (ZSTD_window_init + first ZSTD_window_update, ZstdCompressInternal.cs:723-768) */
     c->ms.window.base = (const BYTE*)src - 2; c->ms.window.dictLimit = 2; c->ms.window.lowLimit = 2;
     /* ZSTD_compressContinue_internal :5013 */
     {   size_t const fhSize = ZSTD_writeFrameHeader(op, dstCapacity, c->cParams.windowLog, checksumFlag, srcSize);
-        if (ERR_isError(fhSize)) { result = fhSize; goto done; }
+        if (ERR_isError(fhSize)) return fhSize;
         op += fhSize; dstCapacity -= fhSize; }
     if (srcSize) {
         size_t const cSize = ZSTD_compress_frameChunk(c, op, dstCapacity, src, srcSize);
-        if (ERR_isError(cSize)) { result = cSize; goto done; }
+        if (ERR_isError(cSize)) return cSize;
         op += cSize; dstCapacity -= cSize;
     }
     /* ZSTD_writeEpilogue :5598 */
-    if (srcSize == 0 || op == ostart) {   /* stage != ending : write one empty last raw block */
+    if (srcSize == 0) {   /* stage != ending : write one empty last raw block */
         U32 const cBlockHeader24 = 1 + (((U32)bt_raw) << 1);
-        if (dstCapacity < 4) { result = ERROR(dstSize_tooSmall); goto done; }
+        if (dstCapacity < 4) return ERROR(dstSize_tooSmall);
         MEM_writeLE24(op, cBlockHeader24); op += ZSTD_blockHeaderSize; dstCapacity -= ZSTD_blockHeaderSize;
     }
     if (checksumFlag) {
         U32 const checksum = (U32)zo_xxh64(src, srcSize, 0);
-        if (dstCapacity < 4) { result = ERROR(dstSize_tooSmall); goto done; }
+        if (dstCapacity < 4) return ERROR(dstSize_tooSmall);
         MEM_write32(op, checksum); op += 4;
     }
-    result = (size_t)(op - ostart);
-done:
-    zo_ctx_free(c); free(c);
-    return result;
+    return (size_t)(op - ostart);
+}
+
+size_t zo_compress_advanced(void* dst, size_t dstCapacity, const void* src, size_t srcSize, int level, int checksumFlag)
+{
+    void* const c = zo_createCCtx(); size_t r;
+    if (!c) return ERROR(memory_allocation);
+    r = zo_compressCCtx(c, dst, dstCapacity, src, srcSize, level, checksumFlag);
+    zo_freeCCtx(c);
+    return r;
 }
 
 size_t zo_compress(void* dst, size_t dstCapacity, const void* src, size_t srcSize, int level)
@@ -1373,7 +1399,7 @@ size_t zo_compress(void* dst, size_t dstCapacity, const void* src, size_t srcSiz
 size_t zo_matchfinder_block(int level, const void* src, size_t srcSize, zo_seqDef* seqs, uint8_t* lits, size_t* litSize,
                             uint32_t longLength[2], uint32_t repOut[3])
 {
-    zo_CCtx* const c = (zo_CCtx*)malloc(sizeof(zo_CCtx)); size_t nbSeq;
+    zo_CCtx* const c = (zo_CCtx*)calloc(1, sizeof(zo_CCtx)); size_t nbSeq;
     if (!c) return ERROR(memory_allocation);
     if (srcSize > ZSTD_BLOCKSIZE_MAX) { free(c); return ERROR(srcSize_wrong); }
     {   size_t const r = zo_ctx_alloc(c, srcSize, level); if (ERR_isError(r)) { free(c); return r; } }

@@ -38,6 +38,12 @@ class Oracle:
         _sig(L.zo_compress, st, [vp, st, vp, st, ci])
         _sig(L.zo_compress_advanced, st, [vp, st, vp, st, ci, ci])
         _sig(L.zo_decompress, st, [vp, st, vp, st])
+        _sig(L.zo_createCCtx, vp, [])
+        _sig(L.zo_freeCCtx, None, [vp])
+        _sig(L.zo_compressCCtx, st, [vp, vp, st, vp, st, ci, ci])
+        _sig(L.zo_createDCtx, vp, [])
+        _sig(L.zo_freeDCtx, None, [vp])
+        _sig(L.zo_decompressDCtx, st, [vp, vp, st, vp, st])
         _sig(L.zo_compressBound, st, [st])
         _sig(L.zo_decompressBound, ctypes.c_ulonglong, [vp, st])
         _sig(L.zo_isError, ctypes.c_uint, [st])

@@ -1,0 +1,154 @@
+"""Pins the CPU oracle (oracle/, a plain-C restatement of the reference's C# code) -- runs without a GPU.
+
+What pins it:
+  * the reference tests' known answers: frame-header descriptor bytes (ZstdNetTests.cs:194-204), compressBound,
+    error codes (dst too small -> 70, ZstdNetTests.cs:214-258), empty / 1-byte / size-sweep round trips (:456-496);
+  * committed golden vectors (tests/golden/golden_vectors.json, produced by upstream libzstd 1.5.5);
+  * live differential runs against system libzstd 1.5.5 (the upstream C the reference translates at v1.5.1):
+    byte-identical frames at levels 1..3, identical decoded bytes for frames of any level.
+"""
+import hashlib
+import json
+import os
+
+import numpy as np
+import pytest
+
+from zstdsharp_b200 import datagen as dg
+
+from _oracle import oracle, libzstd
+
+FRAME = dg.FRAME
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def _golden_inputs():
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("make_golden", os.path.join(HERE, "golden", "make_golden.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return dict(mod.inputs())
+
+
+def test_golden_vectors():
+    o = oracle()
+    with open(os.path.join(HERE, "golden", "golden_vectors.json")) as f:
+        gold = json.load(f)
+    inputs = _golden_inputs()
+    assert len(gold["vectors"]) >= 45
+    for v in gold["vectors"]:
+        data = inputs[v["name"]]
+        assert hashlib.sha256(data).hexdigest() == v["src_sha256"], "generator drifted: " + v["name"]
+        whole = len(data) <= FRAME or "multiblock" in v["name"]
+        pieces = [data] if whole else [data[i:i + FRAME] for i in range(0, len(data), FRAME)]
+        frames = [o.compress(p, v["level"]) for p in pieces]
+        assert [len(f) for f in frames] == v["frame_sizes"], v["name"]
+        blob = b"".join(frames)
+        assert hashlib.sha256(blob).hexdigest() == v["frames_sha256"], v["name"]
+        if "frames_hex" in v:
+            assert blob.hex() == v["frames_hex"]
+        # and the decoder side of the oracle regenerates the input
+        assert b"".join(o.decompress(f, len(p)) for f, p in zip(frames, pieces)) == data
+
+
+@pytest.mark.parametrize("workload", ["text", "silesia", "incompressible", "literal_heavy", "literal_mix"])
+def test_encoder_byte_identical_to_libzstd(workload):
+    o, z = oracle(), libzstd()
+    data = dg.WORKLOADS[workload](8 * FRAME)
+    for i in range(0, data.size, FRAME):
+        c = data[i:i + FRAME]
+        for level in (1, 2, 3):
+            assert o.compress(c, level) == z.compress(c, level)
+
+
+def test_encoder_sizes_and_parameter_buckets():
+    o, z = oracle(), libzstd()
+    text = dg.text_like(2 * FRAME)
+    sizes = [0, 1, 2, 6, 7, 8, 63, 64, 255, 256, 257, 1023, 1024, 4096, 16383, 16384, 16385, 40959, 40960, 65535, 65536,
+             65791, 65792, 100001, 131071, 131072] + list(range(2, 100000, 9000))
+    for n in sizes:
+        for src in (dg.byte_ramp(n), text[:n]):
+            for level in (1, 3):
+                assert o.compress(src, level) == z.compress(src, level), (n, level)
+
+
+def test_multiblock_frames_match_libzstd():
+    """config[0]: 10 MB synthetic text, level 1 Wrap/Unwrap round trip on the CPU (multi-block: window, repcodes and
+    Huffman repeat mode carry across blocks)."""
+    o, z = oracle(), libzstd()
+    data = dg.text_like(80 * FRAME)[: 10 * 1000 * 1000]
+    for level in (1, 3):
+        f = o.compress(data, level)
+        assert f == z.compress(data, level)
+        assert o.decompress(f, data.size) == data.tobytes()
+
+
+def test_cparams_table():
+    o = oracle()
+    # Clevels.cs:490 / :510 (rows 1 and 3 of the <=128 KB table) and the <=16 KB table (:713-743)
+    assert o.cparams(1, FRAME) == (17, 12, 13, 1, 6, 0, 1)
+    assert o.cparams(3, FRAME) == (17, 15, 16, 2, 5, 0, 2)
+    assert o.cparams(0, FRAME) == o.cparams(3, FRAME)
+    assert o.cparams(1, 16384) == (14, 14, 15, 1, 5, 0, 1)
+    assert o.cparams(1, FRAME + 1)[0] == 18
+    assert o.lib.zo_compressBound(FRAME) == 131584
+
+
+def test_decoder_matches_libzstd_on_all_levels():
+    o, z = oracle(), libzstd()
+    data = dg.silesia_mix(6 * FRAME)
+    for lvl in (1, 2, 3, 4, 6, 9, 13, 19):
+        f = z.compress(data, lvl, checksum=lvl & 1)
+        assert o.decompress(f, data.size) == data.tobytes()
+        assert o.decompress_bound(f) == data.size
+
+
+def test_known_answers_and_errors():
+    o, z = oracle(), libzstd()
+    # frame header of a 128 KiB chunk: SURVEY.md Appendix B
+    f = o.compress(dg.text_like(FRAME), 1)
+    assert f[:9] == bytes.fromhex("28b52ffda000000200")
+    # small no-dictionary frame: single-segment descriptor (ZstdNetTests.cs:194-204 expects 0x60 for its 2-byte FCS sample)
+    assert o.compress(bytes(300), 1)[4] == 0x60
+    assert o.compress(b"", 1) == bytes.fromhex("28b52ffd2000010000")
+    # dst too small -> ZSTD_error_dstSize_tooSmall (70) on both sides (ZstdNetTests.cs:232-233, 411-412)
+    src = dg.text_like(FRAME)
+    r, _ = o.compress_raw(src, 1, cap=20)
+    assert o.error_code(r) == 70
+    r, _ = o.decompress_raw(f, 20)
+    assert o.error_code(r) == 70 == z.error_code(z.decompress_raw(f, 20)[0])
+    # unknown magic -> prefix_unknown (10); truncated -> srcSize_wrong (72); flipped FCS -> corruption_detected (20)
+    assert o.error_code(o.decompress_raw(bytes(range(1, 100)), 1000)[0]) == 10
+    assert o.error_code(o.decompress_raw(f[:100], FRAME)[0]) == 72 == z.error_code(z.decompress_raw(f[:100], FRAME)[0])
+    g = bytearray(f)
+    g[6] ^= 1
+    assert o.error_code(o.decompress_raw(bytes(g), FRAME * 2)[0]) == 20
+    # checksum flag adds exactly 4 bytes (ZstdNetTests.cs:41-73) and a wrong checksum is detected (22)
+    fc = o.compress(src, 1, checksum=1)
+    assert len(fc) == len(f) + 4 and fc == z.compress(src, 1, checksum=1)
+    bad = bytearray(fc)
+    bad[-1] ^= 0xFF
+    assert o.error_code(o.decompress_raw(bytes(bad), FRAME)[0]) == 22
+
+
+def test_corrupted_frames_agree_with_libzstd():
+    """Damaged payloads: the oracle's verdict class (ok / error) follows upstream, and accepted frames give the same bytes."""
+    o, z = oracle(), libzstd()
+    rng = np.random.default_rng(11)
+    f = o.compress(dg.text_like(FRAME), 1)
+    agree = 0
+    for _ in range(200):
+        g = bytearray(f)
+        pos = int(rng.integers(9, len(g)))
+        g[pos] ^= 1 << int(rng.integers(0, 8))
+        ro, outo = o.decompress_raw(bytes(g), FRAME)
+        rz, outz = z.decompress_raw(bytes(g), FRAME)
+        eo, ez = bool(o.lib.zo_isError(ro)), bool(z.lib.ZSTD_isError(rz))
+        if eo == ez:
+            agree += 1
+            if not eo:
+                assert ro == rz and outo[:ro].tobytes() == outz[:rz].tobytes()
+    # Verdicts may differ on a few damaged frames, and the reference (1.5.1 semantics) is the authority: e.g. the 1.5.1
+    # Huffman decoder insists on exact stream consumption (HufDecompress.cs:526-533) where 1.5.5's fast loop only
+    # checks the symbol count, so a flipped literal bit that keeps code lengths is accepted by 1.5.5, rejected by 1.5.1.
+    assert agree >= 170

@@ -21,7 +21,7 @@ EXPORTED_SYMBOLS = [
     "ZSTD_getErrorName", "ZSTD_versionNumber", "ZSTD_versionString",
     "ZSTDB200_decompressBatch", "ZSTDB200_compressBatch", "ZSTDB200_decompressBatchDevice",
     "ZSTDB200_compressBatchDevice", "ZSTDB200_getLastTimings", "ZSTDB200_getLastLaunchCount",
-    "ZSTDB200_lastErrorString", "ZSTDB200_deviceCount",
+    "ZSTDB200_lastErrorString", "ZSTDB200_deviceCount", "ZSTDB200_setStream",
 ]
 
 
@@ -75,6 +75,8 @@ def _load() -> ctypes.CDLL:
     lib.ZSTDB200_getLastLaunchCount.argtypes = [c_void_p]
     lib.ZSTDB200_lastErrorString.restype = ctypes.c_char_p
     lib.ZSTDB200_deviceCount.restype = c_int
+    lib.ZSTDB200_setStream.restype = c_size_t
+    lib.ZSTDB200_setStream.argtypes = [c_void_p, c_void_p]
     return lib
 
 

@@ -70,7 +70,8 @@ constexpr int kEvents = 24;
 struct Engine {
     int device = -1;
     bool ready = false;
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr;      // stream all work of this context is issued on
+    cudaStream_t ownStream = nullptr;   // created by the context; replaced by ZSTDB200_setStream
     cudaEvent_t ev[kEvents] = {};
     // decode arena
     DevBuf dItems, dInit, dHuf, dFse, dLit, dSeqLL, dSeqML, dSeqOF, dDefaultFse, dHufList, dSeqList, dCounters, dResults;
@@ -96,7 +97,8 @@ struct Engine {
         if (dev < 0 || dev >= count) { set_error("ZSTDB200_DEVICE out of range"); return false; }
         device = dev;
         ZB_CUDA(cudaSetDevice(device));
-        ZB_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+        ZB_CUDA(cudaStreamCreateWithFlags(&ownStream, cudaStreamNonBlocking));
+        if (!stream) stream = ownStream;
         for (int i = 0; i < kEvents; i++) ZB_CUDA(cudaEventCreate(&ev[i]));
         ready = true;
         return true;
@@ -108,7 +110,7 @@ struct Engine {
         PinBuf* h[] = {&hInit, &hCounters, &hResults, &hStage, &hEncInit};
         for (auto* b : h) b->release();
         enc.release();
-        if (ready) { for (int i = 0; i < kEvents; i++) cudaEventDestroy(ev[i]); cudaStreamDestroy(stream); }
+        if (ready) { for (int i = 0; i < kEvents; i++) cudaEventDestroy(ev[i]); cudaStreamDestroy(ownStream); }
         ready = false;
     }
     bool bind() { ZB_CUDA(cudaSetDevice(device)); return true; }
@@ -543,6 +545,14 @@ void ZSTDB200_getLastTimings(const void* ctx, float* msOut)
 }
 unsigned ZSTDB200_getLastLaunchCount(const void* ctx) { const zb::Engine* E = (const zb::Engine*)ctx; return E ? E->launches : 0; }
 const char* ZSTDB200_lastErrorString(void) { return zb::t_lastError.c_str(); }
+size_t ZSTDB200_setStream(void* ctx, void* stream)
+{
+    zb::Engine* E = (zb::Engine*)ctx;
+    if (!E) return (size_t)make_error(zb::kGeneric);
+    if (!E->init()) return (size_t)make_error(zb::kGeneric);
+    E->stream = stream ? (cudaStream_t)stream : E->ownStream;
+    return 0;
+}
 int ZSTDB200_deviceCount(void) { int c = 0; if (cudaGetDeviceCount(&c) != cudaSuccess) return 0; return c; }
 
 }  // extern "C"
