@@ -561,46 +561,77 @@ __global__ void __launch_bounds__(kSetupWarps * 32) dec_setup_kernel(DecPass p)
 }
 
 // =====================================================================================================
-//  Backward bit reader over global memory (32-bit aligned word refills, one word prefetched).
-//  Semantics of BIT_DStream_t (Bitstream.cs:172-425) for well-formed streams; over-reads are tracked in `left`.
+//  Backward bit reader.  The stream is staged through a small per-lane shared-memory ring that is filled with
+//  cp.async (LDGSTS) one chunk ahead, so the decode loops never wait on an HBM/L2 round trip: with 32 lanes
+//  refilling at different times, a register-prefetched word made the whole warp stall at nearly every refill
+//  (profiles/r01_notes.md).  Semantics of BIT_DStream_t (Bitstream.cs:172-425) for well-formed streams;
+//  over-reads are tracked in `left`.
 // =====================================================================================================
+template <int H>           // words per chunk (chunk = 4*H bytes, ring = 2 chunks)
 struct BitReader {
-    uint64_t w;            // unread bits, left aligned
-    int32_t cnt;           // valid bits in w
+    // 96-bit register window over the stream, most significant word first; `off` bits of w0 are already consumed.
+    // Fields are cut out with funnel shifts, so a read costs two dependent ALU instructions and the refill (a shared
+    // memory load whose result is needed two refills later) stays off the critical path.
+    uint32_t w0, w1, w2;
+    uint32_t off;          // 0..31 after normalize()
     int32_t left;          // unread bits of the stream (negative = over-read)
-    const uint32_t* wp;    // next (lower) word to fetch
-    const uint32_t* lo;    // lowest word that may be read
-    uint32_t nxt;          // prefetched *wp
+    uint32_t* ring;        // 2*H words of shared memory private to this lane (16-byte aligned)
+    const uint8_t* chunk;  // global address of the chunk being consumed (multiple of 4*H)
+    const uint8_t* lowest; // lowest chunk that may be fetched (contains the first byte of the item)
+    int32_t widx;          // next word to consume inside the current chunk
+    uint32_t half;
 
-    __device__ __forceinline__ bool init(const uint8_t* itemBase, uint32_t off, uint32_t len) {
-        const uint8_t* const last = itemBase + off + len - 1;
-        uint32_t const lastByte = *last;
-        if (lastByte == 0) return false;
+    static __device__ __forceinline__ void fetch(uint32_t* dstS, const uint8_t* g) {
+        uint32_t const sa = (uint32_t)__cvta_generic_to_shared(dstS);
+#pragma unroll
+        for (int i = 0; i < H / 4; i++) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa + 16 * i), "l"(g + 16 * i));
+        asm volatile("cp.async.commit_group;");
+    }
+    static __device__ __forceinline__ void wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+    __device__ __forceinline__ uint32_t next_word() {
+        if (widx < 0) {
+            wait_all();
+            chunk -= 4 * H; half ^= 1; widx = H - 1;
+            const uint8_t* const nx = chunk - 4 * H;
+            if (nx >= lowest) fetch(ring + (half ^ 1) * H, nx);
+        }
+        uint32_t const v = chunk >= lowest ? ring[half * H + widx] : 0u;
+        widx--;
+        return v;
+    }
+    __device__ __forceinline__ bool init(uint32_t* ringS, const uint8_t* itemBase, uint32_t offB, uint32_t len) {
+        ring = ringS;
+        const uint8_t* const last = itemBase + offB + len - 1;
+        uintptr_t const a = (uintptr_t)last;
+        chunk = (const uint8_t*)(a & ~(uintptr_t)(4 * H - 1));
+        lowest = (const uint8_t*)((uintptr_t)itemBase & ~(uintptr_t)(4 * H - 1));
+        half = 0;
+        fetch(ring, chunk);
+        if (chunk - 4 * H >= lowest) fetch(ring + H, chunk - 4 * H);
+        wait_all();
+        widx = (int32_t)((a & (uintptr_t)(4 * H - 1)) >> 2);
+        uint32_t const v = ring[widx];
+        widx--;
+        uint32_t const lastByte = (v >> ((a & 3) * 8)) & 0xFF;
+        w0 = v; w1 = next_word(); w2 = next_word();
+        if (lastByte == 0) { off = 0; left = 0; return false; }
         uint32_t const hb = highbit32(lastByte);
         left = (int32_t)((len - 1) * 8 + hb);
-        uintptr_t const a = (uintptr_t)last;
-        const uint32_t* const word = (const uint32_t*)(a & ~(uintptr_t)3);
-        lo = (const uint32_t*)((uintptr_t)itemBase & ~(uintptr_t)3);
-        uint32_t const bitsInWord = (uint32_t)(a & 3) * 8 + hb;
-        uint32_t const v = *word;
-        w = bitsInWord ? ((uint64_t)v << (64 - bitsInWord)) : 0ull;
-        cnt = (int32_t)bitsInWord;
-        wp = word - 1;
-        nxt = wp >= lo ? *wp : 0u;
-        refill();
+        off = 32 - ((uint32_t)(a & 3) * 8 + hb);       // everything from the end mark upwards is "consumed"
+        normalize();
         return true;
     }
-    __device__ __forceinline__ void refill() {
-        if (cnt <= 32) {
-            w |= (uint64_t)nxt << (32 - cnt);
-            cnt += 32;
-            wp--;
-            nxt = wp >= lo ? *wp : 0u;
-        }
+    __device__ __forceinline__ void normalize() { if (off >= 32) { off -= 32; w0 = w1; w1 = w2; w2 = next_word(); } }
+    // nb bits starting `o` bits below the top of w0; o in [0,31], nb in [0,31]
+    __device__ __forceinline__ uint32_t field_lo(uint32_t o, uint32_t nb) const { return (__funnelshift_l(w1, w0, o) >> 1) >> (31 - nb); }
+    // same for o in [0,63]
+    __device__ __forceinline__ uint32_t field(uint32_t o, uint32_t nb) const {
+        uint32_t const a = __funnelshift_l(w1, w0, o), b = __funnelshift_l(w2, w1, o);
+        return ((o < 32 ? a : b) >> 1) >> (31 - nb);
     }
-    __device__ __forceinline__ uint32_t peek(uint32_t nb) const { return (uint32_t)((w >> 1) >> (63 - nb)); }   // nb in [0,32]
-    __device__ __forceinline__ void skip(uint32_t nb) { w <<= nb; cnt -= (int32_t)nb; left -= (int32_t)nb; }
-    __device__ __forceinline__ uint32_t read(uint32_t nb) { uint32_t const v = peek(nb); skip(nb); return v; }
+    __device__ __forceinline__ void consume(uint32_t nb) { off += nb; left -= (int32_t)nb; }
+    __device__ __forceinline__ uint32_t read(uint32_t nb) { uint32_t const v = field_lo(off, nb); consume(nb); normalize(); return v; }
 };
 
 // =====================================================================================================
@@ -610,12 +641,15 @@ struct BitReader {
 constexpr int kHufItemsPerCta = 16;
 constexpr int kHufThreads = kHufItemsPerCta * 4;
 constexpr uint32_t kHufSmemEntries = 2048;     // tables with tableLog <= 11 are staged; log-12 tables are read from HBM/L2
+constexpr int kHufRingWords = 16;              // 64-byte chunks, 128 B of ring per stream
+constexpr uint32_t kHufSmemBytes = kHufItemsPerCta * kHufSmemEntries * 2 + kHufThreads * 2 * kHufRingWords * 4;
 
 __device__ __forceinline__ uint32_t lit_segment_stride(uint32_t litSize) { uint32_t const seg = (litSize + 3) / 4; return (seg + 15) & ~15u; }
 
 __global__ void __launch_bounds__(kHufThreads) dec_huf_kernel(DecPass p)
 {
-    extern __shared__ uint16_t s_tab[];       // [kHufItemsPerCta][2048]
+    extern __shared__ __align__(16) uint16_t s_tab[];       // [kHufItemsPerCta][2048] tables, then [kHufThreads][2*kHufRingWords] stream rings
+    uint32_t* const s_ring = (uint32_t*)(s_tab + kHufItemsPerCta * kHufSmemEntries) + threadIdx.x * (2 * kHufRingWords);
     uint32_t const nWork = p.counters[0];
     uint32_t const first = blockIdx.x * kHufItemsPerCta;
     if (first >= nWork) return;
@@ -646,13 +680,14 @@ __global__ void __launch_bounds__(kHufThreads) dec_huf_kernel(DecPass p)
     else { count = stream < 3 ? seg : litSize - 3 * seg; outOff = stream * lit_segment_stride(litSize); }
     uint8_t* out = p.litBuf + (size_t)item * kLitStride + outOff;
     const uint8_t* const src = p.src + it.srcOff;
-    BitReader br;
-    bool ok = br.init(src, it.streamOff[stream], it.streamLen[stream]);
+    BitReader<kHufRingWords> br;
+    bool ok = br.init(s_ring, src, it.streamOff[stream], it.streamLen[stream]);
     if (ok) {
         const uint16_t* tab; bool const inSmem = log <= 11;
         const uint16_t* const gtab = p.hufTable + (size_t)item * kHufTableEntries;
         tab = s_tab + slot * kHufSmemEntries;
         uint32_t i = 0;
+        uint32_t const sh = 32 - log;
         // 16 symbols -> one 16-byte store (out is 16-byte aligned by construction)
         for (; i + 16 <= count && br.left >= 0; i += 16) {
             uint32_t v[4];
@@ -661,10 +696,10 @@ __global__ void __launch_bounds__(kHufThreads) dec_huf_kernel(DecPass p)
                 uint32_t acc = 0;
 #pragma unroll
                 for (int r = 0; r < 4; r++) {
-                    if ((r & 1) == 0) br.refill();
-                    uint32_t const idx = br.peek(log);
+                    uint32_t const idx = __funnelshift_l(br.w1, br.w0, br.off) >> sh;
                     uint32_t const e = inSmem ? tab[idx] : gtab[idx];
-                    br.skip(e & 0xFF);
+                    br.consume(e & 0xFF);
+                    br.normalize();
                     acc |= (e >> 8) << (8 * r);
                 }
                 v[q] = acc;
@@ -672,10 +707,10 @@ __global__ void __launch_bounds__(kHufThreads) dec_huf_kernel(DecPass p)
             *(uint4*)(out + i) = make_uint4(v[0], v[1], v[2], v[3]);
         }
         for (; i < count && br.left >= 0; i++) {
-            br.refill();
-            uint32_t const idx = br.peek(log);
+            uint32_t const idx = __funnelshift_l(br.w1, br.w0, br.off) >> sh;
             uint32_t const e = inSmem ? tab[idx] : gtab[idx];
-            br.skip(e & 0xFF);
+            br.consume(e & 0xFF);
+            br.normalize();
             out[i] = (uint8_t)(e >> 8);
         }
         ok = (br.left == 0) && (i == count);      // BIT_endOfDStream: the stream must be consumed exactly (:526-533)
@@ -688,11 +723,13 @@ __global__ void __launch_bounds__(kHufThreads) dec_huf_kernel(DecPass p)
 //  ZSTD_decompressSequences_body / ZSTD_decodeSequence (ZstdDecompressBlock.cs:2668, :2360) incl. the checks of
 //  ZSTD_execSequenceEnd (:2083-2103), so that the exec kernel can copy without re-validating.
 // =====================================================================================================
-constexpr int kSeqItemsPerCta = 11;
+constexpr int kSeqItemsPerCta = 10;            // 10 x (5 KB tables + 256 B ring) -> 4 CTAs (40 items) per SM
+constexpr int kSeqRingWords = 32;              // 128-byte chunks, 256 B of ring per item
+constexpr uint32_t kSeqSmemBytes = kSeqItemsPerCta * (kFseTableEntries + 2 * kSeqRingWords) * 4;
 
 __global__ void __launch_bounds__(32) dec_seq_kernel(DecPass p)
 {
-    extern __shared__ __align__(16) uint32_t s_seqTab[];   // [kSeqItemsPerCta][kFseTableEntries]
+    extern __shared__ __align__(16) uint32_t s_seqTab[];   // [kSeqItemsPerCta][kFseTableEntries] tables, then [kSeqItemsPerCta][2*kSeqRingWords] rings
     __shared__ uint32_t s_llBase[36], s_mlBase[53];
     uint32_t const nWork = p.counters[1];
     uint32_t const first = blockIdx.x * kSeqItemsPerCta;
@@ -720,50 +757,54 @@ __global__ void __launch_bounds__(32) dec_seq_kernel(DecPass p)
     uint32_t* const oOF = p.seqOF + (size_t)item * kSeqCap;
     const uint8_t* const src = p.src + it.srcOff;
     uint32_t const nbSeq = it.nbSeq;
-    BitReader br;
+    BitReader<kSeqRingWords> br;
     uint32_t err = 0;
-    if (!br.init(src, it.seqOff, it.seqLen)) err = kCorruptionDetected;
+    if (!br.init(s_seqTab + kSeqItemsPerCta * kFseTableEntries + lane * (2 * kSeqRingWords), src, it.seqOff, it.seqLen)) err = kCorruptionDetected;
     uint32_t rep0 = it.rep[0], rep1 = it.rep[1], rep2 = it.rep[2];
     uint32_t outPos = it.outPos; uint32_t const frameStart = it.frameStart, dstCap = it.dstCap;
     uint32_t litPos = 0; uint32_t const litSize = it.litSize;
     if (!err) {
-        uint32_t sL = br.read(it.llLog); br.refill();
-        uint32_t sO = br.read(it.ofLog); br.refill();
-        uint32_t sM = br.read(it.mlLog); br.refill();
+        uint32_t sL = br.read(it.llLog);
+        uint32_t sO = br.read(it.ofLog);
+        uint32_t sM = br.read(it.mlLog);
         if (br.left < 0) err = kCorruptionDetected;
         for (uint32_t n = 0; n < nbSeq && !err; n++) {
             uint32_t const eL = tLL[sL], eO = tOF[sO], eM = tML[sM];
             uint32_t const llBits = (eL >> 4) & 31, mlBits = (eM >> 4) & 31, ofBits = (eO >> 4) & 31;
             uint32_t const llSym = (eL >> 9) & 63, mlSym = (eM >> 9) & 63;
             uint32_t ll = s_llBase[llSym], ml = s_mlBase[mlSym];
+            // stream order: offset extra, matchLength extra, litLength extra, then LL / ML / OF state bits (:2397-2480)
+            uint32_t const ofExtra = br.field_lo(br.off, ofBits);              // ofBits <= 31
+            br.consume(ofBits); br.normalize();
+            uint32_t const o1 = br.off, o2 = o1 + mlBits;                      // <= 31 + 16
+            ml += br.field(o1, mlBits);
+            ll += br.field(o2, llBits);
+            br.consume(mlBits + llBits); br.normalize();
+            bool const overRead = br.left < 0;
+            uint32_t const nbL = eL & 15, nbM = eM & 15, nbO = eO & 15;
+            uint32_t const p1 = br.off, p2 = p1 + nbL, p3 = p2 + nbM;          // <= 31 + 9 + 9
+            sL = (eL >> 16) + br.field(p1, nbL);
+            sM = (eM >> 16) + br.field(p2, nbM);
+            sO = (eO >> 16) + br.field(p3, nbO);
+            br.consume(nbL + nbM + nbO); br.normalize();
             uint32_t offset;
             if (ofBits > 1) {
-                offset = ((1u << ofBits) - 3u) + br.read(ofBits);           // OF_base[n] = (1<<n)-3 for n >= 2
+                offset = ((1u << ofBits) - 3u) + ofExtra;                    // OF_base[n] = (1<<n)-3 for n >= 2
                 rep2 = rep1; rep1 = rep0; rep0 = offset;
-                br.refill();
             } else {
-                uint32_t const ll0 = (ll == 0);                              // baseValue == 0 <=> code 0
+                uint32_t const ll0 = (llSym == 0);                           // baseValue == 0 <=> code 0
                 if (ofBits == 0) {
                     offset = ll0 ? rep1 : rep0;
                     rep1 = ll0 ? rep0 : rep1;
                     rep0 = offset;
                 } else {
-                    uint32_t const ofv = 1u + ll0 + br.read(1);              // OF_base[1] = 1
+                    uint32_t const ofv = 1u + ll0 + ofExtra;                 // OF_base[1] = 1
                     uint32_t temp = (ofv == 3) ? rep0 - 1 : (ofv == 1 ? rep1 : rep2);
                     temp += !temp;
                     if (ofv != 1) rep2 = rep1;
                     rep1 = rep0; rep0 = offset = temp;
                 }
             }
-            if (mlBits) ml += br.read(mlBits);
-            if (llBits) ll += br.read(llBits);
-            br.refill();
-            bool const overRead = br.left < 0;
-            // state updates in the reference's order LL, ML, OF (:2473-2480)
-            sL = (eL >> 16) + br.read(eL & 15);
-            sM = (eM >> 16) + br.read(eM & 15);
-            sO = (eO >> 16) + br.read(eO & 15);
-            br.refill();
             // validity (ZSTD_execSequenceEnd order): output overflow, literal overrun, offset beyond frame start
             uint32_t const seqLen = ll + ml;
             if (seqLen > dstCap - outPos) err = kDstSizeTooSmall;
@@ -821,7 +862,8 @@ __global__ void __launch_bounds__(kExecThreads) dec_exec_kernel(DecPass p)
 {
     __shared__ __align__(16) uint8_t tile[kTileBytes];
     __shared__ uint32_t s_scanA[kExecThreads / 32], s_scanB[kExecThreads / 32];
-    __shared__ uint32_t s_water, s_pending, s_count, s_span, s_litSpan, s_big[3];
+    __shared__ uint32_t s_count, s_span, s_litSpan, s_big[3];
+    __shared__ uint32_t s_oStart[kExecThreads + 1], s_done[kExecThreads / 32];
     uint32_t const item = blockIdx.x;
     DecItem& it = p.items[item];
     if (it.status != kStRunning || it.blkType == kBlkNone) return;
@@ -883,37 +925,56 @@ __global__ void __launch_bounds__(kExecThreads) dec_exec_kernel(DecPass p)
                 continue;
             }
             bool const mine = tid < cnt;
-            // tile span = end of sequence cnt-1
-            if (tid == cnt - 1) { s_span = oStart + ll + ml; s_litSpan = lStart + ll; }
+            // publish the tile-relative start of every sequence (and the end of the last one) for dependency look-ups
+            if (mine) s_oStart[tid] = oStart; else if (tid > cnt) s_oStart[tid] = 0xFFFFFFFFu;
+            if (tid == cnt - 1) { s_span = oStart + ll + ml; s_litSpan = lStart + ll; s_oStart[cnt] = oStart + ll + ml; }
+            if (tid < kExecThreads / 32) s_done[tid] = 0;
             // literals -> tile
             if (mine) for (uint32_t k = 0; k < ll; k++) tile[oStart + k] = lit_at(litPos + lStart + k);
-            if (tid == 0) { s_pending = 0; s_water = 0xFFFFFFFFu; }
             __syncthreads();
             uint32_t const span = s_span;
-            // matches: rounds. A match is ready when the non-self part of its source lies below the watermark
-            // (= first byte of the earliest unfinished match).
+            // Matches.  Sequence s needs the non-self part of its source, tile range [a, b): every earlier sequence whose
+            // output intersects that range must be finished.  [jLo, jHi] = those sequences (binary search over the starts).
             uint32_t const mDst = oStart + ll;                  // tile-relative
-            bool pending = mine && ml > 0;
-            int64_t const srcRel = (int64_t)mDst - (int64_t)of; // tile-relative source start (may be negative: finished bytes in HBM)
-            uint32_t const nonSelf = of < ml ? of : ml;         // bytes of the source that are not produced by this match itself
+            int64_t const srcRel = (int64_t)mDst - (int64_t)of; // may be negative: finished bytes behind the tile (HBM/L2)
+            uint32_t const nonSelf = of < ml ? of : ml;
+            bool pending = mine;
+            uint32_t jLo = 1, jHi = 0;                          // empty range = no dependency inside the tile
+            if (mine && srcRel + (int64_t)nonSelf > 0) {
+                uint32_t const a = srcRel > 0 ? (uint32_t)srcRel : 0u, b = (uint32_t)(srcRel + (int64_t)nonSelf);
+                // jLo = first j with end_j > a  (end_j = s_oStart[j+1]);  jHi = last j with start_j < b, clipped to tid-1
+                uint32_t lo = 0, hi = tid;                      // search in [0, tid)
+                while (lo < hi) { uint32_t const mid = (lo + hi) >> 1; if (s_oStart[mid + 1] > a) hi = mid; else lo = mid + 1; }
+                jLo = lo;
+                lo = 0; hi = tid;
+                while (lo < hi) { uint32_t const mid = (lo + hi) >> 1; if (s_oStart[mid] < b) lo = mid + 1; else hi = mid; }
+                jHi = lo ? lo - 1 : 0;
+                if (lo == 0 || jLo > jHi) { jLo = 1; jHi = 0; }
+            }
             for (;;) {
-                if (pending) atomicMin(&s_water, mDst);
-                __syncthreads();
-                uint32_t const water = s_water;
-                if (water == 0xFFFFFFFFu) break;
-                bool const ready = pending && (srcRel + (int64_t)nonSelf <= (int64_t)water || mDst == water);
+                bool ready = pending;
+                if (ready && jLo <= jHi) {
+                    // all bits jLo..jHi of the done mask must be set
+                    uint32_t const wLo = jLo >> 5, wHi = jHi >> 5;
+                    for (uint32_t wq = wLo; wq <= wHi && ready; wq++) {
+                        uint32_t need = 0xFFFFFFFFu;
+                        if (wq == wLo) need &= 0xFFFFFFFFu << (jLo & 31);
+                        if (wq == wHi) need &= 0xFFFFFFFFu >> (31 - (jHi & 31));
+                        if ((s_done[wq] & need) != need) ready = false;
+                    }
+                }
                 if (ready) {
                     const uint8_t* const gsrc = dst + outPos;   // tile origin in HBM
-                    for (uint32_t k = 0; k < ml; k++) {
-                        int64_t const sp = srcRel + (int64_t)(of < ml ? (k % of) : k);
-                        uint8_t const v = sp >= 0 ? tile[sp] : gsrc[sp];
-                        tile[mDst + k] = v;
+                    if (of >= ml) {
+                        for (uint32_t k = 0; k < ml; k++) { int64_t const sp = srcRel + (int64_t)k; tile[mDst + k] = sp >= 0 ? tile[sp] : gsrc[sp]; }
+                    } else {
+                        uint32_t r = 0;                          // k % of without a division
+                        for (uint32_t k = 0; k < ml; k++) { int64_t const sp = srcRel + (int64_t)r; tile[mDst + k] = sp >= 0 ? tile[sp] : gsrc[sp]; if (++r == of) r = 0; }
                     }
-                    pending = false;
                 }
-                __syncthreads();
-                if (tid == 0) s_water = 0xFFFFFFFFu;
-                __syncthreads();
+                __syncthreads();                                 // copies of this round are visible; done mask was only read so far
+                if (ready) { atomicOr(&s_done[tid >> 5], 1u << (tid & 31)); pending = false; }
+                if (!__syncthreads_or(pending)) break;
             }
             // flush tile
             for (uint32_t i = tid; i < span; i += kExecThreads) dst[outPos + i] = tile[i];
@@ -968,8 +1029,8 @@ static void dec_set_attrs()
     static bool done[64] = {};
     int dev = 0; cudaGetDevice(&dev);
     if (dev < 0 || dev >= 64 || done[dev]) return;
-    cudaFuncSetAttribute(dec_huf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kHufItemsPerCta * kHufSmemEntries * 2);
-    cudaFuncSetAttribute(dec_seq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSeqItemsPerCta * kFseTableEntries * 4);
+    cudaFuncSetAttribute(dec_huf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kHufSmemBytes);
+    cudaFuncSetAttribute(dec_seq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSeqSmemBytes);
     done[dev] = true;
 }
 
@@ -978,8 +1039,8 @@ void dec_launch_wave(const DecPass& p, cudaStream_t s)
     dec_reset_counters_kernel<<<1, 32, 0, s>>>(p.counters);
     dec_setup_kernel<<<(p.nItems + kSetupWarps - 1) / kSetupWarps, kSetupWarps * 32, 0, s>>>(p);
     dec_set_attrs();
-    dec_huf_kernel<<<(p.nItems + kHufItemsPerCta - 1) / kHufItemsPerCta, kHufThreads, kHufItemsPerCta * kHufSmemEntries * 2, s>>>(p);
-    dec_seq_kernel<<<(p.nItems + kSeqItemsPerCta - 1) / kSeqItemsPerCta, 32, kSeqItemsPerCta * kFseTableEntries * 4, s>>>(p);
+    dec_huf_kernel<<<(p.nItems + kHufItemsPerCta - 1) / kHufItemsPerCta, kHufThreads, kHufSmemBytes, s>>>(p);
+    dec_seq_kernel<<<(p.nItems + kSeqItemsPerCta - 1) / kSeqItemsPerCta, 32, kSeqSmemBytes, s>>>(p);
     dec_exec_kernel<<<p.nItems, kExecThreads, 0, s>>>(p);
 }
 
@@ -990,9 +1051,9 @@ void dec_launch_wave_timed(const DecPass& p, cudaStream_t s, cudaEvent_t* ev)
     dec_setup_kernel<<<(p.nItems + kSetupWarps - 1) / kSetupWarps, kSetupWarps * 32, 0, s>>>(p);
     cudaEventRecord(ev[1], s);
     dec_set_attrs();
-    dec_huf_kernel<<<(p.nItems + kHufItemsPerCta - 1) / kHufItemsPerCta, kHufThreads, kHufItemsPerCta * kHufSmemEntries * 2, s>>>(p);
+    dec_huf_kernel<<<(p.nItems + kHufItemsPerCta - 1) / kHufItemsPerCta, kHufThreads, kHufSmemBytes, s>>>(p);
     cudaEventRecord(ev[2], s);
-    dec_seq_kernel<<<(p.nItems + kSeqItemsPerCta - 1) / kSeqItemsPerCta, 32, kSeqItemsPerCta * kFseTableEntries * 4, s>>>(p);
+    dec_seq_kernel<<<(p.nItems + kSeqItemsPerCta - 1) / kSeqItemsPerCta, 32, kSeqSmemBytes, s>>>(p);
     cudaEventRecord(ev[3], s);
     dec_exec_kernel<<<p.nItems, kExecThreads, 0, s>>>(p);
     cudaEventRecord(ev[4], s);

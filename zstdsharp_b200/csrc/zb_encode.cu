@@ -57,6 +57,7 @@ static CParams get_cparams(int level, uint64_t srcSize)
 // ------------------------------------------------------------------------------------------------------------
 constexpr uint32_t kEncSeqCap = kBlockSizeMax / 4 + 1;      // maxNbSeq = blockSize / 4 (minMatch != 3), ZstdCompress.cs:2570
 constexpr uint32_t kEncLitStride = kBlockSizeMax + 64;
+constexpr uint32_t kWarpMatchMaxHashLog = 13;             // 2^13 x 4 B = 32 KB of shared memory per chunk
 
 struct __align__(16) EncItem {
     uint64_t srcOff, dstOff;
@@ -293,10 +294,163 @@ _match_stored:
     }
 }
 
-__global__ void __launch_bounds__(32) enc_match_kernel(EncPass p)
+// ------------------------------------------------------------------------------------------------------------
+//  Warp-parallel, exact ZSTD_fast parse: one warp per chunk, hash table (<= 2^13 entries) in shared memory.
+//  The reference loop (ZstdFast.cs:147-230) visits positions ip0, ip0+1, ip0+d, ip0+d+1, ... on a schedule that
+//  depends only on (ip0, step, nextStep) until a match is found.  The warp therefore evaluates a window of 16
+//  iterations (32 hash probes + 16 repcode probes) speculatively: lane 2k / 2k+1 own the positions of iteration k,
+//  a probe sees earlier lanes of the same window through __match_any_sync and older positions through the table,
+//  and the first event in the reference's order (repcode@ip2, hash@ip0, hash@ip1 of the lowest iteration) wins.
+//  Table writes are committed up to that event only, so the table always equals the serial algorithm's table.
+// ------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t hash_val(uint64_t x, uint32_t hBits, uint32_t mls)
 {
-    uint32_t const i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= p.nItems) return;
+    switch (mls) {
+    default:
+    case 4: return ((uint32_t)x * 2654435761u) >> (32 - hBits);
+    case 5: return (uint32_t)(((x << 24) * 889523592379ull) >> (64 - hBits));
+    case 6: return (uint32_t)(((x << 16) * 227718039650203ull) >> (64 - hBits));
+    case 7: return (uint32_t)(((x << 8) * 58295818150454627ull) >> (64 - hBits));
+    }
+}
+
+// common-prefix length of src[a..) and src[b..) (b < a), bounded by `limit`; the whole warp cooperates (ZSTD_count :264)
+__device__ __forceinline__ int warp_count(const uint8_t* src, int a, int b, int limit, uint32_t lane)
+{
+    int total = 0;
+    for (;;) {
+        int const pa = a + total + 4 * (int)lane, pb = b + total + 4 * (int)lane;
+        int const rem = limit - pa;
+        uint32_t n = 0;
+        if (rem >= 4) { uint32_t const diff = rd32(src + pa) ^ rd32(src + pb); n = diff ? (uint32_t)(__ffs((int)diff) - 1) >> 3 : 4u; }
+        else { for (int j = 0; j < rem; j++) { if (src[pa + j] == src[pb + j]) n++; else break; } }
+        uint32_t const notFull = __ballot_sync(0xFFFFFFFFu, n != 4);
+        if (notFull) { int const f = __ffs((int)notFull) - 1; return total + 4 * f + (int)__shfl_sync(0xFFFFFFFFu, n, f); }
+        total += 128;
+    }
+}
+
+__global__ void __launch_bounds__(32) enc_match_warp_kernel(EncPass p, const uint32_t* __restrict__ workList)
+{
+    extern __shared__ uint32_t T[];
+    uint32_t const item = workList[blockIdx.x];
+    uint32_t const lane = threadIdx.x;
+    EncItem& it = p.items[item];
+    uint32_t const hlog = it.hashLog, mls = it.minMatch;
+    int const srcSize = (int)it.srcSize;
+    const uint8_t* const src = p.src + it.srcOff;
+    uint32_t* const oLL = p.seqLL + (size_t)item * kEncSeqCap;
+    uint32_t* const oML = p.seqML + (size_t)item * kEncSeqCap;
+    uint32_t* const oOF = p.seqOF + (size_t)item * kEncSeqCap;
+    for (uint32_t i = lane; i < (1u << hlog); i += 32) T[i] = 0;
+    __syncwarp();
+    int const ilimit = srcSize - 8;
+    int ip0 = 1, anchor = 0;                         // first position is skipped (:129)
+    uint32_t rep1 = 1, rep2 = 0;                     // rep2 = 4 exceeds the history at frame start (:131-145)
+    uint32_t nseq = 0;
+    uint32_t const k = lane >> 1, odd = lane & 1;
+    uint32_t const FULL = 0xFFFFFFFFu;
+    for (;;) {                                       // _start
+        int step = 2, nextStep = ip0 + 128, d = 2;
+        bool matched = false;
+        for (;;) {                                   // one window of 16 iterations
+            int pk, dk, pW, dW, stepW, nextStepW;
+            if (ip0 + d + 16 * step < nextStep) {    // no step change inside the window
+                pk = k == 0 ? ip0 : ip0 + d + ((int)k - 1) * step; dk = k == 0 ? d : step;
+                pW = ip0 + d + 15 * step; dW = step; stepW = step; nextStepW = nextStep;
+            } else {
+                int P = ip0, D = d, S = step, N = nextStep; pk = 0; dk = 0;
+#pragma unroll
+                for (int j = 0; j < 16; j++) { if (j == (int)k) { pk = P; dk = D; } P += D; int const ip2n = P + S; D = S; if (ip2n >= N) { S++; N += 128; } }
+                pW = P; dW = D; stepW = S; nextStepW = N;
+            }
+            bool const vk = pk + dk + 1 < ilimit;    // loop condition ip3 < ilimit for this iteration
+            uint32_t const validMask = __ballot_sync(FULL, vk);
+            if (!(validMask & 1)) break;             // iteration 0 does not run: _cleanup
+            int const q = pk + (int)odd;
+            uint64_t const x = vk ? rd64(src + q) : 0ull;
+            uint32_t const cur4 = (uint32_t)x;
+            bool repHit = false;
+            if (vk && !odd && rep1) { int const r = pk + dk; repHit = rd32(src + r) == rd32(src + r - (int)rep1); }
+            uint32_t const h = hash_val(x, hlog, mls);
+            uint32_t const tv = vk ? T[h] : 0u;
+            uint32_t const peers = __match_any_sync(FULL, vk ? h : (0x80000000u | lane));
+            uint32_t const lower = peers & ((1u << lane) - 1u);
+            int const cl = lower ? 31 - __clz((int)lower) : (int)lane;
+            int const cq = __shfl_sync(FULL, q, cl);
+            int const cand = lower ? cq : (int)tv - 2;                  // table stores position + 2, 0 = empty
+            bool hit = false;
+            if (vk && cand >= 0) hit = rd32(src + cand) == cur4;
+            uint32_t key = 0xFFFFFFFFu;
+            if (hit) key = 3 * k + 1 + odd;
+            if (repHit) key = 3 * k;
+            uint32_t const best = __reduce_min_sync(FULL, key);
+            if (best == 0xFFFFFFFFu) {
+                if (vk && ((peers >> lane) >> 1) == 0) T[h] = (uint32_t)q + 2;   // the latest position of a bucket wins
+                __syncwarp();
+                if (validMask != FULL) break;        // the loop condition failed inside the window: _cleanup
+                ip0 = pW; d = dW; step = stepW; nextStep = nextStepW;
+                continue;
+            }
+            // ---- first event of the window ----
+            uint32_t const ke = best / 3, type = best - 3 * ke;
+            uint32_t const lastLane = 2 * ke + 1;
+            {   uint32_t const peersC = peers & (lastLane == 31 ? FULL : ((2u << lastLane) - 1u));
+                if (vk && lane <= lastLane && ((peersC >> lane) >> 1) == 0) T[h] = (uint32_t)q + 2; }
+            __syncwarp();
+            int const pke = __shfl_sync(FULL, pk, 2 * ke), dke = __shfl_sync(FULL, dk, 2 * ke);
+            uint32_t const evLane = 2 * ke + (type == 2 ? 1u : 0u);
+            int const qe = __shfl_sync(FULL, q, evLane), ce = __shfl_sync(FULL, cand, evLane);
+            int mpos, msrc, mlen, current0; uint32_t offcode;
+            if (type == 0) {                          // repcode at ip2 (:163-178)
+                mpos = pke + dke; msrc = mpos - (int)rep1;
+                int const back = src[mpos - 1] == src[msrc - 1];
+                mpos -= back; msrc -= back; mlen = 4 + back; offcode = 0; current0 = pke;
+            } else {                                  // _offset (:236-247)
+                mpos = qe; msrc = ce; rep2 = rep1; rep1 = (uint32_t)(qe - ce); offcode = rep1 + 2; mlen = 4; current0 = qe;
+                while (mpos > anchor && msrc > 0 && src[mpos - 1] == src[msrc - 1]) { mpos--; msrc--; mlen++; }
+            }
+            mlen += warp_count(src, mpos + mlen, msrc + mlen, srcSize, lane);
+            if (lane == 0) { oLL[nseq] = (uint32_t)(mpos - anchor); oOF[nseq] = offcode + 1; oML[nseq] = (uint32_t)mlen - 3; }
+            nseq++;
+            int const mend = mpos + mlen;
+            if (type == 2 && pke + dke < mend) {      // `if (ip1 < ip0) hashTable[hash1] = ip1` with ip1 = old ip2 (:254-257)
+                int const pp = pke + dke;
+                if (lane == 0) T[hash_val(rd64(src + pp), hlog, mls)] = (uint32_t)pp + 2;
+                __syncwarp();
+            }
+            ip0 = mend; anchor = mend;
+            if (ip0 <= ilimit) {
+                if (lane == 0) {
+                    T[hash_val(rd64(src + current0 + 2), hlog, mls)] = (uint32_t)current0 + 2 + 2;
+                    T[hash_val(rd64(src + ip0 - 2), hlog, mls)] = (uint32_t)(ip0 - 2) + 2;
+                }
+                __syncwarp();
+                while (ip0 <= ilimit && rep2 > 0 && rd32(src + ip0) == rd32(src + ip0 - (int)rep2)) {    // :264-285
+                    int const rlen = warp_count(src, ip0 + 4, ip0 + 4 - (int)rep2, srcSize, lane) + 4;
+                    { uint32_t const t = rep2; rep2 = rep1; rep1 = t; }
+                    if (lane == 0) {
+                        T[hash_val(rd64(src + ip0), hlog, mls)] = (uint32_t)ip0 + 2;
+                        oLL[nseq] = 0; oOF[nseq] = 1; oML[nseq] = (uint32_t)rlen - 3;
+                    }
+                    __syncwarp();
+                    nseq++;
+                    ip0 += rlen; anchor = ip0;
+                }
+            }
+            matched = true;
+            break;
+        }
+        if (!matched) break;
+    }
+    if (lane == 0) { it.nbSeq = nseq; it.lastLL = (uint32_t)(srcSize - anchor); }
+}
+
+__global__ void __launch_bounds__(32) enc_match_kernel(EncPass p, const uint32_t* __restrict__ workList, uint32_t nWork)
+{
+    uint32_t const w = blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= nWork) return;
+    uint32_t const i = workList[w];
     EncItem& it = p.items[i];
     it.nbSeq = 0; it.lastLL = it.srcSize;
     if (it.srcSize < 7 || it.srcSize > kBlockSizeMax) return;      // ZSTD_buildSeqStore: srcSize < MIN_CBLOCK_SIZE+blockHeader+1 -> noCompress (:3438)
@@ -1112,17 +1266,17 @@ struct HBuf { void* p = nullptr; size_t cap = 0;
     void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; } };
 
 struct EncArenaImpl {
-    DBuf items, tables, seqLL, seqML, seqOF, lit, stateBits, results, compact, cSrcOff, cSizes, cDstOff;
-    HBuf hItems, hResults, hC;
+    DBuf items, tables, seqLL, seqML, seqOF, lit, stateBits, results, compact, cSrcOff, cSizes, cDstOff, workLists;
+    HBuf hItems, hResults, hC, hWork;
 };
 static thread_local std::string t_encErr;
 const char* enc_last_error() { return t_encErr.c_str(); }
 void EncArena::release()
 {
     if (!impl) return;
-    DBuf* d[] = {&impl->items, &impl->tables, &impl->seqLL, &impl->seqML, &impl->seqOF, &impl->lit, &impl->stateBits, &impl->results, &impl->compact, &impl->cSrcOff, &impl->cSizes, &impl->cDstOff};
+    DBuf* d[] = {&impl->items, &impl->tables, &impl->seqLL, &impl->seqML, &impl->seqOF, &impl->lit, &impl->stateBits, &impl->results, &impl->compact, &impl->cSrcOff, &impl->cSizes, &impl->cDstOff, &impl->workLists};
     for (auto* b : d) b->release();
-    impl->hItems.release(); impl->hResults.release(); impl->hC.release();
+    impl->hItems.release(); impl->hResults.release(); impl->hC.release(); impl->hWork.release();
     delete impl; impl = nullptr;
 }
 const uint8_t* EncArena::compactBuf() const { return impl ? (const uint8_t*)impl->compact.p : nullptr; }
@@ -1130,6 +1284,15 @@ const uint8_t* EncArena::compactBuf() const { return impl ? (const uint8_t*)impl
 #define ENC_CUDA(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { t_encErr = std::string(#call) + ": " + cudaGetErrorString(e_); fprintf(stderr, "[zstdb200] CUDA failure: %s\n", t_encErr.c_str()); return false; } } while (0)
 
 constexpr size_t kEncMaxItemsPerPass = 8192;
+
+static void enc_set_attrs()
+{
+    static bool done[64] = {};
+    int dev = 0; cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64 || done[dev]) return;
+    cudaFuncSetAttribute(enc_match_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (1u << kWarpMatchMaxHashLog) * 4);
+    done[dev] = true;
+}
 
 bool enc_compress_device(EncArena& A, cudaStream_t stream, cudaEvent_t* ev, size_t n, int level,
                          const uint8_t* d_src, const uint64_t* srcOff, const size_t* srcSize,
@@ -1142,7 +1305,10 @@ bool enc_compress_device(EncArena& A, cudaStream_t stream, cudaEvent_t* ev, size
     for (size_t base = 0; base < n; base += kEncMaxItemsPerPass) {
         size_t const m = std::min(kEncMaxItemsPerPass, n - base);
         if (!I.hItems.ensure(m * sizeof(EncItem)) || !I.items.ensure(m * sizeof(EncItem)) || !I.results.ensure(m * 8) || !I.hResults.ensure(m * 8)) { t_encErr = "out of memory (items)"; return false; }
+        if (!I.hWork.ensure(m * 8) || !I.workLists.ensure(m * 8)) { t_encErr = "out of memory (work lists)"; return false; }
         EncItem* hi = (EncItem*)I.hItems.p;
+        uint32_t* const warpList = (uint32_t*)I.hWork.p; uint32_t* const serialList = warpList + m;
+        uint32_t nWarp = 0, nSerial = 0;
         size_t tableEntries = 0;
         for (size_t i = 0; i < m; i++) {
             size_t const ss = srcSize[base + i];
@@ -1152,24 +1318,33 @@ bool enc_compress_device(EncArena& A, cudaStream_t stream, cudaEvent_t* ev, size
             e.srcSize = (uint32_t)std::min<size_t>(ss, 0xFFFFFFF0u); e.dstCap = (uint32_t)std::min<size_t>(dstCap[base + i], 0xFFFFFFF0u);
             CParams const c = get_cparams(level, std::min<size_t>(ss, kBlockSizeMax));
             e.windowLog = c.windowLog; e.hashLog = c.hashLog; e.chainLog = c.chainLog; e.minMatch = c.minMatch; e.strategy = c.strategy;
+            e.nbSeq = 0; e.lastLL = e.srcSize;
+            if (ss < 7 || ss > kBlockSizeMax) continue;              // raw block / unsupported: no match finding
+            // ZSTD_fast with a table that fits shared memory -> warp-parallel kernel; everything else (level-2 2^15 tables,
+            // dfast's two tables) keeps its tables in HBM/L2 and is parsed by the lane-serial kernel
+            if (c.strategy == 1 && c.hashLog <= kWarpMatchMaxHashLog && ss >= 64) { warpList[nWarp++] = (uint32_t)i; continue; }
+            serialList[nSerial++] = (uint32_t)i;
             e.tableOff = (uint32_t)tableEntries;
             tableEntries += ((size_t)1 << c.hashLog) + (c.strategy == 2 ? ((size_t)1 << c.chainLog) : 0);
         }
         if (tableEntries >= 0xFFFFFFFFull) { t_encErr = "hash-table arena exceeds 32-bit indexing"; return false; }
-        if (!I.tables.ensure(tableEntries * 4) || !I.seqLL.ensure(m * (size_t)kEncSeqCap * 4) || !I.seqML.ensure(m * (size_t)kEncSeqCap * 4) ||
+        if (!I.tables.ensure(tableEntries * 4 + 16) || !I.seqLL.ensure(m * (size_t)kEncSeqCap * 4) || !I.seqML.ensure(m * (size_t)kEncSeqCap * 4) ||
             !I.seqOF.ensure(m * (size_t)kEncSeqCap * 4) || !I.lit.ensure(m * (size_t)kEncLitStride) || !I.stateBits.ensure(m * (size_t)kEncSeqCap * 8)) { t_encErr = "out of memory (arena)"; return false; }
         ENC_CUDA(cudaMemcpyAsync(I.items.p, hi, m * sizeof(EncItem), cudaMemcpyHostToDevice, stream));
         ENC_CUDA(cudaEventRecord(ev[14], stream));
-        ENC_CUDA(cudaMemsetAsync(I.tables.p, 0, tableEntries * 4, stream));      // tables are zeroed per frame (ZstdCompress.cs:2472,2481)
+        ENC_CUDA(cudaMemcpyAsync(I.workLists.p, I.hWork.p, m * 8, cudaMemcpyHostToDevice, stream));
+        if (tableEntries) ENC_CUDA(cudaMemsetAsync(I.tables.p, 0, tableEntries * 4, stream));      // tables are zeroed per frame (ZstdCompress.cs:2472,2481)
         EncPass p;
         p.items = (EncItem*)I.items.p; p.nItems = (uint32_t)m; p.src = d_src; p.dst = d_dst; p.tables = (uint32_t*)I.tables.p;
         p.seqLL = (uint32_t*)I.seqLL.p; p.seqML = (uint32_t*)I.seqML.p; p.seqOF = (uint32_t*)I.seqOF.p; p.litBuf = (uint8_t*)I.lit.p;
         p.stateBits = (uint64_t*)I.stateBits.p; p.results = (uint64_t*)I.results.p;
-        enc_match_kernel<<<(unsigned)((m + 31) / 32), 32, 0, stream>>>(p);
+        enc_set_attrs();
+        if (nWarp) enc_match_warp_kernel<<<nWarp, 32, (1u << kWarpMatchMaxHashLog) * 4, stream>>>(p, (const uint32_t*)I.workLists.p);
+        if (nSerial) enc_match_kernel<<<(nSerial + 31) / 32, 32, 0, stream>>>(p, (const uint32_t*)I.workLists.p + m, nSerial);
         ENC_CUDA(cudaEventRecord(ev[15], stream));
         enc_entropy_kernel<<<(unsigned)m, kEntThreads, 0, stream>>>(p);
         ENC_CUDA(cudaEventRecord(ev[16], stream));
-        *launches += 3;
+        *launches += 1 + (nWarp ? 1 : 0) + (nSerial ? 1 : 0) + (tableEntries ? 1 : 0);
         ENC_CUDA(cudaMemcpyAsync(I.hResults.p, I.results.p, m * 8, cudaMemcpyDeviceToHost, stream));
         ENC_CUDA(cudaStreamSynchronize(stream));
         ENC_CUDA(cudaGetLastError());
