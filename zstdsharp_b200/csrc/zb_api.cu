@@ -74,7 +74,7 @@ struct Engine {
     cudaStream_t ownStream = nullptr;   // created by the context; replaced by ZSTDB200_setStream
     cudaEvent_t ev[kEvents] = {};
     // decode arena
-    DevBuf dItems, dInit, dHuf, dFse, dLit, dSeqLL, dSeqML, dSeqOF, dDefaultFse, dHufList, dSeqList, dCounters, dResults;
+    DevBuf dItems, dInit, dHuf, dFse, dLit, dSeq, dDefaultFse, dHufList, dSeqList, dCounters, dResults;
     PinBuf hInit, hCounters, hResults;
     bool defaultTablesBuilt = false;
     // host<->device staging for the host-pointer API
@@ -105,7 +105,7 @@ struct Engine {
     }
     void destroy() {
         if (device >= 0) cudaSetDevice(device);
-        DevBuf* d[] = {&dItems, &dInit, &dHuf, &dFse, &dLit, &dSeqLL, &dSeqML, &dSeqOF, &dDefaultFse, &dHufList, &dSeqList, &dCounters, &dResults, &dSrc, &dDst, &dEncInit};
+        DevBuf* d[] = {&dItems, &dInit, &dHuf, &dFse, &dLit, &dSeq, &dDefaultFse, &dHufList, &dSeqList, &dCounters, &dResults, &dSrc, &dDst, &dEncInit};
         for (auto* b : d) b->release();
         PinBuf* h[] = {&hInit, &hCounters, &hResults, &hStage, &hEncInit};
         for (auto* b : h) b->release();
@@ -128,7 +128,7 @@ static bool decode_device(Engine& E, size_t n, const uint8_t* d_src, const uint6
         size_t const m = std::min(kMaxItemsPerPass, n - base);
         if (!E.dItems.ensure(m * sizeof(DecItem)) || !E.dInit.ensure(m * sizeof(DecItemInit)) || !E.hInit.ensure(m * sizeof(DecItemInit)) ||
             !E.dHuf.ensure(m * kHufTableEntries * 2) || !E.dFse.ensure(m * kFseTableEntries * 4) || !E.dLit.ensure(m * (size_t)kLitStride) ||
-            !E.dSeqLL.ensure(m * (size_t)kSeqCap * 4) || !E.dSeqML.ensure(m * (size_t)kSeqCap * 4) || !E.dSeqOF.ensure(m * (size_t)kSeqCap * 4) ||
+            !E.dSeq.ensure(m * (size_t)kSeqCap * 16) ||
             !E.dDefaultFse.ensure(kFseTableEntries * 4) || !E.dHufList.ensure(m * 4) || !E.dSeqList.ensure(m * 4) ||
             !E.dCounters.ensure(64) || !E.hCounters.ensure(64) || !E.dResults.ensure(m * 8) || !E.hResults.ensure(m * 8))
             return false;
@@ -146,7 +146,7 @@ static bool decode_device(Engine& E, size_t n, const uint8_t* d_src, const uint6
         DecPass p;
         p.items = E.dItems.as<DecItem>(); p.nItems = (uint32_t)m; p.src = d_src; p.dst = d_dst;
         p.hufTable = E.dHuf.as<uint16_t>(); p.fseTable = E.dFse.as<uint32_t>(); p.litBuf = E.dLit.as<uint8_t>();
-        p.seqLL = E.dSeqLL.as<uint32_t>(); p.seqML = E.dSeqML.as<uint32_t>(); p.seqOF = E.dSeqOF.as<uint32_t>();
+        p.seq = E.dSeq.as<uint4>();
         p.defaultFse = E.dDefaultFse.as<uint32_t>(); p.hufList = E.dHufList.as<uint32_t>(); p.seqList = E.dSeqList.as<uint32_t>();
         p.counters = E.dCounters.as<uint32_t>(); p.results = E.dResults.as<uint64_t>();
         ZB_CUDA(cudaEventRecord(E.ev[0], E.stream));

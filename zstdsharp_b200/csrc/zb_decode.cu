@@ -567,52 +567,52 @@ __global__ void __launch_bounds__(kSetupWarps * 32) dec_setup_kernel(DecPass p)
 //  (profiles/r01_notes.md).  Semantics of BIT_DStream_t (Bitstream.cs:172-425) for well-formed streams;
 //  over-reads are tracked in `left`.
 // =====================================================================================================
-template <int H>           // words per chunk (chunk = 4*H bytes, ring = 2 chunks)
+__device__ __forceinline__ uint32_t lds32(uint32_t saddr) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(saddr)); return v; }
+__device__ __forceinline__ uint32_t lds16(uint32_t saddr) { uint16_t v; asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(saddr)); return v; }
+
+template <int H>           // words per chunk (chunk CH = 4*H bytes); the ring holds 2 chunks and is aligned to 2*CH bytes
 struct BitReader {
     // 96-bit register window over the stream, most significant word first; `off` bits of w0 are already consumed.
-    // Fields are cut out with funnel shifts, so a read costs two dependent ALU instructions and the refill (a shared
-    // memory load whose result is needed two refills later) stays off the critical path.
+    // Fields are cut out with funnel shifts; the refill reads the private shared-memory ring through a 32-bit shared
+    // address that mirrors the low bits of the global address (ring byte = global byte mod 2*CH), so walking down the
+    // stream is one subtract-and-mask and chunk switches (1 in H refills) are the only place that touches cp.async.
+    static constexpr uint32_t CH = 4 * H;
     uint32_t w0, w1, w2;
     uint32_t off;          // 0..31 after normalize()
     int32_t left;          // unread bits of the stream (negative = over-read)
-    uint32_t* ring;        // 2*H words of shared memory private to this lane (16-byte aligned)
-    const uint8_t* chunk;  // global address of the chunk being consumed (multiple of 4*H)
-    const uint8_t* lowest; // lowest chunk that may be fetched (contains the first byte of the item)
-    int32_t widx;          // next word to consume inside the current chunk
-    uint32_t half;
+    uint32_t rp;           // shared address of the next word to fetch
+    const uint8_t* gnext;  // next global chunk to stage
+    const uint8_t* lowest; // lowest chunk that may be staged (contains the first byte of the item)
 
-    static __device__ __forceinline__ void fetch(uint32_t* dstS, const uint8_t* g) {
-        uint32_t const sa = (uint32_t)__cvta_generic_to_shared(dstS);
+    static __device__ __forceinline__ void fetch(uint32_t sa, const uint8_t* g) {
 #pragma unroll
-        for (int i = 0; i < H / 4; i++) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa + 16 * i), "l"(g + 16 * i));
+        for (uint32_t i = 0; i < CH / 16; i++) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa + 16 * i), "l"(g + 16 * i));
         asm volatile("cp.async.commit_group;");
     }
     static __device__ __forceinline__ void wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
     __device__ __forceinline__ uint32_t next_word() {
-        if (widx < 0) {
+        uint32_t const v = lds32(rp);
+        if ((rp & (CH - 1)) == 0) {          // lowest word of a chunk consumed: the other half must have landed; restage this half
             wait_all();
-            chunk -= 4 * H; half ^= 1; widx = H - 1;
-            const uint8_t* const nx = chunk - 4 * H;
-            if (nx >= lowest) fetch(ring + (half ^ 1) * H, nx);
+            if (gnext >= lowest) fetch(rp, gnext);
+            gnext -= CH;
         }
-        uint32_t const v = chunk >= lowest ? ring[half * H + widx] : 0u;
-        widx--;
+        rp = (rp & ~(2 * CH - 1)) | ((rp - 4) & (2 * CH - 1));
         return v;
     }
     __device__ __forceinline__ bool init(uint32_t* ringS, const uint8_t* itemBase, uint32_t offB, uint32_t len) {
-        ring = ringS;
+        uint32_t const R = (uint32_t)__cvta_generic_to_shared(ringS);
         const uint8_t* const last = itemBase + offB + len - 1;
         uintptr_t const a = (uintptr_t)last;
-        chunk = (const uint8_t*)(a & ~(uintptr_t)(4 * H - 1));
-        lowest = (const uint8_t*)((uintptr_t)itemBase & ~(uintptr_t)(4 * H - 1));
-        half = 0;
-        fetch(ring, chunk);
-        if (chunk - 4 * H >= lowest) fetch(ring + H, chunk - 4 * H);
+        const uint8_t* const c = (const uint8_t*)(a & ~(uintptr_t)(CH - 1));
+        lowest = (const uint8_t*)((uintptr_t)itemBase & ~(uintptr_t)(CH - 1));
+        fetch(R + (uint32_t)((uintptr_t)c & (2 * CH - 1)), c);
+        if (c - CH >= lowest) fetch(R + (uint32_t)((uintptr_t)(c - CH) & (2 * CH - 1)), c - CH);
+        gnext = c - 2 * CH;
         wait_all();
-        widx = (int32_t)((a & (uintptr_t)(4 * H - 1)) >> 2);
-        uint32_t const v = ring[widx];
-        widx--;
+        rp = R + (uint32_t)(a & (2 * CH - 1) & ~(uintptr_t)3);
+        uint32_t const v = next_word();
         uint32_t const lastByte = (v >> ((a & 3) * 8)) & 0xFF;
         w0 = v; w1 = next_word(); w2 = next_word();
         if (lastByte == 0) { off = 0; left = 0; return false; }
@@ -648,7 +648,7 @@ __device__ __forceinline__ uint32_t lit_segment_stride(uint32_t litSize) { uint3
 
 __global__ void __launch_bounds__(kHufThreads) dec_huf_kernel(DecPass p)
 {
-    extern __shared__ __align__(16) uint16_t s_tab[];       // [kHufItemsPerCta][2048] tables, then [kHufThreads][2*kHufRingWords] stream rings
+    extern __shared__ __align__(256) uint16_t s_tab[];       // [kHufItemsPerCta][2048] tables, then [kHufThreads][2*kHufRingWords] stream rings
     uint32_t* const s_ring = (uint32_t*)(s_tab + kHufItemsPerCta * kHufSmemEntries) + threadIdx.x * (2 * kHufRingWords);
     uint32_t const nWork = p.counters[0];
     uint32_t const first = blockIdx.x * kHufItemsPerCta;
@@ -683,35 +683,44 @@ __global__ void __launch_bounds__(kHufThreads) dec_huf_kernel(DecPass p)
     BitReader<kHufRingWords> br;
     bool ok = br.init(s_ring, src, it.streamOff[stream], it.streamLen[stream]);
     if (ok) {
-        const uint16_t* tab; bool const inSmem = log <= 11;
-        const uint16_t* const gtab = p.hufTable + (size_t)item * kHufTableEntries;
-        tab = s_tab + slot * kHufSmemEntries;
-        uint32_t i = 0;
         uint32_t const sh = 32 - log;
-        // 16 symbols -> one 16-byte store (out is 16-byte aligned by construction)
-        for (; i + 16 <= count && br.left >= 0; i += 16) {
-            uint32_t v[4];
+        uint32_t i = 0;
+        if (log <= 11) {
+            uint32_t const tabS = (uint32_t)__cvta_generic_to_shared(s_tab + slot * kHufSmemEntries);
+            // 16 symbols -> one 16-byte store (out is 16-byte aligned by construction)
+            for (; i + 16 <= count && br.left >= 0; i += 16) {
+                uint32_t v[4];
 #pragma unroll
-            for (int q = 0; q < 4; q++) {
-                uint32_t acc = 0;
+                for (int q = 0; q < 4; q++) {
+                    uint32_t acc = 0;
 #pragma unroll
-                for (int r = 0; r < 4; r++) {
-                    uint32_t const idx = __funnelshift_l(br.w1, br.w0, br.off) >> sh;
-                    uint32_t const e = inSmem ? tab[idx] : gtab[idx];
-                    br.consume(e & 0xFF);
-                    br.normalize();
-                    acc |= (e >> 8) << (8 * r);
+                    for (int r = 0; r < 4; r++) {
+                        uint32_t const idx = __funnelshift_l(br.w1, br.w0, br.off) >> sh;
+                        uint32_t const e = lds16(tabS + idx * 2);
+                        br.consume(e & 0xFF);
+                        br.normalize();
+                        acc |= (e >> 8) << (8 * r);
+                    }
+                    v[q] = acc;
                 }
-                v[q] = acc;
+                *(uint4*)(out + i) = make_uint4(v[0], v[1], v[2], v[3]);
             }
-            *(uint4*)(out + i) = make_uint4(v[0], v[1], v[2], v[3]);
-        }
-        for (; i < count && br.left >= 0; i++) {
-            uint32_t const idx = __funnelshift_l(br.w1, br.w0, br.off) >> sh;
-            uint32_t const e = inSmem ? tab[idx] : gtab[idx];
-            br.consume(e & 0xFF);
-            br.normalize();
-            out[i] = (uint8_t)(e >> 8);
+            for (; i < count && br.left >= 0; i++) {
+                uint32_t const idx = __funnelshift_l(br.w1, br.w0, br.off) >> sh;
+                uint32_t const e = lds16(tabS + idx * 2);
+                br.consume(e & 0xFF);
+                br.normalize();
+                out[i] = (uint8_t)(e >> 8);
+            }
+        } else {                                   // tableLog 12: the table stays in HBM/L2 (rare: zstd encoders cap at 11)
+            const uint16_t* const gtab = p.hufTable + (size_t)item * kHufTableEntries;
+            for (; i < count && br.left >= 0; i++) {
+                uint32_t const idx = __funnelshift_l(br.w1, br.w0, br.off) >> sh;
+                uint32_t const e = gtab[idx];
+                br.consume(e & 0xFF);
+                br.normalize();
+                out[i] = (uint8_t)(e >> 8);
+            }
         }
         ok = (br.left == 0) && (i == count);      // BIT_endOfDStream: the stream must be consumed exactly (:526-533)
     }
@@ -729,7 +738,7 @@ constexpr uint32_t kSeqSmemBytes = kSeqItemsPerCta * (kFseTableEntries + 2 * kSe
 
 __global__ void __launch_bounds__(32) dec_seq_kernel(DecPass p)
 {
-    extern __shared__ __align__(16) uint32_t s_seqTab[];   // [kSeqItemsPerCta][kFseTableEntries] tables, then [kSeqItemsPerCta][2*kSeqRingWords] rings
+    extern __shared__ __align__(256) uint32_t s_seqTab[];   // [kSeqItemsPerCta][kFseTableEntries] tables, then [kSeqItemsPerCta][2*kSeqRingWords] rings
     __shared__ uint32_t s_llBase[36], s_mlBase[53];
     uint32_t const nWork = p.counters[1];
     uint32_t const first = blockIdx.x * kSeqItemsPerCta;
@@ -752,9 +761,7 @@ __global__ void __launch_bounds__(32) dec_seq_kernel(DecPass p)
     const uint32_t* const tLL = s_seqTab + lane * kFseTableEntries + kFseLLOff;
     const uint32_t* const tML = s_seqTab + lane * kFseTableEntries + kFseMLOff;
     const uint32_t* const tOF = s_seqTab + lane * kFseTableEntries + kFseOFOff;
-    uint32_t* const oLL = p.seqLL + (size_t)item * kSeqCap;
-    uint32_t* const oML = p.seqML + (size_t)item * kSeqCap;
-    uint32_t* const oOF = p.seqOF + (size_t)item * kSeqCap;
+    uint4* const oSeq = p.seq + (size_t)item * kSeqCap;
     const uint8_t* const src = p.src + it.srcOff;
     uint32_t const nbSeq = it.nbSeq;
     BitReader<kSeqRingWords> br;
@@ -807,12 +814,10 @@ __global__ void __launch_bounds__(32) dec_seq_kernel(DecPass p)
             }
             // validity (ZSTD_execSequenceEnd order): output overflow, literal overrun, offset beyond frame start
             uint32_t const seqLen = ll + ml;
-            if (seqLen > dstCap - outPos) err = kDstSizeTooSmall;
-            else if (ll > litSize - litPos) err = kCorruptionDetected;
-            else if (offset > (outPos + ll) - frameStart) err = kCorruptionDetected;
-            else if (overRead) err = kCorruptionDetected;
-            else if (n + 1 < nbSeq && br.left < 0) err = kCorruptionDetected;
-            oLL[n] = ll; oML[n] = ml; oOF[n] = offset;
+            bool const e1 = seqLen > dstCap - outPos, e2 = ll > litSize - litPos, e3 = offset > (outPos + ll) - frameStart;
+            bool const e4 = overRead | ((n + 1 < nbSeq) & (br.left < 0));
+            if (e1 | e2 | e3 | e4) err = e1 ? kDstSizeTooSmall : kCorruptionDetected;
+            oSeq[n] = make_uint4(ll, ml, offset, 0u);
             outPos += seqLen; litPos += ll;
         }
         // the stream must not have unread bits left (BIT_reloadDStream >= completed, :2730)
@@ -892,14 +897,12 @@ __global__ void __launch_bounds__(kExecThreads) dec_exec_kernel(DecPass p)
             return litSrc[idx];
         };
         uint32_t const nbSeq = it.nbSeq;
-        const uint32_t* const aLL = p.seqLL + (size_t)item * kSeqCap;
-        const uint32_t* const aML = p.seqML + (size_t)item * kSeqCap;
-        const uint32_t* const aOF = p.seqOF + (size_t)item * kSeqCap;
+        const uint4* const aSeq = p.seq + (size_t)item * kSeqCap;
         uint32_t seqBase = 0, outPos = outBase, litPos = 0;
         while (seqBase < nbSeq) {
             uint32_t const n = seqBase + tid;
             uint32_t ll = 0, ml = 0, of = 0;
-            if (n < nbSeq) { ll = aLL[n]; ml = aML[n]; of = aOF[n]; }
+            if (n < nbSeq) { uint4 const r = aSeq[n]; ll = r.x; ml = r.y; of = r.z; }
             uint32_t totOut, totLit;
             uint32_t const oStart = block_exclusive_scan<uint32_t>(ll + ml, s_scanA, &totOut);   // tile-relative start of my literals
             uint32_t const lStart = block_exclusive_scan<uint32_t>(ll, s_scanB, &totLit);

@@ -5,7 +5,7 @@
 //   uint16_t     hufTable[n][4096]         single-symbol Huffman table, entry = byte<<8 | nbBits (HufDecompress.cs:80)
 //   uint32_t     fseTable[n][1280]         compact LL(512) | ML(512) | OF(256) sequence tables (ZstdDecompressBlock.cs:1571)
 //   uint8_t      litBuf[n][kLitStride]     regenerated literals, 4 segments each padded to 16 B
-//   uint32_t     seqLL/ML/OF[n][kSeqCap]   decoded (litLength, matchLength, offset) triples, struct-of-arrays
+//   uint4        seq[n][kSeqCap]           decoded (litLength, matchLength, offset, -) records, one 16-byte store each
 // Blocks of a frame are processed in "waves": wave k handles the k-th block of every item that still has one, so
 // repeat-mode tables, rep codes and the window carry over through the persistent per-item state.
 #pragma once
@@ -75,9 +75,7 @@ struct DecPass {
     uint16_t* hufTable;
     uint32_t* fseTable;
     uint8_t* litBuf;
-    uint32_t* seqLL;
-    uint32_t* seqML;
-    uint32_t* seqOF;
+    uint4* seq;             // decoded (litLength, matchLength, offset, -) records
     const uint32_t* defaultFse;  // predefined LL|ML|OF tables (ZstdDecompressBlock.cs:398/:857/:1092)
     uint32_t* hufList;      // item indices that need literal decoding this wave
     uint32_t* seqList;      // item indices that need sequence decoding this wave
