@@ -128,7 +128,7 @@ static bool decode_device(Engine& E, size_t n, const uint8_t* d_src, const uint6
         size_t const m = std::min(kMaxItemsPerPass, n - base);
         if (!E.dItems.ensure(m * sizeof(DecItem)) || !E.dInit.ensure(m * sizeof(DecItemInit)) || !E.hInit.ensure(m * sizeof(DecItemInit)) ||
             !E.dHuf.ensure(m * kHufTableEntries * 2) || !E.dFse.ensure(m * kFseTableEntries * 4) || !E.dLit.ensure(m * (size_t)kLitStride) ||
-            !E.dSeq.ensure(m * (size_t)kSeqCap * 16) ||
+            !E.dSeq.ensure(m * (size_t)kSeqCap * 8) ||
             !E.dDefaultFse.ensure(kFseTableEntries * 4) || !E.dHufList.ensure(m * 4) || !E.dSeqList.ensure(m * 4) ||
             !E.dCounters.ensure(64) || !E.hCounters.ensure(64) || !E.dResults.ensure(m * 8) || !E.hResults.ensure(m * 8))
             return false;
@@ -146,7 +146,7 @@ static bool decode_device(Engine& E, size_t n, const uint8_t* d_src, const uint6
         DecPass p;
         p.items = E.dItems.as<DecItem>(); p.nItems = (uint32_t)m; p.src = d_src; p.dst = d_dst;
         p.hufTable = E.dHuf.as<uint16_t>(); p.fseTable = E.dFse.as<uint32_t>(); p.litBuf = E.dLit.as<uint8_t>();
-        p.seq = E.dSeq.as<uint4>();
+        p.seq = E.dSeq.as<uint2>();
         p.defaultFse = E.dDefaultFse.as<uint32_t>(); p.hufList = E.dHufList.as<uint32_t>(); p.seqList = E.dSeqList.as<uint32_t>();
         p.counters = E.dCounters.as<uint32_t>(); p.results = E.dResults.as<uint64_t>();
         ZB_CUDA(cudaEventRecord(E.ev[0], E.stream));

@@ -761,7 +761,7 @@ __global__ void __launch_bounds__(32) dec_seq_kernel(DecPass p)
     const uint32_t* const tLL = s_seqTab + lane * kFseTableEntries + kFseLLOff;
     const uint32_t* const tML = s_seqTab + lane * kFseTableEntries + kFseMLOff;
     const uint32_t* const tOF = s_seqTab + lane * kFseTableEntries + kFseOFOff;
-    uint4* const oSeq = p.seq + (size_t)item * kSeqCap;
+    uint2* const oSeq = p.seq + (size_t)item * kSeqCap;
     const uint8_t* const src = p.src + it.srcOff;
     uint32_t const nbSeq = it.nbSeq;
     BitReader<kSeqRingWords> br;
@@ -815,9 +815,9 @@ __global__ void __launch_bounds__(32) dec_seq_kernel(DecPass p)
             // validity (ZSTD_execSequenceEnd order): output overflow, literal overrun, offset beyond frame start
             uint32_t const seqLen = ll + ml;
             bool const e1 = seqLen > dstCap - outPos, e2 = ll > litSize - litPos, e3 = offset > (outPos + ll) - frameStart;
-            bool const e4 = overRead | ((n + 1 < nbSeq) & (br.left < 0));
+            bool const e4 = overRead | ((n + 1 < nbSeq) & (br.left < 0)) | ((offset >> 30) != 0);   // offsets >= 1 GiB do not fit seq_pack
             if (e1 | e2 | e3 | e4) err = e1 ? kDstSizeTooSmall : kCorruptionDetected;
-            oSeq[n] = make_uint4(ll, ml, offset, 0u);
+            oSeq[n] = seq_pack(ll, ml, offset);
             outPos += seqLen; litPos += ll;
         }
         // the stream must not have unread bits left (BIT_reloadDStream >= completed, :2730)
@@ -831,169 +831,275 @@ __global__ void __launch_bounds__(32) dec_seq_kernel(DecPass p)
 }
 
 // =====================================================================================================
-//  Sequence execution + raw/RLE blocks: one CTA per item.
-//  Sequences are processed in batches whose regenerated bytes fit a shared-memory tile: literals and matches are
-//  assembled in the tile (matches that reach behind the tile read finished bytes from HBM/L2), dependent matches
-//  are resolved in rounds, then the tile is flushed with coalesced stores.  ZSTD_execSequence (:2187).
+//  Sequence execution + raw/RLE blocks: one warp per item (ZSTD_execSequence, ZstdDecompressBlock.cs:2187).
+//  All items of a batch are resident at once (up to 64 warps per SM), so there is no block-level barrier anywhere:
+//  the warp takes 32 sequences at a time (lane = sequence), a warp scan places them in a private shared-memory
+//  tile, literals and matches are copied lane-parallel, matches whose source lies inside the same batch wait for
+//  the lanes they depend on (rounds of ballots), long copies are taken over by the whole warp, and the tile is
+//  flushed to HBM with 16-byte stores whenever the next batch does not fit.  Match sources behind the tile are read
+//  back from HBM/L2 (they were flushed by this same warp earlier).
 // =====================================================================================================
-constexpr int kExecThreads = 256;
-constexpr uint32_t kTileBytes = 16384;
+constexpr int kExecWarps = 2;                       // items per CTA
+constexpr uint32_t kExecTileMem = 6656;             // shared memory per item; 32 warps x 6.5 KB (+1 KB reserved per CTA) = 224 KB per SM
+constexpr uint32_t kExecTile = kExecTileMem - 16;   // usable bytes (the tile starts at the 16-byte phase of its HBM address)
+constexpr uint32_t kExecLong = 40;                  // copies longer than this are done by the whole warp
 
-__device__ __forceinline__ uint32_t lit_addr(uint32_t idx, uint32_t seg, uint32_t pad)   // padded 4-segment literal layout
-{ uint32_t const s = (idx >= seg) + (idx >= 2 * seg) + (idx >= 3 * seg); return idx + s * pad; }
-
-template <typename T> __device__ __forceinline__ T block_exclusive_scan(T v, T* warpSums, T* total)
+__device__ __forceinline__ uint32_t warp_incl_scan(uint32_t v, uint32_t lane)
 {
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { uint32_t const o = __shfl_up_sync(0xFFFFFFFFu, v, d); if (lane >= (uint32_t)d) v += o; }
+    return v;
+}
+
+// forward copy of n bytes between two global buffers that do not overlap, any alignment, whole warp
+__device__ void warp_copy_g2g(uint8_t* dst, const uint8_t* src, uint32_t n, uint32_t lane)
+{
+    uint32_t const head = min(n, (uint32_t)((16 - ((uintptr_t)dst & 15)) & 15));
+    if (lane < head) dst[lane] = src[lane];
+    dst += head; src += head; n -= head;
+    uint32_t const m = (uint32_t)((uintptr_t)src & 3), sh = m * 8;
+    const uint32_t* const sw = (const uint32_t*)(src - m);
+    uint32_t const nChunks = n >> 4;
+    for (uint32_t c = lane; c < nChunks; c += 32) {
+        const uint32_t* const w = sw + 4 * c;
+        uint32_t const w0 = w[0], w1 = w[1], w2 = w[2], w3 = w[3], w4 = m ? w[4] : 0u;
+        uint4 v;
+        v.x = __funnelshift_r(w0, w1, sh); v.y = __funnelshift_r(w1, w2, sh); v.z = __funnelshift_r(w2, w3, sh); v.w = __funnelshift_r(w3, w4, sh);
+        *(uint4*)(dst + 16 * (size_t)c) = v;
+    }
+    uint32_t const done = nChunks << 4, rem = n - done;
+    if (lane < rem) dst[done + lane] = src[done + lane];
+}
+
+__device__ void warp_fill_g(uint8_t* dst, uint32_t byte, uint32_t n, uint32_t lane)
+{
+    uint32_t const head = min(n, (uint32_t)((16 - ((uintptr_t)dst & 15)) & 15));
+    if (lane < head) dst[lane] = (uint8_t)byte;
+    dst += head; n -= head;
+    uint32_t const w = byte * 0x01010101u; uint4 const v = make_uint4(w, w, w, w);
+    uint32_t const nChunks = n >> 4;
+    for (uint32_t c = lane; c < nChunks; c += 32) *(uint4*)(dst + 16 * (size_t)c) = v;
+    uint32_t const done = nChunks << 4, rem = n - done;
+    if (lane < rem) dst[done + lane] = (uint8_t)byte;
+}
+
+// tile (shared) -> HBM; tile and g have the same address modulo 16
+__device__ __forceinline__ void warp_flush_tile(uint8_t* g, const uint8_t* tile, uint32_t n, uint32_t lane)
+{
+    uint32_t const head = min(n, (uint32_t)((16 - ((uintptr_t)g & 15)) & 15));
+    if (lane < head) g[lane] = tile[lane];
+    g += head; tile += head; n -= head;
+    uint32_t const nChunks = n >> 4;
+    for (uint32_t c = lane; c < nChunks; c += 32) *(uint4*)(g + 16 * c) = *(const uint4*)(tile + 16 * c);
+    uint32_t const done = nChunks << 4, rem = n - done;
+    if (lane < rem) g[done + lane] = tile[done + lane];
+}
+
+// Literal source of a block: raw bytes inside the frame, one repeated byte, or the Huffman output (4 padded segments)
+struct LitSrc {
+    const uint8_t* base; uint32_t type, rle, seg, pad;
+    __device__ __forceinline__ uint32_t addr(uint32_t idx) const { uint32_t const s = (idx >= seg) + (idx >= 2 * seg) + (idx >= 3 * seg); return idx + s * pad; }
+    // literals [idx, idx+n) -> global memory, whole warp
+    __device__ void to_global(uint8_t* dst, uint32_t idx, uint32_t n, uint32_t lane) const {
+        if (type == kLitRle) { warp_fill_g(dst, rle, n, lane); return; }
+        while (n) {
+            uint32_t const s = (idx >= seg) + (idx >= 2 * seg) + (idx >= 3 * seg);
+            uint32_t const segEnd = s >= 3 ? 0xFFFFFFFFu : (s + 1) * seg;
+            uint32_t const m = min(n, segEnd - idx);
+            warp_copy_g2g(dst, base + idx + s * pad, m, lane);
+            dst += m; idx += m; n -= m;
+        }
+    }
+};
+
+__global__ void __launch_bounds__(kExecWarps * 32) dec_exec_kernel(DecPass p)
+{
+    extern __shared__ __align__(16) uint8_t s_exec[];
     uint32_t const lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    T incl = v;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) { T const o = __shfl_up_sync(0xFFFFFFFFu, incl, d); if (lane >= (uint32_t)d) incl += o; }
-    if (lane == 31) warpSums[warp] = incl;
-    __syncthreads();
-    T base = 0, tot = 0;
-#pragma unroll
-    for (int k = 0; k < kExecThreads / 32; k++) { T const s = warpSums[k]; if ((uint32_t)k < warp) base += s; tot += s; }
-    __syncthreads();
-    *total = tot;
-    return base + incl - v;
-}
-
-__device__ void cta_copy(uint8_t* dst, const uint8_t* src, uint32_t n)
-{
-    for (uint32_t i = threadIdx.x; i < n; i += kExecThreads) dst[i] = src[i];
-}
-
-__global__ void __launch_bounds__(kExecThreads) dec_exec_kernel(DecPass p)
-{
-    __shared__ __align__(16) uint8_t tile[kTileBytes];
-    __shared__ uint32_t s_scanA[kExecThreads / 32], s_scanB[kExecThreads / 32];
-    __shared__ uint32_t s_count, s_span, s_litSpan, s_big[3];
-    __shared__ uint32_t s_oStart[kExecThreads + 1], s_done[kExecThreads / 32];
-    uint32_t const item = blockIdx.x;
+    uint32_t const item = blockIdx.x * kExecWarps + warp;
+    if (item >= p.nItems) return;
     DecItem& it = p.items[item];
     if (it.status != kStRunning || it.blkType == kBlkNone) return;
     const uint8_t* const src = p.src + it.srcOff;
     uint8_t* const dst = p.dst + it.dstOff;
     uint32_t const outBase = it.outPos;
     uint32_t blockOut = 0;
-    uint32_t const tid = threadIdx.x;
+    uint32_t const FULL = 0xFFFFFFFFu;
 
     if (it.blkType == kBlkRaw) {
         blockOut = it.blkSize;
-        cta_copy(dst + outBase, src + it.blkSrcOff, blockOut);
+        warp_copy_g2g(dst + outBase, src + it.blkSrcOff, blockOut, lane);
     } else if (it.blkType == kBlkRle) {
         blockOut = it.blkSize;
-        uint8_t const b = src[it.blkSrcOff];
-        for (uint32_t i = tid; i < blockOut; i += kExecThreads) dst[outBase + i] = b;
+        warp_fill_g(dst + outBase, src[it.blkSrcOff], blockOut, lane);
     } else {
-        uint32_t const litType = it.litType, litSize = it.litSize;
-        uint32_t const seg = it.nStreams == 4 ? (litSize + 3) / 4 : 0xFFFFFFFFu;
-        uint32_t const pad = it.nStreams == 4 ? lit_segment_stride(litSize) - (litSize + 3) / 4 : 0;
-        const uint8_t* const litSrc = litType == kLitHuf ? p.litBuf + (size_t)item * kLitStride : src + it.litOff;
-        uint32_t const rleByte = litType == kLitRle ? src[it.litOff] : 0;
-        auto lit_at = [&](uint32_t idx) -> uint8_t {
-            if (litType == kLitRle) return (uint8_t)rleByte;
-            if (litType == kLitHuf) return litSrc[lit_addr(idx, seg, pad)];
-            return litSrc[idx];
-        };
+        uint8_t* const tileMem = s_exec + warp * kExecTileMem;
+        uint32_t const litSize = it.litSize;
+        LitSrc L;
+        L.type = it.litType;
+        bool const fourSeg = L.type == kLitHuf && it.nStreams == 4;      // only the Huffman output buffer is segmented
+        L.seg = fourSeg ? (litSize + 3) / 4 : 0x40000000u;
+        L.pad = fourSeg ? lit_segment_stride(litSize) - (litSize + 3) / 4 : 0;
+        L.base = L.type == kLitHuf ? p.litBuf + (size_t)item * kLitStride : src + it.litOff;
+        L.rle = L.type == kLitRle ? src[it.litOff] : 0;
         uint32_t const nbSeq = it.nbSeq;
-        const uint4* const aSeq = p.seq + (size_t)item * kSeqCap;
-        uint32_t seqBase = 0, outPos = outBase, litPos = 0;
+        const uint2* const aSeq = p.seq + (size_t)item * kSeqCap;
+        uint32_t seqBase = 0, litPos = 0;
+        uint32_t tileBase = outBase, fill = 0;                 // tile = output bytes [tileBase, tileBase + fill)
+        uint8_t* tile = tileMem + ((uintptr_t)(dst + tileBase) & 15);
+        uint2 rec = make_uint2(0u, 0u);
+        if (lane < nbSeq) rec = aSeq[lane];
         while (seqBase < nbSeq) {
-            uint32_t const n = seqBase + tid;
+            uint32_t const n = seqBase + lane;
             uint32_t ll = 0, ml = 0, of = 0;
-            if (n < nbSeq) { uint4 const r = aSeq[n]; ll = r.x; ml = r.y; of = r.z; }
-            uint32_t totOut, totLit;
-            uint32_t const oStart = block_exclusive_scan<uint32_t>(ll + ml, s_scanA, &totOut);   // tile-relative start of my literals
-            uint32_t const lStart = block_exclusive_scan<uint32_t>(ll, s_scanB, &totLit);
-            // how many sequences of this batch fit the tile?
-            if (tid == 0) s_count = 0;
-            __syncthreads();
-            bool const fits = (n < nbSeq) && (oStart + ll + ml <= kTileBytes);
-            if (fits) atomicMax(&s_count, tid + 1);
-            __syncthreads();
-            uint32_t const cnt = s_count;     // sequences [0, cnt) fit (prefix property: oStart is monotone)
-            if (cnt == 0) {
-                // a single sequence larger than the tile: copy it straight to HBM with the whole CTA
-                if (tid == 0) { s_big[0] = ll; s_big[1] = ml; s_big[2] = of; }
-                __syncthreads();
-                uint32_t const bl = s_big[0], bm = s_big[1], bo = s_big[2];
-                for (uint32_t i = tid; i < bl; i += kExecThreads) dst[outPos + i] = lit_at(litPos + i);
-                __syncthreads();
-                uint8_t* const md = dst + outPos + bl;
-                if (bo >= bm) { for (uint32_t i = tid; i < bm; i += kExecThreads) md[i] = md[(int64_t)i - bo]; }
-                else { for (uint32_t i = tid; i < bm; i += kExecThreads) md[i] = *(md - bo + (i % bo)); }   // periodic pattern
-                __syncthreads();
-                outPos += bl + bm; litPos += bl; seqBase += 1;
-                continue;
-            }
-            bool const mine = tid < cnt;
-            // publish the tile-relative start of every sequence (and the end of the last one) for dependency look-ups
-            if (mine) s_oStart[tid] = oStart; else if (tid > cnt) s_oStart[tid] = 0xFFFFFFFFu;
-            if (tid == cnt - 1) { s_span = oStart + ll + ml; s_litSpan = lStart + ll; s_oStart[cnt] = oStart + ll + ml; }
-            if (tid < kExecThreads / 32) s_done[tid] = 0;
-            // literals -> tile
-            if (mine) for (uint32_t k = 0; k < ll; k++) tile[oStart + k] = lit_at(litPos + lStart + k);
-            __syncthreads();
-            uint32_t const span = s_span;
-            // Matches.  Sequence s needs the non-self part of its source, tile range [a, b): every earlier sequence whose
-            // output intersects that range must be finished.  [jLo, jHi] = those sequences (binary search over the starts).
-            uint32_t const mDst = oStart + ll;                  // tile-relative
-            int64_t const srcRel = (int64_t)mDst - (int64_t)of; // may be negative: finished bytes behind the tile (HBM/L2)
-            uint32_t const nonSelf = of < ml ? of : ml;
-            bool pending = mine;
-            uint32_t jLo = 1, jHi = 0;                          // empty range = no dependency inside the tile
-            if (mine && srcRel + (int64_t)nonSelf > 0) {
-                uint32_t const a = srcRel > 0 ? (uint32_t)srcRel : 0u, b = (uint32_t)(srcRel + (int64_t)nonSelf);
-                // jLo = first j with end_j > a  (end_j = s_oStart[j+1]);  jHi = last j with start_j < b, clipped to tid-1
-                uint32_t lo = 0, hi = tid;                      // search in [0, tid)
-                while (lo < hi) { uint32_t const mid = (lo + hi) >> 1; if (s_oStart[mid + 1] > a) hi = mid; else lo = mid + 1; }
-                jLo = lo;
-                lo = 0; hi = tid;
-                while (lo < hi) { uint32_t const mid = (lo + hi) >> 1; if (s_oStart[mid] < b) lo = mid + 1; else hi = mid; }
-                jHi = lo ? lo - 1 : 0;
-                if (lo == 0 || jLo > jHi) { jLo = 1; jHi = 0; }
-            }
-            for (;;) {
-                bool ready = pending;
-                if (ready && jLo <= jHi) {
-                    // all bits jLo..jHi of the done mask must be set
-                    uint32_t const wLo = jLo >> 5, wHi = jHi >> 5;
-                    for (uint32_t wq = wLo; wq <= wHi && ready; wq++) {
-                        uint32_t need = 0xFFFFFFFFu;
-                        if (wq == wLo) need &= 0xFFFFFFFFu << (jLo & 31);
-                        if (wq == wHi) need &= 0xFFFFFFFFu >> (31 - (jHi & 31));
-                        if ((s_done[wq] & need) != need) ready = false;
+            if (n < nbSeq) seq_unpack(rec, ll, ml, of);
+            uint32_t const len = ll + ml;
+            uint32_t const oEnd = warp_incl_scan(len, lane), lEnd = warp_incl_scan(ll, lane);
+            uint32_t const oStart = oEnd - len, lStart = lEnd - ll;
+            uint32_t const fitMask = __ballot_sync(FULL, (n < nbSeq) && (fill + oEnd <= kExecTile));
+            uint32_t const take = fitMask == FULL ? 32u : (uint32_t)__ffs((int)~fitMask) - 1u;   // leading sequences that fit (oEnd is monotone)
+            if (take == 0) {
+                {
+                    // nothing fits: flush what we have, or (tile already empty) execute this one sequence straight in HBM
+                    if (fill) {
+                        warp_flush_tile(dst + tileBase, tile, fill, lane);
+                        tileBase += fill; fill = 0; tile = tileMem + ((uintptr_t)(dst + tileBase) & 15);
+                        __syncwarp();
+                        continue;
                     }
-                }
-                if (ready) {
-                    const uint8_t* const gsrc = dst + outPos;   // tile origin in HBM
-                    if (of >= ml) {
-                        for (uint32_t k = 0; k < ml; k++) { int64_t const sp = srcRel + (int64_t)k; tile[mDst + k] = sp >= 0 ? tile[sp] : gsrc[sp]; }
+                    uint32_t const bl = __shfl_sync(FULL, ll, 0), bm = __shfl_sync(FULL, ml, 0), bo = __shfl_sync(FULL, of, 0);
+                    __threadfence_block(); __syncwarp();
+                    L.to_global(dst + tileBase, litPos, bl, lane);
+                    __threadfence_block(); __syncwarp();
+                    uint8_t* const md = dst + tileBase + bl;
+                    if (bo >= 32 || bo >= bm) {
+                        for (uint32_t c = 0; c < bm; c += 32) {          // every 32-byte step only reads bytes finished before it
+                            uint32_t const k = c + lane;
+                            if (k < bm) md[k] = __ldcg(md + ((int64_t)k - (int64_t)bo));
+                            __threadfence_block(); __syncwarp();
+                        }
                     } else {
-                        uint32_t r = 0;                          // k % of without a division
-                        for (uint32_t k = 0; k < ml; k++) { int64_t const sp = srcRel + (int64_t)r; tile[mDst + k] = sp >= 0 ? tile[sp] : gsrc[sp]; if (++r == of) r = 0; }
+                        for (uint32_t k = lane; k < bm; k += 32) md[k] = __ldcg(md - bo + (k % bo));   // periodic pattern
+                    }
+                    __threadfence_block(); __syncwarp();
+                    tileBase += bl + bm; litPos += bl; seqBase += 1;
+                    tile = tileMem + ((uintptr_t)(dst + tileBase) & 15);
+                    rec = make_uint2(0u, 0u);
+                    if (seqBase + lane < nbSeq) rec = aSeq[seqBase + lane];
+                    continue;
+                }
+            }
+            bool const mine = lane < take;
+            // prefetch the next batch of records while this one is executed
+            uint2 recNext = make_uint2(0u, 0u);
+            if (seqBase + take + lane < nbSeq) recNext = aSeq[seqBase + take + lane];
+            uint32_t const span = __shfl_sync(FULL, oEnd, take - 1), litSpan = __shfl_sync(FULL, lEnd, take - 1);
+            // ---- literals -> tile ----
+            {
+                uint32_t const d0 = fill + oStart;
+                uint32_t longMask = __ballot_sync(FULL, mine && ll > kExecLong);
+                uint32_t const myLL = (mine && ll <= kExecLong) ? ll : 0u;
+                if (L.type == kLitRle) {
+                    for (uint32_t k = 0; k < myLL; k++) tile[d0 + k] = (uint8_t)L.rle;
+                } else {
+                    uint32_t idx = litPos + lStart;
+                    uint32_t const s = (idx >= L.seg) + (idx >= 2 * L.seg) + (idx >= 3 * L.seg);
+                    uint32_t a = idx + s * L.pad, nb = s >= 3 ? 0xFFFFFFFFu : (s + 1) * L.seg;
+                    for (uint32_t k = 0; k < myLL; k++) {
+                        tile[d0 + k] = __ldg(L.base + a);
+                        a++; idx++;
+                        if (idx == nb) { a += L.pad; nb += L.seg; }
                     }
                 }
-                __syncthreads();                                 // copies of this round are visible; done mask was only read so far
-                if (ready) { atomicOr(&s_done[tid >> 5], 1u << (tid & 31)); pending = false; }
-                if (!__syncthreads_or(pending)) break;
+                while (longMask) {
+                    uint32_t const j = (uint32_t)__ffs((int)longMask) - 1u; longMask &= longMask - 1;
+                    uint32_t const jl = __shfl_sync(FULL, ll, j), jd = __shfl_sync(FULL, d0, j), ji = __shfl_sync(FULL, litPos + lStart, j);
+                    if (L.type == kLitRle) { for (uint32_t k = lane; k < jl; k += 32) tile[jd + k] = (uint8_t)L.rle; }
+                    else { for (uint32_t k = lane; k < jl; k += 32) tile[jd + k] = __ldg(L.base + L.addr(ji + k)); }
+                }
             }
-            // flush tile
-            for (uint32_t i = tid; i < span; i += kExecThreads) dst[outPos + i] = tile[i];
-            uint32_t const litSpan = s_litSpan;
-            __syncthreads();
-            outPos += span; litPos += litSpan; seqBase += cnt;
+            __syncwarp();
+            // ---- matches ----
+            uint32_t const mDst = fill + oStart + ll;                    // tile-relative destination of my match
+            int32_t const srcRel = (int32_t)mDst - (int32_t)of;          // tile-relative source (negative: behind the tile, in HBM)
+            uint32_t const nonSelf = of < ml ? of : ml;
+            // lanes j < lane whose match output [mDst_j, oEnd_j) intersects my source [srcRel, srcRel + nonSelf)
+            uint32_t depMask = 0;
+            {
+                int32_t const a = srcRel, b = srcRel + (int32_t)nonSelf;
+                bool const inBatch = mine && ml && (b > (int32_t)fill);
+                if (__any_sync(FULL, inBatch)) {
+                    int32_t const myEnd = (int32_t)(fill + oEnd), myMD = (int32_t)mDst;
+                    // jLo = first j with end_j > a ; jHi = last j with mDst_j < b   (both sorted by lane)
+                    uint32_t lo = 0, hi = lane;
+#pragma unroll
+                    for (int stp = 0; stp < 5; stp++) {
+                        uint32_t const mid = (lo + hi) >> 1;
+                        int32_t const e = __shfl_sync(FULL, myEnd, mid & 31);
+                        if (lo < hi) { if (e > a) hi = mid; else lo = mid + 1; }
+                    }
+                    uint32_t const jLo = lo;
+                    lo = 0; hi = lane;
+#pragma unroll
+                    for (int stp = 0; stp < 5; stp++) {
+                        uint32_t const mid = (lo + hi) >> 1;
+                        int32_t const sft = __shfl_sync(FULL, myMD, mid & 31);
+                        if (lo < hi) { if (sft < b) lo = mid + 1; else hi = mid; }
+                    }
+                    // lo = number of lanes j < lane with mDst_j < b
+                    if (inBatch && lo > jLo) depMask = ((lo >= 32 ? 0u : (1u << lo)) - 1u) & ~((1u << jLo) - 1u);
+                }
+            }
+            uint32_t done = ~(take >= 32 ? FULL : ((1u << take) - 1u));   // lanes outside the batch count as finished
+            bool pending = mine;
+            if (mine && ml == 0) pending = false;
+            done |= __ballot_sync(FULL, mine && !pending);
+            while (__any_sync(FULL, pending)) {
+                bool const ready = pending && ((depMask & ~done) == 0);
+                bool const isLong = ready && ml > kExecLong;
+                if (ready && !isLong) {
+                    const uint8_t* const gsrc = dst + tileBase;            // tile origin in HBM
+                    uint32_t k = 0;
+                    if (srcRel < 0) {
+                        uint32_t const k0 = min(ml, (uint32_t)(-srcRel));
+                        for (; k < k0; k++) tile[mDst + k] = gsrc[srcRel + (int32_t)k];
+                    }
+                    volatile uint8_t* const vt = tile;                   // overlapping matches read bytes this lane wrote
+                    for (; k < ml; k++) vt[mDst + k] = vt[(uint32_t)(srcRel + (int32_t)k)];
+                }
+                uint32_t longMask = __ballot_sync(FULL, isLong);
+                while (longMask) {
+                    uint32_t const j = (uint32_t)__ffs((int)longMask) - 1u; longMask &= longMask - 1;
+                    uint32_t const jm = __shfl_sync(FULL, ml, j), jo = __shfl_sync(FULL, of, j), jd = __shfl_sync(FULL, mDst, j);
+                    int32_t const js = __shfl_sync(FULL, srcRel, j);
+                    const uint8_t* const gsrc = dst + tileBase;
+                    if (jo >= 32 || jo >= jm) {
+                        for (uint32_t c = 0; c < jm; c += 32) {
+                            uint32_t const k = c + lane;
+                            if (k < jm) { int32_t const sp = js + (int32_t)k; tile[jd + k] = sp >= 0 ? tile[sp] : gsrc[sp]; }
+                            __syncwarp();
+                        }
+                    } else {
+                        for (uint32_t k = lane; k < jm; k += 32) { int32_t const sp = js + (int32_t)(k % jo); tile[jd + k] = sp >= 0 ? tile[sp] : gsrc[sp]; }
+                    }
+                }
+                __syncwarp();
+                done |= __ballot_sync(FULL, ready);
+                if (ready) pending = false;
+            }
+            fill += span; litPos += litSpan; seqBase += take;
+            rec = recNext;
         }
-        // last literals (ZstdDecompressBlock.cs:2748-2760)
+        // flush, then the last literals go straight to HBM (ZstdDecompressBlock.cs:2748-2760)
+        __syncwarp();
+        if (fill) { warp_flush_tile(dst + tileBase, tile, fill, lane); tileBase += fill; }
         uint32_t const lastLL = litSize - litPos;
-        for (uint32_t i = tid; i < lastLL; i += kExecThreads) dst[outPos + i] = lit_at(litPos + i);
-        outPos += lastLL;
-        blockOut = outPos - outBase;
+        L.to_global(dst + tileBase, litPos, lastLL, lane);
+        blockOut = tileBase + lastLL - outBase;
     }
-    __syncthreads();
+    __syncwarp();
     // ---- end of block bookkeeping (ZSTD_decompressFrame loop tail, ZstdDecompress.cs:1156-1212) ----
-    if (tid == 0) {
+    if (lane == 0) {
         it.outPos = outBase + blockOut;
         if (it.lastBlock) {
             uint32_t err = 0;
@@ -1034,6 +1140,8 @@ static void dec_set_attrs()
     if (dev < 0 || dev >= 64 || done[dev]) return;
     cudaFuncSetAttribute(dec_huf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kHufSmemBytes);
     cudaFuncSetAttribute(dec_seq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSeqSmemBytes);
+    cudaFuncSetAttribute(dec_exec_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kExecWarps * kExecTileMem);
+    cudaFuncSetAttribute(dec_exec_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
     done[dev] = true;
 }
 
@@ -1044,7 +1152,7 @@ void dec_launch_wave(const DecPass& p, cudaStream_t s)
     dec_set_attrs();
     dec_huf_kernel<<<(p.nItems + kHufItemsPerCta - 1) / kHufItemsPerCta, kHufThreads, kHufSmemBytes, s>>>(p);
     dec_seq_kernel<<<(p.nItems + kSeqItemsPerCta - 1) / kSeqItemsPerCta, 32, kSeqSmemBytes, s>>>(p);
-    dec_exec_kernel<<<p.nItems, kExecThreads, 0, s>>>(p);
+    dec_exec_kernel<<<(p.nItems + kExecWarps - 1) / kExecWarps, kExecWarps * 32, kExecWarps * kExecTileMem, s>>>(p);
 }
 
 void dec_launch_wave_timed(const DecPass& p, cudaStream_t s, cudaEvent_t* ev)
@@ -1058,7 +1166,7 @@ void dec_launch_wave_timed(const DecPass& p, cudaStream_t s, cudaEvent_t* ev)
     cudaEventRecord(ev[2], s);
     dec_seq_kernel<<<(p.nItems + kSeqItemsPerCta - 1) / kSeqItemsPerCta, 32, kSeqSmemBytes, s>>>(p);
     cudaEventRecord(ev[3], s);
-    dec_exec_kernel<<<p.nItems, kExecThreads, 0, s>>>(p);
+    dec_exec_kernel<<<(p.nItems + kExecWarps - 1) / kExecWarps, kExecWarps * 32, kExecWarps * kExecTileMem, s>>>(p);
     cudaEventRecord(ev[4], s);
 }
 

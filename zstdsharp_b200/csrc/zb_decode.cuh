@@ -5,7 +5,7 @@
 //   uint16_t     hufTable[n][4096]         single-symbol Huffman table, entry = byte<<8 | nbBits (HufDecompress.cs:80)
 //   uint32_t     fseTable[n][1280]         compact LL(512) | ML(512) | OF(256) sequence tables (ZstdDecompressBlock.cs:1571)
 //   uint8_t      litBuf[n][kLitStride]     regenerated literals, 4 segments each padded to 16 B
-//   uint4        seq[n][kSeqCap]           decoded (litLength, matchLength, offset, -) records, one 16-byte store each
+//   uint2        seq[n][kSeqCap]           decoded (litLength, matchLength, offset) records packed into 8 bytes
 // Blocks of a frame are processed in "waves": wave k handles the k-th block of every item that still has one, so
 // repeat-mode tables, rep codes and the window carry over through the persistent per-item state.
 #pragma once
@@ -24,6 +24,13 @@ enum : uint32_t { kLitRaw = 0, kLitRle = 1, kLitHuf = 2 };
 // Compact FSE decode entry: [0,4) nbBits | [4,9) nbAdditionalBits | [9,15) symbol | [16,26) nextState base
 __host__ __device__ inline uint32_t fse_pack(uint32_t nbBits, uint32_t addBits, uint32_t sym, uint32_t next)
 { return nbBits | (addBits << 4) | (sym << 9) | (next << 16); }
+
+// One decoded sequence in 8 bytes: litLength (17 bits) | matchLength-3 (17 bits) | offset (30 bits).  The sequence
+// decoder rejects values outside these ranges (they cannot occur in a block that regenerates <= 128 KiB of a frame < 1 GiB).
+__host__ __device__ inline uint2 seq_pack(uint32_t ll, uint32_t ml, uint32_t of)
+{ uint32_t const m = ml - 3; uint2 r; r.x = ll | (m << 17); r.y = (m >> 15) | (of << 2); return r; }
+__host__ __device__ inline void seq_unpack(uint2 r, uint32_t& ll, uint32_t& ml, uint32_t& of)
+{ ll = r.x & 0x1FFFFu; ml = ((r.x >> 17) | ((r.y & 3u) << 15)) + 3u; of = r.y >> 2; }
 
 struct __align__(16) DecItem {
     // ---- static for the pass ----
@@ -75,7 +82,7 @@ struct DecPass {
     uint16_t* hufTable;
     uint32_t* fseTable;
     uint8_t* litBuf;
-    uint4* seq;             // decoded (litLength, matchLength, offset, -) records
+    uint2* seq;             // decoded sequences, packed by seq_pack()
     const uint32_t* defaultFse;  // predefined LL|ML|OF tables (ZstdDecompressBlock.cs:398/:857/:1092)
     uint32_t* hufList;      // item indices that need literal decoding this wave
     uint32_t* seqList;      // item indices that need sequence decoding this wave
