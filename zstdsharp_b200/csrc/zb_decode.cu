@@ -561,108 +561,112 @@ __global__ void __launch_bounds__(kSetupWarps * 32) dec_setup_kernel(DecPass p)
 }
 
 // =====================================================================================================
-//  Backward bit reader.  The stream is staged through a small per-lane shared-memory ring that is filled with
-//  cp.async (LDGSTS) one chunk ahead, so the decode loops never wait on an HBM/L2 round trip: with 32 lanes
-//  refilling at different times, a register-prefetched word made the whole warp stall at nearly every refill
-//  (profiles/r01_notes.md).  Semantics of BIT_DStream_t (Bitstream.cs:172-425) for well-formed streams;
-//  over-reads are tracked in `left`.
+//  Backward bit reader (semantics of BIT_DStream_t, Bitstream.cs:172-425, for the hot loops).
+//  A stream is consumed from its last byte downwards.  It is staged through a private shared-memory ring of four
+//  chunks that mirrors the low bits of the global address (ring byte = global byte mod 4*CH) and is filled with
+//  cp.async two chunks ahead, so the decode loops never wait on HBM/L2.  The reader state is one integer: G, the
+//  bit address (relative to the ring-aligned base) just above the next unread bit.  A read is two shared loads and
+//  one funnel shift, with no branch: that keeps every lane of a warp on the same instruction stream, which is
+//  what bounds these latency-limited kernels (profiles/r01_notes.md).
 // =====================================================================================================
 __device__ __forceinline__ uint32_t lds32(uint32_t saddr) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(saddr)); return v; }
 __device__ __forceinline__ uint32_t lds16(uint32_t saddr) { uint16_t v; asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(saddr)); return v; }
 
-template <int H>           // words per chunk (chunk CH = 4*H bytes); the ring holds 2 chunks and is aligned to 2*CH bytes
-struct BitReader {
-    // 96-bit register window over the stream, most significant word first; `off` bits of w0 are already consumed.
-    // Fields are cut out with funnel shifts; the refill reads the private shared-memory ring through a 32-bit shared
-    // address that mirrors the low bits of the global address (ring byte = global byte mod 2*CH), so walking down the
-    // stream is one subtract-and-mask and chunk switches (1 in H refills) are the only place that touches cp.async.
-    static constexpr uint32_t CH = 4 * H;
-    uint32_t w0, w1, w2;
-    uint32_t off;          // 0..31 after normalize()
-    int32_t left;          // unread bits of the stream (negative = over-read)
-    uint32_t rp;           // shared address of the next word to fetch
-    const uint8_t* gnext;  // next global chunk to stage
-    const uint8_t* lowest; // lowest chunk that may be staged (contains the first byte of the item)
+template <uint32_t CH>     // chunk bytes (power of two >= 64); ring = 4 chunks, aligned to 4*CH in shared memory
+struct BitRing {
+    static constexpr uint32_t RB = 4 * CH, MASK = RB - 1;
+    uint32_t sbase;         // shared address of the ring
+    const uint8_t* gbase;   // global address of chunk 0 (multiple of RB)
+    int32_t cur;            // chunk that holds the next unread bit
+    int32_t cLow;           // lowest chunk that may be staged (holds the first byte of the stream)
+    uint32_t gZero;         // G of "no unread bits left" (= 8 * offset of the first stream byte from gbase)
 
-    static __device__ __forceinline__ void fetch(uint32_t sa, const uint8_t* g) {
+    __device__ __forceinline__ void fetch(int32_t c) const {
+        if (c >= cLow) {
+            uint32_t const sa = sbase + (((uint32_t)c * CH) & MASK);
+            const uint8_t* const g = gbase + (size_t)(uint32_t)c * CH;
 #pragma unroll
-        for (uint32_t i = 0; i < CH / 16; i++) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa + 16 * i), "l"(g + 16 * i));
+            for (uint32_t i = 0; i < CH / 16; i++) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa + 16 * i), "l"(g + 16 * i));
+        }
         asm volatile("cp.async.commit_group;");
     }
-    static __device__ __forceinline__ void wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
-
-    __device__ __forceinline__ uint32_t next_word() {
-        uint32_t const v = lds32(rp);
-        if ((rp & (CH - 1)) == 0) {          // lowest word of a chunk consumed: the other half must have landed; restage this half
-            wait_all();
-            if (gnext >= lowest) fetch(rp, gnext);
-            gnext -= CH;
+    // Returns G of the stream start (top), or 0 when the last byte is zero (no end mark: corruption).
+    __device__ __forceinline__ uint32_t init(uint32_t ringShared, const uint8_t* first, uint32_t len) {
+        sbase = ringShared;
+        uintptr_t const a0 = (uintptr_t)first;
+        gbase = (const uint8_t*)(a0 & ~(uintptr_t)MASK);
+        uint32_t const rel = (uint32_t)(a0 & MASK);
+        gZero = rel * 8;
+        cLow = (int32_t)(rel / CH);
+        uint32_t const lastByte = first[len - 1];
+        if (lastByte == 0) return 0;
+        uint32_t const G = gZero + (len - 1) * 8 + highbit32(lastByte);
+        cur = (int32_t)((G - 1) >> 3) / (int32_t)CH;
+        fetch(cur); fetch(cur - 1); fetch(cur - 2);
+        asm volatile("cp.async.wait_group 1;" ::: "memory");      // cur and cur-1 have landed; cur-2 may still be in flight
+        return G;
+    }
+    // Call once per step (a step consumes < CH bytes): when the read position entered a new chunk, the chunk below it
+    // has landed (it was requested one chunk ago) and the chunk two below is requested into the slot that became free.
+    __device__ __forceinline__ void advance(uint32_t G) {
+        int32_t const c = (int32_t)(G - 1) >> (3 + __builtin_ctz(CH));
+        if (c != cur) {
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+            cur = c;
+            fetch(c - 2);
         }
-        rp = (rp & ~(2 * CH - 1)) | ((rp - 4) & (2 * CH - 1));
-        return v;
     }
-    __device__ __forceinline__ bool init(uint32_t* ringS, const uint8_t* itemBase, uint32_t offB, uint32_t len) {
-        uint32_t const R = (uint32_t)__cvta_generic_to_shared(ringS);
-        const uint8_t* const last = itemBase + offB + len - 1;
-        uintptr_t const a = (uintptr_t)last;
-        const uint8_t* const c = (const uint8_t*)(a & ~(uintptr_t)(CH - 1));
-        lowest = (const uint8_t*)((uintptr_t)itemBase & ~(uintptr_t)(CH - 1));
-        fetch(R + (uint32_t)((uintptr_t)c & (2 * CH - 1)), c);
-        if (c - CH >= lowest) fetch(R + (uint32_t)((uintptr_t)(c - CH) & (2 * CH - 1)), c - CH);
-        gnext = c - 2 * CH;
-        wait_all();
-        rp = R + (uint32_t)(a & (2 * CH - 1) & ~(uintptr_t)3);
-        uint32_t const v = next_word();
-        uint32_t const lastByte = (v >> ((a & 3) * 8)) & 0xFF;
-        w0 = v; w1 = next_word(); w2 = next_word();
-        if (lastByte == 0) { off = 0; left = 0; return false; }
-        uint32_t const hb = highbit32(lastByte);
-        left = (int32_t)((len - 1) * 8 + hb);
-        off = 32 - ((uint32_t)(a & 3) * 8 + hb);       // everything from the end mark upwards is "consumed"
-        normalize();
-        return true;
+    // the next 32 unread bits below G, left-justified (bits beyond them are garbage-free: they come from the stream)
+    __device__ __forceinline__ uint32_t peek32(uint32_t G) const {
+        uint32_t const o = ((G - 1) >> 3) & (MASK & ~3u);
+        uint32_t const hi = lds32(sbase + o), lo = lds32(sbase + ((o - 4) & MASK));
+        return __funnelshift_l(lo, hi, 0u - G);
     }
-    __device__ __forceinline__ void normalize() { if (off >= 32) { off -= 32; w0 = w1; w1 = w2; w2 = next_word(); } }
-    // nb bits starting `o` bits below the top of w0; o in [0,31], nb in [0,31]
-    __device__ __forceinline__ uint32_t field_lo(uint32_t o, uint32_t nb) const { return (__funnelshift_l(w1, w0, o) >> 1) >> (31 - nb); }
-    // same for o in [0,63]
-    __device__ __forceinline__ uint32_t field(uint32_t o, uint32_t nb) const {
-        uint32_t const a = __funnelshift_l(w1, w0, o), b = __funnelshift_l(w2, w1, o);
-        return ((o < 32 ? a : b) >> 1) >> (31 - nb);
+    // the next 64 unread bits below G, left-justified in (x0:x1)
+    __device__ __forceinline__ void peek64(uint32_t G, uint32_t& x0, uint32_t& x1) const {
+        uint32_t const o = ((G - 1) >> 3) & (MASK & ~3u);
+        uint32_t const w0 = lds32(sbase + o), w1 = lds32(sbase + ((o - 4) & MASK)), w2 = lds32(sbase + ((o - 8) & MASK));
+        x0 = __funnelshift_l(w1, w0, 0u - G); x1 = __funnelshift_l(w2, w1, 0u - G);
     }
-    __device__ __forceinline__ void consume(uint32_t nb) { off += nb; left -= (int32_t)nb; }
-    __device__ __forceinline__ uint32_t read(uint32_t nb) { uint32_t const v = field_lo(off, nb); consume(nb); normalize(); return v; }
 };
+// top `nb` bits (0..31) of a left-justified word
+__device__ __forceinline__ uint32_t top_bits(uint32_t x, uint32_t nb) { return (x >> 1) >> (31 - nb); }
 
 // =====================================================================================================
-//  Huffman literal decoding: one lane per stream, 16 items (64 streams) per CTA, tables in shared memory.
+//  Huffman literal decoding: one lane per stream, 16 items (64 streams) per CTA.
 //  HUF_decompress4X1_usingDTable_internal_body / HUF_decodeStreamX1 (HufDecompress.cs:342, :264)
+//  Shared memory holds a first-level table of min(tableLog, 10) bits per item (2 KB), so that every item of a
+//  8192-frame batch is resident at once (5 CTAs x 40 KB per SM); codes of 11 or 12 bits (rare symbols) escape to the
+//  full table in HBM, which stays L1-resident because only a few of its lines are ever touched.
 // =====================================================================================================
 constexpr int kHufItemsPerCta = 16;
 constexpr int kHufThreads = kHufItemsPerCta * 4;
-constexpr uint32_t kHufSmemEntries = 2048;     // tables with tableLog <= 11 are staged; log-12 tables are read from HBM/L2
-constexpr int kHufRingWords = 16;              // 64-byte chunks, 128 B of ring per stream
-constexpr uint32_t kHufSmemBytes = kHufItemsPerCta * kHufSmemEntries * 2 + kHufThreads * 2 * kHufRingWords * 4;
+constexpr uint32_t kHufL1Log = 10;
+constexpr uint32_t kHufSmemEntries = 1u << kHufL1Log;
+constexpr uint32_t kHufChunk = 64;              // 4 x 64 B of ring per stream
+constexpr uint32_t kHufSmemBytes = kHufItemsPerCta * kHufSmemEntries * 2 + kHufThreads * 4 * kHufChunk;
 
 __device__ __forceinline__ uint32_t lit_segment_stride(uint32_t litSize) { uint32_t const seg = (litSize + 3) / 4; return (seg + 15) & ~15u; }
 
 __global__ void __launch_bounds__(kHufThreads) dec_huf_kernel(DecPass p)
 {
-    extern __shared__ __align__(256) uint16_t s_tab[];       // [kHufItemsPerCta][2048] tables, then [kHufThreads][2*kHufRingWords] stream rings
-    uint32_t* const s_ring = (uint32_t*)(s_tab + kHufItemsPerCta * kHufSmemEntries) + threadIdx.x * (2 * kHufRingWords);
+    extern __shared__ __align__(256) uint8_t s_huf_raw[];    // [kHufThreads] rings of 256 B, then [kHufItemsPerCta][1024] first-level tables
+    uint16_t* const s_tab = (uint16_t*)(s_huf_raw + kHufThreads * 4 * kHufChunk);
     uint32_t const nWork = p.counters[0];
     uint32_t const first = blockIdx.x * kHufItemsPerCta;
     if (first >= nWork) return;
     uint32_t const nHere = min((uint32_t)kHufItemsPerCta, nWork - first);
-    // stage tables (coalesced 16-byte copies)
     for (uint32_t k = 0; k < nHere; k++) {
         uint32_t const item = p.hufList[first + k];
         uint32_t const log = p.items[item].hufLog;
-        if (log <= 11) {
-            const uint4* g = (const uint4*)(p.hufTable + (size_t)item * kHufTableEntries);
-            uint4* s = (uint4*)(s_tab + k * kHufSmemEntries);
+        const uint16_t* const g = p.hufTable + (size_t)item * kHufTableEntries;
+        uint16_t* const st = s_tab + k * kHufSmemEntries;
+        if (log <= kHufL1Log) {
             uint32_t const n16 = ((1u << log) * 2 + 15) / 16;
-            for (uint32_t u = threadIdx.x; u < n16; u += kHufThreads) s[u] = g[u];
+            for (uint32_t u = threadIdx.x; u < n16; u += kHufThreads) ((uint4*)st)[u] = ((const uint4*)g)[u];
+        } else {
+            uint32_t const sh = log - kHufL1Log;            // a code of <= 10 bits fills the whole aligned group: its first cell decides
+            for (uint32_t u = threadIdx.x; u < kHufSmemEntries; u += kHufThreads) st[u] = g[u << sh];
         }
     }
     __syncthreads();
@@ -678,51 +682,48 @@ __global__ void __launch_bounds__(kHufThreads) dec_huf_kernel(DecPass p)
     uint32_t count, outOff;
     if (nStreams == 1) { count = litSize; outOff = 0; }
     else { count = stream < 3 ? seg : litSize - 3 * seg; outOff = stream * lit_segment_stride(litSize); }
-    uint8_t* out = p.litBuf + (size_t)item * kLitStride + outOff;
+    uint8_t* const out = p.litBuf + (size_t)item * kLitStride + outOff;
     const uint8_t* const src = p.src + it.srcOff;
-    BitReader<kHufRingWords> br;
-    bool ok = br.init(s_ring, src, it.streamOff[stream], it.streamLen[stream]);
+    BitRing<kHufChunk> br;
+    uint32_t G = br.init((uint32_t)__cvta_generic_to_shared(s_huf_raw) + threadIdx.x * (4 * kHufChunk), src + it.streamOff[stream], it.streamLen[stream]);
+    bool ok = G != 0;
     if (ok) {
-        uint32_t const sh = 32 - log;
+        uint32_t const l1 = log < kHufL1Log ? log : kHufL1Log;
+        uint32_t const sh1 = 32 - l1, shF = 32 - log;
+        uint32_t const tabS = (uint32_t)__cvta_generic_to_shared(s_tab + slot * kHufSmemEntries);
+        const uint16_t* const gtab = p.hufTable + (size_t)item * kHufTableEntries;
+        int32_t const gz = (int32_t)br.gZero;
         uint32_t i = 0;
-        if (log <= 11) {
-            uint32_t const tabS = (uint32_t)__cvta_generic_to_shared(s_tab + slot * kHufSmemEntries);
-            // 16 symbols -> one 16-byte store (out is 16-byte aligned by construction)
-            for (; i + 16 <= count && br.left >= 0; i += 16) {
-                uint32_t v[4];
+        // 16 symbols -> one 16-byte store (out is 16-byte aligned by construction); 4 symbols (<= 48 bits) per window refill
+        for (; i + 16 <= count && (int32_t)G >= gz; i += 16) {
+            br.advance(G);
+            uint32_t v[4];
 #pragma unroll
-                for (int q = 0; q < 4; q++) {
-                    uint32_t acc = 0;
+            for (int q = 0; q < 4; q++) {
+                uint32_t x0, x1; br.peek64(G, x0, x1);
+                uint32_t acc = 0, used = 0;
 #pragma unroll
-                    for (int r = 0; r < 4; r++) {
-                        uint32_t const idx = __funnelshift_l(br.w1, br.w0, br.off) >> sh;
-                        uint32_t const e = lds16(tabS + idx * 2);
-                        br.consume(e & 0xFF);
-                        br.normalize();
-                        acc |= (e >> 8) << (8 * r);
-                    }
-                    v[q] = acc;
+                for (int r = 0; r < 4; r++) {
+                    uint32_t e = lds16(tabS + (x0 >> sh1) * 2);
+                    if ((e & 0xFF) > kHufL1Log) e = __ldg(gtab + (x0 >> shF));
+                    uint32_t const nb = e & 0xFF;
+                    x0 = __funnelshift_l(x1, x0, nb); x1 <<= nb; used += nb;
+                    acc |= (e >> 8) << (8 * r);
                 }
-                *(uint4*)(out + i) = make_uint4(v[0], v[1], v[2], v[3]);
+                G -= used;
+                v[q] = acc;
             }
-            for (; i < count && br.left >= 0; i++) {
-                uint32_t const idx = __funnelshift_l(br.w1, br.w0, br.off) >> sh;
-                uint32_t const e = lds16(tabS + idx * 2);
-                br.consume(e & 0xFF);
-                br.normalize();
-                out[i] = (uint8_t)(e >> 8);
-            }
-        } else {                                   // tableLog 12: the table stays in HBM/L2 (rare: zstd encoders cap at 11)
-            const uint16_t* const gtab = p.hufTable + (size_t)item * kHufTableEntries;
-            for (; i < count && br.left >= 0; i++) {
-                uint32_t const idx = __funnelshift_l(br.w1, br.w0, br.off) >> sh;
-                uint32_t const e = gtab[idx];
-                br.consume(e & 0xFF);
-                br.normalize();
-                out[i] = (uint8_t)(e >> 8);
-            }
+            *(uint4*)(out + i) = make_uint4(v[0], v[1], v[2], v[3]);
         }
-        ok = (br.left == 0) && (i == count);      // BIT_endOfDStream: the stream must be consumed exactly (:526-533)
+        for (; i < count && (int32_t)G >= gz; i++) {
+            br.advance(G);
+            uint32_t const x0 = br.peek32(G);
+            uint32_t e = lds16(tabS + (x0 >> sh1) * 2);
+            if ((e & 0xFF) > kHufL1Log) e = __ldg(gtab + (x0 >> shF));
+            G -= e & 0xFF;
+            out[i] = (uint8_t)(e >> 8);
+        }
+        ok = ((int32_t)G == gz) && (i == count);      // BIT_endOfDStream: the stream must be consumed exactly (:526-533)
     }
     if (!ok) { it.errCode = kCorruptionDetected; it.status = kStError; }
 }
@@ -731,15 +732,18 @@ __global__ void __launch_bounds__(kHufThreads) dec_huf_kernel(DecPass p)
 //  Sequence decoding: one lane per item; LL/ML/OF tables staged in shared memory (5 KB per item).
 //  ZSTD_decompressSequences_body / ZSTD_decodeSequence (ZstdDecompressBlock.cs:2668, :2360) incl. the checks of
 //  ZSTD_execSequenceEnd (:2083-2103), so that the exec kernel can copy without re-validating.
+//  One step = three table loads, three bit-group reads (offset extra | matchLength+litLength extra | the three
+//  state updates: each group is <= 32 bits), all branch-free.
 // =====================================================================================================
 constexpr int kSeqItemsPerCta = 10;            // 10 x (5 KB tables + 256 B ring) -> 4 CTAs (40 items) per SM
-constexpr int kSeqRingWords = 32;              // 128-byte chunks, 256 B of ring per item
-constexpr uint32_t kSeqSmemBytes = kSeqItemsPerCta * (kFseTableEntries + 2 * kSeqRingWords) * 4;
+constexpr uint32_t kSeqChunk = 64;             // 4 x 64 B of ring per item
+constexpr uint32_t kSeqSmemBytes = kSeqItemsPerCta * (kFseTableEntries * 4 + 4 * kSeqChunk);
 
 __global__ void __launch_bounds__(32) dec_seq_kernel(DecPass p)
 {
-    extern __shared__ __align__(256) uint32_t s_seqTab[];   // [kSeqItemsPerCta][kFseTableEntries] tables, then [kSeqItemsPerCta][2*kSeqRingWords] rings
-    __shared__ uint32_t s_llBase[36], s_mlBase[53];
+    extern __shared__ __align__(256) uint8_t s_seq_raw[];   // [kSeqItemsPerCta] rings of 256 B, then [kSeqItemsPerCta][kFseTableEntries] tables
+    uint32_t* const s_seqTab = (uint32_t*)(s_seq_raw + kSeqItemsPerCta * 4 * kSeqChunk);
+    __shared__ uint32_t s_llBase[64], s_mlBase[64];
     uint32_t const nWork = p.counters[1];
     uint32_t const first = blockIdx.x * kSeqItemsPerCta;
     if (first >= nWork) return;
@@ -751,77 +755,80 @@ __global__ void __launch_bounds__(32) dec_seq_kernel(DecPass p)
         uint4* s = (uint4*)(s_seqTab + k * kFseTableEntries);
         for (uint32_t u = lane; u < kFseTableEntries / 4; u += 32) s[u] = g[u];
     }
-    for (uint32_t u = lane; u < 36; u += 32) s_llBase[u] = c_LL_base[u];
-    for (uint32_t u = lane; u < 53; u += 32) s_mlBase[u] = c_ML_base[u];
+    for (uint32_t u = lane; u < 64; u += 32) { s_llBase[u] = u < 36 ? c_LL_base[u] : 0u; s_mlBase[u] = u < 53 ? c_ML_base[u] : 0u; }
     __syncwarp();
     if (lane >= nHere) return;
     uint32_t const item = p.seqList[first + lane];
     DecItem& it = p.items[item];
     if (it.status != kStRunning) return;
-    const uint32_t* const tLL = s_seqTab + lane * kFseTableEntries + kFseLLOff;
-    const uint32_t* const tML = s_seqTab + lane * kFseTableEntries + kFseMLOff;
-    const uint32_t* const tOF = s_seqTab + lane * kFseTableEntries + kFseOFOff;
+    uint32_t const tS = (uint32_t)__cvta_generic_to_shared(s_seqTab + lane * kFseTableEntries);
+    uint32_t const tLL = tS + kFseLLOff * 4, tML = tS + kFseMLOff * 4, tOF = tS + kFseOFOff * 4;
+    uint32_t const llBaseS = (uint32_t)__cvta_generic_to_shared(s_llBase), mlBaseS = (uint32_t)__cvta_generic_to_shared(s_mlBase);
     uint2* const oSeq = p.seq + (size_t)item * kSeqCap;
     const uint8_t* const src = p.src + it.srcOff;
     uint32_t const nbSeq = it.nbSeq;
-    BitReader<kSeqRingWords> br;
+    BitRing<kSeqChunk> br;
     uint32_t err = 0;
-    if (!br.init(s_seqTab + kSeqItemsPerCta * kFseTableEntries + lane * (2 * kSeqRingWords), src, it.seqOff, it.seqLen)) err = kCorruptionDetected;
+    uint32_t G = br.init((uint32_t)__cvta_generic_to_shared(s_seq_raw) + lane * (4 * kSeqChunk), src + it.seqOff, it.seqLen);
+    if (G == 0) err = kCorruptionDetected;
+    int32_t const gz = (int32_t)br.gZero;
     uint32_t rep0 = it.rep[0], rep1 = it.rep[1], rep2 = it.rep[2];
     uint32_t outPos = it.outPos; uint32_t const frameStart = it.frameStart, dstCap = it.dstCap;
     uint32_t litPos = 0; uint32_t const litSize = it.litSize;
     if (!err) {
-        uint32_t sL = br.read(it.llLog);
-        uint32_t sO = br.read(it.ofLog);
-        uint32_t sM = br.read(it.mlLog);
-        if (br.left < 0) err = kCorruptionDetected;
+        // ZSTD_initFseState x3 in the order LL, OF, ML (:2702-2704)
+        uint32_t const llLog = it.llLog, ofLog = it.ofLog, mlLog = it.mlLog;
+        uint32_t x = br.peek32(G);
+        uint32_t aL = tLL + top_bits(x, llLog) * 4; x <<= llLog;
+        uint32_t aO = tOF + top_bits(x, ofLog) * 4; x <<= ofLog;
+        uint32_t aM = tML + top_bits(x, mlLog) * 4;
+        G -= llLog + ofLog + mlLog;
+        if ((int32_t)G < gz) err = kCorruptionDetected;
         for (uint32_t n = 0; n < nbSeq && !err; n++) {
-            uint32_t const eL = tLL[sL], eO = tOF[sO], eM = tML[sM];
+            br.advance(G);
+            uint32_t const eL = lds32(aL), eO = lds32(aO), eM = lds32(aM);
             uint32_t const llBits = (eL >> 4) & 31, mlBits = (eM >> 4) & 31, ofBits = (eO >> 4) & 31;
-            uint32_t const llSym = (eL >> 9) & 63, mlSym = (eM >> 9) & 63;
-            uint32_t ll = s_llBase[llSym], ml = s_mlBase[mlSym];
-            // stream order: offset extra, matchLength extra, litLength extra, then LL / ML / OF state bits (:2397-2480)
-            uint32_t const ofExtra = br.field_lo(br.off, ofBits);              // ofBits <= 31
-            br.consume(ofBits); br.normalize();
-            uint32_t const o1 = br.off, o2 = o1 + mlBits;                      // <= 31 + 16
-            ml += br.field(o1, mlBits);
-            ll += br.field(o2, llBits);
-            br.consume(mlBits + llBits); br.normalize();
-            bool const overRead = br.left < 0;
             uint32_t const nbL = eL & 15, nbM = eM & 15, nbO = eO & 15;
-            uint32_t const p1 = br.off, p2 = p1 + nbL, p3 = p2 + nbM;          // <= 31 + 9 + 9
-            sL = (eL >> 16) + br.field(p1, nbL);
-            sM = (eM >> 16) + br.field(p2, nbM);
-            sO = (eO >> 16) + br.field(p3, nbO);
-            br.consume(nbL + nbM + nbO); br.normalize();
+            // stream order: offset extra, matchLength extra, litLength extra, then LL / ML / OF state bits (:2397-2480)
+            uint32_t const G1 = G - ofBits, G2 = G1 - (mlBits + llBits), G3 = G2 - (nbL + nbM + nbO);
+            uint32_t const xA = br.peek32(G), xB = br.peek32(G1), xC = br.peek32(G2);
+            uint32_t const llSym = (eL >> 9) & 63, mlSym = (eM >> 9) & 63;
+            uint32_t const ofExtra = top_bits(xA, ofBits);
+            uint32_t const ml = lds32(mlBaseS + mlSym * 4) + top_bits(xB, mlBits);
+            uint32_t const ll = lds32(llBaseS + llSym * 4) + top_bits(xB << mlBits, llBits);     // mlBits <= 16
+            aL = tLL + ((eL >> 16) + top_bits(xC, nbL)) * 4;
+            uint32_t const xC2 = xC << nbL;
+            aM = tML + ((eM >> 16) + top_bits(xC2, nbM)) * 4;
+            aO = tOF + ((eO >> 16) + top_bits(xC2 << nbM, nbO)) * 4;
+            bool const overRead = (int32_t)G2 < gz;                      // the extra bits must exist; the last state update may run dry
+            bool const dry = (int32_t)G3 < gz;
+            G = G3;
             uint32_t offset;
-            if (ofBits > 1) {
-                offset = ((1u << ofBits) - 3u) + ofExtra;                    // OF_base[n] = (1<<n)-3 for n >= 2
-                rep2 = rep1; rep1 = rep0; rep0 = offset;
-            } else {
-                uint32_t const ll0 = (llSym == 0);                           // baseValue == 0 <=> code 0
-                if (ofBits == 0) {
-                    offset = ll0 ? rep1 : rep0;
-                    rep1 = ll0 ? rep0 : rep1;
-                    rep0 = offset;
-                } else {
-                    uint32_t const ofv = 1u + ll0 + ofExtra;                 // OF_base[1] = 1
-                    uint32_t temp = (ofv == 3) ? rep0 - 1 : (ofv == 1 ? rep1 : rep2);
-                    temp += !temp;
-                    if (ofv != 1) rep2 = rep1;
-                    rep1 = rep0; rep0 = offset = temp;
-                }
+            {   // ZSTD_decodeSequence offset rules (:2397-2445), as selects
+                uint32_t const ll0 = (llSym == 0);                        // baseValue == 0 <=> code 0
+                uint32_t const ofv = 1u + ll0 + ofExtra;                  // only meaningful for ofBits == 1 (OF_base[1] = 1)
+                uint32_t t1 = (ofv == 3) ? rep0 - 1 : (ofv == 1 ? rep1 : rep2);
+                t1 += !t1;
+                uint32_t const big = ((1u << ofBits) - 3u) + ofExtra;     // OF_base[n] = (1<<n)-3 for n >= 2
+                uint32_t const t0 = ll0 ? rep1 : rep0;
+                offset = ofBits > 1 ? big : (ofBits == 0 ? t0 : t1);
+                // history update
+                bool const shift2 = (ofBits > 1) | ((ofBits == 1) & (ofv != 1));     // rep2 <- rep1
+                bool const shift1 = (ofBits > 0) | (ll0 != 0);                       // rep1 <- rep0
+                uint32_t const n2 = shift2 ? rep1 : rep2;
+                uint32_t const n1 = shift1 ? rep0 : rep1;
+                rep2 = n2; rep1 = n1; rep0 = offset;
             }
             // validity (ZSTD_execSequenceEnd order): output overflow, literal overrun, offset beyond frame start
             uint32_t const seqLen = ll + ml;
             bool const e1 = seqLen > dstCap - outPos, e2 = ll > litSize - litPos, e3 = offset > (outPos + ll) - frameStart;
-            bool const e4 = overRead | ((n + 1 < nbSeq) & (br.left < 0)) | ((offset >> 30) != 0);   // offsets >= 1 GiB do not fit seq_pack
+            bool const e4 = overRead | ((n + 1 < nbSeq) & dry) | ((offset >> 30) != 0);   // offsets >= 1 GiB do not fit seq_pack
             if (e1 | e2 | e3 | e4) err = e1 ? kDstSizeTooSmall : kCorruptionDetected;
             oSeq[n] = seq_pack(ll, ml, offset);
             outPos += seqLen; litPos += ll;
         }
         // the stream must not have unread bits left (BIT_reloadDStream >= completed, :2730)
-        if (!err && br.left > 0) err = kCorruptionDetected;
+        if (!err && (int32_t)G > gz) err = kCorruptionDetected;
         if (!err && (litSize - litPos) > dstCap - outPos) err = kDstSizeTooSmall;   // last literals, :2748
     }
     if (err) { it.status = kStError; it.errCode = err; return; }
