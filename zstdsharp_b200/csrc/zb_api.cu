@@ -66,6 +66,29 @@ struct PinBuf {
 
 constexpr size_t kMaxItemsPerPass = 8192;
 constexpr int kEvents = 24;
+constexpr int kPipeMax = 8;                    // upper bound of sub-batches in flight in the host-pointer path (one scratch arena + compute stream each)
+static int env_int(const char* name, int def, int lo, int hi) { const char* e = getenv(name); if (!e) return def; int v = atoi(e); return v < lo ? lo : (v > hi ? hi : v); }
+// sub-batches in flight / target sub-batch size (items); tunable for experiments, defaults chosen on B200 (profiles/r01_notes.md)
+static int pipe_depth() { static int v = env_int("ZSTDB200_PIPE", 3, 1, kPipeMax); return v; }
+static size_t pipe_items() { static int v = env_int("ZSTDB200_PIPE_ITEMS", 2048, 16, 8192); return (size_t)v; }
+
+// scratch of one decode pass (DecPass layout, zb_decode.cuh)
+struct DecArena {
+    DevBuf dItems, dInit, dHuf, dFse, dLit, dSeq, dHufList, dSeqList, dCounters, dResults;
+    PinBuf hInit, hCounters, hResults;
+    bool ensure(size_t m) {
+        return dItems.ensure(m * sizeof(DecItem)) && dInit.ensure(m * sizeof(DecItemInit)) && hInit.ensure(m * sizeof(DecItemInit)) &&
+               dHuf.ensure(m * kHufTableEntries * 2) && dFse.ensure(m * kFseTableEntries * 4) && dLit.ensure(m * (size_t)kLitStride) &&
+               dSeq.ensure(m * (size_t)kSeqCap * 8) && dHufList.ensure(m * 4) && dSeqList.ensure(m * 4) &&
+               dCounters.ensure(64) && hCounters.ensure(64) && dResults.ensure(m * 8) && hResults.ensure(m * 8);
+    }
+    void release() {
+        DevBuf* d[] = {&dItems, &dInit, &dHuf, &dFse, &dLit, &dSeq, &dHufList, &dSeqList, &dCounters, &dResults};
+        for (auto* b : d) b->release();
+        PinBuf* h[] = {&hInit, &hCounters, &hResults};
+        for (auto* b : h) b->release();
+    }
+};
 
 struct Engine {
     int device = -1;
@@ -73,12 +96,15 @@ struct Engine {
     cudaStream_t stream = nullptr;      // stream all work of this context is issued on
     cudaStream_t ownStream = nullptr;   // created by the context; replaced by ZSTDB200_setStream
     cudaEvent_t ev[kEvents] = {};
-    // decode arena
-    DevBuf dItems, dInit, dHuf, dFse, dLit, dSeq, dDefaultFse, dHufList, dSeqList, dCounters, dResults;
-    PinBuf hInit, hCounters, hResults;
+    // decode arenas ([0] also serves the device-pointer API) and the copy/compute streams of the host-pointer pipeline
+    DecArena dec[kPipeMax];
+    DevBuf dDefaultFse;
     bool defaultTablesBuilt = false;
+    cudaStream_t sIn = nullptr, sOut = nullptr, sComp[kPipeMax] = {};
+    cudaEvent_t evStart = nullptr, evIn[2] = {}, evOut[2] = {};
+    std::vector<cudaEvent_t> evPool;
     // host<->device staging for the host-pointer API
-    DevBuf dSrc, dDst; PinBuf hStage;
+    DevBuf dSrc, dDst; PinBuf hStage, hStageOut;
     // encode arena
     EncArena enc;
     DevBuf dEncInit; PinBuf hEncInit;
@@ -100,83 +126,113 @@ struct Engine {
         ZB_CUDA(cudaStreamCreateWithFlags(&ownStream, cudaStreamNonBlocking));
         if (!stream) stream = ownStream;
         for (int i = 0; i < kEvents; i++) ZB_CUDA(cudaEventCreate(&ev[i]));
+        ZB_CUDA(cudaStreamCreateWithFlags(&sIn, cudaStreamNonBlocking));
+        ZB_CUDA(cudaStreamCreateWithFlags(&sOut, cudaStreamNonBlocking));
+        for (int i = 0; i < kPipeMax; i++) ZB_CUDA(cudaStreamCreateWithFlags(&sComp[i], cudaStreamNonBlocking));
+        ZB_CUDA(cudaEventCreate(&evStart));
+        for (int i = 0; i < 2; i++) { ZB_CUDA(cudaEventCreate(&evIn[i])); ZB_CUDA(cudaEventCreate(&evOut[i])); }
         ready = true;
         return true;
     }
     void destroy() {
         if (device >= 0) cudaSetDevice(device);
-        DevBuf* d[] = {&dItems, &dInit, &dHuf, &dFse, &dLit, &dSeq, &dDefaultFse, &dHufList, &dSeqList, &dCounters, &dResults, &dSrc, &dDst, &dEncInit};
+        DevBuf* d[] = {&dDefaultFse, &dSrc, &dDst, &dEncInit};
         for (auto* b : d) b->release();
-        PinBuf* h[] = {&hInit, &hCounters, &hResults, &hStage, &hEncInit};
+        for (auto& a : dec) a.release();
+        PinBuf* h[] = {&hStage, &hStageOut, &hEncInit};
         for (auto* b : h) b->release();
         enc.release();
-        if (ready) { for (int i = 0; i < kEvents; i++) cudaEventDestroy(ev[i]); cudaStreamDestroy(ownStream); }
+        if (ready) {
+            for (int i = 0; i < kEvents; i++) cudaEventDestroy(ev[i]);
+            for (auto e : evPool) cudaEventDestroy(e);
+            evPool.clear();
+            cudaEventDestroy(evStart);
+            for (int i = 0; i < 2; i++) { cudaEventDestroy(evIn[i]); cudaEventDestroy(evOut[i]); }
+            cudaStreamDestroy(sIn); cudaStreamDestroy(sOut);
+            for (int i = 0; i < kPipeMax; i++) cudaStreamDestroy(sComp[i]);
+            cudaStreamDestroy(ownStream);
+        }
         ready = false;
     }
     bool bind() { ZB_CUDA(cudaSetDevice(device)); return true; }
+    bool need_events(size_t n) { while (evPool.size() < n) { cudaEvent_t e; ZB_CUDA(cudaEventCreate(&e)); evPool.push_back(e); } return true; }
 };
 
 // ---------------------------------------------------------------------------------------------------------------
 //  Decode pass over device-resident frames
 // ---------------------------------------------------------------------------------------------------------------
+// Enqueues one pass (m <= kMaxItemsPerPass items) on `stream` using arena A.  nWaves == 0: the block count is read back
+// from the scan kernel (one host sync); otherwise the caller already knows it (host-pointer path) and nothing blocks.
+// The per-item results land in A.hResults once the stream has drained.
+static bool decode_enqueue(Engine& E, DecArena& A, cudaStream_t stream, size_t m, const uint8_t* d_src, const uint64_t* srcOff, const size_t* srcSize,
+                           uint8_t* d_dst, const uint64_t* dstOff, const size_t* dstCap, uint32_t nWaves, cudaEvent_t* timeEv /* [7] or null */)
+{
+    if (!A.ensure(m) || !E.dDefaultFse.ensure(kFseTableEntries * 4)) return false;
+    if (!E.defaultTablesBuilt) {
+        dec_build_default_tables(E.dDefaultFse.as<uint32_t>(), E.stream); E.launches++; E.defaultTablesBuilt = true;
+        ZB_CUDA(cudaStreamSynchronize(E.stream));       // built once per context; every stream may use it afterwards
+    }
+    DecItemInit* hi = A.hInit.as<DecItemInit>();
+    // oversized items cannot be addressed by the 32-bit cursors: they are reported per item by decode_collect
+    for (size_t i = 0; i < m; i++) {
+        hi[i].srcOff = srcOff[i]; hi[i].dstOff = dstOff[i];
+        hi[i].srcSize = (uint32_t)std::min<size_t>(srcSize[i], 0xFFFFFFF0u);
+        hi[i].dstCap = (uint32_t)std::min<size_t>(dstCap[i], 0xFFFFFFF0u);
+    }
+    ZB_CUDA(cudaMemcpyAsync(A.dInit.p, hi, m * sizeof(DecItemInit), cudaMemcpyHostToDevice, stream));
+    ZB_CUDA(cudaMemsetAsync(A.dCounters.p, 0, 64, stream));
+    DecPass p;
+    p.items = A.dItems.as<DecItem>(); p.nItems = (uint32_t)m; p.src = d_src; p.dst = d_dst;
+    p.hufTable = A.dHuf.as<uint16_t>(); p.fseTable = A.dFse.as<uint32_t>(); p.litBuf = A.dLit.as<uint8_t>();
+    p.seq = A.dSeq.as<uint2>();
+    p.defaultFse = E.dDefaultFse.as<uint32_t>(); p.hufList = A.dHufList.as<uint32_t>(); p.seqList = A.dSeqList.as<uint32_t>();
+    p.counters = A.dCounters.as<uint32_t>(); p.results = A.dResults.as<uint64_t>();
+    if (timeEv) ZB_CUDA(cudaEventRecord(timeEv[0], stream));
+    dec_launch_scan_init(p, A.dInit.p, stream); E.launches++;
+    if (nWaves == 0) {
+        ZB_CUDA(cudaMemcpyAsync(A.hCounters.p, A.dCounters.p, 16, cudaMemcpyDeviceToHost, stream));
+        ZB_CUDA(cudaStreamSynchronize(stream));
+        nWaves = A.hCounters.as<uint32_t>()[3];
+    }
+    for (uint32_t w = 0; w < nWaves; w++) {
+        if (timeEv && w == 0) dec_launch_wave_timed(p, stream, &timeEv[2]);   // records timeEv[2..6] between the kernels of the first wave
+        else dec_launch_wave(p, stream);
+        E.launches += 5;
+    }
+    dec_launch_finish(p, stream); E.launches++;
+    if (timeEv) ZB_CUDA(cudaEventRecord(timeEv[1], stream));
+    ZB_CUDA(cudaMemcpyAsync(A.hResults.p, A.dResults.p, m * 8, cudaMemcpyDeviceToHost, stream));
+    return true;
+}
+
+static void decode_collect(const DecArena& A, size_t m, const size_t* srcSize, size_t* result)
+{
+    const uint64_t* hr = A.hResults.as<uint64_t>();
+    for (size_t i = 0; i < m; i++) result[i] = srcSize[i] > 0xFFFFFFF0u ? (size_t)make_error(kSrcSizeWrong) : (size_t)hr[i];
+}
+
 static bool decode_device(Engine& E, size_t n, const uint8_t* d_src, const uint64_t* srcOff, const size_t* srcSize,
                           uint8_t* d_dst, const uint64_t* dstOff, const size_t* dstCap, size_t* result, bool timeKernels)
 {
     if (!E.bind()) return false;
     float kernelMs = 0; float slotMs[5] = {0, 0, 0, 0, 0};
+    DecArena& A = E.dec[0];
     for (size_t base = 0; base < n; base += kMaxItemsPerPass) {
         size_t const m = std::min(kMaxItemsPerPass, n - base);
-        if (!E.dItems.ensure(m * sizeof(DecItem)) || !E.dInit.ensure(m * sizeof(DecItemInit)) || !E.hInit.ensure(m * sizeof(DecItemInit)) ||
-            !E.dHuf.ensure(m * kHufTableEntries * 2) || !E.dFse.ensure(m * kFseTableEntries * 4) || !E.dLit.ensure(m * (size_t)kLitStride) ||
-            !E.dSeq.ensure(m * (size_t)kSeqCap * 8) ||
-            !E.dDefaultFse.ensure(kFseTableEntries * 4) || !E.dHufList.ensure(m * 4) || !E.dSeqList.ensure(m * 4) ||
-            !E.dCounters.ensure(64) || !E.hCounters.ensure(64) || !E.dResults.ensure(m * 8) || !E.hResults.ensure(m * 8))
-            return false;
-        if (!E.defaultTablesBuilt) { dec_build_default_tables(E.dDefaultFse.as<uint32_t>(), E.stream); E.launches++; E.defaultTablesBuilt = true; }
-        DecItemInit* hi = E.hInit.as<DecItemInit>();
-        // oversized items cannot be addressed by the 32-bit cursors: they are reported per item below
-        for (size_t i = 0; i < m; i++) {
-            size_t const ss = srcSize[base + i], dc = dstCap[base + i];
-            hi[i].srcOff = srcOff[base + i]; hi[i].dstOff = dstOff[base + i];
-            hi[i].srcSize = (uint32_t)std::min<size_t>(ss, 0xFFFFFFF0u);
-            hi[i].dstCap = (uint32_t)std::min<size_t>(dc, 0xFFFFFFF0u);
-        }
-        ZB_CUDA(cudaMemcpyAsync(E.dInit.p, hi, m * sizeof(DecItemInit), cudaMemcpyHostToDevice, E.stream));
-        ZB_CUDA(cudaMemsetAsync(E.dCounters.p, 0, 64, E.stream));
-        DecPass p;
-        p.items = E.dItems.as<DecItem>(); p.nItems = (uint32_t)m; p.src = d_src; p.dst = d_dst;
-        p.hufTable = E.dHuf.as<uint16_t>(); p.fseTable = E.dFse.as<uint32_t>(); p.litBuf = E.dLit.as<uint8_t>();
-        p.seq = E.dSeq.as<uint2>();
-        p.defaultFse = E.dDefaultFse.as<uint32_t>(); p.hufList = E.dHufList.as<uint32_t>(); p.seqList = E.dSeqList.as<uint32_t>();
-        p.counters = E.dCounters.as<uint32_t>(); p.results = E.dResults.as<uint64_t>();
-        ZB_CUDA(cudaEventRecord(E.ev[0], E.stream));
-        dec_launch_scan_init(p, E.dInit.p, E.stream); E.launches++;
-        ZB_CUDA(cudaMemcpyAsync(E.hCounters.p, E.dCounters.p, 16, cudaMemcpyDeviceToHost, E.stream));
-        ZB_CUDA(cudaStreamSynchronize(E.stream));
-        uint32_t const nWaves = E.hCounters.as<uint32_t>()[3];
-        for (uint32_t w = 0; w < nWaves; w++) {
-            if (timeKernels && w == 0) {
-                dec_launch_wave_timed(p, E.stream, &E.ev[2]);   // records ev[2..6] between the kernels of the first wave
-            } else dec_launch_wave(p, E.stream);
-            E.launches += 5;
-        }
-        dec_launch_finish(p, E.stream); E.launches++;
-        ZB_CUDA(cudaEventRecord(E.ev[1], E.stream));
-        ZB_CUDA(cudaMemcpyAsync(E.hResults.p, E.dResults.p, m * 8, cudaMemcpyDeviceToHost, E.stream));
+        if (!decode_enqueue(E, A, E.stream, m, d_src, srcOff + base, srcSize + base, d_dst, dstOff + base, dstCap + base, 0, &E.ev[0])) return false;
         ZB_CUDA(cudaStreamSynchronize(E.stream));
         ZB_CUDA(cudaGetLastError());
         float ms = 0; cudaEventElapsedTime(&ms, E.ev[0], E.ev[1]); kernelMs += ms;
-        if (timeKernels && nWaves > 0) {
+        if (timeKernels) {
             float t;
-            cudaEventElapsedTime(&t, E.ev[0], E.ev[2]); slotMs[0] += t;              // scan (+ sync gap)
-            for (int k = 0; k < 4; k++) { cudaEventElapsedTime(&t, E.ev[2 + k], E.ev[3 + k]); slotMs[1 + k] += t; }
+            if (cudaEventElapsedTime(&t, E.ev[0], E.ev[2]) == cudaSuccess) {
+                slotMs[0] += t;              // scan (+ sync gap)
+                for (int k = 0; k < 4; k++) { cudaEventElapsedTime(&t, E.ev[2 + k], E.ev[3 + k]); slotMs[1 + k] += t; }
+            }
         }
-        const uint64_t* hr = E.hResults.as<uint64_t>();
-        for (size_t i = 0; i < m; i++) {
-            if (srcSize[base + i] > 0xFFFFFFF0u) result[base + i] = (size_t)make_error(kSrcSizeWrong);
-            else result[base + i] = (size_t)hr[i];
-        }
+        decode_collect(A, m, srcSize + base, result + base);
     }
+    (void)cudaGetLastError();
     E.timings[1] = kernelMs;
     for (int k = 0; k < 5; k++) E.timings[3 + k] = slotMs[k];
     return true;
@@ -237,70 +293,140 @@ static bool upload_items(Engine& E, size_t n, const void* const* src, const size
     return true;
 }
 
-// copies result[i] bytes of every item back to the caller
-static bool download_items(Engine& E, size_t n, void* const* dst, const size_t* dstCap, const std::vector<uint64_t>& off, const size_t* result, size_t total)
-{
-    std::vector<Run> runs;
-    find_runs(runs, n, (const void* const*)dst, dstCap);
-    auto ok = [&](size_t i) { return !is_error(result[i]); };
-    if (runs.size() <= 512) {
-        for (auto& r : runs) {
-            // one DMA while items are completely filled; partial / failed items are copied individually
-            size_t k = 0;
-            while (k < r.count) {
-                size_t i = r.first + k; size_t j = k; size_t bytes = 0;
-                while (j < r.count && ok(r.first + j) && result[r.first + j] == dstCap[r.first + j]) { bytes += dstCap[r.first + j]; j++; }
-                if (j < r.count && ok(r.first + j)) { bytes += result[r.first + j]; j++; }
-                else if (j == k) { j++; }   // failed item: nothing to copy
-                if (bytes) ZB_CUDA(cudaMemcpyAsync(dst[i], E.dDst.as<uint8_t>() + off[i], bytes, cudaMemcpyDeviceToHost, E.stream));
-                k = j;
-            }
-        }
-        ZB_CUDA(cudaStreamSynchronize(E.stream));
-    } else {
-        if (!E.hStage.ensure(total)) return false;
-        ZB_CUDA(cudaMemcpyAsync(E.hStage.p, E.dDst.p, total, cudaMemcpyDeviceToHost, E.stream));
-        ZB_CUDA(cudaStreamSynchronize(E.stream));
-        const uint8_t* st = E.hStage.as<uint8_t>();
-        parallel_for(n, 256, [&](size_t a, size_t b) { for (size_t i = a; i < b; i++) if (ok(i)) memcpy(dst[i], st + off[i], result[i]); });
-    }
-    return true;
-}
-
-
-static void layout_dst(size_t n, void* const* dst, const size_t* dstCap, std::vector<uint64_t>& off, size_t* total)
+static size_t layout_dst(size_t n, void* const* dst, const size_t* dstCap, std::vector<uint64_t>& off, size_t* total)
 {
     std::vector<Run> runs;
     find_runs(runs, n, (const void* const*)dst, dstCap);
     off.resize(n);
-    size_t t = 16;
+    // every run starts on its own 128-byte line: items of different runs never share a cache line on the device
+    size_t t = 128;
     for (auto& r : runs) {
         size_t o = t;
         for (size_t k = 0; k < r.count; k++) { off[r.first + k] = o; o += dstCap[r.first + k]; }
-        t = (o + 15) & ~(size_t)15;
+        t = (o + 127) & ~(size_t)127;
     }
-    *total = t + 16;
+    *total = t + 128;
+    return runs.size();
 }
 
+// copies result[i] bytes of items [first, first+count) back to the caller on stream `st`
+static bool download_range(Engine& E, size_t first, size_t count, void* const* dst, const size_t* dstCap, const std::vector<uint64_t>& off,
+                           const size_t* result, cudaStream_t st)
+{
+    auto ok = [&](size_t i) { return !is_error(result[i]); };
+    size_t k = first; size_t const end = first + count;
+    while (k < end) {
+        // longest run of host-adjacent items that are completely filled, plus one final partial item: one DMA
+        size_t j = k; size_t bytes = 0;
+        while (j < end && ok(j) && result[j] == dstCap[j] && (j == k || (const uint8_t*)dst[j] == (const uint8_t*)dst[j - 1] + dstCap[j - 1])) { bytes += dstCap[j]; j++; }
+        if (j < end && ok(j) && (j == k || (const uint8_t*)dst[j] == (const uint8_t*)dst[j - 1] + dstCap[j - 1])) { bytes += result[j]; j++; }
+        else if (j == k) { j++; }   // failed item: nothing to copy
+        if (bytes) ZB_CUDA(cudaMemcpyAsync(dst[k], E.dDst.as<uint8_t>() + off[k], bytes, cudaMemcpyDeviceToHost, st));
+        k = j;
+    }
+    return true;
+}
+
+// Host-pointer batch decode.  The batch is cut into sub-batches that flow through three stages on separate streams:
+// H2D of the compressed bytes (sIn), the kernel pipeline (sComp[k % kPipe], one scratch arena each), D2H of the
+// regenerated bytes (sOut).  The number of waves of a sub-batch comes from a host-side walk over the block headers, so
+// no stage waits for a read-back; the host only waits for a sub-batch's results before it issues that sub-batch's D2H.
 static size_t decompress_batch_host(Engine& E, size_t n, const void* const* src, const size_t* srcSize, void* const* dst, const size_t* dstCap, size_t* result)
 {
     if (!E.init() || !E.bind()) return (size_t)make_error(kGeneric);
     E.launches = 0; memset(E.timings, 0, sizeof(E.timings));
     if (n == 0) return 0;
-    std::vector<uint64_t> sOff, dOff; size_t sTotal = 0, dTotal = 0;
-    cudaEventRecord(E.ev[10], E.stream);
-    if (!upload_items(E, n, src, srcSize, sOff, &sTotal)) return (size_t)make_error(kMemoryAllocation);
-    cudaEventRecord(E.ev[11], E.stream);
-    layout_dst(n, dst, dstCap, dOff, &dTotal);
-    if (!E.dDst.ensure(dTotal)) return (size_t)make_error(kMemoryAllocation);
-    if (!decode_device(E, n, E.dSrc.as<uint8_t>(), sOff.data(), srcSize, E.dDst.as<uint8_t>(), dOff.data(), dstCap, result, false))
-        return (size_t)make_error(kGeneric);
-    cudaEventRecord(E.ev[12], E.stream);
-    if (!download_items(E, n, dst, dstCap, dOff, result, dTotal)) return (size_t)make_error(kGeneric);
-    cudaEventRecord(E.ev[13], E.stream);
-    cudaEventSynchronize(E.ev[13]);
-    cudaEventElapsedTime(&E.timings[0], E.ev[10], E.ev[11]);
-    cudaEventElapsedTime(&E.timings[2], E.ev[12], E.ev[13]);
+    // ---- layout of the packed source / destination buffers (runs of host-adjacent items stay adjacent) ----
+    std::vector<uint64_t> sOff(n), dOff; size_t sTotal = 16, dTotal = 0;
+    std::vector<Run> runs;
+    find_runs(runs, n, src, srcSize);
+    for (auto& r : runs) {
+        size_t o = sTotal;
+        for (size_t k = 0; k < r.count; k++) { sOff[r.first + k] = o; o += srcSize[r.first + k]; }
+        sTotal = (o + 15) & ~(size_t)15;
+    }
+    sTotal += 64;
+    size_t const dstRuns = layout_dst(n, dst, dstCap, dOff, &dTotal);
+    if (!E.dSrc.ensure(sTotal) || !E.dDst.ensure(dTotal)) return (size_t)make_error(kMemoryAllocation);
+    bool const gather = runs.size() > 512;                     // many scattered buffers: stage through pinned memory
+    bool const scatter = dstRuns > 512;
+    if (gather && !E.hStage.ensure(sTotal)) return (size_t)make_error(kMemoryAllocation);
+    if (scatter && !E.hStageOut.ensure(dTotal)) return (size_t)make_error(kMemoryAllocation);
+    // ---- sub-batches ----
+    size_t const kPipe = (size_t)pipe_depth(), kPipeItems = pipe_items();
+    size_t const nSub = (n + kPipeItems - 1) / kPipeItems;
+    size_t const per = (n + nSub - 1) / nSub;
+    if (!E.need_events(4 * nSub)) return (size_t)make_error(kGeneric);
+    cudaEvent_t* const evH2D = E.evPool.data(); cudaEvent_t* const evDone = evH2D + nSub; cudaEvent_t* const evBegin = evDone + nSub; cudaEvent_t* const evD2H = evBegin + nSub;
+    auto fail = [&](ErrorCode c) { cudaDeviceSynchronize(); (void)cudaGetLastError(); return (size_t)make_error(c); };
+    if (cudaEventRecord(E.evStart, E.stream) != cudaSuccess) return fail(kGeneric);   // order after the caller's stream
+    cudaStreamWaitEvent(E.sIn, E.evStart, 0);
+    cudaEventRecord(E.evIn[0], E.sIn);
+    // stage 1: all uploads are queued up front
+    size_t runIdx = 0;
+    for (size_t k = 0; k < nSub; k++) {
+        size_t const a = k * per, b = std::min(n, a + per);
+        if (gather) {
+            uint8_t* st = E.hStage.as<uint8_t>();
+            parallel_for(b - a, 256, [&](size_t x, size_t y) { for (size_t i = a + x; i < a + y; i++) memcpy(st + sOff[i], src[i], srcSize[i]); });
+            size_t const lo = sOff[a], hi = sOff[b - 1] + srcSize[b - 1];
+            if (hi > lo && cudaMemcpyAsync(E.dSrc.as<uint8_t>() + lo, st + lo, hi - lo, cudaMemcpyHostToDevice, E.sIn) != cudaSuccess) return fail(kGeneric);
+        } else {
+            // the pieces of the runs that intersect [a, b): one DMA each
+            size_t i = a;
+            while (i < b) {
+                while (runs[runIdx].first + runs[runIdx].count <= i) runIdx++;
+                size_t const e = std::min(b, runs[runIdx].first + runs[runIdx].count);
+                size_t const bytes = sOff[e - 1] + srcSize[e - 1] - sOff[i];
+                if (bytes && cudaMemcpyAsync(E.dSrc.as<uint8_t>() + sOff[i], src[i], bytes, cudaMemcpyHostToDevice, E.sIn) != cudaSuccess) return fail(kGeneric);
+                i = e;
+            }
+        }
+        cudaEventRecord(evH2D[k], E.sIn);
+    }
+    cudaEventRecord(E.evIn[1], E.sIn);
+    // stage 2 + 3
+    bool firstOut = true;
+    // scattered destinations: the sub-batch's device region comes back with one DMA into pinned staging and is copied
+    // out by host threads one sub-batch later (while the next DMA is in flight)
+    auto scatter_out = [&](size_t k) -> bool {
+        size_t const a = k * per, b = std::min(n, a + per);
+        if (cudaEventSynchronize(evD2H[k]) != cudaSuccess) return false;
+        const uint8_t* st = E.hStageOut.as<uint8_t>();
+        parallel_for(b - a, 256, [&](size_t x, size_t y) { for (size_t i = a + x; i < a + y; i++) if (!is_error(result[i])) memcpy(dst[i], st + dOff[i], result[i]); });
+        return true;
+    };
+    auto finish = [&](size_t k) -> bool {
+        size_t const a = k * per, b = std::min(n, a + per);
+        if (cudaEventSynchronize(evDone[k]) != cudaSuccess) return false;
+        decode_collect(E.dec[k % kPipe], b - a, srcSize + a, result + a);
+        if (firstOut) { cudaEventRecord(E.evOut[0], E.sOut); firstOut = false; }
+        if (!scatter) return download_range(E, a, b - a, dst, dstCap, dOff, result, E.sOut);
+        size_t const lo = dOff[a], hi = dOff[b - 1] + dstCap[b - 1];
+        if (hi > lo && cudaMemcpyAsync(E.hStageOut.as<uint8_t>() + lo, E.dDst.as<uint8_t>() + lo, hi - lo, cudaMemcpyDeviceToHost, E.sOut) != cudaSuccess) return false;
+        cudaEventRecord(evD2H[k], E.sOut);
+        return k == 0 || scatter_out(k - 1);
+    };
+    for (size_t k = 0; k < nSub; k++) {
+        size_t const a = k * per, b = std::min(n, a + per);
+        if (k >= kPipe && !finish(k - kPipe)) return fail(kGeneric);
+        uint32_t waves = 1;
+        for (size_t i = a; i < b; i++) waves = std::max(waves, count_item_blocks((const uint8_t*)src[i], (uint32_t)std::min<size_t>(srcSize[i], 0xFFFFFFF0u)));
+        cudaStream_t const cs = E.sComp[k % kPipe];
+        cudaStreamWaitEvent(cs, evH2D[k], 0);
+        cudaEventRecord(evBegin[k], cs);
+        if (!decode_enqueue(E, E.dec[k % kPipe], cs, b - a, E.dSrc.as<uint8_t>(), sOff.data() + a, srcSize + a, E.dDst.as<uint8_t>(), dOff.data() + a, dstCap + a, waves, nullptr))
+            return fail(kMemoryAllocation);
+        cudaEventRecord(evDone[k], cs);
+    }
+    for (size_t k = nSub > kPipe ? nSub - kPipe : 0; k < nSub; k++) if (!finish(k)) return fail(kGeneric);
+    if (scatter && !scatter_out(nSub - 1)) return fail(kGeneric);
+    cudaEventRecord(E.evOut[1], E.sOut);
+    if (cudaStreamSynchronize(E.sOut) != cudaSuccess || cudaGetLastError() != cudaSuccess) return fail(kGeneric);
+    // the stages overlap: [0] / [2] are the spans of the copy streams, [1] is the sum of the sub-batch kernel spans
+    cudaEventElapsedTime(&E.timings[0], E.evIn[0], E.evIn[1]);
+    cudaEventElapsedTime(&E.timings[2], E.evOut[0], E.evOut[1]);
+    for (size_t k = 0; k < nSub; k++) { float t = 0; cudaEventElapsedTime(&t, evBegin[k], evDone[k]); E.timings[1] += t; }
     return 0;
 }
 

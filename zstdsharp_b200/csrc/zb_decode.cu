@@ -297,39 +297,7 @@ __global__ void dec_scan_kernel(DecPass p, const DecItemInit* init)
     it.srcPos = 0; it.outPos = 0; it.frameStart = 0; it.status = kStRunning; it.errCode = 0; it.inFrame = 0;
     it.moreThan1Frame = 0; it.checksumFlag = 0; it.hasFcs = 0; it.fcs = 0; it.litEntropy = 0; it.fseEntropy = 0;
     it.blkType = kBlkNone;
-    const uint8_t* src = p.src + in.srcOff; uint32_t const size = in.srcSize;
-    uint32_t pos = 0, blocks = 0;
-    for (;;) {
-        uint32_t rem = size - pos;
-        if (rem < 5) break;
-        uint32_t const magic = ld_le32(src + pos);
-        if ((magic & kMagicSkippableMask) == kMagicSkippableStart) {
-            if (rem < 8) break;
-            uint32_t const sz = ld_le32(src + pos + 4);
-            if ((uint64_t)sz + 8 > rem) break;
-            pos += sz + 8; continue;
-        }
-        if (magic != kMagic) break;
-        uint32_t const fhd = src[pos + 4];
-        uint32_t const hs = frame_header_size(fhd);
-        if (rem < hs + 3) break;
-        pos += hs;
-        bool bad = false;
-        for (;;) {
-            if (size - pos < 3) { bad = true; break; }
-            uint32_t const h = ld_le24(src + pos);
-            uint32_t const type = (h >> 1) & 3, cs = h >> 3;
-            uint32_t const csz = type == kBlkRle ? 1 : cs;
-            blocks++;
-            pos += 3;
-            if (type == 3 || csz > size - pos) { bad = true; break; }
-            pos += csz;
-            if (h & 1) break;
-        }
-        if (bad) break;
-        if (fhd & 4) { if (size - pos < 4) break; pos += 4; }
-    }
-    if (blocks == 0) blocks = 1;
+    uint32_t const blocks = count_item_blocks(p.src + in.srcOff, in.srcSize);
     atomicMax(&p.counters[3], blocks);
 }
 

@@ -90,6 +90,47 @@ struct DecPass {
     uint64_t* results;      // per item: regenerated size or error code
 };
 
+// Number of blocks of the longest frame chain of an item = number of waves the item needs.  Walks headers like
+// ZSTD_findFrameSizeInfo (ZstdDecompress.cs:877); malformed input simply stops the walk (errors are diagnosed by the
+// setup kernel).  Shared by the device scan kernel and the host scheduler (which then needs no read-back).
+__host__ __device__ inline uint32_t count_item_blocks(const uint8_t* src, uint32_t size)
+{
+    auto le32 = [](const uint8_t* q) { return (uint32_t)q[0] | ((uint32_t)q[1] << 8) | ((uint32_t)q[2] << 16) | ((uint32_t)q[3] << 24); };
+    uint32_t pos = 0, blocks = 0;
+    for (;;) {
+        uint32_t const rem = size - pos;
+        if (rem < 5) break;
+        uint32_t const magic = le32(src + pos);
+        if ((magic & kMagicSkippableMask) == kMagicSkippableStart) {
+            if (rem < 8) break;
+            uint32_t const sz = le32(src + pos + 4);
+            if ((uint64_t)sz + 8 > rem) break;
+            pos += sz + 8; continue;
+        }
+        if (magic != kMagic) break;
+        uint32_t const fhd = src[pos + 4];
+        uint32_t const dictID = fhd & 3, single = (fhd >> 5) & 1, fcsId = fhd >> 6;
+        uint32_t const hs = 5 + !single + (dictID == 3 ? 4 : dictID) + (fcsId == 0 ? 0 : (1u << fcsId)) + (single && !fcsId);
+        if (rem < hs + 3) break;
+        pos += hs;
+        bool bad = false;
+        for (;;) {
+            if (size - pos < 3) { bad = true; break; }
+            uint32_t const h = (uint32_t)src[pos] | ((uint32_t)src[pos + 1] << 8) | ((uint32_t)src[pos + 2] << 16);
+            uint32_t const type = (h >> 1) & 3, cs = h >> 3;
+            uint32_t const csz = type == kBlkRle ? 1 : cs;
+            blocks++;
+            pos += 3;
+            if (type == 3 || csz > size - pos) { bad = true; break; }
+            pos += csz;
+            if (h & 1) break;
+        }
+        if (bad) break;
+        if (fhd & 4) { if (size - pos < 4) break; pos += 4; }
+    }
+    return blocks ? blocks : 1;
+}
+
 // host-callable launchers (zb_decode.cu)
 void dec_build_default_tables(uint32_t* d_defaultFse, cudaStream_t s);
 struct DecItemInit { uint64_t srcOff; uint64_t dstOff; uint32_t srcSize; uint32_t dstCap; };
