@@ -446,6 +446,293 @@ __global__ void __launch_bounds__(32) enc_match_warp_kernel(EncPass p, const uin
     if (lane == 0) { it.nbSeq = nseq; it.lastLL = (uint32_t)(srcSize - anchor); }
 }
 
+// ------------------------------------------------------------------------------------------------------------
+//  Lane-per-chunk, exact ZSTD_fast parse with speculative windows: every chunk of the batch is in flight at once
+//  (8192 chunks = 256 warps), hash tables live in HBM/L2, and what bounds the kernel is the chain of dependent
+//  memory round trips per sequence (source words -> table entries -> candidate bytes).  A lane therefore issues the
+//  loads of TWO reference iterations (4 hash probes + 2 repcode probes, ZstdFast.cs:147-230) before it looks at any
+//  result, forwards table writes of earlier probes of the same window to later ones, resolves the first event in the
+//  reference's order and only then commits the table writes up to that event -- the table always equals the
+//  serial algorithm's table.
+// ------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t lane_count(const uint8_t* src, int a, int b, int limit)   // ZSTD_count (:264) on positions
+{
+    int n = 0;
+    while (a + n + 8 <= limit) {
+        uint64_t const diff = rd64(src + a + n) ^ rd64(src + b + n);
+        if (diff) return (uint32_t)n + (uint32_t)((__ffsll((long long)diff) - 1) >> 3);
+        n += 8;
+    }
+    while (a + n < limit && src[a + n] == src[b + n]) n++;
+    return (uint32_t)n;
+}
+
+// ---- 16-byte register windows -------------------------------------------------------------------------------
+// With one lane per chunk every load instruction touches 32 different cache lines, and it is the number of such
+// lane-loads (L1 wavefronts), not their latency, that bounds the kernel.  All source bytes are therefore fetched
+// as 16-byte "windows" (one or two LDG.128 from the chunk's 16-byte grid) and every 4/8-byte value the parse
+// needs is cut out of registers.
+struct SrcView {
+    const uint4* g;         // chunk bytes on their 16-byte grid (block 0 holds byte 0 of the chunk)
+    uint32_t D;             // offset of byte 0 inside block 0
+    uint32_t lastBlk;       // block that holds the last byte of the chunk (loads never go beyond it)
+};
+struct Win16 { uint64_t lo, hi; };                 // 16 bytes starting at some position, little endian
+__device__ __forceinline__ uint64_t fsr64(uint64_t a, uint64_t b, uint32_t s)   // low 64 bits of (b:a) >> s, s in [0,63]
+{
+    uint32_t const a0 = (uint32_t)a, a1 = (uint32_t)(a >> 32), b0 = (uint32_t)b, b1 = (uint32_t)(b >> 32);
+    uint32_t const w0 = s < 32 ? a0 : a1, w1 = s < 32 ? a1 : b0, w2 = s < 32 ? b0 : b1;
+    return (uint64_t)__funnelshift_r(w0, w1, s) | ((uint64_t)__funnelshift_r(w1, w2, s) << 32);
+}
+// 16 bytes starting at `pos`.  Every global read of the parse goes through cp.async (LDGSTS) into a per-lane
+// shared-memory slot: all the copies of a phase are queued first, one wait covers them, and only then are the values
+// read back -- so the round trips of a phase always overlap, whatever the instruction scheduler does with the
+// code that consumes them (plain loads were serialised by register reuse: profiles/r01_notes.md).
+// Slot s of lane l = smem + s*512 + l*16: a warp-wide 16-byte read of one slot is conflict free.
+__device__ __forceinline__ void stage16(uint32_t sdst, const void* g, bool pred)     // predicated off: zero fill, no global access
+{ asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(sdst), "l"(g), "r"(pred ? 16 : 0)); }
+__device__ __forceinline__ void stage4(uint32_t sdst, const void* g, bool pred)
+{ asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(sdst), "l"(g), "r"(pred ? 4 : 0)); }
+__device__ __forceinline__ void stage_wait() { asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ uint4 lds128(uint32_t sa) { uint4 v; asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(sa)); return v; }
+// queue the two blocks that hold [pos, pos+16); returns the offset of pos inside the first block
+__device__ __forceinline__ uint32_t stage_win(const SrcView& v, uint32_t slot, int pos, bool pred)
+{
+    uint32_t const P = pred ? (uint32_t)pos + v.D : v.D, blk = P >> 4, o = P & 15;
+    stage16(slot, v.g + blk, pred);
+    stage16(slot + 512, v.g + min(blk + 1, v.lastBlk), pred && o);
+    return o;
+}
+__device__ __forceinline__ Win16 take_win(uint32_t slot, uint32_t o)
+{
+    uint4 const a = lds128(slot), b = lds128(slot + 512);
+    uint64_t const q0 = (uint64_t)a.x | ((uint64_t)a.y << 32), q1 = (uint64_t)a.z | ((uint64_t)a.w << 32);
+    uint64_t const q2 = (uint64_t)b.x | ((uint64_t)b.y << 32), q3 = (uint64_t)b.z | ((uint64_t)b.w << 32);
+    bool const j = o >= 8; uint32_t const sft = (o & 7) * 8;
+    Win16 r;
+    r.lo = fsr64(j ? q1 : q0, j ? q2 : q1, sft);
+    r.hi = fsr64(j ? q2 : q1, j ? q3 : q2, sft);
+    return r;
+}
+constexpr uint32_t kMatchSlots = 24;             // 12 KB of shared memory per warp
+// 8 bytes at byte offset k (0..8) of a window
+__device__ __forceinline__ uint64_t win64(const Win16& w, uint32_t k) { return k >= 8 ? w.hi : fsr64(w.lo, w.hi, k * 8); }
+// 4 bytes at byte offset k (0..12) of a window
+__device__ __forceinline__ uint32_t win32(const Win16& w, uint32_t k)
+{
+    uint32_t const w0 = (uint32_t)w.lo, w1 = (uint32_t)(w.lo >> 32), w2 = (uint32_t)w.hi, w3 = (uint32_t)(w.hi >> 32);
+    uint32_t const j = k >> 2;
+    uint32_t const a = j == 0 ? w0 : (j == 1 ? w1 : (j == 2 ? w2 : w3)), b = j == 0 ? w1 : (j == 1 ? w2 : w3);
+    return __funnelshift_r(a, b, (k & 3) * 8);
+}
+// the window moved down by k bytes (0..16), zero filled at the top
+__device__ __forceinline__ Win16 win_from(const Win16& w, uint32_t k)
+{
+    Win16 r;
+    if (k >= 8) { r.lo = k >= 16 ? 0ull : w.hi >> ((k - 8) * 8); r.hi = 0; }
+    else { r.lo = fsr64(w.lo, w.hi, k * 8); r.hi = w.hi >> (k * 8); }
+    return r;
+}
+// number of equal leading bytes (0..n) of window a from byte ka and window b from byte kb; n <= 16 - max(ka, kb)
+__device__ __forceinline__ uint32_t win_common(const Win16& a, uint32_t ka, const Win16& b, uint32_t kb, uint32_t n)
+{
+    Win16 const x = win_from(a, ka), y = win_from(b, kb);
+    uint64_t const d0 = x.lo ^ y.lo, d1 = x.hi ^ y.hi;
+    uint32_t c = d0 ? (uint32_t)(__ffsll((long long)d0) - 1) >> 3 : 8u;
+    if (c == 8) c += d1 ? (uint32_t)(__ffsll((long long)d1) - 1) >> 3 : 8u;
+    return min(c, n);
+}
+
+__global__ void __launch_bounds__(32) enc_match_fast_kernel(EncPass p, const uint32_t* __restrict__ workList, uint32_t nWork)
+{
+    // Warp-uniform state machine: all 32 lanes (32 chunks) walk through the same phases in every iteration, so that the
+    // loads of a phase are issued together and their latencies overlap across lanes; a lane whose state does not
+    // need a phase is predicated off.  Left to diverge, the lanes' dependent-load chains execute one after another.
+    uint32_t const FULL = 0xFFFFFFFFu;
+    uint32_t const w = blockIdx.x * blockDim.x + threadIdx.x;
+    bool active = w < nWork;
+    uint32_t const item = active ? workList[w] : 0u;
+    EncItem& it = p.items[item];
+    uint32_t const hlog = it.hashLog, mls = it.minMatch;
+    int const srcSize = active ? (int)it.srcSize : 64;
+    const uint8_t* __restrict__ const src = p.src + it.srcOff;
+    SrcView V;
+    V.D = (uint32_t)((uintptr_t)src & 15);
+    V.g = (const uint4*)(src - V.D);
+    V.lastBlk = ((uint32_t)srcSize - 1 + V.D) >> 4;
+    uint32_t* __restrict__ const T = p.tables + it.tableOff;
+    uint32_t* __restrict__ const oLL = p.seqLL + (size_t)item * kEncSeqCap;
+    uint32_t* __restrict__ const oML = p.seqML + (size_t)item * kEncSeqCap;
+    uint32_t* __restrict__ const oOF = p.seqOF + (size_t)item * kEncSeqCap;
+    int const ilimit = srcSize - 8;
+    int ip0 = 1, anchor = 0;                         // first position is skipped (:129)
+    uint32_t rep1 = 1, rep2 = 0;                     // rep2 = 4 exceeds the history at frame start (:131-145)
+    uint32_t nseq = 0;
+    int step = 2, nextStep = ip0 + 128, d = 2;       // _start
+    bool afterMatch = false;                         // the greedy rep2 loop (:264-285) is still open at ip0
+    Win16 X; X.lo = 0; X.hi = 0; int xPos = -1000; uint32_t xLen = 16;   // carried source window: xLen valid bytes at xPos
+    __shared__ __align__(16) uint8_t s_slots[kMatchSlots * 512];
+    uint32_t const S0 = (uint32_t)__cvta_generic_to_shared(s_slots) + (threadIdx.x & 31) * 16;   // slot k of this lane = S0 + k*512
+    auto slot = [&](uint32_t k) { return S0 + k * 512; };
+    while (__any_sync(FULL, active)) {
+        // ---- schedule of the two speculative iterations ----
+        int const pA = ip0, dA = d;
+        bool const vA = active && (pA + dA + 1 < ilimit);       // loop condition ip3 < ilimit
+        int const pB = pA + dA;
+        int S = step, N = nextStep;
+        int const dB = S;
+        if (pB + S >= N) { S++; N += 128; }
+        bool const vB = vA && (pB + dB + 1 < ilimit);
+        int const pC = pB + dB;                                  // ip0 after the second iteration
+        int S2 = S, N2 = N;
+        int const dC = S2;
+        if (pC + S2 >= N2) { S2++; N2 += 128; }
+        bool const r2 = active && afterMatch && ip0 <= ilimit && rep2 > 0;
+        bool const pr = vA && rep1 != 0, prB = vB && rep1 != 0;
+        // ---- round trip 1: source window at ip0 (skipped when the previous iteration left it behind) ----
+        bool const needX = (vA || r2) && xPos != pA;
+        if (__any_sync(FULL, needX)) {
+            uint32_t const o = stage_win(V, slot(0), pA, needX);
+            stage_wait();
+            Win16 const nx = take_win(slot(0), o);
+            if (needX) { X = nx; xPos = pA; xLen = 16; }
+        }
+        // the window covers ip0, ip0+1, ip2, ip2+1 and the repcode probe of the second iteration for steps <= 5
+        bool const wide = vA && (dA + 9 > 16 || (vB && dA + dB + 4 > 16));
+        Win16 XB = X, XC = X; uint32_t kB = (uint32_t)dA, kC = (uint32_t)(dA + dB);
+        if (__any_sync(FULL, wide)) {                              // long literal runs only
+            uint32_t const ob = stage_win(V, slot(0), pB, wide), oc = stage_win(V, slot(2), pC, wide && vB);
+            stage_wait();
+            Win16 const nb = take_win(slot(0), ob), nc = take_win(slot(2), oc);
+            if (wide) { XB = nb; XC = nc; kB = 0; kC = 0; }
+        }
+        uint64_t const x0 = X.lo, x1 = win64(X, 1), x2 = win64(XB, kB), x3 = win64(XB, kB + 1);
+        uint32_t const h0 = hash_val(x0, hlog, mls), h1 = hash_val(x1, hlog, mls), h2 = hash_val(x2, hlog, mls), h3 = hash_val(x3, hlog, mls);
+        // ---- round trip 2: table entries (position + 2, 0 = empty), repcode sources ----
+        bool const farB = prB && dB + 4 > 16;
+        uint32_t const oRA = stage_win(V, slot(0), pB - (int)rep1, pr), oQ = stage_win(V, slot(2), pA - (int)rep2, r2);
+        uint32_t const oRB = stage_win(V, slot(4), pC - (int)rep1, farB);
+        stage4(slot(6), T + h0, vA); stage4(slot(6) + 4, T + h1, vA); stage4(slot(6) + 8, T + h2, vB); stage4(slot(6) + 12, T + h3, vB);
+        stage_wait();
+        uint4 const tv = lds128(slot(6));
+        uint32_t const t0 = tv.x, t1 = tv.y, t2 = tv.z, t3 = tv.w;
+        Win16 const RA = take_win(slot(0), oRA);                   // 16 bytes at ip2 - rep1 (the second probe sits dB bytes further)
+        Win16 RB = RA; uint32_t kRB = (uint32_t)dB;
+        if (farB) { RB = take_win(slot(4), oRB); kRB = 0; }
+        Win16 const Q = take_win(slot(2), oQ);                     // rep2 probe (:264)
+        // a probe sees the writes of the earlier probes of this window
+        uint32_t const c0 = t0;
+        uint32_t const c1 = h1 == h0 ? (uint32_t)pA + 2 : t1;
+        uint32_t const c2 = h2 == h1 ? (uint32_t)pA + 3 : (h2 == h0 ? (uint32_t)pA + 2 : t2);
+        uint32_t const c3 = h3 == h2 ? (uint32_t)pB + 2 : (h3 == h1 ? (uint32_t)pA + 3 : (h3 == h0 ? (uint32_t)pA + 2 : t3));
+        // ---- round trip 3: candidate bytes ----
+        bool const k0 = vA && c0, k1 = vA && c1, k2 = vB && c2, k3 = vB && c3;
+        uint32_t const o0 = stage_win(V, slot(8), (int)c0 - 2, k0), o1 = stage_win(V, slot(10), (int)c1 - 2, k1);
+        uint32_t const o2 = stage_win(V, slot(12), (int)c2 - 2, k2), o3 = stage_win(V, slot(14), (int)c3 - 2, k3);
+        stage_wait();
+        Win16 const C0 = take_win(slot(8), o0), C1 = take_win(slot(10), o1), C2 = take_win(slot(12), o2), C3 = take_win(slot(14), o3);
+        // ---- first event in the reference's order: open rep2 loop first, then the window ----
+        // type 3: rep2 match at ip0 (:264-285); 0: repcode at ip2; 1 / 2: hash match at ip0 / ip1; -1: none
+        int type = -1, pke = pA, dke = dA, cand = 0;
+        Win16 MW = Q;                  // window at the match source
+        Win16 SW = X; uint32_t kS = 0, lenS = xLen; // window that holds the match position, its byte offset inside, its valid bytes
+        uint32_t const lenB = wide ? 16u : xLen;    // valid bytes of XB / XC
+        if (r2 && (uint32_t)Q.lo == (uint32_t)x0) type = 3;
+        else if (vA) {
+            if (pr && (uint32_t)x2 == (uint32_t)RA.lo) { type = 0; MW = RA; SW = XB; kS = kB; lenS = lenB; }
+            else if (k0 && (uint32_t)C0.lo == (uint32_t)x0) { type = 1; cand = (int)c0 - 2; MW = C0; }
+            else if (k1 && (uint32_t)C1.lo == (uint32_t)x1) { type = 2; cand = (int)c1 - 2; MW = C1; kS = 1; }
+            else if (vB) {
+                pke = pB; dke = dB;
+                if (prB && win32(XC, kC) == win32(RB, kRB)) { type = 0; MW = RB; SW = XC; kS = kC; lenS = lenB; }
+                else if (k2 && (uint32_t)C2.lo == (uint32_t)x2) { type = 1; cand = (int)c2 - 2; MW = C2; SW = XB; kS = kB; lenS = lenB; }
+                else if (k3 && (uint32_t)C3.lo == (uint32_t)x3) { type = 2; cand = (int)c3 - 2; MW = C3; SW = XB; kS = kB + 1; lenS = lenB; }
+            }
+        }
+        uint32_t const kM = (type == 0 && pke == pB) ? kRB : 0u;   // byte offset of the match source inside MW
+        if (active && type != 3) afterMatch = false;             // the rep2 loop is closed: this iteration ran from _start
+        // ---- table writes that precede the event (`ip1 < ip0` insert of types 0/1 included, :254-257) ----
+        if (vA && type != 3) {
+            T[h0] = (uint32_t)pA + 2; T[h1] = (uint32_t)pA + 3;
+            if (vB && (type < 0 || pke == pB)) { T[h2] = (uint32_t)pB + 2; T[h3] = (uint32_t)pB + 3; }
+        }
+        if (type == 3) T[h0] = (uint32_t)pA + 2;                 // the rep2 loop inserts ip0 before advancing (:278)
+        // ---- match geometry ----
+        int mpos = 0, msrc = 0, mlen = 0, current0 = 0; uint32_t offcode = 0;
+        bool const ev = type >= 0;
+        if (type == 3) { mpos = pA; msrc = pA - (int)rep2; uint32_t const t = rep2; rep2 = rep1; rep1 = t; }
+        else if (type == 0) { mpos = pke + dke; msrc = mpos - (int)rep1; current0 = pke; }
+        else if (type > 0) { int const qe = pke + (type == 2 ? 1 : 0); mpos = qe; msrc = cand; rep2 = rep1; rep1 = (uint32_t)(qe - cand); offcode = rep1 + 2; current0 = qe; }
+        // forward extension (ZSTD_count :264): first from the windows already in registers, then 16 bytes per round
+        {
+            uint32_t const avail = min(lenS - kS, 16u - kM);       // bytes both windows hold from the match start
+            uint32_t const room = ev ? (uint32_t)(srcSize - mpos) : 0u;
+            uint32_t const n = min(avail, room);
+            uint32_t const c = ev ? win_common(SW, kS, MW, kM, n) : 0u;   // >= 4 by construction of the event
+            mlen = (int)c;
+            bool cnt = ev && c == n && (uint32_t)c < room;
+            while (__any_sync(FULL, cnt)) {
+                int const a = mpos + mlen, b = msrc + mlen;
+                uint32_t const oa = stage_win(V, slot(16), a, cnt), ob = stage_win(V, slot(18), b, cnt);
+                stage_wait();
+                Win16 const wa = take_win(slot(16), oa), wb = take_win(slot(18), ob);
+                if (cnt) {
+                    uint32_t const r = (uint32_t)(srcSize - a), nn = min(16u, r);
+                    uint32_t const cc = win_common(wa, 0, wb, 0, nn);
+                    mlen += (int)cc;
+                    cnt = cc == nn && nn < r;
+                }
+            }
+        }
+        // backward extension: one byte without anchor test for the repcode (:171), as far as it goes for hash matches (:236-247)
+        {
+            uint32_t const bA = type == 0 ? src[mpos - 1] : 0u, bB = type == 0 ? src[msrc - 1] : 1u;
+            if (type == 0) { int const back = bA == bB; mpos -= back; msrc -= back; mlen += back; }
+            bool ext = (type == 1 || type == 2) && mpos > anchor && msrc > 0;
+            while (__any_sync(FULL, ext)) {
+                uint32_t const a = ext ? src[mpos - 1] : 0u, b = ext ? src[msrc - 1] : 1u;
+                if (ext && a == b) { mpos--; msrc--; mlen++; ext = mpos > anchor && msrc > 0; } else ext = false;
+            }
+        }
+        // ---- sequence, post-match inserts (:251-263), state for the next iteration ----
+        int const mend = mpos + mlen;
+        bool const ins = ev && type != 3 && mend <= ilimit;
+        // the window at mend-2 serves the insert of ip0-2 and is the source window of the next iteration (ip0 = mend)
+        uint32_t const oNW = stage_win(V, slot(20), mend - 2, ev && mend <= ilimit);
+        stage_wait();
+        Win16 const NW = take_win(slot(20), oNW);
+        if (ev) {
+            oLL[nseq] = (uint32_t)(mpos - anchor); oOF[nseq] = offcode + 1; oML[nseq] = (uint32_t)mlen - 3;
+            nseq++;
+            if (type == 2 && pke + dke < mend) {      // `if (ip1 < ip0) hashTable[hash1] = ip1` with ip1 = old ip2
+                uint64_t xp;                                           // 8 bytes at ip2 of the event's iteration
+                if (pke == pA) xp = x2;
+                else if (kC + 8 <= lenB) xp = win_from(XC, kC).lo;
+                else xp = rd64(src + pke + dke);
+                T[hash_val(xp, hlog, mls)] = (uint32_t)(pke + dke) + 2;
+            }
+            if (ins) {
+                // 8 bytes at current0 + 2: inside the window of the event's iteration
+                bool const inB = pke == pB && wide;                    // otherwise everything sits in X
+                uint32_t const off2 = (uint32_t)(current0 + 2 - (inB ? pB : pA));
+                uint64_t xc;
+                if (off2 + 8 <= (inB ? 16u : xLen)) xc = win_from(inB ? XB : X, off2).lo;
+                else xc = rd64(src + current0 + 2);
+                T[hash_val(xc, hlog, mls)] = (uint32_t)current0 + 2 + 2;
+                T[hash_val(NW.lo, hlog, mls)] = (uint32_t)(mend - 2) + 2;
+            }
+            ip0 = mend; anchor = mend;
+            if (mend <= ilimit) { X = win_from(NW, 2); xPos = mend; xLen = 14; }   // 14 valid bytes: enough for a step-2 window
+            afterMatch = true;                        // the rep2 loop test runs first in the next iteration
+            step = 2; nextStep = ip0 + 128; d = 2;    // _start
+        } else if (active) {
+            if (!vB) active = false;                  // the loop condition failed in the first or second iteration: _cleanup
+            else { ip0 = pC; d = dC; step = S2; nextStep = N2; }
+        }
+    }
+    if (w < nWork) { it.nbSeq = nseq; it.lastLL = (uint32_t)(srcSize - anchor); }
+}
+
 __global__ void __launch_bounds__(32) enc_match_kernel(EncPass p, const uint32_t* __restrict__ workList, uint32_t nWork)
 {
     uint32_t const w = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1305,10 +1592,11 @@ bool enc_compress_device(EncArena& A, cudaStream_t stream, cudaEvent_t* ev, size
     for (size_t base = 0; base < n; base += kEncMaxItemsPerPass) {
         size_t const m = std::min(kEncMaxItemsPerPass, n - base);
         if (!I.hItems.ensure(m * sizeof(EncItem)) || !I.items.ensure(m * sizeof(EncItem)) || !I.results.ensure(m * 8) || !I.hResults.ensure(m * 8)) { t_encErr = "out of memory (items)"; return false; }
-        if (!I.hWork.ensure(m * 8) || !I.workLists.ensure(m * 8)) { t_encErr = "out of memory (work lists)"; return false; }
+        if (!I.hWork.ensure(m * 12) || !I.workLists.ensure(m * 12)) { t_encErr = "out of memory (work lists)"; return false; }
         EncItem* hi = (EncItem*)I.hItems.p;
-        uint32_t* const warpList = (uint32_t*)I.hWork.p; uint32_t* const serialList = warpList + m;
-        uint32_t nWarp = 0, nSerial = 0;
+        uint32_t* const warpList = (uint32_t*)I.hWork.p; uint32_t* const serialList = warpList + m; uint32_t* const fastList = serialList + m;
+        uint32_t nWarp = 0, nSerial = 0, nFast = 0;
+        static bool const useWarp = getenv("ZSTDB200_ENC_WARP") != nullptr;    // A/B switch: warp-per-chunk kernel with shared-memory tables
         size_t tableEntries = 0;
         for (size_t i = 0; i < m; i++) {
             size_t const ss = srcSize[base + i];
@@ -1322,8 +1610,9 @@ bool enc_compress_device(EncArena& A, cudaStream_t stream, cudaEvent_t* ev, size
             if (ss < 7 || ss > kBlockSizeMax) continue;              // raw block / unsupported: no match finding
             // ZSTD_fast with a table that fits shared memory -> warp-parallel kernel; everything else (level-2 2^15 tables,
             // dfast's two tables) keeps its tables in HBM/L2 and is parsed by the lane-serial kernel
-            if (c.strategy == 1 && c.hashLog <= kWarpMatchMaxHashLog && ss >= 64) { warpList[nWarp++] = (uint32_t)i; continue; }
-            serialList[nSerial++] = (uint32_t)i;
+            if (useWarp && c.strategy == 1 && c.hashLog <= kWarpMatchMaxHashLog && ss >= 64) { warpList[nWarp++] = (uint32_t)i; continue; }
+            if (c.strategy == 1 && ss >= 64) { fastList[nFast++] = (uint32_t)i; }
+            else serialList[nSerial++] = (uint32_t)i;
             e.tableOff = (uint32_t)tableEntries;
             tableEntries += ((size_t)1 << c.hashLog) + (c.strategy == 2 ? ((size_t)1 << c.chainLog) : 0);
         }
@@ -1332,7 +1621,7 @@ bool enc_compress_device(EncArena& A, cudaStream_t stream, cudaEvent_t* ev, size
             !I.seqOF.ensure(m * (size_t)kEncSeqCap * 4) || !I.lit.ensure(m * (size_t)kEncLitStride) || !I.stateBits.ensure(m * (size_t)kEncSeqCap * 8)) { t_encErr = "out of memory (arena)"; return false; }
         ENC_CUDA(cudaMemcpyAsync(I.items.p, hi, m * sizeof(EncItem), cudaMemcpyHostToDevice, stream));
         ENC_CUDA(cudaEventRecord(ev[14], stream));
-        ENC_CUDA(cudaMemcpyAsync(I.workLists.p, I.hWork.p, m * 8, cudaMemcpyHostToDevice, stream));
+        ENC_CUDA(cudaMemcpyAsync(I.workLists.p, I.hWork.p, m * 12, cudaMemcpyHostToDevice, stream));
         if (tableEntries) ENC_CUDA(cudaMemsetAsync(I.tables.p, 0, tableEntries * 4, stream));      // tables are zeroed per frame (ZstdCompress.cs:2472,2481)
         EncPass p;
         p.items = (EncItem*)I.items.p; p.nItems = (uint32_t)m; p.src = d_src; p.dst = d_dst; p.tables = (uint32_t*)I.tables.p;
@@ -1341,10 +1630,11 @@ bool enc_compress_device(EncArena& A, cudaStream_t stream, cudaEvent_t* ev, size
         enc_set_attrs();
         if (nWarp) enc_match_warp_kernel<<<nWarp, 32, (1u << kWarpMatchMaxHashLog) * 4, stream>>>(p, (const uint32_t*)I.workLists.p);
         if (nSerial) enc_match_kernel<<<(nSerial + 31) / 32, 32, 0, stream>>>(p, (const uint32_t*)I.workLists.p + m, nSerial);
+        if (nFast) enc_match_fast_kernel<<<(nFast + 31) / 32, 32, 0, stream>>>(p, (const uint32_t*)I.workLists.p + 2 * m, nFast);
         ENC_CUDA(cudaEventRecord(ev[15], stream));
         enc_entropy_kernel<<<(unsigned)m, kEntThreads, 0, stream>>>(p);
         ENC_CUDA(cudaEventRecord(ev[16], stream));
-        *launches += 1 + (nWarp ? 1 : 0) + (nSerial ? 1 : 0) + (tableEntries ? 1 : 0);
+        *launches += 1 + (nWarp ? 1 : 0) + (nSerial ? 1 : 0) + (nFast ? 1 : 0) + (tableEntries ? 1 : 0);
         ENC_CUDA(cudaMemcpyAsync(I.hResults.p, I.results.p, m * 8, cudaMemcpyDeviceToHost, stream));
         ENC_CUDA(cudaStreamSynchronize(stream));
         ENC_CUDA(cudaGetLastError());
