@@ -703,14 +703,18 @@ __global__ void __launch_bounds__(kHufThreads) dec_huf_kernel(DecPass p)
 //  One step = three table loads, three bit-group reads (offset extra | matchLength+litLength extra | the three
 //  state updates: each group is <= 32 bits), all branch-free.
 // =====================================================================================================
-constexpr int kSeqItemsPerCta = 10;            // 10 x (5 KB tables + 256 B ring) -> 4 CTAs (40 items) per SM
-constexpr uint32_t kSeqChunk = 64;             // 4 x 64 B of ring per item
-constexpr uint32_t kSeqSmemBytes = kSeqItemsPerCta * (kFseTableEntries * 4 + 4 * kSeqChunk);
+constexpr int kSeqItemsPerCta = 14;            // 14 x (3.75 KB tables + 128 B ring) = 54.25 KB -> 4 CTAs = 56 items per SM: 8192 items are resident in ONE wave
+constexpr uint32_t kSeqChunk = 32;             // 4 x 32 B of ring per item (a step consumes <= 12 bytes and reads <= 8 below)
+// shared-memory table entry = 24 bits: u16 {nbBits 4 | addBits 5 | symbol 6 | next-state base bit 8} + u8 {next-state base bits 0..7}
+constexpr uint32_t kSeqTab16Bytes = kFseTableEntries * 2, kSeqTab8Bytes = kFseTableEntries;
+constexpr uint32_t kSeqItemBytes = kSeqTab16Bytes + kSeqTab8Bytes;
+constexpr uint32_t kSeqSmemBytes = kSeqItemsPerCta * (kSeqItemBytes + 4 * kSeqChunk);
+__device__ __forceinline__ uint32_t lds8(uint32_t saddr) { uint16_t v; asm volatile("ld.shared.u8 %0, [%1];" : "=h"(v) : "r"(saddr)); return v; }
 
 __global__ void __launch_bounds__(32) dec_seq_kernel(DecPass p)
 {
-    extern __shared__ __align__(256) uint8_t s_seq_raw[];   // [kSeqItemsPerCta] rings of 256 B, then [kSeqItemsPerCta][kFseTableEntries] tables
-    uint32_t* const s_seqTab = (uint32_t*)(s_seq_raw + kSeqItemsPerCta * 4 * kSeqChunk);
+    extern __shared__ __align__(256) uint8_t s_seq_raw[];   // [kSeqItemsPerCta] rings of 128 B, then per item: u16[1280] | u8[1280] tables
+    uint8_t* const s_tabs = s_seq_raw + kSeqItemsPerCta * 4 * kSeqChunk;
     __shared__ uint32_t s_llBase[64], s_mlBase[64];
     uint32_t const nWork = p.counters[1];
     uint32_t const first = blockIdx.x * kSeqItemsPerCta;
@@ -720,8 +724,14 @@ __global__ void __launch_bounds__(32) dec_seq_kernel(DecPass p)
     for (uint32_t k = 0; k < nHere; k++) {
         uint32_t const item = p.seqList[first + k];
         const uint4* g = (const uint4*)(p.fseTable + (size_t)item * kFseTableEntries);
-        uint4* s = (uint4*)(s_seqTab + k * kFseTableEntries);
-        for (uint32_t u = lane; u < kFseTableEntries / 4; u += 32) s[u] = g[u];
+        uint2* const s16 = (uint2*)(s_tabs + k * kSeqItemBytes);
+        uint32_t* const s8 = (uint32_t*)(s_tabs + k * kSeqItemBytes + kSeqTab16Bytes);
+        for (uint32_t u = lane; u < kFseTableEntries / 4; u += 32) {       // 4 compact u32 entries -> 4 x u16 + 4 x u8
+            uint4 const e = g[u];
+            auto h = [](uint32_t x) { return (x & 0x7FFFu) | (((x >> 24) & 1u) << 15); };   // nb | add | sym | next bit 8
+            s16[u] = make_uint2(h(e.x) | (h(e.y) << 16), h(e.z) | (h(e.w) << 16));
+            s8[u] = ((e.x >> 16) & 0xFF) | (((e.y >> 16) & 0xFF) << 8) | (((e.z >> 16) & 0xFF) << 16) | (((e.w >> 16) & 0xFF) << 24);
+        }
     }
     for (uint32_t u = lane; u < 64; u += 32) { s_llBase[u] = u < 36 ? c_LL_base[u] : 0u; s_mlBase[u] = u < 53 ? c_ML_base[u] : 0u; }
     __syncwarp();
@@ -729,8 +739,8 @@ __global__ void __launch_bounds__(32) dec_seq_kernel(DecPass p)
     uint32_t const item = p.seqList[first + lane];
     DecItem& it = p.items[item];
     if (it.status != kStRunning) return;
-    uint32_t const tS = (uint32_t)__cvta_generic_to_shared(s_seqTab + lane * kFseTableEntries);
-    uint32_t const tLL = tS + kFseLLOff * 4, tML = tS + kFseMLOff * 4, tOF = tS + kFseOFOff * 4;
+    // state registers hold the entry INDEX (table offset included); the u16 part sits at t16 + 2*idx, the u8 part at t8 + idx
+    uint32_t const t16 = (uint32_t)__cvta_generic_to_shared(s_tabs + lane * kSeqItemBytes), t8 = t16 + kSeqTab16Bytes;
     uint32_t const llBaseS = (uint32_t)__cvta_generic_to_shared(s_llBase), mlBaseS = (uint32_t)__cvta_generic_to_shared(s_mlBase);
     uint2* const oSeq = p.seq + (size_t)item * kSeqCap;
     const uint8_t* const src = p.src + it.srcOff;
@@ -747,14 +757,15 @@ __global__ void __launch_bounds__(32) dec_seq_kernel(DecPass p)
         // ZSTD_initFseState x3 in the order LL, OF, ML (:2702-2704)
         uint32_t const llLog = it.llLog, ofLog = it.ofLog, mlLog = it.mlLog;
         uint32_t x = br.peek32(G);
-        uint32_t aL = tLL + top_bits(x, llLog) * 4; x <<= llLog;
-        uint32_t aO = tOF + top_bits(x, ofLog) * 4; x <<= ofLog;
-        uint32_t aM = tML + top_bits(x, mlLog) * 4;
+        uint32_t aL = kFseLLOff + top_bits(x, llLog); x <<= llLog;
+        uint32_t aO = kFseOFOff + top_bits(x, ofLog); x <<= ofLog;
+        uint32_t aM = kFseMLOff + top_bits(x, mlLog);
         G -= llLog + ofLog + mlLog;
         if ((int32_t)G < gz) err = kCorruptionDetected;
         for (uint32_t n = 0; n < nbSeq && !err; n++) {
             br.advance(G);
-            uint32_t const eL = lds32(aL), eO = lds32(aO), eM = lds32(aM);
+            uint32_t const eL = lds16(t16 + 2 * aL), eO = lds16(t16 + 2 * aO), eM = lds16(t16 + 2 * aM);
+            uint32_t const nL = lds8(t8 + aL), nO = lds8(t8 + aO), nM = lds8(t8 + aM);
             uint32_t const llBits = (eL >> 4) & 31, mlBits = (eM >> 4) & 31, ofBits = (eO >> 4) & 31;
             uint32_t const nbL = eL & 15, nbM = eM & 15, nbO = eO & 15;
             // stream order: offset extra, matchLength extra, litLength extra, then LL / ML / OF state bits (:2397-2480)
@@ -764,10 +775,10 @@ __global__ void __launch_bounds__(32) dec_seq_kernel(DecPass p)
             uint32_t const ofExtra = top_bits(xA, ofBits);
             uint32_t const ml = lds32(mlBaseS + mlSym * 4) + top_bits(xB, mlBits);
             uint32_t const ll = lds32(llBaseS + llSym * 4) + top_bits(xB << mlBits, llBits);     // mlBits <= 16
-            aL = tLL + ((eL >> 16) + top_bits(xC, nbL)) * 4;
+            aL = kFseLLOff + (nL | ((eL >> 15) << 8)) + top_bits(xC, nbL);
             uint32_t const xC2 = xC << nbL;
-            aM = tML + ((eM >> 16) + top_bits(xC2, nbM)) * 4;
-            aO = tOF + ((eO >> 16) + top_bits(xC2 << nbM, nbO)) * 4;
+            aM = kFseMLOff + (nM | ((eM >> 15) << 8)) + top_bits(xC2, nbM);
+            aO = kFseOFOff + (nO | ((eO >> 15) << 8)) + top_bits(xC2 << nbM, nbO);
             bool const overRead = (int32_t)G2 < gz;                      // the extra bits must exist; the last state update may run dry
             bool const dry = (int32_t)G3 < gz;
             G = G3;
@@ -1117,6 +1128,7 @@ static void dec_set_attrs()
     cudaFuncSetAttribute(dec_seq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSeqSmemBytes);
     cudaFuncSetAttribute(dec_exec_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kExecWarps * kExecTileMem);
     cudaFuncSetAttribute(dec_exec_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+    cudaFuncSetAttribute(dec_seq_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
     done[dev] = true;
 }
 
