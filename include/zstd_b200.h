@@ -54,7 +54,8 @@ ZSTDB200_API size_t     ZSTD_freeDCtx(ZSTD_DCtx* dctx);                         
 ZSTDB200_API size_t     ZSTD_decompressDCtx(ZSTD_DCtx* dctx, void* dst, size_t dstCapacity,
                                             const void* src, size_t srcSize);                      /* :30 */
 ZSTDB200_API size_t     ZSTD_compressBound(size_t srcSize);                                        /* :34 */
-/* param: ZSTD_c_compressionLevel = 100 (levels 0..3; 0 means 3), ZSTD_c_checksumFlag = 201 (0 only in this round);
+/* param: ZSTD_c_compressionLevel = 100 (levels 0..3; 0 means 3), ZSTD_c_checksumFlag = 201 (0/1: XXH64 trailer, U/ZstdCompress.cs:5641-5652),
+ * ZSTD_c_contentSizeFlag = 200 (1 only);
  * anything else -> ZSTD_error_parameter_unsupported. */
 ZSTDB200_API size_t     ZSTD_CCtx_setParameter(ZSTD_CCtx* cctx, int param, int value);             /* :37 */
 /* needed by the safe wrappers in addition (Decompressor.cs:53, ThrowHelper.cs:12-13) */

@@ -145,3 +145,26 @@ def test_corrupted_payload_never_crashes(dec):
                 assert r == out[:rv].tobytes()
         else:
             assert isinstance(r, ZstdException)
+
+
+def test_frame_checksum_is_verified(dec):
+    """ZSTD_c_checksumFlag frames (SURVEY 8f.1): the XXH64 trailer is checked on the GPU (ZstdDecompress.cs:1186-1207);
+    a damaged trailer or damaged content is checksum_wrong (22), exactly as the oracle reports."""
+    from zstdsharp_b200 import ZstdException, ZSTD_ErrorCode
+    o, z = oracle(), libzstd()
+    sizes = [0, 1, 3, 4, 7, 8, 31, 32, 33, 63, 64, 255, 256, 257, 1000, 4096, 65537, FRAME]
+    data = dg.silesia_mix(2 * FRAME)
+    frames = [o.compress(data[:n], 1, checksum=1) for n in sizes]
+    assert dec.UnwrapBatch(frames) == [data[:n].tobytes() for n in sizes]
+    big = dg.text_like(4 * FRAME)[: 3 * FRAME + 777]                      # multi-block frame, one checksum over all blocks
+    assert dec.Unwrap(z.compress(big, 3, checksum=1)) == big.tobytes()
+    good = o.compress(data[:FRAME], 1, checksum=1)
+    assert len(good) == len(o.compress(data[:FRAME], 1)) + 4               # ZstdNetTests.cs:65
+    bad_trailer = bytearray(good); bad_trailer[-1] ^= 0x40
+    raw = bytearray(o.compress(dg.incompressible(FRAME), 1, checksum=1))   # raw block: content damage is only caught by the checksum
+    raw[5000] ^= 1
+    res = dec.UnwrapBatch([bytes(bad_trailer), bytes(raw), good], raise_on_error=False)
+    for r, f in zip(res[:2], (bad_trailer, raw)):
+        assert isinstance(r, ZstdException) and r.Code == ZSTD_ErrorCode.checksum_wrong
+        assert o.error_code(o.decompress_raw(bytes(f), FRAME)[0]) == 22
+    assert res[2] == data[:FRAME].tobytes()

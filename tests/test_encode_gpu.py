@@ -132,3 +132,25 @@ def test_frame_header_known_answers(comp):
     assert g[:6] == bytes.fromhex("28b52ffd2064")
     h = comp.Wrap(bytes(300))
     assert h[:7] == bytes.fromhex("28b52ffd602c00")
+
+
+def test_checksum_flag(comp, dec):
+    """ZSTD_c_checksumFlag = 1: 4 more bytes per frame (ZstdNetTests.cs:65), byte-identical to the oracle,
+    accepted by libzstd (which verifies the XXH64 trailer) and by the GPU decoder."""
+    from zstdsharp_b200 import ZSTD_cParameter
+    o, z = oracle(), libzstd()
+    data = dg.silesia_mix(6 * FRAME)
+    chunks = _chunks(data) + [data[:n] for n in (0, 1, 5, 31, 32, 33, 100, 255, 256, 300, 4097, 70000)] + [dg.incompressible(FRAME)]
+    comp.Level = 1
+    plain = comp.WrapBatch(chunks)
+    comp.SetParameter(ZSTD_cParameter.ZSTD_c_checksumFlag, 1)
+    try:
+        frames = comp.WrapBatch(chunks)
+    finally:
+        comp.SetParameter(ZSTD_cParameter.ZSTD_c_checksumFlag, 0)
+    for c, f, q in zip(chunks, frames, plain):
+        assert len(f) == len(q) + 4
+        want = o.compress(c, 1, checksum=1)
+        assert f == want, _first_diff(f, want)
+        assert z.decompress(f, max(c.size, 1)) == c.tobytes()
+    assert dec.UnwrapBatch(frames) == [c.tobytes() for c in chunks]

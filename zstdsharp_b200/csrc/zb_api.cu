@@ -435,7 +435,6 @@ static size_t compress_batch_host(Engine& E, size_t n, int level, int checksum, 
     if (!E.init() || !E.bind()) return (size_t)make_error(kGeneric);
     E.launches = 0; memset(E.timings, 0, sizeof(E.timings));
     if (n == 0) return 0;
-    if (checksum) { for (size_t i = 0; i < n; i++) result[i] = (size_t)make_error(kParameterUnsupported); return 0; }
     std::vector<uint64_t> sOff, dOff; size_t sTotal = 0;
     cudaEventRecord(E.ev[10], E.stream);
     if (!upload_items(E, n, src, srcSize, sOff, &sTotal)) return (size_t)make_error(kMemoryAllocation);
@@ -446,7 +445,7 @@ static size_t compress_batch_host(Engine& E, size_t n, int level, int checksum, 
     dTotal += 16;
     if (!E.dDst.ensure(dTotal)) return (size_t)make_error(kMemoryAllocation);
     std::vector<size_t> r(n);
-    if (!enc_compress_device(E.enc, E.stream, E.ev, n, level, E.dSrc.as<uint8_t>(), sOff.data(), srcSize, E.dDst.as<uint8_t>(), dOff.data(), slotCap.data(), r.data(), E.timings, &E.launches))
+    if (!enc_compress_device(E.enc, E.stream, E.ev, n, level, checksum, E.dSrc.as<uint8_t>(), sOff.data(), srcSize, E.dDst.as<uint8_t>(), dOff.data(), slotCap.data(), r.data(), E.timings, &E.launches))
         { set_error(enc_last_error()); return (size_t)make_error(kGeneric); }
     cudaEventRecord(E.ev[12], E.stream);
     // results that do not fit the caller's capacity become dstSize_tooSmall (ZstdCompress.cs:4690-4800 error paths)
@@ -592,8 +591,8 @@ size_t ZSTD_CCtx_setParameter(ZSTD_CCtx* cctx, int param, int value)
         cctx->level = value; return 0;
     }
     if (param == 201) {   // ZSTD_c_checksumFlag
-        if (value != 0) return (size_t)make_error(zb::kParameterUnsupported);
-        cctx->checksum = 0; return 0;
+        if (value != 0 && value != 1) return (size_t)make_error(zb::kParameterOutOfBound);
+        cctx->checksum = value; return 0;
     }
     if (param == 200) { if (value != 1) return (size_t)make_error(zb::kParameterUnsupported); return 0; }   // ZSTD_c_contentSizeFlag: always on
     return (size_t)make_error(zb::kParameterUnsupported);
@@ -652,7 +651,7 @@ size_t ZSTDB200_compressBatchDevice(ZSTD_CCtx* cctx, size_t n, int level, const 
     E.launches = 0; memset(E.timings, 0, sizeof(E.timings));
     if (n == 0) return 0;
     if (level < 0 || level > 3) { for (size_t i = 0; i < n; i++) result[i] = (size_t)make_error(zb::kParameterUnsupported); return 0; }
-    if (!zb::enc_compress_device(E.enc, E.stream, E.ev, n, level, (const uint8_t*)d_src, srcOffset, srcSize, (uint8_t*)d_dst, dstOffset, dstCapacity, result, E.timings, &E.launches))
+    if (!zb::enc_compress_device(E.enc, E.stream, E.ev, n, level, cctx->checksum, (const uint8_t*)d_src, srcOffset, srcSize, (uint8_t*)d_dst, dstOffset, dstCapacity, result, E.timings, &E.launches))
         { zb::set_error(zb::enc_last_error()); return (size_t)make_error(zb::kGeneric); }
     return 0;
 }

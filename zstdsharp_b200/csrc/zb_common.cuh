@@ -79,4 +79,57 @@ __device__ __forceinline__ uint32_t ld_le24(const uint8_t* p) { return (uint32_t
 __device__ __forceinline__ uint32_t ld_le32(const uint8_t* p) { return (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24); }
 __device__ __forceinline__ uint64_t ld_le64(const uint8_t* p) { return (uint64_t)ld_le32(p) | ((uint64_t)ld_le32(p + 4) << 32); }
 
+// ---- XXH64 (Xxhash.cs) for the optional frame checksum: ZSTD_c_checksumFlag, low 32 bits stored after the last block
+// (ZstdCompress.cs:5641-5652; verified in ZstdDecompress.cs:1186-1207).  One warp hashes one buffer: all lanes fetch
+// 8 bytes each (256 coalesced bytes = 8 stripes per round, next round prefetched), lanes 0..3 own the four accumulators
+// and pick their words up with shuffles.  Every lane returns the hash.  `p` may have any alignment.
+__device__ __forceinline__ uint64_t xxh_rotl(uint64_t x, int r) { return (x << r) | (x >> (64 - r)); }
+__device__ __forceinline__ uint64_t xxh_round(uint64_t acc, uint64_t in)
+{ acc += in * 0xC2B2AE3D27D4EB4FULL; acc = xxh_rotl(acc, 31); return acc * 0x9E3779B185EBCA87ULL; }
+__device__ __forceinline__ uint64_t xxh_merge(uint64_t acc, uint64_t v)
+{ v = xxh_round(0, v); acc ^= v; return acc * 0x9E3779B185EBCA87ULL + 0x85EBCA77C2B2AE63ULL; }
+__device__ __forceinline__ uint64_t xxh_ld64(const uint8_t* p)       // unaligned 8-byte read, L2-coherent (the buffer may have just been written)
+{
+    uintptr_t const a = (uintptr_t)p; const uint32_t* w = (const uint32_t*)(a & ~(uintptr_t)3); uint32_t const sh = (uint32_t)(a & 3) * 8;
+    uint32_t const w0 = __ldcg(w), w1 = __ldcg(w + 1), w2 = sh ? __ldcg(w + 2) : 0u;
+    return (uint64_t)__funnelshift_r(w0, w1, sh) | ((uint64_t)__funnelshift_r(w1, w2, sh) << 32);
+}
+__device__ inline uint64_t xxh64_warp(const uint8_t* p, uint32_t len, uint32_t lane)
+{
+    uint64_t const P1 = 0x9E3779B185EBCA87ULL, P2 = 0xC2B2AE3D27D4EB4FULL, P3 = 0x165667B19E3779F9ULL, P4 = 0x85EBCA77C2B2AE63ULL, P5 = 0x27D4EB2F165667C5ULL;
+    uint32_t const FULL = 0xFFFFFFFFu;
+    uint64_t h;
+    uint32_t pos = 0;
+    if (len >= 32) {
+        uint64_t v = lane == 0 ? P1 + P2 : (lane == 1 ? P2 : (lane == 2 ? 0ull : 0ull - P1));   // seed 0
+        uint32_t const nStripes = len >> 5;
+        uint64_t cur = (8 * lane + 8 <= nStripes * 32) ? xxh_ld64(p + 8 * lane) : 0ull;
+        for (uint32_t s0 = 0; s0 < nStripes; s0 += 8) {
+            uint32_t const nextOff = (s0 + 8) * 32 + 8 * lane;
+            uint64_t const nxt = (nextOff + 8 <= nStripes * 32) ? xxh_ld64(p + nextOff) : 0ull;
+            uint32_t const m = min(8u, nStripes - s0);
+#pragma unroll
+            for (uint32_t k = 0; k < 8; k++) {
+                uint64_t const in = __shfl_sync(FULL, cur, (4 * k + lane) & 31);       // lane a < 4 takes word 4k + a of the round
+                if (k < m) v = xxh_round(v, in);
+            }
+            cur = nxt;
+        }
+        uint64_t const v1 = __shfl_sync(FULL, v, 0), v2 = __shfl_sync(FULL, v, 1), v3 = __shfl_sync(FULL, v, 2), v4 = __shfl_sync(FULL, v, 3);
+        h = xxh_rotl(v1, 1) + xxh_rotl(v2, 7) + xxh_rotl(v3, 12) + xxh_rotl(v4, 18);
+        h = xxh_merge(h, v1); h = xxh_merge(h, v2); h = xxh_merge(h, v3); h = xxh_merge(h, v4);
+        pos = nStripes * 32;
+    } else h = P5;
+    h += (uint64_t)len;
+    // tail (< 32 bytes): every lane computes it redundantly
+    while (pos + 8 <= len) { h ^= xxh_round(0, xxh_ld64(p + pos)); h = xxh_rotl(h, 27) * P1 + P4; pos += 8; }
+    if (pos + 4 <= len) {
+        uint32_t const w = (uint32_t)__ldcg(p + pos) | ((uint32_t)__ldcg(p + pos + 1) << 8) | ((uint32_t)__ldcg(p + pos + 2) << 16) | ((uint32_t)__ldcg(p + pos + 3) << 24);
+        h ^= (uint64_t)w * P1; h = xxh_rotl(h, 23) * P2 + P3; pos += 4;
+    }
+    while (pos < len) { h ^= (uint64_t)__ldcg(p + pos) * P5; h = xxh_rotl(h, 11) * P1; pos++; }
+    h ^= h >> 33; h *= P2; h ^= h >> 29; h *= P3; h ^= h >> 32;
+    return h;
+}
+
 }  // namespace zb

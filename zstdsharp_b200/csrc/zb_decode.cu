@@ -1083,8 +1083,13 @@ __global__ void __launch_bounds__(kExecWarps * 32) dec_exec_kernel(DecPass p)
         L.to_global(dst + tileBase, litPos, lastLL, lane);
         blockOut = tileBase + lastLL - outBase;
     }
-    __syncwarp();
+    __threadfence_block(); __syncwarp();
     // ---- end of block bookkeeping (ZSTD_decompressFrame loop tail, ZstdDecompress.cs:1156-1212) ----
+    // frame checksum: low 32 bits of XXH64 over the regenerated frame (:1186-1207), hashed by the whole warp
+    uint32_t checkCalc = 0;
+    bool const wantCheck = it.lastBlock && it.checksumFlag && (it.srcSize - it.srcPos >= 4) &&
+                           !(it.hasFcs && (uint64_t)(outBase + blockOut - it.frameStart) != it.fcs);
+    if (wantCheck) checkCalc = (uint32_t)xxh64_warp(dst + it.frameStart, outBase + blockOut - it.frameStart, lane);
     if (lane == 0) {
         it.outPos = outBase + blockOut;
         if (it.lastBlock) {
@@ -1092,7 +1097,8 @@ __global__ void __launch_bounds__(kExecWarps * 32) dec_exec_kernel(DecPass p)
             if (it.hasFcs && (uint64_t)(it.outPos - it.frameStart) != it.fcs) err = kCorruptionDetected;
             uint32_t pos = it.srcPos;
             if (!err && it.checksumFlag) {
-                if (it.srcSize - pos < 4) err = kChecksumWrong; else pos += 4;   // XXH64 content check: see DESIGN.md (next row f.1)
+                if (it.srcSize - pos < 4) err = kChecksumWrong;
+                else { if (ld_le32(src + pos) != checkCalc) err = kChecksumWrong; pos += 4; }
             }
             if (err) { it.status = kStError; it.errCode = err; }
             else {

@@ -76,6 +76,7 @@ struct EncPass {
     uint8_t* litBuf;        // gathered literals
     uint64_t* stateBits;    // per sequence: FSE state bits of OF | ML | LL (13 bits each: 9 value + 4 count)
     uint64_t* results;
+    uint32_t checksumFlag;  // ZSTD_c_checksumFlag: append the low 32 bits of XXH64(src) to every frame
 };
 
 __device__ __forceinline__ uint32_t rd32(const uint8_t* p)
@@ -1198,7 +1199,7 @@ __global__ void __launch_bounds__(kEntThreads) enc_entropy_kernel(EncPass p)
         fhSize = 4 + 1 + (fcsCode == 0 ? 1 : (fcsCode == 1 ? 2 : 4));      // singleSegment always holds: windowSize >= srcSize
         if (tid == 0) {
             dst[0] = 0x28; dst[1] = 0xB5; dst[2] = 0x2F; dst[3] = 0xFD;
-            dst[4] = (uint8_t)((1u << 5) + (fcsCode << 6));
+            dst[4] = (uint8_t)((p.checksumFlag ? 4u : 0u) + (1u << 5) + (fcsCode << 6));   // FHD: checksum bit 2, singleSegment bit 5, fcsID bits 6-7 (:4823-4829)
             if (fcsCode == 0) dst[5] = (uint8_t)srcSize;
             else if (fcsCode == 1) { uint32_t const v = srcSize - 256; dst[5] = (uint8_t)v; dst[6] = (uint8_t)(v >> 8); }
             else { dst[5] = (uint8_t)srcSize; dst[6] = (uint8_t)(srcSize >> 8); dst[7] = (uint8_t)(srcSize >> 16); dst[8] = (uint8_t)(srcSize >> 24); }
@@ -1209,7 +1210,12 @@ __global__ void __launch_bounds__(kEntThreads) enc_entropy_kernel(EncPass p)
     bool raw = false;
     uint32_t cSize = 0;
     if (srcSize == 0) {                                         // ZSTD_writeEpilogue: one empty last raw block (:5621-5631)
-        if (tid == 0) { blk[0] = 1; blk[1] = 0; blk[2] = 0; p.results[item] = fhSize + 3; }
+        if (tid == 0) {
+            blk[0] = 1; blk[1] = 0; blk[2] = 0;
+            uint32_t total = fhSize + 3;
+            if (p.checksumFlag) { uint32_t const c = 0x51D8E999u; /* low 32 bits of XXH64("", seed 0) = 0xEF46DB3751D8E999 */ dst[total] = (uint8_t)c; dst[total + 1] = (uint8_t)(c >> 8); dst[total + 2] = (uint8_t)(c >> 16); dst[total + 3] = (uint8_t)(c >> 24); total += 4; }
+            p.results[item] = total;
+        }
         return;
     }
     uint32_t const nbSeq = it.nbSeq;
@@ -1520,18 +1526,27 @@ __global__ void __launch_bounds__(kEntThreads) enc_entropy_kernel(EncPass p)
         if (cSize >= srcSize - ((srcSize >> 6) + 2)) raw = true;
     }
     __syncthreads();
+    uint32_t total;
     if (raw) {          // ZSTD_noCompressBlock (ZstdCompressInternal.cs:102)
         for (uint32_t k = tid; k < srcSize; k += kEntThreads) dst[payload + k] = src[k];
         if (tid == 0) {
             uint32_t const h = 1 + (0u << 1) + (srcSize << 3);
             blk[0] = (uint8_t)h; blk[1] = (uint8_t)(h >> 8); blk[2] = (uint8_t)(h >> 16);
-            p.results[item] = payload + srcSize;
         }
-    } else if (tid == 0) {
-        uint32_t const h = 1 + (2u << 1) + (cSize << 3);
-        blk[0] = (uint8_t)h; blk[1] = (uint8_t)(h >> 8); blk[2] = (uint8_t)(h >> 16);
-        p.results[item] = payload + cSize;
+        total = payload + srcSize;
+    } else {
+        if (tid == 0) {
+            uint32_t const h = 1 + (2u << 1) + (cSize << 3);
+            blk[0] = (uint8_t)h; blk[1] = (uint8_t)(h >> 8); blk[2] = (uint8_t)(h >> 16);
+        }
+        total = payload + cSize;
     }
+    // ZSTD_writeEpilogue (:5641-5652): optional content checksum, hashed by warp 0
+    if (p.checksumFlag && tid < 32) {
+        uint32_t const c = (uint32_t)xxh64_warp(src, srcSize, tid);
+        if (tid == 0) { dst[total] = (uint8_t)c; dst[total + 1] = (uint8_t)(c >> 8); dst[total + 2] = (uint8_t)(c >> 16); dst[total + 3] = (uint8_t)(c >> 24); }
+    }
+    if (tid == 0) p.results[item] = total + (p.checksumFlag ? 4u : 0u);
 }
 
 __global__ void enc_compact_kernel(const uint8_t* src, const uint64_t* srcOff, const uint64_t* sizes, const uint64_t* dstOff, uint8_t* dst)
@@ -1581,7 +1596,7 @@ static void enc_set_attrs()
     done[dev] = true;
 }
 
-bool enc_compress_device(EncArena& A, cudaStream_t stream, cudaEvent_t* ev, size_t n, int level,
+bool enc_compress_device(EncArena& A, cudaStream_t stream, cudaEvent_t* ev, size_t n, int level, int checksumFlag,
                          const uint8_t* d_src, const uint64_t* srcOff, const size_t* srcSize,
                          uint8_t* d_dst, const uint64_t* dstOff, const size_t* dstCap, size_t* result,
                          float* timings, unsigned* launches)
@@ -1626,7 +1641,7 @@ bool enc_compress_device(EncArena& A, cudaStream_t stream, cudaEvent_t* ev, size
         EncPass p;
         p.items = (EncItem*)I.items.p; p.nItems = (uint32_t)m; p.src = d_src; p.dst = d_dst; p.tables = (uint32_t*)I.tables.p;
         p.seqLL = (uint32_t*)I.seqLL.p; p.seqML = (uint32_t*)I.seqML.p; p.seqOF = (uint32_t*)I.seqOF.p; p.litBuf = (uint8_t*)I.lit.p;
-        p.stateBits = (uint64_t*)I.stateBits.p; p.results = (uint64_t*)I.results.p;
+        p.stateBits = (uint64_t*)I.stateBits.p; p.results = (uint64_t*)I.results.p; p.checksumFlag = checksumFlag ? 1u : 0u;
         enc_set_attrs();
         if (nWarp) enc_match_warp_kernel<<<nWarp, 32, (1u << kWarpMatchMaxHashLog) * 4, stream>>>(p, (const uint32_t*)I.workLists.p);
         if (nSerial) enc_match_kernel<<<(nSerial + 31) / 32, 32, 0, stream>>>(p, (const uint32_t*)I.workLists.p + m, nSerial);

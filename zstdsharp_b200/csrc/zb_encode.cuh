@@ -17,7 +17,7 @@ inline size_t enc_compress_bound(size_t srcSize)
 
 // Compresses n device-resident chunks (each one frame) at `level` (0..3). result[i] = frame size or error code.
 // timings: [1] all kernels, [8] match finder, [9] entropy stage.
-bool enc_compress_device(EncArena& A, cudaStream_t stream, cudaEvent_t* ev, size_t n, int level,
+bool enc_compress_device(EncArena& A, cudaStream_t stream, cudaEvent_t* ev, size_t n, int level, int checksumFlag,
                          const uint8_t* d_src, const uint64_t* srcOff, const size_t* srcSize,
                          uint8_t* d_dst, const uint64_t* dstOff, const size_t* dstCap, size_t* result,
                          float* timings, unsigned* launches);
