@@ -60,6 +60,9 @@ ZSTDB200_API size_t     ZSTD_compressBound(size_t srcSize);                     
 ZSTDB200_API size_t     ZSTD_CCtx_setParameter(ZSTD_CCtx* cctx, int param, int value);             /* :37 */
 /* needed by the safe wrappers in addition (Decompressor.cs:53, ThrowHelper.cs:12-13) */
 ZSTDB200_API unsigned long long ZSTD_decompressBound(const void* src, size_t srcSize);
+/* compressed size of the first frame (regular or skippable) at src; used by the stream adapter to cut a concatenated
+ * stream into independent items (U/ZstdDecompress.cs:958) */
+ZSTDB200_API size_t     ZSTD_findFrameCompressedSize(const void* src, size_t srcSize);
 ZSTDB200_API unsigned    ZSTD_isError(size_t code);
 ZSTDB200_API const char* ZSTD_getErrorName(size_t code);
 ZSTDB200_API unsigned    ZSTD_versionNumber(void);

@@ -49,8 +49,14 @@ def test_parameter_surface():
     c = api.Compressor(1)
     assert c.Level == 1
     c.Level = 3
+    c.SetParameter(api.ZSTD_cParameter.ZSTD_c_checksumFlag, 1)
     c.SetParameter(api.ZSTD_cParameter.ZSTD_c_checksumFlag, 0)
-    for bad in ((api.ZSTD_cParameter.ZSTD_c_compressionLevel, 7), (api.ZSTD_cParameter.ZSTD_c_checksumFlag, 1), (160, 1)):
+    try:
+        c.SetParameter(api.ZSTD_cParameter.ZSTD_c_checksumFlag, 2)
+        raise AssertionError("expected parameter_outOfBound")
+    except api.ZstdException as e:
+        assert e.Code == api.ZSTD_ErrorCode.parameter_outOfBound
+    for bad in ((api.ZSTD_cParameter.ZSTD_c_compressionLevel, 7), (160, 1)):
         try:
             c.SetParameter(*bad)
             raise AssertionError("expected parameter_unsupported")

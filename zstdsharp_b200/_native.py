@@ -18,7 +18,7 @@ TIMING_SLOTS = 12
 EXPORTED_SYMBOLS = [
     "ZSTD_createCCtx", "ZSTD_freeCCtx", "ZSTD_compressCCtx", "ZSTD_compress2", "ZSTD_createDCtx", "ZSTD_freeDCtx",
     "ZSTD_decompressDCtx", "ZSTD_compressBound", "ZSTD_CCtx_setParameter", "ZSTD_decompressBound", "ZSTD_isError",
-    "ZSTD_getErrorName", "ZSTD_versionNumber", "ZSTD_versionString",
+    "ZSTD_getErrorName", "ZSTD_versionNumber", "ZSTD_versionString", "ZSTD_findFrameCompressedSize",
     "ZSTDB200_decompressBatch", "ZSTDB200_compressBatch", "ZSTDB200_decompressBatchDevice",
     "ZSTDB200_compressBatchDevice", "ZSTDB200_getLastTimings", "ZSTDB200_getLastLaunchCount",
     "ZSTDB200_lastErrorString", "ZSTDB200_deviceCount", "ZSTDB200_setStream",
@@ -47,6 +47,8 @@ def _load() -> ctypes.CDLL:
     lib.ZSTD_freeDCtx.argtypes = [c_void_p]
     lib.ZSTD_decompressDCtx.restype = c_size_t
     lib.ZSTD_decompressDCtx.argtypes = [c_void_p, c_void_p, c_size_t, c_void_p, c_size_t]
+    lib.ZSTD_findFrameCompressedSize.restype = c_size_t
+    lib.ZSTD_findFrameCompressedSize.argtypes = [c_void_p, c_size_t]
     lib.ZSTD_compressBound.restype = c_size_t
     lib.ZSTD_compressBound.argtypes = [c_size_t]
     lib.ZSTD_CCtx_setParameter.restype = c_size_t

@@ -485,46 +485,56 @@ static uint32_t h_le24(const uint8_t* p) { return p[0] | (p[1] << 8) | (p[2] << 
 static uint32_t h_le32(const uint8_t* p) { return p[0] | (p[1] << 8) | (p[2] << 16) | ((uint32_t)p[3] << 24); }
 static uint64_t h_le64(const uint8_t* p) { return (uint64_t)h_le32(p) | ((uint64_t)h_le32(p + 4) << 32); }
 
+// ZSTD_findFrameSizeInfo (ZstdDecompress.cs:877): header walking only, host logic.  Returns the compressed size of the
+// frame at src (or an error code in the size_t convention) and its decompressed bound.
+static size_t frame_size_info_host(const uint8_t* src, size_t srcSize, unsigned long long* dBoundOut)
+{
+    *dBoundOut = 0ULL - 2;
+    if (srcSize >= 8 && (h_le32(src) & kMagicSkippableMask) == kMagicSkippableStart) {      // readSkippableFrameSize :674
+        uint32_t const sz = h_le32(src + 4);
+        if ((uint32_t)(sz + 8) < sz) return (size_t)make_error(kFrameParameterUnsupported);
+        if ((size_t)sz + 8 > srcSize) return (size_t)make_error(kSrcSizeWrong);
+        *dBoundOut = 0;
+        return (size_t)sz + 8;
+    }
+    if (srcSize < 5) return (size_t)make_error(kSrcSizeWrong);
+    if (h_le32(src) != kMagic) return (size_t)make_error(kPrefixUnknown);
+    uint32_t const fhd = src[4];
+    uint32_t const dictID = fhd & 3, single = (fhd >> 5) & 1, fcsId = fhd >> 6;
+    static const uint32_t did[4] = {0, 1, 2, 4}, fcsz[4] = {0, 2, 4, 8};
+    size_t const hs = 5 + !single + did[dictID] + fcsz[fcsId] + (single && !fcsId);
+    if (srcSize < hs) return (size_t)make_error(kSrcSizeWrong);
+    if (fhd & 8) return (size_t)make_error(kFrameParameterUnsupported);
+    size_t pos = 5; unsigned long long windowSize = 0, fcs = 0ULL - 1;
+    if (!single) { uint32_t const wl = (src[pos] >> 3) + 10; if (wl > 31) return (size_t)make_error(kWindowTooLarge); windowSize = 1ULL << wl; windowSize += (windowSize >> 3) * (src[pos] & 7); pos++; }
+    pos += did[dictID];
+    if (fcsId == 0) { if (single) fcs = src[pos]; } else if (fcsId == 1) fcs = h_le16(src + pos) + 256; else if (fcsId == 2) fcs = h_le32(src + pos); else fcs = h_le64(src + pos);
+    if (single) windowSize = fcs;
+    unsigned long long const blockSizeMax = windowSize < kBlockSizeMax ? windowSize : kBlockSizeMax;
+    size_t ip = hs, remaining = srcSize - hs, nbBlocks = 0;
+    for (;;) {
+        if (remaining < 3) return (size_t)make_error(kSrcSizeWrong);
+        uint32_t const h = h_le24(src + ip); uint32_t const type = (h >> 1) & 3, cs = h >> 3;
+        if (type == 3) return (size_t)make_error(kCorruptionDetected);
+        size_t const csz = type == 1 ? 1 : cs;
+        if (3 + csz > remaining) return (size_t)make_error(kSrcSizeWrong);
+        ip += 3 + csz; remaining -= 3 + csz; nbBlocks++;
+        if (h & 1) break;
+    }
+    if (fhd & 4) { if (remaining < 4) return (size_t)make_error(kSrcSizeWrong); ip += 4; }
+    *dBoundOut = (fcs != 0ULL - 1) ? fcs : (unsigned long long)nbBlocks * blockSizeMax;
+    return ip;
+}
+
+// ZSTD_decompressBound (ZstdDecompress.cs:971)
 static unsigned long long decompress_bound_host(const void* srcV, size_t srcSize)
 {
     const uint8_t* src = rd(srcV);
-    unsigned long long const kErr = 0ULL - 2; unsigned long long bound = 0;
+    unsigned long long bound = 0;
     while (srcSize > 0) {
-        size_t compressedSize; unsigned long long dBound;
-        if (srcSize >= 8 && (h_le32(src) & kMagicSkippableMask) == kMagicSkippableStart) {
-            uint32_t const sz = h_le32(src + 4);
-            if ((uint32_t)(sz + 8) < sz) return kErr;
-            if ((size_t)sz + 8 > srcSize) return kErr;
-            compressedSize = (size_t)sz + 8; dBound = 0;
-        } else {
-            if (srcSize < 5) return kErr;
-            if (h_le32(src) != kMagic) return kErr;
-            uint32_t const fhd = src[4];
-            uint32_t const dictID = fhd & 3, single = (fhd >> 5) & 1, fcsId = fhd >> 6;
-            static const uint32_t did[4] = {0, 1, 2, 4}, fcsz[4] = {0, 2, 4, 8};
-            size_t const hs = 5 + !single + did[dictID] + fcsz[fcsId] + (single && !fcsId);
-            if (srcSize < hs) return kErr;
-            if (fhd & 8) return kErr;
-            size_t pos = 5; unsigned long long windowSize = 0, fcs = 0ULL - 1;
-            if (!single) { uint32_t const wl = (src[pos] >> 3) + 10; if (wl > 31) return kErr; windowSize = 1ULL << wl; windowSize += (windowSize >> 3) * (src[pos] & 7); pos++; }
-            pos += did[dictID];
-            if (fcsId == 0) { if (single) fcs = src[pos]; } else if (fcsId == 1) fcs = h_le16(src + pos) + 256; else if (fcsId == 2) fcs = h_le32(src + pos); else fcs = h_le64(src + pos);
-            if (single) windowSize = fcs;
-            unsigned long long const blockSizeMax = windowSize < kBlockSizeMax ? windowSize : kBlockSizeMax;
-            size_t ip = hs, remaining = srcSize - hs, nbBlocks = 0;
-            for (;;) {
-                if (remaining < 3) return kErr;
-                uint32_t const h = h_le24(src + ip); uint32_t const type = (h >> 1) & 3, cs = h >> 3;
-                if (type == 3) return kErr;
-                size_t const csz = type == 1 ? 1 : cs;
-                if (3 + csz > remaining) return kErr;
-                ip += 3 + csz; remaining -= 3 + csz; nbBlocks++;
-                if (h & 1) break;
-            }
-            if (fhd & 4) { if (remaining < 4) return kErr; ip += 4; }
-            compressedSize = ip;
-            dBound = (fcs != 0ULL - 1) ? fcs : (unsigned long long)nbBlocks * blockSizeMax;
-        }
+        unsigned long long dBound;
+        size_t const compressedSize = frame_size_info_host(src, srcSize, &dBound);
+        if (is_error(compressedSize) || dBound == 0ULL - 2) return 0ULL - 2;
         src += compressedSize; srcSize -= compressedSize; bound += dBound;
     }
     return bound;
@@ -657,6 +667,7 @@ size_t ZSTDB200_compressBatchDevice(ZSTD_CCtx* cctx, size_t n, int level, const 
 }
 
 unsigned long long ZSTD_decompressBound(const void* src, size_t srcSize) { return zb::decompress_bound_host(src, srcSize); }
+size_t ZSTD_findFrameCompressedSize(const void* src, size_t srcSize) { unsigned long long b; return zb::frame_size_info_host((const uint8_t*)src, srcSize, &b); }
 unsigned ZSTD_isError(size_t code) { return zb::is_error(code); }
 const char* ZSTD_getErrorName(size_t code) { return zb::error_name(zb::is_error(code) ? (uint32_t)(0 - code) : 0); }
 unsigned ZSTD_versionNumber(void) { return 1 * 100 * 100 + 5 * 100 + 1; }     /* format/behaviour of zstd 1.5.1 (ZstdCommon.cs:11-20) */
