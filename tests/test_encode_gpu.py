@@ -154,3 +154,23 @@ def test_checksum_flag(comp, dec):
         assert f == want, _first_diff(f, want)
         assert z.decompress(f, max(c.size, 1)) == c.tobytes()
     assert dec.UnwrapBatch(frames) == [c.tobytes() for c in chunks]
+
+
+def test_wrap_larger_than_one_block(comp, dec):
+    """BASELINE.json configs[0]: 10 MB of text-like data through Compressor.Wrap / Decompressor.Unwrap.
+    Inputs above 128 KiB are written as back-to-back independent 128 KiB frames (deviations): any zstd decoder
+    regenerates the input, ZSTD_decompressBound equals the input size, the first piece is byte-identical to Wrap(piece)."""
+    o, z = oracle(), libzstd()
+    data = dg.text_like(80 * FRAME)[: 10 * 1000 * 1000]
+    comp.Level = 1
+    blob = comp.Wrap(data)
+    assert dec.GetDecompressedSize(blob) == data.size
+    assert z.decompress(blob, data.size) == data.tobytes()
+    assert dec.Unwrap(blob) == data.tobytes()
+    first = o.compress(data[:FRAME], 1)
+    assert blob[:len(first)] == first
+    single = o.compress(data, 1)                       # the reference's one multi-block frame (window spans the blocks)
+    assert len(blob) < 1.06 * len(single)              # independent pieces cost a few percent of ratio, not more
+    # capacity contract: compressBound(srcSize) is always enough, 1 byte less than needed is dstSize_tooSmall
+    small = np.empty(len(blob) - 1, dtype=np.uint8)
+    assert comp.TryWrap(data, small) == (False, 0)

@@ -430,46 +430,67 @@ static size_t decompress_batch_host(Engine& E, size_t n, const void* const* src,
     return 0;
 }
 
+// Host-pointer batch compression.  An item of at most 128 KiB becomes one single-block frame, byte-identical to the
+// reference's Wrap.  A larger item is cut into 128 KiB pieces that are compressed as independent frames and written
+// back to back: a valid zstd stream for any decoder (ZSTD_decompressMultiFrame, ZstdDecompress.cs:1216) whose
+// ZSTD_decompressBound is the item size, but NOT the reference's bytes (it would emit one multi-block frame with a
+// window that spans the blocks) -- see DESIGN.md, deviations.
 static size_t compress_batch_host(Engine& E, size_t n, int level, int checksum, const void* const* src, const size_t* srcSize, void* const* dst, const size_t* dstCap, size_t* result)
 {
     if (!E.init() || !E.bind()) return (size_t)make_error(kGeneric);
     E.launches = 0; memset(E.timings, 0, sizeof(E.timings));
     if (n == 0) return 0;
-    std::vector<uint64_t> sOff, dOff; size_t sTotal = 0;
+    std::vector<uint64_t> sOff; size_t sTotal = 0;
     cudaEventRecord(E.ev[10], E.stream);
     if (!upload_items(E, n, src, srcSize, sOff, &sTotal)) return (size_t)make_error(kMemoryAllocation);
     cudaEventRecord(E.ev[11], E.stream);
-    // device output: one slot of compressBound(srcSize) per item (the reference's Wrap contract, Compressor.cs:80)
-    dOff.resize(n); std::vector<size_t> slotCap(n); size_t dTotal = 16;
-    for (size_t i = 0; i < n; i++) { dOff[i] = dTotal; slotCap[i] = enc_compress_bound(srcSize[i]); dTotal += (slotCap[i] + 15) & ~(size_t)15; }
+    // pieces: item i owns pieces [first[i], first[i+1])
+    std::vector<size_t> first(n + 1);
+    size_t np = 0;
+    for (size_t i = 0; i < n; i++) { first[i] = np; np += srcSize[i] <= kBlockSizeMax ? 1 : (srcSize[i] + kBlockSizeMax - 1) / kBlockSizeMax; }
+    first[n] = np;
+    // device output: one slot of compressBound(pieceSize) per piece (the reference's Wrap contract, Compressor.cs:80)
+    std::vector<uint64_t> pSrcOff(np), pDstOff(np); std::vector<size_t> pSize(np), slotCap(np), r(np);
+    size_t dTotal = 16;
+    for (size_t i = 0; i < n; i++)
+        for (size_t k = first[i]; k < first[i + 1]; k++) {
+            size_t const o = (k - first[i]) * (size_t)kBlockSizeMax;
+            pSrcOff[k] = sOff[i] + o; pSize[k] = std::min<size_t>(srcSize[i] - o, kBlockSizeMax);
+            pDstOff[k] = dTotal; slotCap[k] = enc_compress_bound(pSize[k]); dTotal += (slotCap[k] + 15) & ~(size_t)15;
+        }
     dTotal += 16;
     if (!E.dDst.ensure(dTotal)) return (size_t)make_error(kMemoryAllocation);
-    std::vector<size_t> r(n);
-    if (!enc_compress_device(E.enc, E.stream, E.ev, n, level, checksum, E.dSrc.as<uint8_t>(), sOff.data(), srcSize, E.dDst.as<uint8_t>(), dOff.data(), slotCap.data(), r.data(), E.timings, &E.launches))
+    if (!enc_compress_device(E.enc, E.stream, E.ev, np, level, checksum, E.dSrc.as<uint8_t>(), pSrcOff.data(), pSize.data(), E.dDst.as<uint8_t>(), pDstOff.data(), slotCap.data(), r.data(), E.timings, &E.launches))
         { set_error(enc_last_error()); return (size_t)make_error(kGeneric); }
     cudaEventRecord(E.ev[12], E.stream);
-    // results that do not fit the caller's capacity become dstSize_tooSmall (ZstdCompress.cs:4690-4800 error paths)
+    // per item: total size, first error of its pieces, dstSize_tooSmall when the caller's buffer cannot take it (ZstdCompress.cs:4690-4800)
     for (size_t i = 0; i < n; i++) {
-        if (!is_error(r[i]) && r[i] > dstCap[i]) r[i] = (size_t)make_error(kDstSizeTooSmall);
-        result[i] = r[i];
+        size_t tot = 0;
+        for (size_t k = first[i]; k < first[i + 1]; k++) { if (is_error(r[k])) { tot = r[k]; break; } tot += r[k]; }
+        if (!is_error(tot) && tot > dstCap[i]) tot = (size_t)make_error(kDstSizeTooSmall);
+        result[i] = tot;
     }
-    // copy back: gather compacted frames. Contiguous caller buffers with exact sizes are rare here (sizes are data dependent),
-    // so each frame is one DMA when n is small, otherwise the whole slot area is staged through pinned memory.
-    if (n <= 512) {
-        for (size_t i = 0; i < n; i++)
-            if (!is_error(result[i]) && result[i])
-                if (cudaMemcpyAsync(dst[i], E.dDst.as<uint8_t>() + dOff[i], result[i], cudaMemcpyDeviceToHost, E.stream) != cudaSuccess) return (size_t)make_error(kGeneric);
+    if (np <= 512) {
+        for (size_t i = 0; i < n; i++) {
+            if (is_error(result[i])) continue;
+            size_t o = 0;
+            for (size_t k = first[i]; k < first[i + 1]; k++) {
+                if (r[k] && cudaMemcpyAsync((uint8_t*)dst[i] + o, E.dDst.as<uint8_t>() + pDstOff[k], r[k], cudaMemcpyDeviceToHost, E.stream) != cudaSuccess) return (size_t)make_error(kGeneric);
+                o += r[k];
+            }
+        }
         if (cudaStreamSynchronize(E.stream) != cudaSuccess) return (size_t)make_error(kGeneric);
     } else {
-        // compact on the device first so that only compressed bytes cross PCIe
-        std::vector<uint64_t> cOff(n); size_t cTotal = 0;
-        for (size_t i = 0; i < n; i++) { cOff[i] = cTotal; cTotal += is_error(result[i]) ? 0 : result[i]; }
+        // compact on the device first so that only compressed bytes cross PCIe; the pieces of an item end up adjacent
+        std::vector<uint64_t> cOff(np); std::vector<size_t> cSize(np); size_t cTotal = 0;
+        for (size_t i = 0; i < n; i++)
+            for (size_t k = first[i]; k < first[i + 1]; k++) { cOff[k] = cTotal; cSize[k] = is_error(result[i]) ? 0 : r[k]; cTotal += cSize[k]; }
         if (!E.hStage.ensure(cTotal + 16)) return (size_t)make_error(kMemoryAllocation);
-        if (!enc_compact_device(E.enc, E.stream, n, E.dDst.as<uint8_t>(), dOff.data(), result, cOff.data(), cTotal, &E.launches)) return (size_t)make_error(kGeneric);
+        if (!enc_compact_device(E.enc, E.stream, np, E.dDst.as<uint8_t>(), pDstOff.data(), cSize.data(), cOff.data(), cTotal, &E.launches)) return (size_t)make_error(kGeneric);
         if (cudaMemcpyAsync(E.hStage.p, E.enc.compactBuf(), cTotal, cudaMemcpyDeviceToHost, E.stream) != cudaSuccess) return (size_t)make_error(kGeneric);
         if (cudaStreamSynchronize(E.stream) != cudaSuccess) return (size_t)make_error(kGeneric);
         const uint8_t* st = E.hStage.as<uint8_t>();
-        parallel_for(n, 256, [&](size_t a, size_t b) { for (size_t i = a; i < b; i++) if (!is_error(result[i])) memcpy(dst[i], st + cOff[i], result[i]); });
+        parallel_for(n, 256, [&](size_t a, size_t b) { for (size_t i = a; i < b; i++) if (!is_error(result[i])) memcpy(dst[i], st + cOff[first[i]], result[i]); });
     }
     cudaEventRecord(E.ev[13], E.stream);
     cudaEventSynchronize(E.ev[13]);
