@@ -70,7 +70,7 @@ constexpr int kPipeMax = 8;                    // upper bound of sub-batches in 
 static int env_int(const char* name, int def, int lo, int hi) { const char* e = getenv(name); if (!e) return def; int v = atoi(e); return v < lo ? lo : (v > hi ? hi : v); }
 // sub-batches in flight / target sub-batch size (items); tunable for experiments, defaults chosen on B200 (profiles/r01_notes.md)
 static int pipe_depth() { static int v = env_int("ZSTDB200_PIPE", 3, 1, kPipeMax); return v; }
-static size_t pipe_items() { static int v = env_int("ZSTDB200_PIPE_ITEMS", 2048, 16, 8192); return (size_t)v; }
+static size_t pipe_items() { static int v = env_int("ZSTDB200_PIPE_ITEMS", 4096, 16, 8192); return (size_t)v; }
 
 // scratch of one decode pass (DecPass layout, zb_decode.cuh)
 struct DecArena {
@@ -179,16 +179,18 @@ static bool decode_enqueue(Engine& E, DecArena& A, cudaStream_t stream, size_t m
         hi[i].srcSize = (uint32_t)std::min<size_t>(srcSize[i], 0xFFFFFFF0u);
         hi[i].dstCap = (uint32_t)std::min<size_t>(dstCap[i], 0xFFFFFFF0u);
     }
-    ZB_CUDA(cudaMemcpyAsync(A.dInit.p, hi, m * sizeof(DecItemInit), cudaMemcpyHostToDevice, stream));
+    // The item descriptors and the per-item results stay in pinned host memory and are read / written by the kernels
+    // directly (zero copy): a tiny cudaMemcpyAsync would queue behind the bulk transfers of the other sub-batches on
+    // the copy engines and stall this sub-batch's kernels for milliseconds.
     ZB_CUDA(cudaMemsetAsync(A.dCounters.p, 0, 64, stream));
     DecPass p;
     p.items = A.dItems.as<DecItem>(); p.nItems = (uint32_t)m; p.src = d_src; p.dst = d_dst;
     p.hufTable = A.dHuf.as<uint16_t>(); p.fseTable = A.dFse.as<uint32_t>(); p.litBuf = A.dLit.as<uint8_t>();
     p.seq = A.dSeq.as<uint2>();
     p.defaultFse = E.dDefaultFse.as<uint32_t>(); p.hufList = A.dHufList.as<uint32_t>(); p.seqList = A.dSeqList.as<uint32_t>();
-    p.counters = A.dCounters.as<uint32_t>(); p.results = A.dResults.as<uint64_t>();
+    p.counters = A.dCounters.as<uint32_t>(); p.results = A.hResults.as<uint64_t>();
     if (timeEv) ZB_CUDA(cudaEventRecord(timeEv[0], stream));
-    dec_launch_scan_init(p, A.dInit.p, stream); E.launches++;
+    dec_launch_scan_init(p, hi, stream); E.launches++;
     if (nWaves == 0) {
         ZB_CUDA(cudaMemcpyAsync(A.hCounters.p, A.dCounters.p, 16, cudaMemcpyDeviceToHost, stream));
         ZB_CUDA(cudaStreamSynchronize(stream));
@@ -201,7 +203,6 @@ static bool decode_enqueue(Engine& E, DecArena& A, cudaStream_t stream, size_t m
     }
     dec_launch_finish(p, stream); E.launches++;
     if (timeEv) ZB_CUDA(cudaEventRecord(timeEv[1], stream));
-    ZB_CUDA(cudaMemcpyAsync(A.hResults.p, A.dResults.p, m * 8, cudaMemcpyDeviceToHost, stream));
     return true;
 }
 
@@ -352,10 +353,21 @@ static size_t decompress_batch_host(Engine& E, size_t n, const void* const* src,
     bool const scatter = dstRuns > 512;
     if (gather && !E.hStage.ensure(sTotal)) return (size_t)make_error(kMemoryAllocation);
     if (scatter && !E.hStageOut.ensure(dTotal)) return (size_t)make_error(kMemoryAllocation);
-    // ---- sub-batches ----
+    // ---- sub-batches: sizes grow geometrically (n/16, n/8, n/4, ...) so that the first D2H starts early and the D2H
+    // stream -- the slowest stage -- then never runs dry; no sub-batch exceeds the configured target ----
     size_t const kPipe = (size_t)pipe_depth(), kPipeItems = pipe_items();
-    size_t const nSub = (n + kPipeItems - 1) / kPipeItems;
-    size_t const per = (n + nSub - 1) / nSub;
+    std::vector<size_t> sub;                     // sub-batch k = items [sub[k], sub[k+1])
+    {
+        size_t pos = 0, sz = std::max<size_t>(64, std::min(kPipeItems, n / 16));
+        while (pos < n) {
+            size_t take = std::min(sz, n - pos);
+            if (n - pos - take < take / 2) take = n - pos;      // fold a small remainder into the last sub-batch
+            sub.push_back(pos); pos += take;
+            sz = std::min(kPipeItems, sz * 2);
+        }
+        sub.push_back(n);
+    }
+    size_t const nSub = sub.size() - 1;
     if (!E.need_events(4 * nSub)) return (size_t)make_error(kGeneric);
     cudaEvent_t* const evH2D = E.evPool.data(); cudaEvent_t* const evDone = evH2D + nSub; cudaEvent_t* const evBegin = evDone + nSub; cudaEvent_t* const evD2H = evBegin + nSub;
     auto fail = [&](ErrorCode c) { cudaDeviceSynchronize(); (void)cudaGetLastError(); return (size_t)make_error(c); };
@@ -365,7 +377,7 @@ static size_t decompress_batch_host(Engine& E, size_t n, const void* const* src,
     // stage 1: all uploads are queued up front
     size_t runIdx = 0;
     for (size_t k = 0; k < nSub; k++) {
-        size_t const a = k * per, b = std::min(n, a + per);
+        size_t const a = sub[k], b = sub[k + 1];
         if (gather) {
             uint8_t* st = E.hStage.as<uint8_t>();
             parallel_for(b - a, 256, [&](size_t x, size_t y) { for (size_t i = a + x; i < a + y; i++) memcpy(st + sOff[i], src[i], srcSize[i]); });
@@ -390,14 +402,14 @@ static size_t decompress_batch_host(Engine& E, size_t n, const void* const* src,
     // scattered destinations: the sub-batch's device region comes back with one DMA into pinned staging and is copied
     // out by host threads one sub-batch later (while the next DMA is in flight)
     auto scatter_out = [&](size_t k) -> bool {
-        size_t const a = k * per, b = std::min(n, a + per);
+        size_t const a = sub[k], b = sub[k + 1];
         if (cudaEventSynchronize(evD2H[k]) != cudaSuccess) return false;
         const uint8_t* st = E.hStageOut.as<uint8_t>();
         parallel_for(b - a, 256, [&](size_t x, size_t y) { for (size_t i = a + x; i < a + y; i++) if (!is_error(result[i])) memcpy(dst[i], st + dOff[i], result[i]); });
         return true;
     };
     auto finish = [&](size_t k) -> bool {
-        size_t const a = k * per, b = std::min(n, a + per);
+        size_t const a = sub[k], b = sub[k + 1];
         if (cudaEventSynchronize(evDone[k]) != cudaSuccess) return false;
         decode_collect(E.dec[k % kPipe], b - a, srcSize + a, result + a);
         if (firstOut) { cudaEventRecord(E.evOut[0], E.sOut); firstOut = false; }
@@ -408,7 +420,7 @@ static size_t decompress_batch_host(Engine& E, size_t n, const void* const* src,
         return k == 0 || scatter_out(k - 1);
     };
     for (size_t k = 0; k < nSub; k++) {
-        size_t const a = k * per, b = std::min(n, a + per);
+        size_t const a = sub[k], b = sub[k + 1];
         if (k >= kPipe && !finish(k - kPipe)) return fail(kGeneric);
         uint32_t waves = 1;
         for (size_t i = a; i < b; i++) waves = std::max(waves, count_item_blocks((const uint8_t*)src[i], (uint32_t)std::min<size_t>(srcSize[i], 0xFFFFFFF0u)));
@@ -427,6 +439,14 @@ static size_t decompress_batch_host(Engine& E, size_t n, const void* const* src,
     cudaEventElapsedTime(&E.timings[0], E.evIn[0], E.evIn[1]);
     cudaEventElapsedTime(&E.timings[2], E.evOut[0], E.evOut[1]);
     for (size_t k = 0; k < nSub; k++) { float t = 0; cudaEventElapsedTime(&t, evBegin[k], evDone[k]); E.timings[1] += t; }
+    if (getenv("ZSTDB200_TRACE")) {               // developer aid: stage times of every sub-batch relative to the first H2D
+        for (size_t k = 0; k < nSub; k++) {
+            float h = 0, b0 = 0, b1 = 0; cudaEventElapsedTime(&h, E.evIn[0], evH2D[k]); cudaEventElapsedTime(&b0, E.evIn[0], evBegin[k]); cudaEventElapsedTime(&b1, E.evIn[0], evDone[k]);
+            fprintf(stderr, "[zstdb200] sub %zu items %zu: h2d done %.2f  kernels %.2f .. %.2f ms\n", k, sub[k + 1] - sub[k], h, b0, b1);
+        }
+        float o0 = 0, o1 = 0; cudaEventElapsedTime(&o0, E.evIn[0], E.evOut[0]); cudaEventElapsedTime(&o1, E.evIn[0], E.evOut[1]);
+        fprintf(stderr, "[zstdb200] d2h %.2f .. %.2f ms\n", o0, o1);
+    }
     return 0;
 }
 

@@ -1133,8 +1133,15 @@ static void dec_set_attrs()
     cudaFuncSetAttribute(dec_huf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kHufSmemBytes);
     cudaFuncSetAttribute(dec_seq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSeqSmemBytes);
     cudaFuncSetAttribute(dec_exec_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kExecWarps * kExecTileMem);
-    cudaFuncSetAttribute(dec_exec_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+    // One shared-memory carve-out for every kernel of the pipeline: kernels of different sub-batches (streams) can only
+    // share an SM when they agree on the L1/shared split, otherwise each switch waits for the SM to drain.
+    cudaFuncSetAttribute(dec_scan_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+    cudaFuncSetAttribute(dec_reset_counters_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+    cudaFuncSetAttribute(dec_setup_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+    cudaFuncSetAttribute(dec_huf_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
     cudaFuncSetAttribute(dec_seq_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+    cudaFuncSetAttribute(dec_exec_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+    cudaFuncSetAttribute(dec_finish_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
     done[dev] = true;
 }
 
