@@ -826,7 +826,7 @@ __global__ void __launch_bounds__(32) dec_seq_kernel(DecPass p)
 //  back from HBM/L2 (they were flushed by this same warp earlier).
 // =====================================================================================================
 constexpr int kExecWarps = 2;                       // items per CTA
-constexpr uint32_t kExecTileMem = 6656;             // shared memory per item; 32 warps x 6.5 KB (+1 KB reserved per CTA) = 224 KB per SM
+constexpr uint32_t kExecTileMem = 6656;             // shared memory per item; 32 warps x 6.5 KB (+1 KB reserved per CTA) = 224 KB per SM (48 warps x 4 KB: register spills, 6.2 ms)
 constexpr uint32_t kExecTile = kExecTileMem - 16;   // usable bytes (the tile starts at the 16-byte phase of its HBM address)
 constexpr uint32_t kExecLong = 40;                  // copies longer than this are done by the whole warp
 
@@ -879,6 +879,68 @@ __device__ __forceinline__ void warp_flush_tile(uint8_t* g, const uint8_t* tile,
     for (uint32_t c = lane; c < nChunks; c += 32) *(uint4*)(g + 16 * c) = *(const uint4*)(tile + 16 * c);
     uint32_t const done = nChunks << 4, rem = n - done;
     if (lane < rem) g[done + lane] = tile[done + lane];
+}
+
+// ---- per-lane copies into the tile: 4 bytes per step (unaligned source = two aligned words + funnel shift) ----
+__device__ __forceinline__ uint32_t g_rd32(const uint8_t* p)        // global, any alignment; reads the two aligned words that hold p[0..3]
+{
+    uintptr_t const a = (uintptr_t)p; const uint32_t* w = (const uint32_t*)(a & ~(uintptr_t)3); uint32_t const sh = (uint32_t)(a & 3) * 8;
+    uint32_t const lo = w[0], hi = sh ? w[1] : 0u;
+    return __funnelshift_r(lo, hi, sh);
+}
+// m (1..16) bytes out of four left-aligned words into the tile: 16 predicated byte stores, no loop
+__device__ __forceinline__ void lane_put16(uint8_t* t, uint32_t v0, uint32_t v1, uint32_t v2, uint32_t v3, uint32_t m)
+{
+    uint32_t const v[4] = {v0, v1, v2, v3};
+#pragma unroll
+    for (uint32_t i = 0; i < 16; i++) if (i < m) t[i] = (uint8_t)(v[i >> 2] >> ((i & 3) * 8));
+}
+// up to 16 bytes at g (any alignment): raw aligned words now, left-aligned words later (so that several loads overlap)
+struct Raw16 { uint32_t w0, w1, w2, w3, w4, sh; };
+__device__ __forceinline__ Raw16 lane_ld16(const uint8_t* g, uint32_t m)      // m = 0: nothing is read
+{
+    uintptr_t const a = (uintptr_t)g; const uint32_t* w = (const uint32_t*)(a & ~(uintptr_t)3);
+    uint32_t const o = (uint32_t)(a & 3), need = m ? o + m : 0u;
+    Raw16 r; r.sh = o * 8;
+    r.w0 = need > 0 ? w[0] : 0u; r.w1 = need > 4 ? w[1] : 0u; r.w2 = need > 8 ? w[2] : 0u; r.w3 = need > 12 ? w[3] : 0u; r.w4 = need > 16 ? w[4] : 0u;
+    return r;
+}
+__device__ __forceinline__ void lane_st16(uint8_t* t, const Raw16& r, uint32_t m)
+{ lane_put16(t, __funnelshift_r(r.w0, r.w1, r.sh), __funnelshift_r(r.w1, r.w2, r.sh), __funnelshift_r(r.w2, r.w3, r.sh), __funnelshift_r(r.w3, r.w4, r.sh), m); }
+// n bytes from global memory (any alignment) into the tile: the five aligned words of a 16-byte step are loaded
+// together, so a copy costs one memory round trip per 16 bytes instead of one per byte
+__device__ __forceinline__ void lane_copy_g2t(uint8_t* tile, uint32_t d, const uint8_t* g, uint32_t n)
+{
+    for (uint32_t k = 0; k < n; k += 16) {
+        uint32_t const m = min(16u, n - k);
+        uintptr_t const a = (uintptr_t)(g + k); const uint32_t* w = (const uint32_t*)(a & ~(uintptr_t)3);
+        uint32_t const o = (uint32_t)(a & 3), sh = o * 8, need = o + m;          // bytes [0, need) of the aligned words are wanted
+        uint32_t const w0 = w[0], w1 = need > 4 ? w[1] : 0u, w2 = need > 8 ? w[2] : 0u, w3 = need > 12 ? w[3] : 0u, w4 = need > 16 ? w[4] : 0u;
+        lane_put16(tile + d + k, __funnelshift_r(w0, w1, sh), __funnelshift_r(w1, w2, sh), __funnelshift_r(w2, w3, sh), __funnelshift_r(w3, w4, sh), m);
+    }
+}
+// forward copy inside the tile, distance d - s >= 4: every 4-byte read only touches bytes that are already final;
+// with a distance >= 16 a whole 16-byte step is read before it is written
+__device__ __forceinline__ void lane_copy_t2t(uint8_t* tile, uint32_t d, uint32_t s, uint32_t n)
+{
+    uint32_t k = 0;
+    if (d - s >= 16) {
+        for (; k < n; k += 16) {
+            uint32_t const m = min(16u, n - k);
+            uintptr_t const a = (uintptr_t)(tile + s + k); const uint32_t* w = (const uint32_t*)(a & ~(uintptr_t)3);
+            uint32_t const o = (uint32_t)(a & 3), sh = o * 8, need = o + m;
+            uint32_t const w0 = w[0], w1 = need > 4 ? w[1] : 0u, w2 = need > 8 ? w[2] : 0u, w3 = need > 12 ? w[3] : 0u, w4 = need > 16 ? w[4] : 0u;
+            lane_put16(tile + d + k, __funnelshift_r(w0, w1, sh), __funnelshift_r(w1, w2, sh), __funnelshift_r(w2, w3, sh), __funnelshift_r(w3, w4, sh), m);
+        }
+        return;
+    }
+    for (; k + 4 <= n; k += 4) {
+        uintptr_t const a = (uintptr_t)(tile + s + k); const uint32_t* w = (const uint32_t*)(a & ~(uintptr_t)3); uint32_t const sh = (uint32_t)(a & 3) * 8;
+        uint32_t const lo = w[0], hi = sh ? w[1] : 0u;
+        uint32_t const v = __funnelshift_r(lo, hi, sh);
+        tile[d + k] = (uint8_t)v; tile[d + k + 1] = (uint8_t)(v >> 8); tile[d + k + 2] = (uint8_t)(v >> 16); tile[d + k + 3] = (uint8_t)(v >> 24);
+    }
+    for (; k < n; k++) tile[d + k] = tile[s + k];
 }
 
 // Literal source of a block: raw bytes inside the frame, one repeated byte, or the Huffman output (4 padded segments)
@@ -980,22 +1042,32 @@ __global__ void __launch_bounds__(kExecWarps * 32) dec_exec_kernel(DecPass p)
             uint2 recNext = make_uint2(0u, 0u);
             if (seqBase + take + lane < nbSeq) recNext = aSeq[seqBase + take + lane];
             uint32_t const span = __shfl_sync(FULL, oEnd, take - 1), litSpan = __shfl_sync(FULL, lEnd, take - 1);
-            // ---- literals -> tile ----
+            // ---- literals -> tile; the part of every match that lies behind the tile (final bytes in HBM) is fetched in the
+            // same round trip: it depends on nothing in this batch ----
+            uint32_t const mDst = fill + oStart + ll;                    // tile-relative destination of my match
+            int32_t const srcRel = (int32_t)mDst - (int32_t)of;          // tile-relative source (negative: behind the tile, in HBM)
+            uint32_t const farN = (mine && ml && ml <= kExecLong && srcRel < 0) ? min(ml, (uint32_t)(-srcRel)) : 0u;
+            uint32_t const farFast = farN <= 16 ? farN : 0u;             // longer far parts are copied in the rounds below
             {
                 uint32_t const d0 = fill + oStart;
                 uint32_t longMask = __ballot_sync(FULL, mine && ll > kExecLong);
                 uint32_t const myLL = (mine && ll <= kExecLong) ? ll : 0u;
                 if (L.type == kLitRle) {
+                    Raw16 const fm = lane_ld16(dst + tileBase + srcRel, farFast);
                     for (uint32_t k = 0; k < myLL; k++) tile[d0 + k] = (uint8_t)L.rle;
+                    if (farFast) lane_st16(tile + mDst, fm, farFast);
                 } else {
-                    uint32_t idx = litPos + lStart;
+                    uint32_t const idx = litPos + lStart;
                     uint32_t const s = (idx >= L.seg) + (idx >= 2 * L.seg) + (idx >= 3 * L.seg);
-                    uint32_t a = idx + s * L.pad, nb = s >= 3 ? 0xFFFFFFFFu : (s + 1) * L.seg;
-                    for (uint32_t k = 0; k < myLL; k++) {
-                        tile[d0 + k] = __ldg(L.base + a);
-                        a++; idx++;
-                        if (idx == nb) { a += L.pad; nb += L.seg; }
-                    }
+                    uint32_t const a = idx + s * L.pad;
+                    uint32_t const n1 = s >= 3 ? myLL : min(myLL, (s + 1) * L.seg - idx);      // bytes before the next segment boundary
+                    uint32_t const l16 = min(n1, 16u);
+                    Raw16 const lt = lane_ld16(L.base + a, l16);
+                    Raw16 const fm = lane_ld16(dst + tileBase + srcRel, farFast);
+                    if (l16) lane_st16(tile + d0, lt, l16);
+                    if (farFast) lane_st16(tile + mDst, fm, farFast);
+                    if (n1 > 16) lane_copy_g2t(tile, d0 + 16, L.base + a + 16, n1 - 16);
+                    if (n1 < myLL) lane_copy_g2t(tile, d0 + n1, L.base + a + n1 + L.pad, myLL - n1);   // a run crosses at most one boundary (kExecLong < segment)
                 }
                 while (longMask) {
                     uint32_t const j = (uint32_t)__ffs((int)longMask) - 1u; longMask &= longMask - 1;
@@ -1006,8 +1078,6 @@ __global__ void __launch_bounds__(kExecWarps * 32) dec_exec_kernel(DecPass p)
             }
             __syncwarp();
             // ---- matches ----
-            uint32_t const mDst = fill + oStart + ll;                    // tile-relative destination of my match
-            int32_t const srcRel = (int32_t)mDst - (int32_t)of;          // tile-relative source (negative: behind the tile, in HBM)
             uint32_t const nonSelf = of < ml ? of : ml;
             // lanes j < lane whose match output [mDst_j, oEnd_j) intersects my source [srcRel, srcRel + nonSelf)
             uint32_t depMask = 0;
@@ -1045,13 +1115,12 @@ __global__ void __launch_bounds__(kExecWarps * 32) dec_exec_kernel(DecPass p)
                 bool const isLong = ready && ml > kExecLong;
                 if (ready && !isLong) {
                     const uint8_t* const gsrc = dst + tileBase;            // tile origin in HBM
-                    uint32_t k = 0;
-                    if (srcRel < 0) {
-                        uint32_t const k0 = min(ml, (uint32_t)(-srcRel));
-                        for (; k < k0; k++) tile[mDst + k] = gsrc[srcRel + (int32_t)k];
+                    uint32_t k0 = 0;
+                    if (srcRel < 0) { k0 = min(ml, (uint32_t)(-srcRel)); if (!farFast) lane_copy_g2t(tile, mDst, gsrc + srcRel, k0); }
+                    if (k0 < ml) {
+                        if (of >= 4) lane_copy_t2t(tile, mDst + k0, (uint32_t)(srcRel + (int32_t)k0), ml - k0);
+                        else { volatile uint8_t* const vt = tile; for (uint32_t k = k0; k < ml; k++) vt[mDst + k] = vt[(uint32_t)(srcRel + (int32_t)k)]; }   // offsets 1..3: byte by byte
                     }
-                    volatile uint8_t* const vt = tile;                   // overlapping matches read bytes this lane wrote
-                    for (; k < ml; k++) vt[mDst + k] = vt[(uint32_t)(srcRel + (int32_t)k)];
                 }
                 uint32_t longMask = __ballot_sync(FULL, isLong);
                 while (longMask) {
