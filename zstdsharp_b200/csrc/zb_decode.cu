@@ -601,25 +601,28 @@ struct BitRing {
 __device__ __forceinline__ uint32_t top_bits(uint32_t x, uint32_t nb) { return (x >> 1) >> (31 - nb); }
 
 // =====================================================================================================
-//  Huffman literal decoding: one lane per stream, 16 items (64 streams) per CTA.
+//  Huffman literal decoding: one lane per stream, 14 items (56 streams) per CTA.
 //  HUF_decompress4X1_usingDTable_internal_body / HUF_decodeStreamX1 (HufDecompress.cs:342, :264)
-//  Shared memory holds a first-level table of min(tableLog, 10) bits per item (2 KB), so that every item of a
-//  8192-frame batch is resident at once (5 CTAs x 40 KB per SM); codes of 11 or 12 bits (rare symbols) escape to the
-//  full table in HBM, which stays L1-resident because only a few of its lines are ever touched.
+//  The single-symbol table is split for shared memory: symbol bytes u8[2^log] and code lengths u8[2^(log-1)] -- cells
+//  2j and 2j+1 always hold the same length, because every rank starts at an even cell (rankStats[1] is even,
+//  EntropyCommon.cs:398).  3 KB per item for tableLog 11 instead of 4 KB, so that 56 items fit one SM and a batch of
+//  8192 items is resident in ONE wave (any item needs a full stream time: 1.15 waves would cost 2x).
+//  tableLog 12 (legal, never produced by zstd's encoder) is decoded from the table in HBM.
 // =====================================================================================================
-constexpr int kHufItemsPerCta = 16;
+constexpr int kHufItemsPerCta = 14;
 constexpr int kHufThreads = kHufItemsPerCta * 4;
-constexpr uint32_t kHufL1Log = 10;
-constexpr uint32_t kHufSmemEntries = 1u << kHufL1Log;
-constexpr uint32_t kHufChunk = 64;              // 4 x 64 B of ring per stream
-constexpr uint32_t kHufSmemBytes = kHufItemsPerCta * kHufSmemEntries * 2 + kHufThreads * 4 * kHufChunk;
+constexpr uint32_t kHufSmemLog = 11;
+constexpr uint32_t kHufSymBytes = 1u << kHufSmemLog, kHufLenBytes = 1u << (kHufSmemLog - 1), kHufItemBytes = kHufSymBytes + kHufLenBytes;
+constexpr uint32_t kHufChunk = 32;              // 4 x 32 B of ring per stream (8 symbols consume <= 12 bytes, a refill reads 12 more)
+constexpr uint32_t kHufSmemBytes = kHufThreads * 4 * kHufChunk + kHufItemsPerCta * kHufItemBytes;
+__device__ __forceinline__ uint32_t lds8u(uint32_t saddr) { uint16_t v; asm volatile("ld.shared.u8 %0, [%1];" : "=h"(v) : "r"(saddr)); return v; }
 
 __device__ __forceinline__ uint32_t lit_segment_stride(uint32_t litSize) { uint32_t const seg = (litSize + 3) / 4; return (seg + 15) & ~15u; }
 
 __global__ void __launch_bounds__(kHufThreads) dec_huf_kernel(DecPass p)
 {
-    extern __shared__ __align__(256) uint8_t s_huf_raw[];    // [kHufThreads] rings of 256 B, then [kHufItemsPerCta][1024] first-level tables
-    uint16_t* const s_tab = (uint16_t*)(s_huf_raw + kHufThreads * 4 * kHufChunk);
+    extern __shared__ __align__(256) uint8_t s_huf_raw[];    // [kHufThreads] rings of 128 B, then per item: u8 sym[2048] | u8 len[1024]
+    uint8_t* const s_tab = s_huf_raw + kHufThreads * 4 * kHufChunk;
     uint32_t const nWork = p.counters[0];
     uint32_t const first = blockIdx.x * kHufItemsPerCta;
     if (first >= nWork) return;
@@ -627,14 +630,15 @@ __global__ void __launch_bounds__(kHufThreads) dec_huf_kernel(DecPass p)
     for (uint32_t k = 0; k < nHere; k++) {
         uint32_t const item = p.hufList[first + k];
         uint32_t const log = p.items[item].hufLog;
-        const uint16_t* const g = p.hufTable + (size_t)item * kHufTableEntries;
-        uint16_t* const st = s_tab + k * kHufSmemEntries;
-        if (log <= kHufL1Log) {
-            uint32_t const n16 = ((1u << log) * 2 + 15) / 16;
-            for (uint32_t u = threadIdx.x; u < n16; u += kHufThreads) ((uint4*)st)[u] = ((const uint4*)g)[u];
-        } else {
-            uint32_t const sh = log - kHufL1Log;            // a code of <= 10 bits fills the whole aligned group: its first cell decides
-            for (uint32_t u = threadIdx.x; u < kHufSmemEntries; u += kHufThreads) st[u] = g[u << sh];
+        if (log > kHufSmemLog) continue;
+        const uint32_t* const g = (const uint32_t*)(p.hufTable + (size_t)item * kHufTableEntries);      // two u16 cells {byte<<8 | nbBits} per word
+        uint16_t* const sym = (uint16_t*)(s_tab + k * kHufItemBytes);
+        uint8_t* const len = s_tab + k * kHufItemBytes + kHufSymBytes;
+        uint32_t const pairs = max(1u, (1u << log) >> 1);
+        for (uint32_t u = threadIdx.x; u < pairs; u += kHufThreads) {
+            uint32_t const w = g[u];
+            sym[u] = (uint16_t)(((w >> 8) & 0xFF) | ((w >> 24) << 8));
+            len[u] = (uint8_t)(w & 0xFF);
         }
     }
     __syncthreads();
@@ -656,40 +660,46 @@ __global__ void __launch_bounds__(kHufThreads) dec_huf_kernel(DecPass p)
     uint32_t G = br.init((uint32_t)__cvta_generic_to_shared(s_huf_raw) + threadIdx.x * (4 * kHufChunk), src + it.streamOff[stream], it.streamLen[stream]);
     bool ok = G != 0;
     if (ok) {
-        uint32_t const l1 = log < kHufL1Log ? log : kHufL1Log;
-        uint32_t const sh1 = 32 - l1, shF = 32 - log;
-        uint32_t const tabS = (uint32_t)__cvta_generic_to_shared(s_tab + slot * kHufSmemEntries);
-        const uint16_t* const gtab = p.hufTable + (size_t)item * kHufTableEntries;
+        uint32_t const sh = 32 - log;
+        uint32_t const symS = (uint32_t)__cvta_generic_to_shared(s_tab + slot * kHufItemBytes), lenS = symS + kHufSymBytes;
         int32_t const gz = (int32_t)br.gZero;
         uint32_t i = 0;
-        // 16 symbols -> one 16-byte store (out is 16-byte aligned by construction); 4 symbols (<= 48 bits) per window refill
-        for (; i + 16 <= count && (int32_t)G >= gz; i += 16) {
-            br.advance(G);
-            uint32_t v[4];
+        if (log <= kHufSmemLog) {
+            // 16 symbols -> one 16-byte store (out is 16-byte aligned by construction); 4 symbols (<= 44 bits) per window refill
+            for (; i + 16 <= count && (int32_t)G >= gz; i += 16) {
+                uint32_t v[4];
 #pragma unroll
-            for (int q = 0; q < 4; q++) {
-                uint32_t x0, x1; br.peek64(G, x0, x1);
-                uint32_t acc = 0, used = 0;
+                for (int q = 0; q < 4; q++) {
+                    if ((q & 1) == 0) br.advance(G);
+                    uint32_t x0, x1; br.peek64(G, x0, x1);
+                    uint32_t acc = 0, used = 0;
 #pragma unroll
-                for (int r = 0; r < 4; r++) {
-                    uint32_t e = lds16(tabS + (x0 >> sh1) * 2);
-                    if ((e & 0xFF) > kHufL1Log) e = __ldg(gtab + (x0 >> shF));
-                    uint32_t const nb = e & 0xFF;
-                    x0 = __funnelshift_l(x1, x0, nb); x1 <<= nb; used += nb;
-                    acc |= (e >> 8) << (8 * r);
+                    for (int r = 0; r < 4; r++) {
+                        uint32_t const idx = x0 >> sh;
+                        uint32_t const nb = lds8u(lenS + (idx >> 1));
+                        uint32_t const sy = lds8u(symS + idx);
+                        x0 = __funnelshift_l(x1, x0, nb); x1 <<= nb; used += nb;
+                        acc |= sy << (8 * r);
+                    }
+                    G -= used;
+                    v[q] = acc;
                 }
-                G -= used;
-                v[q] = acc;
+                *(uint4*)(out + i) = make_uint4(v[0], v[1], v[2], v[3]);
             }
-            *(uint4*)(out + i) = make_uint4(v[0], v[1], v[2], v[3]);
-        }
-        for (; i < count && (int32_t)G >= gz; i++) {
-            br.advance(G);
-            uint32_t const x0 = br.peek32(G);
-            uint32_t e = lds16(tabS + (x0 >> sh1) * 2);
-            if ((e & 0xFF) > kHufL1Log) e = __ldg(gtab + (x0 >> shF));
-            G -= e & 0xFF;
-            out[i] = (uint8_t)(e >> 8);
+            for (; i < count && (int32_t)G >= gz; i++) {
+                br.advance(G);
+                uint32_t const idx = br.peek32(G) >> sh;
+                G -= lds8u(lenS + (idx >> 1));
+                out[i] = (uint8_t)lds8u(symS + idx);
+            }
+        } else {
+            const uint16_t* const gtab = p.hufTable + (size_t)item * kHufTableEntries;
+            for (; i < count && (int32_t)G >= gz; i++) {
+                br.advance(G);
+                uint32_t const e = __ldg(gtab + (br.peek32(G) >> sh));
+                G -= e & 0xFF;
+                out[i] = (uint8_t)(e >> 8);
+            }
         }
         ok = ((int32_t)G == gz) && (i == count);      // BIT_endOfDStream: the stream must be consumed exactly (:526-533)
     }
