@@ -1182,7 +1182,7 @@ __device__ __forceinline__ void put_bits(uint32_t* w, uint64_t bit, uint32_t v, 
     if (sh + nb > 32) atomicOr(&w[(bit >> 5) + 1], (uint32_t)(x >> 32));
 }
 
-__global__ void __launch_bounds__(kEntThreads) enc_entropy_kernel(EncPass p)
+__global__ void __launch_bounds__(kEntThreads, 8) enc_entropy_kernel(EncPass p)
 {
     __shared__ EntShared S;
     uint32_t const item = blockIdx.x, tid = threadIdx.x;
@@ -1442,17 +1442,39 @@ __global__ void __launch_bounds__(kEntThreads) enc_entropy_kernel(EncPass p)
             }
             if (tid == 0) dst[seqHead] = (uint8_t)((types[0] << 6) + (types[1] << 4) + (types[2] << 2));
             // ---- 4. FSE state chains: three lanes walk the sequences last -> first (ZSTD_encodeSequences_body :585) ----
+            // The chain state -> nbBits -> next state is serial; everything else is taken off it: all threads first write
+            // the three symbol codes of every sequence into the chain's own output slots, and each chain lane then works
+            // in steps of 8 sequences: 8 code loads, 8 symbol-transform loads, 8 dependent state steps.
             uint64_t* const sb = p.stateBits + (size_t)item * kEncSeqCap;
+            for (uint32_t n = tid; n < nbSeq; n += kEntThreads) {
+                uint32_t const llc = ll_code(aLL[n]), ofc = highbit32(aOF[n]), mlc = ml_code(aML[n]);
+                sb[n] = (uint64_t)llc | ((uint64_t)ofc << 16) | ((uint64_t)mlc << 32);      // u16 slots: [0] LL [1] OF [2] ML
+            }
+            __syncthreads();
             if (tid < 96 && (tid & 31) == 0) {
                 int const k = tid >> 5;    // 0 LL, 1 OF, 2 ML
                 const FseCTable& ct = S.ct[k];
-                auto code_at = [&](uint32_t n) { return k == 0 ? ll_code(aLL[n]) : (k == 1 ? highbit32(aOF[n]) : ml_code(aML[n])); };
-                uint32_t state = fse_init_state(ct, code_at(nbSeq - 1));
-                // stateBits layout per sequence: bits [13k, 13k+13) = value(9) | count(4)<<9 ; written with 3 separate arrays to avoid races
+                // slot layout per sequence afterwards: value(<= 9 bits) | count << 12
                 uint16_t* const out16 = (uint16_t*)sb + k;                          // 4 x u16 per sequence
+                uint32_t state = fse_init_state(ct, out16[(size_t)(nbSeq - 1) * 4]);
                 out16[(size_t)(nbSeq - 1) * 4] = 0;
-                for (uint32_t n = nbSeq - 1; n-- > 0; ) {
-                    SymbolTT const tt = ct.tt[code_at(n)];
+                uint32_t n = nbSeq - 1;                                             // sequences n-1 .. 0 are still to do
+                while (n >= 8) {
+                    uint32_t c[8]; SymbolTT t[8];
+#pragma unroll
+                    for (int j = 0; j < 8; j++) c[j] = out16[(size_t)(n - 1 - j) * 4];
+#pragma unroll
+                    for (int j = 0; j < 8; j++) t[j] = ct.tt[c[j]];
+#pragma unroll
+                    for (int j = 0; j < 8; j++) {
+                        uint32_t const nb = (state + t[j].deltaNbBits) >> 16;
+                        out16[(size_t)(n - 1 - j) * 4] = (uint16_t)((state & ((1u << nb) - 1)) | (nb << 12));
+                        state = ct.stateTable[(int32_t)(state >> nb) + t[j].deltaFindState];
+                    }
+                    n -= 8;
+                }
+                while (n-- > 0) {
+                    SymbolTT const tt = ct.tt[out16[(size_t)n * 4]];
                     uint32_t const nb = (state + tt.deltaNbBits) >> 16;
                     out16[(size_t)n * 4] = (uint16_t)((state & ((1u << nb) - 1)) | (nb << 12));
                     state = ct.stateTable[(int32_t)(state >> nb) + tt.deltaFindState];
