@@ -504,9 +504,11 @@ __device__ __forceinline__ uint32_t stage_win(const SrcView& v, uint32_t slot, i
     stage16(slot + 512, v.g + min(blk + 1, v.lastBlk), pred && o);
     return o;
 }
-__device__ __forceinline__ Win16 take_win(uint32_t slot, uint32_t o)
+__device__ __forceinline__ Win16 take_win2(uint32_t slotA, uint32_t slotB, uint32_t o);
+__device__ __forceinline__ Win16 take_win(uint32_t slot, uint32_t o) { return take_win2(slot, slot + 512, o); }
+__device__ __forceinline__ Win16 take_win2(uint32_t slotA, uint32_t slotB, uint32_t o)
 {
-    uint4 const a = lds128(slot), b = lds128(slot + 512);
+    uint4 const a = lds128(slotA), b = lds128(slotB);
     uint64_t const q0 = (uint64_t)a.x | ((uint64_t)a.y << 32), q1 = (uint64_t)a.z | ((uint64_t)a.w << 32);
     uint64_t const q2 = (uint64_t)b.x | ((uint64_t)b.y << 32), q3 = (uint64_t)b.z | ((uint64_t)b.w << 32);
     bool const j = o >= 8; uint32_t const sft = (o & 7) * 8;
@@ -515,7 +517,8 @@ __device__ __forceinline__ Win16 take_win(uint32_t slot, uint32_t o)
     r.hi = fsr64(j ? q2 : q1, j ? q3 : q2, sft);
     return r;
 }
-constexpr uint32_t kMatchSlots = 24;             // 12 KB of shared memory per warp
+constexpr uint32_t kMatchSlots = 32;             // 16 KB of shared memory per warp: 24 staging slots + an 8-block source ring
+constexpr uint32_t kRingSlot0 = 24, kRingBlocks = 8;
 // 8 bytes at byte offset k (0..8) of a window
 __device__ __forceinline__ uint64_t win64(const Win16& w, uint32_t k) { return k >= 8 ? w.hi : fsr64(w.lo, w.hi, k * 8); }
 // 4 bytes at byte offset k (0..12) of a window
@@ -572,6 +575,7 @@ __global__ void __launch_bounds__(32) enc_match_fast_kernel(EncPass p, const uin
     int step = 2, nextStep = ip0 + 128, d = 2;       // _start
     bool afterMatch = false;                         // the greedy rep2 loop (:264-285) is still open at ip0
     Win16 X; X.lo = 0; X.hi = 0; int xPos = -1000; uint32_t xLen = 16;   // carried source window: xLen valid bytes at xPos
+    uint32_t ringStart = 0, ringHi = 0, ringOk = 0;   // source ring: blocks [ringStart, ringHi) were queued, those below ringOk have landed
     __shared__ __align__(16) uint8_t s_slots[kMatchSlots * 512];
     uint32_t const S0 = (uint32_t)__cvta_generic_to_shared(s_slots) + (threadIdx.x & 31) * 16;   // slot k of this lane = S0 + k*512
     auto slot = [&](uint32_t k) { return S0 + k * 512; };
@@ -590,7 +594,29 @@ __global__ void __launch_bounds__(32) enc_match_fast_kernel(EncPass p, const uin
         if (pC + S2 >= N2) { S2++; N2 += 128; }
         bool const r2 = active && afterMatch && ip0 <= ilimit && rep2 > 0;
         bool const pr = vA && rep1 != 0, prB = vB && rep1 != 0;
-        // ---- round trip 1: source window at ip0 (skipped when the previous iteration left it behind) ----
+        // ---- source ring: the 16-byte blocks ahead of the scan front are queued here without waiting (they land at the next
+        // wait of this lane); a window that the ring already holds costs no round trip ----
+        uint32_t const bA = ((uint32_t)pA + V.D) >> 4;                                       // block of ip0
+        if (active) {
+            if (bA >= ringHi) { ringStart = bA; ringHi = bA; ringOk = bA; }                   // the front ran past the ring: restart it
+            uint32_t const want = min(((uint32_t)pA + V.D + 112) >> 4, V.lastBlk + 1);        // keep ~100 bytes ahead staged
+#pragma unroll
+            for (int q = 0; q < 3; q++) {
+                bool const go = ringHi < want && ringHi < bA + kRingBlocks;                   // never overwrite the block of ip0
+                stage16(slot(kRingSlot0 + (ringHi & (kRingBlocks - 1))), V.g + min(ringHi, V.lastBlk), go);
+                if (go) ringHi++;
+            }
+        }
+        auto ring_has = [&](int pos) {          // all 16 bytes at pos lie in blocks that have landed and are still in the ring
+            uint32_t const P = (uint32_t)pos + V.D, b0 = P >> 4, b1 = (P + 15) >> 4;
+            return b0 >= ringStart && b0 + kRingBlocks >= ringHi && b1 < ringOk;
+        };
+        auto ring_take = [&](int pos) {
+            uint32_t const P = (uint32_t)pos + V.D, b0 = P >> 4;
+            return take_win2(slot(kRingSlot0 + (b0 & (kRingBlocks - 1))), slot(kRingSlot0 + ((b0 + 1) & (kRingBlocks - 1))), P & 15);
+        };
+        // ---- round trip 1: source window at ip0 (skipped when the previous iteration left it behind or the ring holds it) ----
+        if ((vA || r2) && xPos != pA && ring_has(pA)) { X = ring_take(pA); xPos = pA; xLen = 16; }
         bool const needX = (vA || r2) && xPos != pA;
         if (__any_sync(FULL, needX)) {
             uint32_t const o = stage_win(V, slot(0), pA, needX);
@@ -615,6 +641,7 @@ __global__ void __launch_bounds__(32) enc_match_fast_kernel(EncPass p, const uin
         uint32_t const oRB = stage_win(V, slot(4), pC - (int)rep1, farB);
         stage4(slot(6), T + h0, vA); stage4(slot(6) + 4, T + h1, vA); stage4(slot(6) + 8, T + h2, vB); stage4(slot(6) + 12, T + h3, vB);
         stage_wait();
+        ringOk = ringHi;                                            // everything queued so far has landed
         uint4 const tv = lds128(slot(6));
         uint32_t const t0 = tv.x, t1 = tv.y, t2 = tv.z, t3 = tv.w;
         Win16 const RA = take_win(slot(0), oRA);                   // 16 bytes at ip2 - rep1 (the second probe sits dB bytes further)
@@ -699,9 +726,15 @@ __global__ void __launch_bounds__(32) enc_match_fast_kernel(EncPass p, const uin
         int const mend = mpos + mlen;
         bool const ins = ev && type != 3 && mend <= ilimit;
         // the window at mend-2 serves the insert of ip0-2 and is the source window of the next iteration (ip0 = mend)
-        uint32_t const oNW = stage_win(V, slot(20), mend - 2, ev && mend <= ilimit);
-        stage_wait();
-        Win16 const NW = take_win(slot(20), oNW);
+        bool const wantNW = ev && mend <= ilimit;
+        bool const ringNW = wantNW && ring_has(mend - 2);
+        Win16 NW;
+        if (__any_sync(FULL, wantNW && !ringNW)) {
+            uint32_t const oNW = stage_win(V, slot(20), mend - 2, wantNW && !ringNW);
+            stage_wait();
+            NW = take_win(slot(20), oNW);
+        }
+        if (ringNW) NW = ring_take(mend - 2);
         if (ev) {
             oLL[nseq] = (uint32_t)(mpos - anchor); oOF[nseq] = offcode + 1; oML[nseq] = (uint32_t)mlen - 3;
             nseq++;
