@@ -901,9 +901,15 @@ __device__ __forceinline__ uint32_t g_rd32(const uint8_t* p)        // global, a
 // m (1..16) bytes out of four left-aligned words into the tile: 16 predicated byte stores, no loop
 __device__ __forceinline__ void lane_put16(uint8_t* t, uint32_t v0, uint32_t v1, uint32_t v2, uint32_t v3, uint32_t m)
 {
-    uint32_t const v[4] = {v0, v1, v2, v3};
+    // two levels: most copies are at most 8 bytes long, and 16 flat predicated stores would all issue every time
+    {   uint32_t const v[2] = {v0, v1};
 #pragma unroll
-    for (uint32_t i = 0; i < 16; i++) if (i < m) t[i] = (uint8_t)(v[i >> 2] >> ((i & 3) * 8));
+        for (uint32_t i = 0; i < 8; i++) if (i < m) t[i] = (uint8_t)(v[i >> 2] >> ((i & 3) * 8)); }
+    if (m > 8) {
+        uint32_t const v[2] = {v2, v3};
+#pragma unroll
+        for (uint32_t i = 0; i < 8; i++) if (i + 8 < m) t[i + 8] = (uint8_t)(v[i >> 2] >> ((i & 3) * 8));
+    }
 }
 // up to 16 bytes at g (any alignment): raw aligned words now, left-aligned words later (so that several loads overlap)
 struct Raw16 { uint32_t w0, w1, w2, w3, w4, sh; };
