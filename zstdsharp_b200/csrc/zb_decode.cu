@@ -133,6 +133,11 @@ struct SetupScratch {
     uint16_t start[260];
     int16_t norm[64];
     uint32_t rankStart[16];
+    // sequence tables to be built by the whole warp after lane 0 has parsed the headers (index: 0 LL, 1 ML, 2 OF)
+    int16_t normT[3][64];
+    uint16_t cum[65];
+    uint32_t tabAct[3];      // 0 nothing (repeat), 1 rle, 2 predefined, 3 compressed
+    uint32_t tabArg[3];      // rle: symbol; compressed: maxSV | tableLog << 8
 };
 
 // HUF_readStats_body (EntropyCommon.cs:292) executed by one lane. Returns header size (iSize+1) or 0 on error.
@@ -238,6 +243,73 @@ __device__ void build_seq_table(uint32_t* out, SetupScratch& sc, uint32_t maxSV,
     }
 }
 
+// Warp-parallel ZSTD_buildFSETable_body (ZstdDecompressBlock.cs:1571).  The serial algorithm walks the table with a
+// fixed odd step and skips the cells above highThreshold; here every lane evaluates walk index j directly
+// (cell = j*step mod size), a ballot-prefix gives the rank of the cell among the cells that are kept, and the rank is
+// mapped to its symbol through the cumulated counts.  The second pass needs, for each cell, how many earlier cells hold
+// the same symbol: __match_any_sync per 32 cells plus a running counter per symbol.
+__device__ void build_seq_table_warp(uint32_t* out, SetupScratch& sc, const int16_t* norm, uint32_t maxSV, uint32_t tableLog, int kind, uint32_t lane)
+{
+    uint32_t const FULL = 0xFFFFFFFFu, ltMask = (1u << lane) - 1u;
+    uint32_t const tableSize = 1u << tableLog, tableMask = tableSize - 1;
+    uint32_t const step = (tableSize >> 1) + (tableSize >> 3) + 3;
+    // pass 0: low-probability symbols take the top cells in symbol order; cumulated counts of the others
+    uint32_t nLow = 0, run = 0;
+    for (uint32_t s0 = 0; s0 <= maxSV; s0 += 32) {
+        uint32_t const s = s0 + lane;
+        int const nv = s <= maxSV ? (int)norm[s] : 0;
+        bool const low = nv == -1;
+        uint32_t const lowBallot = __ballot_sync(FULL, low);
+        if (low) { sc.cell[tableSize - 1 - (nLow + __popc(lowBallot & ltMask))] = (uint8_t)s; }
+        if (s <= maxSV) sc.symNext[s] = low ? 1 : (uint16_t)nv;
+        uint32_t const c = nv > 0 ? (uint32_t)nv : 0u;
+        uint32_t incl = c;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { uint32_t const o = __shfl_up_sync(FULL, incl, d); if (lane >= (uint32_t)d) incl += o; }
+        if (s <= maxSV) sc.cum[s] = (uint16_t)(run + incl - c);
+        run += __shfl_sync(FULL, incl, 31);
+        nLow += __popc(lowBallot);
+    }
+    if (lane == 0) sc.cum[maxSV + 1] = (uint16_t)run;
+    __syncwarp();
+    uint32_t const high = tableSize - 1 - nLow;
+    // pass 1: spread
+    uint32_t placed = 0;
+    for (uint32_t j0 = 0; j0 < tableSize; j0 += 32) {
+        uint32_t const j = j0 + lane;
+        uint32_t const pos = (j * step) & tableMask;
+        bool const keep = j < tableSize && pos <= high;
+        uint32_t const kb = __ballot_sync(FULL, keep);
+        if (keep) {
+            uint32_t const k = placed + __popc(kb & ltMask);
+            uint32_t lo = 0, hi = maxSV;                   // largest s with cum[s] <= k (symbols with count 0 share a value: take the last)
+            while (lo < hi) { uint32_t const mid = (lo + hi + 1) >> 1; if (sc.cum[mid] <= k) lo = mid; else hi = mid - 1; }
+            sc.cell[pos] = (uint8_t)lo;
+        }
+        placed += __popc(kb);
+    }
+    __syncwarp();
+    // pass 2: entries in cell order
+    for (uint32_t u0 = 0; u0 < tableSize; u0 += 32) {
+        uint32_t const u = u0 + lane;
+        bool const v = u < tableSize;
+        uint32_t const sym = v ? sc.cell[u] : 0xFFu;
+        uint32_t const peers = __match_any_sync(FULL, sym);
+        uint32_t const base = v ? sc.symNext[sym] : 0u;
+        __syncwarp();
+        uint32_t const ns = base + __popc(peers & ltMask);
+        if (v && (peers >> lane) == 1u) sc.symNext[sym] = (uint16_t)(base + __popc(peers));     // highest lane of the group
+        __syncwarp();
+        if (v) {
+            uint32_t const nbBits = tableLog - highbit32(ns);
+            uint32_t const next = (ns << nbBits) - tableSize;
+            uint32_t const add = kind == 0 ? c_LL_bits[sym] : (kind == 1 ? c_ML_bits[sym] : sym);
+            out[u] = fse_pack(nbBits, add, sym, next);
+        }
+    }
+    __syncwarp();
+}
+
 __global__ void dec_default_tables_kernel(uint32_t* out)
 {
     __shared__ SetupScratch sc;
@@ -323,27 +395,23 @@ __device__ uint32_t setup_seq_headers(DecItem& it, const DecPass& p, uint32_t it
     it.nbSeq = nbSeq;
     if (ip + 1 > srcSize) { *err = kSrcSizeWrong; return 0xFFFFFFFFu; }
     uint32_t const modes = src[ip++];
-    uint32_t* const tbl = p.fseTable + (size_t)item * kFseTableEntries;
     *err = kCorruptionDetected;
     for (int k = 0; k < 3; k++) {   // order: LL, OF, ML
         uint32_t const type = k == 0 ? (modes >> 6) : (k == 1 ? ((modes >> 4) & 3) : ((modes >> 2) & 3));
         int const kind = k == 0 ? 0 : (k == 1 ? 2 : 1);
         uint32_t const maxSym = kind == 0 ? kMaxLL : (kind == 1 ? kMaxML : kMaxOff);
         uint32_t const maxLog = kind == 2 ? kOffFSELog : kLLFSELog;
-        uint32_t const off = kind == 0 ? kFseLLOff : (kind == 1 ? kFseMLOff : kFseOFOff);
         uint32_t* const logPtr = kind == 0 ? &it.llLog : (kind == 1 ? &it.mlLog : &it.ofLog);
         switch (type) {
         case 1: {   // set_rle
             if (ip >= srcSize) return 0xFFFFFFFFu;
             uint32_t const sym = src[ip++];
             if (sym > maxSym) return 0xFFFFFFFFu;
-            uint32_t const add = kind == 0 ? c_LL_bits[sym] : (kind == 1 ? c_ML_bits[sym] : sym);
-            tbl[off] = fse_pack(0, add, sym, 0);
+            sc.tabAct[kind] = 1; sc.tabArg[kind] = sym;
             *logPtr = 0;
             break; }
         case 0: {   // set_basic: predefined table
-            uint32_t const n = kind == 2 ? (1u << kOFDefaultNormLog) : (1u << kLLDefaultNormLog);
-            for (uint32_t u = 0; u < n; u++) tbl[off + u] = p.defaultFse[off + u];
+            sc.tabAct[kind] = 2;
             *logPtr = kind == 2 ? kOFDefaultNormLog : kLLDefaultNormLog;
             break; }
         case 3:     // set_repeat
@@ -351,10 +419,10 @@ __device__ uint32_t setup_seq_headers(DecItem& it, const DecPass& p, uint32_t it
             break;
         default: {  // set_compressed
             uint32_t maxSV = maxSym, tableLog;
-            uint32_t const hs = fse_read_ncount(sc.norm, &maxSV, &tableLog, src + ip, srcSize - ip);
+            uint32_t const hs = fse_read_ncount(sc.normT[kind], &maxSV, &tableLog, src + ip, srcSize - ip);
             if (hs == 0) return 0xFFFFFFFFu;
             if (tableLog > maxLog) return 0xFFFFFFFFu;
-            build_seq_table(tbl + off, sc, maxSV, tableLog, kind);
+            sc.tabAct[kind] = 3; sc.tabArg[kind] = maxSV | (tableLog << 8);
             *logPtr = tableLog;
             ip += hs;
             break; }
@@ -376,6 +444,7 @@ __global__ void __launch_bounds__(kSetupWarps * 32) dec_setup_kernel(DecPass p)
     const uint8_t* const src = p.src + it.srcOff;
     if (lane == 0) {
         s_huf[warp][0] = 0;
+        sc.tabAct[0] = sc.tabAct[1] = sc.tabAct[2] = 0;
         do {
             if (it.status != kStRunning) { it.blkType = kBlkNone; break; }
             uint32_t pos = it.srcPos; uint32_t const size = it.srcSize;
@@ -511,6 +580,23 @@ __global__ void __launch_bounds__(kSetupWarps * 32) dec_setup_kernel(DecPass p)
             }
             if (it.litType == kLitHuf) { uint32_t const slot = atomicAdd(&p.counters[0], 1u); p.hufList[slot] = item; }
         } while (0);
+    }
+    __syncwarp();
+    // sequence tables: built by the whole warp (ZSTD_buildSeqTable :1746)
+    if (it.status == kStRunning && it.blkType == kBlkCompressed) {
+        uint32_t* const tbl = p.fseTable + (size_t)item * kFseTableEntries;
+        for (int kind = 0; kind < 3; kind++) {
+            uint32_t const act = sc.tabAct[kind], arg = sc.tabArg[kind];
+            uint32_t const off = kind == 0 ? kFseLLOff : (kind == 1 ? kFseMLOff : kFseOFOff);
+            if (act == 1) {
+                if (lane == 0) { uint32_t const add = kind == 0 ? c_LL_bits[arg] : (kind == 1 ? c_ML_bits[arg] : arg); tbl[off] = fse_pack(0, add, arg, 0); }
+            } else if (act == 2) {
+                uint32_t const n = kind == 2 ? (1u << kOFDefaultNormLog) : (1u << kLLDefaultNormLog);
+                for (uint32_t u = lane; u < n; u += 32) tbl[off + u] = p.defaultFse[off + u];
+            } else if (act == 3) {
+                build_seq_table_warp(tbl + off, sc, sc.normT[kind], arg & 0xFF, arg >> 8, kind, lane);
+            }
+        }
     }
     __syncwarp();
     // warp-cooperative fill of the single-symbol Huffman table at its native tableLog: every symbol of weight w
