@@ -447,6 +447,122 @@ __global__ void __launch_bounds__(32) enc_match_warp_kernel(EncPass p, const uin
     if (lane == 0) { it.nbSeq = nseq; it.lastLL = (uint32_t)(srcSize - anchor); }
 }
 
+// Same warp-per-chunk parse with the table in HBM/L2 instead of shared memory: no 6-chunks-per-SM limit, all chunks in flight.
+__global__ void __launch_bounds__(32) enc_match_warpg_kernel(EncPass p, const uint32_t* __restrict__ workList)
+{
+    uint32_t const item = workList[blockIdx.x];
+    uint32_t const lane = threadIdx.x;
+    EncItem& it = p.items[item];
+    uint32_t const hlog = it.hashLog, mls = it.minMatch;
+    int const srcSize = (int)it.srcSize;
+    const uint8_t* const src = p.src + it.srcOff;
+    uint32_t* const oLL = p.seqLL + (size_t)item * kEncSeqCap;
+    uint32_t* const oML = p.seqML + (size_t)item * kEncSeqCap;
+    uint32_t* const oOF = p.seqOF + (size_t)item * kEncSeqCap;
+    uint32_t* const T = p.tables + it.tableOff;      // zero-initialised, HBM/L2-resident: every chunk of the batch is in flight
+    int const ilimit = srcSize - 8;
+    int ip0 = 1, anchor = 0;                         // first position is skipped (:129)
+    uint32_t rep1 = 1, rep2 = 0;                     // rep2 = 4 exceeds the history at frame start (:131-145)
+    uint32_t nseq = 0;
+    uint32_t const k = lane >> 1, odd = lane & 1;
+    uint32_t const FULL = 0xFFFFFFFFu;
+    for (;;) {                                       // _start
+        int step = 2, nextStep = ip0 + 128, d = 2;
+        bool matched = false;
+        for (;;) {                                   // one window of 16 iterations
+            int pk, dk, pW, dW, stepW, nextStepW;
+            if (ip0 + d + 16 * step < nextStep) {    // no step change inside the window
+                pk = k == 0 ? ip0 : ip0 + d + ((int)k - 1) * step; dk = k == 0 ? d : step;
+                pW = ip0 + d + 15 * step; dW = step; stepW = step; nextStepW = nextStep;
+            } else {
+                int P = ip0, D = d, S = step, N = nextStep; pk = 0; dk = 0;
+#pragma unroll
+                for (int j = 0; j < 16; j++) { if (j == (int)k) { pk = P; dk = D; } P += D; int const ip2n = P + S; D = S; if (ip2n >= N) { S++; N += 128; } }
+                pW = P; dW = D; stepW = S; nextStepW = N;
+            }
+            bool const vk = pk + dk + 1 < ilimit;    // loop condition ip3 < ilimit for this iteration
+            uint32_t const validMask = __ballot_sync(FULL, vk);
+            if (!(validMask & 1)) break;             // iteration 0 does not run: _cleanup
+            int const q = pk + (int)odd;
+            uint64_t const x = vk ? rd64(src + q) : 0ull;
+            uint32_t const cur4 = (uint32_t)x;
+            bool repHit = false;
+            if (vk && !odd && rep1) { int const r = pk + dk; repHit = rd32(src + r) == rd32(src + r - (int)rep1); }
+            uint32_t const h = hash_val(x, hlog, mls);
+            uint32_t const tv = vk ? __ldcg(T + h) : 0u;
+            uint32_t const peers = __match_any_sync(FULL, vk ? h : (0x80000000u | lane));
+            uint32_t const lower = peers & ((1u << lane) - 1u);
+            int const cl = lower ? 31 - __clz((int)lower) : (int)lane;
+            int const cq = __shfl_sync(FULL, q, cl);
+            int const cand = lower ? cq : (int)tv - 2;                  // table stores position + 2, 0 = empty
+            bool hit = false;
+            if (vk && cand >= 0) hit = rd32(src + cand) == cur4;
+            uint32_t key = 0xFFFFFFFFu;
+            if (hit) key = 3 * k + 1 + odd;
+            if (repHit) key = 3 * k;
+            uint32_t const best = __reduce_min_sync(FULL, key);
+            if (best == 0xFFFFFFFFu) {
+                if (vk && ((peers >> lane) >> 1) == 0) T[h] = (uint32_t)q + 2;   // the latest position of a bucket wins
+                __syncwarp();
+                if (validMask != FULL) break;        // the loop condition failed inside the window: _cleanup
+                ip0 = pW; d = dW; step = stepW; nextStep = nextStepW;
+                continue;
+            }
+            // ---- first event of the window ----
+            uint32_t const ke = best / 3, type = best - 3 * ke;
+            uint32_t const lastLane = 2 * ke + 1;
+            {   uint32_t const peersC = peers & (lastLane == 31 ? FULL : ((2u << lastLane) - 1u));
+                if (vk && lane <= lastLane && ((peersC >> lane) >> 1) == 0) T[h] = (uint32_t)q + 2; }
+            __syncwarp();
+            int const pke = __shfl_sync(FULL, pk, 2 * ke), dke = __shfl_sync(FULL, dk, 2 * ke);
+            uint32_t const evLane = 2 * ke + (type == 2 ? 1u : 0u);
+            int const qe = __shfl_sync(FULL, q, evLane), ce = __shfl_sync(FULL, cand, evLane);
+            int mpos, msrc, mlen, current0; uint32_t offcode;
+            if (type == 0) {                          // repcode at ip2 (:163-178)
+                mpos = pke + dke; msrc = mpos - (int)rep1;
+                int const back = src[mpos - 1] == src[msrc - 1];
+                mpos -= back; msrc -= back; mlen = 4 + back; offcode = 0; current0 = pke;
+            } else {                                  // _offset (:236-247)
+                mpos = qe; msrc = ce; rep2 = rep1; rep1 = (uint32_t)(qe - ce); offcode = rep1 + 2; mlen = 4; current0 = qe;
+                while (mpos > anchor && msrc > 0 && src[mpos - 1] == src[msrc - 1]) { mpos--; msrc--; mlen++; }
+            }
+            mlen += warp_count(src, mpos + mlen, msrc + mlen, srcSize, lane);
+            if (lane == 0) { oLL[nseq] = (uint32_t)(mpos - anchor); oOF[nseq] = offcode + 1; oML[nseq] = (uint32_t)mlen - 3; }
+            nseq++;
+            int const mend = mpos + mlen;
+            if (type == 2 && pke + dke < mend) {      // `if (ip1 < ip0) hashTable[hash1] = ip1` with ip1 = old ip2 (:254-257)
+                int const pp = pke + dke;
+                if (lane == 0) T[hash_val(rd64(src + pp), hlog, mls)] = (uint32_t)pp + 2;
+                __syncwarp();
+            }
+            ip0 = mend; anchor = mend;
+            if (ip0 <= ilimit) {
+                if (lane == 0) {
+                    T[hash_val(rd64(src + current0 + 2), hlog, mls)] = (uint32_t)current0 + 2 + 2;
+                    T[hash_val(rd64(src + ip0 - 2), hlog, mls)] = (uint32_t)(ip0 - 2) + 2;
+                }
+                __syncwarp();
+                while (ip0 <= ilimit && rep2 > 0 && rd32(src + ip0) == rd32(src + ip0 - (int)rep2)) {    // :264-285
+                    int const rlen = warp_count(src, ip0 + 4, ip0 + 4 - (int)rep2, srcSize, lane) + 4;
+                    { uint32_t const t = rep2; rep2 = rep1; rep1 = t; }
+                    if (lane == 0) {
+                        T[hash_val(rd64(src + ip0), hlog, mls)] = (uint32_t)ip0 + 2;
+                        oLL[nseq] = 0; oOF[nseq] = 1; oML[nseq] = (uint32_t)rlen - 3;
+                    }
+                    __syncwarp();
+                    nseq++;
+                    ip0 += rlen; anchor = ip0;
+                }
+            }
+            matched = true;
+            break;
+        }
+        if (!matched) break;
+    }
+    if (lane == 0) { it.nbSeq = nseq; it.lastLL = (uint32_t)(srcSize - anchor); }
+}
+
+
 // ------------------------------------------------------------------------------------------------------------
 //  Lane-per-chunk, exact ZSTD_fast parse with speculative windows: every chunk of the batch is in flight at once
 //  (8192 chunks = 256 warps), hash tables live in HBM/L2, and what bounds the kernel is the chain of dependent
@@ -1667,6 +1783,7 @@ bool enc_compress_device(EncArena& A, cudaStream_t stream, cudaEvent_t* ev, size
         uint32_t* const warpList = (uint32_t*)I.hWork.p; uint32_t* const serialList = warpList + m; uint32_t* const fastList = serialList + m;
         uint32_t nWarp = 0, nSerial = 0, nFast = 0;
         static bool const useWarp = getenv("ZSTDB200_ENC_WARP") != nullptr;    // A/B switch: warp-per-chunk kernel with shared-memory tables
+        static bool const useWarpG = getenv("ZSTDB200_ENC_LANE") == nullptr;   // default: warp-per-chunk kernel with HBM tables; ZSTDB200_ENC_LANE=1 selects the lane-per-chunk state machine
         size_t tableEntries = 0;
         for (size_t i = 0; i < m; i++) {
             size_t const ss = srcSize[base + i];
@@ -1681,7 +1798,8 @@ bool enc_compress_device(EncArena& A, cudaStream_t stream, cudaEvent_t* ev, size
             // ZSTD_fast with a table that fits shared memory -> warp-parallel kernel; everything else (level-2 2^15 tables,
             // dfast's two tables) keeps its tables in HBM/L2 and is parsed by the lane-serial kernel
             if (useWarp && c.strategy == 1 && c.hashLog <= kWarpMatchMaxHashLog && ss >= 64) { warpList[nWarp++] = (uint32_t)i; continue; }
-            if (c.strategy == 1 && ss >= 64) { fastList[nFast++] = (uint32_t)i; }
+            if (useWarpG && c.strategy == 1 && ss >= 64) { warpList[nWarp++] = (uint32_t)i; }
+            else if (c.strategy == 1 && ss >= 64) { fastList[nFast++] = (uint32_t)i; }
             else serialList[nSerial++] = (uint32_t)i;
             e.tableOff = (uint32_t)tableEntries;
             tableEntries += ((size_t)1 << c.hashLog) + (c.strategy == 2 ? ((size_t)1 << c.chainLog) : 0);
@@ -1698,7 +1816,8 @@ bool enc_compress_device(EncArena& A, cudaStream_t stream, cudaEvent_t* ev, size
         p.seqLL = (uint32_t*)I.seqLL.p; p.seqML = (uint32_t*)I.seqML.p; p.seqOF = (uint32_t*)I.seqOF.p; p.litBuf = (uint8_t*)I.lit.p;
         p.stateBits = (uint64_t*)I.stateBits.p; p.results = (uint64_t*)I.results.p; p.checksumFlag = checksumFlag ? 1u : 0u;
         enc_set_attrs();
-        if (nWarp) enc_match_warp_kernel<<<nWarp, 32, (1u << kWarpMatchMaxHashLog) * 4, stream>>>(p, (const uint32_t*)I.workLists.p);
+        if (nWarp && useWarpG) enc_match_warpg_kernel<<<nWarp, 32, 0, stream>>>(p, (const uint32_t*)I.workLists.p);
+        else if (nWarp) enc_match_warp_kernel<<<nWarp, 32, (1u << kWarpMatchMaxHashLog) * 4, stream>>>(p, (const uint32_t*)I.workLists.p);
         if (nSerial) enc_match_kernel<<<(nSerial + 31) / 32, 32, 0, stream>>>(p, (const uint32_t*)I.workLists.p + m, nSerial);
         if (nFast) enc_match_fast_kernel<<<(nFast + 31) / 32, 32, 0, stream>>>(p, (const uint32_t*)I.workLists.p + 2 * m, nFast);
         ENC_CUDA(cudaEventRecord(ev[15], stream));
