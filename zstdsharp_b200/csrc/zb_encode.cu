@@ -14,6 +14,7 @@
 //                                       block/frame assembly with the reference's accept/reject gates
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -562,6 +563,144 @@ __global__ void __launch_bounds__(32) enc_match_warpg_kernel(EncPass p, const ui
     if (lane == 0) { it.nbSeq = nseq; it.lastLL = (uint32_t)(srcSize - anchor); }
 }
 
+
+// ------------------------------------------------------------------------------------------------------------
+//  Group-per-chunk, exact ZSTD_fast parse: GS lanes (8 / 16 / 32) own one chunk, a warp carries 32/GS chunks.
+//  Same speculative window as the warp kernel above (lane 2k / 2k+1 = the two probes of reference iteration k, GS/2
+//  iterations per window), but written as a warp-uniform state machine: every group walks through the same phases in
+//  every round and a group that has nothing to do in a phase is predicated off, so the groups of a warp share one
+//  instruction stream.  A 32-lane window wastes ~28 of its 32 probes on text (the first event sits within the first few
+//  probes): ncu showed 33 G warp instructions and 120 GB of DRAM reads per GiB; 8 lanes per chunk cut both.
+// ------------------------------------------------------------------------------------------------------------
+template <int GS>
+__global__ void __launch_bounds__(32) enc_match_group_kernel(EncPass p, const uint32_t* __restrict__ workList, uint32_t nWork)
+{
+    constexpr uint32_t FULL = 0xFFFFFFFFu;
+    constexpr int NG = 32 / GS, NIT = GS / 2;
+    constexpr uint32_t LOW = GS == 32 ? FULL : ((1u << (GS & 31)) - 1u);
+    uint32_t const lane = threadIdx.x, g = lane / GS, l = lane % GS, gbase = g * GS;
+    uint32_t const gmask = LOW << gbase;
+    uint32_t const wi = blockIdx.x * NG + g;
+    bool active = wi < nWork;
+    uint32_t const item = workList[active ? wi : 0];
+    EncItem& it = p.items[item];
+    uint32_t const hlog = it.hashLog, mls = it.minMatch;
+    int const srcSize = active ? (int)it.srcSize : 64;
+    const uint8_t* const src = p.src + it.srcOff;
+    uint32_t* const T = p.tables + it.tableOff;      // zero-initialised, HBM/L2-resident
+    uint32_t* const oLL = p.seqLL + (size_t)item * kEncSeqCap;
+    uint32_t* const oML = p.seqML + (size_t)item * kEncSeqCap;
+    uint32_t* const oOF = p.seqOF + (size_t)item * kEncSeqCap;
+    int const ilimit = srcSize - 8;
+    int ip0 = 1, anchor = 0;                         // first position is skipped (:129)
+    uint32_t rep1 = 1, rep2 = 0;                     // rep2 = 4 exceeds the history at frame start (:131-145)
+    uint32_t nseq = 0;
+    int step = 2, nextStep = ip0 + 128, d = 2;       // _start
+    bool afterMatch = false;                         // the greedy rep2 loop (:264-285) is still open at ip0
+    uint32_t const k = l >> 1, odd = l & 1;
+    auto gballot = [&](bool pr) -> uint32_t { return (__ballot_sync(FULL, pr) >> gbase) & LOW; };
+    while (__any_sync(FULL, active)) {
+        // ---- positions of this lane's probe: iteration k of the window (ZstdFast.cs:147-230 schedule) ----
+        int P = ip0, D = d, S = step, N = nextStep, pk = 0, dk = 0;
+#pragma unroll
+        for (int j = 0; j < NIT; j++) { if (j == (int)k) { pk = P; dk = D; } P += D; int const ip2n = P + S; D = S; if (ip2n >= N) { S++; N += 128; } }
+        bool const vk = active && (pk + dk + 1 < ilimit);          // loop condition ip3 < ilimit for this iteration
+        uint32_t const validMask = gballot(vk);
+        // ---- open rep2 loop first (:264-285): same answer in every lane of the group ----
+        bool const r2 = active && afterMatch && ip0 <= ilimit && rep2 > 0;
+        bool const r2hit = r2 && rd32(src + ip0) == rd32(src + ip0 - (int)rep2);
+        // ---- probes ----
+        int const q = pk + (int)odd;
+        uint64_t const x = vk ? rd64(src + q) : 0ull;
+        uint32_t const cur4 = (uint32_t)x;
+        bool repHit = false;
+        if (vk && !odd && rep1) { int const r = pk + dk; repHit = rd32(src + r) == rd32(src + r - (int)rep1); }
+        uint32_t const h = hash_val(x, hlog, mls);
+        uint32_t const tv = vk ? __ldcg(T + h) : 0u;
+        uint32_t const peers = (__match_any_sync(FULL, vk ? (h | (g << 24)) : (0x80000000u | lane)) >> gbase) & LOW;
+        uint32_t const lower = peers & ((1u << l) - 1u);
+        int const cl = lower ? 31 - __clz((int)lower) : (int)l;
+        int const cq = __shfl_sync(FULL, q, gbase + cl);
+        int const cand = lower ? cq : (int)tv - 2;                  // table stores position + 2, 0 = empty
+        bool const hit = vk && cand >= 0 && rd32(src + cand) == cur4;
+        uint32_t key = 0xFFFFFFFFu;                                 // 0: rep2 at ip0; 1 + 3k: repcode at ip2; 2 + 3k / 3 + 3k: hash hit at ip0 / ip1
+        if (hit) key = 3 * k + 2 + odd;
+        if (repHit) key = 3 * k + 1;
+        if (r2hit) key = 0;
+        uint32_t const best = __reduce_min_sync(gmask, key);
+        bool const ev = active && best != 0xFFFFFFFFu;
+        int const type = !ev ? -1 : (best == 0 ? 3 : (int)((best - 1) % 3));
+        uint32_t const ke = (ev && best) ? (best - 1) / 3 : 0u;
+        if (active && type != 3) afterMatch = false;
+        // ---- table writes that precede the event; the latest position of a bucket wins ----
+        {
+            uint32_t const lastLane = type < 0 ? (uint32_t)GS - 1 : 2 * ke + 1;
+            uint32_t const peersC = peers & (lastLane >= 31 ? FULL : ((2u << lastLane) - 1u));
+            if (vk && type != 3 && l <= lastLane && ((peersC >> l) >> 1) == 0) T[h] = (uint32_t)q + 2;
+        }
+        if (type == 3 && l == 0) T[hash_val(rd64(src + ip0), hlog, mls)] = (uint32_t)ip0 + 2;     // :278
+        // ---- match geometry (group-uniform) ----
+        int const pke = __shfl_sync(FULL, pk, gbase + 2 * ke), dke = __shfl_sync(FULL, dk, gbase + 2 * ke);
+        uint32_t const evLane = 2 * ke + (type == 2 ? 1u : 0u);
+        int const qe = __shfl_sync(FULL, q, gbase + evLane), ce = __shfl_sync(FULL, cand, gbase + evLane);
+        int mpos = 0, msrc = 0, mlen = 0, current0 = 0; uint32_t offcode = 0;
+        if (type == 3) { mpos = ip0; msrc = ip0 - (int)rep2; mlen = 4; uint32_t const t = rep2; rep2 = rep1; rep1 = t; }
+        else if (type == 0) {
+            mpos = pke + dke; msrc = mpos - (int)rep1;
+            int const back = src[mpos - 1] == src[msrc - 1];        // one byte, no anchor test (:171)
+            mpos -= back; msrc -= back; mlen = 4 + back; current0 = pke;
+        } else if (type > 0) { mpos = qe; msrc = ce; rep2 = rep1; rep1 = (uint32_t)(qe - ce); offcode = rep1 + 2; mlen = 4; current0 = qe; }
+        // backward extension of hash matches (:236-247): lane l looks l+1 bytes back, GS bytes per round
+        {
+            bool ext = type == 1 || type == 2;
+            while (__any_sync(FULL, ext)) {
+                int const a = mpos - 1 - (int)l, b = msrc - 1 - (int)l;
+                bool const ok = ext && a >= anchor && b >= 0 && src[a] == src[b];
+                uint32_t const okm = gballot(ok);
+                uint32_t const n = okm == LOW ? (uint32_t)GS : (uint32_t)__ffs((int)~okm) - 1u;
+                if (ext) { mpos -= (int)n; msrc -= (int)n; mlen += (int)n; ext = n == (uint32_t)GS; }
+            }
+        }
+        // forward extension (ZSTD_count :264): lane l compares 4 bytes, 4*GS bytes per round
+        {
+            bool cnt = ev;
+            while (__any_sync(FULL, cnt)) {
+                int const pa = mpos + mlen + 4 * (int)l, pb = msrc + mlen + 4 * (int)l;
+                int const rem = srcSize - pa;
+                uint32_t n = 4;
+                if (cnt) {
+                    if (rem >= 4) { uint32_t const diff = rd32(src + pa) ^ rd32(src + pb); n = diff ? (uint32_t)(__ffs((int)diff) - 1) >> 3 : 4u; }
+                    else { n = 0; for (int j = 0; j < rem; j++) { if (src[pa + j] == src[pb + j]) n++; else break; } }
+                }
+                uint32_t const notFull = gballot(cnt && n != 4);
+                uint32_t const f = notFull ? (uint32_t)__ffs((int)notFull) - 1u : 0u;
+                uint32_t const nf = __shfl_sync(FULL, n, gbase + f);
+                if (cnt) { if (notFull) { mlen += 4 * (int)f + (int)nf; cnt = false; } else mlen += 4 * GS; }
+            }
+        }
+        // ---- sequence, post-match inserts (:251-263), next state ----
+        if (ev) {
+            if (l == 0) { oLL[nseq] = (uint32_t)(mpos - anchor); oOF[nseq] = offcode + 1; oML[nseq] = (uint32_t)mlen - 3; }
+            nseq++;
+            int const mend = mpos + mlen;
+            if (l == 0) {
+                if (type == 2 && pke + dke < mend) { int const pp = pke + dke; T[hash_val(rd64(src + pp), hlog, mls)] = (uint32_t)pp + 2; }   // `if (ip1 < ip0) hashTable[hash1] = ip1`
+                if (type != 3 && mend <= ilimit) {
+                    T[hash_val(rd64(src + current0 + 2), hlog, mls)] = (uint32_t)current0 + 2 + 2;
+                    T[hash_val(rd64(src + mend - 2), hlog, mls)] = (uint32_t)(mend - 2) + 2;
+                }
+            }
+            ip0 = mend; anchor = mend;
+            afterMatch = true;
+            step = 2; nextStep = ip0 + 128; d = 2;    // _start
+        } else if (active) {
+            if (validMask != LOW) active = false;     // the loop condition failed inside the window: _cleanup
+            else { ip0 = P; d = D; step = S; nextStep = N; }
+        }
+        __syncwarp();
+    }
+    if (wi < nWork && l == 0) { it.nbSeq = nseq; it.lastLL = (uint32_t)(srcSize - anchor); }
+}
 
 // ------------------------------------------------------------------------------------------------------------
 //  Lane-per-chunk, exact ZSTD_fast parse with speculative windows: every chunk of the batch is in flight at once
@@ -1816,7 +1955,11 @@ bool enc_compress_device(EncArena& A, cudaStream_t stream, cudaEvent_t* ev, size
         p.seqLL = (uint32_t*)I.seqLL.p; p.seqML = (uint32_t*)I.seqML.p; p.seqOF = (uint32_t*)I.seqOF.p; p.litBuf = (uint8_t*)I.lit.p;
         p.stateBits = (uint64_t*)I.stateBits.p; p.results = (uint64_t*)I.results.p; p.checksumFlag = checksumFlag ? 1u : 0u;
         enc_set_attrs();
-        if (nWarp && useWarpG) enc_match_warpg_kernel<<<nWarp, 32, 0, stream>>>(p, (const uint32_t*)I.workLists.p);
+        static int const groupLanes = getenv("ZSTDB200_ENC_GROUP") ? atoi(getenv("ZSTDB200_ENC_GROUP")) : 16;   // lanes per chunk: 16 measured best (8: 49/52 ms, 16: 42/49 ms, 32: 63/72 ms Silesia-mix/text); 0 = one-chunk warp kernel
+        if (nWarp && useWarpG && groupLanes == 8) enc_match_group_kernel<8><<<(nWarp + 3) / 4, 32, 0, stream>>>(p, (const uint32_t*)I.workLists.p, nWarp);
+        else if (nWarp && useWarpG && groupLanes == 16) enc_match_group_kernel<16><<<(nWarp + 1) / 2, 32, 0, stream>>>(p, (const uint32_t*)I.workLists.p, nWarp);
+        else if (nWarp && useWarpG && groupLanes == 32) enc_match_group_kernel<32><<<nWarp, 32, 0, stream>>>(p, (const uint32_t*)I.workLists.p, nWarp);
+        else if (nWarp && useWarpG) enc_match_warpg_kernel<<<nWarp, 32, 0, stream>>>(p, (const uint32_t*)I.workLists.p);
         else if (nWarp) enc_match_warp_kernel<<<nWarp, 32, (1u << kWarpMatchMaxHashLog) * 4, stream>>>(p, (const uint32_t*)I.workLists.p);
         if (nSerial) enc_match_kernel<<<(nSerial + 31) / 32, 32, 0, stream>>>(p, (const uint32_t*)I.workLists.p + m, nSerial);
         if (nFast) enc_match_fast_kernel<<<(nFast + 31) / 32, 32, 0, stream>>>(p, (const uint32_t*)I.workLists.p + 2 * m, nFast);
