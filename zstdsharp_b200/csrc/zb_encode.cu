@@ -703,6 +703,168 @@ __global__ void __launch_bounds__(32) enc_match_group_kernel(EncPass p, const ui
 }
 
 // ------------------------------------------------------------------------------------------------------------
+//  Group-per-chunk, exact ZSTD_dfast parse (level 3; ZstdDoubleFast.cs:51-248), same warp-uniform construction.
+//  Lane j < GS-1 owns probe position ip_j of the window (the schedule ip_{j+1} = ip_j + step, step + 1 every 256 bytes,
+//  depends only on the state until a match is found); lane GS-1 only supplies the long-table probe of the position
+//  after the last one ("_search_next_long", :167-205).  Both tables are read before they are written at every position,
+//  in position order: a probe sees earlier probes of its window through __match_any_sync and older positions
+//  through the tables, and writes are committed up to the first event only.
+// ------------------------------------------------------------------------------------------------------------
+template <int GS>
+__global__ void __launch_bounds__(32) enc_match_dfast_group_kernel(EncPass p, const uint32_t* __restrict__ workList, uint32_t nWork)
+{
+    constexpr uint32_t FULL = 0xFFFFFFFFu;
+    constexpr int NG = 32 / GS;
+    constexpr uint32_t LOW = GS == 32 ? FULL : ((1u << (GS & 31)) - 1u);
+    uint32_t const lane = threadIdx.x, g = lane / GS, l = lane % GS, gbase = g * GS;
+    uint32_t const gmask = LOW << gbase;
+    uint32_t const wi = blockIdx.x * NG + g;
+    bool active = wi < nWork;
+    uint32_t const item = workList[active ? wi : 0];
+    EncItem& it = p.items[item];
+    uint32_t const hBitsL = it.hashLog, hBitsS = it.chainLog, mls = it.minMatch;
+    int const srcSize = active ? (int)it.srcSize : 64;
+    const uint8_t* const src = p.src + it.srcOff;
+    uint32_t* const TL = p.tables + it.tableOff;                  // long table (hash8), then short table (hash mls)
+    uint32_t* const TS = TL + (1u << hBitsL);
+    uint32_t* const oLL = p.seqLL + (size_t)item * kEncSeqCap;
+    uint32_t* const oML = p.seqML + (size_t)item * kEncSeqCap;
+    uint32_t* const oOF = p.seqOF + (size_t)item * kEncSeqCap;
+    int const ilimit = srcSize - 8;
+    int ip = 1, anchor = 0;                          // first position is skipped (:84)
+    uint32_t off1 = 1, off2 = 0;                     // offset_2 = 4 exceeds the history at frame start
+    uint32_t nseq = 0;
+    int step = 1, nextStep = ip + 256;
+    bool afterMatch = false;
+    auto gballot = [&](bool pr) -> uint32_t { return (__ballot_sync(FULL, pr) >> gbase) & LOW; };
+    auto hashL = [&](uint64_t x) { return (uint32_t)((x * 0xCF1BBCDCB7A56463ull) >> (64 - hBitsL)); };
+    // common prefix of src[a..) and src[b..) by the group, lane l compares 4 bytes per round (ZSTD_count :264); valid in every lane
+    auto gcount = [&](bool on, int a, int b) -> int {
+        int total = 0; bool cnt = on;
+        while (__any_sync(FULL, cnt)) {
+            int const pa = a + total + 4 * (int)l, pb = b + total + 4 * (int)l;
+            int const rem = srcSize - pa;
+            uint32_t n = 4;
+            if (cnt) {
+                if (rem >= 4) { uint32_t const diff = rd32(src + pa) ^ rd32(src + pb); n = diff ? (uint32_t)(__ffs((int)diff) - 1) >> 3 : 4u; }
+                else { n = 0; for (int j = 0; j < rem; j++) { if (src[pa + j] == src[pb + j]) n++; else break; } }
+            }
+            uint32_t const notFull = gballot(cnt && n != 4);
+            uint32_t const f = notFull ? (uint32_t)__ffs((int)notFull) - 1u : 0u;
+            uint32_t const nf = __shfl_sync(FULL, n, gbase + f);
+            if (cnt) { if (notFull) { total += 4 * (int)f + (int)nf; cnt = false; } else total += 4 * GS; }
+        }
+        return total;
+    };
+    while (__any_sync(FULL, active)) {
+        // ---- window schedule: position of lane l, the step in force there, state after GS-1 positions ----
+        int P = ip, S = step, N = nextStep, pj = 0, sj = 1;
+        int Pn = 0, Sn = 0, Nn = 0;
+#pragma unroll
+        for (int j = 0; j < GS; j++) {
+            if (j == (int)l) { pj = P; sj = S; }
+            if (j == GS - 1) { Pn = P; Sn = S; Nn = N; }           // state if positions 0..GS-2 all fail
+            int const p1 = P + S;
+            if (p1 >= N) { S++; N += 256; }
+            P = p1;
+        }
+        bool const vj = active && (pj + sj <= ilimit);             // loop condition ip1 <= ilimit at this position
+        bool const probe = vj && l < GS - 1;                        // lane GS-1 only looks ahead
+        uint32_t const validMask = gballot(vj);
+        // ---- open offset_2 loop (:231-243) ----
+        bool const r2 = active && afterMatch && ip <= ilimit && off2 > 0;
+        bool const r2hit = r2 && rd32(src + ip) == rd32(src + ip - (int)off2);
+        // ---- probes ----
+        bool const rdok = active && pj <= ilimit;                   // 8 readable bytes (the look-ahead lane may sit beyond the last position)
+        uint64_t const x = rdok ? rd64(src + pj) : 0ull;
+        uint32_t const hl = hashL(x), hs = hash_val(x, hBitsS, mls);
+        bool const repHit = probe && off1 > 0 && rd32(src + pj + 1) == rd32(src + pj + 1 - (int)off1);
+        uint32_t const tl = rdok ? __ldcg(TL + hl) : 0u, ts = probe ? __ldcg(TS + hs) : 0u;
+        uint32_t const peersL = (__match_any_sync(FULL, rdok ? (hl | (g << 24)) : (0x80000000u | lane)) >> gbase) & LOW;
+        uint32_t const peersS = (__match_any_sync(FULL, probe ? (hs | (g << 24)) : (0x80000000u | lane)) >> gbase) & LOW;
+        uint32_t const lowL = peersL & ((1u << l) - 1u), lowS = peersS & ((1u << l) - 1u);
+        int const fl = lowL ? 31 - __clz((int)lowL) : (int)l, fs = lowS ? 31 - __clz((int)lowS) : (int)l;
+        int const pfl = __shfl_sync(FULL, pj, gbase + fl), pfs = __shfl_sync(FULL, pj, gbase + fs);
+        int const candL = lowL ? pfl : (int)tl - 2, candS = lowS ? pfs : (int)ts - 2;     // tables store position + 2; valid iff index > 2
+        bool const Lhit = rdok && candL >= 1 && rd64(src + candL) == x;
+        bool const Shit = probe && candS >= 1 && rd32(src + candS) == (uint32_t)x;
+        uint32_t key = 0xFFFFFFFFu;                                 // 0: offset_2 repeat at ip; 1+3j: repcode at ip+1; 2+3j: long at ip; 3+3j: short at ip
+        if (probe) { if (Shit) key = 3 * l + 3; if (Lhit) key = 3 * l + 2; if (repHit) key = 3 * l + 1; }
+        if (r2hit) key = 0;
+        uint32_t const best = __reduce_min_sync(gmask, key);
+        bool const ev = active && best != 0xFFFFFFFFu;
+        int const type = !ev ? -1 : (best == 0 ? 3 : (int)((best - 1) % 3));         // 0 repcode, 1 long, 2 short (-> next long?), 3 offset_2 repeat
+        uint32_t const je = (ev && best) ? (best - 1) / 3 : 0u;
+        if (active && type != 3) afterMatch = false;
+        // ---- both tables are written at every position up to the event (:122); the latest position of a bucket wins ----
+        {
+            uint32_t const lastLane = type < 0 ? (uint32_t)GS - 2 : je;
+            uint32_t const keep = (2u << lastLane) - 1u;
+            if (probe && type != 3 && l <= lastLane) {
+                if ((((peersL & keep) >> l) >> 1) == 0) TL[hl] = (uint32_t)pj + 2;
+                if ((((peersS & keep) >> l) >> 1) == 0) TS[hs] = (uint32_t)pj + 2;
+            }
+        }
+        if (type == 3 && l == 0) { uint64_t const xi = rd64(src + ip); TS[hash_val(xi, hBitsS, mls)] = (uint32_t)ip + 2; TL[hashL(xi)] = (uint32_t)ip + 2; }   // :237-238
+        // ---- event data (group-uniform) ----
+        int const pe = __shfl_sync(FULL, pj, gbase + je), se = __shfl_sync(FULL, sj, gbase + je);
+        int const cLe = __shfl_sync(FULL, candL, gbase + je), cSe = __shfl_sync(FULL, candS, gbase + je);
+        uint32_t const nx = je + 1 < (uint32_t)GS ? je + 1 : je;
+        bool const nextLong = __shfl_sync(FULL, (int)Lhit, gbase + nx) != 0;       // long match at ip1 (:167-177); Lhit implies 8 readable bytes there
+        int const cLn = __shfl_sync(FULL, candL, gbase + nx);
+        uint32_t const hln = __shfl_sync(FULL, hl, gbase + nx);
+        int const p1e = pe + se;                                    // ip1 of the event position
+        int mpos = 0, msrc = 0, mlen = 0, curr = pe; uint32_t offcode = 0; int base8 = 4;
+        bool bext = false;
+        if (type == 3) { mpos = ip; msrc = ip - (int)off2; curr = 0; uint32_t const t = off2; off2 = off1; off1 = t; }
+        else if (type == 0) { mpos = pe + 1; msrc = mpos - (int)off1; }
+        else if (type == 1) { mpos = pe; msrc = cLe; base8 = 8; bext = true; }
+        else if (type == 2) {
+            if (nextLong && p1e <= ilimit) { mpos = p1e; msrc = cLn; base8 = 8; } else { mpos = pe; msrc = cSe; }
+            bext = true;
+        }
+        mlen = base8 + gcount(ev, mpos + base8, msrc + base8);
+        // backward extension (:141-146, :178-205): lane l looks l+1 bytes back
+        {
+            bool ext = bext;
+            while (__any_sync(FULL, ext)) {
+                int const a = mpos - 1 - (int)l, b = msrc - 1 - (int)l;
+                bool const ok = ext && a >= anchor && b >= 0 && src[a] == src[b];     // ip > anchor and match > prefixLowest before every step
+                uint32_t const okm = gballot(ok);
+                uint32_t const n = okm == LOW ? (uint32_t)GS : (uint32_t)__ffs((int)~okm) - 1u;
+                if (ext) { mpos -= (int)n; msrc -= (int)n; mlen += (int)n; ext = n == (uint32_t)GS; }
+            }
+        }
+        if (ev) {
+            if (type == 1 || type == 2) {
+                uint32_t const offset = (uint32_t)(mpos - msrc);
+                off2 = off1; off1 = offset; offcode = offset + 2;
+                if (l == 0 && se < 4 && p1e <= ilimit) TL[hln] = (uint32_t)p1e + 2;   // complementary insertion (:210-213): hashLong[hl1] = ip1
+            }
+            if (l == 0) { oLL[nseq] = (uint32_t)(mpos - anchor); oOF[nseq] = offcode + 1; oML[nseq] = (uint32_t)mlen - 3; }
+            nseq++;
+            int const mend = mpos + mlen;
+            if (l == 0 && type != 3 && mend <= ilimit) {             // :221-229
+                int const ins = curr + 2;
+                uint64_t const xa = rd64(src + ins), xb = rd64(src + mend - 2), xc = rd64(src + mend - 1);
+                TL[hashL(xa)] = (uint32_t)ins + 2;
+                TL[hashL(xb)] = (uint32_t)(mend - 2) + 2;
+                TS[hash_val(xa, hBitsS, mls)] = (uint32_t)ins + 2;
+                TS[hash_val(xc, hBitsS, mls)] = (uint32_t)(mend - 1) + 2;
+            }
+            ip = mend; anchor = mend;
+            afterMatch = true;
+            step = 1; nextStep = ip + 256;
+        } else if (active) {
+            if ((validMask & (LOW >> 1)) != (LOW >> 1)) active = false;     // a position of the window failed the loop condition: _cleanup
+            else { ip = Pn; step = Sn; nextStep = Nn; }
+        }
+        __syncwarp();
+    }
+    if (wi < nWork && l == 0) { it.nbSeq = nseq; it.lastLL = (uint32_t)(srcSize - anchor); }
+}
+
+// ------------------------------------------------------------------------------------------------------------
 //  Lane-per-chunk, exact ZSTD_fast parse with speculative windows: every chunk of the batch is in flight at once
 //  (8192 chunks = 256 warps), hash tables live in HBM/L2, and what bounds the kernel is the chain of dependent
 //  memory round trips per sequence (source words -> table entries -> candidate bytes).  A lane therefore issues the
@@ -1917,10 +2079,10 @@ bool enc_compress_device(EncArena& A, cudaStream_t stream, cudaEvent_t* ev, size
     for (size_t base = 0; base < n; base += kEncMaxItemsPerPass) {
         size_t const m = std::min(kEncMaxItemsPerPass, n - base);
         if (!I.hItems.ensure(m * sizeof(EncItem)) || !I.items.ensure(m * sizeof(EncItem)) || !I.results.ensure(m * 8) || !I.hResults.ensure(m * 8)) { t_encErr = "out of memory (items)"; return false; }
-        if (!I.hWork.ensure(m * 12) || !I.workLists.ensure(m * 12)) { t_encErr = "out of memory (work lists)"; return false; }
+        if (!I.hWork.ensure(m * 16) || !I.workLists.ensure(m * 16)) { t_encErr = "out of memory (work lists)"; return false; }
         EncItem* hi = (EncItem*)I.hItems.p;
-        uint32_t* const warpList = (uint32_t*)I.hWork.p; uint32_t* const serialList = warpList + m; uint32_t* const fastList = serialList + m;
-        uint32_t nWarp = 0, nSerial = 0, nFast = 0;
+        uint32_t* const warpList = (uint32_t*)I.hWork.p; uint32_t* const serialList = warpList + m; uint32_t* const fastList = serialList + m; uint32_t* const dfastList = fastList + m;
+        uint32_t nWarp = 0, nSerial = 0, nFast = 0, nDfast = 0;
         static bool const useWarp = getenv("ZSTDB200_ENC_WARP") != nullptr;    // A/B switch: warp-per-chunk kernel with shared-memory tables
         static bool const useWarpG = getenv("ZSTDB200_ENC_LANE") == nullptr;   // default: warp-per-chunk kernel with HBM tables; ZSTDB200_ENC_LANE=1 selects the lane-per-chunk state machine
         size_t tableEntries = 0;
@@ -1937,7 +2099,8 @@ bool enc_compress_device(EncArena& A, cudaStream_t stream, cudaEvent_t* ev, size
             // ZSTD_fast with a table that fits shared memory -> warp-parallel kernel; everything else (level-2 2^15 tables,
             // dfast's two tables) keeps its tables in HBM/L2 and is parsed by the lane-serial kernel
             if (useWarp && c.strategy == 1 && c.hashLog <= kWarpMatchMaxHashLog && ss >= 64) { warpList[nWarp++] = (uint32_t)i; continue; }
-            if (useWarpG && c.strategy == 1 && ss >= 64) { warpList[nWarp++] = (uint32_t)i; }
+            if (useWarpG && c.strategy == 2 && ss >= 64) { dfastList[nDfast++] = (uint32_t)i; }
+            else if (useWarpG && c.strategy == 1 && ss >= 64) { warpList[nWarp++] = (uint32_t)i; }
             else if (c.strategy == 1 && ss >= 64) { fastList[nFast++] = (uint32_t)i; }
             else serialList[nSerial++] = (uint32_t)i;
             e.tableOff = (uint32_t)tableEntries;
@@ -1948,7 +2111,7 @@ bool enc_compress_device(EncArena& A, cudaStream_t stream, cudaEvent_t* ev, size
             !I.seqOF.ensure(m * (size_t)kEncSeqCap * 4) || !I.lit.ensure(m * (size_t)kEncLitStride) || !I.stateBits.ensure(m * (size_t)kEncSeqCap * 8)) { t_encErr = "out of memory (arena)"; return false; }
         ENC_CUDA(cudaMemcpyAsync(I.items.p, hi, m * sizeof(EncItem), cudaMemcpyHostToDevice, stream));
         ENC_CUDA(cudaEventRecord(ev[14], stream));
-        ENC_CUDA(cudaMemcpyAsync(I.workLists.p, I.hWork.p, m * 12, cudaMemcpyHostToDevice, stream));
+        ENC_CUDA(cudaMemcpyAsync(I.workLists.p, I.hWork.p, m * 16, cudaMemcpyHostToDevice, stream));
         if (tableEntries) ENC_CUDA(cudaMemsetAsync(I.tables.p, 0, tableEntries * 4, stream));      // tables are zeroed per frame (ZstdCompress.cs:2472,2481)
         EncPass p;
         p.items = (EncItem*)I.items.p; p.nItems = (uint32_t)m; p.src = d_src; p.dst = d_dst; p.tables = (uint32_t*)I.tables.p;
@@ -1963,10 +2126,11 @@ bool enc_compress_device(EncArena& A, cudaStream_t stream, cudaEvent_t* ev, size
         else if (nWarp) enc_match_warp_kernel<<<nWarp, 32, (1u << kWarpMatchMaxHashLog) * 4, stream>>>(p, (const uint32_t*)I.workLists.p);
         if (nSerial) enc_match_kernel<<<(nSerial + 31) / 32, 32, 0, stream>>>(p, (const uint32_t*)I.workLists.p + m, nSerial);
         if (nFast) enc_match_fast_kernel<<<(nFast + 31) / 32, 32, 0, stream>>>(p, (const uint32_t*)I.workLists.p + 2 * m, nFast);
+        if (nDfast) enc_match_dfast_group_kernel<16><<<(nDfast + 1) / 2, 32, 0, stream>>>(p, (const uint32_t*)I.workLists.p + 3 * m, nDfast);
         ENC_CUDA(cudaEventRecord(ev[15], stream));
         enc_entropy_kernel<<<(unsigned)m, kEntThreads, 0, stream>>>(p);
         ENC_CUDA(cudaEventRecord(ev[16], stream));
-        *launches += 1 + (nWarp ? 1 : 0) + (nSerial ? 1 : 0) + (nFast ? 1 : 0) + (tableEntries ? 1 : 0);
+        *launches += 1 + (nWarp ? 1 : 0) + (nSerial ? 1 : 0) + (nFast ? 1 : 0) + (nDfast ? 1 : 0) + (tableEntries ? 1 : 0);
         ENC_CUDA(cudaMemcpyAsync(I.hResults.p, I.results.p, m * 8, cudaMemcpyDeviceToHost, stream));
         ENC_CUDA(cudaStreamSynchronize(stream));
         ENC_CUDA(cudaGetLastError());
