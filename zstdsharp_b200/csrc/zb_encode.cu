@@ -1222,7 +1222,10 @@ struct EntShared {
     int16_t norm[64];
     uint16_t cumul[64];
     uint8_t tableSymbol[512];
-    uint8_t hdr[192];               // Huffman tree description / NCount headers staging
+    uint8_t hdr[192];               // Huffman tree description staging
+    // the three sequence tables (0 LL, 1 OF, 2 ML) are built concurrently by three threads: private scratch each
+    uint32_t count3[3][64]; int16_t norm3[3][64]; uint16_t cumul3[3][64]; uint8_t tableSymbol3[3][512]; uint8_t hdr3[3][128];
+    uint32_t res3[3][2];            // [k] = {countSize, type}
     uint32_t scanA[kEntThreads / 32], scanB[kEntThreads / 32];
     uint32_t streamBits[4];
     // scalars
@@ -1382,30 +1385,30 @@ __device__ uint32_t fse_write_ncount(uint8_t* out0, const int16_t* norm, uint32_
 }
 
 // FSE_buildCTable_wksp (:13)
-__device__ void fse_build_ctable(FseCTable& ct, EntShared& S, const int16_t* norm, uint32_t maxSymbolValue, uint32_t tableLog)
+__device__ void fse_build_ctable(FseCTable& ct, uint16_t* cumul, uint8_t* tableSymbol, const int16_t* norm, uint32_t maxSymbolValue, uint32_t tableLog)
 {
     uint32_t const tableSize = 1u << tableLog, tableMask = tableSize - 1;
     uint32_t const step = (tableSize >> 1) + (tableSize >> 3) + 3;
     uint32_t const maxSV1 = maxSymbolValue + 1;
     uint32_t highThreshold = tableSize - 1;
     ct.tableLog = tableLog;
-    S.cumul[0] = 0;
+    cumul[0] = 0;
     for (uint32_t u = 1; u <= maxSV1; u++) {
-        if (norm[u - 1] == -1) { S.cumul[u] = (uint16_t)(S.cumul[u - 1] + 1); S.tableSymbol[highThreshold--] = (uint8_t)(u - 1); }
-        else S.cumul[u] = (uint16_t)(S.cumul[u - 1] + (uint16_t)norm[u - 1]);
+        if (norm[u - 1] == -1) { cumul[u] = (uint16_t)(cumul[u - 1] + 1); tableSymbol[highThreshold--] = (uint8_t)(u - 1); }
+        else cumul[u] = (uint16_t)(cumul[u - 1] + (uint16_t)norm[u - 1]);
     }
-    S.cumul[maxSV1] = (uint16_t)(tableSize + 1);
+    cumul[maxSV1] = (uint16_t)(tableSize + 1);
     {   uint32_t position = 0;
         for (uint32_t symbol = 0; symbol < maxSV1; symbol++) {
             int const freq = norm[symbol];
             for (int n = 0; n < freq; n++) {
-                S.tableSymbol[position] = (uint8_t)symbol;
+                tableSymbol[position] = (uint8_t)symbol;
                 position = (position + step) & tableMask;
                 while (position > highThreshold) position = (position + step) & tableMask;
             }
         }
     }
-    for (uint32_t u = 0; u < tableSize; u++) { uint8_t const s = S.tableSymbol[u]; ct.stateTable[S.cumul[s]++] = (uint16_t)(tableSize + u); }
+    for (uint32_t u = 0; u < tableSize; u++) { uint8_t const s = tableSymbol[u]; ct.stateTable[cumul[s]++] = (uint16_t)(tableSize + u); }
     {   uint32_t total = 0;
         for (uint32_t s = 0; s <= maxSymbolValue; s++) {
             int const nc = norm[s];
@@ -1452,7 +1455,7 @@ __device__ uint32_t huf_compress_weights(uint8_t* dst, uint32_t dstSize, EntShar
     if (!fse_normalize_count(S.norm, tableLog, count, wtSize, maxSymbolValue, 0)) return 0xFFFFFFFFu;
     uint32_t const hSize = fse_write_ncount(dst, S.norm, maxSymbolValue, tableLog);
     if (!hSize) return 0xFFFFFFFFu;
-    fse_build_ctable(S.wct, S, S.norm, maxSymbolValue, tableLog);
+    fse_build_ctable(S.wct, S.cumul, S.tableSymbol, S.norm, maxSymbolValue, tableLog);
     // FSE_compress_usingCTable_generic (FseCompress.cs:722), 64-bit variant
     if (wtSize <= 2) return 0;
     if (dstSize - hSize <= 8) return 0;
@@ -1844,63 +1847,64 @@ __global__ void __launch_bounds__(kEntThreads, 8) enc_entropy_kernel(EncPass p)
             uint32_t const strategy = it.strategy;
             uint32_t const seqHead = op; op += 1;
             uint32_t lastCountSize = 0; uint32_t types[3];
-            // three statistics passes, in the reference's order LL, OF, ML (ZSTD_buildSequencesStatistics :3127)
-            for (int k = 0; k < 3; k++) {
-                uint32_t const maxCode = k == 0 ? kMaxLL : (k == 1 ? kMaxOff : kMaxML);
-                for (uint32_t q = tid; q < 64; q += kEntThreads) S.count[q] = 0;
-                __syncthreads();
-                for (uint32_t n = tid; n < nbSeq; n += kEntThreads) {
-                    uint32_t const code = k == 0 ? ll_code(aLL[n]) : (k == 1 ? highbit32(aOF[n]) : ml_code(aML[n]));
-                    atomicAdd(&S.count[code], 1u);
-                }
-                __syncthreads();
-                if (tid == 0) {
-                    uint32_t max = maxCode; while (!S.count[max]) max--;
-                    uint32_t mostFrequent = 0; for (uint32_t s = 0; s <= max; s++) if (S.count[s] > mostFrequent) mostFrequent = S.count[s];
-                    uint32_t const defLog = k == 1 ? kOFDefaultNormLog : kLLDefaultNormLog;
-                    bool const defAllowed = k == 1 ? (max <= (uint32_t)kDefaultMaxOff) : true;
-                    uint32_t const type = select_encoding_type(mostFrequent, nbSeq, defLog, defAllowed, strategy);
-                    uint32_t const lastCode = k == 0 ? ll_code(aLL[nbSeq - 1]) : (k == 1 ? highbit32(aOF[nbSeq - 1]) : ml_code(aML[nbSeq - 1]));
-                    uint32_t countSize = 0;
-                    FseCTable& ct = S.ct[k];
-                    uint8_t* o = dst + op;
-                    if (type == 1) {            // set_rle: FSE_buildCTable_rle (FseCompress.cs:706)
-                        ct.tableLog = 0; ct.stateTable[0] = 0; ct.stateTable[1] = 0; ct.tt[max].deltaNbBits = 0; ct.tt[max].deltaFindState = 0;
-                        // the reference writes codeTable[0], the code of the FIRST sequence (all codes are equal here)
-                        o[0] = (uint8_t)(k == 0 ? ll_code(aLL[0]) : (k == 1 ? highbit32(aOF[0]) : ml_code(aML[0])));
-                        countSize = 1;
-                    } else if (type == 0) {     // set_basic
-                        uint32_t const dmax = k == 0 ? kMaxLL : (k == 1 ? kDefaultMaxOff : kMaxML);
-                        for (uint32_t s = 0; s <= dmax; s++) S.norm[s] = k == 0 ? c_LL_defaultNorm[s] : (k == 1 ? c_OF_defaultNorm[s] : c_ML_defaultNorm[s]);
-                        fse_build_ctable(ct, S, S.norm, dmax, defLog);
-                    } else {                    // set_compressed: ZSTD_buildCTable (ZstdCompressSequences.cs:471)
-                        uint32_t const FSELog = k == 1 ? kOffFSELog : kLLFSELog;
-                        uint32_t nbSeq_1 = nbSeq;
-                        uint32_t const tableLog = fse_optimal_table_log(FSELog, nbSeq, max, 2);
-                        if (S.count[lastCode] > 1) { S.count[lastCode]--; nbSeq_1--; }
-                        fse_normalize_count(S.norm, tableLog, S.count, nbSeq_1, max, nbSeq_1 >= 2048);
-                        countSize = fse_write_ncount(S.hdr, S.norm, max, tableLog);
-                        for (uint32_t q = 0; q < countSize; q++) o[q] = S.hdr[q];
-                        fse_build_ctable(ct, S, S.norm, max, tableLog);
-                        lastCountSize = countSize;
-                    }
-                    S.scanA[0] = countSize; S.scanA[1] = type; S.scanA[2] = lastCountSize;
-                }
-                __syncthreads();
-                op += S.scanA[0]; types[k] = S.scanA[1]; if (S.scanA[1] == 2) lastCountSize = S.scanA[2];
-                __syncthreads();
+            // ZSTD_buildSequencesStatistics (:3127): one pass writes the three symbol codes of every sequence (into the slots
+            // the state chains will overwrite) and counts them; then three threads build the LL / OF / ML tables
+            // concurrently, each with private scratch; thread 0 finally lays the table descriptions out in order.
+            uint64_t* const sb = p.stateBits + (size_t)item * kEncSeqCap;
+            for (uint32_t q = tid; q < 192; q += kEntThreads) (&S.count3[0][0])[q] = 0;
+            __syncthreads();
+            for (uint32_t n = tid; n < nbSeq; n += kEntThreads) {
+                uint32_t const llc = ll_code(aLL[n]), ofc = highbit32(aOF[n]), mlc = ml_code(aML[n]);
+                sb[n] = (uint64_t)llc | ((uint64_t)ofc << 16) | ((uint64_t)mlc << 32);      // u16 slots: [0] LL [1] OF [2] ML
+                atomicAdd(&S.count3[0][llc], 1u); atomicAdd(&S.count3[1][ofc], 1u); atomicAdd(&S.count3[2][mlc], 1u);
             }
+            __syncthreads();
+            if (tid < 96 && (tid & 31) == 0) {
+                int const k = tid >> 5;
+                uint32_t* const count = S.count3[k]; int16_t* const norm = S.norm3[k];
+                const uint16_t* const codes = (const uint16_t*)sb + k;                   // 4 x u16 per sequence
+                uint32_t const maxCode = k == 0 ? kMaxLL : (k == 1 ? kMaxOff : kMaxML);
+                uint32_t max = maxCode; while (!count[max]) max--;
+                uint32_t mostFrequent = 0; for (uint32_t q = 0; q <= max; q++) if (count[q] > mostFrequent) mostFrequent = count[q];
+                uint32_t const defLog = k == 1 ? kOFDefaultNormLog : kLLDefaultNormLog;
+                bool const defAllowed = k == 1 ? (max <= (uint32_t)kDefaultMaxOff) : true;
+                uint32_t const type = select_encoding_type(mostFrequent, nbSeq, defLog, defAllowed, strategy);
+                uint32_t const lastCode = codes[(size_t)(nbSeq - 1) * 4];
+                uint32_t countSize = 0;
+                FseCTable& ct = S.ct[k];
+                if (type == 1) {            // set_rle: FSE_buildCTable_rle (FseCompress.cs:706)
+                    ct.tableLog = 0; ct.stateTable[0] = 0; ct.stateTable[1] = 0; ct.tt[max].deltaNbBits = 0; ct.tt[max].deltaFindState = 0;
+                    S.hdr3[k][0] = (uint8_t)codes[0];   // the reference writes codeTable[0], the code of the FIRST sequence (all codes are equal here)
+                    countSize = 1;
+                } else if (type == 0) {     // set_basic
+                    uint32_t const dmax = k == 0 ? kMaxLL : (k == 1 ? kDefaultMaxOff : kMaxML);
+                    for (uint32_t q = 0; q <= dmax; q++) norm[q] = k == 0 ? c_LL_defaultNorm[q] : (k == 1 ? c_OF_defaultNorm[q] : c_ML_defaultNorm[q]);
+                    fse_build_ctable(ct, S.cumul3[k], S.tableSymbol3[k], norm, dmax, defLog);
+                } else {                    // set_compressed: ZSTD_buildCTable (ZstdCompressSequences.cs:471)
+                    uint32_t const FSELog = k == 1 ? kOffFSELog : kLLFSELog;
+                    uint32_t nbSeq_1 = nbSeq;
+                    uint32_t const tableLog = fse_optimal_table_log(FSELog, nbSeq, max, 2);
+                    if (count[lastCode] > 1) { count[lastCode]--; nbSeq_1--; }
+                    fse_normalize_count(norm, tableLog, count, nbSeq_1, max, nbSeq_1 >= 2048);
+                    countSize = fse_write_ncount(S.hdr3[k], norm, max, tableLog);
+                    fse_build_ctable(ct, S.cumul3[k], S.tableSymbol3[k], norm, max, tableLog);
+                }
+                S.res3[k][0] = countSize; S.res3[k][1] = type;
+            }
+            __syncthreads();
+            for (int k = 0; k < 3; k++) {
+                uint32_t const cs = S.res3[k][0];
+                types[k] = S.res3[k][1];
+                for (uint32_t q = tid; q < cs; q += kEntThreads) dst[op + q] = S.hdr3[k][q];
+                op += cs;
+                if (types[k] == 2) lastCountSize = cs;
+            }
+            __syncthreads();
             if (tid == 0) dst[seqHead] = (uint8_t)((types[0] << 6) + (types[1] << 4) + (types[2] << 2));
             // ---- 4. FSE state chains: three lanes walk the sequences last -> first (ZSTD_encodeSequences_body :585) ----
             // The chain state -> nbBits -> next state is serial; everything else is taken off it: all threads first write
             // the three symbol codes of every sequence into the chain's own output slots, and each chain lane then works
             // in steps of 8 sequences: 8 code loads, 8 symbol-transform loads, 8 dependent state steps.
-            uint64_t* const sb = p.stateBits + (size_t)item * kEncSeqCap;
-            for (uint32_t n = tid; n < nbSeq; n += kEntThreads) {
-                uint32_t const llc = ll_code(aLL[n]), ofc = highbit32(aOF[n]), mlc = ml_code(aML[n]);
-                sb[n] = (uint64_t)llc | ((uint64_t)ofc << 16) | ((uint64_t)mlc << 32);      // u16 slots: [0] LL [1] OF [2] ML
-            }
-            __syncthreads();
             if (tid < 96 && (tid & 31) == 0) {
                 int const k = tid >> 5;    // 0 LL, 1 OF, 2 ML
                 const FseCTable& ct = S.ct[k];
