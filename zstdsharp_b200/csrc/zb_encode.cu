@@ -8,10 +8,15 @@
 //        FSE_buildCTable), ZSTD_encodeSequences                                                     (:3357; HufCompress.cs; FseCompress.cs; ZstdCompressSequences.cs)
 // The output of every chunk is byte-identical to what the reference's Compressor.Wrap produces for that chunk.
 // Kernels:
-//   enc_match_kernel     lane / chunk   exact restatement of the greedy hash-table parse (serial by construction)
-//   enc_entropy_kernel   CTA  / chunk   literal gather + histograms, Huffman/FSE table construction (one thread),
-//                                       parallel bit scatter of the 4 Huffman streams and of the sequence bitstream,
-//                                       block/frame assembly with the reference's accept/reject gates
+//   enc_match_group_kernel<16>        16 lanes / chunk   exact ZSTD_fast parse (levels 1-2), speculative window of 8 reference iterations
+//   enc_match_dfast_group_kernel<16>  16 lanes / chunk   exact ZSTD_dfast parse (level 3), 15 probe positions + 1 look-ahead per window
+//   enc_match_kernel                  lane / chunk       serial restatement, chunks below 64 bytes only
+//   enc_entropy_kernel                CTA  / chunk       literal gather + histograms, Huffman/FSE table construction, FSE state chains,
+//                                                        parallel bit scatter of the 4 Huffman streams and of the sequence bitstream,
+//                                                        block/frame assembly with the reference's accept/reject gates, XXH64 trailer
+//   enc_compact_kernel                CTA  / chunk       packs the frames densely before D2H
+// All hash tables live in HBM/L2 (zeroed per call) and every chunk of a pass is in flight at once: the parse is a chain of
+// dependent memory round trips per sequence, and only concurrency across chunks hides it (profiles/r01_notes.md).
 #include <algorithm>
 #include <cstdio>
 #include <cstdlib>
@@ -58,7 +63,6 @@ static CParams get_cparams(int level, uint64_t srcSize)
 // ------------------------------------------------------------------------------------------------------------
 constexpr uint32_t kEncSeqCap = kBlockSizeMax / 4 + 1;      // maxNbSeq = blockSize / 4 (minMatch != 3), ZstdCompress.cs:2570
 constexpr uint32_t kEncLitStride = kBlockSizeMax + 64;
-constexpr uint32_t kWarpMatchMaxHashLog = 13;             // 2^13 x 4 B = 32 KB of shared memory per chunk
 
 struct __align__(16) EncItem {
     uint64_t srcOff, dstOff;
@@ -296,15 +300,7 @@ _match_stored:
     }
 }
 
-// ------------------------------------------------------------------------------------------------------------
-//  Warp-parallel, exact ZSTD_fast parse: one warp per chunk, hash table (<= 2^13 entries) in shared memory.
-//  The reference loop (ZstdFast.cs:147-230) visits positions ip0, ip0+1, ip0+d, ip0+d+1, ... on a schedule that
-//  depends only on (ip0, step, nextStep) until a match is found.  The warp therefore evaluates a window of 16
-//  iterations (32 hash probes + 16 repcode probes) speculatively: lane 2k / 2k+1 own the positions of iteration k,
-//  a probe sees earlier lanes of the same window through __match_any_sync and older positions through the table,
-//  and the first event in the reference's order (repcode@ip2, hash@ip0, hash@ip1 of the lowest iteration) wins.
-//  Table writes are committed up to that event only, so the table always equals the serial algorithm's table.
-// ------------------------------------------------------------------------------------------------------------
+// ZSTD_hashPtr on 8 loaded bytes (ZstdCompressInternal.cs:340-437)
 __device__ __forceinline__ uint32_t hash_val(uint64_t x, uint32_t hBits, uint32_t mls)
 {
     switch (mls) {
@@ -316,258 +312,14 @@ __device__ __forceinline__ uint32_t hash_val(uint64_t x, uint32_t hBits, uint32_
     }
 }
 
-// common-prefix length of src[a..) and src[b..) (b < a), bounded by `limit`; the whole warp cooperates (ZSTD_count :264)
-__device__ __forceinline__ int warp_count(const uint8_t* src, int a, int b, int limit, uint32_t lane)
-{
-    int total = 0;
-    for (;;) {
-        int const pa = a + total + 4 * (int)lane, pb = b + total + 4 * (int)lane;
-        int const rem = limit - pa;
-        uint32_t n = 0;
-        if (rem >= 4) { uint32_t const diff = rd32(src + pa) ^ rd32(src + pb); n = diff ? (uint32_t)(__ffs((int)diff) - 1) >> 3 : 4u; }
-        else { for (int j = 0; j < rem; j++) { if (src[pa + j] == src[pb + j]) n++; else break; } }
-        uint32_t const notFull = __ballot_sync(0xFFFFFFFFu, n != 4);
-        if (notFull) { int const f = __ffs((int)notFull) - 1; return total + 4 * f + (int)__shfl_sync(0xFFFFFFFFu, n, f); }
-        total += 128;
-    }
-}
-
-__global__ void __launch_bounds__(32) enc_match_warp_kernel(EncPass p, const uint32_t* __restrict__ workList)
-{
-    extern __shared__ uint32_t T[];
-    uint32_t const item = workList[blockIdx.x];
-    uint32_t const lane = threadIdx.x;
-    EncItem& it = p.items[item];
-    uint32_t const hlog = it.hashLog, mls = it.minMatch;
-    int const srcSize = (int)it.srcSize;
-    const uint8_t* const src = p.src + it.srcOff;
-    uint32_t* const oLL = p.seqLL + (size_t)item * kEncSeqCap;
-    uint32_t* const oML = p.seqML + (size_t)item * kEncSeqCap;
-    uint32_t* const oOF = p.seqOF + (size_t)item * kEncSeqCap;
-    for (uint32_t i = lane; i < (1u << hlog); i += 32) T[i] = 0;
-    __syncwarp();
-    int const ilimit = srcSize - 8;
-    int ip0 = 1, anchor = 0;                         // first position is skipped (:129)
-    uint32_t rep1 = 1, rep2 = 0;                     // rep2 = 4 exceeds the history at frame start (:131-145)
-    uint32_t nseq = 0;
-    uint32_t const k = lane >> 1, odd = lane & 1;
-    uint32_t const FULL = 0xFFFFFFFFu;
-    for (;;) {                                       // _start
-        int step = 2, nextStep = ip0 + 128, d = 2;
-        bool matched = false;
-        for (;;) {                                   // one window of 16 iterations
-            int pk, dk, pW, dW, stepW, nextStepW;
-            if (ip0 + d + 16 * step < nextStep) {    // no step change inside the window
-                pk = k == 0 ? ip0 : ip0 + d + ((int)k - 1) * step; dk = k == 0 ? d : step;
-                pW = ip0 + d + 15 * step; dW = step; stepW = step; nextStepW = nextStep;
-            } else {
-                int P = ip0, D = d, S = step, N = nextStep; pk = 0; dk = 0;
-#pragma unroll
-                for (int j = 0; j < 16; j++) { if (j == (int)k) { pk = P; dk = D; } P += D; int const ip2n = P + S; D = S; if (ip2n >= N) { S++; N += 128; } }
-                pW = P; dW = D; stepW = S; nextStepW = N;
-            }
-            bool const vk = pk + dk + 1 < ilimit;    // loop condition ip3 < ilimit for this iteration
-            uint32_t const validMask = __ballot_sync(FULL, vk);
-            if (!(validMask & 1)) break;             // iteration 0 does not run: _cleanup
-            int const q = pk + (int)odd;
-            uint64_t const x = vk ? rd64(src + q) : 0ull;
-            uint32_t const cur4 = (uint32_t)x;
-            bool repHit = false;
-            if (vk && !odd && rep1) { int const r = pk + dk; repHit = rd32(src + r) == rd32(src + r - (int)rep1); }
-            uint32_t const h = hash_val(x, hlog, mls);
-            uint32_t const tv = vk ? T[h] : 0u;
-            uint32_t const peers = __match_any_sync(FULL, vk ? h : (0x80000000u | lane));
-            uint32_t const lower = peers & ((1u << lane) - 1u);
-            int const cl = lower ? 31 - __clz((int)lower) : (int)lane;
-            int const cq = __shfl_sync(FULL, q, cl);
-            int const cand = lower ? cq : (int)tv - 2;                  // table stores position + 2, 0 = empty
-            bool hit = false;
-            if (vk && cand >= 0) hit = rd32(src + cand) == cur4;
-            uint32_t key = 0xFFFFFFFFu;
-            if (hit) key = 3 * k + 1 + odd;
-            if (repHit) key = 3 * k;
-            uint32_t const best = __reduce_min_sync(FULL, key);
-            if (best == 0xFFFFFFFFu) {
-                if (vk && ((peers >> lane) >> 1) == 0) T[h] = (uint32_t)q + 2;   // the latest position of a bucket wins
-                __syncwarp();
-                if (validMask != FULL) break;        // the loop condition failed inside the window: _cleanup
-                ip0 = pW; d = dW; step = stepW; nextStep = nextStepW;
-                continue;
-            }
-            // ---- first event of the window ----
-            uint32_t const ke = best / 3, type = best - 3 * ke;
-            uint32_t const lastLane = 2 * ke + 1;
-            {   uint32_t const peersC = peers & (lastLane == 31 ? FULL : ((2u << lastLane) - 1u));
-                if (vk && lane <= lastLane && ((peersC >> lane) >> 1) == 0) T[h] = (uint32_t)q + 2; }
-            __syncwarp();
-            int const pke = __shfl_sync(FULL, pk, 2 * ke), dke = __shfl_sync(FULL, dk, 2 * ke);
-            uint32_t const evLane = 2 * ke + (type == 2 ? 1u : 0u);
-            int const qe = __shfl_sync(FULL, q, evLane), ce = __shfl_sync(FULL, cand, evLane);
-            int mpos, msrc, mlen, current0; uint32_t offcode;
-            if (type == 0) {                          // repcode at ip2 (:163-178)
-                mpos = pke + dke; msrc = mpos - (int)rep1;
-                int const back = src[mpos - 1] == src[msrc - 1];
-                mpos -= back; msrc -= back; mlen = 4 + back; offcode = 0; current0 = pke;
-            } else {                                  // _offset (:236-247)
-                mpos = qe; msrc = ce; rep2 = rep1; rep1 = (uint32_t)(qe - ce); offcode = rep1 + 2; mlen = 4; current0 = qe;
-                while (mpos > anchor && msrc > 0 && src[mpos - 1] == src[msrc - 1]) { mpos--; msrc--; mlen++; }
-            }
-            mlen += warp_count(src, mpos + mlen, msrc + mlen, srcSize, lane);
-            if (lane == 0) { oLL[nseq] = (uint32_t)(mpos - anchor); oOF[nseq] = offcode + 1; oML[nseq] = (uint32_t)mlen - 3; }
-            nseq++;
-            int const mend = mpos + mlen;
-            if (type == 2 && pke + dke < mend) {      // `if (ip1 < ip0) hashTable[hash1] = ip1` with ip1 = old ip2 (:254-257)
-                int const pp = pke + dke;
-                if (lane == 0) T[hash_val(rd64(src + pp), hlog, mls)] = (uint32_t)pp + 2;
-                __syncwarp();
-            }
-            ip0 = mend; anchor = mend;
-            if (ip0 <= ilimit) {
-                if (lane == 0) {
-                    T[hash_val(rd64(src + current0 + 2), hlog, mls)] = (uint32_t)current0 + 2 + 2;
-                    T[hash_val(rd64(src + ip0 - 2), hlog, mls)] = (uint32_t)(ip0 - 2) + 2;
-                }
-                __syncwarp();
-                while (ip0 <= ilimit && rep2 > 0 && rd32(src + ip0) == rd32(src + ip0 - (int)rep2)) {    // :264-285
-                    int const rlen = warp_count(src, ip0 + 4, ip0 + 4 - (int)rep2, srcSize, lane) + 4;
-                    { uint32_t const t = rep2; rep2 = rep1; rep1 = t; }
-                    if (lane == 0) {
-                        T[hash_val(rd64(src + ip0), hlog, mls)] = (uint32_t)ip0 + 2;
-                        oLL[nseq] = 0; oOF[nseq] = 1; oML[nseq] = (uint32_t)rlen - 3;
-                    }
-                    __syncwarp();
-                    nseq++;
-                    ip0 += rlen; anchor = ip0;
-                }
-            }
-            matched = true;
-            break;
-        }
-        if (!matched) break;
-    }
-    if (lane == 0) { it.nbSeq = nseq; it.lastLL = (uint32_t)(srcSize - anchor); }
-}
-
-// Same warp-per-chunk parse with the table in HBM/L2 instead of shared memory: no 6-chunks-per-SM limit, all chunks in flight.
-__global__ void __launch_bounds__(32) enc_match_warpg_kernel(EncPass p, const uint32_t* __restrict__ workList)
-{
-    uint32_t const item = workList[blockIdx.x];
-    uint32_t const lane = threadIdx.x;
-    EncItem& it = p.items[item];
-    uint32_t const hlog = it.hashLog, mls = it.minMatch;
-    int const srcSize = (int)it.srcSize;
-    const uint8_t* const src = p.src + it.srcOff;
-    uint32_t* const oLL = p.seqLL + (size_t)item * kEncSeqCap;
-    uint32_t* const oML = p.seqML + (size_t)item * kEncSeqCap;
-    uint32_t* const oOF = p.seqOF + (size_t)item * kEncSeqCap;
-    uint32_t* const T = p.tables + it.tableOff;      // zero-initialised, HBM/L2-resident: every chunk of the batch is in flight
-    int const ilimit = srcSize - 8;
-    int ip0 = 1, anchor = 0;                         // first position is skipped (:129)
-    uint32_t rep1 = 1, rep2 = 0;                     // rep2 = 4 exceeds the history at frame start (:131-145)
-    uint32_t nseq = 0;
-    uint32_t const k = lane >> 1, odd = lane & 1;
-    uint32_t const FULL = 0xFFFFFFFFu;
-    for (;;) {                                       // _start
-        int step = 2, nextStep = ip0 + 128, d = 2;
-        bool matched = false;
-        for (;;) {                                   // one window of 16 iterations
-            int pk, dk, pW, dW, stepW, nextStepW;
-            if (ip0 + d + 16 * step < nextStep) {    // no step change inside the window
-                pk = k == 0 ? ip0 : ip0 + d + ((int)k - 1) * step; dk = k == 0 ? d : step;
-                pW = ip0 + d + 15 * step; dW = step; stepW = step; nextStepW = nextStep;
-            } else {
-                int P = ip0, D = d, S = step, N = nextStep; pk = 0; dk = 0;
-#pragma unroll
-                for (int j = 0; j < 16; j++) { if (j == (int)k) { pk = P; dk = D; } P += D; int const ip2n = P + S; D = S; if (ip2n >= N) { S++; N += 128; } }
-                pW = P; dW = D; stepW = S; nextStepW = N;
-            }
-            bool const vk = pk + dk + 1 < ilimit;    // loop condition ip3 < ilimit for this iteration
-            uint32_t const validMask = __ballot_sync(FULL, vk);
-            if (!(validMask & 1)) break;             // iteration 0 does not run: _cleanup
-            int const q = pk + (int)odd;
-            uint64_t const x = vk ? rd64(src + q) : 0ull;
-            uint32_t const cur4 = (uint32_t)x;
-            bool repHit = false;
-            if (vk && !odd && rep1) { int const r = pk + dk; repHit = rd32(src + r) == rd32(src + r - (int)rep1); }
-            uint32_t const h = hash_val(x, hlog, mls);
-            uint32_t const tv = vk ? __ldcg(T + h) : 0u;
-            uint32_t const peers = __match_any_sync(FULL, vk ? h : (0x80000000u | lane));
-            uint32_t const lower = peers & ((1u << lane) - 1u);
-            int const cl = lower ? 31 - __clz((int)lower) : (int)lane;
-            int const cq = __shfl_sync(FULL, q, cl);
-            int const cand = lower ? cq : (int)tv - 2;                  // table stores position + 2, 0 = empty
-            bool hit = false;
-            if (vk && cand >= 0) hit = rd32(src + cand) == cur4;
-            uint32_t key = 0xFFFFFFFFu;
-            if (hit) key = 3 * k + 1 + odd;
-            if (repHit) key = 3 * k;
-            uint32_t const best = __reduce_min_sync(FULL, key);
-            if (best == 0xFFFFFFFFu) {
-                if (vk && ((peers >> lane) >> 1) == 0) T[h] = (uint32_t)q + 2;   // the latest position of a bucket wins
-                __syncwarp();
-                if (validMask != FULL) break;        // the loop condition failed inside the window: _cleanup
-                ip0 = pW; d = dW; step = stepW; nextStep = nextStepW;
-                continue;
-            }
-            // ---- first event of the window ----
-            uint32_t const ke = best / 3, type = best - 3 * ke;
-            uint32_t const lastLane = 2 * ke + 1;
-            {   uint32_t const peersC = peers & (lastLane == 31 ? FULL : ((2u << lastLane) - 1u));
-                if (vk && lane <= lastLane && ((peersC >> lane) >> 1) == 0) T[h] = (uint32_t)q + 2; }
-            __syncwarp();
-            int const pke = __shfl_sync(FULL, pk, 2 * ke), dke = __shfl_sync(FULL, dk, 2 * ke);
-            uint32_t const evLane = 2 * ke + (type == 2 ? 1u : 0u);
-            int const qe = __shfl_sync(FULL, q, evLane), ce = __shfl_sync(FULL, cand, evLane);
-            int mpos, msrc, mlen, current0; uint32_t offcode;
-            if (type == 0) {                          // repcode at ip2 (:163-178)
-                mpos = pke + dke; msrc = mpos - (int)rep1;
-                int const back = src[mpos - 1] == src[msrc - 1];
-                mpos -= back; msrc -= back; mlen = 4 + back; offcode = 0; current0 = pke;
-            } else {                                  // _offset (:236-247)
-                mpos = qe; msrc = ce; rep2 = rep1; rep1 = (uint32_t)(qe - ce); offcode = rep1 + 2; mlen = 4; current0 = qe;
-                while (mpos > anchor && msrc > 0 && src[mpos - 1] == src[msrc - 1]) { mpos--; msrc--; mlen++; }
-            }
-            mlen += warp_count(src, mpos + mlen, msrc + mlen, srcSize, lane);
-            if (lane == 0) { oLL[nseq] = (uint32_t)(mpos - anchor); oOF[nseq] = offcode + 1; oML[nseq] = (uint32_t)mlen - 3; }
-            nseq++;
-            int const mend = mpos + mlen;
-            if (type == 2 && pke + dke < mend) {      // `if (ip1 < ip0) hashTable[hash1] = ip1` with ip1 = old ip2 (:254-257)
-                int const pp = pke + dke;
-                if (lane == 0) T[hash_val(rd64(src + pp), hlog, mls)] = (uint32_t)pp + 2;
-                __syncwarp();
-            }
-            ip0 = mend; anchor = mend;
-            if (ip0 <= ilimit) {
-                if (lane == 0) {
-                    T[hash_val(rd64(src + current0 + 2), hlog, mls)] = (uint32_t)current0 + 2 + 2;
-                    T[hash_val(rd64(src + ip0 - 2), hlog, mls)] = (uint32_t)(ip0 - 2) + 2;
-                }
-                __syncwarp();
-                while (ip0 <= ilimit && rep2 > 0 && rd32(src + ip0) == rd32(src + ip0 - (int)rep2)) {    // :264-285
-                    int const rlen = warp_count(src, ip0 + 4, ip0 + 4 - (int)rep2, srcSize, lane) + 4;
-                    { uint32_t const t = rep2; rep2 = rep1; rep1 = t; }
-                    if (lane == 0) {
-                        T[hash_val(rd64(src + ip0), hlog, mls)] = (uint32_t)ip0 + 2;
-                        oLL[nseq] = 0; oOF[nseq] = 1; oML[nseq] = (uint32_t)rlen - 3;
-                    }
-                    __syncwarp();
-                    nseq++;
-                    ip0 += rlen; anchor = ip0;
-                }
-            }
-            matched = true;
-            break;
-        }
-        if (!matched) break;
-    }
-    if (lane == 0) { it.nbSeq = nseq; it.lastLL = (uint32_t)(srcSize - anchor); }
-}
-
-
 // ------------------------------------------------------------------------------------------------------------
 //  Group-per-chunk, exact ZSTD_fast parse: GS lanes (8 / 16 / 32) own one chunk, a warp carries 32/GS chunks.
-//  Same speculative window as the warp kernel above (lane 2k / 2k+1 = the two probes of reference iteration k, GS/2
-//  iterations per window), but written as a warp-uniform state machine: every group walks through the same phases in
+//  The reference loop (ZstdFast.cs:147-230) visits positions ip0, ip0+1, ip0+d, ip0+d+1, ... on a schedule that depends only
+//  on (ip0, step, nextStep) until a match is found, so a window of GS/2 iterations is evaluated speculatively: lane 2k / 2k+1
+//  own the two probes of iteration k, a probe sees earlier lanes of the window through __match_any_sync and older positions
+//  through the table, the first event in the reference's order (repcode@ip2, hash@ip0, hash@ip1 of the lowest iteration) wins,
+//  and table writes are committed up to that event only -- the table always equals the serial algorithm's table.
+//  The kernel is a warp-uniform state machine: every group walks through the same phases in
 //  every round and a group that has nothing to do in a phase is predicated off, so the groups of a warp share one
 //  instruction stream.  A 32-lane window wastes ~28 of its 32 probes on text (the first event sits within the first few
 //  probes): ncu showed 33 G warp instructions and 120 GB of DRAM reads per GiB; 8 lanes per chunk cut both.
@@ -864,326 +616,7 @@ __global__ void __launch_bounds__(32) enc_match_dfast_group_kernel(EncPass p, co
     if (wi < nWork && l == 0) { it.nbSeq = nseq; it.lastLL = (uint32_t)(srcSize - anchor); }
 }
 
-// ------------------------------------------------------------------------------------------------------------
-//  Lane-per-chunk, exact ZSTD_fast parse with speculative windows: every chunk of the batch is in flight at once
-//  (8192 chunks = 256 warps), hash tables live in HBM/L2, and what bounds the kernel is the chain of dependent
-//  memory round trips per sequence (source words -> table entries -> candidate bytes).  A lane therefore issues the
-//  loads of TWO reference iterations (4 hash probes + 2 repcode probes, ZstdFast.cs:147-230) before it looks at any
-//  result, forwards table writes of earlier probes of the same window to later ones, resolves the first event in the
-//  reference's order and only then commits the table writes up to that event -- the table always equals the
-//  serial algorithm's table.
-// ------------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t lane_count(const uint8_t* src, int a, int b, int limit)   // ZSTD_count (:264) on positions
-{
-    int n = 0;
-    while (a + n + 8 <= limit) {
-        uint64_t const diff = rd64(src + a + n) ^ rd64(src + b + n);
-        if (diff) return (uint32_t)n + (uint32_t)((__ffsll((long long)diff) - 1) >> 3);
-        n += 8;
-    }
-    while (a + n < limit && src[a + n] == src[b + n]) n++;
-    return (uint32_t)n;
-}
-
-// ---- 16-byte register windows -------------------------------------------------------------------------------
-// With one lane per chunk every load instruction touches 32 different cache lines, and it is the number of such
-// lane-loads (L1 wavefronts), not their latency, that bounds the kernel.  All source bytes are therefore fetched
-// as 16-byte "windows" (one or two LDG.128 from the chunk's 16-byte grid) and every 4/8-byte value the parse
-// needs is cut out of registers.
-struct SrcView {
-    const uint4* g;         // chunk bytes on their 16-byte grid (block 0 holds byte 0 of the chunk)
-    uint32_t D;             // offset of byte 0 inside block 0
-    uint32_t lastBlk;       // block that holds the last byte of the chunk (loads never go beyond it)
-};
-struct Win16 { uint64_t lo, hi; };                 // 16 bytes starting at some position, little endian
-__device__ __forceinline__ uint64_t fsr64(uint64_t a, uint64_t b, uint32_t s)   // low 64 bits of (b:a) >> s, s in [0,63]
-{
-    uint32_t const a0 = (uint32_t)a, a1 = (uint32_t)(a >> 32), b0 = (uint32_t)b, b1 = (uint32_t)(b >> 32);
-    uint32_t const w0 = s < 32 ? a0 : a1, w1 = s < 32 ? a1 : b0, w2 = s < 32 ? b0 : b1;
-    return (uint64_t)__funnelshift_r(w0, w1, s) | ((uint64_t)__funnelshift_r(w1, w2, s) << 32);
-}
-// 16 bytes starting at `pos`.  Every global read of the parse goes through cp.async (LDGSTS) into a per-lane
-// shared-memory slot: all the copies of a phase are queued first, one wait covers them, and only then are the values
-// read back -- so the round trips of a phase always overlap, whatever the instruction scheduler does with the
-// code that consumes them (plain loads were serialised by register reuse: profiles/r01_notes.md).
-// Slot s of lane l = smem + s*512 + l*16: a warp-wide 16-byte read of one slot is conflict free.
-__device__ __forceinline__ void stage16(uint32_t sdst, const void* g, bool pred)     // predicated off: zero fill, no global access
-{ asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(sdst), "l"(g), "r"(pred ? 16 : 0)); }
-__device__ __forceinline__ void stage4(uint32_t sdst, const void* g, bool pred)
-{ asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(sdst), "l"(g), "r"(pred ? 4 : 0)); }
-__device__ __forceinline__ void stage_wait() { asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory"); }
-__device__ __forceinline__ uint4 lds128(uint32_t sa) { uint4 v; asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(sa)); return v; }
-// queue the two blocks that hold [pos, pos+16); returns the offset of pos inside the first block
-__device__ __forceinline__ uint32_t stage_win(const SrcView& v, uint32_t slot, int pos, bool pred)
-{
-    uint32_t const P = pred ? (uint32_t)pos + v.D : v.D, blk = P >> 4, o = P & 15;
-    stage16(slot, v.g + blk, pred);
-    stage16(slot + 512, v.g + min(blk + 1, v.lastBlk), pred && o);
-    return o;
-}
-__device__ __forceinline__ Win16 take_win2(uint32_t slotA, uint32_t slotB, uint32_t o);
-__device__ __forceinline__ Win16 take_win(uint32_t slot, uint32_t o) { return take_win2(slot, slot + 512, o); }
-__device__ __forceinline__ Win16 take_win2(uint32_t slotA, uint32_t slotB, uint32_t o)
-{
-    uint4 const a = lds128(slotA), b = lds128(slotB);
-    uint64_t const q0 = (uint64_t)a.x | ((uint64_t)a.y << 32), q1 = (uint64_t)a.z | ((uint64_t)a.w << 32);
-    uint64_t const q2 = (uint64_t)b.x | ((uint64_t)b.y << 32), q3 = (uint64_t)b.z | ((uint64_t)b.w << 32);
-    bool const j = o >= 8; uint32_t const sft = (o & 7) * 8;
-    Win16 r;
-    r.lo = fsr64(j ? q1 : q0, j ? q2 : q1, sft);
-    r.hi = fsr64(j ? q2 : q1, j ? q3 : q2, sft);
-    return r;
-}
-constexpr uint32_t kMatchSlots = 32;             // 16 KB of shared memory per warp: 24 staging slots + an 8-block source ring
-constexpr uint32_t kRingSlot0 = 24, kRingBlocks = 8;
-// 8 bytes at byte offset k (0..8) of a window
-__device__ __forceinline__ uint64_t win64(const Win16& w, uint32_t k) { return k >= 8 ? w.hi : fsr64(w.lo, w.hi, k * 8); }
-// 4 bytes at byte offset k (0..12) of a window
-__device__ __forceinline__ uint32_t win32(const Win16& w, uint32_t k)
-{
-    uint32_t const w0 = (uint32_t)w.lo, w1 = (uint32_t)(w.lo >> 32), w2 = (uint32_t)w.hi, w3 = (uint32_t)(w.hi >> 32);
-    uint32_t const j = k >> 2;
-    uint32_t const a = j == 0 ? w0 : (j == 1 ? w1 : (j == 2 ? w2 : w3)), b = j == 0 ? w1 : (j == 1 ? w2 : w3);
-    return __funnelshift_r(a, b, (k & 3) * 8);
-}
-// the window moved down by k bytes (0..16), zero filled at the top
-__device__ __forceinline__ Win16 win_from(const Win16& w, uint32_t k)
-{
-    Win16 r;
-    if (k >= 8) { r.lo = k >= 16 ? 0ull : w.hi >> ((k - 8) * 8); r.hi = 0; }
-    else { r.lo = fsr64(w.lo, w.hi, k * 8); r.hi = w.hi >> (k * 8); }
-    return r;
-}
-// number of equal leading bytes (0..n) of window a from byte ka and window b from byte kb; n <= 16 - max(ka, kb)
-__device__ __forceinline__ uint32_t win_common(const Win16& a, uint32_t ka, const Win16& b, uint32_t kb, uint32_t n)
-{
-    Win16 const x = win_from(a, ka), y = win_from(b, kb);
-    uint64_t const d0 = x.lo ^ y.lo, d1 = x.hi ^ y.hi;
-    uint32_t c = d0 ? (uint32_t)(__ffsll((long long)d0) - 1) >> 3 : 8u;
-    if (c == 8) c += d1 ? (uint32_t)(__ffsll((long long)d1) - 1) >> 3 : 8u;
-    return min(c, n);
-}
-
-__global__ void __launch_bounds__(32) enc_match_fast_kernel(EncPass p, const uint32_t* __restrict__ workList, uint32_t nWork)
-{
-    // Warp-uniform state machine: all 32 lanes (32 chunks) walk through the same phases in every iteration, so that the
-    // loads of a phase are issued together and their latencies overlap across lanes; a lane whose state does not
-    // need a phase is predicated off.  Left to diverge, the lanes' dependent-load chains execute one after another.
-    uint32_t const FULL = 0xFFFFFFFFu;
-    uint32_t const w = blockIdx.x * blockDim.x + threadIdx.x;
-    bool active = w < nWork;
-    uint32_t const item = active ? workList[w] : 0u;
-    EncItem& it = p.items[item];
-    uint32_t const hlog = it.hashLog, mls = it.minMatch;
-    int const srcSize = active ? (int)it.srcSize : 64;
-    const uint8_t* __restrict__ const src = p.src + it.srcOff;
-    SrcView V;
-    V.D = (uint32_t)((uintptr_t)src & 15);
-    V.g = (const uint4*)(src - V.D);
-    V.lastBlk = ((uint32_t)srcSize - 1 + V.D) >> 4;
-    uint32_t* __restrict__ const T = p.tables + it.tableOff;
-    uint32_t* __restrict__ const oLL = p.seqLL + (size_t)item * kEncSeqCap;
-    uint32_t* __restrict__ const oML = p.seqML + (size_t)item * kEncSeqCap;
-    uint32_t* __restrict__ const oOF = p.seqOF + (size_t)item * kEncSeqCap;
-    int const ilimit = srcSize - 8;
-    int ip0 = 1, anchor = 0;                         // first position is skipped (:129)
-    uint32_t rep1 = 1, rep2 = 0;                     // rep2 = 4 exceeds the history at frame start (:131-145)
-    uint32_t nseq = 0;
-    int step = 2, nextStep = ip0 + 128, d = 2;       // _start
-    bool afterMatch = false;                         // the greedy rep2 loop (:264-285) is still open at ip0
-    Win16 X; X.lo = 0; X.hi = 0; int xPos = -1000; uint32_t xLen = 16;   // carried source window: xLen valid bytes at xPos
-    uint32_t ringStart = 0, ringHi = 0, ringOk = 0;   // source ring: blocks [ringStart, ringHi) were queued, those below ringOk have landed
-    __shared__ __align__(16) uint8_t s_slots[kMatchSlots * 512];
-    uint32_t const S0 = (uint32_t)__cvta_generic_to_shared(s_slots) + (threadIdx.x & 31) * 16;   // slot k of this lane = S0 + k*512
-    auto slot = [&](uint32_t k) { return S0 + k * 512; };
-    while (__any_sync(FULL, active)) {
-        // ---- schedule of the two speculative iterations ----
-        int const pA = ip0, dA = d;
-        bool const vA = active && (pA + dA + 1 < ilimit);       // loop condition ip3 < ilimit
-        int const pB = pA + dA;
-        int S = step, N = nextStep;
-        int const dB = S;
-        if (pB + S >= N) { S++; N += 128; }
-        bool const vB = vA && (pB + dB + 1 < ilimit);
-        int const pC = pB + dB;                                  // ip0 after the second iteration
-        int S2 = S, N2 = N;
-        int const dC = S2;
-        if (pC + S2 >= N2) { S2++; N2 += 128; }
-        bool const r2 = active && afterMatch && ip0 <= ilimit && rep2 > 0;
-        bool const pr = vA && rep1 != 0, prB = vB && rep1 != 0;
-        // ---- source ring: the 16-byte blocks ahead of the scan front are queued here without waiting (they land at the next
-        // wait of this lane); a window that the ring already holds costs no round trip ----
-        uint32_t const bA = ((uint32_t)pA + V.D) >> 4;                                       // block of ip0
-        if (active) {
-            if (bA >= ringHi) { ringStart = bA; ringHi = bA; ringOk = bA; }                   // the front ran past the ring: restart it
-            uint32_t const want = min(((uint32_t)pA + V.D + 112) >> 4, V.lastBlk + 1);        // keep ~100 bytes ahead staged
-#pragma unroll
-            for (int q = 0; q < 3; q++) {
-                bool const go = ringHi < want && ringHi < bA + kRingBlocks;                   // never overwrite the block of ip0
-                stage16(slot(kRingSlot0 + (ringHi & (kRingBlocks - 1))), V.g + min(ringHi, V.lastBlk), go);
-                if (go) ringHi++;
-            }
-        }
-        auto ring_has = [&](int pos) {          // all 16 bytes at pos lie in blocks that have landed and are still in the ring
-            uint32_t const P = (uint32_t)pos + V.D, b0 = P >> 4, b1 = (P + 15) >> 4;
-            return b0 >= ringStart && b0 + kRingBlocks >= ringHi && b1 < ringOk;
-        };
-        auto ring_take = [&](int pos) {
-            uint32_t const P = (uint32_t)pos + V.D, b0 = P >> 4;
-            return take_win2(slot(kRingSlot0 + (b0 & (kRingBlocks - 1))), slot(kRingSlot0 + ((b0 + 1) & (kRingBlocks - 1))), P & 15);
-        };
-        // ---- round trip 1: source window at ip0 (skipped when the previous iteration left it behind or the ring holds it) ----
-        if ((vA || r2) && xPos != pA && ring_has(pA)) { X = ring_take(pA); xPos = pA; xLen = 16; }
-        bool const needX = (vA || r2) && xPos != pA;
-        if (__any_sync(FULL, needX)) {
-            uint32_t const o = stage_win(V, slot(0), pA, needX);
-            stage_wait();
-            Win16 const nx = take_win(slot(0), o);
-            if (needX) { X = nx; xPos = pA; xLen = 16; }
-        }
-        // the window covers ip0, ip0+1, ip2, ip2+1 and the repcode probe of the second iteration for steps <= 5
-        bool const wide = vA && (dA + 9 > 16 || (vB && dA + dB + 4 > 16));
-        Win16 XB = X, XC = X; uint32_t kB = (uint32_t)dA, kC = (uint32_t)(dA + dB);
-        if (__any_sync(FULL, wide)) {                              // long literal runs only
-            uint32_t const ob = stage_win(V, slot(0), pB, wide), oc = stage_win(V, slot(2), pC, wide && vB);
-            stage_wait();
-            Win16 const nb = take_win(slot(0), ob), nc = take_win(slot(2), oc);
-            if (wide) { XB = nb; XC = nc; kB = 0; kC = 0; }
-        }
-        uint64_t const x0 = X.lo, x1 = win64(X, 1), x2 = win64(XB, kB), x3 = win64(XB, kB + 1);
-        uint32_t const h0 = hash_val(x0, hlog, mls), h1 = hash_val(x1, hlog, mls), h2 = hash_val(x2, hlog, mls), h3 = hash_val(x3, hlog, mls);
-        // ---- round trip 2: table entries (position + 2, 0 = empty), repcode sources ----
-        bool const farB = prB && dB + 4 > 16;
-        uint32_t const oRA = stage_win(V, slot(0), pB - (int)rep1, pr), oQ = stage_win(V, slot(2), pA - (int)rep2, r2);
-        uint32_t const oRB = stage_win(V, slot(4), pC - (int)rep1, farB);
-        stage4(slot(6), T + h0, vA); stage4(slot(6) + 4, T + h1, vA); stage4(slot(6) + 8, T + h2, vB); stage4(slot(6) + 12, T + h3, vB);
-        stage_wait();
-        ringOk = ringHi;                                            // everything queued so far has landed
-        uint4 const tv = lds128(slot(6));
-        uint32_t const t0 = tv.x, t1 = tv.y, t2 = tv.z, t3 = tv.w;
-        Win16 const RA = take_win(slot(0), oRA);                   // 16 bytes at ip2 - rep1 (the second probe sits dB bytes further)
-        Win16 RB = RA; uint32_t kRB = (uint32_t)dB;
-        if (farB) { RB = take_win(slot(4), oRB); kRB = 0; }
-        Win16 const Q = take_win(slot(2), oQ);                     // rep2 probe (:264)
-        // a probe sees the writes of the earlier probes of this window
-        uint32_t const c0 = t0;
-        uint32_t const c1 = h1 == h0 ? (uint32_t)pA + 2 : t1;
-        uint32_t const c2 = h2 == h1 ? (uint32_t)pA + 3 : (h2 == h0 ? (uint32_t)pA + 2 : t2);
-        uint32_t const c3 = h3 == h2 ? (uint32_t)pB + 2 : (h3 == h1 ? (uint32_t)pA + 3 : (h3 == h0 ? (uint32_t)pA + 2 : t3));
-        // ---- round trip 3: candidate bytes ----
-        bool const k0 = vA && c0, k1 = vA && c1, k2 = vB && c2, k3 = vB && c3;
-        uint32_t const o0 = stage_win(V, slot(8), (int)c0 - 2, k0), o1 = stage_win(V, slot(10), (int)c1 - 2, k1);
-        uint32_t const o2 = stage_win(V, slot(12), (int)c2 - 2, k2), o3 = stage_win(V, slot(14), (int)c3 - 2, k3);
-        stage_wait();
-        Win16 const C0 = take_win(slot(8), o0), C1 = take_win(slot(10), o1), C2 = take_win(slot(12), o2), C3 = take_win(slot(14), o3);
-        // ---- first event in the reference's order: open rep2 loop first, then the window ----
-        // type 3: rep2 match at ip0 (:264-285); 0: repcode at ip2; 1 / 2: hash match at ip0 / ip1; -1: none
-        int type = -1, pke = pA, dke = dA, cand = 0;
-        Win16 MW = Q;                  // window at the match source
-        Win16 SW = X; uint32_t kS = 0, lenS = xLen; // window that holds the match position, its byte offset inside, its valid bytes
-        uint32_t const lenB = wide ? 16u : xLen;    // valid bytes of XB / XC
-        if (r2 && (uint32_t)Q.lo == (uint32_t)x0) type = 3;
-        else if (vA) {
-            if (pr && (uint32_t)x2 == (uint32_t)RA.lo) { type = 0; MW = RA; SW = XB; kS = kB; lenS = lenB; }
-            else if (k0 && (uint32_t)C0.lo == (uint32_t)x0) { type = 1; cand = (int)c0 - 2; MW = C0; }
-            else if (k1 && (uint32_t)C1.lo == (uint32_t)x1) { type = 2; cand = (int)c1 - 2; MW = C1; kS = 1; }
-            else if (vB) {
-                pke = pB; dke = dB;
-                if (prB && win32(XC, kC) == win32(RB, kRB)) { type = 0; MW = RB; SW = XC; kS = kC; lenS = lenB; }
-                else if (k2 && (uint32_t)C2.lo == (uint32_t)x2) { type = 1; cand = (int)c2 - 2; MW = C2; SW = XB; kS = kB; lenS = lenB; }
-                else if (k3 && (uint32_t)C3.lo == (uint32_t)x3) { type = 2; cand = (int)c3 - 2; MW = C3; SW = XB; kS = kB + 1; lenS = lenB; }
-            }
-        }
-        uint32_t const kM = (type == 0 && pke == pB) ? kRB : 0u;   // byte offset of the match source inside MW
-        if (active && type != 3) afterMatch = false;             // the rep2 loop is closed: this iteration ran from _start
-        // ---- table writes that precede the event (`ip1 < ip0` insert of types 0/1 included, :254-257) ----
-        if (vA && type != 3) {
-            T[h0] = (uint32_t)pA + 2; T[h1] = (uint32_t)pA + 3;
-            if (vB && (type < 0 || pke == pB)) { T[h2] = (uint32_t)pB + 2; T[h3] = (uint32_t)pB + 3; }
-        }
-        if (type == 3) T[h0] = (uint32_t)pA + 2;                 // the rep2 loop inserts ip0 before advancing (:278)
-        // ---- match geometry ----
-        int mpos = 0, msrc = 0, mlen = 0, current0 = 0; uint32_t offcode = 0;
-        bool const ev = type >= 0;
-        if (type == 3) { mpos = pA; msrc = pA - (int)rep2; uint32_t const t = rep2; rep2 = rep1; rep1 = t; }
-        else if (type == 0) { mpos = pke + dke; msrc = mpos - (int)rep1; current0 = pke; }
-        else if (type > 0) { int const qe = pke + (type == 2 ? 1 : 0); mpos = qe; msrc = cand; rep2 = rep1; rep1 = (uint32_t)(qe - cand); offcode = rep1 + 2; current0 = qe; }
-        // forward extension (ZSTD_count :264): first from the windows already in registers, then 16 bytes per round
-        {
-            uint32_t const avail = min(lenS - kS, 16u - kM);       // bytes both windows hold from the match start
-            uint32_t const room = ev ? (uint32_t)(srcSize - mpos) : 0u;
-            uint32_t const n = min(avail, room);
-            uint32_t const c = ev ? win_common(SW, kS, MW, kM, n) : 0u;   // >= 4 by construction of the event
-            mlen = (int)c;
-            bool cnt = ev && c == n && (uint32_t)c < room;
-            while (__any_sync(FULL, cnt)) {
-                int const a = mpos + mlen, b = msrc + mlen;
-                uint32_t const oa = stage_win(V, slot(16), a, cnt), ob = stage_win(V, slot(18), b, cnt);
-                stage_wait();
-                Win16 const wa = take_win(slot(16), oa), wb = take_win(slot(18), ob);
-                if (cnt) {
-                    uint32_t const r = (uint32_t)(srcSize - a), nn = min(16u, r);
-                    uint32_t const cc = win_common(wa, 0, wb, 0, nn);
-                    mlen += (int)cc;
-                    cnt = cc == nn && nn < r;
-                }
-            }
-        }
-        // backward extension: one byte without anchor test for the repcode (:171), as far as it goes for hash matches (:236-247)
-        {
-            uint32_t const bA = type == 0 ? src[mpos - 1] : 0u, bB = type == 0 ? src[msrc - 1] : 1u;
-            if (type == 0) { int const back = bA == bB; mpos -= back; msrc -= back; mlen += back; }
-            bool ext = (type == 1 || type == 2) && mpos > anchor && msrc > 0;
-            while (__any_sync(FULL, ext)) {
-                uint32_t const a = ext ? src[mpos - 1] : 0u, b = ext ? src[msrc - 1] : 1u;
-                if (ext && a == b) { mpos--; msrc--; mlen++; ext = mpos > anchor && msrc > 0; } else ext = false;
-            }
-        }
-        // ---- sequence, post-match inserts (:251-263), state for the next iteration ----
-        int const mend = mpos + mlen;
-        bool const ins = ev && type != 3 && mend <= ilimit;
-        // the window at mend-2 serves the insert of ip0-2 and is the source window of the next iteration (ip0 = mend)
-        bool const wantNW = ev && mend <= ilimit;
-        bool const ringNW = wantNW && ring_has(mend - 2);
-        Win16 NW;
-        if (__any_sync(FULL, wantNW && !ringNW)) {
-            uint32_t const oNW = stage_win(V, slot(20), mend - 2, wantNW && !ringNW);
-            stage_wait();
-            NW = take_win(slot(20), oNW);
-        }
-        if (ringNW) NW = ring_take(mend - 2);
-        if (ev) {
-            oLL[nseq] = (uint32_t)(mpos - anchor); oOF[nseq] = offcode + 1; oML[nseq] = (uint32_t)mlen - 3;
-            nseq++;
-            if (type == 2 && pke + dke < mend) {      // `if (ip1 < ip0) hashTable[hash1] = ip1` with ip1 = old ip2
-                uint64_t xp;                                           // 8 bytes at ip2 of the event's iteration
-                if (pke == pA) xp = x2;
-                else if (kC + 8 <= lenB) xp = win_from(XC, kC).lo;
-                else xp = rd64(src + pke + dke);
-                T[hash_val(xp, hlog, mls)] = (uint32_t)(pke + dke) + 2;
-            }
-            if (ins) {
-                // 8 bytes at current0 + 2: inside the window of the event's iteration
-                bool const inB = pke == pB && wide;                    // otherwise everything sits in X
-                uint32_t const off2 = (uint32_t)(current0 + 2 - (inB ? pB : pA));
-                uint64_t xc;
-                if (off2 + 8 <= (inB ? 16u : xLen)) xc = win_from(inB ? XB : X, off2).lo;
-                else xc = rd64(src + current0 + 2);
-                T[hash_val(xc, hlog, mls)] = (uint32_t)current0 + 2 + 2;
-                T[hash_val(NW.lo, hlog, mls)] = (uint32_t)(mend - 2) + 2;
-            }
-            ip0 = mend; anchor = mend;
-            if (mend <= ilimit) { X = win_from(NW, 2); xPos = mend; xLen = 14; }   // 14 valid bytes: enough for a step-2 window
-            afterMatch = true;                        // the rep2 loop test runs first in the next iteration
-            step = 2; nextStep = ip0 + 128; d = 2;    // _start
-        } else if (active) {
-            if (!vB) active = false;                  // the loop condition failed in the first or second iteration: _cleanup
-            else { ip0 = pC; d = dC; step = S2; nextStep = N2; }
-        }
-    }
-    if (w < nWork) { it.nbSeq = nseq; it.lastLL = (uint32_t)(srcSize - anchor); }
-}
-
+// Serial restatement (one lane per chunk): used for chunks below 64 bytes only; everything else goes to the group kernels.
 __global__ void __launch_bounds__(32) enc_match_kernel(EncPass p, const uint32_t* __restrict__ workList, uint32_t nWork)
 {
     uint32_t const w = blockIdx.x * blockDim.x + threadIdx.x;
@@ -2063,15 +1496,6 @@ const uint8_t* EncArena::compactBuf() const { return impl ? (const uint8_t*)impl
 
 constexpr size_t kEncMaxItemsPerPass = 8192;
 
-static void enc_set_attrs()
-{
-    static bool done[64] = {};
-    int dev = 0; cudaGetDevice(&dev);
-    if (dev < 0 || dev >= 64 || done[dev]) return;
-    cudaFuncSetAttribute(enc_match_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (1u << kWarpMatchMaxHashLog) * 4);
-    done[dev] = true;
-}
-
 bool enc_compress_device(EncArena& A, cudaStream_t stream, cudaEvent_t* ev, size_t n, int level, int checksumFlag,
                          const uint8_t* d_src, const uint64_t* srcOff, const size_t* srcSize,
                          uint8_t* d_dst, const uint64_t* dstOff, const size_t* dstCap, size_t* result,
@@ -2083,12 +1507,10 @@ bool enc_compress_device(EncArena& A, cudaStream_t stream, cudaEvent_t* ev, size
     for (size_t base = 0; base < n; base += kEncMaxItemsPerPass) {
         size_t const m = std::min(kEncMaxItemsPerPass, n - base);
         if (!I.hItems.ensure(m * sizeof(EncItem)) || !I.items.ensure(m * sizeof(EncItem)) || !I.results.ensure(m * 8) || !I.hResults.ensure(m * 8)) { t_encErr = "out of memory (items)"; return false; }
-        if (!I.hWork.ensure(m * 16) || !I.workLists.ensure(m * 16)) { t_encErr = "out of memory (work lists)"; return false; }
+        if (!I.hWork.ensure(m * 12) || !I.workLists.ensure(m * 12)) { t_encErr = "out of memory (work lists)"; return false; }
         EncItem* hi = (EncItem*)I.hItems.p;
-        uint32_t* const warpList = (uint32_t*)I.hWork.p; uint32_t* const serialList = warpList + m; uint32_t* const fastList = serialList + m; uint32_t* const dfastList = fastList + m;
-        uint32_t nWarp = 0, nSerial = 0, nFast = 0, nDfast = 0;
-        static bool const useWarp = getenv("ZSTDB200_ENC_WARP") != nullptr;    // A/B switch: warp-per-chunk kernel with shared-memory tables
-        static bool const useWarpG = getenv("ZSTDB200_ENC_LANE") == nullptr;   // default: warp-per-chunk kernel with HBM tables; ZSTDB200_ENC_LANE=1 selects the lane-per-chunk state machine
+        uint32_t* const fastList = (uint32_t*)I.hWork.p; uint32_t* const serialList = fastList + m; uint32_t* const dfastList = serialList + m;
+        uint32_t nFast = 0, nSerial = 0, nDfast = 0;
         size_t tableEntries = 0;
         for (size_t i = 0; i < m; i++) {
             size_t const ss = srcSize[base + i];
@@ -2100,12 +1522,9 @@ bool enc_compress_device(EncArena& A, cudaStream_t stream, cudaEvent_t* ev, size
             e.windowLog = c.windowLog; e.hashLog = c.hashLog; e.chainLog = c.chainLog; e.minMatch = c.minMatch; e.strategy = c.strategy;
             e.nbSeq = 0; e.lastLL = e.srcSize;
             if (ss < 7 || ss > kBlockSizeMax) continue;              // raw block / unsupported: no match finding
-            // ZSTD_fast with a table that fits shared memory -> warp-parallel kernel; everything else (level-2 2^15 tables,
-            // dfast's two tables) keeps its tables in HBM/L2 and is parsed by the lane-serial kernel
-            if (useWarp && c.strategy == 1 && c.hashLog <= kWarpMatchMaxHashLog && ss >= 64) { warpList[nWarp++] = (uint32_t)i; continue; }
-            if (useWarpG && c.strategy == 2 && ss >= 64) { dfastList[nDfast++] = (uint32_t)i; }
-            else if (useWarpG && c.strategy == 1 && ss >= 64) { warpList[nWarp++] = (uint32_t)i; }
-            else if (c.strategy == 1 && ss >= 64) { fastList[nFast++] = (uint32_t)i; }
+            // group kernels (16 lanes per chunk) for ZSTD_fast and ZSTD_dfast; chunks below 64 bytes take the serial lane kernel
+            if (ss >= 64 && c.strategy == 1) fastList[nFast++] = (uint32_t)i;
+            else if (ss >= 64 && c.strategy == 2) dfastList[nDfast++] = (uint32_t)i;
             else serialList[nSerial++] = (uint32_t)i;
             e.tableOff = (uint32_t)tableEntries;
             tableEntries += ((size_t)1 << c.hashLog) + (c.strategy == 2 ? ((size_t)1 << c.chainLog) : 0);
@@ -2115,26 +1534,20 @@ bool enc_compress_device(EncArena& A, cudaStream_t stream, cudaEvent_t* ev, size
             !I.seqOF.ensure(m * (size_t)kEncSeqCap * 4) || !I.lit.ensure(m * (size_t)kEncLitStride) || !I.stateBits.ensure(m * (size_t)kEncSeqCap * 8)) { t_encErr = "out of memory (arena)"; return false; }
         ENC_CUDA(cudaMemcpyAsync(I.items.p, hi, m * sizeof(EncItem), cudaMemcpyHostToDevice, stream));
         ENC_CUDA(cudaEventRecord(ev[14], stream));
-        ENC_CUDA(cudaMemcpyAsync(I.workLists.p, I.hWork.p, m * 16, cudaMemcpyHostToDevice, stream));
+        ENC_CUDA(cudaMemcpyAsync(I.workLists.p, I.hWork.p, m * 12, cudaMemcpyHostToDevice, stream));
         if (tableEntries) ENC_CUDA(cudaMemsetAsync(I.tables.p, 0, tableEntries * 4, stream));      // tables are zeroed per frame (ZstdCompress.cs:2472,2481)
         EncPass p;
         p.items = (EncItem*)I.items.p; p.nItems = (uint32_t)m; p.src = d_src; p.dst = d_dst; p.tables = (uint32_t*)I.tables.p;
         p.seqLL = (uint32_t*)I.seqLL.p; p.seqML = (uint32_t*)I.seqML.p; p.seqOF = (uint32_t*)I.seqOF.p; p.litBuf = (uint8_t*)I.lit.p;
         p.stateBits = (uint64_t*)I.stateBits.p; p.results = (uint64_t*)I.results.p; p.checksumFlag = checksumFlag ? 1u : 0u;
-        enc_set_attrs();
-        static int const groupLanes = getenv("ZSTDB200_ENC_GROUP") ? atoi(getenv("ZSTDB200_ENC_GROUP")) : 16;   // lanes per chunk: 16 measured best (8: 49/52 ms, 16: 42/49 ms, 32: 63/72 ms Silesia-mix/text); 0 = one-chunk warp kernel
-        if (nWarp && useWarpG && groupLanes == 8) enc_match_group_kernel<8><<<(nWarp + 3) / 4, 32, 0, stream>>>(p, (const uint32_t*)I.workLists.p, nWarp);
-        else if (nWarp && useWarpG && groupLanes == 16) enc_match_group_kernel<16><<<(nWarp + 1) / 2, 32, 0, stream>>>(p, (const uint32_t*)I.workLists.p, nWarp);
-        else if (nWarp && useWarpG && groupLanes == 32) enc_match_group_kernel<32><<<nWarp, 32, 0, stream>>>(p, (const uint32_t*)I.workLists.p, nWarp);
-        else if (nWarp && useWarpG) enc_match_warpg_kernel<<<nWarp, 32, 0, stream>>>(p, (const uint32_t*)I.workLists.p);
-        else if (nWarp) enc_match_warp_kernel<<<nWarp, 32, (1u << kWarpMatchMaxHashLog) * 4, stream>>>(p, (const uint32_t*)I.workLists.p);
+        // lanes per chunk: 16 measured best for ZSTD_fast (8: 49/52 ms, 16: 42/49 ms, 32: 63/72 ms per GiB Silesia-mix / text)
+        if (nFast) enc_match_group_kernel<16><<<(nFast + 1) / 2, 32, 0, stream>>>(p, (const uint32_t*)I.workLists.p, nFast);
         if (nSerial) enc_match_kernel<<<(nSerial + 31) / 32, 32, 0, stream>>>(p, (const uint32_t*)I.workLists.p + m, nSerial);
-        if (nFast) enc_match_fast_kernel<<<(nFast + 31) / 32, 32, 0, stream>>>(p, (const uint32_t*)I.workLists.p + 2 * m, nFast);
-        if (nDfast) enc_match_dfast_group_kernel<16><<<(nDfast + 1) / 2, 32, 0, stream>>>(p, (const uint32_t*)I.workLists.p + 3 * m, nDfast);
+        if (nDfast) enc_match_dfast_group_kernel<16><<<(nDfast + 1) / 2, 32, 0, stream>>>(p, (const uint32_t*)I.workLists.p + 2 * m, nDfast);
         ENC_CUDA(cudaEventRecord(ev[15], stream));
         enc_entropy_kernel<<<(unsigned)m, kEntThreads, 0, stream>>>(p);
         ENC_CUDA(cudaEventRecord(ev[16], stream));
-        *launches += 1 + (nWarp ? 1 : 0) + (nSerial ? 1 : 0) + (nFast ? 1 : 0) + (nDfast ? 1 : 0) + (tableEntries ? 1 : 0);
+        *launches += 1 + (nSerial ? 1 : 0) + (nFast ? 1 : 0) + (nDfast ? 1 : 0) + (tableEntries ? 1 : 0);
         ENC_CUDA(cudaMemcpyAsync(I.hResults.p, I.results.p, m * 8, cudaMemcpyDeviceToHost, stream));
         ENC_CUDA(cudaStreamSynchronize(stream));
         ENC_CUDA(cudaGetLastError());
