@@ -425,6 +425,13 @@ def run_b200(args):
             dev_call(lib.ZSTDB200_compressBatch, comp, n, 1, csp, css, cdp, cdc, cres)
             return comp.launch_count(), np.array(comp.timings())
         _, ce_wall_ms, _, _ = timed_steps(e2e_comp_step, 1, 2)
+        # the host-pointer path must hand back exactly the frames of the device-resident pass
+        e2e_sizes = np.array(list(cres), dtype=np.int64)
+        assert np.array_equal(e2e_sizes, csizes), "host-pointer compress sizes differ from the device-resident pass"
+        dcheck = d_cout.cpu().numpy()
+        hcheck = h_cout.numpy()
+        for i in range(0, n, max(1, n // 97)):
+            assert np.array_equal(hcheck[i * slot:i * slot + csizes[i]], dcheck[i * slot:i * slot + csizes[i]]), "host-pointer compress bytes differ"
         compress["e2e"] = {"value": round(total_u * 2 / (ce_wall_ms * 1e-3) / 1e9, 3), "unit": "GB/s",
                            "h2d_bytes_per_step": int(total_u), "d2h_bytes_per_step": int(c_total_c)}
         del h_in, h_cout

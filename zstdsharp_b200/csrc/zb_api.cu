@@ -106,7 +106,8 @@ struct Engine {
     // host<->device staging for the host-pointer API
     DevBuf dSrc, dDst; PinBuf hStage, hStageOut;
     // encode arena
-    EncArena enc;
+    EncArena enc;                       // device-pointer API and small host batches
+    EncArena encPipe[kPipeMax];         // one per sub-batch in flight in the pipelined host path
     DevBuf dEncInit; PinBuf hEncInit;
     // instrumentation
     float timings[ZSTDB200_TIMING_SLOTS] = {};
@@ -142,6 +143,7 @@ struct Engine {
         PinBuf* h[] = {&hStage, &hStageOut, &hEncInit};
         for (auto* b : h) b->release();
         enc.release();
+        for (auto& a : encPipe) a.release();
         if (ready) {
             for (int i = 0; i < kEvents; i++) cudaEventDestroy(ev[i]);
             for (auto e : evPool) cudaEventDestroy(e);
@@ -460,15 +462,29 @@ static size_t compress_batch_host(Engine& E, size_t n, int level, int checksum, 
     if (!E.init() || !E.bind()) return (size_t)make_error(kGeneric);
     E.launches = 0; memset(E.timings, 0, sizeof(E.timings));
     if (n == 0) return 0;
-    std::vector<uint64_t> sOff; size_t sTotal = 0;
-    cudaEventRecord(E.ev[10], E.stream);
-    if (!upload_items(E, n, src, srcSize, sOff, &sTotal)) return (size_t)make_error(kMemoryAllocation);
-    cudaEventRecord(E.ev[11], E.stream);
     // pieces: item i owns pieces [first[i], first[i+1])
     std::vector<size_t> first(n + 1);
     size_t np = 0;
     for (size_t i = 0; i < n; i++) { first[i] = np; np += srcSize[i] <= kBlockSizeMax ? 1 : (srcSize[i] + kBlockSizeMax - 1) / kBlockSizeMax; }
     first[n] = np;
+    std::vector<Run> runs;
+    find_runs(runs, n, src, srcSize);
+    // One contiguous host buffer and enough pieces: sub-batches flow through H2D (sIn) -> kernels (sComp[k], one arena each)
+    // -> compaction + D2H (sOut).  The match finder is latency bound (26 ms for 1024 chunks, 43 ms for 8192), so the
+    // sub-batches are NOT run one after the other: their kernels overlap each other and the uploads that are still in flight.
+    static int const encPipe = env_int("ZSTDB200_ENC_PIPE", 2, 1, kPipeMax);
+    size_t const nSub = (runs.size() == 1 && np >= 4096) ? std::min<size_t>((size_t)encPipe, np / 2048) : 1;
+    std::vector<uint64_t> sOff(n); size_t sTotal = 16;
+    if (nSub > 1) {
+        size_t o = sTotal;
+        for (size_t i = 0; i < n; i++) { sOff[i] = o; o += srcSize[i]; }
+        sTotal = ((o + 15) & ~(size_t)15) + 64;
+        if (!E.dSrc.ensure(sTotal)) return (size_t)make_error(kMemoryAllocation);
+    } else {
+        cudaEventRecord(E.ev[10], E.stream);
+        if (!upload_items(E, n, src, srcSize, sOff, &sTotal)) return (size_t)make_error(kMemoryAllocation);
+        cudaEventRecord(E.ev[11], E.stream);
+    }
     // device output: one slot of compressBound(pieceSize) per piece (the reference's Wrap contract, Compressor.cs:80)
     std::vector<uint64_t> pSrcOff(np), pDstOff(np); std::vector<size_t> pSize(np), slotCap(np), r(np);
     size_t dTotal = 16;
@@ -480,15 +496,71 @@ static size_t compress_batch_host(Engine& E, size_t n, int level, int checksum, 
         }
     dTotal += 16;
     if (!E.dDst.ensure(dTotal)) return (size_t)make_error(kMemoryAllocation);
-    if (!enc_compress_device(E.enc, E.stream, E.ev, np, level, checksum, E.dSrc.as<uint8_t>(), pSrcOff.data(), pSize.data(), E.dDst.as<uint8_t>(), pDstOff.data(), slotCap.data(), r.data(), E.timings, &E.launches))
-        { set_error(enc_last_error()); return (size_t)make_error(kGeneric); }
-    cudaEventRecord(E.ev[12], E.stream);
+    std::vector<uint64_t> hOff(np);              // where piece k ends up in the pinned staging buffer (pipelined / compacted paths)
+    auto fail = [&](ErrorCode c) { cudaDeviceSynchronize(); (void)cudaGetLastError(); return (size_t)make_error(c); };
+    if (nSub > 1) {
+        if (!E.hStage.ensure(dTotal) || !E.need_events(4 * nSub)) return (size_t)make_error(kMemoryAllocation);
+        cudaEvent_t* const evK = E.evPool.data();                  // [3k..3k+2]: before match / after match / after entropy
+        cudaEvent_t* const evOutK = evK + 3 * nSub;
+        size_t const per = (np + nSub - 1) / nSub;
+        if (cudaEventRecord(E.evStart, E.stream) != cudaSuccess) return fail(kGeneric);   // order after the caller's stream
+        cudaStreamWaitEvent(E.sIn, E.evStart, 0);
+        cudaEventRecord(E.evIn[0], E.sIn);
+        const uint8_t* const hostBase = (const uint8_t*)src[0];
+        for (size_t k = 0; k < nSub; k++) {
+            size_t const a = k * per, b = std::min(np, a + per);
+            size_t const lo = pSrcOff[a], hi = pSrcOff[b - 1] + pSize[b - 1];
+            if (hi > lo && cudaMemcpyAsync(E.dSrc.as<uint8_t>() + lo, hostBase + (lo - sOff[0]), hi - lo, cudaMemcpyHostToDevice, E.sIn) != cudaSuccess) return fail(kGeneric);
+            if (!enc_enqueue(E.encPipe[k], E.sComp[k], E.sIn, b - a, level, checksum, E.dSrc.as<uint8_t>(), pSrcOff.data() + a, pSize.data() + a,
+                             E.dDst.as<uint8_t>(), pDstOff.data() + a, slotCap.data() + a, evK + 3 * k, &E.launches)) { set_error(enc_last_error()); return fail(kGeneric); }
+        }
+        cudaEventRecord(E.evIn[1], E.sIn);
+        size_t stageBase = 0;
+        for (size_t k = 0; k < nSub; k++) {
+            size_t const a = k * per, b = std::min(np, a + per);
+            if (cudaEventSynchronize(evK[3 * k + 2]) != cudaSuccess) return fail(kGeneric);
+            const uint64_t* hr = enc_results(E.encPipe[k]);
+            std::vector<uint64_t> cOff(b - a); std::vector<size_t> cSize(b - a); size_t cTotal = 0;
+            for (size_t q = a; q < b; q++) { r[q] = (size_t)hr[q - a]; cOff[q - a] = cTotal; cSize[q - a] = is_error(r[q]) ? 0 : r[q]; hOff[q] = stageBase + cTotal; cTotal += cSize[q - a]; }
+            if (k == 0) cudaEventRecord(E.evOut[0], E.sOut);
+            if (!enc_compact_device(E.encPipe[k], E.sOut, b - a, E.dDst.as<uint8_t>(), pDstOff.data() + a, cSize.data(), cOff.data(), cTotal, &E.launches)) return fail(kGeneric);
+            if (cTotal && cudaMemcpyAsync(E.hStage.as<uint8_t>() + stageBase, E.encPipe[k].compactBuf(), cTotal, cudaMemcpyDeviceToHost, E.sOut) != cudaSuccess) return fail(kGeneric);
+            cudaEventRecord(evOutK[k], E.sOut);
+            // enc_compact_device keeps its offset arrays in the arena's pinned buffer: wait before the vectors above go away? no: they were copied into that buffer
+            stageBase += cTotal;
+        }
+        cudaEventRecord(E.evOut[1], E.sOut);
+        if (cudaStreamSynchronize(E.sOut) != cudaSuccess || cudaGetLastError() != cudaSuccess) return fail(kGeneric);
+        cudaEventElapsedTime(&E.timings[0], E.evIn[0], E.evIn[1]);
+        cudaEventElapsedTime(&E.timings[2], E.evOut[0], E.evOut[1]);
+        for (size_t k = 0; k < nSub; k++) {
+            float t = 0;
+            cudaEventElapsedTime(&t, evK[3 * k], evK[3 * k + 2]); E.timings[1] += t;
+            cudaEventElapsedTime(&t, evK[3 * k], evK[3 * k + 1]); E.timings[8] += t;
+            cudaEventElapsedTime(&t, evK[3 * k + 1], evK[3 * k + 2]); E.timings[9] += t;
+        }
+    } else {
+        if (!enc_compress_device(E.enc, E.stream, E.ev, np, level, checksum, E.dSrc.as<uint8_t>(), pSrcOff.data(), pSize.data(), E.dDst.as<uint8_t>(), pDstOff.data(), slotCap.data(), r.data(), E.timings, &E.launches))
+            { set_error(enc_last_error()); return (size_t)make_error(kGeneric); }
+        cudaEventRecord(E.ev[12], E.stream);
+    }
     // per item: total size, first error of its pieces, dstSize_tooSmall when the caller's buffer cannot take it (ZstdCompress.cs:4690-4800)
     for (size_t i = 0; i < n; i++) {
         size_t tot = 0;
         for (size_t k = first[i]; k < first[i + 1]; k++) { if (is_error(r[k])) { tot = r[k]; break; } tot += r[k]; }
         if (!is_error(tot) && tot > dstCap[i]) tot = (size_t)make_error(kDstSizeTooSmall);
         result[i] = tot;
+    }
+    if (nSub > 1) {
+        const uint8_t* st = E.hStage.as<uint8_t>();
+        parallel_for(n, 256, [&](size_t a, size_t b) {
+            for (size_t i = a; i < b; i++) {
+                if (is_error(result[i])) continue;
+                size_t o = 0;
+                for (size_t k = first[i]; k < first[i + 1]; k++) { memcpy((uint8_t*)dst[i] + o, st + hOff[k], r[k]); o += r[k]; }
+            }
+        });
+        return 0;
     }
     if (np <= 512) {
         for (size_t i = 0; i < n; i++) {

@@ -1479,6 +1479,9 @@ struct HBuf { void* p = nullptr; size_t cap = 0;
 struct EncArenaImpl {
     DBuf items, tables, seqLL, seqML, seqOF, lit, stateBits, results, compact, cSrcOff, cSizes, cDstOff, workLists;
     HBuf hItems, hResults, hC, hWork;
+    cudaEvent_t copied = nullptr;
+    EncArenaImpl() { cudaEventCreateWithFlags(&copied, cudaEventDisableTiming); }
+    ~EncArenaImpl() { if (copied) cudaEventDestroy(copied); }
 };
 static thread_local std::string t_encErr;
 const char* enc_last_error() { return t_encErr.c_str(); }
@@ -1496,66 +1499,84 @@ const uint8_t* EncArena::compactBuf() const { return impl ? (const uint8_t*)impl
 
 constexpr size_t kEncMaxItemsPerPass = 8192;
 
+// Queues one pass (m <= kEncMaxItemsPerPass chunks) without waiting: the chunk descriptors and work lists are copied on
+// `copyStream` (pass the stream that carries the bulk H2D of the same chunks, so that the small copies do not queue
+// behind later bulk transfers; `stream` must then wait for that stream's event before this call), all kernels
+// run on `stream`, and the per-chunk results are written straight into pinned host memory (enc_results).
+// ev3 (optional): [0] before the match finder, [1] after it, [2] after the entropy stage.
+bool enc_enqueue(EncArena& A, cudaStream_t stream, cudaStream_t copyStream, size_t m, int level, int checksumFlag,
+                 const uint8_t* d_src, const uint64_t* srcOff, const size_t* srcSize,
+                 uint8_t* d_dst, const uint64_t* dstOff, const size_t* dstCap, cudaEvent_t* ev3, unsigned* launches)
+{
+    if (!A.impl) A.impl = new EncArenaImpl();
+    EncArenaImpl& I = *A.impl;
+    if (m > kEncMaxItemsPerPass) { t_encErr = "pass too large"; return false; }
+    if (!I.hItems.ensure(m * sizeof(EncItem)) || !I.items.ensure(m * sizeof(EncItem)) || !I.hResults.ensure(m * 8)) { t_encErr = "out of memory (items)"; return false; }
+    if (!I.hWork.ensure(m * 12) || !I.workLists.ensure(m * 12)) { t_encErr = "out of memory (work lists)"; return false; }
+    EncItem* hi = (EncItem*)I.hItems.p;
+    uint32_t* const fastList = (uint32_t*)I.hWork.p; uint32_t* const serialList = fastList + m; uint32_t* const dfastList = serialList + m;
+    uint32_t nFast = 0, nSerial = 0, nDfast = 0;
+    size_t tableEntries = 0;
+    for (size_t i = 0; i < m; i++) {
+        size_t const ss = srcSize[i];
+        EncItem& e = hi[i];
+        memset(&e, 0, sizeof(e));
+        e.srcOff = srcOff[i]; e.dstOff = dstOff[i];
+        e.srcSize = (uint32_t)std::min<size_t>(ss, 0xFFFFFFF0u); e.dstCap = (uint32_t)std::min<size_t>(dstCap[i], 0xFFFFFFF0u);
+        CParams const c = get_cparams(level, std::min<size_t>(ss, kBlockSizeMax));
+        e.windowLog = c.windowLog; e.hashLog = c.hashLog; e.chainLog = c.chainLog; e.minMatch = c.minMatch; e.strategy = c.strategy;
+        e.nbSeq = 0; e.lastLL = e.srcSize;
+        if (ss < 7 || ss > kBlockSizeMax) continue;              // raw block / unsupported: no match finding
+        // group kernels (16 lanes per chunk) for ZSTD_fast and ZSTD_dfast; chunks below 64 bytes take the serial lane kernel
+        if (ss >= 64 && c.strategy == 1) fastList[nFast++] = (uint32_t)i;
+        else if (ss >= 64 && c.strategy == 2) dfastList[nDfast++] = (uint32_t)i;
+        else serialList[nSerial++] = (uint32_t)i;
+        e.tableOff = (uint32_t)tableEntries;
+        tableEntries += ((size_t)1 << c.hashLog) + (c.strategy == 2 ? ((size_t)1 << c.chainLog) : 0);
+    }
+    if (tableEntries >= 0xFFFFFFFFull) { t_encErr = "hash-table arena exceeds 32-bit indexing"; return false; }
+    if (!I.tables.ensure(tableEntries * 4 + 16) || !I.seqLL.ensure(m * (size_t)kEncSeqCap * 4) || !I.seqML.ensure(m * (size_t)kEncSeqCap * 4) ||
+        !I.seqOF.ensure(m * (size_t)kEncSeqCap * 4) || !I.lit.ensure(m * (size_t)kEncLitStride) || !I.stateBits.ensure(m * (size_t)kEncSeqCap * 8)) { t_encErr = "out of memory (arena)"; return false; }
+    ENC_CUDA(cudaMemcpyAsync(I.items.p, hi, m * sizeof(EncItem), cudaMemcpyHostToDevice, copyStream));
+    ENC_CUDA(cudaMemcpyAsync(I.workLists.p, I.hWork.p, m * 12, cudaMemcpyHostToDevice, copyStream));
+    if (copyStream != stream) {                                   // order the kernels after the two small copies
+        ENC_CUDA(cudaEventRecord(I.copied, copyStream));
+        ENC_CUDA(cudaStreamWaitEvent(stream, I.copied, 0));
+    }
+    if (ev3) ENC_CUDA(cudaEventRecord(ev3[0], stream));
+    if (tableEntries) ENC_CUDA(cudaMemsetAsync(I.tables.p, 0, tableEntries * 4, stream));      // tables are zeroed per frame (ZstdCompress.cs:2472,2481)
+    EncPass p;
+    p.items = (EncItem*)I.items.p; p.nItems = (uint32_t)m; p.src = d_src; p.dst = d_dst; p.tables = (uint32_t*)I.tables.p;
+    p.seqLL = (uint32_t*)I.seqLL.p; p.seqML = (uint32_t*)I.seqML.p; p.seqOF = (uint32_t*)I.seqOF.p; p.litBuf = (uint8_t*)I.lit.p;
+    p.stateBits = (uint64_t*)I.stateBits.p; p.results = (uint64_t*)I.hResults.p; p.checksumFlag = checksumFlag ? 1u : 0u;
+    // lanes per chunk: 16 measured best for ZSTD_fast (8: 49/52 ms, 16: 42/49 ms, 32: 63/72 ms per GiB Silesia-mix / text)
+    if (nFast) enc_match_group_kernel<16><<<(nFast + 1) / 2, 32, 0, stream>>>(p, (const uint32_t*)I.workLists.p, nFast);
+    if (nSerial) enc_match_kernel<<<(nSerial + 31) / 32, 32, 0, stream>>>(p, (const uint32_t*)I.workLists.p + m, nSerial);
+    if (nDfast) enc_match_dfast_group_kernel<16><<<(nDfast + 1) / 2, 32, 0, stream>>>(p, (const uint32_t*)I.workLists.p + 2 * m, nDfast);
+    if (ev3) ENC_CUDA(cudaEventRecord(ev3[1], stream));
+    enc_entropy_kernel<<<(unsigned)m, kEntThreads, 0, stream>>>(p);
+    if (ev3) ENC_CUDA(cudaEventRecord(ev3[2], stream));
+    *launches += 1 + (nSerial ? 1 : 0) + (nFast ? 1 : 0) + (nDfast ? 1 : 0) + (tableEntries ? 1 : 0);
+    return true;
+}
+const uint64_t* enc_results(const EncArena& A) { return A.impl ? (const uint64_t*)A.impl->hResults.p : nullptr; }
+
 bool enc_compress_device(EncArena& A, cudaStream_t stream, cudaEvent_t* ev, size_t n, int level, int checksumFlag,
                          const uint8_t* d_src, const uint64_t* srcOff, const size_t* srcSize,
                          uint8_t* d_dst, const uint64_t* dstOff, const size_t* dstCap, size_t* result,
                          float* timings, unsigned* launches)
 {
-    if (!A.impl) A.impl = new EncArenaImpl();
-    EncArenaImpl& I = *A.impl;
     float msAll = 0, msMatch = 0, msEnt = 0;
     for (size_t base = 0; base < n; base += kEncMaxItemsPerPass) {
         size_t const m = std::min(kEncMaxItemsPerPass, n - base);
-        if (!I.hItems.ensure(m * sizeof(EncItem)) || !I.items.ensure(m * sizeof(EncItem)) || !I.results.ensure(m * 8) || !I.hResults.ensure(m * 8)) { t_encErr = "out of memory (items)"; return false; }
-        if (!I.hWork.ensure(m * 12) || !I.workLists.ensure(m * 12)) { t_encErr = "out of memory (work lists)"; return false; }
-        EncItem* hi = (EncItem*)I.hItems.p;
-        uint32_t* const fastList = (uint32_t*)I.hWork.p; uint32_t* const serialList = fastList + m; uint32_t* const dfastList = serialList + m;
-        uint32_t nFast = 0, nSerial = 0, nDfast = 0;
-        size_t tableEntries = 0;
-        for (size_t i = 0; i < m; i++) {
-            size_t const ss = srcSize[base + i];
-            EncItem& e = hi[i];
-            memset(&e, 0, sizeof(e));
-            e.srcOff = srcOff[base + i]; e.dstOff = dstOff[base + i];
-            e.srcSize = (uint32_t)std::min<size_t>(ss, 0xFFFFFFF0u); e.dstCap = (uint32_t)std::min<size_t>(dstCap[base + i], 0xFFFFFFF0u);
-            CParams const c = get_cparams(level, std::min<size_t>(ss, kBlockSizeMax));
-            e.windowLog = c.windowLog; e.hashLog = c.hashLog; e.chainLog = c.chainLog; e.minMatch = c.minMatch; e.strategy = c.strategy;
-            e.nbSeq = 0; e.lastLL = e.srcSize;
-            if (ss < 7 || ss > kBlockSizeMax) continue;              // raw block / unsupported: no match finding
-            // group kernels (16 lanes per chunk) for ZSTD_fast and ZSTD_dfast; chunks below 64 bytes take the serial lane kernel
-            if (ss >= 64 && c.strategy == 1) fastList[nFast++] = (uint32_t)i;
-            else if (ss >= 64 && c.strategy == 2) dfastList[nDfast++] = (uint32_t)i;
-            else serialList[nSerial++] = (uint32_t)i;
-            e.tableOff = (uint32_t)tableEntries;
-            tableEntries += ((size_t)1 << c.hashLog) + (c.strategy == 2 ? ((size_t)1 << c.chainLog) : 0);
-        }
-        if (tableEntries >= 0xFFFFFFFFull) { t_encErr = "hash-table arena exceeds 32-bit indexing"; return false; }
-        if (!I.tables.ensure(tableEntries * 4 + 16) || !I.seqLL.ensure(m * (size_t)kEncSeqCap * 4) || !I.seqML.ensure(m * (size_t)kEncSeqCap * 4) ||
-            !I.seqOF.ensure(m * (size_t)kEncSeqCap * 4) || !I.lit.ensure(m * (size_t)kEncLitStride) || !I.stateBits.ensure(m * (size_t)kEncSeqCap * 8)) { t_encErr = "out of memory (arena)"; return false; }
-        ENC_CUDA(cudaMemcpyAsync(I.items.p, hi, m * sizeof(EncItem), cudaMemcpyHostToDevice, stream));
-        ENC_CUDA(cudaEventRecord(ev[14], stream));
-        ENC_CUDA(cudaMemcpyAsync(I.workLists.p, I.hWork.p, m * 12, cudaMemcpyHostToDevice, stream));
-        if (tableEntries) ENC_CUDA(cudaMemsetAsync(I.tables.p, 0, tableEntries * 4, stream));      // tables are zeroed per frame (ZstdCompress.cs:2472,2481)
-        EncPass p;
-        p.items = (EncItem*)I.items.p; p.nItems = (uint32_t)m; p.src = d_src; p.dst = d_dst; p.tables = (uint32_t*)I.tables.p;
-        p.seqLL = (uint32_t*)I.seqLL.p; p.seqML = (uint32_t*)I.seqML.p; p.seqOF = (uint32_t*)I.seqOF.p; p.litBuf = (uint8_t*)I.lit.p;
-        p.stateBits = (uint64_t*)I.stateBits.p; p.results = (uint64_t*)I.results.p; p.checksumFlag = checksumFlag ? 1u : 0u;
-        // lanes per chunk: 16 measured best for ZSTD_fast (8: 49/52 ms, 16: 42/49 ms, 32: 63/72 ms per GiB Silesia-mix / text)
-        if (nFast) enc_match_group_kernel<16><<<(nFast + 1) / 2, 32, 0, stream>>>(p, (const uint32_t*)I.workLists.p, nFast);
-        if (nSerial) enc_match_kernel<<<(nSerial + 31) / 32, 32, 0, stream>>>(p, (const uint32_t*)I.workLists.p + m, nSerial);
-        if (nDfast) enc_match_dfast_group_kernel<16><<<(nDfast + 1) / 2, 32, 0, stream>>>(p, (const uint32_t*)I.workLists.p + 2 * m, nDfast);
-        ENC_CUDA(cudaEventRecord(ev[15], stream));
-        enc_entropy_kernel<<<(unsigned)m, kEntThreads, 0, stream>>>(p);
-        ENC_CUDA(cudaEventRecord(ev[16], stream));
-        *launches += 1 + (nSerial ? 1 : 0) + (nFast ? 1 : 0) + (nDfast ? 1 : 0) + (tableEntries ? 1 : 0);
-        ENC_CUDA(cudaMemcpyAsync(I.hResults.p, I.results.p, m * 8, cudaMemcpyDeviceToHost, stream));
+        if (!enc_enqueue(A, stream, stream, m, level, checksumFlag, d_src, srcOff + base, srcSize + base, d_dst, dstOff + base, dstCap + base, &ev[14], launches)) return false;
         ENC_CUDA(cudaStreamSynchronize(stream));
         ENC_CUDA(cudaGetLastError());
         float t;
         cudaEventElapsedTime(&t, ev[14], ev[16]); msAll += t;
         cudaEventElapsedTime(&t, ev[14], ev[15]); msMatch += t;
         cudaEventElapsedTime(&t, ev[15], ev[16]); msEnt += t;
-        const uint64_t* hr = (const uint64_t*)I.hResults.p;
+        const uint64_t* hr = enc_results(A);
         for (size_t i = 0; i < m; i++) {
             size_t const ss = srcSize[base + i];
             if (ss > kBlockSizeMax) result[base + i] = (size_t)make_error(kSrcSizeWrong);   // multi-block frames: DESIGN.md "next" (f.2)
@@ -1566,18 +1587,17 @@ bool enc_compress_device(EncArena& A, cudaStream_t stream, cudaEvent_t* ev, size
     return true;
 }
 
+// Gathers n variable-size frames into the arena's dense buffer; the offset / size arrays stay in pinned host memory and
+// are read by the kernel directly.
 bool enc_compact_device(EncArena& A, cudaStream_t stream, size_t n, const uint8_t* d_dst, const uint64_t* dstOff,
                         const size_t* sizes, const uint64_t* cOff, size_t total, unsigned* launches)
 {
     if (!A.impl) A.impl = new EncArenaImpl();
     EncArenaImpl& I = *A.impl;
-    if (!I.compact.ensure(total + 16) || !I.cSrcOff.ensure(n * 8) || !I.cSizes.ensure(n * 8) || !I.cDstOff.ensure(n * 8) || !I.hC.ensure(n * 24)) { t_encErr = "out of memory (compact)"; return false; }
+    if (!I.compact.ensure(total + 16) || !I.hC.ensure(n * 24)) { t_encErr = "out of memory (compact)"; return false; }
     uint64_t* h = (uint64_t*)I.hC.p;
     for (size_t i = 0; i < n; i++) { h[i] = dstOff[i]; h[n + i] = is_error(sizes[i]) ? 0 : sizes[i]; h[2 * n + i] = cOff[i]; }
-    ENC_CUDA(cudaMemcpyAsync(I.cSrcOff.p, h, n * 8, cudaMemcpyHostToDevice, stream));
-    ENC_CUDA(cudaMemcpyAsync(I.cSizes.p, h + n, n * 8, cudaMemcpyHostToDevice, stream));
-    ENC_CUDA(cudaMemcpyAsync(I.cDstOff.p, h + 2 * n, n * 8, cudaMemcpyHostToDevice, stream));
-    enc_compact_kernel<<<(unsigned)n, 256, 0, stream>>>(d_dst, (const uint64_t*)I.cSrcOff.p, (const uint64_t*)I.cSizes.p, (const uint64_t*)I.cDstOff.p, (uint8_t*)I.compact.p);
+    enc_compact_kernel<<<(unsigned)n, 256, 0, stream>>>(d_dst, h, h + n, h + 2 * n, (uint8_t*)I.compact.p);
     *launches += 1;
     return true;
 }

@@ -21,6 +21,12 @@ bool enc_compress_device(EncArena& A, cudaStream_t stream, cudaEvent_t* ev, size
                          const uint8_t* d_src, const uint64_t* srcOff, const size_t* srcSize,
                          uint8_t* d_dst, const uint64_t* dstOff, const size_t* dstCap, size_t* result,
                          float* timings, unsigned* launches);
+// Queues one pass (m <= 8192 chunks) on `stream` without waiting; descriptors are copied on `copyStream`; results land in
+// pinned host memory (enc_results) once `stream` has drained.  ev3 (optional): events before/after match, after entropy.
+bool enc_enqueue(EncArena& A, cudaStream_t stream, cudaStream_t copyStream, size_t m, int level, int checksumFlag,
+                 const uint8_t* d_src, const uint64_t* srcOff, const size_t* srcSize,
+                 uint8_t* d_dst, const uint64_t* dstOff, const size_t* dstCap, cudaEvent_t* ev3, unsigned* launches);
+const uint64_t* enc_results(const EncArena& A);
 // Gathers the n variable-size frames into one dense device buffer (A.compactBuf()) at offsets cOff.
 bool enc_compact_device(EncArena& A, cudaStream_t stream, size_t n, const uint8_t* d_dst, const uint64_t* dstOff,
                         const size_t* sizes, const uint64_t* cOff, size_t total, unsigned* launches);
