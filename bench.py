@@ -215,6 +215,10 @@ def run_reference(args):
 #  GPU side
 # ----------------------------------------------------------------------------------------------------------------
 def run_b200(args):
+    # stdout carries exactly one JSON line: libraries (NCCL prints its version banner there) are sent to stderr meanwhile
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    os.environ.setdefault("NCCL_DEBUG", "WARN")
     import torch
     import torch.distributed as dist
     from zstdsharp_b200 import api, _native
@@ -461,7 +465,8 @@ def run_b200(args):
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
             "cpu_baseline": cpu, "compress_l1": compress,
         }
-        print(json.dumps(line), flush=True)
+        sys.stdout.flush()
+        os.write(real_stdout, (json.dumps(line) + "\n").encode())
     if world > 1:
         dist.destroy_process_group()
 
