@@ -55,8 +55,13 @@ ZSTDB200_API size_t     ZSTD_decompressDCtx(ZSTD_DCtx* dctx, void* dst, size_t d
                                             const void* src, size_t srcSize);                      /* :30 */
 ZSTDB200_API size_t     ZSTD_compressBound(size_t srcSize);                                        /* :34 */
 /* param: ZSTD_c_compressionLevel = 100 (levels 0..3; 0 means 3), ZSTD_c_checksumFlag = 201 (0/1: XXH64 trailer, U/ZstdCompress.cs:5641-5652),
- * ZSTD_c_contentSizeFlag = 200 (1 only);
+ * ZSTD_c_contentSizeFlag = 200 (1 only), ZSTDB200_c_independentChunks (below);
  * anything else -> ZSTD_error_parameter_unsupported. */
+/* New, host-pointer API only.  0 (default): every item becomes one frame with the reference's bytes; items above 128 KiB are
+ * multi-block frames (U/ZstdCompress.cs:4690 ZSTD_compress_frameChunk), whose blocks the GPU must take one after the other.
+ * 1: items above 128 KiB are cut into independent 128 KiB frames written back to back (all pieces in parallel; valid for every
+ * zstd decoder, ZSTD_decompressBound = item size, a few percent larger, NOT the reference's bytes). */
+#define ZSTDB200_c_independentChunks 10001
 ZSTDB200_API size_t     ZSTD_CCtx_setParameter(ZSTD_CCtx* cctx, int param, int value);             /* :37 */
 /* needed by the safe wrappers in addition (Decompressor.cs:53, ThrowHelper.cs:12-13) */
 ZSTDB200_API unsigned long long ZSTD_decompressBound(const void* src, size_t srcSize);

@@ -60,6 +60,7 @@ class ZSTD_cParameter(enum.IntEnum):        # Unsafe/ZSTD_cParameter.cs (the one
     ZSTD_c_compressionLevel = 100
     ZSTD_c_contentSizeFlag = 200
     ZSTD_c_checksumFlag = 201
+    ZSTDB200_c_independentChunks = 10001     # new (include/zstd_b200.h): 1 = cut items above 128 KiB into independent frames
 
 
 class ZstdException(Exception):

@@ -452,20 +452,23 @@ static size_t decompress_batch_host(Engine& E, size_t n, const void* const* src,
     return 0;
 }
 
-// Host-pointer batch compression.  An item of at most 128 KiB becomes one single-block frame, byte-identical to the
-// reference's Wrap.  A larger item is cut into 128 KiB pieces that are compressed as independent frames and written
-// back to back: a valid zstd stream for any decoder (ZSTD_decompressMultiFrame, ZstdDecompress.cs:1216) whose
-// ZSTD_decompressBound is the item size, but NOT the reference's bytes (it would emit one multi-block frame with a
-// window that spans the blocks) -- see DESIGN.md, deviations.
-static size_t compress_batch_host(Engine& E, size_t n, int level, int checksum, const void* const* src, const size_t* srcSize, void* const* dst, const size_t* dstCap, size_t* result)
+// Host-pointer batch compression.  Every item becomes ONE frame, byte-identical to the reference's Wrap: a single block up
+// to 128 KiB, a multi-block frame above (window, repcodes and Huffman table carried from block to block; the blocks of a
+// frame are a serial chain on the GPU, so this pays off for batches of frames, not for one huge input).
+// With ZSTDB200_c_independentChunks = 1 (or for items of 2 GiB and more) a larger item is instead cut into 128 KiB pieces that
+// are compressed as independent frames and written back to back: a valid zstd stream for any decoder
+// (ZSTD_decompressMultiFrame, ZstdDecompress.cs:1216) whose ZSTD_decompressBound is the item size, all pieces in
+// parallel, but NOT the reference's bytes -- see DESIGN.md, deviations.
+static size_t compress_batch_host(Engine& E, size_t n, int level, int checksum, int chunked, const void* const* src, const size_t* srcSize, void* const* dst, const size_t* dstCap, size_t* result)
 {
+    auto cut = [&](size_t ss) { return ss > kBlockSizeMax && (chunked || ss > enc_max_frame_bytes()); };
     if (!E.init() || !E.bind()) return (size_t)make_error(kGeneric);
     E.launches = 0; memset(E.timings, 0, sizeof(E.timings));
     if (n == 0) return 0;
     // pieces: item i owns pieces [first[i], first[i+1])
     std::vector<size_t> first(n + 1);
     size_t np = 0;
-    for (size_t i = 0; i < n; i++) { first[i] = np; np += srcSize[i] <= kBlockSizeMax ? 1 : (srcSize[i] + kBlockSizeMax - 1) / kBlockSizeMax; }
+    for (size_t i = 0; i < n; i++) { first[i] = np; np += !cut(srcSize[i]) ? 1 : (srcSize[i] + kBlockSizeMax - 1) / kBlockSizeMax; }
     first[n] = np;
     std::vector<Run> runs;
     find_runs(runs, n, src, srcSize);
@@ -491,7 +494,7 @@ static size_t compress_batch_host(Engine& E, size_t n, int level, int checksum, 
     for (size_t i = 0; i < n; i++)
         for (size_t k = first[i]; k < first[i + 1]; k++) {
             size_t const o = (k - first[i]) * (size_t)kBlockSizeMax;
-            pSrcOff[k] = sOff[i] + o; pSize[k] = std::min<size_t>(srcSize[i] - o, kBlockSizeMax);
+            pSrcOff[k] = sOff[i] + o; pSize[k] = cut(srcSize[i]) ? std::min<size_t>(srcSize[i] - o, kBlockSizeMax) : srcSize[i];
             pDstOff[k] = dTotal; slotCap[k] = enc_compress_bound(pSize[k]); dTotal += (slotCap[k] + 15) & ~(size_t)15;
         }
     dTotal += 16;
@@ -692,7 +695,7 @@ static const char* error_name(uint32_t code)   // ErrorPrivate.cs:34-184
 // =================================================================================================================
 //  extern "C" surface
 // =================================================================================================================
-struct ZSTD_CCtx_s { zb::Engine E; int level = 3; int checksum = 0; };
+struct ZSTD_CCtx_s { zb::Engine E; int level = 3; int checksum = 0; int chunked = 0; };
 struct ZSTD_DCtx_s { zb::Engine E; };
 
 using zb::make_error;
@@ -718,6 +721,10 @@ size_t ZSTD_CCtx_setParameter(ZSTD_CCtx* cctx, int param, int value)
         cctx->checksum = value; return 0;
     }
     if (param == 200) { if (value != 1) return (size_t)make_error(zb::kParameterUnsupported); return 0; }   // ZSTD_c_contentSizeFlag: always on
+    if (param == ZSTDB200_c_independentChunks) {
+        if (value != 0 && value != 1) return (size_t)make_error(zb::kParameterOutOfBound);
+        cctx->chunked = value; return 0;
+    }
     return (size_t)make_error(zb::kParameterUnsupported);
 }
 
@@ -725,7 +732,7 @@ size_t ZSTDB200_compressBatch(ZSTD_CCtx* cctx, size_t n, int level, const void* 
 {
     if (!cctx) return (size_t)make_error(zb::kGeneric);
     if (level < 0 || level > 3) { for (size_t i = 0; i < n; i++) result[i] = (size_t)make_error(zb::kParameterUnsupported); return 0; }
-    return zb::compress_batch_host(cctx->E, n, level, cctx->checksum, src, srcSize, dst, dstCap, result);
+    return zb::compress_batch_host(cctx->E, n, level, cctx->checksum, cctx->chunked, src, srcSize, dst, dstCap, result);
 }
 
 size_t ZSTD_compressCCtx(ZSTD_CCtx* cctx, void* dst, size_t dstCapacity, const void* src, size_t srcSize, int level)

@@ -63,15 +63,41 @@ static CParams get_cparams(int level, uint64_t srcSize)
 // ------------------------------------------------------------------------------------------------------------
 constexpr uint32_t kEncSeqCap = kBlockSizeMax / 4 + 1;      // maxNbSeq = blockSize / 4 (minMatch != 3), ZstdCompress.cs:2570
 constexpr uint32_t kEncLitStride = kBlockSizeMax + 64;
+constexpr size_t kEncMaxFrameBytes = 0x7FFF0000u;           // positions inside a frame are 31-bit integers in the match kernels
 
 struct __align__(16) EncItem {
     uint64_t srcOff, dstOff;
-    uint32_t srcSize, dstCap;
+    uint32_t srcSize, dstCap;      // whole frame
     uint32_t windowLog, hashLog, chainLog, minMatch, strategy;
-    uint32_t tableOff;      // offset (in u32 entries) of this chunk's hash table(s) inside the table arena
-    uint32_t nbSeq, lastLL;
-    uint32_t _pad[2];
+    uint32_t tableOff;      // offset (in u32 entries) of this frame's hash table(s) inside the table arena
+    uint32_t nbSeq, lastLL; // current block
+    // ---- state carried from block to block of a multi-block frame (ZSTD_compressedBlockState_t, ZstdCompressInternal.cs) ----
+    uint32_t rep[2];        // prevCBlock->rep[0..1]: repcodes confirmed by the last compressed block (rep[2] stays 8: fast/dfast never touch it)
+    uint32_t repNext[2];    // nextCBlock->rep[0..1]: repcodes after the current block's parse, confirmed by the entropy stage
+    uint32_t outPos;        // bytes of the frame written so far
+    uint32_t hufRepeat;     // prevCBlock->entropy.huf.repeatMode: 0 none, 1 check (valid needs a dictionary)
+    uint32_t hufCur;        // which of the frame's two Huffman table slots holds prevCBlock's table
+    uint32_t _pad;
 };
+
+// Geometry of block `wave` of a frame (ZSTD_compress_frameChunk :4690 + ZSTD_window_enforceMaxDist, ZstdCompressInternal.cs:630;
+// ZSTD_getLowestPrefixIndex :802).  Positions are byte offsets from the frame start; the reference's index of a position is +2.
+struct BlkGeom { int B, end, lowPos, ip0; uint32_t maxRep; };
+__device__ __forceinline__ BlkGeom blk_geom(uint32_t frameSize, uint32_t windowLog, uint32_t wave)
+{
+    BlkGeom g;
+    uint32_t const B = wave * kBlockSizeMax, size = min(kBlockSizeMax, frameSize - B), end = B + size;
+    uint32_t const maxDist = 1u << windowLog;
+    uint32_t const startIdx = B + 2, endIdx = end + 2;
+    uint32_t const dictLimit = startIdx > maxDist ? max(2u, startIdx - maxDist) : 2u;      // lowLimit == dictLimit without a dictionary
+    uint32_t const prefixStartIndex = (endIdx - dictLimit > maxDist) ? endIdx - maxDist : dictLimit;
+    g.B = (int)B; g.end = (int)end; g.lowPos = (int)prefixStartIndex - 2;
+    g.ip0 = (int)B + (g.B == g.lowPos);                                                     // ip0 += (ip0 == prefixStart)
+    uint32_t const curr = (uint32_t)g.ip0 + 2;
+    uint32_t const windowLow = (curr - dictLimit > maxDist) ? curr - maxDist : dictLimit;
+    g.maxRep = curr - windowLow;
+    return g;
+}
 
 struct EncPass {
     EncItem* items; uint32_t nItems;
@@ -81,8 +107,10 @@ struct EncPass {
     uint8_t* litBuf;        // gathered literals
     uint64_t* stateBits;    // per sequence: FSE state bits of OF | ML | LL (13 bits each: 9 value + 4 count)
     uint64_t* results;
+    uint8_t* hufState;      // multi-block frames: 2 slots of {u8 nbBits[256]; u16 value[256]} per frame (prev / next Huffman CTable)
     uint32_t checksumFlag;  // ZSTD_c_checksumFlag: append the low 32 bits of XXH64(src) to every frame
 };
+constexpr uint32_t kHufStateSlot = 768;
 
 __device__ __forceinline__ uint32_t rd32(const uint8_t* p)
 {
@@ -131,21 +159,19 @@ struct SeqWriter {
     { ll[n] = litLength; of[n] = offCode + 1; ml[n] = mlBase; n++; }
 };
 
-// ZSTD_compressBlock_fast_noDict_generic, ZstdFast.cs:96 (first block of a frame: base index 2, prefixStart = istart)
-__device__ uint32_t match_fast(uint32_t* hashTable, uint32_t hlog, uint32_t mls, const uint8_t* istart, uint32_t srcSize, SeqWriter& sw)
+// ZSTD_compressBlock_fast_noDict_generic, ZstdFast.cs:96, on block g of the frame at `frame` (serial restatement)
+__device__ uint32_t match_fast(uint32_t* hashTable, uint32_t hlog, uint32_t mls, const uint8_t* frame, const BlkGeom& g, uint32_t rep[2], SeqWriter& sw)
 {
-    const uint8_t* const base = istart - 2;
-    uint32_t const prefixStartIndex = 2;
-    const uint8_t* const prefixStart = istart;
-    const uint8_t* const iend = istart + srcSize; const uint8_t* const ilimit = iend - 8;
-    const uint8_t* anchor = istart; const uint8_t* ip0 = istart; const uint8_t* ip1; const uint8_t* ip2; const uint8_t* ip3;
-    uint32_t current0 = 0; uint32_t rep1 = 1, rep2 = 4;
+    const uint8_t* const base = frame - 2;
+    uint32_t const prefixStartIndex = (uint32_t)g.lowPos + 2;
+    const uint8_t* const prefixStart = frame + g.lowPos;
+    const uint8_t* const istart = frame + g.B;
+    const uint8_t* const iend = frame + g.end; const uint8_t* const ilimit = iend - 8;
+    const uint8_t* anchor = istart; const uint8_t* ip0 = frame + g.ip0; const uint8_t* ip1; const uint8_t* ip2; const uint8_t* ip3;
+    uint32_t current0 = 0; uint32_t rep1 = rep[0], rep2 = rep[1], offsetSaved = 0;
     uint32_t hash0, hash1, idx, mval, offcode; const uint8_t* match0; uint32_t mLength; uint32_t step; const uint8_t* nextStep;
-    ip0 += 1;                                           // ip0 == prefixStart (:129)
-    {   uint32_t const maxRep = 1;                      // curr - windowLow = 3 - 2 (:131-145)
-        if (rep2 > maxRep) rep2 = 0;
-        if (rep1 > maxRep) rep1 = 0;
-    }
+    if (rep2 > g.maxRep) { offsetSaved = rep2; rep2 = 0; }          // :131-145
+    if (rep1 > g.maxRep) { offsetSaved = rep1; rep1 = 0; }
 _start:
     step = 2; nextStep = ip0 + 128;
     ip1 = ip0 + 1; ip2 = ip0 + step; ip3 = ip2 + 1;
@@ -178,6 +204,8 @@ _start:
         if (ip2 >= nextStep) { step++; nextStep += 128; }
     } while (ip3 < ilimit);
 _cleanup:
+    rep[0] = rep1 ? rep1 : offsetSaved;                 // :232-233
+    rep[1] = rep2 ? rep2 : offsetSaved;
     return (uint32_t)(iend - anchor);
 _offset:
     match0 = base + idx;
@@ -207,25 +235,23 @@ _match:
     goto _start;
 }
 
-// ZSTD_compressBlock_doubleFast_noDict_generic, ZstdDoubleFast.cs:51
+// ZSTD_compressBlock_doubleFast_noDict_generic, ZstdDoubleFast.cs:51, on block g of the frame at `frame` (serial restatement)
 __device__ uint32_t match_dfast(uint32_t* hashLong, uint32_t hBitsL, uint32_t* hashSmall, uint32_t hBitsS, uint32_t mls,
-                                const uint8_t* istart, uint32_t srcSize, SeqWriter& sw)
+                                const uint8_t* frame, const BlkGeom& g, uint32_t rep[2], SeqWriter& sw)
 {
-    const uint8_t* const base = istart - 2;
-    uint32_t const prefixLowestIndex = 2;
-    const uint8_t* const prefixLowest = istart;
-    const uint8_t* const iend = istart + srcSize; const uint8_t* const ilimit = iend - 8;
+    const uint8_t* const base = frame - 2;
+    uint32_t const prefixLowestIndex = (uint32_t)g.lowPos + 2;
+    const uint8_t* const prefixLowest = frame + g.lowPos;
+    const uint8_t* const istart = frame + g.B;
+    const uint8_t* const iend = frame + g.end; const uint8_t* const ilimit = iend - 8;
     const uint8_t* anchor = istart;
-    uint32_t offset_1 = 1, offset_2 = 4;
+    uint32_t offset_1 = rep[0], offset_2 = rep[1], offsetSaved = 0;
     uint32_t mLength, offset, curr = 0;
     const uint8_t* nextStep; uint32_t step; uint32_t hl0, hl1 = 0; uint32_t idxl0, idxl1 = 0;
     const uint8_t* matchl0; const uint8_t* matchs0; const uint8_t* matchl1 = istart;
-    const uint8_t* ip = istart; const uint8_t* ip1;
-    ip += 1;
-    {   uint32_t const maxRep = 1;
-        if (offset_2 > maxRep) offset_2 = 0;
-        if (offset_1 > maxRep) offset_1 = 0;
-    }
+    const uint8_t* ip = frame + g.ip0; const uint8_t* ip1;
+    if (offset_2 > g.maxRep) { offsetSaved = offset_2; offset_2 = 0; }
+    if (offset_1 > g.maxRep) { offsetSaved = offset_1; offset_1 = 0; }
     while (1) {
         step = 1; nextStep = ip + 256; ip1 = ip + step;
         if (ip1 > ilimit) goto _cleanup;
@@ -261,6 +287,8 @@ __device__ uint32_t match_dfast(uint32_t* hashLong, uint32_t hBitsL, uint32_t* h
             hl0 = hl1; idxl0 = idxl1; matchl0 = matchl1;
         } while (ip1 <= ilimit);
 _cleanup:
+        rep[0] = offset_1 ? offset_1 : offsetSaved;     // :215-216
+        rep[1] = offset_2 ? offset_2 : offsetSaved;
         return (uint32_t)(iend - anchor);
 _search_next_long:
         if (idxl1 > prefixLowestIndex) {
@@ -324,8 +352,8 @@ __device__ __forceinline__ uint32_t hash_val(uint64_t x, uint32_t hBits, uint32_
 //  instruction stream.  A 32-lane window wastes ~28 of its 32 probes on text (the first event sits within the first few
 //  probes): ncu showed 33 G warp instructions and 120 GB of DRAM reads per GiB; 8 lanes per chunk cut both.
 // ------------------------------------------------------------------------------------------------------------
-template <int GS>
-__global__ void __launch_bounds__(32) enc_match_group_kernel(EncPass p, const uint32_t* __restrict__ workList, uint32_t nWork)
+template <int GS, bool MB>
+__global__ void __launch_bounds__(32) enc_match_group_kernel(EncPass p, const uint32_t* __restrict__ workList, uint32_t nWork, uint32_t wave)
 {
     constexpr uint32_t FULL = 0xFFFFFFFFu;
     constexpr int NG = 32 / GS, NIT = GS / 2;
@@ -337,15 +365,23 @@ __global__ void __launch_bounds__(32) enc_match_group_kernel(EncPass p, const ui
     uint32_t const item = workList[active ? wi : 0];
     EncItem& it = p.items[item];
     uint32_t const hlog = it.hashLog, mls = it.minMatch;
-    int const srcSize = active ? (int)it.srcSize : 64;
-    const uint8_t* const src = p.src + it.srcOff;
-    uint32_t* const T = p.tables + it.tableOff;      // zero-initialised, HBM/L2-resident
+    const uint8_t* const src = p.src + it.srcOff;    // frame start; every position below is an offset from it
+    uint32_t* const T = p.tables + it.tableOff;      // zero-initialised per frame, HBM/L2-resident; entries hold position + 2 (the reference's index)
     uint32_t* const oLL = p.seqLL + (size_t)item * kEncSeqCap;
     uint32_t* const oML = p.seqML + (size_t)item * kEncSeqCap;
     uint32_t* const oOF = p.seqOF + (size_t)item * kEncSeqCap;
+    // block geometry: first block of a frame unless MB (then block `wave`, with the window and repcodes of the blocks before it)
+    int srcSize = active ? (int)it.srcSize : 64;     // end of the block
+    int ip0 = 1, anchor = 0, lowPos = 0;             // first position of a frame is skipped (:129)
+    uint32_t rep1 = 1, rep2 = 0, offsetSaved = 4;    // rep2 = 4 exceeds the history at frame start (:131-145)
+    if (MB && active) {
+        BlkGeom const bg = blk_geom(it.srcSize, it.windowLog, wave);
+        srcSize = bg.end; ip0 = bg.ip0; anchor = bg.B; lowPos = bg.lowPos;
+        rep1 = it.rep[0]; rep2 = it.rep[1]; offsetSaved = 0;
+        if (rep2 > bg.maxRep) { offsetSaved = rep2; rep2 = 0; }
+        if (rep1 > bg.maxRep) { offsetSaved = rep1; rep1 = 0; }
+    }
     int const ilimit = srcSize - 8;
-    int ip0 = 1, anchor = 0;                         // first position is skipped (:129)
-    uint32_t rep1 = 1, rep2 = 0;                     // rep2 = 4 exceeds the history at frame start (:131-145)
     uint32_t nseq = 0;
     int step = 2, nextStep = ip0 + 128, d = 2;       // _start
     bool afterMatch = false;                         // the greedy rep2 loop (:264-285) is still open at ip0
@@ -374,7 +410,7 @@ __global__ void __launch_bounds__(32) enc_match_group_kernel(EncPass p, const ui
         int const cl = lower ? 31 - __clz((int)lower) : (int)l;
         int const cq = __shfl_sync(FULL, q, gbase + cl);
         int const cand = lower ? cq : (int)tv - 2;                  // table stores position + 2, 0 = empty
-        bool const hit = vk && cand >= 0 && rd32(src + cand) == cur4;
+        bool const hit = vk && cand >= lowPos && rd32(src + cand) == cur4;   // idx >= prefixStartIndex
         uint32_t key = 0xFFFFFFFFu;                                 // 0: rep2 at ip0; 1 + 3k: repcode at ip2; 2 + 3k / 3 + 3k: hash hit at ip0 / ip1
         if (hit) key = 3 * k + 2 + odd;
         if (repHit) key = 3 * k + 1;
@@ -407,7 +443,7 @@ __global__ void __launch_bounds__(32) enc_match_group_kernel(EncPass p, const ui
             bool ext = type == 1 || type == 2;
             while (__any_sync(FULL, ext)) {
                 int const a = mpos - 1 - (int)l, b = msrc - 1 - (int)l;
-                bool const ok = ext && a >= anchor && b >= 0 && src[a] == src[b];
+                bool const ok = ext && a >= anchor && b >= lowPos && src[a] == src[b];     // ip0 > anchor and match0 > prefixStart before every step
                 uint32_t const okm = gballot(ok);
                 uint32_t const n = okm == LOW ? (uint32_t)GS : (uint32_t)__ffs((int)~okm) - 1u;
                 if (ext) { mpos -= (int)n; msrc -= (int)n; mlen += (int)n; ext = n == (uint32_t)GS; }
@@ -451,7 +487,10 @@ __global__ void __launch_bounds__(32) enc_match_group_kernel(EncPass p, const ui
         }
         __syncwarp();
     }
-    if (wi < nWork && l == 0) { it.nbSeq = nseq; it.lastLL = (uint32_t)(srcSize - anchor); }
+    if (wi < nWork && l == 0) {
+        it.nbSeq = nseq; it.lastLL = (uint32_t)(srcSize - anchor);
+        if (MB) { it.repNext[0] = rep1 ? rep1 : offsetSaved; it.repNext[1] = rep2 ? rep2 : offsetSaved; }     // :232-233
+    }
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -462,8 +501,8 @@ __global__ void __launch_bounds__(32) enc_match_group_kernel(EncPass p, const ui
 //  in position order: a probe sees earlier probes of its window through __match_any_sync and older positions
 //  through the tables, and writes are committed up to the first event only.
 // ------------------------------------------------------------------------------------------------------------
-template <int GS>
-__global__ void __launch_bounds__(32) enc_match_dfast_group_kernel(EncPass p, const uint32_t* __restrict__ workList, uint32_t nWork)
+template <int GS, bool MB>
+__global__ void __launch_bounds__(32) enc_match_dfast_group_kernel(EncPass p, const uint32_t* __restrict__ workList, uint32_t nWork, uint32_t wave)
 {
     constexpr uint32_t FULL = 0xFFFFFFFFu;
     constexpr int NG = 32 / GS;
@@ -475,16 +514,23 @@ __global__ void __launch_bounds__(32) enc_match_dfast_group_kernel(EncPass p, co
     uint32_t const item = workList[active ? wi : 0];
     EncItem& it = p.items[item];
     uint32_t const hBitsL = it.hashLog, hBitsS = it.chainLog, mls = it.minMatch;
-    int const srcSize = active ? (int)it.srcSize : 64;
-    const uint8_t* const src = p.src + it.srcOff;
+    const uint8_t* const src = p.src + it.srcOff;                 // frame start
     uint32_t* const TL = p.tables + it.tableOff;                  // long table (hash8), then short table (hash mls)
     uint32_t* const TS = TL + (1u << hBitsL);
     uint32_t* const oLL = p.seqLL + (size_t)item * kEncSeqCap;
     uint32_t* const oML = p.seqML + (size_t)item * kEncSeqCap;
     uint32_t* const oOF = p.seqOF + (size_t)item * kEncSeqCap;
+    int srcSize = active ? (int)it.srcSize : 64;     // end of the block
+    int ip = 1, anchor = 0, lowPos = 0;              // first position of a frame is skipped (:84)
+    uint32_t off1 = 1, off2 = 0, offsetSaved = 4;    // offset_2 = 4 exceeds the history at frame start
+    if (MB && active) {
+        BlkGeom const bg = blk_geom(it.srcSize, it.windowLog, wave);
+        srcSize = bg.end; ip = bg.ip0; anchor = bg.B; lowPos = bg.lowPos;
+        off1 = it.rep[0]; off2 = it.rep[1]; offsetSaved = 0;
+        if (off2 > bg.maxRep) { offsetSaved = off2; off2 = 0; }
+        if (off1 > bg.maxRep) { offsetSaved = off1; off1 = 0; }
+    }
     int const ilimit = srcSize - 8;
-    int ip = 1, anchor = 0;                          // first position is skipped (:84)
-    uint32_t off1 = 1, off2 = 0;                     // offset_2 = 4 exceeds the history at frame start
     uint32_t nseq = 0;
     int step = 1, nextStep = ip + 256;
     bool afterMatch = false;
@@ -538,8 +584,8 @@ __global__ void __launch_bounds__(32) enc_match_dfast_group_kernel(EncPass p, co
         int const fl = lowL ? 31 - __clz((int)lowL) : (int)l, fs = lowS ? 31 - __clz((int)lowS) : (int)l;
         int const pfl = __shfl_sync(FULL, pj, gbase + fl), pfs = __shfl_sync(FULL, pj, gbase + fs);
         int const candL = lowL ? pfl : (int)tl - 2, candS = lowS ? pfs : (int)ts - 2;     // tables store position + 2; valid iff index > 2
-        bool const Lhit = rdok && candL >= 1 && rd64(src + candL) == x;
-        bool const Shit = probe && candS >= 1 && rd32(src + candS) == (uint32_t)x;
+        bool const Lhit = rdok && candL > lowPos && rd64(src + candL) == x;          // idx > prefixLowestIndex
+        bool const Shit = probe && candS > lowPos && rd32(src + candS) == (uint32_t)x;
         uint32_t key = 0xFFFFFFFFu;                                 // 0: offset_2 repeat at ip; 1+3j: repcode at ip+1; 2+3j: long at ip; 3+3j: short at ip
         if (probe) { if (Shit) key = 3 * l + 3; if (Lhit) key = 3 * l + 2; if (repHit) key = 3 * l + 1; }
         if (r2hit) key = 0;
@@ -581,7 +627,7 @@ __global__ void __launch_bounds__(32) enc_match_dfast_group_kernel(EncPass p, co
             bool ext = bext;
             while (__any_sync(FULL, ext)) {
                 int const a = mpos - 1 - (int)l, b = msrc - 1 - (int)l;
-                bool const ok = ext && a >= anchor && b >= 0 && src[a] == src[b];     // ip > anchor and match > prefixLowest before every step
+                bool const ok = ext && a >= anchor && b >= lowPos && src[a] == src[b];     // ip > anchor and match > prefixLowest before every step
                 uint32_t const okm = gballot(ok);
                 uint32_t const n = okm == LOW ? (uint32_t)GS : (uint32_t)__ffs((int)~okm) - 1u;
                 if (ext) { mpos -= (int)n; msrc -= (int)n; mlen += (int)n; ext = n == (uint32_t)GS; }
@@ -613,25 +659,30 @@ __global__ void __launch_bounds__(32) enc_match_dfast_group_kernel(EncPass p, co
         }
         __syncwarp();
     }
-    if (wi < nWork && l == 0) { it.nbSeq = nseq; it.lastLL = (uint32_t)(srcSize - anchor); }
+    if (wi < nWork && l == 0) {
+        it.nbSeq = nseq; it.lastLL = (uint32_t)(srcSize - anchor);
+        if (MB) { it.repNext[0] = off1 ? off1 : offsetSaved; it.repNext[1] = off2 ? off2 : offsetSaved; }     // :215-216
+    }
 }
 
-// Serial restatement (one lane per chunk): used for chunks below 64 bytes only; everything else goes to the group kernels.
-__global__ void __launch_bounds__(32) enc_match_kernel(EncPass p, const uint32_t* __restrict__ workList, uint32_t nWork)
+// Serial restatement (one lane per block): used for blocks below 64 bytes only; everything else goes to the group kernels.
+__global__ void __launch_bounds__(32) enc_match_kernel(EncPass p, const uint32_t* __restrict__ workList, uint32_t nWork, uint32_t wave)
 {
     uint32_t const w = blockIdx.x * blockDim.x + threadIdx.x;
     if (w >= nWork) return;
     uint32_t const i = workList[w];
     EncItem& it = p.items[i];
-    it.nbSeq = 0; it.lastLL = it.srcSize;
-    if (it.srcSize < 7 || it.srcSize > kBlockSizeMax) return;      // ZSTD_buildSeqStore: srcSize < MIN_CBLOCK_SIZE+blockHeader+1 -> noCompress (:3438)
+    BlkGeom const bg = blk_geom(it.srcSize, it.windowLog, wave);
+    it.nbSeq = 0; it.lastLL = (uint32_t)(bg.end - bg.B);
+    if (bg.end - bg.B < 7) return;      // ZSTD_buildSeqStore: srcSize < MIN_CBLOCK_SIZE+blockHeader+1 -> noCompress (:3438)
     SeqWriter sw{p.seqLL + (size_t)i * kEncSeqCap, p.seqML + (size_t)i * kEncSeqCap, p.seqOF + (size_t)i * kEncSeqCap, 0};
     const uint8_t* const src = p.src + it.srcOff;
     uint32_t* const tab = p.tables + it.tableOff;
+    uint32_t rep[2] = {it.rep[0], it.rep[1]};
     uint32_t lastLL;
-    if (it.strategy == 1) lastLL = match_fast(tab, it.hashLog, it.minMatch, src, it.srcSize, sw);
-    else lastLL = match_dfast(tab, it.hashLog, tab + (1u << it.hashLog), it.chainLog, it.minMatch, src, it.srcSize, sw);
-    it.nbSeq = sw.n; it.lastLL = lastLL;
+    if (it.strategy == 1) lastLL = match_fast(tab, it.hashLog, it.minMatch, src, bg, rep, sw);
+    else lastLL = match_dfast(tab, it.hashLog, tab + (1u << it.hashLog), it.chainLog, it.minMatch, src, bg, rep, sw);
+    it.nbSeq = sw.n; it.lastLL = lastLL; it.repNext[0] = rep[0]; it.repNext[1] = rep[1];
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -1078,34 +1129,47 @@ __device__ __forceinline__ void put_bits(uint32_t* w, uint64_t bit, uint32_t v, 
     if (sh + nb > 32) atomicOr(&w[(bit >> 5) + 1], (uint32_t)(x >> 32));
 }
 
-__global__ void __launch_bounds__(kEntThreads, 15) enc_entropy_kernel(EncPass p)
+// MB = false: every frame is one block (srcSize <= 128 KiB), one CTA per frame, no state.  MB = true: the CTA handles block
+// `wave` of frame workList[blockIdx.x]; the frame's write cursor, confirmed repcodes and previous Huffman table live in
+// EncItem / hufState and are advanced here (ZSTD_compress_frameChunk :4690, ZSTD_compressBlock_internal :4528,
+// ZSTD_blockState_confirmRepcodesAndEntropyTables).  Without a dictionary and below ZSTD_lazy the FSE tables never repeat
+// (ZSTD_selectEncodingType returns set_repeat only for FSE_repeat_valid), so the Huffman table is the only entropy state.
+template <bool MB>
+__global__ void __launch_bounds__(kEntThreads, MB ? 8 : 15) enc_entropy_kernel(EncPass p, const uint32_t* __restrict__ workList, uint32_t wave)
 {
     __shared__ EntShared S;
-    uint32_t const item = blockIdx.x, tid = threadIdx.x;
+    uint32_t const item = MB ? workList[blockIdx.x] : blockIdx.x, tid = threadIdx.x;
     EncItem& it = p.items[item];
-    const uint8_t* const src = p.src + it.srcOff;
-    uint8_t* const dst = p.dst + it.dstOff;                    // 16-byte aligned slot of compressBound(srcSize) bytes
+    uint32_t const frameSize = it.srcSize;
+    uint32_t const blkStart = MB ? wave * kBlockSizeMax : 0u;
+    const uint8_t* const src = p.src + it.srcOff + blkStart;   // the block
+    uint8_t* const dst = p.dst + it.dstOff;                    // 16-byte aligned slot of compressBound(frameSize) bytes
     uint32_t* const dstW = (uint32_t*)dst;
-    uint32_t const srcSize = it.srcSize;
-    if (srcSize > kBlockSizeMax) { if (tid == 0) p.results[item] = make_error(kSrcSizeWrong); return; }
-    // ---- frame header: ZSTD_writeFrameHeader (ZstdCompress.cs:4817), contentSizeFlag = 1, no dictID, no checksum ----
-    uint32_t fhSize;
-    {
-        uint32_t const fcsCode = (srcSize >= 256) + (srcSize >= 65536 + 256);
-        fhSize = 4 + 1 + (fcsCode == 0 ? 1 : (fcsCode == 1 ? 2 : 4));      // singleSegment always holds: windowSize >= srcSize
+    uint32_t const srcSize = MB ? min(kBlockSizeMax, frameSize - blkStart) : frameSize;     // block size
+    bool const firstBlock = !MB || wave == 0, lastBlock = !MB || blkStart + srcSize == frameSize;
+    if (!MB && srcSize > kBlockSizeMax) { if (tid == 0) p.results[item] = make_error(kSrcSizeWrong); return; }
+    // ---- frame header: ZSTD_writeFrameHeader (ZstdCompress.cs:4817), contentSizeFlag = 1, no dictID ----
+    uint32_t fhSize = 0;
+    if (firstBlock) {
+        uint32_t const fcsCode = (frameSize >= 256) + (frameSize >= 65536 + 256);
+        bool const singleSegment = !MB || ((1u << it.windowLog) >= frameSize);     // windowSize >= pledgedSrcSize (:4823); always for one-block frames
+        fhSize = 4 + 1 + (singleSegment ? 0 : 1) + (fcsCode == 0 ? (singleSegment ? 1 : 0) : (fcsCode == 1 ? 2 : 4));
         if (tid == 0) {
             dst[0] = 0x28; dst[1] = 0xB5; dst[2] = 0x2F; dst[3] = 0xFD;
-            dst[4] = (uint8_t)((p.checksumFlag ? 4u : 0u) + (1u << 5) + (fcsCode << 6));   // FHD: checksum bit 2, singleSegment bit 5, fcsID bits 6-7 (:4823-4829)
-            if (fcsCode == 0) dst[5] = (uint8_t)srcSize;
-            else if (fcsCode == 1) { uint32_t const v = srcSize - 256; dst[5] = (uint8_t)v; dst[6] = (uint8_t)(v >> 8); }
-            else { dst[5] = (uint8_t)srcSize; dst[6] = (uint8_t)(srcSize >> 8); dst[7] = (uint8_t)(srcSize >> 16); dst[8] = (uint8_t)(srcSize >> 24); }
+            dst[4] = (uint8_t)((p.checksumFlag ? 4u : 0u) + ((singleSegment ? 1u : 0u) << 5) + (fcsCode << 6));   // FHD: checksum bit 2, singleSegment bit 5, fcsID bits 6-7 (:4823-4829)
+            uint32_t pos = 5;
+            if (!singleSegment) dst[pos++] = (uint8_t)((it.windowLog - 10) << 3);
+            if (fcsCode == 0) { if (singleSegment) dst[pos++] = (uint8_t)frameSize; }
+            else if (fcsCode == 1) { uint32_t const v = frameSize - 256; dst[pos] = (uint8_t)v; dst[pos + 1] = (uint8_t)(v >> 8); }
+            else { dst[pos] = (uint8_t)frameSize; dst[pos + 1] = (uint8_t)(frameSize >> 8); dst[pos + 2] = (uint8_t)(frameSize >> 16); dst[pos + 3] = (uint8_t)(frameSize >> 24); }
         }
     }
-    uint8_t* const blk = dst + fhSize;                          // block header goes here
-    uint32_t const payload = fhSize + 3;                        // byte offset of the block content
-    bool raw = false;
+    uint32_t const blkPos = firstBlock ? fhSize : it.outPos;    // block header goes here
+    uint8_t* const blk = dst + blkPos;
+    uint32_t const payload = blkPos + 3;                        // byte offset of the block content
+    bool raw = false, rle = false, newHuf = false;
     uint32_t cSize = 0;
-    if (srcSize == 0) {                                         // ZSTD_writeEpilogue: one empty last raw block (:5621-5631)
+    if (frameSize == 0) {                                       // ZSTD_writeEpilogue: one empty last raw block (:5621-5631)
         if (tid == 0) {
             blk[0] = 1; blk[1] = 0; blk[2] = 0;
             uint32_t total = fhSize + 3;
@@ -1187,15 +1251,40 @@ __global__ void __launch_bounds__(kEntThreads, 15) enc_entropy_kernel(EncPass p)
                 if (largest == litSize) litMode = 1;                              // all same byte -> rle (HufCompress.cs:1458)
                 else if (largest <= (litSize >> 7) + 4) litMode = 0;              // not compressible enough (:1463)
                 else {
-                    if (tid == 0) {
-                        uint32_t huffLog = fse_optimal_table_log(11, litSize, maxSym, 1);       // HUF_optimalTableLog :12
-                        huffLog = huf_build_ctable(S, maxSym, huffLog);
-                        S.hufLog = huffLog;
-                        S.hSize = huffLog > 12 ? 0 : huf_write_ctable(S, maxSym, huffLog);
+                    // HUF_repeat (HufCompress.cs:1475-1530): the previous block's table may be reused (literals header type set_repeat, no
+                    // table description).  repeatMode is `check` after any block that shipped a new table; `valid` needs a dictionary.
+                    bool useOld = false;
+                    uint32_t repeat = MB ? it.hufRepeat : 0u;
+                    const uint8_t* const oldNb = p.hufState + ((size_t)item * 2 + (MB ? it.hufCur : 0u)) * kHufStateSlot;
+                    if (MB && repeat) {
+                        int bad = 0;                                               // HUF_validateCTable: every present symbol has a code
+                        for (uint32_t q = tid; q <= maxSym; q += kEntThreads) bad |= (S.count[q] != 0) & (oldNb[q] == 0);
+                        if (__syncthreads_or(bad)) repeat = 0;
+                        if (repeat && litSize <= 1024) useOld = true;              // preferRepeat (ZstdCompressLiterals.cs:121)
                     }
-                    __syncthreads();
-                    uint32_t const hSize = S.hSize;
-                    if (hSize == 0 || hSize + 12 >= litSize) litMode = 0;          // (:1525-1528)
+                    if (!useOld) {
+                        if (tid == 0) {
+                            uint32_t huffLog = fse_optimal_table_log(11, litSize, maxSym, 1);       // HUF_optimalTableLog :12
+                            huffLog = huf_build_ctable(S, maxSym, huffLog);
+                            S.hufLog = huffLog;
+                            S.hSize = huffLog > 12 ? 0 : huf_write_ctable(S, maxSym, huffLog);
+                        }
+                        __syncthreads();
+                        if (MB && repeat && S.hSize != 0) {                        // old table vs header + new table (:1511-1520)
+                            uint32_t o = 0, nw = 0, totO, totN;
+                            for (uint32_t q = tid; q <= maxSym; q += kEntThreads) { uint32_t const c = S.count[q]; o += oldNb[q] * c; nw += S.hufNbBits[q] * c; }
+                            ent_scan_excl(o, S.scanA, &totO); ent_scan_excl(nw, S.scanB, &totN);
+                            if ((totO >> 3) <= S.hSize + (totN >> 3) || S.hSize + 12 >= litSize) useOld = true;
+                        }
+                    }
+                    if (MB && useOld) {
+                        const uint16_t* const oldVal = (const uint16_t*)(oldNb + 256);
+                        __syncthreads();
+                        for (uint32_t q = tid; q < 256; q += kEntThreads) { S.hufNbBits[q] = oldNb[q]; S.hufValue[q] = oldVal[q]; }
+                        __syncthreads();
+                    }
+                    uint32_t const hSize = useOld ? 0u : S.hSize;
+                    if (!useOld && (hSize == 0 || hSize + 12 >= litSize)) litMode = 0;          // (:1525-1528)
                     else {
                         // stream sizes from the per-segment histograms
                         uint32_t const nStreams = singleStream ? 1 : 4;
@@ -1243,12 +1332,18 @@ __global__ void __launch_bounds__(kEntThreads, 15) enc_entropy_kernel(EncPass p)
                                 strOff += sz[k];
                             }
                             __syncthreads();
+                            if (MB && !useOld) {            // nextCBlock's table: becomes prevCBlock's if this block is confirmed
+                                uint8_t* const nNb = p.hufState + ((size_t)item * 2 + (it.hufCur ^ 1u)) * kHufStateSlot; uint16_t* const nVal = (uint16_t*)(nNb + 256);
+                                for (uint32_t q = tid; q < 256; q += kEntThreads) { nNb[q] = S.hufNbBits[q]; nVal[q] = S.hufValue[q]; }
+                                newHuf = true;
+                            }
                             if (tid == 0) {
                                 uint8_t* o = dst + payload;
                                 uint32_t const cLitSize = total;
-                                if (lhSize == 3) { uint32_t const lhc = 2 + ((!singleStream) << 2) + (litSize << 4) + (cLitSize << 14); o[0] = (uint8_t)lhc; o[1] = (uint8_t)(lhc >> 8); o[2] = (uint8_t)(lhc >> 16); }
-                                else if (lhSize == 4) { uint32_t const lhc = 2 + (2 << 2) + (litSize << 4) + (cLitSize << 18); o[0] = (uint8_t)lhc; o[1] = (uint8_t)(lhc >> 8); o[2] = (uint8_t)(lhc >> 16); o[3] = (uint8_t)(lhc >> 24); }
-                                else { uint32_t const lhc = 2 + (3 << 2) + (litSize << 4) + (cLitSize << 22); o[0] = (uint8_t)lhc; o[1] = (uint8_t)(lhc >> 8); o[2] = (uint8_t)(lhc >> 16); o[3] = (uint8_t)(lhc >> 24); o[4] = (uint8_t)(cLitSize >> 10); }
+                                uint32_t const hType = useOld ? 3u : 2u;           // set_repeat / set_compressed
+                                if (lhSize == 3) { uint32_t const lhc = hType + ((!singleStream) << 2) + (litSize << 4) + (cLitSize << 14); o[0] = (uint8_t)lhc; o[1] = (uint8_t)(lhc >> 8); o[2] = (uint8_t)(lhc >> 16); }
+                                else if (lhSize == 4) { uint32_t const lhc = hType + (2 << 2) + (litSize << 4) + (cLitSize << 18); o[0] = (uint8_t)lhc; o[1] = (uint8_t)(lhc >> 8); o[2] = (uint8_t)(lhc >> 16); o[3] = (uint8_t)(lhc >> 24); }
+                                else { uint32_t const lhc = hType + (3 << 2) + (litSize << 4) + (cLitSize << 22); o[0] = (uint8_t)lhc; o[1] = (uint8_t)(lhc >> 8); o[2] = (uint8_t)(lhc >> 16); o[3] = (uint8_t)(lhc >> 24); o[4] = (uint8_t)(cLitSize >> 10); }
                                 for (uint32_t k = 0; k < hSize; k++) o[lhSize + k] = S.hdr[k];
                                 if (!singleStream) { uint8_t* j = o + lhSize + hSize; j[0] = (uint8_t)sz[0]; j[1] = (uint8_t)(sz[0] >> 8); j[2] = (uint8_t)sz[1]; j[3] = (uint8_t)(sz[1] >> 8); j[4] = (uint8_t)sz[2]; j[5] = (uint8_t)(sz[2] >> 8); }
                                 S.litSectionSize = lhSize + cLitSize;
@@ -1450,24 +1545,47 @@ __global__ void __launch_bounds__(kEntThreads, 15) enc_entropy_kernel(EncPass p)
         if (cSize >= srcSize - ((srcSize >> 6) + 2)) raw = true;
     }
     __syncthreads();
+    // ZSTD_compressBlock_internal :4563-4568: after the first block, a block of one repeated byte whose compressed form is tiny becomes an RLE block
+    if (MB && !firstBlock && srcSize >= 7 && (raw ? 0u : cSize) < 25) {
+        int diff = 0; uint8_t const b0 = src[0];
+        for (uint32_t k = tid; k < srcSize; k += kEntThreads) diff |= src[k] != b0;
+        if (!__syncthreads_or(diff)) { rle = true; raw = false; }
+    }
+    uint32_t const lastBit = lastBlock ? 1u : 0u;
     uint32_t total;
     if (raw) {          // ZSTD_noCompressBlock (ZstdCompressInternal.cs:102)
         for (uint32_t k = tid; k < srcSize; k += kEntThreads) dst[payload + k] = src[k];
         if (tid == 0) {
-            uint32_t const h = 1 + (0u << 1) + (srcSize << 3);
+            uint32_t const h = lastBit + (0u << 1) + (srcSize << 3);
             blk[0] = (uint8_t)h; blk[1] = (uint8_t)(h >> 8); blk[2] = (uint8_t)(h >> 16);
         }
         total = payload + srcSize;
+    } else if (rle) {   // bt_rle: one byte of content, the header carries the regenerated size (:4750)
+        if (tid == 0) {
+            uint32_t const h = lastBit + (1u << 1) + (srcSize << 3);
+            blk[0] = (uint8_t)h; blk[1] = (uint8_t)(h >> 8); blk[2] = (uint8_t)(h >> 16);
+            dst[payload] = src[0];
+        }
+        total = payload + 1;
     } else {
         if (tid == 0) {
-            uint32_t const h = 1 + (2u << 1) + (cSize << 3);
+            uint32_t const h = lastBit + (2u << 1) + (cSize << 3);
             blk[0] = (uint8_t)h; blk[1] = (uint8_t)(h >> 8); blk[2] = (uint8_t)(h >> 16);
         }
         total = payload + cSize;
     }
-    // ZSTD_writeEpilogue (:5641-5652): optional content checksum, hashed by warp 0
+    if (MB && tid == 0) {
+        // ZSTD_blockState_confirmRepcodesAndEntropyTables (:4575): only a compressed block (cSize > 1) moves the repcodes and the Huffman table on
+        if (!raw && !rle) {
+            it.rep[0] = it.repNext[0]; it.rep[1] = it.repNext[1];
+            if (newHuf) { it.hufCur ^= 1u; it.hufRepeat = 1u; }
+        }
+        it.outPos = total;
+    }
+    if (!lastBlock) return;
+    // ZSTD_writeEpilogue (:5641-5652): optional content checksum over the whole frame, hashed by warp 0
     if (p.checksumFlag && tid < 32) {
-        uint32_t const c = (uint32_t)xxh64_warp(src, srcSize, tid);
+        uint32_t const c = (uint32_t)xxh64_warp(p.src + it.srcOff, frameSize, tid);
         if (tid == 0) { dst[total] = (uint8_t)c; dst[total + 1] = (uint8_t)(c >> 8); dst[total + 2] = (uint8_t)(c >> 16); dst[total + 3] = (uint8_t)(c >> 24); }
     }
     if (tid == 0) p.results[item] = total + (p.checksumFlag ? 4u : 0u);
@@ -1492,7 +1610,7 @@ struct HBuf { void* p = nullptr; size_t cap = 0;
     void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; } };
 
 struct EncArenaImpl {
-    DBuf items, tables, seqLL, seqML, seqOF, lit, stateBits, results, compact, cSrcOff, cSizes, cDstOff, workLists;
+    DBuf items, tables, seqLL, seqML, seqOF, lit, stateBits, results, compact, cSrcOff, cSizes, cDstOff, workLists, hufState;
     HBuf hItems, hResults, hC, hWork;
     cudaEvent_t copied = nullptr;
     EncArenaImpl() { cudaEventCreateWithFlags(&copied, cudaEventDisableTiming); }
@@ -1500,10 +1618,11 @@ struct EncArenaImpl {
 };
 static thread_local std::string t_encErr;
 const char* enc_last_error() { return t_encErr.c_str(); }
+size_t enc_max_frame_bytes() { return kEncMaxFrameBytes; }
 void EncArena::release()
 {
     if (!impl) return;
-    DBuf* d[] = {&impl->items, &impl->tables, &impl->seqLL, &impl->seqML, &impl->seqOF, &impl->lit, &impl->stateBits, &impl->results, &impl->compact, &impl->cSrcOff, &impl->cSizes, &impl->cDstOff, &impl->workLists};
+    DBuf* d[] = {&impl->items, &impl->tables, &impl->seqLL, &impl->seqML, &impl->seqOF, &impl->lit, &impl->stateBits, &impl->results, &impl->compact, &impl->cSrcOff, &impl->cSizes, &impl->cDstOff, &impl->workLists, &impl->hufState};
     for (auto* b : d) b->release();
     impl->hItems.release(); impl->hResults.release(); impl->hC.release(); impl->hWork.release();
     delete impl; impl = nullptr;
@@ -1514,11 +1633,15 @@ const uint8_t* EncArena::compactBuf() const { return impl ? (const uint8_t*)impl
 
 constexpr size_t kEncMaxItemsPerPass = 8192;
 
-// Queues one pass (m <= kEncMaxItemsPerPass chunks) without waiting: the chunk descriptors and work lists are copied on
-// `copyStream` (pass the stream that carries the bulk H2D of the same chunks, so that the small copies do not queue
+// Queues one pass (m <= kEncMaxItemsPerPass frames) without waiting: the frame descriptors and work lists are copied on
+// `copyStream` (pass the stream that carries the bulk H2D of the same frames, so that the small copies do not queue
 // behind later bulk transfers; `stream` must then wait for that stream's event before this call), all kernels
-// run on `stream`, and the per-chunk results are written straight into pinned host memory (enc_results).
-// ev3 (optional): [0] before the match finder, [1] after it, [2] after the entropy stage.
+// run on `stream`, and the per-frame results are written straight into pinned host memory (enc_results).
+// Frames of at most 128 KiB (the batch shape of BASELINE.json) take one match launch and one entropy launch.  If the pass
+// holds larger frames, it runs in waves: wave b = block b of every frame that has one, match finder then entropy stage,
+// because block b+1 of a frame needs the hash table, the confirmed repcodes and the Huffman table that block b leaves behind
+// (ZSTD_compress_frameChunk, ZstdCompress.cs:4690).  A frame is a serial chain of ~25 ms per block; the batch is what is parallel.
+// ev3 (optional): [0] before the match finder, [1] after it (first wave), [2] after the last entropy stage.
 bool enc_enqueue(EncArena& A, cudaStream_t stream, cudaStream_t copyStream, size_t m, int level, int checksumFlag,
                  const uint8_t* d_src, const uint64_t* srcOff, const size_t* srcSize,
                  uint8_t* d_dst, const uint64_t* dstOff, const size_t* dstCap, cudaEvent_t* ev3, unsigned* launches)
@@ -1527,33 +1650,67 @@ bool enc_enqueue(EncArena& A, cudaStream_t stream, cudaStream_t copyStream, size
     EncArenaImpl& I = *A.impl;
     if (m > kEncMaxItemsPerPass) { t_encErr = "pass too large"; return false; }
     if (!I.hItems.ensure(m * sizeof(EncItem)) || !I.items.ensure(m * sizeof(EncItem)) || !I.hResults.ensure(m * 8)) { t_encErr = "out of memory (items)"; return false; }
-    if (!I.hWork.ensure(m * 12) || !I.workLists.ensure(m * 12)) { t_encErr = "out of memory (work lists)"; return false; }
     EncItem* hi = (EncItem*)I.hItems.p;
-    uint32_t* const fastList = (uint32_t*)I.hWork.p; uint32_t* const serialList = fastList + m; uint32_t* const dfastList = serialList + m;
-    uint32_t nFast = 0, nSerial = 0, nDfast = 0;
-    size_t tableEntries = 0;
+    uint64_t* const hr = (uint64_t*)I.hResults.p;
+    size_t tableEntries = 0, maxWaves = 1, totalBlocks = 0;
+    bool mb = false;
+    std::vector<uint32_t> nBlk(m);
     for (size_t i = 0; i < m; i++) {
         size_t const ss = srcSize[i];
         EncItem& e = hi[i];
         memset(&e, 0, sizeof(e));
         e.srcOff = srcOff[i]; e.dstOff = dstOff[i];
         e.srcSize = (uint32_t)std::min<size_t>(ss, 0xFFFFFFF0u); e.dstCap = (uint32_t)std::min<size_t>(dstCap[i], 0xFFFFFFF0u);
-        CParams const c = get_cparams(level, std::min<size_t>(ss, kBlockSizeMax));
+        CParams const c = get_cparams(level, ss);
         e.windowLog = c.windowLog; e.hashLog = c.hashLog; e.chainLog = c.chainLog; e.minMatch = c.minMatch; e.strategy = c.strategy;
-        e.nbSeq = 0; e.lastLL = e.srcSize;
-        if (ss < 7 || ss > kBlockSizeMax) continue;              // raw block / unsupported: no match finding
-        // group kernels (16 lanes per chunk) for ZSTD_fast and ZSTD_dfast; chunks below 64 bytes take the serial lane kernel
-        if (ss >= 64 && c.strategy == 1) fastList[nFast++] = (uint32_t)i;
-        else if (ss >= 64 && c.strategy == 2) dfastList[nDfast++] = (uint32_t)i;
-        else serialList[nSerial++] = (uint32_t)i;
+        e.nbSeq = 0; e.lastLL = (uint32_t)std::min<size_t>(ss, kBlockSizeMax);
+        e.rep[0] = 1; e.rep[1] = 4;                               // repStartValue (ZstdInternal.cs:13)
+        if (ss > kEncMaxFrameBytes) { nBlk[i] = 0; hr[i] = make_error(kSrcSizeWrong); mb = true; continue; }   // positions are 31-bit
+        nBlk[i] = ss <= kBlockSizeMax ? 1u : (uint32_t)((ss + kBlockSizeMax - 1) / kBlockSizeMax);
+        if (nBlk[i] > 1) mb = true;
+        maxWaves = std::max<size_t>(maxWaves, nBlk[i]); totalBlocks += nBlk[i];
+        if (ss < 7) continue;                                     // raw block: no match finding, no table
         e.tableOff = (uint32_t)tableEntries;
         tableEntries += ((size_t)1 << c.hashLog) + (c.strategy == 2 ? ((size_t)1 << c.chainLog) : 0);
     }
     if (tableEntries >= 0xFFFFFFFFull) { t_encErr = "hash-table arena exceeds 32-bit indexing"; return false; }
+    // work lists: per wave [ZSTD_fast groups | serial | ZSTD_dfast groups | entropy]; blocks of 64 bytes and more take the group kernels
+    struct WaveLists { size_t off[4]; uint32_t n[4]; };
+    std::vector<WaveLists> waves(maxWaves);
+    size_t const listCap = 2 * totalBlocks + 4;
+    if (!I.hWork.ensure(listCap * 4) || !I.workLists.ensure(listCap * 4)) { t_encErr = "out of memory (work lists)"; return false; }
+    uint32_t* const hw = (uint32_t*)I.hWork.p;
+    {
+        std::vector<uint32_t> alive; alive.reserve(m);
+        for (size_t i = 0; i < m; i++) if (nBlk[i]) alive.push_back((uint32_t)i);
+        size_t pos = 0;
+        std::vector<uint32_t> tmp[4];
+        for (size_t b = 0; b < maxWaves; b++) {
+            for (auto& t : tmp) t.clear();
+            size_t keep = 0;
+            for (size_t q = 0; q < alive.size(); q++) {
+                uint32_t const i = alive[q];
+                if (nBlk[i] <= b) continue;
+                alive[keep++] = i;
+                size_t const ss = srcSize[i];
+                size_t const bs = std::min<size_t>(kBlockSizeMax, ss - b * (size_t)kBlockSizeMax);
+                tmp[3].push_back(i);
+                if (ss < 7 || bs < 7) continue;                   // ZSTD_buildSeqStore: noCompress (:3438)
+                if (bs >= 64) tmp[hi[i].strategy == 1 ? 0 : 2].push_back(i); else tmp[1].push_back(i);
+            }
+            alive.resize(keep);
+            for (int k = 0; k < 4; k++) {
+                waves[b].off[k] = pos; waves[b].n[k] = (uint32_t)tmp[k].size();
+                if (!tmp[k].empty()) memcpy(hw + pos, tmp[k].data(), tmp[k].size() * 4);
+                pos += tmp[k].size();
+            }
+        }
+    }
     if (!I.tables.ensure(tableEntries * 4 + 16) || !I.seqLL.ensure(m * (size_t)kEncSeqCap * 4) || !I.seqML.ensure(m * (size_t)kEncSeqCap * 4) ||
-        !I.seqOF.ensure(m * (size_t)kEncSeqCap * 4) || !I.lit.ensure(m * (size_t)kEncLitStride) || !I.stateBits.ensure(m * (size_t)kEncSeqCap * 8)) { t_encErr = "out of memory (arena)"; return false; }
+        !I.seqOF.ensure(m * (size_t)kEncSeqCap * 4) || !I.lit.ensure(m * (size_t)kEncLitStride) || !I.stateBits.ensure(m * (size_t)kEncSeqCap * 8) ||
+        (mb && !I.hufState.ensure(m * 2 * (size_t)kHufStateSlot))) { t_encErr = "out of memory (arena)"; return false; }
     ENC_CUDA(cudaMemcpyAsync(I.items.p, hi, m * sizeof(EncItem), cudaMemcpyHostToDevice, copyStream));
-    ENC_CUDA(cudaMemcpyAsync(I.workLists.p, I.hWork.p, m * 12, cudaMemcpyHostToDevice, copyStream));
+    ENC_CUDA(cudaMemcpyAsync(I.workLists.p, I.hWork.p, listCap * 4, cudaMemcpyHostToDevice, copyStream));
     if (copyStream != stream) {                                   // order the kernels after the two small copies
         ENC_CUDA(cudaEventRecord(I.copied, copyStream));
         ENC_CUDA(cudaStreamWaitEvent(stream, I.copied, 0));
@@ -1563,15 +1720,30 @@ bool enc_enqueue(EncArena& A, cudaStream_t stream, cudaStream_t copyStream, size
     EncPass p;
     p.items = (EncItem*)I.items.p; p.nItems = (uint32_t)m; p.src = d_src; p.dst = d_dst; p.tables = (uint32_t*)I.tables.p;
     p.seqLL = (uint32_t*)I.seqLL.p; p.seqML = (uint32_t*)I.seqML.p; p.seqOF = (uint32_t*)I.seqOF.p; p.litBuf = (uint8_t*)I.lit.p;
-    p.stateBits = (uint64_t*)I.stateBits.p; p.results = (uint64_t*)I.hResults.p; p.checksumFlag = checksumFlag ? 1u : 0u;
-    // lanes per chunk: 16 measured best for ZSTD_fast (8: 49/52 ms, 16: 42/49 ms, 32: 63/72 ms per GiB Silesia-mix / text)
-    if (nFast) enc_match_group_kernel<16><<<(nFast + 1) / 2, 32, 0, stream>>>(p, (const uint32_t*)I.workLists.p, nFast);
-    if (nSerial) enc_match_kernel<<<(nSerial + 31) / 32, 32, 0, stream>>>(p, (const uint32_t*)I.workLists.p + m, nSerial);
-    if (nDfast) enc_match_dfast_group_kernel<16><<<(nDfast + 1) / 2, 32, 0, stream>>>(p, (const uint32_t*)I.workLists.p + 2 * m, nDfast);
-    if (ev3) ENC_CUDA(cudaEventRecord(ev3[1], stream));
-    enc_entropy_kernel<<<(unsigned)m, kEntThreads, 0, stream>>>(p);
+    p.stateBits = (uint64_t*)I.stateBits.p; p.results = hr; p.hufState = (uint8_t*)I.hufState.p; p.checksumFlag = checksumFlag ? 1u : 0u;
+    const uint32_t* const dw = (const uint32_t*)I.workLists.p;
+    *launches += tableEntries ? 1 : 0;
+    for (size_t b = 0; b < maxWaves; b++) {
+        WaveLists const& w = waves[b];
+        uint32_t const wave = (uint32_t)b;
+        // lanes per chunk: 16 measured best for ZSTD_fast (8: 49/52 ms, 16: 42/49 ms, 32: 63/72 ms per GiB Silesia-mix / text)
+        if (mb) {
+            if (w.n[0]) enc_match_group_kernel<16, true><<<(w.n[0] + 1) / 2, 32, 0, stream>>>(p, dw + w.off[0], w.n[0], wave);
+            if (w.n[1]) enc_match_kernel<<<(w.n[1] + 31) / 32, 32, 0, stream>>>(p, dw + w.off[1], w.n[1], wave);
+            if (w.n[2]) enc_match_dfast_group_kernel<16, true><<<(w.n[2] + 1) / 2, 32, 0, stream>>>(p, dw + w.off[2], w.n[2], wave);
+            if (ev3 && b == 0) ENC_CUDA(cudaEventRecord(ev3[1], stream));
+            if (w.n[3]) enc_entropy_kernel<true><<<w.n[3], kEntThreads, 0, stream>>>(p, dw + w.off[3], wave);
+        } else {
+            if (w.n[0]) enc_match_group_kernel<16, false><<<(w.n[0] + 1) / 2, 32, 0, stream>>>(p, dw + w.off[0], w.n[0], 0u);
+            if (w.n[1]) enc_match_kernel<<<(w.n[1] + 31) / 32, 32, 0, stream>>>(p, dw + w.off[1], w.n[1], 0u);
+            if (w.n[2]) enc_match_dfast_group_kernel<16, false><<<(w.n[2] + 1) / 2, 32, 0, stream>>>(p, dw + w.off[2], w.n[2], 0u);
+            if (ev3) ENC_CUDA(cudaEventRecord(ev3[1], stream));
+            enc_entropy_kernel<false><<<(unsigned)m, kEntThreads, 0, stream>>>(p, dw, 0u);
+        }
+        *launches += (w.n[0] ? 1 : 0) + (w.n[1] ? 1 : 0) + (w.n[2] ? 1 : 0) + ((mb ? w.n[3] : 1) ? 1 : 0);
+    }
     if (ev3) ENC_CUDA(cudaEventRecord(ev3[2], stream));
-    *launches += 1 + (nSerial ? 1 : 0) + (nFast ? 1 : 0) + (nDfast ? 1 : 0) + (tableEntries ? 1 : 0);
+    ENC_CUDA(cudaGetLastError());
     return true;
 }
 const uint64_t* enc_results(const EncArena& A) { return A.impl ? (const uint64_t*)A.impl->hResults.p : nullptr; }
@@ -1594,8 +1766,7 @@ bool enc_compress_device(EncArena& A, cudaStream_t stream, cudaEvent_t* ev, size
         const uint64_t* hr = enc_results(A);
         for (size_t i = 0; i < m; i++) {
             size_t const ss = srcSize[base + i];
-            if (ss > kBlockSizeMax) result[base + i] = (size_t)make_error(kSrcSizeWrong);   // multi-block frames: DESIGN.md "next" (f.2)
-            else result[base + i] = (size_t)hr[i];
+            result[base + i] = ss > kEncMaxFrameBytes ? (size_t)make_error(kSrcSizeWrong) : (size_t)hr[i];
         }
     }
     timings[1] = msAll; timings[8] = msMatch; timings[9] = msEnt;

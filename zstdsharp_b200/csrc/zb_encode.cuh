@@ -15,7 +15,10 @@ struct EncArena {
 inline size_t enc_compress_bound(size_t srcSize)
 { return srcSize + (srcSize >> 8) + ((srcSize < (128u << 10)) ? (((128u << 10) - srcSize) >> 11) : 0); }
 
-// Compresses n device-resident chunks (each one frame) at `level` (0..3). result[i] = frame size or error code.
+// Largest frame the encoder takes (positions inside a frame are 31-bit integers); above: ZSTD_error_srcSize_wrong.
+size_t enc_max_frame_bytes();
+
+// Compresses n device-resident chunks (each one frame; frames above 128 KiB are multi-block frames, see enc_enqueue) at `level` (0..3). result[i] = frame size or error code.
 // timings: [1] all kernels, [8] match finder, [9] entropy stage.
 bool enc_compress_device(EncArena& A, cudaStream_t stream, cudaEvent_t* ev, size_t n, int level, int checksumFlag,
                          const uint8_t* d_src, const uint64_t* srcOff, const size_t* srcSize,
