@@ -616,9 +616,9 @@ __global__ void __launch_bounds__(kSetupWarps * 32) dec_setup_kernel(DecPass p)
 
 // =====================================================================================================
 //  Backward bit reader (semantics of BIT_DStream_t, Bitstream.cs:172-425, for the hot loops).
-//  A stream is consumed from its last byte downwards.  It is staged through a private shared-memory ring of four
-//  chunks that mirrors the low bits of the global address (ring byte = global byte mod 4*CH) and is filled with
-//  cp.async two chunks ahead, so the decode loops never wait on HBM/L2.  The reader state is one integer: G, the
+//  A stream is consumed from its last byte downwards.  It is staged through a private shared-memory ring of 128 bytes
+//  that mirrors the low bits of the global address (ring byte = global byte mod 128) and is filled with cp.async
+//  several chunks ahead, so the decode loops never wait on HBM/L2.  The reader state is one integer: G, the
 //  bit address (relative to the ring-aligned base) just above the next unread bit.  A read is two shared loads and
 //  one funnel shift, with no branch: that keeps every lane of a warp on the same instruction stream, which is
 //  what bounds these latency-limited kernels (profiles/r01_notes.md).
@@ -626,25 +626,32 @@ __global__ void __launch_bounds__(kSetupWarps * 32) dec_setup_kernel(DecPass p)
 __device__ __forceinline__ uint32_t lds32(uint32_t saddr) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(saddr)); return v; }
 __device__ __forceinline__ uint32_t lds16(uint32_t saddr) { uint16_t v; asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(saddr)); return v; }
 
-template <uint32_t CH>     // chunk bytes (power of two >= 64); ring = 4 chunks, aligned to 4*CH in shared memory
-struct BitRing {
-    static constexpr uint32_t RB = 4 * CH, MASK = RB - 1;
-    uint32_t sbase;         // shared address of the ring
-    const uint8_t* gbase;   // global address of chunk 0 (multiple of RB)
-    int32_t cur;            // chunk that holds the next unread bit
-    int32_t cLow;           // lowest chunk that may be staged (holds the first byte of the stream)
-    uint32_t gZero;         // G of "no unread bits left" (= 8 * offset of the first stream byte from gbase)
+// top `nb` bits (0..31) of a left-justified word
+__device__ __forceinline__ uint32_t top_bits(uint32_t x, uint32_t nb) { return (x >> 1) >> (31 - nb); }
 
-    __device__ __forceinline__ void fetch(int32_t c) const {
-        if (c >= cLow) {
-            uint32_t const sa = sbase + (((uint32_t)c * CH) & MASK);
-            const uint8_t* const g = gbase + (size_t)(uint32_t)c * CH;
-#pragma unroll
-            for (uint32_t i = 0; i < CH / 16; i++) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa + 16 * i), "l"(g + 16 * i));
-        }
-        asm volatile("cp.async.commit_group;");
+// UNIFORM refill: ring of 8 chunks of 16 bytes, topped up by at most NF chunks per step, by every lane at the same
+// instruction (predicated cp.async, no branch), D chunks ahead of the read position; the wait only covers groups
+// committed more than W steps ago, so it never stalls in practice.
+// Why: the first reader let every lane switch (32-byte) chunks on its own schedule.  A warp of independent streams then took
+// the switch branch in most steps, and its `wait_group 0` waited -- through the warp-wide scoreboard -- for the cp.async that
+// ANOTHER lane had issued one step earlier: 22 % of all stall samples of the sequence decoder sat on that wait
+// (profiles/r01_notes.md; Silesia-mix decode 8.6 -> 7.0 ms with this reader).
+// Contract: call step() once per step, all lanes together; a step consumes less than 16 bytes (one chunk per step keeps up)
+// and reads only chunks cur .. cur-R of its starting position.  Chunk cur-R was requested when the reader was in chunk
+// cur-R+D, i.e. more than (D-R-1)*16 bytes ago: W must be below that many bytes / the bytes a step can consume.
+// The slot of chunk c-D is the slot of chunk c-D+8, which must lie above cur: D <= 6.
+template <int D, int W>
+struct BitRingU {
+    static constexpr uint32_t CH = 16, NCH = 8, RB = CH * NCH, MASK = RB - 1;
+    uint32_t sbase; const uint8_t* gbase; int32_t fetched, cLow; uint32_t gZero;
+    __device__ __forceinline__ void fetch(int32_t c, bool on) const {
+        uint32_t const sa = sbase + (((uint32_t)c * CH) & MASK);
+        const uint8_t* const g = gbase + (ptrdiff_t)c * (ptrdiff_t)CH;
+        uint32_t const pr = (on && c >= cLow) ? 1u : 0u;
+        asm volatile("{ .reg .pred p; setp.ne.u32 p, %2, 0; @p cp.async.cg.shared.global [%0], [%1], 16; }" ::"r"(sa), "l"(g), "r"(pr) : "memory");
     }
-    // Returns G of the stream start (top), or 0 when the last byte is zero (no end mark: corruption).
+    // Returns G of the stream start (top), or 0 when the last byte is zero (no end mark: corruption).  The caller follows up
+    // with settle() once all lanes are back together.
     __device__ __forceinline__ uint32_t init(uint32_t ringShared, const uint8_t* first, uint32_t len) {
         sbase = ringShared;
         uintptr_t const a0 = (uintptr_t)first;
@@ -652,39 +659,41 @@ struct BitRing {
         uint32_t const rel = (uint32_t)(a0 & MASK);
         gZero = rel * 8;
         cLow = (int32_t)(rel / CH);
+        fetched = cLow;
         uint32_t const lastByte = first[len - 1];
         if (lastByte == 0) return 0;
         uint32_t const G = gZero + (len - 1) * 8 + highbit32(lastByte);
-        cur = (int32_t)((G - 1) >> 3) / (int32_t)CH;
-        fetch(cur); fetch(cur - 1); fetch(cur - 2);
-        asm volatile("cp.async.wait_group 1;" ::: "memory");      // cur and cur-1 have landed; cur-2 may still be in flight
+        int32_t const cur = (int32_t)((G - 1) >> 3) / (int32_t)CH;
+#pragma unroll
+        for (int j = 0; j <= D; j++) fetch(cur - j, true);
+        fetched = cur - D;
         return G;
     }
-    // Call once per step (a step consumes < CH bytes): when the read position entered a new chunk, the chunk below it
-    // has landed (it was requested one chunk ago) and the chunk two below is requested into the slot that became free.
-    __device__ __forceinline__ void advance(uint32_t G) {
-        int32_t const c = (int32_t)(G - 1) >> (3 + __builtin_ctz(CH));
-        if (c != cur) {
-            asm volatile("cp.async.wait_group 0;" ::: "memory");
-            cur = c;
-            fetch(c - 2);
+    __device__ __forceinline__ void idle() { sbase = 0; gbase = nullptr; fetched = 0; cLow = 0x7FFFFFFF; gZero = 0; }   // a lane without a stream
+    static __device__ __forceinline__ void settle() { asm volatile("cp.async.commit_group;" ::: "memory"); asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+    template <int NF = 1>      // chunks a step may consume (NF * 16 bytes at most)
+    __device__ __forceinline__ void step(uint32_t G, bool on) {
+        int32_t const cur = (int32_t)(G - 1) >> 7;
+#pragma unroll
+        for (int f = 0; f < NF; f++) {
+            bool const need = on && fetched > cur - D;
+            fetched -= need ? 1 : 0;
+            fetch(fetched, need);
         }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        asm volatile("cp.async.wait_group %0;" ::"n"(W) : "memory");
     }
-    // the next 32 unread bits below G, left-justified (bits beyond them are garbage-free: they come from the stream)
     __device__ __forceinline__ uint32_t peek32(uint32_t G) const {
         uint32_t const o = ((G - 1) >> 3) & (MASK & ~3u);
         uint32_t const hi = lds32(sbase + o), lo = lds32(sbase + ((o - 4) & MASK));
         return __funnelshift_l(lo, hi, 0u - G);
     }
-    // the next 64 unread bits below G, left-justified in (x0:x1)
     __device__ __forceinline__ void peek64(uint32_t G, uint32_t& x0, uint32_t& x1) const {
         uint32_t const o = ((G - 1) >> 3) & (MASK & ~3u);
         uint32_t const w0 = lds32(sbase + o), w1 = lds32(sbase + ((o - 4) & MASK)), w2 = lds32(sbase + ((o - 8) & MASK));
         x0 = __funnelshift_l(w1, w0, 0u - G); x1 = __funnelshift_l(w2, w1, 0u - G);
     }
 };
-// top `nb` bits (0..31) of a left-justified word
-__device__ __forceinline__ uint32_t top_bits(uint32_t x, uint32_t nb) { return (x >> 1) >> (31 - nb); }
 
 // =====================================================================================================
 //  Huffman literal decoding: one lane per stream, 14 items (56 streams) per CTA.
@@ -742,8 +751,11 @@ __global__ void __launch_bounds__(kHufThreads) dec_huf_kernel(DecPass p)
     else { count = stream < 3 ? seg : litSize - 3 * seg; outOff = stream * lit_segment_stride(litSize); }
     uint8_t* const out = p.litBuf + (size_t)item * kLitStride + outOff;
     const uint8_t* const src = p.src + it.srcOff;
-    BitRing<kHufChunk> br;
+    // one refill (up to two chunks) per 16 symbols (<= 22 bytes) in the main loop, per symbol in the tails; the end of a main
+    // step reads down to chunk cur-2, which was requested more than 48 bytes = more than 2 steps ago
+    BitRingU<6, 2> br;
     uint32_t G = br.init((uint32_t)__cvta_generic_to_shared(s_huf_raw) + threadIdx.x * (4 * kHufChunk), src + it.streamOff[stream], it.streamLen[stream]);
+    br.settle();
     bool ok = G != 0;
     if (ok) {
         uint32_t const sh = 32 - log;
@@ -756,7 +768,7 @@ __global__ void __launch_bounds__(kHufThreads) dec_huf_kernel(DecPass p)
                 uint32_t v[4];
 #pragma unroll
                 for (int q = 0; q < 4; q++) {
-                    if ((q & 1) == 0) br.advance(G);
+                    if (q == 0) br.step<2>(G, true);
                     uint32_t x0, x1; br.peek64(G, x0, x1);
                     uint32_t acc = 0, used = 0;
 #pragma unroll
@@ -773,7 +785,7 @@ __global__ void __launch_bounds__(kHufThreads) dec_huf_kernel(DecPass p)
                 *(uint4*)(out + i) = make_uint4(v[0], v[1], v[2], v[3]);
             }
             for (; i < count && (int32_t)G >= gz; i++) {
-                br.advance(G);
+                br.step(G, true);
                 uint32_t const idx = br.peek32(G) >> sh;
                 G -= lds8u(lenS + (idx >> 1));
                 out[i] = (uint8_t)lds8u(symS + idx);
@@ -781,7 +793,7 @@ __global__ void __launch_bounds__(kHufThreads) dec_huf_kernel(DecPass p)
         } else {
             const uint16_t* const gtab = p.hufTable + (size_t)item * kHufTableEntries;
             for (; i < count && (int32_t)G >= gz; i++) {
-                br.advance(G);
+                br.step(G, true);
                 uint32_t const e = __ldg(gtab + (br.peek32(G) >> sh));
                 G -= e & 0xFF;
                 out[i] = (uint8_t)(e >> 8);
@@ -841,9 +853,10 @@ __global__ void __launch_bounds__(32) dec_seq_kernel(DecPass p)
     uint2* const oSeq = p.seq + (size_t)item * kSeqCap;
     const uint8_t* const src = p.src + it.srcOff;
     uint32_t const nbSeq = it.nbSeq;
-    BitRing<kSeqChunk> br;
+    BitRingU<6, 5> br;         // a step consumes <= 89 bits and reads chunks cur, cur-1: cur-1 was requested more than 64 / 11.2 > 5 steps ago
     uint32_t err = 0;
     uint32_t G = br.init((uint32_t)__cvta_generic_to_shared(s_seq_raw) + lane * (4 * kSeqChunk), src + it.seqOff, it.seqLen);
+    br.settle();
     if (G == 0) err = kCorruptionDetected;
     int32_t const gz = (int32_t)br.gZero;
     uint32_t rep0 = it.rep[0], rep1 = it.rep[1], rep2 = it.rep[2];
@@ -859,7 +872,7 @@ __global__ void __launch_bounds__(32) dec_seq_kernel(DecPass p)
         G -= llLog + ofLog + mlLog;
         if ((int32_t)G < gz) err = kCorruptionDetected;
         for (uint32_t n = 0; n < nbSeq && !err; n++) {
-            br.advance(G);
+            br.step(G, true);
             uint32_t const eL = lds16(t16 + 2 * aL), eO = lds16(t16 + 2 * aO), eM = lds16(t16 + 2 * aM);
             uint32_t const nL = lds8(t8 + aL), nO = lds8(t8 + aO), nM = lds8(t8 + aM);
             uint32_t const llBits = (eL >> 4) & 31, mlBits = (eM >> 4) & 31, ofBits = (eO >> 4) & 31;
