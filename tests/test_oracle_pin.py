@@ -83,6 +83,18 @@ def test_multiblock_frames_match_libzstd():
         assert o.decompress(f, data.size) == data.tobytes()
 
 
+def test_multiblock_shapes_match_libzstd():
+    """The inputs of the GPU multi-block parity test (tests/_cases.py): raw / RLE blocks inside a frame, Huffman table reuse,
+    windows smaller than the frame, tiny last blocks.  Pins the oracle's block-to-block state on each of them."""
+    from _cases import multiblock_inputs
+    o, z = oracle(), libzstd()
+    for name, data in multiblock_inputs().items():
+        for level in (1, 3):
+            f = o.compress(data, level)
+            assert f == z.compress(data, level), (name, level)
+        assert o.decompress(f, data.size) == data.tobytes(), name
+
+
 def test_cparams_table():
     o = oracle()
     # Clevels.cs:490 / :510 (rows 1 and 3 of the <=128 KB table) and the <=16 KB table (:713-743)

@@ -623,11 +623,11 @@ __global__ void __launch_bounds__(kSetupWarps * 32) dec_setup_kernel(DecPass p)
 //  one funnel shift, with no branch: that keeps every lane of a warp on the same instruction stream, which is
 //  what bounds these latency-limited kernels (profiles/r01_notes.md).
 // =====================================================================================================
-__device__ __forceinline__ uint32_t lds32(uint32_t saddr) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(saddr)); return v; }
-__device__ __forceinline__ uint32_t lds16(uint32_t saddr) { uint16_t v; asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(saddr)); return v; }
+__device__ __forceinline__ uint32_t lds32(uint32_t saddr) { uint32_t v; asm("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(saddr)); return v; }
+__device__ __forceinline__ uint32_t lds16(uint32_t saddr) { uint16_t v; asm("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(saddr)); return v; }
 
 // top `nb` bits (0..31) of a left-justified word
-__device__ __forceinline__ uint32_t top_bits(uint32_t x, uint32_t nb) { return (x >> 1) >> (31 - nb); }
+__device__ __forceinline__ uint32_t top_bits(uint32_t x, uint32_t nb) { return __funnelshift_l(x, 0u, nb); }   // one SHF: high word of (0:x) << nb
 
 // UNIFORM refill: ring of 8 chunks of 16 bytes, topped up by at most NF chunks per step, by every lane at the same
 // instruction (predicated cp.async, no branch), D chunks ahead of the read position; the wait only covers groups
@@ -710,7 +710,7 @@ constexpr uint32_t kHufSmemLog = 11;
 constexpr uint32_t kHufSymBytes = 1u << kHufSmemLog, kHufLenBytes = 1u << (kHufSmemLog - 1), kHufItemBytes = kHufSymBytes + kHufLenBytes;
 constexpr uint32_t kHufChunk = 32;              // 4 x 32 B of ring per stream (8 symbols consume <= 12 bytes, a refill reads 12 more)
 constexpr uint32_t kHufSmemBytes = kHufThreads * 4 * kHufChunk + kHufItemsPerCta * kHufItemBytes;
-__device__ __forceinline__ uint32_t lds8u(uint32_t saddr) { uint16_t v; asm volatile("ld.shared.u8 %0, [%1];" : "=h"(v) : "r"(saddr)); return v; }
+__device__ __forceinline__ uint32_t lds8u(uint32_t saddr) { uint16_t v; asm("ld.shared.u8 %0, [%1];" : "=h"(v) : "r"(saddr)); return v; }
 
 __device__ __forceinline__ uint32_t lit_segment_stride(uint32_t litSize) { uint32_t const seg = (litSize + 3) / 4; return (seg + 15) & ~15u; }
 
@@ -817,7 +817,7 @@ constexpr uint32_t kSeqChunk = 32;             // 4 x 32 B of ring per item (a s
 constexpr uint32_t kSeqTab16Bytes = kFseTableEntries * 2, kSeqTab8Bytes = kFseTableEntries;
 constexpr uint32_t kSeqItemBytes = kSeqTab16Bytes + kSeqTab8Bytes;
 constexpr uint32_t kSeqSmemBytes = kSeqItemsPerCta * (kSeqItemBytes + 4 * kSeqChunk);
-__device__ __forceinline__ uint32_t lds8(uint32_t saddr) { uint16_t v; asm volatile("ld.shared.u8 %0, [%1];" : "=h"(v) : "r"(saddr)); return v; }
+__device__ __forceinline__ uint32_t lds8(uint32_t saddr) { uint16_t v; asm("ld.shared.u8 %0, [%1];" : "=h"(v) : "r"(saddr)); return v; }
 
 __global__ void __launch_bounds__(32) dec_seq_kernel(DecPass p)
 {
@@ -853,7 +853,9 @@ __global__ void __launch_bounds__(32) dec_seq_kernel(DecPass p)
     uint2* const oSeq = p.seq + (size_t)item * kSeqCap;
     const uint8_t* const src = p.src + it.srcOff;
     uint32_t const nbSeq = it.nbSeq;
-    BitRingU<6, 5> br;         // a step consumes <= 89 bits and reads chunks cur, cur-1: cur-1 was requested more than 64 / 11.2 > 5 steps ago
+    // one refill (up to two chunks) per two sequences: they consume <= 178 bits and read down to chunk cur-2, which was requested
+    // more than 48 bytes = more than 2 refills ago
+    BitRingU<6, 2> br;
     uint32_t err = 0;
     uint32_t G = br.init((uint32_t)__cvta_generic_to_shared(s_seq_raw) + lane * (4 * kSeqChunk), src + it.seqOff, it.seqLen);
     br.settle();
@@ -872,14 +874,15 @@ __global__ void __launch_bounds__(32) dec_seq_kernel(DecPass p)
         G -= llLog + ofLog + mlLog;
         if ((int32_t)G < gz) err = kCorruptionDetected;
         for (uint32_t n = 0; n < nbSeq && !err; n++) {
-            br.step(G, true);
+            if ((n & 1) == 0) br.step<2>(G, true);
             uint32_t const eL = lds16(t16 + 2 * aL), eO = lds16(t16 + 2 * aO), eM = lds16(t16 + 2 * aM);
             uint32_t const nL = lds8(t8 + aL), nO = lds8(t8 + aO), nM = lds8(t8 + aM);
             uint32_t const llBits = (eL >> 4) & 31, mlBits = (eM >> 4) & 31, ofBits = (eO >> 4) & 31;
             uint32_t const nbL = eL & 15, nbM = eM & 15, nbO = eO & 15;
             // stream order: offset extra, matchLength extra, litLength extra, then LL / ML / OF state bits (:2397-2480)
             uint32_t const G1 = G - ofBits, G2 = G1 - (mlBits + llBits), G3 = G2 - (nbL + nbM + nbO);
-            uint32_t const xA = br.peek32(G), xB = br.peek32(G1), xC = br.peek32(G2);
+            uint32_t xA, xA1; br.peek64(G, xA, xA1);                      // offset extra, then matchLength + litLength extra: <= 63 bits
+            uint32_t const xB = __funnelshift_l(xA1, xA, ofBits), xC = br.peek32(G2);
             uint32_t const llSym = (eL >> 9) & 63, mlSym = (eM >> 9) & 63;
             uint32_t const ofExtra = top_bits(xA, ofBits);
             uint32_t const ml = lds32(mlBaseS + mlSym * 4) + top_bits(xB, mlBits);

@@ -99,6 +99,7 @@ __device__ __forceinline__ BlkGeom blk_geom(uint32_t frameSize, uint32_t windowL
     return g;
 }
 
+struct FseGTable; struct EntCarry;
 struct EncPass {
     EncItem* items; uint32_t nItems;
     const uint8_t* src; uint8_t* dst;
@@ -107,6 +108,8 @@ struct EncPass {
     uint8_t* litBuf;        // gathered literals
     uint64_t* stateBits;    // per sequence: FSE state bits of OF | ML | LL (13 bits each: 9 value + 4 count)
     uint64_t* results;
+    FseGTable* fseTabs;     // [item][3]: LL, OF, ML compression tables of the current block
+    EntCarry* carry;        // [item]
     uint8_t* hufState;      // multi-block frames: 2 slots of {u8 nbBits[256]; u16 value[256]} per frame (prev / next Huffman CTable)
     uint32_t checksumFlag;  // ZSTD_c_checksumFlag: append the low 32 bits of XXH64(src) to every frame
 };
@@ -693,6 +696,10 @@ constexpr int kEntThreads = 128;
 struct NodeElt { uint32_t count; uint16_t parent; uint8_t byte; uint8_t nbBits; };   // nodeElt_s.cs
 struct SymbolTT { int32_t deltaFindState; uint32_t deltaNbBits; };                   // FSE_symbolCompressionTransform.cs
 struct FseCTable { uint32_t tableLog; uint16_t stateTable[512]; SymbolTT tt[53]; };
+// the same table in HBM, handed from the front half of the entropy stage to the state-chain kernel (tt first: 8-byte aligned)
+struct __align__(8) FseGTable { SymbolTT tt[53]; uint32_t tableLog; uint32_t _pad; uint16_t stateTable[512]; };
+// per block: what the back half of the entropy stage needs from the front half and from the state chains
+struct EntCarry { uint32_t op, lastCountSize, flags /* 1: has sequences (chains run), 2: new Huffman table */, finalState[3], _pad[2]; };
 
 struct EntShared {
     // The literals section is finished before the sequences section starts, so their scratch shares storage:
@@ -1134,7 +1141,11 @@ __device__ __forceinline__ void put_bits(uint32_t* w, uint64_t bit, uint32_t v, 
 // EncItem / hufState and are advanced here (ZSTD_compress_frameChunk :4690, ZSTD_compressBlock_internal :4528,
 // ZSTD_blockState_confirmRepcodesAndEntropyTables).  Without a dictionary and below ZSTD_lazy the FSE tables never repeat
 // (ZSTD_selectEncodingType returns set_repeat only for FSE_repeat_valid), so the Huffman table is the only entropy state.
-template <bool MB>
+// The stage runs as three launches: PHASE 0 (this kernel: literals section, sequence statistics, the three FSE tables and their
+// descriptions), enc_fse_chain_kernel (one lane per FSE state chain), PHASE 1 (this kernel: bitstream scatter, block and frame
+// assembly).  Inside one kernel the three chains of a chunk kept three single-lane warps busy for 12 K dependent steps each:
+// 70 % of the stage's warp instructions ran with one active lane (profiles/r01_notes.md).
+template <bool MB, int PHASE>
 __global__ void __launch_bounds__(kEntThreads, MB ? 8 : 15) enc_entropy_kernel(EncPass p, const uint32_t* __restrict__ workList, uint32_t wave)
 {
     __shared__ EntShared S;
@@ -1147,14 +1158,14 @@ __global__ void __launch_bounds__(kEntThreads, MB ? 8 : 15) enc_entropy_kernel(E
     uint32_t* const dstW = (uint32_t*)dst;
     uint32_t const srcSize = MB ? min(kBlockSizeMax, frameSize - blkStart) : frameSize;     // block size
     bool const firstBlock = !MB || wave == 0, lastBlock = !MB || blkStart + srcSize == frameSize;
-    if (!MB && srcSize > kBlockSizeMax) { if (tid == 0) p.results[item] = make_error(kSrcSizeWrong); return; }
+    if (!MB && srcSize > kBlockSizeMax) { if (tid == 0) { p.results[item] = make_error(kSrcSizeWrong); p.carry[item].flags = 0; } return; }
     // ---- frame header: ZSTD_writeFrameHeader (ZstdCompress.cs:4817), contentSizeFlag = 1, no dictID ----
     uint32_t fhSize = 0;
     if (firstBlock) {
         uint32_t const fcsCode = (frameSize >= 256) + (frameSize >= 65536 + 256);
         bool const singleSegment = !MB || ((1u << it.windowLog) >= frameSize);     // windowSize >= pledgedSrcSize (:4823); always for one-block frames
         fhSize = 4 + 1 + (singleSegment ? 0 : 1) + (fcsCode == 0 ? (singleSegment ? 1 : 0) : (fcsCode == 1 ? 2 : 4));
-        if (tid == 0) {
+        if (tid == 0 && PHASE == 0) {
             dst[0] = 0x28; dst[1] = 0xB5; dst[2] = 0x2F; dst[3] = 0xFD;
             dst[4] = (uint8_t)((p.checksumFlag ? 4u : 0u) + ((singleSegment ? 1u : 0u) << 5) + (fcsCode << 6));   // FHD: checksum bit 2, singleSegment bit 5, fcsID bits 6-7 (:4823-4829)
             uint32_t pos = 5;
@@ -1169,8 +1180,11 @@ __global__ void __launch_bounds__(kEntThreads, MB ? 8 : 15) enc_entropy_kernel(E
     uint32_t const payload = blkPos + 3;                        // byte offset of the block content
     bool raw = false, rle = false, newHuf = false;
     uint32_t cSize = 0;
+    EntCarry& cy = p.carry[item];
+    FseGTable* const gt = p.fseTabs + (size_t)item * 3;
     if (frameSize == 0) {                                       // ZSTD_writeEpilogue: one empty last raw block (:5621-5631)
-        if (tid == 0) {
+        if (tid == 0 && PHASE == 0) {
+            cy.flags = 0;
             blk[0] = 1; blk[1] = 0; blk[2] = 0;
             uint32_t total = fhSize + 3;
             if (p.checksumFlag) { uint32_t const c = 0x51D8E999u; /* low 32 bits of XXH64("", seed 0) = 0xEF46DB3751D8E999 */ dst[total] = (uint8_t)c; dst[total + 1] = (uint8_t)(c >> 8); dst[total + 2] = (uint8_t)(c >> 16); dst[total + 3] = (uint8_t)(c >> 24); total += 4; }
@@ -1179,11 +1193,14 @@ __global__ void __launch_bounds__(kEntThreads, MB ? 8 : 15) enc_entropy_kernel(E
         return;
     }
     uint32_t const nbSeq = it.nbSeq;
-    if (srcSize < 7) raw = true;
+    if (srcSize < 7) { raw = true; if (PHASE == 0) { if (tid == 0) cy.flags = 0; return; } }
     if (!raw) {
         const uint32_t* const aLL = p.seqLL + (size_t)item * kEncSeqCap;
         const uint32_t* const aML = p.seqML + (size_t)item * kEncSeqCap;
         const uint32_t* const aOF = p.seqOF + (size_t)item * kEncSeqCap;
+        uint64_t* const sb = p.stateBits + (size_t)item * kEncSeqCap;
+        uint32_t op = 0, lastCountSize = 0;
+      if (PHASE == 0) {
         uint8_t* const lit = p.litBuf + (size_t)item * kEncLitStride;
         // ---- 1. gather literals (ZSTD_storeSeq copies + ZSTD_storeLastLiterals) ----
         uint32_t litSize;
@@ -1375,7 +1392,7 @@ __global__ void __launch_bounds__(kEntThreads, MB ? 8 : 15) enc_entropy_kernel(E
             }
         }
         __syncthreads();
-        uint32_t op = payload + S.litSectionSize;
+        op = payload + S.litSectionSize;
         // ---- 3. sequences section (ZstdCompress.cs:3285-3352) ----
         if (tid == 0) {
             uint8_t* o = dst + op;
@@ -1385,15 +1402,13 @@ __global__ void __launch_bounds__(kEntThreads, MB ? 8 : 15) enc_entropy_kernel(E
         }
         __syncthreads();
         op += S.seqHdrSize;
-        bool zeroed = false;
         if (nbSeq > 0) {
             uint32_t const strategy = it.strategy;
             uint32_t const seqHead = op; op += 1;
-            uint32_t lastCountSize = 0; uint32_t types[3];
+            uint32_t types[3];
             // ZSTD_buildSequencesStatistics (:3127): one pass writes the three symbol codes of every sequence (into the slots
             // the state chains will overwrite) and counts them; then three threads build the LL / OF / ML tables
             // concurrently, each with private scratch; thread 0 finally lays the table descriptions out in order.
-            uint64_t* const sb = p.stateBits + (size_t)item * kEncSeqCap;
             for (uint32_t q = tid; q < 192; q += kEntThreads) (&S.count3[0][0])[q] = 0;
             __syncthreads();
             for (uint32_t n = tid; n < nbSeq; n += kEntThreads) {
@@ -1444,41 +1459,23 @@ __global__ void __launch_bounds__(kEntThreads, MB ? 8 : 15) enc_entropy_kernel(E
             }
             __syncthreads();
             if (tid == 0) dst[seqHead] = (uint8_t)((types[0] << 6) + (types[1] << 4) + (types[2] << 2));
-            // ---- 4. FSE state chains: three lanes walk the sequences last -> first (ZSTD_encodeSequences_body :585) ----
-            // The chain state -> nbBits -> next state is serial; everything else is taken off it: all threads first write
-            // the three symbol codes of every sequence into the chain's own output slots, and each chain lane then works
-            // in steps of 8 sequences: 8 code loads, 8 symbol-transform loads, 8 dependent state steps.
-            if (tid < 96 && (tid & 31) == 0) {
-                int const k = tid >> 5;    // 0 LL, 1 OF, 2 ML
-                const FseCTable& ct = S.ct[k];
-                // slot layout per sequence afterwards: value(<= 9 bits) | count << 12
-                uint16_t* const out16 = (uint16_t*)sb + k;                          // 4 x u16 per sequence
-                uint32_t state = fse_init_state(ct, out16[(size_t)(nbSeq - 1) * 4]);
-                out16[(size_t)(nbSeq - 1) * 4] = 0;
-                uint32_t n = nbSeq - 1;                                             // sequences n-1 .. 0 are still to do
-                while (n >= 8) {
-                    uint32_t c[8]; SymbolTT t[8];
-#pragma unroll
-                    for (int j = 0; j < 8; j++) c[j] = out16[(size_t)(n - 1 - j) * 4];
-#pragma unroll
-                    for (int j = 0; j < 8; j++) t[j] = ct.tt[c[j]];
-#pragma unroll
-                    for (int j = 0; j < 8; j++) {
-                        uint32_t const nb = (state + t[j].deltaNbBits) >> 16;
-                        out16[(size_t)(n - 1 - j) * 4] = (uint16_t)((state & ((1u << nb) - 1)) | (nb << 12));
-                        state = ct.stateTable[(int32_t)(state >> nb) + t[j].deltaFindState];
-                    }
-                    n -= 8;
-                }
-                while (n-- > 0) {
-                    SymbolTT const tt = ct.tt[out16[(size_t)n * 4]];
-                    uint32_t const nb = (state + tt.deltaNbBits) >> 16;
-                    out16[(size_t)n * 4] = (uint16_t)((state & ((1u << nb) - 1)) | (nb << 12));
-                    state = ct.stateTable[(int32_t)(state >> nb) + tt.deltaFindState];
-                }
-                S.scanB[k] = state;     // final states, flushed after the last packet
+            // ---- hand the three tables to the state-chain kernel ----
+            for (int k = 0; k < 3; k++) {
+                const FseCTable& ct = S.ct[k]; FseGTable& g = gt[k];
+                uint32_t const tlog = ct.tableLog;
+                const uint32_t* const ttw = (const uint32_t*)ct.tt; uint32_t* const gtw = (uint32_t*)g.tt;
+                for (uint32_t q = tid; q < 106; q += kEntThreads) gtw[q] = ttw[q];
+                for (uint32_t q = tid; q < max(2u, 1u << tlog); q += kEntThreads) g.stateTable[q] = ct.stateTable[q];
+                if (tid == 0) g.tableLog = tlog;
             }
-            __syncthreads();
+        }
+        if (tid == 0) { cy.op = op; cy.lastCountSize = lastCountSize; cy.flags = (nbSeq > 0 ? 1u : 0u) | (newHuf ? 2u : 0u); }
+        return;
+      }
+        // ================= PHASE 1: after the state chains =================
+        op = cy.op; lastCountSize = cy.lastCountSize; newHuf = (cy.flags & 2u) != 0;
+        if (nbSeq > 0) {
+            uint32_t const tl0 = gt[0].tableLog, tl1 = gt[1].tableLog, tl2 = gt[2].tableLog;
             // ---- 5. bitstream scatter ----
             // order inside sequence n's packet (low -> high): [OF state bits][ML state bits][LL state bits] (none for n = nbSeq-1),
             // then LL extra, ML extra, OF extra.  Packets are laid out n = nbSeq-1 first.
@@ -1492,12 +1489,11 @@ __global__ void __launch_bounds__(kEntThreads, MB ? 8 : 15) enc_entropy_kernel(E
                     mine += c_LL_bits[llc] + c_ML_bits[mlc] + ofc + (s16[0] >> 12) + (s16[1] >> 12) + (s16[2] >> 12);
                 }
                 uint32_t tot; ent_scan_excl(mine, S.scanA, &tot);
-                totalBits = tot + S.ct[0].tableLog + S.ct[1].tableLog + S.ct[2].tableLog;
+                totalBits = tot + tl0 + tl1 + tl2;
             }
             uint32_t const streamSize = (totalBits + 1 + 7) / 8;             // BIT_closeCStream: 1-bit end mark
             for (uint32_t k = tid; k < streamSize; k += kEntThreads) dst[op + k] = 0;
             __syncthreads();
-            zeroed = true;
             {
                 uint64_t const bit0 = (uint64_t)op * 8;
                 uint32_t carry = 0;
@@ -1529,16 +1525,15 @@ __global__ void __launch_bounds__(kEntThreads, MB ? 8 : 15) enc_entropy_kernel(E
                 }
                 if (tid == 0) {     // FSE_flushCState x3 in the order ML, OF, LL, then the end mark (:694-700)
                     uint64_t pos = bit0 + carry;
-                    put_bits(dstW, pos, S.scanB[2], S.ct[2].tableLog); pos += S.ct[2].tableLog;
-                    put_bits(dstW, pos, S.scanB[1], S.ct[1].tableLog); pos += S.ct[1].tableLog;
-                    put_bits(dstW, pos, S.scanB[0], S.ct[0].tableLog); pos += S.ct[0].tableLog;
+                    put_bits(dstW, pos, cy.finalState[2], tl2); pos += tl2;
+                    put_bits(dstW, pos, cy.finalState[1], tl1); pos += tl1;
+                    put_bits(dstW, pos, cy.finalState[0], tl0); pos += tl0;
                     put_bits(dstW, pos, 1, 1);
                 }
             }
             op += streamSize;
             if (lastCountSize && (lastCountSize + streamSize) < 4) raw = true;          // ZstdCompress.cs:3346-3350
         }
-        (void)zeroed;
         __syncthreads();
         cSize = op - payload;
         // ZSTD_entropyCompressSeqStore gate (:3381-3389) and capacity of the slot
@@ -1591,6 +1586,75 @@ __global__ void __launch_bounds__(kEntThreads, MB ? 8 : 15) enc_entropy_kernel(E
     if (tid == 0) p.results[item] = total + (p.checksumFlag ? 4u : 0u);
 }
 
+// ------------------------------------------------------------------------------------------------------------
+//  FSE state chains (ZSTD_encodeSequences_body, ZstdCompressSequences.cs:585; FSE_encodeSymbol, Fse.cs:60): one LANE per chain.
+//  A block has three chains (LL, OF, ML), each a walk over its sequences from the last to the first in which the state after
+//  sequence n feeds sequence n-1: state -> nbBits -> next state.  8192 blocks give 24576 independent chains; 32 of them share
+//  a warp (same instruction stream, every lane busy), their state tables (<= 1 KB each) sit in shared memory, the symbol
+//  transforms (independent of the state) are fetched eight steps ahead through L1/L2.  Per sequence the chain leaves
+//  value | nbBits << 12 in the slot that held the symbol code; the final state goes to EntCarry.
+// ------------------------------------------------------------------------------------------------------------
+constexpr uint32_t kChainTabStride = 1028;     // bytes per chain in shared memory: 512 x u16 + 4 (bank skew)
+template <bool MB>
+__global__ void __launch_bounds__(32) enc_fse_chain_kernel(EncPass p, const uint32_t* __restrict__ workList, uint32_t nItems)
+{
+    extern __shared__ __align__(16) uint8_t s_chain[];
+    uint32_t const lane = threadIdx.x;
+    uint32_t const base = blockIdx.x * 32;
+    // cooperative, coalesced staging of the 32 state tables of this warp
+    for (uint32_t t = 0; t < 32; t++) {
+        uint32_t const ch = base + t, idx = ch / 3, k = ch % 3;
+        if (idx >= nItems) break;
+        uint32_t const item = MB ? workList[idx] : idx;
+        if (!(p.carry[item].flags & 1u)) continue;
+        const FseGTable& g = p.fseTabs[(size_t)item * 3 + k];
+        uint32_t const words = max(1u, (1u << g.tableLog) >> 1);
+        const uint32_t* const src = (const uint32_t*)g.stateTable; uint32_t* const dst = (uint32_t*)(s_chain + t * kChainTabStride);
+        for (uint32_t w = lane; w < words; w += 32) dst[w] = src[w];
+    }
+    __syncwarp();
+    uint32_t const ch = base + lane, idx = ch / 3, k = ch % 3;      // k: 0 LL, 1 OF, 2 ML (the u16 slot of the chain inside a sequence's 8 bytes)
+    if (idx >= nItems) return;
+    uint32_t const item = MB ? workList[idx] : idx;
+    EntCarry& cy = p.carry[item];
+    if (!(cy.flags & 1u)) return;
+    const FseGTable& g = p.fseTabs[(size_t)item * 3 + k];
+    const uint2* const gtt = (const uint2*)g.tt;                    // {deltaFindState, deltaNbBits}
+    const uint16_t* const st = (const uint16_t*)(s_chain + lane * kChainTabStride);
+    uint32_t const nbSeq = p.items[item].nbSeq;
+    uint16_t* const out16 = (uint16_t*)(p.stateBits + (size_t)item * kEncSeqCap) + k;     // 4 x u16 per sequence
+    uint32_t state;
+    {   // FSE_initCState2 (Fse.cs:38) on the last sequence's symbol
+        uint2 const tt = __ldg(gtt + out16[(size_t)(nbSeq - 1) * 4]);
+        uint32_t const nbBitsOut = (tt.y + (1u << 15)) >> 16;
+        uint32_t const value = (nbBitsOut << 16) - tt.y;
+        state = st[(int32_t)(value >> nbBitsOut) + (int32_t)tt.x];
+        out16[(size_t)(nbSeq - 1) * 4] = 0;
+    }
+    uint32_t n = nbSeq - 1;                                         // sequences n-1 .. 0 are still to do
+    while (n >= 8) {
+        uint32_t c[8]; uint2 t[8];
+#pragma unroll
+        for (int j = 0; j < 8; j++) c[j] = out16[(size_t)(n - 1 - j) * 4];
+#pragma unroll
+        for (int j = 0; j < 8; j++) t[j] = __ldg(gtt + c[j]);
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            uint32_t const nb = (state + t[j].y) >> 16;
+            out16[(size_t)(n - 1 - j) * 4] = (uint16_t)((state & ((1u << nb) - 1)) | (nb << 12));
+            state = st[(int32_t)(state >> nb) + (int32_t)t[j].x];
+        }
+        n -= 8;
+    }
+    while (n-- > 0) {
+        uint2 const tt = __ldg(gtt + out16[(size_t)n * 4]);
+        uint32_t const nb = (state + tt.y) >> 16;
+        out16[(size_t)n * 4] = (uint16_t)((state & ((1u << nb) - 1)) | (nb << 12));
+        state = st[(int32_t)(state >> nb) + (int32_t)tt.x];
+    }
+    cy.finalState[k] = state;       // flushed after the last packet
+}
+
 __global__ void enc_compact_kernel(const uint8_t* src, const uint64_t* srcOff, const uint64_t* sizes, const uint64_t* dstOff, uint8_t* dst)
 {
     uint32_t const i = blockIdx.x;
@@ -1610,7 +1674,7 @@ struct HBuf { void* p = nullptr; size_t cap = 0;
     void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; } };
 
 struct EncArenaImpl {
-    DBuf items, tables, seqLL, seqML, seqOF, lit, stateBits, results, compact, cSrcOff, cSizes, cDstOff, workLists, hufState;
+    DBuf items, tables, seqLL, seqML, seqOF, lit, stateBits, results, compact, cSrcOff, cSizes, cDstOff, workLists, hufState, fseTabs, carry;
     HBuf hItems, hResults, hC, hWork;
     cudaEvent_t copied = nullptr;
     EncArenaImpl() { cudaEventCreateWithFlags(&copied, cudaEventDisableTiming); }
@@ -1622,7 +1686,7 @@ size_t enc_max_frame_bytes() { return kEncMaxFrameBytes; }
 void EncArena::release()
 {
     if (!impl) return;
-    DBuf* d[] = {&impl->items, &impl->tables, &impl->seqLL, &impl->seqML, &impl->seqOF, &impl->lit, &impl->stateBits, &impl->results, &impl->compact, &impl->cSrcOff, &impl->cSizes, &impl->cDstOff, &impl->workLists, &impl->hufState};
+    DBuf* d[] = {&impl->items, &impl->tables, &impl->seqLL, &impl->seqML, &impl->seqOF, &impl->lit, &impl->stateBits, &impl->results, &impl->compact, &impl->cSrcOff, &impl->cSizes, &impl->cDstOff, &impl->workLists, &impl->hufState, &impl->fseTabs, &impl->carry};
     for (auto* b : d) b->release();
     impl->hItems.release(); impl->hResults.release(); impl->hC.release(); impl->hWork.release();
     delete impl; impl = nullptr;
@@ -1708,7 +1772,7 @@ bool enc_enqueue(EncArena& A, cudaStream_t stream, cudaStream_t copyStream, size
     }
     if (!I.tables.ensure(tableEntries * 4 + 16) || !I.seqLL.ensure(m * (size_t)kEncSeqCap * 4) || !I.seqML.ensure(m * (size_t)kEncSeqCap * 4) ||
         !I.seqOF.ensure(m * (size_t)kEncSeqCap * 4) || !I.lit.ensure(m * (size_t)kEncLitStride) || !I.stateBits.ensure(m * (size_t)kEncSeqCap * 8) ||
-        (mb && !I.hufState.ensure(m * 2 * (size_t)kHufStateSlot))) { t_encErr = "out of memory (arena)"; return false; }
+        (mb && !I.hufState.ensure(m * 2 * (size_t)kHufStateSlot)) || !I.fseTabs.ensure(m * 3 * sizeof(FseGTable)) || !I.carry.ensure(m * sizeof(EntCarry))) { t_encErr = "out of memory (arena)"; return false; }
     ENC_CUDA(cudaMemcpyAsync(I.items.p, hi, m * sizeof(EncItem), cudaMemcpyHostToDevice, copyStream));
     ENC_CUDA(cudaMemcpyAsync(I.workLists.p, I.hWork.p, listCap * 4, cudaMemcpyHostToDevice, copyStream));
     if (copyStream != stream) {                                   // order the kernels after the two small copies
@@ -1720,7 +1784,7 @@ bool enc_enqueue(EncArena& A, cudaStream_t stream, cudaStream_t copyStream, size
     EncPass p;
     p.items = (EncItem*)I.items.p; p.nItems = (uint32_t)m; p.src = d_src; p.dst = d_dst; p.tables = (uint32_t*)I.tables.p;
     p.seqLL = (uint32_t*)I.seqLL.p; p.seqML = (uint32_t*)I.seqML.p; p.seqOF = (uint32_t*)I.seqOF.p; p.litBuf = (uint8_t*)I.lit.p;
-    p.stateBits = (uint64_t*)I.stateBits.p; p.results = hr; p.hufState = (uint8_t*)I.hufState.p; p.checksumFlag = checksumFlag ? 1u : 0u;
+    p.stateBits = (uint64_t*)I.stateBits.p; p.results = hr; p.hufState = (uint8_t*)I.hufState.p; p.fseTabs = (FseGTable*)I.fseTabs.p; p.carry = (EntCarry*)I.carry.p; p.checksumFlag = checksumFlag ? 1u : 0u;
     const uint32_t* const dw = (const uint32_t*)I.workLists.p;
     *launches += tableEntries ? 1 : 0;
     for (size_t b = 0; b < maxWaves; b++) {
@@ -1732,15 +1796,21 @@ bool enc_enqueue(EncArena& A, cudaStream_t stream, cudaStream_t copyStream, size
             if (w.n[1]) enc_match_kernel<<<(w.n[1] + 31) / 32, 32, 0, stream>>>(p, dw + w.off[1], w.n[1], wave);
             if (w.n[2]) enc_match_dfast_group_kernel<16, true><<<(w.n[2] + 1) / 2, 32, 0, stream>>>(p, dw + w.off[2], w.n[2], wave);
             if (ev3 && b == 0) ENC_CUDA(cudaEventRecord(ev3[1], stream));
-            if (w.n[3]) enc_entropy_kernel<true><<<w.n[3], kEntThreads, 0, stream>>>(p, dw + w.off[3], wave);
+            if (w.n[3]) {
+                enc_entropy_kernel<true, 0><<<w.n[3], kEntThreads, 0, stream>>>(p, dw + w.off[3], wave);
+                enc_fse_chain_kernel<true><<<(3 * w.n[3] + 31) / 32, 32, 32 * kChainTabStride, stream>>>(p, dw + w.off[3], w.n[3]);
+                enc_entropy_kernel<true, 1><<<w.n[3], kEntThreads, 0, stream>>>(p, dw + w.off[3], wave);
+            }
         } else {
             if (w.n[0]) enc_match_group_kernel<16, false><<<(w.n[0] + 1) / 2, 32, 0, stream>>>(p, dw + w.off[0], w.n[0], 0u);
             if (w.n[1]) enc_match_kernel<<<(w.n[1] + 31) / 32, 32, 0, stream>>>(p, dw + w.off[1], w.n[1], 0u);
             if (w.n[2]) enc_match_dfast_group_kernel<16, false><<<(w.n[2] + 1) / 2, 32, 0, stream>>>(p, dw + w.off[2], w.n[2], 0u);
             if (ev3) ENC_CUDA(cudaEventRecord(ev3[1], stream));
-            enc_entropy_kernel<false><<<(unsigned)m, kEntThreads, 0, stream>>>(p, dw, 0u);
+            enc_entropy_kernel<false, 0><<<(unsigned)m, kEntThreads, 0, stream>>>(p, dw, 0u);
+            enc_fse_chain_kernel<false><<<(unsigned)(3 * m + 31) / 32, 32, 32 * kChainTabStride, stream>>>(p, dw, (uint32_t)m);
+            enc_entropy_kernel<false, 1><<<(unsigned)m, kEntThreads, 0, stream>>>(p, dw, 0u);
         }
-        *launches += (w.n[0] ? 1 : 0) + (w.n[1] ? 1 : 0) + (w.n[2] ? 1 : 0) + ((mb ? w.n[3] : 1) ? 1 : 0);
+        *launches += (w.n[0] ? 1 : 0) + (w.n[1] ? 1 : 0) + (w.n[2] ? 1 : 0) + ((mb ? w.n[3] : 1) ? 3 : 0);
     }
     if (ev3) ENC_CUDA(cudaEventRecord(ev3[2], stream));
     ENC_CUDA(cudaGetLastError());
