@@ -55,7 +55,7 @@ ZSTDB200_API size_t     ZSTD_decompressDCtx(ZSTD_DCtx* dctx, void* dst, size_t d
                                             const void* src, size_t srcSize);                      /* :30 */
 ZSTDB200_API size_t     ZSTD_compressBound(size_t srcSize);                                        /* :34 */
 /* param: ZSTD_c_compressionLevel = 100 (levels 0..3; 0 means 3), ZSTD_c_checksumFlag = 201 (0/1: XXH64 trailer, U/ZstdCompress.cs:5641-5652),
- * ZSTD_c_contentSizeFlag = 200 (1 only), ZSTDB200_c_independentChunks (below);
+ * ZSTD_c_contentSizeFlag = 200 (1 only), ZSTDB200_c_independentChunks = 10001, see below;
  * anything else -> ZSTD_error_parameter_unsupported. */
 /* New, host-pointer API only.  0 (default): every item becomes one frame with the reference's bytes; items above 128 KiB are
  * multi-block frames (U/ZstdCompress.cs:4690 ZSTD_compress_frameChunk), whose blocks the GPU must take one after the other.

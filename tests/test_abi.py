@@ -56,6 +56,16 @@ def test_parameter_surface():
         raise AssertionError("expected parameter_outOfBound")
     except api.ZstdException as e:
         assert e.Code == api.ZSTD_ErrorCode.parameter_outOfBound
+    # new parameter of this library (include/zstd_b200.h): the value in the header, the Python mirror and the library agree
+    hdr = open(os.path.join(ROOT, "include", "zstd_b200.h")).read()
+    assert int(re.search(r"#define\s+ZSTDB200_c_independentChunks\s+(\d+)", hdr).group(1)) == api.ZSTD_cParameter.ZSTDB200_c_independentChunks
+    c.SetParameter(api.ZSTD_cParameter.ZSTDB200_c_independentChunks, 1)
+    c.SetParameter(api.ZSTD_cParameter.ZSTDB200_c_independentChunks, 0)
+    try:
+        c.SetParameter(api.ZSTD_cParameter.ZSTDB200_c_independentChunks, 2)
+        raise AssertionError("expected parameter_outOfBound")
+    except api.ZstdException as e:
+        assert e.Code == api.ZSTD_ErrorCode.parameter_outOfBound
     for bad in ((api.ZSTD_cParameter.ZSTD_c_compressionLevel, 7), (160, 1)):
         try:
             c.SetParameter(*bad)

@@ -816,19 +816,22 @@ constexpr uint32_t kSeqChunk = 32;             // 4 x 32 B of ring per item (a s
 // shared-memory table entry = 24 bits: u16 {nbBits 4 | addBits 5 | symbol 6 | next-state base bit 8} + u8 {next-state base bits 0..7}
 constexpr uint32_t kSeqTab16Bytes = kFseTableEntries * 2, kSeqTab8Bytes = kFseTableEntries;
 constexpr uint32_t kSeqItemBytes = kSeqTab16Bytes + kSeqTab8Bytes;
-constexpr uint32_t kSeqSmemBytes = kSeqItemsPerCta * (kSeqItemBytes + 4 * kSeqChunk);
+constexpr uint32_t kSeqFlush = 8;              // sequences per record flush
+constexpr uint32_t kSeqSmemBytes = kSeqItemsPerCta * (kSeqItemBytes + 4 * kSeqChunk) + kSeqFlush * kSeqItemsPerCta * 8;
 __device__ __forceinline__ uint32_t lds8(uint32_t saddr) { uint16_t v; asm("ld.shared.u8 %0, [%1];" : "=h"(v) : "r"(saddr)); return v; }
 
 __global__ void __launch_bounds__(32) dec_seq_kernel(DecPass p)
 {
-    extern __shared__ __align__(256) uint8_t s_seq_raw[];   // [kSeqItemsPerCta] rings of 128 B, then per item: u16[1280] | u8[1280] tables
+    extern __shared__ __align__(256) uint8_t s_seq_raw[];   // [14] rings of 128 B | per item: u16[1280] | u8[1280] tables | record staging [8][14] x 8 B
     uint8_t* const s_tabs = s_seq_raw + kSeqItemsPerCta * 4 * kSeqChunk;
+    uint2* const s_stage = (uint2*)(s_tabs + kSeqItemsPerCta * kSeqItemBytes);
     __shared__ uint32_t s_llBase[64], s_mlBase[64];
     uint32_t const nWork = p.counters[1];
     uint32_t const first = blockIdx.x * kSeqItemsPerCta;
     if (first >= nWork) return;
     uint32_t const nHere = min((uint32_t)kSeqItemsPerCta, nWork - first);
     uint32_t const lane = threadIdx.x;
+    constexpr uint32_t FULL = 0xFFFFFFFFu;
     for (uint32_t k = 0; k < nHere; k++) {
         uint32_t const item = p.seqList[first + k];
         const uint4* g = (const uint4*)(p.fseTable + (size_t)item * kFseTableEntries);
@@ -843,89 +846,120 @@ __global__ void __launch_bounds__(32) dec_seq_kernel(DecPass p)
     }
     for (uint32_t u = lane; u < 64; u += 32) { s_llBase[u] = u < 36 ? c_LL_base[u] : 0u; s_mlBase[u] = u < 53 ? c_ML_base[u] : 0u; }
     __syncwarp();
-    if (lane >= nHere) return;
-    uint32_t const item = p.seqList[first + lane];
+    // Lanes 0..13 own one item each; all 32 lanes stay for the record flush (below).
+    bool const mine = lane < nHere;
+    uint32_t const item = p.seqList[first + (mine ? lane : 0)];
     DecItem& it = p.items[item];
-    if (it.status != kStRunning) return;
+    bool const live = mine && it.status == kStRunning;
     // state registers hold the entry INDEX (table offset included); the u16 part sits at t16 + 2*idx, the u8 part at t8 + idx
-    uint32_t const t16 = (uint32_t)__cvta_generic_to_shared(s_tabs + lane * kSeqItemBytes), t8 = t16 + kSeqTab16Bytes;
+    uint32_t const slotL = mine ? lane : 0u;
+    uint32_t const t16 = (uint32_t)__cvta_generic_to_shared(s_tabs + slotL * kSeqItemBytes), t8 = t16 + kSeqTab16Bytes;
     uint32_t const llBaseS = (uint32_t)__cvta_generic_to_shared(s_llBase), mlBaseS = (uint32_t)__cvta_generic_to_shared(s_mlBase);
-    uint2* const oSeq = p.seq + (size_t)item * kSeqCap;
-    const uint8_t* const src = p.src + it.srcOff;
-    uint32_t const nbSeq = it.nbSeq;
+    uint32_t const nbSeq = live ? it.nbSeq : 0u;
     // one refill (up to two chunks) per two sequences: they consume <= 178 bits and read down to chunk cur-2, which was requested
     // more than 48 bytes = more than 2 refills ago
     BitRingU<6, 2> br;
-    uint32_t err = 0;
-    uint32_t G = br.init((uint32_t)__cvta_generic_to_shared(s_seq_raw) + lane * (4 * kSeqChunk), src + it.seqOff, it.seqLen);
+    br.idle();
+    uint32_t err = 0, G = 1;
+    if (live) {
+        G = br.init((uint32_t)__cvta_generic_to_shared(s_seq_raw) + lane * (4 * kSeqChunk), p.src + it.srcOff + it.seqOff, it.seqLen);
+        if (G == 0) { err = kCorruptionDetected; G = 1; }
+    }
     br.settle();
-    if (G == 0) err = kCorruptionDetected;
     int32_t const gz = (int32_t)br.gZero;
     uint32_t rep0 = it.rep[0], rep1 = it.rep[1], rep2 = it.rep[2];
-    uint32_t outPos = it.outPos; uint32_t const frameStart = it.frameStart, dstCap = it.dstCap;
+    uint32_t outPos = it.outPos; uint32_t const outPos0 = outPos, frameStart = it.frameStart, dstCap = it.dstCap;
     uint32_t litPos = 0; uint32_t const litSize = it.litSize;
-    if (!err) {
+    uint32_t aL = kFseLLOff, aO = kFseOFOff, aM = kFseMLOff;
+    if (live && !err) {
         // ZSTD_initFseState x3 in the order LL, OF, ML (:2702-2704)
         uint32_t const llLog = it.llLog, ofLog = it.ofLog, mlLog = it.mlLog;
         uint32_t x = br.peek32(G);
-        uint32_t aL = kFseLLOff + top_bits(x, llLog); x <<= llLog;
-        uint32_t aO = kFseOFOff + top_bits(x, ofLog); x <<= ofLog;
-        uint32_t aM = kFseMLOff + top_bits(x, mlLog);
+        aL = kFseLLOff + top_bits(x, llLog); x <<= llLog;
+        aO = kFseOFOff + top_bits(x, ofLog); x <<= ofLog;
+        aM = kFseMLOff + top_bits(x, mlLog);
         G -= llLog + ofLog + mlLog;
         if ((int32_t)G < gz) err = kCorruptionDetected;
-        for (uint32_t n = 0; n < nbSeq && !err; n++) {
-            if ((n & 1) == 0) br.step<2>(G, true);
-            uint32_t const eL = lds16(t16 + 2 * aL), eO = lds16(t16 + 2 * aO), eM = lds16(t16 + 2 * aM);
-            uint32_t const nL = lds8(t8 + aL), nO = lds8(t8 + aO), nM = lds8(t8 + aM);
-            uint32_t const llBits = (eL >> 4) & 31, mlBits = (eM >> 4) & 31, ofBits = (eO >> 4) & 31;
-            uint32_t const nbL = eL & 15, nbM = eM & 15, nbO = eO & 15;
-            // stream order: offset extra, matchLength extra, litLength extra, then LL / ML / OF state bits (:2397-2480)
-            uint32_t const G1 = G - ofBits, G2 = G1 - (mlBits + llBits), G3 = G2 - (nbL + nbM + nbO);
-            uint32_t xA, xA1; br.peek64(G, xA, xA1);                      // offset extra, then matchLength + litLength extra: <= 63 bits
-            uint32_t const xB = __funnelshift_l(xA1, xA, ofBits), xC = br.peek32(G2);
-            uint32_t const llSym = (eL >> 9) & 63, mlSym = (eM >> 9) & 63;
-            uint32_t const ofExtra = top_bits(xA, ofBits);
-            uint32_t const ml = lds32(mlBaseS + mlSym * 4) + top_bits(xB, mlBits);
-            uint32_t const ll = lds32(llBaseS + llSym * 4) + top_bits(xB << mlBits, llBits);     // mlBits <= 16
-            aL = kFseLLOff + (nL | ((eL >> 15) << 8)) + top_bits(xC, nbL);
-            uint32_t const xC2 = xC << nbL;
-            aM = kFseMLOff + (nM | ((eM >> 15) << 8)) + top_bits(xC2, nbM);
-            aO = kFseOFOff + (nO | ((eO >> 15) << 8)) + top_bits(xC2 << nbM, nbO);
-            bool const overRead = (int32_t)G2 < gz;                      // the extra bits must exist; the last state update may run dry
-            bool const dry = (int32_t)G3 < gz;
-            G = G3;
-            uint32_t offset;
-            {   // ZSTD_decodeSequence offset rules (:2397-2445), as selects
-                uint32_t const ll0 = (llSym == 0);                        // baseValue == 0 <=> code 0
-                uint32_t const ofv = 1u + ll0 + ofExtra;                  // only meaningful for ofBits == 1 (OF_base[1] = 1)
-                uint32_t t1 = (ofv == 3) ? rep0 - 1 : (ofv == 1 ? rep1 : rep2);
-                t1 += !t1;
-                uint32_t const big = ((1u << ofBits) - 3u) + ofExtra;     // OF_base[n] = (1<<n)-3 for n >= 2
-                uint32_t const t0 = ll0 ? rep1 : rep0;
-                offset = ofBits > 1 ? big : (ofBits == 0 ? t0 : t1);
-                // history update
-                bool const shift2 = (ofBits > 1) | ((ofBits == 1) & (ofv != 1));     // rep2 <- rep1
-                bool const shift1 = (ofBits > 0) | (ll0 != 0);                       // rep1 <- rep0
-                uint32_t const n2 = shift2 ? rep1 : rep2;
-                uint32_t const n1 = shift1 ? rep0 : rep1;
-                rep2 = n2; rep1 = n1; rep0 = offset;
-            }
-            // validity (ZSTD_execSequenceEnd order): output overflow, literal overrun, offset beyond frame start
-            uint32_t const seqLen = ll + ml;
-            bool const e1 = seqLen > dstCap - outPos, e2 = ll > litSize - litPos, e3 = offset > (outPos + ll) - frameStart;
-            bool const e4 = overRead | ((n + 1 < nbSeq) & dry) | ((offset >> 30) != 0);   // offsets >= 1 GiB do not fit seq_pack
-            if (e1 | e2 | e3 | e4) err = e1 ? kDstSizeTooSmall : kCorruptionDetected;
-            oSeq[n] = seq_pack(ll, ml, offset);
-            outPos += seqLen; litPos += ll;
-        }
-        // the stream must not have unread bits left (BIT_reloadDStream >= completed, :2730)
-        if (!err && (int32_t)G > gz) err = kCorruptionDetected;
-        if (!err && (litSize - litPos) > dstCap - outPos) err = kDstSizeTooSmall;   // last literals, :2748
     }
+    uint32_t maxSeq = (live && !err) ? nbSeq : 0u;
+#pragma unroll
+    for (int d = 16; d; d >>= 1) maxSeq = max(maxSeq, __shfl_xor_sync(FULL, maxSeq, d));
+    // Records go to HBM through a shared-memory staging block of kSeqFlush steps: one 8-byte store per lane and step to 14
+    // different cache lines cost a quarter of this kernel (the chain's shared loads queue behind the scattered store in the
+    // LSU); the flush writes each item's records of a block as contiguous bytes, 4 items per instruction.
+    uint64_t const seqBase = (uint64_t)item * kSeqCap;
+    for (uint32_t n0 = 0; n0 < maxSeq; n0 += kSeqFlush) {
+        uint32_t cnt = 0;                                  // records this lane staged in the block
+#pragma unroll 2
+        for (uint32_t k = 0; k < kSeqFlush; k++) {
+            uint32_t const n = n0 + k;
+            bool const act = live && !err && n < nbSeq;
+            if ((k & 1) == 0) br.step<2>(G, act);
+            if (act) {
+                uint32_t const eL = lds16(t16 + 2 * aL), eO = lds16(t16 + 2 * aO), eM = lds16(t16 + 2 * aM);
+                uint32_t const nL = lds8(t8 + aL), nO = lds8(t8 + aO), nM = lds8(t8 + aM);
+                uint32_t const llBits = (eL >> 4) & 31, mlBits = (eM >> 4) & 31, ofBits = (eO >> 4) & 31;
+                uint32_t const nbL = eL & 15, nbM = eM & 15, nbO = eO & 15;
+                // stream order: offset extra, matchLength extra, litLength extra, then LL / ML / OF state bits (:2397-2480)
+                uint32_t const G2 = G - (ofBits + mlBits + llBits), G3 = G2 - (nbL + nbM + nbO);
+                uint32_t xA, xA1; br.peek64(G, xA, xA1);                      // offset extra, then matchLength + litLength extra: <= 63 bits
+                uint32_t const xB = __funnelshift_l(xA1, xA, ofBits), xC = br.peek32(G2);
+                uint32_t const llSym = (eL >> 9) & 63, mlSym = (eM >> 9) & 63;
+                uint32_t const ofExtra = top_bits(xA, ofBits);
+                uint32_t const ml = lds32(mlBaseS + mlSym * 4) + top_bits(xB, mlBits);
+                uint32_t const ll = lds32(llBaseS + llSym * 4) + top_bits(xB << mlBits, llBits);     // mlBits <= 16
+                aL = kFseLLOff + (nL | ((eL >> 15) << 8)) + top_bits(xC, nbL);
+                uint32_t const xC2 = xC << nbL;
+                aM = kFseMLOff + (nM | ((eM >> 15) << 8)) + top_bits(xC2, nbM);
+                aO = kFseOFOff + (nO | ((eO >> 15) << 8)) + top_bits(xC2 << nbM, nbO);
+                bool const overRead = (int32_t)G2 < gz;                      // the extra bits must exist; the last state update may run dry
+                bool const dry = (int32_t)G3 < gz;
+                G = G3;
+                uint32_t offset;
+                {   // ZSTD_decodeSequence offset rules (:2397-2445), as selects
+                    uint32_t const ll0 = (llSym == 0);                        // baseValue == 0 <=> code 0
+                    uint32_t const ofv = 1u + ll0 + ofExtra;                  // only meaningful for ofBits == 1 (OF_base[1] = 1)
+                    uint32_t t1 = (ofv == 3) ? rep0 - 1 : (ofv == 1 ? rep1 : rep2);
+                    t1 += !t1;
+                    uint32_t const big = ((1u << ofBits) - 3u) + ofExtra;     // OF_base[n] = (1<<n)-3 for n >= 2
+                    uint32_t const t0 = ll0 ? rep1 : rep0;
+                    offset = ofBits > 1 ? big : (ofBits == 0 ? t0 : t1);
+                    // history update
+                    bool const shift2 = (ofBits > 1) | ((ofBits == 1) & (ofv != 1));     // rep2 <- rep1
+                    bool const shift1 = (ofBits > 0) | (ll0 != 0);                       // rep1 <- rep0
+                    uint32_t const n2 = shift2 ? rep1 : rep2;
+                    uint32_t const n1 = shift1 ? rep0 : rep1;
+                    rep2 = n2; rep1 = n1; rep0 = offset;
+                }
+                // validity (ZSTD_execSequenceEnd order): output overflow, literal overrun, offset beyond frame start
+                uint32_t const seqLen = ll + ml;
+                bool const e1 = seqLen > dstCap - outPos, e2 = ll > litSize - litPos, e3 = offset > (outPos + ll) - frameStart;
+                bool const e4 = overRead | ((n + 1 < nbSeq) & dry) | ((offset >> 30) != 0);   // offsets >= 1 GiB do not fit seq_pack
+                if (e1 | e2 | e3 | e4) err = e1 ? kDstSizeTooSmall : kCorruptionDetected;
+                s_stage[k * kSeqItemsPerCta + lane] = seq_pack(ll, ml, offset);
+                cnt = k + 1;
+                outPos += seqLen; litPos += ll;
+            }
+        }
+        __syncwarp();
+#pragma unroll
+        for (uint32_t q = 0; q < (kSeqFlush * kSeqItemsPerCta + 31) / 32; q++) {
+            uint32_t const idx = q * 32 + lane, slot = idx / kSeqFlush, k = idx % kSeqFlush;
+            uint32_t const srcLane = slot < (uint32_t)kSeqItemsPerCta ? slot : 0u;
+            uint32_t const c = __shfl_sync(FULL, cnt, srcLane);
+            uint64_t const base = __shfl_sync(FULL, seqBase, srcLane);
+            if (slot < (uint32_t)kSeqItemsPerCta && k < c) p.seq[base + n0 + k] = s_stage[k * kSeqItemsPerCta + slot];
+        }
+        __syncwarp();
+    }
+    if (!live) return;
+    // the stream must not have unread bits left (BIT_reloadDStream >= completed, :2730)
+    if (!err && (int32_t)G > gz) err = kCorruptionDetected;
+    if (!err && (litSize - litPos) > dstCap - outPos) err = kDstSizeTooSmall;   // last literals, :2748
     if (err) { it.status = kStError; it.errCode = err; return; }
     it.rep[0] = rep0; it.rep[1] = rep1; it.rep[2] = rep2;
     it.seqLitEnd = litPos;
-    it.blockOut = (outPos - it.outPos) + (litSize - litPos);
+    it.blockOut = (outPos - outPos0) + (litSize - litPos);
 }
 
 // =====================================================================================================
