@@ -37,6 +37,13 @@ def inputs():
     yield "zeros_128k", bytes(dg.FRAME)
     yield "literal_heavy_128k", dg.literal_heavy(dg.FRAME).tobytes()
     yield "text_1m_multiblock", dg.text_like(8 * dg.FRAME).tobytes()
+    # multi-block frames that exercise the block-to-block state (same shapes as tests/_cases.py)
+    text = dg.text_like(6 * dg.FRAME); rnd = dg.incompressible(dg.FRAME); zeros = np.zeros(3 * dg.FRAME, dtype=np.uint8)
+    yield "multiblock_text_128k+6", text[:dg.FRAME + 6].tobytes()                                   # raw last block of 6 bytes
+    yield "multiblock_text_600k", text[:600_000].tobytes()                                          # window smaller than the frame
+    yield "multiblock_zeros_384k", zeros.tobytes()                                                  # RLE blocks after the first
+    yield "multiblock_text_random_text", np.concatenate([text[:dg.FRAME + 5000], rnd, text[dg.FRAME:3 * dg.FRAME]]).tobytes()   # unconfirmed raw block
+    yield "multiblock_literal_heavy_512k", dg.literal_heavy(4 * dg.FRAME).tobytes()                 # Huffman table reuse
 
 
 def main():

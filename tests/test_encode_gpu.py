@@ -220,3 +220,29 @@ def test_independent_chunks_parameter(comp, dec):
     assert blob[:len(first)] == first
     single = o.compress(data, 1)                       # the reference's one multi-block frame (window spans the blocks)
     assert len(blob) < 1.06 * len(single)              # independent pieces cost a few percent of ratio, not more
+
+
+def test_golden_vectors_on_gpu(comp):
+    """The committed golden vectors (tests/golden/golden_vectors.json, written by libzstd 1.5.5; inputs regenerated by
+    make_golden.inputs()) against the GPU compressor directly, without the oracle in between."""
+    import hashlib, importlib.util, json, os
+    here = os.path.dirname(os.path.abspath(__file__))
+    spec = importlib.util.spec_from_file_location("make_golden", os.path.join(here, "golden", "make_golden.py"))
+    mod = importlib.util.module_from_spec(spec); spec.loader.exec_module(mod)
+    inputs = dict(mod.inputs())
+    gold = json.load(open(os.path.join(here, "golden", "golden_vectors.json")))["vectors"]
+    for level in (1, 2, 3):
+        comp.Level = level
+        vs = [v for v in gold if v["level"] == level]
+        pieces, owner = [], []
+        for v in vs:
+            data = np.frombuffer(inputs[v["name"]], dtype=np.uint8)
+            whole = data.size <= FRAME or "multiblock" in v["name"]
+            ps = [data] if whole else _chunks(data)
+            pieces += ps; owner += [v["name"]] * len(ps)
+        frames = comp.WrapBatch(pieces)
+        for v in vs:
+            mine = [f for f, o in zip(frames, owner) if o == v["name"]]
+            assert [len(f) for f in mine] == v["frame_sizes"], (v["name"], level)
+            assert hashlib.sha256(b"".join(mine)).hexdigest() == v["frames_sha256"], (v["name"], level)
+    comp.Level = 1
