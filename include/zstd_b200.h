@@ -63,6 +63,12 @@ ZSTDB200_API size_t     ZSTD_compressBound(size_t srcSize);                     
  * zstd decoder, ZSTD_decompressBound = item size, a few percent larger, NOT the reference's bytes). */
 #define ZSTDB200_c_independentChunks 10001
 ZSTDB200_API size_t     ZSTD_CCtx_setParameter(ZSTD_CCtx* cctx, int param, int value);             /* :37 */
+/* Decompressor.LoadDictionary (Decompressor.cs:43-56 -> U/ZstdDecompress.cs:2239 ZSTD_DCtx_loadDictionary): the dictionary is
+ * copied; a zstd-format dictionary (magic 0xEC30A437: entropy tables, repcodes, content, U/ZstdDecompress.cs:1770-1931) or raw
+ * content.  It then applies to every ZSTD_decompressDCtx / ZSTDB200_decompressBatch call of the context; NULL / 0 removes it.
+ * A corrupted dictionary is reported here (ZSTD_error_dictionary_corrupted) rather than at the first decompression.
+ * With a dictionary, an item holds ONE frame (further frames in the same buffer: ZSTD_error_frameParameter_unsupported). */
+ZSTDB200_API size_t     ZSTD_DCtx_loadDictionary(ZSTD_DCtx* dctx, const void* dict, size_t dictSize);
 /* needed by the safe wrappers in addition (Decompressor.cs:53, ThrowHelper.cs:12-13) */
 ZSTDB200_API unsigned long long ZSTD_decompressBound(const void* src, size_t srcSize);
 /* compressed size of the first frame (regular or skippable) at src; used by the stream adapter to cut a concatenated

@@ -44,6 +44,9 @@ size_t zo_decompressDCtx(void* dctx, void* dst, size_t dstCapacity, const void* 
 
 /* Multi-frame decompression incl. skippable frames and checksum verification. */
 size_t             zo_decompress(void* dst, size_t dstCapacity, const void* src, size_t srcSize);
+/* Decompressor.LoadDictionary + Unwrap (Decompressor.cs:43-56 -> Unsafe/ZstdDecompress.cs:1770-1931): raw-content or
+ * zstd-format dictionary (magic 0xEC30A437: entropy tables + repcodes + content), applied to every frame of src. */
+size_t             zo_decompress_usingDict(void* dst, size_t dstCapacity, const void* src, size_t srcSize, const void* dict, size_t dictSize);
 unsigned long long zo_decompressBound(const void* src, size_t srcSize);
 size_t             zo_findFrameCompressedSize(const void* src, size_t srcSize);
 

@@ -469,6 +469,8 @@ typedef struct {
     const BYTE* litPtr; size_t litSize;
     BYTE litBuffer[ZSTD_BLOCKSIZE_MAX + 32];
     const BYTE* prefixStart;
+    /* dictionary (ZstdDecompress.cs:1752-1931): content = external segment that ends where the frame's output begins */
+    const BYTE* dictEnd; size_t dictContentSize; U32 loadedDictID;
     /* frame params */
     U64 frameContentSize; U64 windowSize; U32 blockSizeMax; U32 dictID; U32 checksumFlag; U32 headerSize;
 } zo_DCtx;
@@ -479,6 +481,7 @@ static void zo_decompressBegin(zo_DCtx* d)    /* ZstdDecompress.cs:1933 ZSTD_dec
     memcpy(d->rep, repStartValue, sizeof(repStartValue));
     d->LLTptr = &d->LLTable; d->MLTptr = &d->MLTable; d->OFTptr = &d->OFTable;
     d->prefixStart = NULL;
+    d->dictEnd = NULL; d->dictContentSize = 0; d->loadedDictID = 0;
 }
 
 /* ---- literals : ZstdDecompressBlock.cs:88 ZSTD_decodeLiteralsBlock ---- */
@@ -687,7 +690,8 @@ static seq_t ZSTD_decodeSequence(seqState_t* seqState)   /* 64-bit build, longOf
 
 /* ZSTD_execSequence / ZSTD_execSequenceEnd semantics (checks in the order of :2083-2103); the copy itself is a
  * byte-forward copy, which is what wildcopy/overlapCopy8 compute for src-before-dst overlaps. */
-static size_t zo_execSequence(BYTE* op, BYTE* const oend, seq_t sequence, const BYTE** litPtr, const BYTE* const litLimit, const BYTE* const prefixStart)
+static size_t zo_execSequence(BYTE* op, BYTE* const oend, seq_t sequence, const BYTE** litPtr, const BYTE* const litLimit, const BYTE* const prefixStart,
+                              const BYTE* const dictEnd, size_t const dictContentSize)
 {
     BYTE* const oLitEnd = op + sequence.litLength;
     size_t const sequenceLength = sequence.litLength + sequence.matchLength;
@@ -696,7 +700,18 @@ static size_t zo_execSequence(BYTE* op, BYTE* const oend, seq_t sequence, const 
     if (sequence.litLength > (size_t)(litLimit - *litPtr)) return ERROR(corruption_detected);
     memmove(op, *litPtr, sequence.litLength);
     *litPtr += sequence.litLength;
-    if (sequence.offset > (size_t)(oLitEnd - prefixStart)) return ERROR(corruption_detected);   /* no dictionary: virtualStart == prefixStart */
+    if (sequence.offset > (size_t)(oLitEnd - prefixStart)) {
+        /* offset beyond prefix -> go into the dictionary segment (:2232-2252); virtualStart = prefixStart - dictContentSize */
+        size_t const back = sequence.offset - (size_t)(oLitEnd - prefixStart);      /* bytes before prefixStart */
+        if (back > dictContentSize) return ERROR(corruption_detected);
+        match = dictEnd - back;
+        if (back >= sequence.matchLength) { memmove(oLitEnd, match, sequence.matchLength); return sequenceLength; }
+        memmove(oLitEnd, match, back);                                              /* span dictionary end and prefix start */
+        {   BYTE* o = oLitEnd + back; size_t const ml = sequence.matchLength - back; size_t i;
+            match = prefixStart;
+            for (i = 0; i < ml; i++) o[i] = match[i]; }
+        return sequenceLength;
+    }
     {   BYTE* o = oLitEnd; size_t const ml = sequence.matchLength;
         if (sequence.offset >= ml) memcpy(o, match, ml);               /* no overlap */
         else if (sequence.offset >= 8) { size_t i = 0; for (; i + 8 <= ml; i += 8) memcpy(o + i, match + i, 8); for (; i < ml; i++) o[i] = match[i]; }
@@ -723,7 +738,7 @@ static size_t zo_decompressSequences(zo_DCtx* dctx, void* dst, size_t maxDstSize
         ZSTD_initFseState(&seqState.stateML, &seqState.DStream, dctx->MLTptr);
         for (;;) {
             seq_t const sequence = ZSTD_decodeSequence(&seqState);
-            size_t const oneSeqSize = zo_execSequence(op, oend, sequence, &litPtr, litEnd, prefixStart);
+            size_t const oneSeqSize = zo_execSequence(op, oend, sequence, &litPtr, litEnd, prefixStart, dctx->dictEnd, dctx->dictContentSize);
             if (tap && tap->n < tap->cap) { tap->triples[3 * tap->n] = (U32)sequence.litLength; tap->triples[3 * tap->n + 1] = (U32)sequence.matchLength; tap->triples[3 * tap->n + 2] = (U32)sequence.offset; }
             if (tap) tap->n++;
             if (ERR_isError(oneSeqSize)) return oneSeqSize;
@@ -906,7 +921,7 @@ static size_t zo_decompressFrame(zo_DCtx* dctx, void* dst, size_t dstCapacity, c
         {   size_t const result = zo_getFrameHeader(&zfh, ip, frameHeaderSize);      /* :834 ZSTD_decodeFrameHeader */
             if (ERR_isError(result)) return result;
             if (result > 0) return ERROR(srcSize_wrong);
-            if (zfh.dictID != 0) return ERROR(dictionary_wrong); }
+            if (zfh.dictID != 0 && dctx->loadedDictID != zfh.dictID) return ERROR(dictionary_wrong); }   /* :849 */
         ip += frameHeaderSize; remainingSrcSize -= frameHeaderSize;
     }
     for (;;) {
@@ -987,6 +1002,76 @@ size_t zo_decompressDCtx(void* ctx, void* dst, size_t dstCapacity, const void* s
     }
     if (srcSize) return ERROR(srcSize_wrong);
     return (size_t)((BYTE*)dst - (BYTE*)dststart);
+}
+
+/* ZstdDecompress.cs:1770 ZSTD_loadDEntropy + :1880 ZSTD_decompress_insertDictionary + :1752 ZSTD_refDictContent, applied at every
+ * frame start as ZSTD_decompressBegin_usingDict does (:1954). */
+static size_t zo_insertDictionary(zo_DCtx* dctx, const void* dict, size_t dictSize)
+{
+    const BYTE* dictPtr = (const BYTE*)dict; const BYTE* const dEnd = dictPtr + dictSize;
+    if (dictSize >= 8 && MEM_read32(dict) == 0xEC30A437U) {
+        dctx->loadedDictID = MEM_read32(dictPtr + 4);
+        dictPtr += 8;
+        {   size_t const hSize = HUF_readDTableX1(&dctx->hufTable, dictPtr, (size_t)(dEnd - dictPtr));     /* the reference builds the X2 form of the same code */
+            if (ERR_isError(hSize)) return ERROR(dictionary_corrupted);
+            dictPtr += hSize; }
+        {   S16 norm[MaxOff + 1]; unsigned maxV = MaxOff, log;
+            size_t const h = FSE_readNCount(norm, &maxV, &log, dictPtr, (size_t)(dEnd - dictPtr));
+            if (ERR_isError(h) || maxV > MaxOff || log > OffFSELog) return ERROR(dictionary_corrupted);
+            ZSTD_buildFSETable(&dctx->OFTable, norm, maxV, OF_base, OF_bits, log);
+            dictPtr += h; }
+        {   S16 norm[MaxML + 1]; unsigned maxV = MaxML, log;
+            size_t const h = FSE_readNCount(norm, &maxV, &log, dictPtr, (size_t)(dEnd - dictPtr));
+            if (ERR_isError(h) || maxV > MaxML || log > MLFSELog) return ERROR(dictionary_corrupted);
+            ZSTD_buildFSETable(&dctx->MLTable, norm, maxV, ML_base, ML_bits, log);
+            dictPtr += h; }
+        {   S16 norm[MaxLL + 1]; unsigned maxV = MaxLL, log;
+            size_t const h = FSE_readNCount(norm, &maxV, &log, dictPtr, (size_t)(dEnd - dictPtr));
+            if (ERR_isError(h) || maxV > MaxLL || log > LLFSELog) return ERROR(dictionary_corrupted);
+            ZSTD_buildFSETable(&dctx->LLTable, norm, maxV, LL_base, LL_bits, log);
+            dictPtr += h; }
+        if (dictPtr + 12 > dEnd) return ERROR(dictionary_corrupted);
+        {   size_t const contentSize = (size_t)(dEnd - (dictPtr + 12)); int i;
+            for (i = 0; i < 3; i++) {
+                U32 const r = MEM_read32(dictPtr); dictPtr += 4;
+                if (r == 0 || r > contentSize) return ERROR(dictionary_corrupted);
+                dctx->rep[i] = r;
+        }   }
+        dctx->litEntropy = dctx->fseEntropy = 1;
+    }
+    dctx->dictEnd = dEnd; dctx->dictContentSize = (size_t)(dEnd - dictPtr);
+    return 0;
+}
+
+/* Decompressor.Unwrap after LoadDictionary: ZSTD_decompress_usingDict -> ZSTD_decompressMultiFrame (:1216) with a dictionary */
+size_t zo_decompress_usingDict(void* dst, size_t dstCapacity, const void* src, size_t srcSize, const void* dict, size_t dictSize)
+{
+    void* const dststart = dst; int moreThan1Frame = 0; size_t result = 0;
+    zo_DCtx* const dctx = (zo_DCtx*)zo_createDCtx();
+    if (!dctx) return ERROR(memory_allocation);
+    while (srcSize >= 5) {
+        {   U32 const magicNumber = MEM_read32(src);
+            if ((magicNumber & ZSTD_MAGIC_SKIPPABLE_MASK) == ZSTD_MAGIC_SKIPPABLE_START) {
+                size_t const skippableSize = zo_readSkippableFrameSize(src, srcSize);
+                if (ERR_isError(skippableSize)) { result = skippableSize; goto done; }
+                src = (const BYTE*)src + skippableSize; srcSize -= skippableSize;
+                continue;
+        }   }
+        zo_decompressBegin(dctx);
+        if (dict && dictSize) { size_t const r = zo_insertDictionary(dctx, dict, dictSize); if (ERR_isError(r)) { result = r; goto done; } }
+        dctx->prefixStart = (const BYTE*)dst;
+        {   size_t const res = zo_decompressFrame(dctx, dst, dstCapacity, &src, &srcSize, NULL, 0);
+            if ((zo_getErrorCode(res) == ZO_error_prefix_unknown) && (moreThan1Frame == 1)) { result = ERROR(srcSize_wrong); goto done; }
+            if (ERR_isError(res)) { result = res; goto done; }
+            if (res != 0) dst = (BYTE*)dst + res;
+            dstCapacity -= res;
+        }
+        moreThan1Frame = 1;
+    }
+    result = srcSize ? ERROR(srcSize_wrong) : (size_t)((BYTE*)dst - (BYTE*)dststart);
+done:
+    zo_freeDCtx(dctx);
+    return result;
 }
 
 size_t zo_decompress(void* dst, size_t dstCapacity, const void* src, size_t srcSize)

@@ -38,6 +38,7 @@ class Oracle:
         _sig(L.zo_compress, st, [vp, st, vp, st, ci])
         _sig(L.zo_compress_advanced, st, [vp, st, vp, st, ci, ci])
         _sig(L.zo_decompress, st, [vp, st, vp, st])
+        _sig(L.zo_decompress_usingDict, st, [vp, st, vp, st, vp, st])
         _sig(L.zo_createCCtx, vp, [])
         _sig(L.zo_freeCCtx, None, [vp])
         _sig(L.zo_compressCCtx, st, [vp, vp, st, vp, st, ci, ci])
@@ -78,6 +79,18 @@ class Oracle:
 
     def decompress(self, frame, cap: int) -> bytes:
         r, out = self.decompress_raw(frame, cap)
+        assert not self.lib.zo_isError(r), self.lib.zo_getErrorName(r)
+        return out[:r].tobytes()
+
+    def decompress_using_dict_raw(self, frame, cap: int, dictionary):
+        a, p = self._buf(frame)
+        d, dp = self._buf(dictionary)
+        out = np.empty(max(cap, 1), dtype=np.uint8)
+        r = self.lib.zo_decompress_usingDict(out.ctypes.data, cap, p, a.size, dp, d.size)
+        return r, out
+
+    def decompress_using_dict(self, frame, cap: int, dictionary) -> bytes:
+        r, out = self.decompress_using_dict_raw(frame, cap, dictionary)
         assert not self.lib.zo_isError(r), self.lib.zo_getErrorName(r)
         return out[:r].tobytes()
 
@@ -137,6 +150,12 @@ class LibZstd:
         _sig(L.ZSTD_freeCCtx, st, [vp])
         _sig(L.ZSTD_CCtx_setParameter, st, [vp, ci, ci])
         _sig(L.ZSTD_compress2, st, [vp, vp, st, vp, st])
+        _sig(L.ZSTD_compress_usingDict, st, [vp, vp, st, vp, st, vp, st, ci])
+        _sig(L.ZSTD_createDCtx, vp, [])
+        _sig(L.ZSTD_freeDCtx, st, [vp])
+        _sig(L.ZSTD_decompress_usingDict, st, [vp, vp, st, vp, st, vp, st])
+        _sig(L.ZDICT_trainFromBuffer, st, [vp, st, vp, ctypes.POINTER(st), ctypes.c_uint])
+        _sig(L.ZDICT_isError, ctypes.c_uint, [st])
 
     def compress(self, data, level: int, checksum: int = 0) -> bytes:
         a, p = Oracle._buf(data)
@@ -166,6 +185,37 @@ class LibZstd:
 
     def error_code(self, rv: int) -> int:
         return self.lib.ZSTD_getErrorCode(rv)
+
+    # ---- dictionaries (test inputs only: ZDICT training and dictionary compression are not on the GPU path) ----
+    def train_dictionary(self, samples, capacity: int) -> bytes:
+        """ZDICT_trainFromBuffer: a zstd-format dictionary (magic 0xEC30A437, entropy tables, repcodes, content)."""
+        blob = b"".join(bytes(x) for x in samples)
+        sizes = (ctypes.c_size_t * len(samples))(*[len(bytes(x)) for x in samples])
+        a = np.frombuffer(blob, dtype=np.uint8)
+        out = np.empty(capacity, dtype=np.uint8)
+        r = self.lib.ZDICT_trainFromBuffer(out.ctypes.data, capacity, a.ctypes.data, sizes, len(samples))
+        assert not self.lib.ZDICT_isError(r), "ZDICT_trainFromBuffer failed"
+        return out[:r].tobytes()
+
+    def compress_using_dict(self, data, level: int, dictionary) -> bytes:
+        a, p = Oracle._buf(data)
+        d, dp = Oracle._buf(dictionary)
+        cap = self.lib.ZSTD_compressBound(a.size)
+        out = np.empty(max(cap, 1), dtype=np.uint8)
+        c = self.lib.ZSTD_createCCtx()
+        r = self.lib.ZSTD_compress_usingDict(c, out.ctypes.data, cap, p, a.size, dp, d.size, level)
+        self.lib.ZSTD_freeCCtx(c)
+        assert not self.lib.ZSTD_isError(r)
+        return out[:r].tobytes()
+
+    def decompress_using_dict_raw(self, frame, cap: int, dictionary):
+        a, p = Oracle._buf(frame)
+        d, dp = Oracle._buf(dictionary)
+        out = np.empty(max(cap, 1), dtype=np.uint8)
+        c = self.lib.ZSTD_createDCtx()
+        r = self.lib.ZSTD_decompress_usingDict(c, out.ctypes.data, cap, p, a.size, dp, d.size)
+        self.lib.ZSTD_freeDCtx(c)
+        return r, out
 
 
 _ORACLE = None

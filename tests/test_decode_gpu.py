@@ -168,3 +168,45 @@ def test_frame_checksum_is_verified(dec):
         assert isinstance(r, ZstdException) and r.Code == ZSTD_ErrorCode.checksum_wrong
         assert o.error_code(o.decompress_raw(bytes(f), FRAME)[0]) == 22
     assert res[2] == data[:FRAME].tobytes()
+
+
+def test_dictionary_decoding(dec):
+    """SURVEY 8f.4, decode side: Decompressor.LoadDictionary + Unwrap (Decompressor.cs:43-56; ZstdDecompress.cs:1770-1931).
+    Frames and dictionaries come from libzstd; the oracle decodes them with the same dictionary."""
+    from _dict_cases import dictionaries, payloads
+    from zstdsharp_b200 import api
+    o, z = oracle(), libzstd()
+    dicts = dictionaries(z)
+    try:
+        for name, d in dicts.items():
+            dec.LoadDictionary(d)
+            srcs, frames = [], []
+            for level in (1, 3, 9, 19):
+                for src in payloads():
+                    srcs.append(src); frames.append(z.compress_using_dict(src, level, d))
+            got = dec.UnwrapBatch(frames)
+            for s_, f, g in zip(srcs, frames, got):
+                assert g == o.decompress_using_dict(f, s_.size, d) == s_.tobytes(), (name, s_.size)
+            # frames that do not use the dictionary still decode, single-call API included
+            plain = z.compress(srcs[3], 3)
+            assert dec.Unwrap(plain) == srcs[3].tobytes()
+            assert dec.Unwrap(frames[3]) == srcs[3].tobytes()
+        # wrong dictionary -> dictionary_wrong (32), as the oracle says; no dictionary -> dictionary_wrong as well
+        f = z.compress_using_dict(payloads()[3], 3, dicts["zdict_32k"])
+        dec.LoadDictionary(dicts["zdict_4k"])
+        with pytest.raises(api.ZstdException) as e:
+            dec.Unwrap(f, np.empty(70000, dtype=np.uint8))
+        assert e.value.Code == api.ZSTD_ErrorCode.dictionary_wrong
+        dec.LoadDictionary(None)
+        with pytest.raises(api.ZstdException) as e:
+            dec.Unwrap(f, np.empty(70000, dtype=np.uint8))
+        assert e.value.Code == api.ZSTD_ErrorCode.dictionary_wrong
+        # a corrupted dictionary is refused when it is loaded
+        bad = bytearray(dicts["zdict_32k"]); bad[8] = 0xFF; bad[9] = 0xFF
+        with pytest.raises(api.ZstdException) as e:
+            dec.LoadDictionary(bytes(bad))
+        assert e.value.Code == api.ZSTD_ErrorCode.dictionary_corrupted
+    finally:
+        dec.LoadDictionary(None)
+    # and the context is back to plain decoding
+    assert dec.Unwrap(z.compress(payloads()[2], 1)) == payloads()[2].tobytes()

@@ -95,6 +95,29 @@ def test_multiblock_shapes_match_libzstd():
         assert o.decompress(f, data.size) == data.tobytes(), name
 
 
+def test_dictionary_decoding_matches_libzstd():
+    """SURVEY 8f.4 (decode side): frames written with a dictionary by libzstd, decoded by the oracle with the same dictionary
+    (zstd-format with entropy tables and repcodes, raw content), concatenated frames, wrong / missing dictionary."""
+    from _dict_cases import dictionaries, payloads
+    o, z = oracle(), libzstd()
+    dicts = dictionaries(z)
+    for name, d in dicts.items():
+        for level in (1, 3, 9, 19):
+            for src in payloads():
+                f = z.compress_using_dict(src, level, d)
+                assert o.decompress_using_dict(f, src.size, d) == src.tobytes(), (name, level, src.size)
+        a, b = payloads()[2], payloads()[3]
+        f = z.compress_using_dict(a, 3, d) + z.compress_using_dict(b, 1, d)
+        assert o.decompress_using_dict(f, a.size + b.size, d) == a.tobytes() + b.tobytes()
+    # wrong dictionary: same verdict as libzstd (dictionary_wrong through the frame's dictID)
+    f = z.compress_using_dict(payloads()[3], 3, dicts["zdict_32k"])
+    r, _ = o.decompress_using_dict_raw(f, 70000, dicts["zdict_4k"])
+    rz, _ = z.decompress_using_dict_raw(f, 70000, dicts["zdict_4k"])
+    assert o.error_code(r) == z.error_code(rz) == 32
+    r, _ = o.decompress_raw(f, 70000)
+    assert o.error_code(r) == 32
+
+
 def test_cparams_table():
     o = oracle()
     # Clevels.cs:490 / :510 (rows 1 and 3 of the <=128 KB table) and the <=16 KB table (:713-743)

@@ -21,7 +21,7 @@ EXPORTED_SYMBOLS = [
     "ZSTD_getErrorName", "ZSTD_versionNumber", "ZSTD_versionString", "ZSTD_findFrameCompressedSize",
     "ZSTDB200_decompressBatch", "ZSTDB200_compressBatch", "ZSTDB200_decompressBatchDevice",
     "ZSTDB200_compressBatchDevice", "ZSTDB200_getLastTimings", "ZSTDB200_getLastLaunchCount",
-    "ZSTDB200_lastErrorString", "ZSTDB200_deviceCount", "ZSTDB200_setStream",
+    "ZSTDB200_lastErrorString", "ZSTDB200_deviceCount", "ZSTDB200_setStream", "ZSTD_DCtx_loadDictionary",
 ]
 
 
@@ -47,6 +47,8 @@ def _load() -> ctypes.CDLL:
     lib.ZSTD_freeDCtx.argtypes = [c_void_p]
     lib.ZSTD_decompressDCtx.restype = c_size_t
     lib.ZSTD_decompressDCtx.argtypes = [c_void_p, c_void_p, c_size_t, c_void_p, c_size_t]
+    lib.ZSTD_DCtx_loadDictionary.restype = c_size_t
+    lib.ZSTD_DCtx_loadDictionary.argtypes = [c_void_p, c_void_p, c_size_t]
     lib.ZSTD_findFrameCompressedSize.restype = c_size_t
     lib.ZSTD_findFrameCompressedSize.argtypes = [c_void_p, c_size_t]
     lib.ZSTD_compressBound.restype = c_size_t

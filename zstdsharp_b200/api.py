@@ -215,6 +215,14 @@ class Decompressor:
         if not self._dctx:
             raise ZstdException(ZSTD_ErrorCode.GENERIC, "Failed to create dctx")
 
+    def LoadDictionary(self, dictionary) -> None:   # Decompressor.cs:43-56: null / empty removes the dictionary
+        self._ensure()
+        if dictionary is None or len(dictionary) == 0:
+            EnsureZstdSuccess(_lib.ZSTD_DCtx_loadDictionary(self._dctx, 0, 0))
+            return
+        d = _as_u8(dictionary)
+        EnsureZstdSuccess(_lib.ZSTD_DCtx_loadDictionary(self._dctx, _ptr(d), d.size))
+
     @staticmethod
     def GetDecompressedSize(src) -> int:    # Decompressor.cs:50-54 + ThrowHelper.EnsureContentSizeOk :26-35
         s = _as_u8(src)

@@ -109,6 +109,11 @@ struct Engine {
     EncArena enc;                       // device-pointer API and small host batches
     EncArena encPipe[kPipeMax];         // one per sub-batch in flight in the pipelined host path
     DevBuf dEncInit; PinBuf hEncInit;
+    // dictionary of a decode context (ZSTD_DCtx_loadDictionary): raw bytes, parsed tables, info words (zb_decode.cuh)
+    DevBuf dDict, dDictHuf, dDictFse, dDictInfo;
+    uint32_t dictInfo[kDictInfoWords] = {};
+    bool dictLoaded = false;
+    size_t dict_headroom() const { return dictLoaded ? (((size_t)dictInfo[11] + 127) & ~(size_t)127) : 0; }
     // instrumentation
     float timings[ZSTDB200_TIMING_SLOTS] = {};
     unsigned launches = 0;
@@ -191,8 +196,11 @@ static bool decode_enqueue(Engine& E, DecArena& A, cudaStream_t stream, size_t m
     p.seq = A.dSeq.as<uint2>();
     p.defaultFse = E.dDefaultFse.as<uint32_t>(); p.hufList = A.dHufList.as<uint32_t>(); p.seqList = A.dSeqList.as<uint32_t>();
     p.counters = A.dCounters.as<uint32_t>(); p.results = A.hResults.as<uint64_t>();
+    p.dictHuf = nullptr; p.dictFse = nullptr; p.dictBytes = nullptr; p.dictInfo = nullptr;
+    if (E.dictLoaded) { p.dictHuf = E.dDictHuf.as<uint16_t>(); p.dictFse = E.dDictFse.as<uint32_t>(); p.dictBytes = E.dDict.as<uint8_t>(); p.dictInfo = E.dDictInfo.as<uint32_t>(); }
     if (timeEv) ZB_CUDA(cudaEventRecord(timeEv[0], stream));
     dec_launch_scan_init(p, hi, stream); E.launches++;
+    if (E.dictLoaded && E.dictInfo[11]) { dec_launch_dict_prefill(p, E.dictInfo[10], E.dictInfo[11], stream); E.launches++; }
     if (nWaves == 0) {
         ZB_CUDA(cudaMemcpyAsync(A.hCounters.p, A.dCounters.p, 16, cudaMemcpyDeviceToHost, stream));
         ZB_CUDA(cudaStreamSynchronize(stream));
@@ -296,8 +304,15 @@ static bool upload_items(Engine& E, size_t n, const void* const* src, const size
     return true;
 }
 
-static size_t layout_dst(size_t n, void* const* dst, const size_t* dstCap, std::vector<uint64_t>& off, size_t* total)
+static size_t layout_dst(size_t n, void* const* dst, const size_t* dstCap, std::vector<uint64_t>& off, size_t* total, size_t headroom)
 {
+    if (headroom) {         // dictionary decoding: every item gets `headroom` bytes in front of its slot (the dictionary content goes there)
+        off.resize(n);
+        size_t t = 128;
+        for (size_t i = 0; i < n; i++) { off[i] = t + headroom; t = (off[i] + dstCap[i] + 127) & ~(size_t)127; }
+        *total = t + 128;
+        return n;
+    }
     std::vector<Run> runs;
     find_runs(runs, n, (const void* const*)dst, dstCap);
     off.resize(n);
@@ -317,6 +332,11 @@ static bool download_range(Engine& E, size_t first, size_t count, void* const* d
                            const size_t* result, cudaStream_t st)
 {
     auto ok = [&](size_t i) { return !is_error(result[i]); };
+    if (E.dictLoaded) {     // items are not adjacent on the device (dictionary headroom between them): one DMA per item
+        for (size_t i = first; i < first + count; i++)
+            if (ok(i) && result[i]) ZB_CUDA(cudaMemcpyAsync(dst[i], E.dDst.as<uint8_t>() + off[i], result[i], cudaMemcpyDeviceToHost, st));
+        return true;
+    }
     size_t k = first; size_t const end = first + count;
     while (k < end) {
         // longest run of host-adjacent items that are completely filled, plus one final partial item: one DMA
@@ -349,7 +369,7 @@ static size_t decompress_batch_host(Engine& E, size_t n, const void* const* src,
         sTotal = (o + 15) & ~(size_t)15;
     }
     sTotal += 64;
-    size_t const dstRuns = layout_dst(n, dst, dstCap, dOff, &dTotal);
+    size_t const dstRuns = layout_dst(n, dst, dstCap, dOff, &dTotal, E.dict_headroom());
     if (!E.dSrc.ensure(sTotal) || !E.dDst.ensure(dTotal)) return (size_t)make_error(kMemoryAllocation);
     bool const gather = runs.size() > 512;                     // many scattered buffers: stage through pinned memory
     bool const scatter = dstRuns > 512;
@@ -759,12 +779,32 @@ size_t ZSTD_decompressDCtx(ZSTD_DCtx* dctx, void* dst, size_t dstCapacity, const
     return zb::is_error(rc) ? rc : r;
 }
 
+size_t ZSTD_DCtx_loadDictionary(ZSTD_DCtx* dctx, const void* dict, size_t dictSize)
+{
+    if (!dctx) return (size_t)make_error(zb::kGeneric);
+    zb::Engine& E = dctx->E;
+    if (!dict || dictSize == 0) { E.dictLoaded = false; return 0; }           // ZSTD_DCtx_loadDictionary(NULL, 0) clears (:2255)
+    if (dictSize > 0x7FFFFFF0u) return (size_t)make_error(zb::kMemoryAllocation);
+    if (!E.init() || !E.bind()) return (size_t)make_error(zb::kGeneric);
+    E.dictLoaded = false;
+    if (!E.dDict.ensure(dictSize + 16) || !E.dDictHuf.ensure(zb::kHufTableEntries * 2) || !E.dDictFse.ensure(zb::kFseTableEntries * 4) || !E.dDictInfo.ensure(zb::kDictInfoWords * 4))
+        return (size_t)make_error(zb::kMemoryAllocation);
+    if (cudaMemcpyAsync(E.dDict.p, dict, dictSize, cudaMemcpyHostToDevice, E.stream) != cudaSuccess) return (size_t)make_error(zb::kGeneric);
+    zb::dec_launch_dict_setup(E.dDict.as<uint8_t>(), (uint32_t)dictSize, E.dDictHuf.as<uint16_t>(), E.dDictFse.as<uint32_t>(), E.dDictInfo.as<uint32_t>(), E.stream);
+    if (cudaMemcpyAsync(E.dictInfo, E.dDictInfo.p, sizeof(E.dictInfo), cudaMemcpyDeviceToHost, E.stream) != cudaSuccess ||
+        cudaStreamSynchronize(E.stream) != cudaSuccess) { (void)cudaGetLastError(); return (size_t)make_error(zb::kGeneric); }
+    if (E.dictInfo[0] != 1) return (size_t)make_error(zb::kDictionaryCorrupted);      // the reference reports it at the first Unwrap (ZstdDecompress.cs:1897)
+    E.dictLoaded = true;
+    return 0;
+}
+
 size_t ZSTDB200_decompressBatchDevice(ZSTD_DCtx* dctx, size_t n, const void* d_src, const uint64_t* srcOffset, const size_t* srcSize,
                                       void* d_dst, const uint64_t* dstOffset, const size_t* dstCapacity, size_t* result)
 {
     if (!dctx) return (size_t)make_error(zb::kGeneric);
     zb::Engine& E = dctx->E;
     if (!E.init()) return (size_t)make_error(zb::kGeneric);
+    if (E.dictLoaded) { zb::set_error("a dictionary is loaded: dictionary decoding lays the output out itself, use ZSTDB200_decompressBatch"); return (size_t)make_error(zb::kGeneric); }
     E.launches = 0; memset(E.timings, 0, sizeof(E.timings));
     if (n == 0) return 0;
     if (!zb::decode_device(E, n, (const uint8_t*)d_src, srcOffset, srcSize, (uint8_t*)d_dst, dstOffset, dstCapacity, result, true))

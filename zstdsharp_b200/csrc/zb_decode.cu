@@ -323,6 +323,67 @@ __global__ void dec_default_tables_kernel(uint32_t* out)
 }
 void dec_build_default_tables(uint32_t* d, cudaStream_t s) { dec_default_tables_kernel<<<1, 32, 0, s>>>(d); }
 
+// ZSTD_decompress_insertDictionary / ZSTD_loadDEntropy (ZstdDecompress.cs:1880, :1770), one thread, once per loaded dictionary.
+// A dictionary without the magic number is pure content.  The Huffman table is stored in the single-symbol form the literal
+// kernel reads (the reference builds the double-symbol form of the same code).
+__global__ void dec_dict_kernel(const uint8_t* dict, uint32_t dictSize, uint16_t* hufOut, uint32_t* fseOut, uint32_t* info)
+{
+    __shared__ SetupScratch sc;
+    if (threadIdx.x != 0) return;
+    for (uint32_t i = 0; i < kDictInfoWords; i++) info[i] = 0;
+    uint32_t pos = 0, status = 1;
+    if (dictSize >= 8 && ld_le32(dict) == 0xEC30A437u) {
+        info[1] = ld_le32(dict + 4);
+        pos = 8;
+        do {
+            uint32_t nbSym = 0, tlog = 0;
+            uint32_t const hs = huf_read_stats(sc, &nbSym, &tlog, dict + pos, dictSize - pos);
+            if (hs == 0) { status = 2; break; }
+            for (uint32_t s = 0; s < nbSym; s++) {
+                uint32_t const w = sc.weights[s];
+                if (!w) continue;
+                uint32_t const len = (1u << w) >> 1, st = sc.start[s];
+                for (uint32_t u = 0; u < len; u++) hufOut[st + u] = (uint16_t)((s << 8) | (tlog + 1 - w));
+            }
+            info[3] = tlog; pos += hs;
+            int const kinds[3] = {2, 1, 0};                         // stored in the order OF, ML, LL
+            for (int q = 0; q < 3 && status == 1; q++) {
+                int const kind = kinds[q];
+                uint32_t const maxSym = kind == 0 ? kMaxLL : (kind == 1 ? kMaxML : kMaxOff), maxLog = kind == 2 ? kOffFSELog : kLLFSELog;
+                uint32_t maxSV = maxSym, tableLog = 0;
+                uint32_t const h = fse_read_ncount(sc.norm, &maxSV, &tableLog, dict + pos, dictSize - pos);
+                if (h == 0 || maxSV > maxSym || tableLog > maxLog) { status = 2; break; }
+                build_seq_table(fseOut + (kind == 0 ? kFseLLOff : (kind == 1 ? kFseMLOff : kFseOFOff)), sc, maxSV, tableLog, kind);
+                info[kind == 0 ? 4 : (kind == 1 ? 6 : 5)] = tableLog;
+                pos += h;
+            }
+            if (status != 1) break;
+            if (pos + 12 > dictSize) { status = 2; break; }
+            uint32_t const contentSize = dictSize - (pos + 12);
+            for (int i = 0; i < 3; i++) {
+                uint32_t const r = ld_le32(dict + pos); pos += 4;
+                if (r == 0 || r > contentSize) status = 2;
+                info[7 + i] = r;
+            }
+            info[2] = 1;
+        } while (0);
+    }
+    info[10] = pos; info[11] = status == 1 ? dictSize - pos : 0;
+    info[0] = status;
+}
+void dec_launch_dict_setup(const uint8_t* d_dict, uint32_t dictSize, uint16_t* d_huf, uint32_t* d_fse, uint32_t* d_info, cudaStream_t s)
+{ dec_dict_kernel<<<1, 32, 0, s>>>(d_dict, dictSize, d_huf, d_fse, d_info); }
+
+__global__ void dec_dict_prefill_kernel(DecPass p, uint32_t contentOff, uint32_t contentSize)
+{
+    uint32_t const i = blockIdx.x;
+    uint8_t* const d = p.dst + p.items[i].dstOff - contentSize;
+    const uint8_t* const s = p.dictBytes + contentOff;
+    for (uint32_t k = threadIdx.x; k < contentSize; k += blockDim.x) d[k] = s[k];
+}
+void dec_launch_dict_prefill(const DecPass& p, uint32_t contentOff, uint32_t contentSize, cudaStream_t s)
+{ if (contentSize) dec_dict_prefill_kernel<<<p.nItems, 256, 0, s>>>(p, contentOff, contentSize); }
+
 // =====================================================================================================
 //  Frame walking helpers
 // =====================================================================================================
@@ -368,7 +429,7 @@ __global__ void dec_scan_kernel(DecPass p, const DecItemInit* init)
     it.srcOff = in.srcOff; it.dstOff = in.dstOff; it.srcSize = in.srcSize; it.dstCap = in.dstCap;
     it.srcPos = 0; it.outPos = 0; it.frameStart = 0; it.status = kStRunning; it.errCode = 0; it.inFrame = 0;
     it.moreThan1Frame = 0; it.checksumFlag = 0; it.hasFcs = 0; it.fcs = 0; it.litEntropy = 0; it.fseEntropy = 0;
-    it.blkType = kBlkNone;
+    it.blkType = kBlkNone; it.prefix = 0;
     uint32_t const blocks = count_item_blocks(p.src + in.srcOff, in.srcSize);
     atomicMax(&p.counters[3], blocks);
 }
@@ -436,6 +497,7 @@ __global__ void __launch_bounds__(kSetupWarps * 32) dec_setup_kernel(DecPass p)
 {
     __shared__ SetupScratch scratch[kSetupWarps];
     __shared__ uint32_t s_huf[kSetupWarps][3];   // [0] fill table? [1] nbSymbols [2] tableLog
+    __shared__ uint32_t s_dict[kSetupWarps];     // a frame starts under a dictionary with entropy tables: copy them into the item's slots
     uint32_t const warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     uint32_t const item = blockIdx.x * kSetupWarps + warp;
     if (item >= p.nItems) return;
@@ -443,7 +505,7 @@ __global__ void __launch_bounds__(kSetupWarps * 32) dec_setup_kernel(DecPass p)
     SetupScratch& sc = scratch[warp];
     const uint8_t* const src = p.src + it.srcOff;
     if (lane == 0) {
-        s_huf[warp][0] = 0;
+        s_huf[warp][0] = 0; s_dict[warp] = 0;
         sc.tabAct[0] = sc.tabAct[1] = sc.tabAct[2] = 0;
         do {
             if (it.status != kStRunning) { it.blkType = kBlkNone; break; }
@@ -465,7 +527,10 @@ __global__ void __launch_bounds__(kSetupWarps * 32) dec_setup_kernel(DecPass p)
                     uint64_t fcs = 0; uint32_t has = 1;
                     if (fcsId == 0) { if (single) fcs = src[q]; else has = 0; }
                     else if (fcsId == 1) fcs = ld_le16(src + q) + 256; else if (fcsId == 2) fcs = ld_le32(src + q); else fcs = ld_le64(src + q);
-                    if (!err && dictID != 0) err = kDictionaryWrong;                              // ZSTD_decodeFrameHeader :834
+                    uint32_t const haveID = p.dictInfo ? p.dictInfo[1] : 0u;
+                    if (!err && dictID != 0 && dictID != haveID) err = kDictionaryWrong;         // ZSTD_decodeFrameHeader :849
+                    // the dictionary content is materialised in front of the item's output, i.e. in front of its FIRST frame only
+                    if (!err && p.dictInfo && it.outPos != 0) err = kFrameParameterUnsupported;  // DESIGN.md, deviations
                     it.fcs = fcs; it.hasFcs = has; it.checksumFlag = (fhd >> 2) & 1;
                 }
                 if (err) {
@@ -474,7 +539,16 @@ __global__ void __launch_bounds__(kSetupWarps * 32) dec_setup_kernel(DecPass p)
                 }
                 pos += fhsize;
                 it.rep[0] = 1; it.rep[1] = 4; it.rep[2] = 8; it.litEntropy = 0; it.fseEntropy = 0;   // ZSTD_decompressBegin :1933
-                it.frameStart = it.outPos; it.inFrame = 1;
+                it.frameStart = it.outPos; it.inFrame = 1; it.prefix = 0;
+                if (p.dictInfo) {                                                                // ZSTD_decompressBegin_usingDict :1954
+                    const uint32_t* const di = p.dictInfo;
+                    it.prefix = di[11];
+                    if (di[2]) {
+                        it.rep[0] = di[7]; it.rep[1] = di[8]; it.rep[2] = di[9]; it.litEntropy = 1; it.fseEntropy = 1;
+                        it.hufLog = di[3]; it.llLog = di[4]; it.ofLog = di[5]; it.mlLog = di[6];
+                        s_dict[warp] = 1;
+                    }
+                }
             }
             // ---- block header: ZSTD_getcBlockSize, ZstdDecompressBlock.cs:19 ----
             uint32_t rem = size - pos;
@@ -580,6 +654,13 @@ __global__ void __launch_bounds__(kSetupWarps * 32) dec_setup_kernel(DecPass p)
             }
             if (it.litType == kLitHuf) { uint32_t const slot = atomicAdd(&p.counters[0], 1u); p.hufList[slot] = item; }
         } while (0);
+    }
+    __syncwarp();
+    if (s_dict[warp]) {     // the dictionary's tables become the frame's "previous block" tables (repeat modes refer to them)
+        const uint4* const sh = (const uint4*)p.dictHuf; uint4* const dh = (uint4*)(p.hufTable + (size_t)item * kHufTableEntries);
+        for (uint32_t u = lane; u < kHufTableEntries * 2 / 16; u += 32) dh[u] = sh[u];
+        const uint4* const sf = (const uint4*)p.dictFse; uint4* const df = (uint4*)(p.fseTable + (size_t)item * kFseTableEntries);
+        for (uint32_t u = lane; u < kFseTableEntries * 4 / 16; u += 32) df[u] = sf[u];
     }
     __syncwarp();
     // sequence tables: built by the whole warp (ZSTD_buildSeqTable :1746)
@@ -868,7 +949,8 @@ __global__ void __launch_bounds__(32) dec_seq_kernel(DecPass p)
     br.settle();
     int32_t const gz = (int32_t)br.gZero;
     uint32_t rep0 = it.rep[0], rep1 = it.rep[1], rep2 = it.rep[2];
-    uint32_t outPos = it.outPos; uint32_t const outPos0 = outPos, frameStart = it.frameStart, dstCap = it.dstCap;
+    uint32_t outPos = it.outPos; uint32_t const outPos0 = outPos, dstCap = it.dstCap;
+    uint32_t const frameStart = it.frameStart - it.prefix;      // virtualStart: the dictionary content sits right in front of the frame (wraps below 0: unsigned differences stay right)
     uint32_t litPos = 0; uint32_t const litSize = it.litSize;
     uint32_t aL = kFseLLOff, aO = kFseOFOff, aM = kFseMLOff;
     if (live && !err) {

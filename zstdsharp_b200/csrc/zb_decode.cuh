@@ -71,8 +71,14 @@ struct __align__(16) DecItem {
     uint32_t seqLen;
     uint32_t blockOut;      // regenerated size of this block (literals-only part added by exec)
     uint32_t seqLitEnd;     // literals consumed by the sequences (set by seq_decode)
-    uint32_t _pad1[3];
+    uint32_t prefix;        // bytes of dictionary content that sit in front of the current frame's output (0 without a dictionary)
+    uint32_t _pad1[2];
 };
+
+// Dictionary of a decode context (ZSTD_decompress_insertDictionary, ZstdDecompress.cs:1880): parsed once on the device.
+// info[]: [0] 1 = usable, 2 = corrupted | [1] dictID | [2] entropy tables present | [3] hufLog | [4] llLog | [5] ofLog | [6] mlLog |
+//         [7..9] repcodes | [10] offset of the content inside the dictionary | [11] content size
+constexpr uint32_t kDictInfoWords = 16;
 
 struct DecPass {
     DecItem* items;
@@ -88,6 +94,8 @@ struct DecPass {
     uint32_t* seqList;      // item indices that need sequence decoding this wave
     uint32_t* counters;     // [0] hufCount [1] seqCount [2] running items after this wave [3] max blocks (scan)
     uint64_t* results;      // per item: regenerated size or error code
+    // dictionary (all null / 0 without one): tables in the layout of hufTable / fseTable, the raw dictionary bytes, info words
+    const uint16_t* dictHuf; const uint32_t* dictFse; const uint8_t* dictBytes; const uint32_t* dictInfo;
 };
 
 // Number of blocks of the longest frame chain of an item = number of waves the item needs.  Walks headers like
@@ -138,5 +146,9 @@ void dec_launch_scan_init(const DecPass& p, const void* d_init, cudaStream_t s);
 void dec_launch_wave(const DecPass& p, cudaStream_t s);
 void dec_launch_wave_timed(const DecPass& p, cudaStream_t s, cudaEvent_t* ev5);
 void dec_launch_finish(const DecPass& p, cudaStream_t s);
+// parses a dictionary that already sits in device memory (one thread; a one-off per ZSTD_DCtx_loadDictionary)
+void dec_launch_dict_setup(const uint8_t* d_dict, uint32_t dictSize, uint16_t* d_huf, uint32_t* d_fse, uint32_t* d_info, cudaStream_t s);
+// copies the dictionary content in front of every item's output slot (the caller left p.dictInfo[11] bytes of headroom there)
+void dec_launch_dict_prefill(const DecPass& p, uint32_t contentOff, uint32_t contentSize, cudaStream_t s);
 
 }  // namespace zb
