@@ -440,6 +440,30 @@ def run_b200(args):
                            "h2d_bytes_per_step": int(total_u), "d2h_bytes_per_step": int(c_total_c)}
         del h_in, h_cout
 
+        # -------------------------------------------------------------- level 3 (ZSTD_dfast) compress + decompress (configs[4])
+        # 1 GiB of the same Silesia-mix-like chunks per GPU (8 GiB at 8 GPUs), device-resident; the frames are byte-identical to the
+        # oracle's level-3 frames (tests/test_encode_gpu.py), so the ratio IS the reference's ratio.
+        def comp3_step():
+            dev_call(lib.ZSTDB200_compressBatchDevice, comp, n, 3, d_sil.data_ptr(), cso, css, d_cout.data_ptr(), cdo, cdc, cres)
+            return comp.launch_count(), np.array(comp.timings())
+        c3_dev_ms, _, c3_launch, c3_slots = timed_steps(comp3_step, 1, 2)
+        c3sizes = np.array(list(cres), dtype=np.int64)
+        assert (c3sizes > 0).all() and (c3sizes <= bound).all()
+        c3ss = (st * n)(*c3sizes.tolist())
+
+        def dec3_step():
+            dev_call(lib.ZSTDB200_decompressBatchDevice, dec, n, d_cout.data_ptr(), cdo, c3ss, d_out.data_ptr(), rdo, dc, res)
+            return dec.launch_count(), np.array(dec.timings())
+        d3_dev_ms, _, _, _ = timed_steps(dec3_step, 1, 3)
+        assert all(r == FRAME for r in res) and torch.equal(d_out, d_sil), "level-3 compress -> decompress round trip failed"
+        c3_total_c = sum_over_ranks(float(c3sizes.sum()))
+        compress["level3"] = {
+            "workload": "level 3 (ZSTD_dfast) compress + decompress of 1 GiB Silesia-mix-like per GPU in 128 KiB chunks (configs[4]: 8 GiB at 8 GPUs), device-resident",
+            "compress": {"value": round(total_u * 2 / (c3_dev_ms * 1e-3) / 1e9, 3), "unit": "GB/s", "ms_per_step": round(c3_dev_ms / 2, 3),
+                         "kernel_ms": {"enc_match": round(float(c3_slots[8]), 3), "enc_entropy": round(float(c3_slots[9]), 3)}, "gpu_launches": int(c3_launch)},
+            "decompress": {"value": round(total_u * 3 / (d3_dev_ms * 1e-3) / 1e9, 3), "unit": "GB/s", "ms_per_step": round(d3_dev_ms / 3, 3)},
+            "ratio": round(n * FRAME * world / c3_total_c, 4)}
+
     # ------------------------------------------------------------------ CPU baseline (rank 0, N == 1 only)
     cpu = None
     if rank == 0 and world == 1 and not args.skip_cpu:
