@@ -210,3 +210,48 @@ def test_dictionary_decoding(dec):
         dec.LoadDictionary(None)
     # and the context is back to plain decoding
     assert dec.Unwrap(z.compress(payloads()[2], 1)) == payloads()[2].tobytes()
+
+
+def test_concurrent_contexts():
+    """ZstdNetTests.cs:498-522: several threads, each with its own Compressor / Decompressor, at the same time.  Every context
+    owns its CUDA streams and scratch arenas, so nothing is shared but the device."""
+    import threading
+    from zstdsharp_b200 import Compressor, Decompressor
+    o = oracle()
+    data = dg.silesia_mix(24 * FRAME)
+    errors = []
+
+    def work(tid):
+        try:
+            with Compressor(1 + tid % 3) as c, Decompressor() as d:
+                lvl = 1 + tid % 3
+                chunks = _chunks(data[tid * 4 * FRAME:(tid * 4 + 6) * FRAME])
+                for _ in range(3):
+                    frames = c.WrapBatch(chunks)
+                    assert [f == o.compress(ch, lvl) for ch, f in zip(chunks, frames)] == [True] * len(chunks)
+                    assert d.UnwrapBatch(frames) == [ch.tobytes() for ch in chunks]
+                    assert d.Unwrap(c.Wrap(chunks[0][:5000])) == chunks[0][:5000].tobytes()
+        except Exception as e:      # noqa: BLE001
+            errors.append((tid, repr(e)))
+
+    ts = [threading.Thread(target=work, args=(t,)) for t in range(4)]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join()
+    assert not errors, errors
+
+
+def test_more_items_than_one_pass(dec):
+    """A batch above the 8192-item pass size runs as several passes (decode and encode), results in caller order."""
+    from zstdsharp_b200 import Compressor
+    o = oracle()
+    text = dg.text_like(4 * FRAME)
+    n = 8192 + 700
+    srcs = [text[(7 * i) % 3000:(7 * i) % 3000 + 200 + (i % 50)] for i in range(n)]
+    with Compressor(1) as c:
+        frames = c.WrapBatch(srcs)
+    for i in (0, 1, 4095, 8191, 8192, 8193, n - 1):
+        assert frames[i] == o.compress(srcs[i], 1), i
+    outs = dec.UnwrapBatch(frames)
+    assert outs == [s.tobytes() for s in srcs]
