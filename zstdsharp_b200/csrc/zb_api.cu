@@ -380,7 +380,8 @@ static size_t decompress_batch_host(Engine& E, size_t n, const void* const* src,
     size_t const kPipe = (size_t)pipe_depth(), kPipeItems = pipe_items();
     std::vector<size_t> sub;                     // sub-batch k = items [sub[k], sub[k+1])
     {
-        size_t pos = 0, sz = std::max<size_t>(64, std::min(kPipeItems, n / 16));
+        static int const firstDiv = env_int("ZSTDB200_PIPE_FIRST_DIV", 16, 2, 256);
+        size_t pos = 0, sz = std::max<size_t>(64, std::min(kPipeItems, n / (size_t)firstDiv));
         while (pos < n) {
             size_t take = std::min(sz, n - pos);
             if (n - pos - take < take / 2) take = n - pos;      // fold a small remainder into the last sub-batch
