@@ -10,8 +10,10 @@
 //   dec_scan_kernel      thread / item   counts blocks (number of waves), initialises cursors
 //   dec_setup_kernel     warp   / item   frame+block+literal+sequence headers, Huffman and FSE table construction
 //   dec_huf_kernel       lane   / stream HUF 4-stream (or single) literal decoding, tables staged in shared memory
-//   dec_seq_kernel       lane   / item   3-state FSE sequence decoding (serial chain), tables staged in shared memory
-//   dec_exec_kernel      CTA    / item   literal + match copies through a shared-memory output tile, raw/RLE blocks
+//   dec_seq_kernel       lane   / item   3-state FSE sequence decoding (serial chain), tables staged in shared memory, records staged and flushed
+//   dec_exec_kernel      warp   / item   literal + match copies through a shared-memory output tile, raw/RLE blocks, XXH64 check
+//   dec_dict_kernel      thread          parses a loaded dictionary once (entropy tables, repcodes); dec_dict_prefill_kernel copies its
+//                                        content in front of every item's output slot
 #include "zb_decode.cuh"
 
 namespace zb {

@@ -1,22 +1,25 @@
 // zb_encode.cu -- batch Zstandard frame encoder for sm_100a, levels 1..3 (product code; no CPU fallback).
 //
-// Replaces, for batches of independent chunks (one frame of one block each, srcSize <= 128 KiB), the reference's
+// Replaces, for batches of independent inputs (one frame each: one block up to 128 KiB, a multi-block frame above), the reference's
 //   ZSTD_compress2 -> ZSTD_compressEnd -> ZSTD_compress_frameChunk -> ZSTD_compressBlock_internal   (ZstdCompress.cs:7138,5665,4690,4528)
 //     -> ZSTD_buildSeqStore -> ZSTD_compressBlock_fast / ZSTD_compressBlock_doubleFast               (:3432, ZstdFast.cs:96, ZstdDoubleFast.cs:51)
 //     -> ZSTD_entropyCompressSeqStore: ZSTD_compressLiterals (HIST_count, HUF_buildCTable, HUF_writeCTable,
 //        HUF_compress{1,4}X_usingCTable), ZSTD_buildSequencesStatistics (FSE_normalizeCount, FSE_writeNCount,
 //        FSE_buildCTable), ZSTD_encodeSequences                                                     (:3357; HufCompress.cs; FseCompress.cs; ZstdCompressSequences.cs)
-// The output of every chunk is byte-identical to what the reference's Compressor.Wrap produces for that chunk.
-// Kernels:
-//   enc_match_group_kernel<16>        16 lanes / chunk   exact ZSTD_fast parse (levels 1-2), speculative window of 8 reference iterations
-//   enc_match_dfast_group_kernel<16>  16 lanes / chunk   exact ZSTD_dfast parse (level 3), 15 probe positions + 1 look-ahead per window
-//   enc_match_kernel                  lane / chunk       serial restatement, chunks below 64 bytes only
-//   enc_entropy_kernel                CTA  / chunk       literal gather + histograms, Huffman/FSE table construction, FSE state chains,
-//                                                        parallel bit scatter of the 4 Huffman streams and of the sequence bitstream,
-//                                                        block/frame assembly with the reference's accept/reject gates, XXH64 trailer
-//   enc_compact_kernel                CTA  / chunk       packs the frames densely before D2H
-// All hash tables live in HBM/L2 (zeroed per call) and every chunk of a pass is in flight at once: the parse is a chain of
-// dependent memory round trips per sequence, and only concurrency across chunks hides it (profiles/r01_notes.md).
+// The output of every input is byte-identical to what the reference's Compressor.Wrap produces for it.
+// Kernels (MB = false: every frame is one block; MB = true: wave b = block b of every frame that has one, with the window,
+// repcodes and Huffman table the blocks before it left behind):
+//   enc_match_group_kernel<16, MB>        16 lanes / block   exact ZSTD_fast parse (levels 1-2), speculative window of 8 reference iterations
+//   enc_match_dfast_group_kernel<16, MB>  16 lanes / block   exact ZSTD_dfast parse (level 3), 15 probe positions + 1 look-ahead per window
+//   enc_match_kernel                      lane / block       serial restatement, blocks below 64 bytes only
+//   enc_entropy_kernel<MB, 0>             CTA  / block       literal gather + histograms, Huffman table (new / repeated), parallel bit scatter of
+//                                                            the 4 Huffman streams, sequence codes + histograms, the three FSE tables and their descriptions
+//   enc_fse_chain_kernel<MB>              lane / FSE chain   the three FSE state chains of every block (3 x blocks lanes)
+//   enc_entropy_kernel<MB, 1>             CTA  / block       parallel bit scatter of the sequence bitstream, block/frame assembly with the
+//                                                            reference's accept/reject gates (raw / RLE / compressed), state confirmation, XXH64 trailer
+//   enc_compact_kernel                    CTA  / frame       packs the frames densely before D2H
+// All hash tables live in HBM/L2 (zeroed per frame) and every block of a wave is in flight at once: the parse is a chain of
+// dependent memory round trips per sequence, and only concurrency across frames hides it (profiles/r01_notes.md).
 #include <algorithm>
 #include <cstdio>
 #include <cstdlib>
