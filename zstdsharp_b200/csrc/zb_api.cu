@@ -6,6 +6,7 @@
 // without a device every call returns ZSTD_error_GENERIC.
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -101,6 +102,7 @@ struct Engine {
     DevBuf dDefaultFse;
     bool defaultTablesBuilt = false;
     cudaStream_t sIn = nullptr, sOut = nullptr, sComp[kPipeMax] = {};
+    cudaStream_t sEnc[kPipeMax] = {};   // compress pipeline: sub-batch k on sEnc[k], earlier sub-batches at higher priority (their entropy stage goes first)
     cudaEvent_t evStart = nullptr, evIn[2] = {}, evOut[2] = {};
     std::vector<cudaEvent_t> evPool;
     // host<->device staging for the host-pointer API
@@ -135,6 +137,11 @@ struct Engine {
         ZB_CUDA(cudaStreamCreateWithFlags(&sIn, cudaStreamNonBlocking));
         ZB_CUDA(cudaStreamCreateWithFlags(&sOut, cudaStreamNonBlocking));
         for (int i = 0; i < kPipeMax; i++) ZB_CUDA(cudaStreamCreateWithFlags(&sComp[i], cudaStreamNonBlocking));
+        {
+            int least = 0, greatest = 0;
+            ZB_CUDA(cudaDeviceGetStreamPriorityRange(&least, &greatest));          // numerically lower = more urgent
+            for (int i = 0; i < kPipeMax; i++) ZB_CUDA(cudaStreamCreateWithPriority(&sEnc[i], cudaStreamNonBlocking, std::min(least, greatest + i)));
+        }
         ZB_CUDA(cudaEventCreate(&evStart));
         for (int i = 0; i < 2; i++) { ZB_CUDA(cudaEventCreate(&evIn[i])); ZB_CUDA(cudaEventCreate(&evOut[i])); }
         ready = true;
@@ -156,7 +163,7 @@ struct Engine {
             cudaEventDestroy(evStart);
             for (int i = 0; i < 2; i++) { cudaEventDestroy(evIn[i]); cudaEventDestroy(evOut[i]); }
             cudaStreamDestroy(sIn); cudaStreamDestroy(sOut);
-            for (int i = 0; i < kPipeMax; i++) cudaStreamDestroy(sComp[i]);
+            for (int i = 0; i < kPipeMax; i++) { cudaStreamDestroy(sComp[i]); cudaStreamDestroy(sEnc[i]); }
             cudaStreamDestroy(ownStream);
         }
         ready = false;
@@ -497,7 +504,8 @@ static size_t compress_batch_host(Engine& E, size_t n, int level, int checksum, 
     // -> compaction + D2H (sOut).  The match finder is latency bound (26 ms for 1024 chunks, 43 ms for 8192), so the
     // sub-batches are NOT run one after the other: their kernels overlap each other and the uploads that are still in flight.
     static int const encPipe = env_int("ZSTDB200_ENC_PIPE", 2, 1, kPipeMax);
-    size_t const nSub = (runs.size() == 1 && np >= 4096) ? std::min<size_t>((size_t)encPipe, np / 2048) : 1;
+    static int const encSub = env_int("ZSTDB200_ENC_SUB", 2048, 256, 8192);       // smallest sub-batch (pieces)
+    size_t const nSub = (runs.size() == 1 && np >= 4096) ? std::min<size_t>((size_t)encPipe, np / (size_t)encSub) : 1;
     std::vector<uint64_t> sOff(n); size_t sTotal = 16;
     if (nSub > 1) {
         size_t o = sTotal;
@@ -522,6 +530,14 @@ static size_t compress_batch_host(Engine& E, size_t n, int level, int checksum, 
     if (!E.dDst.ensure(dTotal)) return (size_t)make_error(kMemoryAllocation);
     std::vector<uint64_t> hOff(np);              // where piece k ends up in the pinned staging buffer (pipelined / compacted paths)
     auto fail = [&](ErrorCode c) { cudaDeviceSynchronize(); (void)cudaGetLastError(); return (size_t)make_error(c); };
+    // per item: total size, first error of its pieces, dstSize_tooSmall when the caller's buffer cannot take it (ZstdCompress.cs:4690-4800)
+    auto item_result = [&](size_t i) {
+        size_t tot = 0;
+        for (size_t k = first[i]; k < first[i + 1]; k++) { if (is_error(r[k])) { tot = r[k]; break; } tot += r[k]; }
+        if (!is_error(tot) && tot > dstCap[i]) tot = (size_t)make_error(kDstSizeTooSmall);
+        result[i] = tot;
+    };
+    enc_set_overlap_mode(nSub > 1);
     if (nSub > 1) {
         if (!E.hStage.ensure(dTotal) || !E.need_events(4 * nSub)) return (size_t)make_error(kMemoryAllocation);
         cudaEvent_t* const evK = E.evPool.data();                  // [3k..3k+2]: before match / after match / after entropy
@@ -535,11 +551,26 @@ static size_t compress_batch_host(Engine& E, size_t n, int level, int checksum, 
             size_t const a = k * per, b = std::min(np, a + per);
             size_t const lo = pSrcOff[a], hi = pSrcOff[b - 1] + pSize[b - 1];
             if (hi > lo && cudaMemcpyAsync(E.dSrc.as<uint8_t>() + lo, hostBase + (lo - sOff[0]), hi - lo, cudaMemcpyHostToDevice, E.sIn) != cudaSuccess) return fail(kGeneric);
-            if (!enc_enqueue(E.encPipe[k], E.sComp[k], E.sIn, b - a, level, checksum, E.dSrc.as<uint8_t>(), pSrcOff.data() + a, pSize.data() + a,
+            if (!enc_enqueue(E.encPipe[k], E.sEnc[k], E.sIn, b - a, level, checksum, E.dSrc.as<uint8_t>(), pSrcOff.data() + a, pSize.data() + a,
                              E.dDst.as<uint8_t>(), pDstOff.data() + a, slotCap.data() + a, evK + 3 * k, &E.launches)) { set_error(enc_last_error()); return fail(kGeneric); }
         }
         cudaEventRecord(E.evIn[1], E.sIn);
-        size_t stageBase = 0;
+        size_t stageBase = 0, itemNext = 0;
+        std::vector<size_t> itemEnd(nSub);           // items [itemEnd[k-1], itemEnd[k]) are complete once sub-batch k is in host memory
+        double scatterMs = 0;
+        // frames of finished items: pinned staging -> the caller's buffers, by host threads, while the next sub-batch is still on its way
+        auto scatter_items = [&](size_t iLo, size_t iHi) {
+            auto const tc0 = std::chrono::steady_clock::now();
+            const uint8_t* st = E.hStage.as<uint8_t>();
+            parallel_for(iHi - iLo, 256, [&](size_t a, size_t b) {
+                for (size_t i = iLo + a; i < iLo + b; i++) {
+                    if (is_error(result[i])) continue;
+                    size_t o = 0;
+                    for (size_t q = first[i]; q < first[i + 1]; q++) { memcpy((uint8_t*)dst[i] + o, st + hOff[q], r[q]); o += r[q]; }
+                }
+            });
+            scatterMs += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tc0).count();
+        };
         for (size_t k = 0; k < nSub; k++) {
             size_t const a = k * per, b = std::min(np, a + per);
             if (cudaEventSynchronize(evK[3 * k + 2]) != cudaSuccess) return fail(kGeneric);
@@ -550,11 +581,17 @@ static size_t compress_batch_host(Engine& E, size_t n, int level, int checksum, 
             if (!enc_compact_device(E.encPipe[k], E.sOut, b - a, E.dDst.as<uint8_t>(), pDstOff.data() + a, cSize.data(), cOff.data(), cTotal, &E.launches)) return fail(kGeneric);
             if (cTotal && cudaMemcpyAsync(E.hStage.as<uint8_t>() + stageBase, E.encPipe[k].compactBuf(), cTotal, cudaMemcpyDeviceToHost, E.sOut) != cudaSuccess) return fail(kGeneric);
             cudaEventRecord(evOutK[k], E.sOut);
-            // enc_compact_device keeps its offset arrays in the arena's pinned buffer: wait before the vectors above go away? no: they were copied into that buffer
             stageBase += cTotal;
+            while (itemNext < n && first[itemNext + 1] <= b) { item_result(itemNext); itemNext++; }
+            itemEnd[k] = itemNext;
+            if (k > 0) {
+                if (cudaEventSynchronize(evOutK[k - 1]) != cudaSuccess) return fail(kGeneric);
+                scatter_items(k > 1 ? itemEnd[k - 2] : 0, itemEnd[k - 1]);
+            }
         }
         cudaEventRecord(E.evOut[1], E.sOut);
         if (cudaStreamSynchronize(E.sOut) != cudaSuccess || cudaGetLastError() != cudaSuccess) return fail(kGeneric);
+        scatter_items(nSub > 1 ? itemEnd[nSub - 2] : 0, n);
         cudaEventElapsedTime(&E.timings[0], E.evIn[0], E.evIn[1]);
         cudaEventElapsedTime(&E.timings[2], E.evOut[0], E.evOut[1]);
         for (size_t k = 0; k < nSub; k++) {
@@ -563,29 +600,23 @@ static size_t compress_batch_host(Engine& E, size_t n, int level, int checksum, 
             cudaEventElapsedTime(&t, evK[3 * k], evK[3 * k + 1]); E.timings[8] += t;
             cudaEventElapsedTime(&t, evK[3 * k + 1], evK[3 * k + 2]); E.timings[9] += t;
         }
+        if (getenv("ZSTDB200_TRACE")) {           // developer aid: stage times of every sub-batch relative to the first H2D
+            for (size_t k = 0; k < nSub; k++) {
+                float m0 = 0, m1 = 0, e1 = 0, o1 = 0;
+                cudaEventElapsedTime(&m0, E.evIn[0], evK[3 * k]); cudaEventElapsedTime(&m1, E.evIn[0], evK[3 * k + 1]);
+                cudaEventElapsedTime(&e1, E.evIn[0], evK[3 * k + 2]); cudaEventElapsedTime(&o1, E.evIn[0], evOutK[k]);
+                fprintf(stderr, "[zstdb200] enc sub %zu: match %.2f .. %.2f  entropy .. %.2f  compact+d2h .. %.2f ms\n", k, m0, m1, e1, o1);
+            }
+            float h1 = 0; cudaEventElapsedTime(&h1, E.evIn[0], E.evIn[1]);
+            fprintf(stderr, "[zstdb200] enc h2d span .. %.2f ms, host scatter %.2f ms in total\n", h1, scatterMs);
+        }
+        return 0;
     } else {
         if (!enc_compress_device(E.enc, E.stream, E.ev, np, level, checksum, E.dSrc.as<uint8_t>(), pSrcOff.data(), pSize.data(), E.dDst.as<uint8_t>(), pDstOff.data(), slotCap.data(), r.data(), E.timings, &E.launches))
             { set_error(enc_last_error()); return (size_t)make_error(kGeneric); }
         cudaEventRecord(E.ev[12], E.stream);
     }
-    // per item: total size, first error of its pieces, dstSize_tooSmall when the caller's buffer cannot take it (ZstdCompress.cs:4690-4800)
-    for (size_t i = 0; i < n; i++) {
-        size_t tot = 0;
-        for (size_t k = first[i]; k < first[i + 1]; k++) { if (is_error(r[k])) { tot = r[k]; break; } tot += r[k]; }
-        if (!is_error(tot) && tot > dstCap[i]) tot = (size_t)make_error(kDstSizeTooSmall);
-        result[i] = tot;
-    }
-    if (nSub > 1) {
-        const uint8_t* st = E.hStage.as<uint8_t>();
-        parallel_for(n, 256, [&](size_t a, size_t b) {
-            for (size_t i = a; i < b; i++) {
-                if (is_error(result[i])) continue;
-                size_t o = 0;
-                for (size_t k = first[i]; k < first[i + 1]; k++) { memcpy((uint8_t*)dst[i] + o, st + hOff[k], r[k]); o += r[k]; }
-            }
-        });
-        return 0;
-    }
+    for (size_t i = 0; i < n; i++) item_result(i);
     if (np <= 512) {
         for (size_t i = 0; i < n; i++) {
             if (is_error(result[i])) continue;

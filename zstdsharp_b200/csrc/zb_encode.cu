@@ -21,6 +21,7 @@
 // All hash tables live in HBM/L2 (zeroed per frame) and every block of a wave is in flight at once: the parse is a chain of
 // dependent memory round trips per sequence, and only concurrency across frames hides it (profiles/r01_notes.md).
 #include <algorithm>
+#include <atomic>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -67,6 +68,10 @@ static CParams get_cparams(int level, uint64_t srcSize)
 constexpr uint32_t kEncSeqCap = kBlockSizeMax / 4 + 1;      // maxNbSeq = blockSize / 4 (minMatch != 3), ZstdCompress.cs:2570
 constexpr uint32_t kEncLitStride = kBlockSizeMax + 64;
 constexpr size_t kEncMaxFrameBytes = 0x7FFF0000u;           // positions inside a frame are 31-bit integers in the match kernels
+// Warps per CTA of the group match kernels.  The warps are independent; four per CTA keep the kernel (one warp per two blocks,
+// ~28 warps per SM for 8192 blocks) from holding 28 of an SM's 32 CTA slots while the entropy kernels of other sub-batches
+// share the SMs with it in the pipelined host path (enc_set_overlap_mode).  No effect on the kernel's own time (42.5 ms either way).
+constexpr uint32_t kMatchWarps = 4;
 
 struct __align__(16) EncItem {
     uint64_t srcOff, dstOff;
@@ -359,14 +364,14 @@ __device__ __forceinline__ uint32_t hash_val(uint64_t x, uint32_t hBits, uint32_
 //  probes): ncu showed 33 G warp instructions and 120 GB of DRAM reads per GiB; 8 lanes per chunk cut both.
 // ------------------------------------------------------------------------------------------------------------
 template <int GS, bool MB>
-__global__ void __launch_bounds__(32) enc_match_group_kernel(EncPass p, const uint32_t* __restrict__ workList, uint32_t nWork, uint32_t wave)
+__global__ void __launch_bounds__(32 * kMatchWarps) enc_match_group_kernel(EncPass p, const uint32_t* __restrict__ workList, uint32_t nWork, uint32_t wave)
 {
     constexpr uint32_t FULL = 0xFFFFFFFFu;
     constexpr int NG = 32 / GS, NIT = GS / 2;
     constexpr uint32_t LOW = GS == 32 ? FULL : ((1u << (GS & 31)) - 1u);
-    uint32_t const lane = threadIdx.x, g = lane / GS, l = lane % GS, gbase = g * GS;
+    uint32_t const lane = threadIdx.x & 31, g = lane / GS, l = lane % GS, gbase = g * GS;
     uint32_t const gmask = LOW << gbase;
-    uint32_t const wi = blockIdx.x * NG + g;
+    uint32_t const wi = (blockIdx.x * kMatchWarps + (threadIdx.x >> 5)) * NG + g;
     bool active = wi < nWork;
     uint32_t const item = workList[active ? wi : 0];
     EncItem& it = p.items[item];
@@ -508,14 +513,14 @@ __global__ void __launch_bounds__(32) enc_match_group_kernel(EncPass p, const ui
 //  through the tables, and writes are committed up to the first event only.
 // ------------------------------------------------------------------------------------------------------------
 template <int GS, bool MB>
-__global__ void __launch_bounds__(32) enc_match_dfast_group_kernel(EncPass p, const uint32_t* __restrict__ workList, uint32_t nWork, uint32_t wave)
+__global__ void __launch_bounds__(32 * kMatchWarps) enc_match_dfast_group_kernel(EncPass p, const uint32_t* __restrict__ workList, uint32_t nWork, uint32_t wave)
 {
     constexpr uint32_t FULL = 0xFFFFFFFFu;
     constexpr int NG = 32 / GS;
     constexpr uint32_t LOW = GS == 32 ? FULL : ((1u << (GS & 31)) - 1u);
-    uint32_t const lane = threadIdx.x, g = lane / GS, l = lane % GS, gbase = g * GS;
+    uint32_t const lane = threadIdx.x & 31, g = lane / GS, l = lane % GS, gbase = g * GS;
     uint32_t const gmask = LOW << gbase;
-    uint32_t const wi = blockIdx.x * NG + g;
+    uint32_t const wi = (blockIdx.x * kMatchWarps + (threadIdx.x >> 5)) * NG + g;
     bool active = wi < nWork;
     uint32_t const item = workList[active ? wi : 0];
     EncItem& it = p.items[item];
@@ -1795,9 +1800,9 @@ bool enc_enqueue(EncArena& A, cudaStream_t stream, cudaStream_t copyStream, size
         uint32_t const wave = (uint32_t)b;
         // lanes per chunk: 16 measured best for ZSTD_fast (8: 49/52 ms, 16: 42/49 ms, 32: 63/72 ms per GiB Silesia-mix / text)
         if (mb) {
-            if (w.n[0]) enc_match_group_kernel<16, true><<<(w.n[0] + 1) / 2, 32, 0, stream>>>(p, dw + w.off[0], w.n[0], wave);
+            if (w.n[0]) enc_match_group_kernel<16, true><<<(w.n[0] + 2 * kMatchWarps - 1) / (2 * kMatchWarps), 32 * kMatchWarps, 0, stream>>>(p, dw + w.off[0], w.n[0], wave);
             if (w.n[1]) enc_match_kernel<<<(w.n[1] + 31) / 32, 32, 0, stream>>>(p, dw + w.off[1], w.n[1], wave);
-            if (w.n[2]) enc_match_dfast_group_kernel<16, true><<<(w.n[2] + 1) / 2, 32, 0, stream>>>(p, dw + w.off[2], w.n[2], wave);
+            if (w.n[2]) enc_match_dfast_group_kernel<16, true><<<(w.n[2] + 2 * kMatchWarps - 1) / (2 * kMatchWarps), 32 * kMatchWarps, 0, stream>>>(p, dw + w.off[2], w.n[2], wave);
             if (ev3 && b == 0) ENC_CUDA(cudaEventRecord(ev3[1], stream));
             if (w.n[3]) {
                 enc_entropy_kernel<true, 0><<<w.n[3], kEntThreads, 0, stream>>>(p, dw + w.off[3], wave);
@@ -1805,9 +1810,9 @@ bool enc_enqueue(EncArena& A, cudaStream_t stream, cudaStream_t copyStream, size
                 enc_entropy_kernel<true, 1><<<w.n[3], kEntThreads, 0, stream>>>(p, dw + w.off[3], wave);
             }
         } else {
-            if (w.n[0]) enc_match_group_kernel<16, false><<<(w.n[0] + 1) / 2, 32, 0, stream>>>(p, dw + w.off[0], w.n[0], 0u);
+            if (w.n[0]) enc_match_group_kernel<16, false><<<(w.n[0] + 2 * kMatchWarps - 1) / (2 * kMatchWarps), 32 * kMatchWarps, 0, stream>>>(p, dw + w.off[0], w.n[0], 0u);
             if (w.n[1]) enc_match_kernel<<<(w.n[1] + 31) / 32, 32, 0, stream>>>(p, dw + w.off[1], w.n[1], 0u);
-            if (w.n[2]) enc_match_dfast_group_kernel<16, false><<<(w.n[2] + 1) / 2, 32, 0, stream>>>(p, dw + w.off[2], w.n[2], 0u);
+            if (w.n[2]) enc_match_dfast_group_kernel<16, false><<<(w.n[2] + 2 * kMatchWarps - 1) / (2 * kMatchWarps), 32 * kMatchWarps, 0, stream>>>(p, dw + w.off[2], w.n[2], 0u);
             if (ev3) ENC_CUDA(cudaEventRecord(ev3[1], stream));
             enc_entropy_kernel<false, 0><<<(unsigned)m, kEntThreads, 0, stream>>>(p, dw, 0u);
             enc_fse_chain_kernel<false><<<(unsigned)(3 * m + 31) / 32, 32, 32 * kChainTabStride, stream>>>(p, dw, (uint32_t)m);
@@ -1819,6 +1824,36 @@ bool enc_enqueue(EncArena& A, cudaStream_t stream, cudaStream_t copyStream, size
     ENC_CUDA(cudaGetLastError());
     return true;
 }
+// Shared-memory carve-out of the encoder's kernels.  An SM keeps ONE L1 / shared-memory split while it has resident CTAs, and a CTA of a
+// kernel launched with a different split waits until the SM has drained.  With the defaults (match finder: no shared memory -> maximum
+// L1; entropy kernels: 13.5 KB per CTA x 15 CTAs -> maximum shared memory) the entropy stage of a sub-batch did not start before the LAST
+// match kernel of the pipelined host path had finished (measured: profiles/r01_notes.md, session 4).  overlap = true gives every encoder
+// kernel the same split so that they can share SMs; overlap = false restores the defaults, which are faster when nothing runs beside them
+// (match 42.5 vs 44.0 ms, entropy 11.0 vs 12.7 ms per GiB at 50 %).
+void enc_set_overlap_mode(bool overlap)
+{
+    static std::atomic<int> applied[64];                        // per device: 0 unknown, 1 defaults, 2 common split
+    int dev = 0; cudaGetDevice(&dev);
+    int const want = overlap ? 2 : 1;
+    if (applied[dev & 63].load(std::memory_order_acquire) == want) return;
+    static int const pct = getenv("ZSTDB200_ENC_CARVEOUT") ? atoi(getenv("ZSTDB200_ENC_CARVEOUT")) : 50;
+    int const x = overlap ? pct : (int)cudaSharedmemCarveoutDefault;
+    auto const A = cudaFuncAttributePreferredSharedMemoryCarveout;
+    cudaFuncSetAttribute(enc_match_group_kernel<16, false>, A, x);
+    cudaFuncSetAttribute(enc_match_group_kernel<16, true>, A, x);
+    cudaFuncSetAttribute(enc_match_dfast_group_kernel<16, false>, A, x);
+    cudaFuncSetAttribute(enc_match_dfast_group_kernel<16, true>, A, x);
+    cudaFuncSetAttribute(enc_match_kernel, A, x);
+    cudaFuncSetAttribute(enc_entropy_kernel<false, 0>, A, x);
+    cudaFuncSetAttribute(enc_entropy_kernel<false, 1>, A, x);
+    cudaFuncSetAttribute(enc_entropy_kernel<true, 0>, A, x);
+    cudaFuncSetAttribute(enc_entropy_kernel<true, 1>, A, x);
+    cudaFuncSetAttribute(enc_fse_chain_kernel<false>, A, x);
+    cudaFuncSetAttribute(enc_fse_chain_kernel<true>, A, x);
+    cudaFuncSetAttribute(enc_compact_kernel, A, x);
+    (void)cudaGetLastError();
+    applied[dev & 63].store(want, std::memory_order_release);
+}
 const uint64_t* enc_results(const EncArena& A) { return A.impl ? (const uint64_t*)A.impl->hResults.p : nullptr; }
 
 bool enc_compress_device(EncArena& A, cudaStream_t stream, cudaEvent_t* ev, size_t n, int level, int checksumFlag,
@@ -1827,6 +1862,7 @@ bool enc_compress_device(EncArena& A, cudaStream_t stream, cudaEvent_t* ev, size
                          float* timings, unsigned* launches)
 {
     float msAll = 0, msMatch = 0, msEnt = 0;
+    enc_set_overlap_mode(false);                 // one pass at a time on one stream: every kernel keeps its own L1 / shared-memory split
     for (size_t base = 0; base < n; base += kEncMaxItemsPerPass) {
         size_t const m = std::min(kEncMaxItemsPerPass, n - base);
         if (!enc_enqueue(A, stream, stream, m, level, checksumFlag, d_src, srcOff + base, srcSize + base, d_dst, dstOff + base, dstCap + base, &ev[14], launches)) return false;

@@ -33,6 +33,8 @@ const uint64_t* enc_results(const EncArena& A);
 // Gathers the n variable-size frames into one dense device buffer (A.compactBuf()) at offsets cOff.
 bool enc_compact_device(EncArena& A, cudaStream_t stream, size_t n, const uint8_t* d_dst, const uint64_t* dstOff,
                         const size_t* sizes, const uint64_t* cOff, size_t total, unsigned* launches);
+// Lets the encoder's kernels of different streams share SMs (pipelined host path) or restores each kernel's own L1 / shared-memory split.
+void enc_set_overlap_mode(bool overlap);
 const char* enc_last_error();
 
 }  // namespace zb
