@@ -503,7 +503,7 @@ static size_t compress_batch_host(Engine& E, size_t n, int level, int checksum, 
     // One contiguous host buffer and enough pieces: sub-batches flow through H2D (sIn) -> kernels (sComp[k], one arena each)
     // -> compaction + D2H (sOut).  The match finder is latency bound (26 ms for 1024 chunks, 43 ms for 8192), so the
     // sub-batches are NOT run one after the other: their kernels overlap each other and the uploads that are still in flight.
-    static int const encPipe = env_int("ZSTDB200_ENC_PIPE", 2, 1, kPipeMax);
+    static int const encPipe = env_int("ZSTDB200_ENC_PIPE", 4, 1, kPipeMax);
     static int const encSub = env_int("ZSTDB200_ENC_SUB", 2048, 256, 8192);       // smallest sub-batch (pieces)
     size_t const nSub = (runs.size() == 1 && np >= 4096) ? std::min<size_t>((size_t)encPipe, np / (size_t)encSub) : 1;
     std::vector<uint64_t> sOff(n); size_t sTotal = 16;

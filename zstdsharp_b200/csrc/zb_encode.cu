@@ -1829,14 +1829,14 @@ bool enc_enqueue(EncArena& A, cudaStream_t stream, cudaStream_t copyStream, size
 // L1; entropy kernels: 13.5 KB per CTA x 15 CTAs -> maximum shared memory) the entropy stage of a sub-batch did not start before the LAST
 // match kernel of the pipelined host path had finished (measured: profiles/r01_notes.md, session 4).  overlap = true gives every encoder
 // kernel the same split so that they can share SMs; overlap = false restores the defaults, which are faster when nothing runs beside them
-// (match 42.5 vs 44.0 ms, entropy 11.0 vs 12.7 ms per GiB at 50 %).
+// (match 42.5 vs 44.0 ms, entropy 11.0 vs 12.7 ms per GiB at a 50 % split).
 void enc_set_overlap_mode(bool overlap)
 {
     static std::atomic<int> applied[64];                        // per device: 0 unknown, 1 defaults, 2 common split
     int dev = 0; cudaGetDevice(&dev);
     int const want = overlap ? 2 : 1;
     if (applied[dev & 63].load(std::memory_order_acquire) == want) return;
-    static int const pct = getenv("ZSTDB200_ENC_CARVEOUT") ? atoi(getenv("ZSTDB200_ENC_CARVEOUT")) : 50;
+    static int const pct = getenv("ZSTDB200_ENC_CARVEOUT") ? atoi(getenv("ZSTDB200_ENC_CARVEOUT")) : 40;   // 100 KB of shared memory per SM: 28 % 77.4 ms, 40 % 74.0 ms, 50 % 75.4 ms per GiB host to host
     int const x = overlap ? pct : (int)cudaSharedmemCarveoutDefault;
     auto const A = cudaFuncAttributePreferredSharedMemoryCarveout;
     cudaFuncSetAttribute(enc_match_group_kernel<16, false>, A, x);
