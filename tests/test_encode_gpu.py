@@ -246,3 +246,21 @@ def test_golden_vectors_on_gpu(comp):
             assert [len(f) for f in mine] == v["frame_sizes"], (v["name"], level)
             assert hashlib.sha256(b"".join(mine)).hexdigest() == v["frames_sha256"], (v["name"], level)
     comp.Level = 1
+
+
+def test_pipelined_host_path_byte_identical(comp, dec):
+    """More than 4096 host-adjacent chunks take the pipelined host path of ZSTDB200_compressBatch (sub-batches in flight on
+    several streams, overlapping match / entropy kernels, per-sub-batch scatter): same bytes as one Wrap per chunk."""
+    o = oracle()
+    rng = np.random.default_rng(0xC0FFEE)
+    data = dg.WORKLOADS["silesia"](20 * FRAME)
+    cuts = np.sort(rng.choice(np.arange(1, data.size), size=4700, replace=False))
+    bounds = np.concatenate([[0], cuts, [data.size]])
+    chunks = [data[int(a):int(b)] for a, b in zip(bounds[:-1], bounds[1:])]
+    assert len(chunks) > 4096
+    comp.Level = 1
+    frames = comp.WrapBatch(chunks)
+    for c, f in zip(chunks, frames):
+        want = o.compress(c, 1)
+        assert f == want, _first_diff(f, want)
+    assert dec.UnwrapBatch(frames) == [c.tobytes() for c in chunks]
