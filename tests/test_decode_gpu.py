@@ -140,11 +140,25 @@ def test_corrupted_payload_never_crashes(dec):
     for g, r in zip(frames, res):
         rv, out = o.decompress_raw(g, FRAME)
         if not o.lib.zo_isError(rv):
-            # the oracle (= reference semantics) accepted the damaged frame: if we accept too, bytes must agree
-            if not isinstance(r, ZstdException):
-                assert r == out[:rv].tobytes()
+            # the oracle (= reference semantics) accepted the damaged frame: so must we, with the same bytes
+            assert not isinstance(r, ZstdException), r
+            assert r == out[:rv].tobytes()
         else:
             assert isinstance(r, ZstdException)
+
+
+def test_streams_that_run_dry_decode_like_the_reference(dec):
+    """tests/golden/overread_frames.json: damaged frames whose sequence bit stream runs dry before its last sequence.  The
+    reference reads on past the stream start (Bitstream.cs:293-340) and only checks the stream after the last sequence
+    (ZstdDecompressBlock.cs:2730); oracle and libzstd 1.5.5 decode them, so the GPU decoder must, to the same bytes."""
+    import hashlib, json, os
+    cases = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "overread_frames.json")))["cases"]
+    frames = [bytes.fromhex(c["frame_hex"]) for c in cases]
+    # many copies: every lane position of the sequence kernel's warps sees such a stream
+    outs = dec.UnwrapBatch(frames * 20)
+    for i, r in enumerate(outs):
+        c = cases[i % len(cases)]
+        assert len(r) == c["size"] and hashlib.sha256(r).hexdigest() == c["sha256"], c["name"]
 
 
 def test_frame_checksum_is_verified(dec):

@@ -187,3 +187,15 @@ def test_corrupted_frames_agree_with_libzstd():
     # Huffman decoder insists on exact stream consumption (HufDecompress.cs:526-533) where 1.5.5's fast loop only
     # checks the symbol count, so a flipped literal bit that keeps code lengths is accepted by 1.5.5, rejected by 1.5.1.
     assert agree >= 170
+
+
+def test_streams_that_run_dry_match_libzstd():
+    """tests/golden/overread_frames.json: the oracle follows the reference's bit reader past the start of a sequence stream
+    (zero fill, then wrapped reads of the 64-bit container); upstream libzstd 1.5.5 gives the same bytes."""
+    import hashlib, json, os
+    o, z = oracle(), libzstd()
+    for c in json.load(open(os.path.join(os.path.dirname(__file__), "golden", "overread_frames.json")))["cases"]:
+        f = bytes.fromhex(c["frame_hex"])
+        got = o.decompress(f, c["size"])
+        assert len(got) == c["size"] and hashlib.sha256(got).hexdigest() == c["sha256"], c["name"]
+        assert z.decompress(f, c["size"]) == got

@@ -903,6 +903,29 @@ constexpr uint32_t kSeqFlush = 8;              // sequences per record flush
 constexpr uint32_t kSeqSmemBytes = kSeqItemsPerCta * (kSeqItemBytes + 4 * kSeqChunk) + kSeqFlush * kSeqItemsPerCta * 8;
 __device__ __forceinline__ uint32_t lds8(uint32_t saddr) { uint16_t v; asm("ld.shared.u8 %0, [%1];" : "=h"(v) : "r"(saddr)); return v; }
 
+// BIT_readBits / BIT_readBitsFast exactly as the reference behaves near, at and beyond the START of a backward bit stream
+// (Bitstream.cs:189-264, 293-340, 381-424).  R = unread bits before the read.  While R >= 0 a read that runs past the start is filled
+// with zero bits (the container is shifted left).  Once bitsConsumed has passed the 64-bit container (R < 0), BIT_reloadDStream
+// reports `overflow` and changes nothing, and the shift count wraps (bitsConsumed & 63): the read returns bits of the stream's first
+// eight bytes again.  The sequence decoder only checks the stream AFTER the last sequence (status >= completed,
+// ZstdDecompressBlock.cs:2730), so a corrupted stream that runs dry early is still decoded and executed if its lengths and offsets
+// happen to be valid; a valid stream gets here with its last few sequences (dec_seq_kernel's tail loop).
+__device__ __noinline__ uint32_t seq_bits_near_start(const uint8_t* s, uint32_t len, int32_t R, uint32_t nb)
+{
+    if (nb == 0) return 0;
+    uint64_t w = 0; uint32_t sh;
+    if (R < 0) {
+        for (int j = 7; j >= 0; j--) w = (w << 8) | ((uint32_t)j < len ? s[j] : 0u);              // the container at ptr == start
+        sh = (uint32_t)(-R) & 63u;
+    } else {
+        int32_t const hiB = (R - 1) >> 3;                                                         // byte that holds the next unread bit
+        for (int j = 0; j < 8; j++) { int32_t const b = hiB - j; w = (w << 8) | (b >= 0 ? s[b] : 0u); }
+        sh = 7u - ((uint32_t)(R - 1) & 7u);
+    }
+    return (uint32_t)((w << sh) >> (64 - nb));
+}
+constexpr int32_t kSeqTailBits = 96;      // a sequence reads at most 31 + 16 + 16 extra bits and 9 + 9 + 8 state bits
+
 __global__ void __launch_bounds__(32) dec_seq_kernel(DecPass p)
 {
     extern __shared__ __align__(256) uint8_t s_seq_raw[];   // [14] rings of 128 B | per item: u16[1280] | u8[1280] tables | record staging [8][14] x 8 B
@@ -962,9 +985,16 @@ __global__ void __launch_bounds__(32) dec_seq_kernel(DecPass p)
         aL = kFseLLOff + top_bits(x, llLog); x <<= llLog;
         aO = kFseOFOff + top_bits(x, ofLog); x <<= ofLog;
         aM = kFseMLOff + top_bits(x, mlLog);
+        if ((int32_t)(G - (llLog + ofLog + mlLog)) < gz) {           // fewer bits than the three initial states need: the reference reads on
+            int32_t const R = (int32_t)G - gz;
+            const uint8_t* const ss = p.src + it.srcOff + it.seqOff; uint32_t const sl = it.seqLen;
+            aL = kFseLLOff + seq_bits_near_start(ss, sl, R, llLog);
+            aO = kFseOFOff + seq_bits_near_start(ss, sl, R - (int32_t)llLog, ofLog);
+            aM = kFseMLOff + seq_bits_near_start(ss, sl, R - (int32_t)(llLog + ofLog), mlLog);
+        }
         G -= llLog + ofLog + mlLog;
-        if ((int32_t)G < gz) err = kCorruptionDetected;
     }
+    uint32_t nDone = 0;                                 // sequences this lane has decoded
     uint32_t maxSeq = (live && !err) ? nbSeq : 0u;
 #pragma unroll
     for (int d = 16; d; d >>= 1) maxSeq = max(maxSeq, __shfl_xor_sync(FULL, maxSeq, d));
@@ -977,7 +1007,7 @@ __global__ void __launch_bounds__(32) dec_seq_kernel(DecPass p)
 #pragma unroll 2
         for (uint32_t k = 0; k < kSeqFlush; k++) {
             uint32_t const n = n0 + k;
-            bool const act = live && !err && n < nbSeq;
+            bool const act = live && !err && n < nbSeq && (int32_t)G - gz >= kSeqTailBits;      // the last bits of a stream are left to the tail loop
             if ((k & 1) == 0) br.step<2>(G, act);
             if (act) {
                 uint32_t const eL = lds16(t16 + 2 * aL), eO = lds16(t16 + 2 * aO), eM = lds16(t16 + 2 * aM);
@@ -996,8 +1026,6 @@ __global__ void __launch_bounds__(32) dec_seq_kernel(DecPass p)
                 uint32_t const xC2 = xC << nbL;
                 aM = kFseMLOff + (nM | ((eM >> 15) << 8)) + top_bits(xC2, nbM);
                 aO = kFseOFOff + (nO | ((eO >> 15) << 8)) + top_bits(xC2 << nbM, nbO);
-                bool const overRead = (int32_t)G2 < gz;                      // the extra bits must exist; the last state update may run dry
-                bool const dry = (int32_t)G3 < gz;
                 G = G3;
                 uint32_t offset;
                 {   // ZSTD_decodeSequence offset rules (:2397-2445), as selects
@@ -1018,10 +1046,10 @@ __global__ void __launch_bounds__(32) dec_seq_kernel(DecPass p)
                 // validity (ZSTD_execSequenceEnd order): output overflow, literal overrun, offset beyond frame start
                 uint32_t const seqLen = ll + ml;
                 bool const e1 = seqLen > dstCap - outPos, e2 = ll > litSize - litPos, e3 = offset > (outPos + ll) - frameStart;
-                bool const e4 = overRead | ((n + 1 < nbSeq) & dry) | ((offset >> 30) != 0);   // offsets >= 1 GiB do not fit seq_pack
+                bool const e4 = (offset >> 30) != 0;                                             // offsets >= 1 GiB do not fit seq_pack
                 if (e1 | e2 | e3 | e4) err = e1 ? kDstSizeTooSmall : kCorruptionDetected;
                 s_stage[k * kSeqItemsPerCta + lane] = seq_pack(ll, ml, offset);
-                cnt = k + 1;
+                cnt = k + 1; nDone = n + 1;
                 outPos += seqLen; litPos += ll;
             }
         }
@@ -1035,6 +1063,45 @@ __global__ void __launch_bounds__(32) dec_seq_kernel(DecPass p)
             if (slot < (uint32_t)kSeqItemsPerCta && k < c) p.seq[base + n0 + k] = s_stage[k * kSeqItemsPerCta + slot];
         }
         __syncwarp();
+    }
+    // ---- tail: the sequences within kSeqTailBits of the stream start, bit reads as the reference does them there ----
+    if (live && !err && nDone < nbSeq) {
+        const uint8_t* const ss = p.src + it.srcOff + it.seqOff; uint32_t const sl = it.seqLen;
+        for (uint32_t n = nDone; n < nbSeq && !err; n++) {
+            uint32_t const eL = lds16(t16 + 2 * aL), eO = lds16(t16 + 2 * aO), eM = lds16(t16 + 2 * aM);
+            uint32_t const nL = lds8(t8 + aL), nO = lds8(t8 + aO), nM = lds8(t8 + aM);
+            uint32_t const llBits = (eL >> 4) & 31, mlBits = (eM >> 4) & 31, ofBits = (eO >> 4) & 31;
+            uint32_t const nbL = eL & 15, nbM = eM & 15, nbO = eO & 15;
+            uint32_t const llSym = (eL >> 9) & 63, mlSym = (eM >> 9) & 63;
+            int32_t R = (int32_t)G - gz;
+            uint32_t const ofExtra = seq_bits_near_start(ss, sl, R, ofBits); R -= (int32_t)ofBits;
+            uint32_t const ml = lds32(mlBaseS + mlSym * 4) + seq_bits_near_start(ss, sl, R, mlBits); R -= (int32_t)mlBits;
+            uint32_t const ll = lds32(llBaseS + llSym * 4) + seq_bits_near_start(ss, sl, R, llBits); R -= (int32_t)llBits;
+            aL = kFseLLOff + (nL | ((eL >> 15) << 8)) + seq_bits_near_start(ss, sl, R, nbL); R -= (int32_t)nbL;
+            aM = kFseMLOff + (nM | ((eM >> 15) << 8)) + seq_bits_near_start(ss, sl, R, nbM); R -= (int32_t)nbM;
+            aO = kFseOFOff + (nO | ((eO >> 15) << 8)) + seq_bits_near_start(ss, sl, R, nbO); R -= (int32_t)nbO;
+            G = (uint32_t)(R + gz);
+            uint32_t offset;
+            {   // ZSTD_decodeSequence offset rules (:2397-2445)
+                uint32_t const ll0 = (llSym == 0);
+                if (ofBits > 1) { offset = ((1u << ofBits) - 3u) + ofExtra; rep2 = rep1; rep1 = rep0; rep0 = offset; }
+                else if (ofBits == 0) {
+                    if (ll0) { offset = rep1; rep1 = rep0; rep0 = offset; } else offset = rep0;
+                } else {
+                    uint32_t const ofv = 1u + ll0 + ofExtra;
+                    uint32_t t = (ofv == 3) ? rep0 - 1 : (ofv == 1 ? rep1 : rep2);
+                    t += !t;
+                    if (ofv != 1) rep2 = rep1;
+                    rep1 = rep0; rep0 = offset = t;
+                }
+            }
+            uint32_t const seqLen = ll + ml;
+            bool const e1 = seqLen > dstCap - outPos, e2 = ll > litSize - litPos, e3 = offset > (outPos + ll) - frameStart;
+            bool const e4 = (offset >> 30) != 0;
+            if (e1 | e2 | e3 | e4) err = e1 ? kDstSizeTooSmall : kCorruptionDetected;
+            p.seq[seqBase + n] = seq_pack(ll, ml, offset);
+            outPos += seqLen; litPos += ll;
+        }
     }
     if (!live) return;
     // the stream must not have unread bits left (BIT_reloadDStream >= completed, :2730)
