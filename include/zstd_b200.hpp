@@ -1,0 +1,245 @@
+/* zstd_b200.hpp — C++17 host-side mirror of ZstdSharp's managed wrapper classes over the C ABI of zstd_b200.h.
+ *
+ * The reference's host side is compiled C# (no .NET in this image), so the host layer above the C ABI is C++:
+ * same class names, method names, argument meaning and error behaviour as
+ *   src/ZstdSharp/Compressor.cs:6-150      (Compressor: Level, SetParameter, Wrap, TryWrap, GetCompressBound, Dispose)
+ *   src/ZstdSharp/Decompressor.cs:6-140    (Decompressor: LoadDictionary, GetDecompressedSize, Unwrap, TryUnwrap, Dispose)
+ *   src/ZstdSharp/ThrowHelper.cs:10-41     (EnsureZstdSuccess / EnsureContentSizeOk -> ZstdException(code, message))
+ *   src/ZstdSharp/ZstdException.cs         (ZstdException.Code)
+ * plus WrapBatch / UnwrapBatch over ZSTDB200_compressBatch / ZSTDB200_decompressBatch (many independent frames per call,
+ * the shape the GPU is built for).  Header-only; link with -lzstdb200.  Nothing here computes: every byte of a frame is
+ * produced or consumed by the CUDA kernels behind the C ABI, and a missing GPU surfaces as ZstdException(GENERIC).
+ * One context per thread, as in the reference (ZstdNetTests.cs:498-522).
+ */
+#ifndef ZSTD_B200_HPP
+#define ZSTD_B200_HPP
+
+#include <cstddef>
+#include <cstdint>
+#include <limits>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "zstd_b200.h"
+
+namespace ZstdSharp {
+
+/* ZSTD_ErrorCode values used by the wrapper (ZstdSharp.Unsafe.ZSTD_ErrorCode; same numbers as zstd_errors.h 1.5.1). */
+enum class ZSTD_ErrorCode : int {
+    no_error = 0, GENERIC = 1, prefix_unknown = 10, version_unsupported = 12, frameParameter_unsupported = 14,
+    frameParameter_windowTooLarge = 16, corruption_detected = 20, checksum_wrong = 22, dictionary_corrupted = 30,
+    dictionary_wrong = 32, dictionaryCreation_failed = 34, parameter_unsupported = 40, parameter_outOfBound = 42,
+    tableLog_tooLarge = 44, maxSymbolValue_tooLarge = 46, maxSymbolValue_tooSmall = 48, stage_wrong = 60,
+    init_missing = 62, memory_allocation = 64, workSpace_tooSmall = 66, dstSize_tooSmall = 70, srcSize_wrong = 72,
+    dstBuffer_null = 74
+};
+
+/* ZSTD_cParameter members this library accepts (Compressor.SetParameter); others answer parameter_unsupported. */
+enum class ZSTD_cParameter : int {
+    ZSTD_c_compressionLevel = 100, ZSTD_c_contentSizeFlag = 200, ZSTD_c_checksumFlag = 201, ZSTD_c_dictIDFlag = 202,
+    independentChunks = ZSTDB200_c_independentChunks   /* enum member cannot share the macro's name */
+};
+
+class ZstdException : public std::runtime_error {
+public:
+    ZstdException(ZSTD_ErrorCode code, const std::string& message) : std::runtime_error(message), Code(code) {}
+    const ZSTD_ErrorCode Code;
+};
+
+class ObjectDisposedException : public std::logic_error {
+public:
+    explicit ObjectDisposedException(const char* name) : std::logic_error(name) {}
+};
+
+namespace ThrowHelper {
+/* ThrowHelper.cs:10-16, 36-40: an error return becomes ZstdException(code = 0 - returnValue, ZSTD_getErrorName). */
+inline size_t EnsureZstdSuccess(size_t returnValue) {
+    if (ZSTD_isError(returnValue))
+        throw ZstdException(static_cast<ZSTD_ErrorCode>(static_cast<int>(size_t(0) - returnValue)),
+                            ZSTD_getErrorName(returnValue));
+    return returnValue;
+}
+/* ThrowHelper.cs:26-35. */
+inline unsigned long long EnsureContentSizeOk(unsigned long long returnValue) {
+    if (returnValue == 0ULL - 1)
+        throw ZstdException(ZSTD_ErrorCode::GENERIC, "Decompressed content size is not specified");
+    if (returnValue == 0ULL - 2)
+        throw ZstdException(ZSTD_ErrorCode::GENERIC,
+                            "Decompressed content size cannot be determined (e.g. invalid magic number, srcSize too small)");
+    return returnValue;
+}
+inline bool IsDstSizeTooSmall(size_t returnValue) {
+    return returnValue == size_t(0) - size_t(ZSTD_ErrorCode::dstSize_tooSmall);
+}
+}  // namespace ThrowHelper
+
+/* Result of one item of a batch call: Size when Code == no_error. */
+struct BatchResult {
+    size_t Size;
+    ZSTD_ErrorCode Code;
+};
+
+namespace detail {
+inline std::vector<BatchResult> ToResults(const std::vector<size_t>& raw) {
+    std::vector<BatchResult> out(raw.size());
+    for (size_t i = 0; i < raw.size(); ++i) {
+        if (ZSTD_isError(raw[i])) out[i] = {0, static_cast<ZSTD_ErrorCode>(static_cast<int>(size_t(0) - raw[i]))};
+        else out[i] = {raw[i], ZSTD_ErrorCode::no_error};
+    }
+    return out;
+}
+}  // namespace detail
+
+/* Compressor.cs:6-150. */
+class Compressor {
+public:
+    static constexpr int DefaultCompressionLevel = 0;                                  /* Compressor.cs:10 */
+    static constexpr int MinCompressionLevel = 0, MaxCompressionLevel = 3;             /* levels this library implements */
+
+    explicit Compressor(int level = DefaultCompressionLevel) : cctx_(ZSTD_createCCtx()) {   /* Compressor.cs:58-65 */
+        if (!cctx_) throw ZstdException(ZSTD_ErrorCode::GENERIC, "Failed to create cctx");
+        try { Level(level); } catch (...) { ZSTD_freeCCtx(cctx_); cctx_ = nullptr; throw; }
+    }
+    ~Compressor() { Dispose(); }
+    Compressor(const Compressor&) = delete;
+    Compressor& operator=(const Compressor&) = delete;
+
+    int Level() const { return level_; }
+    void Level(int value) {                                                            /* Compressor.cs:16-27 */
+        if (level_ != value) {
+            SetParameter(ZSTD_cParameter::ZSTD_c_compressionLevel, value);
+            level_ = value;
+        }
+    }
+    void SetParameter(ZSTD_cParameter parameter, int value) {                          /* Compressor.cs:29-33 */
+        EnsureNotDisposed();
+        ThrowHelper::EnsureZstdSuccess(ZSTD_CCtx_setParameter(cctx_, static_cast<int>(parameter), value));
+    }
+
+    static int GetCompressBound(int length) { return static_cast<int>(ZSTD_compressBound(static_cast<size_t>(length))); }
+    static uint64_t GetCompressBoundLong(uint64_t length) { return ZSTD_compressBound(static_cast<size_t>(length)); }
+
+    /* Span<byte> Wrap(ReadOnlySpan<byte> src)  (Compressor.cs:78-83) */
+    std::vector<uint8_t> Wrap(const void* src, size_t srcLength) {
+        std::vector<uint8_t> dest(ZSTD_compressBound(srcLength));
+        dest.resize(Wrap(src, srcLength, dest.data(), dest.size()));
+        return dest;
+    }
+    std::vector<uint8_t> Wrap(const std::vector<uint8_t>& src) { return Wrap(src.data(), src.size()); }
+    /* int Wrap(ReadOnlySpan<byte> src, Span<byte> dest)  (Compressor.cs:88-96) */
+    size_t Wrap(const void* src, size_t srcLength, void* dest, size_t destLength) {
+        EnsureNotDisposed();
+        return ThrowHelper::EnsureZstdSuccess(ZSTD_compress2(cctx_, dest, destLength, src, srcLength));
+    }
+    /* bool TryWrap(src, dest, out written)  (Compressor.cs:107-126): false only for dstSize_tooSmall. */
+    bool TryWrap(const void* src, size_t srcLength, void* dest, size_t destLength, size_t& written) {
+        EnsureNotDisposed();
+        size_t returnValue = ZSTD_compress2(cctx_, dest, destLength, src, srcLength);
+        if (ThrowHelper::IsDstSizeTooSmall(returnValue)) { written = 0; return false; }
+        written = ThrowHelper::EnsureZstdSuccess(returnValue);
+        return true;
+    }
+
+    /* Many independent inputs in one pass over the GPU (ZSTDB200_compressBatch): item i becomes exactly the frame
+     * Wrap(src[i]) returns.  A failing item carries its own code and does not fail the others; only a library-level
+     * failure (no device, out of memory) throws. */
+    std::vector<BatchResult> WrapBatch(const std::vector<const void*>& src, const std::vector<size_t>& srcLength,
+                                       const std::vector<void*>& dest, const std::vector<size_t>& destLength) {
+        EnsureNotDisposed();
+        size_t n = src.size();
+        if (srcLength.size() != n || dest.size() != n || destLength.size() != n)
+            throw std::invalid_argument("WrapBatch: array lengths differ");
+        std::vector<size_t> raw(n);
+        ThrowHelper::EnsureZstdSuccess(ZSTDB200_compressBatch(cctx_, n, level_ == 0 ? 3 : level_, src.data(), srcLength.data(),
+                                                              dest.data(), destLength.data(), raw.data()));
+        return detail::ToResults(raw);
+    }
+
+    void Dispose() {                                                                   /* Compressor.cs:141-150 */
+        if (cctx_) { ZSTD_freeCCtx(cctx_); cctx_ = nullptr; }
+    }
+    ZSTD_CCtx* Handle() const { return cctx_; }
+
+private:
+    void EnsureNotDisposed() const { if (!cctx_) throw ObjectDisposedException("Compressor"); }
+    ZSTD_CCtx* cctx_;
+    int level_ = DefaultCompressionLevel;
+};
+
+/* Decompressor.cs:6-140. */
+class Decompressor {
+public:
+    Decompressor() : dctx_(ZSTD_createDCtx()) {                                        /* Decompressor.cs:10-15 */
+        if (!dctx_) throw ZstdException(ZSTD_ErrorCode::GENERIC, "Failed to create dctx");
+    }
+    ~Decompressor() { Dispose(); }
+    Decompressor(const Decompressor&) = delete;
+    Decompressor& operator=(const Decompressor&) = delete;
+
+    /* LoadDictionary(byte[] dict): null / empty drops the dictionary  (Decompressor.cs:36-48). */
+    void LoadDictionary(const void* dict, size_t dictLength) {
+        EnsureNotDisposed();
+        ThrowHelper::EnsureZstdSuccess(ZSTD_DCtx_loadDictionary(dctx_, dict, dict ? dictLength : 0));
+    }
+
+    /* Decompressor.cs:50-54: ZSTD_decompressBound over all frames of src. */
+    static uint64_t GetDecompressedSize(const void* src, size_t srcLength) {
+        return ThrowHelper::EnsureContentSizeOk(ZSTD_decompressBound(src, srcLength));
+    }
+
+    /* Span<byte> Unwrap(ReadOnlySpan<byte> src, int maxDecompressedSize = int.MaxValue)  (Decompressor.cs:62-75) */
+    std::vector<uint8_t> Unwrap(const void* src, size_t srcLength,
+                                int maxDecompressedSize = std::numeric_limits<int>::max()) {
+        uint64_t expectedDstSize = GetDecompressedSize(src, srcLength);
+        if (expectedDstSize > static_cast<uint64_t>(maxDecompressedSize))
+            throw ZstdException(ZSTD_ErrorCode::dstSize_tooSmall,
+                                "Decompressed content size " + std::to_string(expectedDstSize) +
+                                    " is greater than maxDecompressedSize " + std::to_string(maxDecompressedSize));
+        std::vector<uint8_t> dest(expectedDstSize);
+        dest.resize(Unwrap(src, srcLength, dest.data(), dest.size()));
+        return dest;
+    }
+    std::vector<uint8_t> Unwrap(const std::vector<uint8_t>& src, int maxDecompressedSize = std::numeric_limits<int>::max()) {
+        return Unwrap(src.data(), src.size(), maxDecompressedSize);
+    }
+    /* int Unwrap(ReadOnlySpan<byte> src, Span<byte> dest)  (Decompressor.cs:80-88) */
+    size_t Unwrap(const void* src, size_t srcLength, void* dest, size_t destLength) {
+        EnsureNotDisposed();
+        return ThrowHelper::EnsureZstdSuccess(ZSTD_decompressDCtx(dctx_, dest, destLength, src, srcLength));
+    }
+    /* bool TryUnwrap(src, dest, out written)  (Decompressor.cs:96-115): false only for dstSize_tooSmall. */
+    bool TryUnwrap(const void* src, size_t srcLength, void* dest, size_t destLength, size_t& written) {
+        EnsureNotDisposed();
+        size_t returnValue = ZSTD_decompressDCtx(dctx_, dest, destLength, src, srcLength);
+        if (ThrowHelper::IsDstSizeTooSmall(returnValue)) { written = 0; return false; }
+        written = ThrowHelper::EnsureZstdSuccess(returnValue);
+        return true;
+    }
+
+    /* Many independent compressed buffers in one pass (ZSTDB200_decompressBatch); per-item sizes / error codes. */
+    std::vector<BatchResult> UnwrapBatch(const std::vector<const void*>& src, const std::vector<size_t>& srcLength,
+                                         const std::vector<void*>& dest, const std::vector<size_t>& destLength) {
+        EnsureNotDisposed();
+        size_t n = src.size();
+        if (srcLength.size() != n || dest.size() != n || destLength.size() != n)
+            throw std::invalid_argument("UnwrapBatch: array lengths differ");
+        std::vector<size_t> raw(n);
+        ThrowHelper::EnsureZstdSuccess(ZSTDB200_decompressBatch(dctx_, n, src.data(), srcLength.data(),
+                                                                dest.data(), destLength.data(), raw.data()));
+        return detail::ToResults(raw);
+    }
+
+    void Dispose() {                                                                   /* Decompressor.cs:117-130 */
+        if (dctx_) { ZSTD_freeDCtx(dctx_); dctx_ = nullptr; }
+    }
+    ZSTD_DCtx* Handle() const { return dctx_; }
+
+private:
+    void EnsureNotDisposed() const { if (!dctx_) throw ObjectDisposedException("Decompressor"); }
+    ZSTD_DCtx* dctx_;
+};
+
+}  // namespace ZstdSharp
+
+#endif /* ZSTD_B200_HPP */
