@@ -63,6 +63,14 @@ ZSTDB200_API size_t     ZSTD_compressBound(size_t srcSize);                     
  * zstd decoder, ZSTD_decompressBound = item size, a few percent larger, NOT the reference's bytes). */
 #define ZSTDB200_c_independentChunks 10001
 ZSTDB200_API size_t     ZSTD_CCtx_setParameter(ZSTD_CCtx* cctx, int param, int value);             /* :37 */
+/* Compressor.GetParameter (Compressor.cs:35-41 -> U/ZstdCompress.cs:1289): reads back the parameters listed above; the level
+ * reads 3 after 0 was set (ZSTD_CLEVEL_DEFAULT), as in the reference. */
+ZSTDB200_API size_t     ZSTD_CCtx_getParameter(const ZSTD_CCtx* cctx, int param, int* value);
+/* Decompressor.SetParameter / GetParameter (Decompressor.cs:22-34 -> U/ZstdDecompress.cs:2532, 2477).  ZSTD_d_windowLogMax = 100:
+ * bounds 10..31, 0 = default 27, else ZSTD_error_parameter_outOfBound; it limits the streaming decoder only, exactly as in the
+ * reference (the one-shot ZSTD_decompressDCtx path never reads it).  Other parameters -> ZSTD_error_parameter_unsupported. */
+ZSTDB200_API size_t     ZSTD_DCtx_setParameter(ZSTD_DCtx* dctx, int param, int value);
+ZSTDB200_API size_t     ZSTD_DCtx_getParameter(const ZSTD_DCtx* dctx, int param, int* value);
 /* Decompressor.LoadDictionary (Decompressor.cs:43-56 -> U/ZstdDecompress.cs:2239 ZSTD_DCtx_loadDictionary): the dictionary is
  * copied; a zstd-format dictionary (magic 0xEC30A437: entropy tables, repcodes, content, U/ZstdDecompress.cs:1770-1931) or raw
  * content.  It then applies to every ZSTD_decompressDCtx / ZSTDB200_decompressBatch call of the context; NULL / 0 removes it.

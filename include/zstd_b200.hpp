@@ -37,9 +37,12 @@ enum class ZSTD_ErrorCode : int {
 
 /* ZSTD_cParameter members this library accepts (Compressor.SetParameter); others answer parameter_unsupported. */
 enum class ZSTD_cParameter : int {
-    ZSTD_c_compressionLevel = 100, ZSTD_c_contentSizeFlag = 200, ZSTD_c_checksumFlag = 201, ZSTD_c_dictIDFlag = 202,
+    ZSTD_c_compressionLevel = 100, ZSTD_c_contentSizeFlag = 200, ZSTD_c_checksumFlag = 201,
     independentChunks = ZSTDB200_c_independentChunks   /* enum member cannot share the macro's name */
 };
+
+/* ZSTD_dParameter (Decompressor.SetParameter / GetParameter). */
+enum class ZSTD_dParameter : int { ZSTD_d_windowLogMax = 100 };
 
 class ZstdException : public std::runtime_error {
 public:
@@ -117,6 +120,13 @@ public:
         ThrowHelper::EnsureZstdSuccess(ZSTD_CCtx_setParameter(cctx_, static_cast<int>(parameter), value));
     }
 
+    int GetParameter(ZSTD_cParameter parameter) const {                                /* Compressor.cs:35-41 */
+        EnsureNotDisposed();
+        int value = 0;
+        ThrowHelper::EnsureZstdSuccess(ZSTD_CCtx_getParameter(cctx_, static_cast<int>(parameter), &value));
+        return value;
+    }
+
     static int GetCompressBound(int length) { return static_cast<int>(ZSTD_compressBound(static_cast<size_t>(length))); }
     static uint64_t GetCompressBoundLong(uint64_t length) { return ZSTD_compressBound(static_cast<size_t>(length)); }
 
@@ -176,6 +186,17 @@ public:
     ~Decompressor() { Dispose(); }
     Decompressor(const Decompressor&) = delete;
     Decompressor& operator=(const Decompressor&) = delete;
+
+    void SetParameter(ZSTD_dParameter parameter, int value) {                          /* Decompressor.cs:22-26 */
+        EnsureNotDisposed();
+        ThrowHelper::EnsureZstdSuccess(ZSTD_DCtx_setParameter(dctx_, static_cast<int>(parameter), value));
+    }
+    int GetParameter(ZSTD_dParameter parameter) const {                                /* Decompressor.cs:28-34 */
+        EnsureNotDisposed();
+        int value = 0;
+        ThrowHelper::EnsureZstdSuccess(ZSTD_DCtx_getParameter(dctx_, static_cast<int>(parameter), &value));
+        return value;
+    }
 
     /* LoadDictionary(byte[] dict): null / empty drops the dictionary  (Decompressor.cs:36-48). */
     void LoadDictionary(const void* dict, size_t dictLength) {

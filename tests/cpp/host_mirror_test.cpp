@@ -87,6 +87,19 @@ static void host_only() {
     CHECK(thrown_code([&] { c.SetParameter(ZSTD_cParameter::ZSTD_c_checksumFlag, 2); }) == ZSTD_ErrorCode::parameter_outOfBound);
     CHECK(thrown_code([&] { c.Level(7); }) == ZSTD_ErrorCode::parameter_unsupported);
     CHECK(c.Level() == 3);
+    // Compressor.GetParameter (Compressor.cs:35-41), Decompressor.SetParameter / GetParameter (Decompressor.cs:22-34)
+    CHECK(c.GetParameter(ZSTD_cParameter::ZSTD_c_compressionLevel) == 3 && c.GetParameter(ZSTD_cParameter::ZSTD_c_checksumFlag) == 1);
+    c.Level(0);                                                       // 0 is stored as ZSTD_CLEVEL_DEFAULT
+    CHECK(c.GetParameter(ZSTD_cParameter::ZSTD_c_compressionLevel) == 3);
+    c.Level(3);
+    CHECK(d.GetParameter(ZSTD_dParameter::ZSTD_d_windowLogMax) == 27);
+    d.SetParameter(ZSTD_dParameter::ZSTD_d_windowLogMax, 31);
+    CHECK(d.GetParameter(ZSTD_dParameter::ZSTD_d_windowLogMax) == 31);
+    d.SetParameter(ZSTD_dParameter::ZSTD_d_windowLogMax, 0);
+    CHECK(d.GetParameter(ZSTD_dParameter::ZSTD_d_windowLogMax) == 27);
+    CHECK(thrown_code([&] { d.SetParameter(ZSTD_dParameter::ZSTD_d_windowLogMax, 9); }) == ZSTD_ErrorCode::parameter_outOfBound);
+    CHECK(thrown_code([&] { d.SetParameter(ZSTD_dParameter::ZSTD_d_windowLogMax, 32); }) == ZSTD_ErrorCode::parameter_outOfBound);
+    CHECK(thrown_code([&] { d.SetParameter(static_cast<ZSTD_dParameter>(1002), 1); }) == ZSTD_ErrorCode::parameter_unsupported);
     // disposed objects (Compressor.cs / Decompressor.cs EnsureNotDisposed)
     c.Dispose();
     bool disposed = false;

@@ -72,6 +72,27 @@ def test_parameter_surface():
             raise AssertionError("expected parameter_unsupported")
         except api.ZstdException as e:
             assert e.Code == api.ZSTD_ErrorCode.parameter_unsupported
+    # Compressor.GetParameter (Compressor.cs:35-41): level 0 reads back as ZSTD_CLEVEL_DEFAULT
+    assert c.GetParameter(api.ZSTD_cParameter.ZSTD_c_compressionLevel) == 3
+    c.Level = 0
+    assert c.GetParameter(api.ZSTD_cParameter.ZSTD_c_compressionLevel) == 3
+    c.Level = 2
+    assert c.GetParameter(api.ZSTD_cParameter.ZSTD_c_compressionLevel) == 2
+    assert c.GetParameter(api.ZSTD_cParameter.ZSTD_c_checksumFlag) == 0
+    # Decompressor.SetParameter / GetParameter (Decompressor.cs:22-34; bounds U/ZstdDecompress.cs:2401-2407, default :2543-2546)
+    d = api.Decompressor()
+    W = api.ZSTD_dParameter.ZSTD_d_windowLogMax
+    assert d.GetParameter(W) == 27
+    d.SetParameter(W, 10)
+    assert d.GetParameter(W) == 10
+    d.SetParameter(W, 0)
+    assert d.GetParameter(W) == 27
+    for bad in (9, 32, -1):
+        try:
+            d.SetParameter(W, bad)
+            raise AssertionError("expected parameter_outOfBound")
+        except api.ZstdException as e:
+            assert e.Code == api.ZSTD_ErrorCode.parameter_outOfBound
     c.Dispose()
     try:
         c.Wrap(b"abc")

@@ -22,6 +22,7 @@ EXPORTED_SYMBOLS = [
     "ZSTDB200_decompressBatch", "ZSTDB200_compressBatch", "ZSTDB200_decompressBatchDevice",
     "ZSTDB200_compressBatchDevice", "ZSTDB200_getLastTimings", "ZSTDB200_getLastLaunchCount",
     "ZSTDB200_lastErrorString", "ZSTDB200_deviceCount", "ZSTDB200_setStream", "ZSTD_DCtx_loadDictionary",
+    "ZSTD_CCtx_getParameter", "ZSTD_DCtx_setParameter", "ZSTD_DCtx_getParameter",
 ]
 
 
@@ -55,6 +56,12 @@ def _load() -> ctypes.CDLL:
     lib.ZSTD_compressBound.argtypes = [c_size_t]
     lib.ZSTD_CCtx_setParameter.restype = c_size_t
     lib.ZSTD_CCtx_setParameter.argtypes = [c_void_p, c_int, c_int]
+    lib.ZSTD_CCtx_getParameter.restype = c_size_t
+    lib.ZSTD_CCtx_getParameter.argtypes = [c_void_p, c_int, ctypes.POINTER(c_int)]
+    lib.ZSTD_DCtx_setParameter.restype = c_size_t
+    lib.ZSTD_DCtx_setParameter.argtypes = [c_void_p, c_int, c_int]
+    lib.ZSTD_DCtx_getParameter.restype = c_size_t
+    lib.ZSTD_DCtx_getParameter.argtypes = [c_void_p, c_int, ctypes.POINTER(c_int)]
     lib.ZSTD_decompressBound.restype = ctypes.c_ulonglong
     lib.ZSTD_decompressBound.argtypes = [c_void_p, c_size_t]
     lib.ZSTD_isError.restype = ctypes.c_uint

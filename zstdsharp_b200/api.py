@@ -63,6 +63,10 @@ class ZSTD_cParameter(enum.IntEnum):        # Unsafe/ZSTD_cParameter.cs (the one
     ZSTDB200_c_independentChunks = 10001     # new (include/zstd_b200.h): 1 = cut items above 128 KiB into independent frames
 
 
+class ZSTD_dParameter(enum.IntEnum):        # Unsafe/ZSTD_dParameter.cs
+    ZSTD_d_windowLogMax = 100
+
+
 class ZstdException(Exception):
     def __init__(self, code: int, message: str):
         super().__init__(message)
@@ -128,6 +132,12 @@ class Compressor:
     def SetParameter(self, parameter: int, value: int) -> None:
         self._ensure()
         EnsureZstdSuccess(_lib.ZSTD_CCtx_setParameter(self._cctx, int(parameter), int(value)))
+
+    def GetParameter(self, parameter: int) -> int:   # Compressor.cs:35-41
+        self._ensure()
+        value = ctypes.c_int(0)
+        EnsureZstdSuccess(_lib.ZSTD_CCtx_getParameter(self._cctx, int(parameter), ctypes.byref(value)))
+        return value.value
 
     @staticmethod
     def GetCompressBound(length: int) -> int:
@@ -214,6 +224,16 @@ class Decompressor:
         self._dctx = _lib.ZSTD_createDCtx()
         if not self._dctx:
             raise ZstdException(ZSTD_ErrorCode.GENERIC, "Failed to create dctx")
+
+    def SetParameter(self, parameter: int, value: int) -> None:   # Decompressor.cs:22-26
+        self._ensure()
+        EnsureZstdSuccess(_lib.ZSTD_DCtx_setParameter(self._dctx, int(parameter), int(value)))
+
+    def GetParameter(self, parameter: int) -> int:   # Decompressor.cs:28-34
+        self._ensure()
+        value = ctypes.c_int(0)
+        EnsureZstdSuccess(_lib.ZSTD_DCtx_getParameter(self._dctx, int(parameter), ctypes.byref(value)))
+        return value.value
 
     def LoadDictionary(self, dictionary) -> None:   # Decompressor.cs:43-56: null / empty removes the dictionary
         self._ensure()

@@ -748,7 +748,7 @@ static const char* error_name(uint32_t code)   // ErrorPrivate.cs:34-184
 //  extern "C" surface
 // =================================================================================================================
 struct ZSTD_CCtx_s { zb::Engine E; int level = 3; int checksum = 0; int chunked = 0; };
-struct ZSTD_DCtx_s { zb::Engine E; };
+struct ZSTD_DCtx_s { zb::Engine E; int windowLogMax = 27; };
 
 using zb::make_error;
 
@@ -777,6 +777,38 @@ size_t ZSTD_CCtx_setParameter(ZSTD_CCtx* cctx, int param, int value)
         if (value != 0 && value != 1) return (size_t)make_error(zb::kParameterOutOfBound);
         cctx->chunked = value; return 0;
     }
+    return (size_t)make_error(zb::kParameterUnsupported);
+}
+
+// Compressor.GetParameter (Compressor.cs:35-41 -> U/ZstdCompress.cs:1289-1299): the parameters ZSTD_CCtx_setParameter accepts.
+size_t ZSTD_CCtx_getParameter(const ZSTD_CCtx* cctx, int param, int* value)
+{
+    if (!cctx || !value) return (size_t)make_error(zb::kGeneric);
+    if (param == 100) { *value = cctx->level == 0 ? 3 : cctx->level; return 0; }   // level 0 is stored as ZSTD_CLEVEL_DEFAULT (U/ZstdCompress.cs:874-881)
+    if (param == 200) { *value = 1; return 0; }
+    if (param == 201) { *value = cctx->checksum; return 0; }
+    if (param == ZSTDB200_c_independentChunks) { *value = cctx->chunked; return 0; }
+    return (size_t)make_error(zb::kParameterUnsupported);
+}
+
+// Decompressor.SetParameter / GetParameter (Decompressor.cs:22-34 -> U/ZstdDecompress.cs:2532-2559, 2477-2486).  ZSTD_d_windowLogMax (100)
+// is kept with the reference's bounds and default (10..31, 0 -> 27); as in the reference it limits the STREAMING decoder only
+// (U/ZstdDecompress.cs:2349-2357), the one-shot path of ZSTD_decompressDCtx never reads it.  The experimental parameters
+// (1000..1003) are not implemented: parameter_unsupported.
+size_t ZSTD_DCtx_setParameter(ZSTD_DCtx* dctx, int param, int value)
+{
+    if (!dctx) return (size_t)make_error(zb::kGeneric);
+    if (param == 100) {
+        if (value == 0) value = 27;
+        if (value < 10 || value > 31) return (size_t)make_error(zb::kParameterOutOfBound);
+        dctx->windowLogMax = value; return 0;
+    }
+    return (size_t)make_error(zb::kParameterUnsupported);
+}
+size_t ZSTD_DCtx_getParameter(const ZSTD_DCtx* dctx, int param, int* value)
+{
+    if (!dctx || !value) return (size_t)make_error(zb::kGeneric);
+    if (param == 100) { *value = dctx->windowLogMax; return 0; }
     return (size_t)make_error(zb::kParameterUnsupported);
 }
 
