@@ -89,6 +89,20 @@ if DRY:
     comp, dec = _C(), _D()
 bad = 0
 allFrames = []
+_dumped = [0]
+
+
+def _dump(tag, frame, expect, got=None):              # failing cases go to gpurun_out/ so that they can be replayed on the CPU
+    if _dumped[0] >= 8:
+        return
+    _dumped[0] += 1
+    d = os.path.join(ROOT, "gpurun_out"); os.makedirs(d, exist_ok=True)
+    open(os.path.join(d, f"soakfail_{SEED}_{tag}.frame"), "wb").write(bytes(frame))
+    open(os.path.join(d, f"soakfail_{SEED}_{tag}.expect"), "wb").write(bytes(expect))
+    if got is not None:
+        open(os.path.join(d, f"soakfail_{SEED}_{tag}.got"), "wb").write(bytes(got))
+
+
 for level in (1, 2, 3):
     comp.Level = level
     t0 = time.time(); frames = comp.WrapBatch(inputs); tg = time.time() - t0
@@ -107,8 +121,12 @@ for level in (1, 2, 3):
 with ThreadPoolExecutor(16) as ex:
     zl = list(ex.map(lambda a: z.compress(a, int(4 + (a.size * 7919) % 16)), inputs))
 for name, frames in (("gpu L1", allFrames[0]), ("gpu L3", allFrames[2]), ("libzstd L4..19", zl)):
-    outs = dec.UnwrapBatch(frames)
+    outs = dec.UnwrapBatch(frames, raise_on_error=False)
     nb = sum(x != a.tobytes() for x, a in zip(outs, inputs))
+    for i, (x, a) in enumerate(zip(outs, inputs)):
+        if x != a.tobytes():
+            print(f"  DECODE FAILURE {name} input {i} size {a.size}: {x if not isinstance(x, (bytes, bytearray)) else len(x)}")
+            _dump(f"decode_{name.replace(' ', '_').replace('.', '')}_{i}", frames[i], a.tobytes())
     bad += nb
     print(f"decode {name}: {nb} mismatches of {N}", flush=True)
 # corrupted frames: same answer as the oracle (bytes, or an error on both sides)
@@ -129,6 +147,7 @@ for i, (m, r) in enumerate(zip(mut, res)):
     nerr += oerr
     if oerr != gerr or (not oerr and out[:rv].tobytes() != r):
         nb += 1
+        _dump(f"corrupt_{i}", m, b"" if oerr else out[:rv].tobytes(), b"" if gerr else r)
         if nb <= 3: print(f"  corrupted frame {i}: oracle {'error' if oerr else rv} gpu {'error ' + str(r) if gerr else len(r)}")
 bad += nb
 print(f"corrupted frames: {nb} disagreements of {N} ({nerr} rejected by the oracle)", flush=True)

@@ -161,6 +161,24 @@ def test_streams_that_run_dry_decode_like_the_reference(dec):
         assert len(r) == c["size"] and hashlib.sha256(r).hexdigest() == c["sha256"], c["name"]
 
 
+def test_sequence_streams_without_data_bits_at_every_alignment(dec):
+    """A block whose three sequence tables are all RLE has a bit stream of ONE byte (0x01, the end mark) and 16383 sequences of
+    zero bits each (input: every byte value repeated 8 times).  The frame sits behind a skippable frame of 0..127 bytes, so that the
+    stream starts on every address modulo 128 -- the bit reader's coordinate origin (soak seed 777002: such a stream on a 128-byte
+    boundary was taken for a stream without end mark)."""
+    o, z = oracle(), libzstd()
+    data = np.repeat(np.arange(3 * 16384 * 8 // 8, dtype=np.uint32).astype(np.uint8), 8)[: 379584]
+    frame = o.compress(data, 1)
+    assert frame == z.compress(data, 1) and o.decompress(frame, data.size) == data.tobytes()
+    items = [(0x184D2A50).to_bytes(4, "little") + k.to_bytes(4, "little") + bytes(k) + frame for k in range(128)]
+    for r in dec.UnwrapBatch(items):
+        assert r == data.tobytes()
+    # single 8-sequence-aligned blocks of the same kind, and the frame alone
+    sizes = (4096, 65536, 131072, 131073)
+    small = [o.compress(data[:n], lvl) for n in sizes for lvl in (1, 3)]
+    assert dec.UnwrapBatch(small + [frame]) == [data[:n].tobytes() for n in sizes for lvl in (1, 3)] + [data.tobytes()]
+
+
 def test_frame_checksum_is_verified(dec):
     """ZSTD_c_checksumFlag frames (SURVEY 8f.1): the XXH64 trailer is checked on the GPU (ZstdDecompress.cs:1186-1207);
     a damaged trailer or damaged content is checksum_wrong (22), exactly as the oracle reports."""

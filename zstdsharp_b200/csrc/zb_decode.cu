@@ -738,8 +738,11 @@ struct BitRingU {
     __device__ __forceinline__ uint32_t init(uint32_t ringShared, const uint8_t* first, uint32_t len) {
         sbase = ringShared;
         uintptr_t const a0 = (uintptr_t)first;
-        gbase = (const uint8_t*)(a0 & ~(uintptr_t)MASK);
-        uint32_t const rel = (uint32_t)(a0 & MASK);
+        // The base lies one ring length BELOW the aligned address, so that G >= 1024 for every stream: a stream without data bits (one
+        // byte 0x01: all three sequence tables RLE) that starts on a 128-byte boundary would otherwise have G == 0, the failure value
+        // (found by the soak, seed 777002: 1 valid frame of 40000 rejected).  Ring slots and peeks only use G modulo 1024 bits.
+        gbase = (const uint8_t*)(a0 & ~(uintptr_t)MASK) - RB;
+        uint32_t const rel = (uint32_t)(a0 & MASK) + RB;
         gZero = rel * 8;
         cLow = (int32_t)(rel / CH);
         fetched = cLow;
