@@ -917,7 +917,7 @@ __device__ __noinline__ uint32_t seq_bits_near_start(const uint8_t* s, uint32_t 
 {
     if (nb == 0) return 0;
     uint64_t w = 0; uint32_t sh;
-    if (R < 0) {
+    if (R <= 0) {                                                                                 // R == 0: bitsConsumed == 64, the shift count is already 0
         for (int j = 7; j >= 0; j--) w = (w << 8) | ((uint32_t)j < len ? s[j] : 0u);              // the container at ptr == start
         sh = (uint32_t)(-R) & 63u;
     } else {
@@ -926,6 +926,20 @@ __device__ __noinline__ uint32_t seq_bits_near_start(const uint8_t* s, uint32_t 
         sh = 7u - ((uint32_t)(R - 1) & 7u);
     }
     return (uint32_t)((w << sh) >> (64 - nb));
+}
+// BIT_readBits (Bitstream.cs:303-306, 329-336: BIT_getMiddleBits, used by FSE_initDState and by the FSE state updates) is NOT
+// BIT_readBitsFast near the stream start: container >> ((64 - bitsConsumed - nbBits) & 63), masked to nbBits.  A read that runs
+// past the start therefore returns bits from the TOP of the first eight bytes in its low positions instead of zero-filled real
+// bits.  (A read past the container only happens once the container sits at the stream start: before that a sequence consumes at
+// most 7 + 31 + 16 = 54 bits up to its mid reload and 7 + 30 + 26 = 63 without one.)  Found by the soak: 3 damaged frames of 80000
+// that the reference decodes were decoded to other bytes / rejected while every state update was read with the fast form.
+__device__ __noinline__ uint32_t seq_state_bits_near_start(const uint8_t* s, uint32_t len, int32_t R, uint32_t nb)
+{
+    if (nb == 0) return 0;
+    if (R >= (int32_t)nb) return seq_bits_near_start(s, len, R, nb);                              // inside the stream: an ordinary read
+    uint64_t w = 0;
+    for (int j = 7; j >= 0; j--) w = (w << 8) | ((uint32_t)j < len ? s[j] : 0u);                  // the container at ptr == start
+    return (uint32_t)(w >> ((uint32_t)(R - (int32_t)nb) & 63u)) & ((1u << nb) - 1u);
 }
 constexpr int32_t kSeqTailBits = 96;      // a sequence reads at most 31 + 16 + 16 extra bits and 9 + 9 + 8 state bits
 
@@ -991,9 +1005,9 @@ __global__ void __launch_bounds__(32) dec_seq_kernel(DecPass p)
         if ((int32_t)(G - (llLog + ofLog + mlLog)) < gz) {           // fewer bits than the three initial states need: the reference reads on
             int32_t const R = (int32_t)G - gz;
             const uint8_t* const ss = p.src + it.srcOff + it.seqOff; uint32_t const sl = it.seqLen;
-            aL = kFseLLOff + seq_bits_near_start(ss, sl, R, llLog);
-            aO = kFseOFOff + seq_bits_near_start(ss, sl, R - (int32_t)llLog, ofLog);
-            aM = kFseMLOff + seq_bits_near_start(ss, sl, R - (int32_t)(llLog + ofLog), mlLog);
+            aL = kFseLLOff + seq_state_bits_near_start(ss, sl, R, llLog);
+            aO = kFseOFOff + seq_state_bits_near_start(ss, sl, R - (int32_t)llLog, ofLog);
+            aM = kFseMLOff + seq_state_bits_near_start(ss, sl, R - (int32_t)(llLog + ofLog), mlLog);
         }
         G -= llLog + ofLog + mlLog;
     }
@@ -1080,9 +1094,9 @@ __global__ void __launch_bounds__(32) dec_seq_kernel(DecPass p)
             uint32_t const ofExtra = seq_bits_near_start(ss, sl, R, ofBits); R -= (int32_t)ofBits;
             uint32_t const ml = lds32(mlBaseS + mlSym * 4) + seq_bits_near_start(ss, sl, R, mlBits); R -= (int32_t)mlBits;
             uint32_t const ll = lds32(llBaseS + llSym * 4) + seq_bits_near_start(ss, sl, R, llBits); R -= (int32_t)llBits;
-            aL = kFseLLOff + (nL | ((eL >> 15) << 8)) + seq_bits_near_start(ss, sl, R, nbL); R -= (int32_t)nbL;
-            aM = kFseMLOff + (nM | ((eM >> 15) << 8)) + seq_bits_near_start(ss, sl, R, nbM); R -= (int32_t)nbM;
-            aO = kFseOFOff + (nO | ((eO >> 15) << 8)) + seq_bits_near_start(ss, sl, R, nbO); R -= (int32_t)nbO;
+            aL = kFseLLOff + (nL | ((eL >> 15) << 8)) + seq_state_bits_near_start(ss, sl, R, nbL); R -= (int32_t)nbL;
+            aM = kFseMLOff + (nM | ((eM >> 15) << 8)) + seq_state_bits_near_start(ss, sl, R, nbM); R -= (int32_t)nbM;
+            aO = kFseOFOff + (nO | ((eO >> 15) << 8)) + seq_state_bits_near_start(ss, sl, R, nbO); R -= (int32_t)nbO;
             G = (uint32_t)(R + gz);
             uint32_t offset;
             {   // ZSTD_decodeSequence offset rules (:2397-2445)
