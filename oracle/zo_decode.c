@@ -7,8 +7,10 @@
  *        -> ZSTD_decodeSeqHeaders / ZSTD_buildFSETable -> ZSTD_decompressSequences_body
  *           (ZSTD_decodeSequence + ZSTD_execSequence)
  * Citations are file:line under /root/reference/src/ZstdSharp/Unsafe/.
- * The result-neutral CPU variants (HUF X2 tables, split literal buffer, prefetching "Long" decoder:
- * ZstdDecompressBlock.cs:2487, :2796; HufDecompress.cs:652-1455) are deliberately not restated.
+ * The result-neutral CPU variants (split literal buffer, prefetching "Long" decoder: ZstdDecompressBlock.cs:2487, :2796)
+ * are deliberately not restated.  The double-symbol Huffman decoder (HufDecompress.cs:652-1455) IS restated: on valid streams
+ * it yields the bytes of the single-symbol decoder, but on damaged streams its verdict differs (HUF_decodeLastSymbolX2's
+ * bit clamp, the op1 > opStart2 checks), and the reference picks it through HUF_selectDecoder (:1688).
  */
 #include "zo_common.h"
 #include "zo.h"
@@ -291,7 +293,8 @@ static size_t FSE_decompress_wksp(BYTE* dst, size_t dstCapacity, const void* cSr
  *  single-symbol stream decoding (HufDecompress.cs:254-537)
  * ===================================================================================== */
 typedef struct { BYTE nbBits; BYTE byte; } HUF_DEltX1;
-typedef struct { unsigned tableLog; HUF_DEltX1 dt[1 << 12]; } HUF_DTable;
+typedef struct { U16 sequence; BYTE nbBits; BYTE length; } HUF_DEltX2;   /* HUF_DEltX2.cs */
+typedef struct { unsigned tableLog; unsigned tableType; HUF_DEltX1 dt[1 << 12]; HUF_DEltX2 dt2[1 << 12]; } HUF_DTable;
 
 static size_t HUF_readStats(BYTE* huffWeight, size_t hwSize, U32* rankStats, U32* nbSymbolsPtr, U32* tableLogPtr, const void* src, size_t srcSize)
 {
@@ -351,7 +354,7 @@ static size_t HUF_readDTableX1(HUF_DTable* DTable, const void* src, size_t srcSi
             tableLog = targetTableLog;
         }
         if (tableLog > maxTableLog) return ERROR(tableLog_tooLarge);
-        DTable->tableLog = tableLog;
+        DTable->tableLog = tableLog; DTable->tableType = 0;
     }
     {   U32 n, nextRankStart = 0;
         for (n = 0; n < tableLog + 1; n++) { U32 const curr = nextRankStart; nextRankStart += rankVal[n]; rankStart[n] = curr; }
@@ -427,6 +430,146 @@ static size_t HUF_decompress4X1_usingDTable(BYTE* dst, size_t dstSize, const voi
         if (!(BIT_endOfDStream(&b1) & BIT_endOfDStream(&b2) & BIT_endOfDStream(&b3) & BIT_endOfDStream(&b4))) return ERROR(corruption_detected);
         return dstSize;
     }
+}
+
+/* ---- double-symbol decoder : HufDecompress.cs:652-1455 -------------------------------------------------------------
+ * HUF_readDTableX2_wksp_bmi2 (:892-1010) builds, at log maxTableLog (11 when tableLog <= 11, else 12 : :934-937), a table
+ * whose cell for an index holds the first symbol s1 (l1 bits) and, when the remaining maxTableLog - l1 bits decide a second
+ * symbol s2 completely (l2 <= maxTableLog - l1, HUF_fillDTableX2 :848 / Level2 :789: the cells below rankVal[minWeight] are
+ * the "skipped" single-symbol ones), both: {sequence = s1 | s2 << 8, nbBits = l1 + l2, length = 2}.  The canonical code
+ * (cells ordered by weight, then symbol) is the one HUF_readDTableX1 lays out, so the cells are derived from that table. */
+static size_t HUF_readDTableX2(HUF_DTable* DTable, const void* src, size_t srcSize)
+{
+    size_t const iSize = HUF_readDTableX1(DTable, src, srcSize);   /* same HUF_readStats verdicts; log 11 unless tableLog == 12 */
+    if (ERR_isError(iSize)) return iSize;
+    {   U32 const dtLog = DTable->tableLog; U32 const size = 1U << dtLog; U32 idx; U32 minBits = 32;
+        for (idx = 0; idx < size; idx++) if (DTable->dt[idx].nbBits < minBits) minBits = DTable->dt[idx].nbBits;
+        for (idx = 0; idx < size; idx++) {
+            HUF_DEltX1 const e1 = DTable->dt[idx];
+            HUF_DEltX2 e; e.sequence = e1.byte; e.nbBits = e1.nbBits; e.length = 1;
+            if (dtLog - e1.nbBits >= minBits) {                       /* :870 enough room for a second symbol */
+                HUF_DEltX1 const e2 = DTable->dt[(idx << e1.nbBits) & (size - 1)];
+                if (e2.nbBits <= dtLog - e1.nbBits) { e.sequence = (U16)(e1.byte | (e2.byte << 8)); e.nbBits = (BYTE)(e1.nbBits + e2.nbBits); e.length = 2; }
+            }
+            DTable->dt2[idx] = e;
+        }
+        DTable->tableType = 1;
+    }
+    return iSize;
+}
+static inline U32 HUF_decodeSymbolX2(BYTE* op, BIT_DStream_t* D, const HUF_DEltX2* dt, U32 dtLog)   /* :1012 */
+{
+    size_t const val = BIT_lookBitsFast(D, dtLog);
+    op[0] = (BYTE)dt[val].sequence; op[1] = (BYTE)(dt[val].sequence >> 8);
+    BIT_skipBits(D, dt[val].nbBits);
+    return dt[val].length;
+}
+static inline U32 HUF_decodeLastSymbolX2(BYTE* op, BIT_DStream_t* D, const HUF_DEltX2* dt, U32 dtLog)   /* :1022 */
+{
+    size_t const val = BIT_lookBitsFast(D, dtLog);
+    op[0] = (BYTE)dt[val].sequence;
+    if (dt[val].length == 1) BIT_skipBits(D, dt[val].nbBits);
+    else if (D->bitsConsumed < 64) {
+        BIT_skipBits(D, dt[val].nbBits);
+        if (D->bitsConsumed > 64) D->bitsConsumed = 64;      /* the reference's "ugly hack": accepted although the pair ran past the start */
+    }
+    return 1;
+}
+/* :1047.  Writes two bytes per step: the reference's literal buffer has room past dstSize (WILDCOPY_OVERLENGTH); here the
+ * caller's buffer is litBuffer[ZSTD_BLOCKSIZE_MAX + 32]. */
+static size_t HUF_decodeStreamX2(BYTE* p, BIT_DStream_t* bitD, BYTE* const pEnd, const HUF_DEltX2* dt, U32 dtLog)
+{
+    BYTE* const pStart = p;
+    if ((size_t)(pEnd - p) >= sizeof(size_t)) {
+        if (dtLog <= 11) {
+            while ((BIT_reloadDStream(bitD) == BIT_DStream_unfinished) && (p < pEnd - 9)) {
+                p += HUF_decodeSymbolX2(p, bitD, dt, dtLog); p += HUF_decodeSymbolX2(p, bitD, dt, dtLog); p += HUF_decodeSymbolX2(p, bitD, dt, dtLog);
+                p += HUF_decodeSymbolX2(p, bitD, dt, dtLog); p += HUF_decodeSymbolX2(p, bitD, dt, dtLog);
+            }
+        } else {
+            while ((BIT_reloadDStream(bitD) == BIT_DStream_unfinished) && (p < pEnd - (sizeof(size_t) - 1))) {
+                p += HUF_decodeSymbolX2(p, bitD, dt, dtLog); p += HUF_decodeSymbolX2(p, bitD, dt, dtLog);
+                p += HUF_decodeSymbolX2(p, bitD, dt, dtLog); p += HUF_decodeSymbolX2(p, bitD, dt, dtLog);
+            }
+        }
+    } else {
+        BIT_reloadDStream(bitD);
+    }
+    if ((size_t)(pEnd - p) >= 2) {
+        while ((BIT_reloadDStream(bitD) == BIT_DStream_unfinished) && (p <= pEnd - 2)) p += HUF_decodeSymbolX2(p, bitD, dt, dtLog);
+        while (p <= pEnd - 2) p += HUF_decodeSymbolX2(p, bitD, dt, dtLog);
+    }
+    if (p < pEnd) p += HUF_decodeLastSymbolX2(p, bitD, dt, dtLog);
+    return (size_t)(p - pStart);
+}
+static size_t HUF_decompress1X2_usingDTable(BYTE* dst, size_t dstSize, const void* cSrc, size_t cSrcSize, const HUF_DTable* DTable)  /* :1114 */
+{
+    BIT_DStream_t bitD;
+    CHECK_F(BIT_initDStream(&bitD, cSrc, cSrcSize));
+    HUF_decodeStreamX2(dst, &bitD, dst + dstSize, DTable->dt2, DTable->tableLog);
+    if (!BIT_endOfDStream(&bitD)) return ERROR(corruption_detected);
+    return dstSize;
+}
+/* :1148 HUF_decompress4X2_usingDTable_internal_body : the interleaved main loop matters here (its stop condition looks at
+ * stream 4 only and the other three may overshoot their segment on damaged input, :1322-1335), so it is restated as is. */
+static size_t HUF_decompress4X2_usingDTable(BYTE* dst, size_t dstSize, const void* cSrc, size_t cSrcSize, const HUF_DTable* DTable)
+{
+    if (cSrcSize < 10) return ERROR(corruption_detected);
+    {   const BYTE* const istart = (const BYTE*)cSrc;
+        BYTE* const ostart = dst; BYTE* const oend = ostart + dstSize; BYTE* const olimit = oend - (sizeof(size_t) - 1);
+        const HUF_DEltX2* const dt = DTable->dt2; U32 const dtLog = DTable->tableLog;
+        size_t const length1 = MEM_read16(istart), length2 = MEM_read16(istart + 2), length3 = MEM_read16(istart + 4);
+        size_t const length4 = cSrcSize - (length1 + length2 + length3 + 6);
+        const BYTE* const istart1 = istart + 6; const BYTE* const istart2 = istart1 + length1;
+        const BYTE* const istart3 = istart2 + length2; const BYTE* const istart4 = istart3 + length3;
+        size_t const segmentSize = (dstSize + 3) / 4;
+        BYTE* const opStart2 = ostart + segmentSize; BYTE* const opStart3 = opStart2 + segmentSize; BYTE* const opStart4 = opStart3 + segmentSize;
+        BYTE* op1 = ostart; BYTE* op2 = opStart2; BYTE* op3 = opStart3; BYTE* op4 = opStart4;
+        U32 endSignal = 1;
+        BIT_DStream_t b1, b2, b3, b4;
+        if (length4 > cSrcSize) return ERROR(corruption_detected);
+        if (opStart4 > oend) return ERROR(corruption_detected);
+        CHECK_F(BIT_initDStream(&b1, istart1, length1));
+        CHECK_F(BIT_initDStream(&b2, istart2, length2));
+        CHECK_F(BIT_initDStream(&b3, istart3, length3));
+        CHECK_F(BIT_initDStream(&b4, istart4, length4));
+        if ((size_t)(oend - op4) >= sizeof(size_t)) {
+            for ( ; endSignal & (U32)(op4 < olimit); ) {
+                int k;
+                for (k = 0; k < 4; k++) op1 += HUF_decodeSymbolX2(op1, &b1, dt, dtLog);
+                for (k = 0; k < 4; k++) op2 += HUF_decodeSymbolX2(op2, &b2, dt, dtLog);
+                endSignal &= (BIT_reloadDStreamFast(&b1) == BIT_DStream_unfinished);
+                endSignal &= (BIT_reloadDStreamFast(&b2) == BIT_DStream_unfinished);
+                for (k = 0; k < 4; k++) op3 += HUF_decodeSymbolX2(op3, &b3, dt, dtLog);
+                for (k = 0; k < 4; k++) op4 += HUF_decodeSymbolX2(op4, &b4, dt, dtLog);
+                endSignal &= (BIT_reloadDStreamFast(&b3) == BIT_DStream_unfinished);
+                endSignal &= (BIT_reloadDStreamFast(&b4) == BIT_DStream_unfinished);
+            }
+        }
+        if (op1 > opStart2) return ERROR(corruption_detected);
+        if (op2 > opStart3) return ERROR(corruption_detected);
+        if (op3 > opStart4) return ERROR(corruption_detected);
+        HUF_decodeStreamX2(op1, &b1, opStart2, dt, dtLog);
+        HUF_decodeStreamX2(op2, &b2, opStart3, dt, dtLog);
+        HUF_decodeStreamX2(op3, &b3, opStart4, dt, dtLog);
+        HUF_decodeStreamX2(op4, &b4, oend, dt, dtLog);
+        if (!(BIT_endOfDStream(&b1) & BIT_endOfDStream(&b2) & BIT_endOfDStream(&b3) & BIT_endOfDStream(&b4))) return ERROR(corruption_detected);
+        return dstSize;
+    }
+}
+/* :1688 HUF_selectDecoder, algoTime :1471-1681 ({tableTime, decode256Time} of the single- and the double-symbol decoder) */
+static const U16 zo_algoTime[16][4] = {
+    {0, 0, 1, 1}, {0, 0, 1, 1}, {150, 216, 381, 119}, {170, 205, 514, 112}, {177, 199, 539, 110}, {197, 194, 644, 107},
+    {221, 192, 735, 107}, {256, 189, 881, 106}, {359, 188, 1167, 109}, {582, 187, 1570, 114}, {688, 187, 1712, 122},
+    {825, 186, 1965, 136}, {976, 185, 2131, 150}, {1180, 186, 2070, 175}, {1377, 185, 1731, 202}, {1412, 185, 1695, 202} };
+static U32 HUF_selectDecoder(size_t dstSize, size_t cSrcSize)
+{
+    U32 const Q = (cSrcSize >= dstSize) ? 15 : (U32)(cSrcSize * 16 / dstSize);
+    U32 const D256 = (U32)(dstSize >> 8);
+    U32 const DTime0 = zo_algoTime[Q][0] + zo_algoTime[Q][1] * D256;
+    U32 DTime1 = zo_algoTime[Q][2] + zo_algoTime[Q][3] * D256;
+    DTime1 += DTime1 >> 5;
+    return DTime1 < DTime0;
 }
 
 /* =====================================================================================
@@ -512,8 +655,10 @@ static size_t zo_decodeLiteralsBlock(zo_DCtx* dctx, const void* src, size_t srcS
                 if (litCSize + lhSize > srcSize) return ERROR(corruption_detected);
                 if (expectedWriteSize < litSize) return ERROR(dstSize_tooSmall);
                 if (litEncType == set_repeat) {
-                    hufSuccess = singleStream ? HUF_decompress1X1_usingDTable(dctx->litBuffer, litSize, istart + lhSize, litCSize, &dctx->hufTable)
-                                              : HUF_decompress4X1_usingDTable(dctx->litBuffer, litSize, istart + lhSize, litCSize, &dctx->hufTable);
+                    /* HUF_decompress{1,4}X_usingDTable_bmi2 (HufDecompress.cs:1759, :1786): by the type the table was built with */
+                    int const x2 = dctx->hufTable.tableType != 0;
+                    hufSuccess = singleStream ? (x2 ? HUF_decompress1X2_usingDTable : HUF_decompress1X1_usingDTable)(dctx->litBuffer, litSize, istart + lhSize, litCSize, &dctx->hufTable)
+                                              : (x2 ? HUF_decompress4X2_usingDTable : HUF_decompress4X1_usingDTable)(dctx->litBuffer, litSize, istart + lhSize, litCSize, &dctx->hufTable);
                 } else {
                     /* HUF_decompress{1X1_DCtx,4X_hufOnly}_wksp_bmi2 : HufDecompress.cs:1793 / :1774.
                      * hufOnly rejects dstSize==0 and cSrcSize==0 up front. */
@@ -521,13 +666,16 @@ static size_t zo_decodeLiteralsBlock(zo_DCtx* dctx, const void* src, size_t srcS
                     if (!singleStream && litSize == 0) hufSuccess = ERROR(dstSize_tooSmall);
                     else if (!singleStream && cSrcSize == 0) hufSuccess = ERROR(corruption_detected);
                     else {
-                        size_t const hSize = HUF_readDTableX1(&dctx->hufTable, ip, cSrcSize);
+                        /* single stream: always the single-symbol decoder (ZstdDecompressBlock.cs:212); four streams: HUF_selectDecoder */
+                        int const x2 = !singleStream && HUF_selectDecoder(litSize, cSrcSize);
+                        size_t const hSize = x2 ? HUF_readDTableX2(&dctx->hufTable, ip, cSrcSize) : HUF_readDTableX1(&dctx->hufTable, ip, cSrcSize);
                         if (ERR_isError(hSize)) hufSuccess = hSize;
                         else if (hSize >= cSrcSize) hufSuccess = ERROR(srcSize_wrong);
                         else {
                             ip += hSize; cSrcSize -= hSize;
                             hufSuccess = singleStream ? HUF_decompress1X1_usingDTable(dctx->litBuffer, litSize, ip, cSrcSize, &dctx->hufTable)
-                                                      : HUF_decompress4X1_usingDTable(dctx->litBuffer, litSize, ip, cSrcSize, &dctx->hufTable);
+                                       : x2 ? HUF_decompress4X2_usingDTable(dctx->litBuffer, litSize, ip, cSrcSize, &dctx->hufTable)
+                                            : HUF_decompress4X1_usingDTable(dctx->litBuffer, litSize, ip, cSrcSize, &dctx->hufTable);
                         }
                     }
                 }
@@ -1012,7 +1160,7 @@ static size_t zo_insertDictionary(zo_DCtx* dctx, const void* dict, size_t dictSi
     if (dictSize >= 8 && MEM_read32(dict) == 0xEC30A437U) {
         dctx->loadedDictID = MEM_read32(dictPtr + 4);
         dictPtr += 8;
-        {   size_t const hSize = HUF_readDTableX1(&dctx->hufTable, dictPtr, (size_t)(dEnd - dictPtr));     /* the reference builds the X2 form of the same code */
+        {   size_t const hSize = HUF_readDTableX2(&dctx->hufTable, dictPtr, (size_t)(dEnd - dictPtr));     /* ZstdDecompress.cs:1786 */
             if (ERR_isError(hSize)) return ERROR(dictionary_corrupted);
             dictPtr += hSize; }
         {   S16 norm[MaxOff + 1]; unsigned maxV = MaxOff, log;

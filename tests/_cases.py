@@ -37,3 +37,44 @@ def multiblock_inputs():
         "tiny_tail_literals": np.concatenate([text[:FRAME], lit[:900]]),   # last block literals <= 1024: preferRepeat
     }
     return cases
+
+
+def handbuilt_small_4stream_frames():
+    """Hand-built frames whose literal section has FOUR Huffman streams although it is tiny (segments of 20 / 7 literals; the
+    reference's encoder never does this below 256 literals, other encoders may) and whose sequences take literal runs of
+    <= 40 bytes across TWO segment boundaries.  Returns [(frame, expected_bytes)]."""
+    code = {1: "000", 2: "001", 0: "01", 3: "1"}           # weights {0: 2, 1: 1, 2: 1, 3: 3 (implied)}, tableLog 3
+
+    def stream(symbols):
+        bits = "1" + "".join(code[s] for s in symbols)      # end mark, then the symbols in decoding order
+        bits = "0" * (-len(bits) % 8) + bits
+        return int(bits, 2).to_bytes(len(bits) // 8, "little")
+
+    out = []
+    rng = np.random.default_rng(5)
+    for lit_size, lls in ((80, (32, 38)), (28, (13, 13)), (80, (39, 39))):
+        lits = rng.choice([0, 1, 2, 3], size=lit_size, p=[0.3, 0.1, 0.1, 0.5]).astype(np.uint8)
+        seg = (lit_size + 3) // 4
+        streams = [stream(lits[i * seg:min(lit_size, (i + 1) * seg)].tolist()) for i in range(4)]
+        tree = bytes([127 + 3, 0x21, 0x10])
+        jump = b"".join(len(s).to_bytes(2, "little") for s in streams[:3])
+        payload = tree + jump + b"".join(streams)
+        lit_hdr = (2 | (1 << 2) | (lit_size << 4) | (len(payload) << 14)).to_bytes(3, "little")
+        if lls[0] >= 32:        # LL code 22: 32 + 3 extra bits; RLE tables: no state bits
+            ll_code, extra = 22, "".join(format(ll - 32, "03b") for ll in lls)
+        else:                   # LL codes below 16 have no extra bits: both runs must then be equal ... use code = ll directly twice
+            ll_code, extra, lls = lls[0], "", (lls[0], lls[0])
+        bits = "1" + extra
+        bits = "0" * (-len(bits) % 8) + bits
+        seq = bytes([2, 0x54, ll_code, 0, 0]) + int(bits, 2).to_bytes(len(bits) // 8, "little")
+        block = lit_hdr + payload + seq
+        expect = bytearray()
+        pos = 0
+        for ll in lls:
+            expect += lits[pos:pos + ll].tobytes(); pos += ll
+            expect += bytes([expect[-1]]) * 3                # matchLength code 0 = 3 bytes at repeat offset 1
+        expect += lits[pos:].tobytes()
+        hdr = (1 | (2 << 1) | (len(block) << 3)).to_bytes(3, "little")
+        frame = bytes.fromhex("28b52ffd") + bytes([0x20, len(expect)]) + hdr + block
+        out.append((frame, bytes(expect)))
+    return out

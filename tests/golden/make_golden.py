@@ -1,13 +1,11 @@
-"""Generates tests/golden/golden_vectors.json.
+"""Generates tests/golden/golden_vectors.json from the REFERENCE'S OWN native oracle.
 
-The reference (C#) cannot run in this image and its own fixtures are unusable here (`dickens` is missing, libzstd.dll
-is a Windows binary: SURVEY.md section 8c), so the golden vectors are produced by the upstream C implementation the
-reference is a mechanical translation of -- system libzstd (1.5.5) -- on small deterministic inputs, at levels 1..3
-where 1.5.5 was verified byte-identical to the reference's 1.5.1 logic on this path.  For larger inputs only the
-SHA-256 of the frame is stored.  Run:  python tests/golden/make_golden.py
+src/Zstd.Extern/libzstd.dll (zstd 1.5.1) is the binary the reference's differential test asserts ZstdSharp equals byte for
+byte at every level (src/ZstdSharp.Test/ZstdTest.cs:64-90).  It runs here through the PE mapper in oracle/ref_pe
+(oracle/_ref/libzstdref.so), so the vectors are reference-held answers, not the output of some other zstd release.
+The generator needs /root/reference (this container); the vectors travel.  For larger inputs only the SHA-256 of the
+frame is stored.  Run:  python tests/golden/make_golden.py
 """
-import ctypes
-import ctypes.util
 import hashlib
 import json
 import os
@@ -17,7 +15,10 @@ import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+sys.path.insert(0, os.path.dirname(HERE))
 from zstdsharp_b200 import datagen as dg  # noqa: E402
+
+LEVELS = (1, 2, 3)
 
 
 def inputs():
@@ -47,23 +48,15 @@ def inputs():
 
 
 def main():
-    z = ctypes.CDLL(ctypes.util.find_library("zstd") or "libzstd.so.1")
-    z.ZSTD_compress.restype = ctypes.c_size_t
-    z.ZSTD_compress.argtypes = [ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int]
-    z.ZSTD_compressBound.restype = ctypes.c_size_t
-    z.ZSTD_compressBound.argtypes = [ctypes.c_size_t]
-    z.ZSTD_versionNumber.restype = ctypes.c_uint
-    out = {"generator": "system libzstd", "libzstd_version": int(z.ZSTD_versionNumber()), "vectors": []}
+    from _oracle import refdll
+    z = refdll()
+    assert z.version() == 10501
+    out = {"generator": "reference src/Zstd.Extern/libzstd.dll through oracle/ref_pe", "libzstd_version": z.version(), "vectors": []}
     for name, data in inputs():
         whole = len(data) <= dg.FRAME or "multiblock" in name
         pieces = [data] if whole else [data[i:i + dg.FRAME] for i in range(0, len(data), dg.FRAME)]
-        for level in (1, 2, 3):
-            frames = []
-            for p in pieces:
-                cap = z.ZSTD_compressBound(len(p))
-                buf = ctypes.create_string_buffer(max(cap, 1))
-                r = z.ZSTD_compress(buf, cap, p, len(p), level)
-                frames.append(buf.raw[:r])
+        for level in LEVELS:
+            frames = [z.compress(p, level) for p in pieces]
             blob = b"".join(frames)
             v = {"name": name, "level": level, "src_len": len(data), "src_sha256": hashlib.sha256(data).hexdigest(),
                  "frame_sizes": [len(f) for f in frames], "frames_sha256": hashlib.sha256(blob).hexdigest()}

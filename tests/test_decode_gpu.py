@@ -147,6 +147,54 @@ def test_corrupted_payload_never_crashes(dec):
             assert isinstance(r, ZstdException)
 
 
+@pytest.mark.parametrize("workload", ["text", "literal_heavy", "literal_mix", "silesia"])
+def test_damaged_frames_get_the_reference_verdict(dec, workload):
+    """360 damaged frames per workload: same error code as the oracle (which tests/test_reference_pin.py holds to the reference's
+    own libzstd.dll on the same construction) or the same bytes.  Literal-heavy frames reach the double-symbol Huffman decoder's
+    acceptance rules (huf_x2_replay); when the reference binary is present the answers are checked against it directly as well."""
+    from zstdsharp_b200 import ZstdException
+    from _oracle import refdll_available, refdll
+    o = oracle()
+    r = refdll() if refdll_available() else None
+    rng = np.random.default_rng({"text": 21, "literal_heavy": 22, "literal_mix": 23, "silesia": 24}[workload])
+    data = dg.WORKLOADS[workload](3 * FRAME)
+    frames = []
+    for ci in range(3):
+        src = data[ci * FRAME:(ci + 1) * FRAME]
+        for level in (1, 3):
+            f = o.compress(src, level, checksum=ci & 1)
+            for _ in range(60):
+                g = bytearray(f)
+                for _k in range(int(rng.integers(1, 3))):
+                    pos = int(rng.integers(0, len(g)))
+                    g[pos] ^= 1 << int(rng.integers(0, 8))
+                frames.append(bytes(g))
+    res = dec.UnwrapBatch(frames, raise_on_error=False, capacity=FRAME)
+    accepted = 0
+    for g, got in zip(frames, res):
+        rv, out = o.decompress_raw(g, FRAME)
+        if r is not None:
+            rr, outr = r.decompress_raw(g, FRAME)
+            assert o.error_code(rv) == r.error_code(rr) and (r.lib.ZREF_isError(rr) or outr[:rr].tobytes() == out[:rv].tobytes())
+        if o.lib.zo_isError(rv):
+            assert isinstance(got, ZstdException) and got.Code == o.error_code(rv), (got, o.error_code(rv))
+        else:
+            assert not isinstance(got, ZstdException), got
+            assert got == out[:rv].tobytes()
+            accepted += 1
+    assert accepted > 0
+
+
+def test_handbuilt_tiny_four_stream_literals(dec):
+    """Four Huffman streams over 28 / 80 literals with literal runs of <= 40 bytes across two segment boundaries (legal; never
+    written by zstd's encoder): dec_exec's per-lane literal path must not be used for them."""
+    from _cases import handbuilt_small_4stream_frames
+    cases = handbuilt_small_4stream_frames()
+    outs = dec.UnwrapBatch([f for f, _ in cases] * 40)
+    for (f, expect), got in zip(cases * 40, outs):
+        assert got == expect
+
+
 def test_streams_that_run_dry_decode_like_the_reference(dec):
     """tests/golden/overread_frames.json: damaged frames whose sequence bit stream runs dry before its last sequence.  The
     reference reads on past the stream start (Bitstream.cs:293-340) and only checks the stream after the last sequence

@@ -3,9 +3,11 @@
 What pins it:
   * the reference tests' known answers: frame-header descriptor bytes (ZstdNetTests.cs:194-204), compressBound,
     error codes (dst too small -> 70, ZstdNetTests.cs:214-258), empty / 1-byte / size-sweep round trips (:456-496);
-  * committed golden vectors (tests/golden/golden_vectors.json, produced by upstream libzstd 1.5.5);
-  * live differential runs against system libzstd 1.5.5 (the upstream C the reference translates at v1.5.1):
+  * committed golden vectors (tests/golden/golden_vectors.json, produced by the reference's own libzstd.dll 1.5.1 through
+    oracle/ref_pe: tests/golden/make_golden.py);
+  * live differential runs against system libzstd 1.5.5 (a second, independent checker that also exists on the GPU box):
     byte-identical frames at levels 1..3, identical decoded bytes for frames of any level.
+The live pin against the reference's native binary itself is tests/test_reference_pin.py.
 """
 import hashlib
 import json
@@ -167,11 +169,13 @@ def test_known_answers_and_errors():
 
 
 def test_corrupted_frames_agree_with_libzstd():
-    """Damaged payloads: the oracle's verdict class (ok / error) follows upstream, and accepted frames give the same bytes."""
+    """Damaged payloads against the SECOND checker (libzstd 1.5.5, present on the GPU box too): the verdict class mostly follows
+    it.  The authority is the reference's own 1.5.1 binary: tests/test_reference_pin.py::test_damaged_frames_get_the_dlls_verdict
+    demands the same error code or the same bytes on every damaged frame."""
     o, z = oracle(), libzstd()
     rng = np.random.default_rng(11)
     f = o.compress(dg.text_like(FRAME), 1)
-    agree = 0
+    agree = same_bytes = both_ok = 0
     for _ in range(200):
         g = bytearray(f)
         pos = int(rng.integers(9, len(g)))
@@ -182,11 +186,12 @@ def test_corrupted_frames_agree_with_libzstd():
         if eo == ez:
             agree += 1
             if not eo:
-                assert ro == rz and outo[:ro].tobytes() == outz[:rz].tobytes()
-    # Verdicts may differ on a few damaged frames, and the reference (1.5.1 semantics) is the authority: e.g. the 1.5.1
-    # Huffman decoder insists on exact stream consumption (HufDecompress.cs:526-533) where 1.5.5's fast loop only
-    # checks the symbol count, so a flipped literal bit that keeps code lengths is accepted by 1.5.5, rejected by 1.5.1.
-    assert agree >= 170
+                both_ok += 1
+                same_bytes += ro == rz and outo[:ro].tobytes() == outz[:rz].tobytes()
+    # Verdicts differ on a few damaged frames: the 1.5.1 Huffman decoders insist on exact stream consumption
+    # (HufDecompress.cs:526-533, :1337-1343) where 1.5.5's fast loops only check the symbol count; and where 1.5.1's double-symbol
+    # decoder accepts a last code that runs past the stream start (HUF_decodeLastSymbolX2, :1022-1045) the last literal differs.
+    assert agree >= 170 and same_bytes >= both_ok - 5
 
 
 def test_streams_that_run_dry_match_libzstd():

@@ -278,30 +278,40 @@ class Decompressor:
             return False, 0
         return True, EnsureZstdSuccess(rv)
 
-    def UnwrapBatch(self, frames: Sequence, raise_on_error: bool = True):
+    def UnwrapBatch(self, frames: Sequence, raise_on_error: bool = True, max_decompressed_size: int = MAX_BYTE_ARRAY_LENGTH,
+                    capacity: Optional[int] = None):
         """Decompresses every element of ``frames`` as ``Unwrap`` would. Returns a list of bytes (or, with
-        ``raise_on_error=False``, of bytes / ZstdException per item)."""
+        ``raise_on_error=False``, of bytes / ZstdException per item).  ``max_decompressed_size`` is Unwrap's guard
+        (Decompressor.cs:47-59) applied per item: an item whose declared size exceeds it fails with dstSize_tooSmall and is
+        not staged, so one frame declaring a huge content size never poisons the batch.  ``capacity`` instead gives every item
+        exactly that many output bytes (what ``Unwrap(src, dest)`` with a caller buffer does), whatever its header declares."""
         self._ensure()
         srcs = [_as_u8(f) for f in frames]
         n = len(srcs)
         if n == 0:
             return []
-        caps = []
+        caps, oversize = [], []
         for s in srcs:
+            if capacity is not None:
+                caps.append(int(capacity)); oversize.append(False)
+                continue
             b = int(_lib.ZSTD_decompressBound(_ptr(s), s.size))
-            caps.append(0 if b >= CONTENTSIZE_ERROR else b)
+            b = 0 if b >= CONTENTSIZE_ERROR else b
+            oversize.append(b > max_decompressed_size)
+            caps.append(0 if oversize[-1] else b)
         offs = np.concatenate([[0], np.cumsum(caps)]).astype(np.int64)
         out = np.empty(max(int(offs[-1]), 1), dtype=np.uint8)
         sp = (ctypes.c_void_p * n)(*[_ptr(s) for s in srcs])
-        ss = (ctypes.c_size_t * n)(*[s.size for s in srcs])
+        ss = (ctypes.c_size_t * n)(*[0 if o else s.size for s, o in zip(srcs, oversize)])
         dp = (ctypes.c_void_p * n)(*[out.ctypes.data + int(o) for o in offs[:-1]])
         dc = (ctypes.c_size_t * n)(*caps)
         res = (ctypes.c_size_t * n)()
         EnsureZstdSuccess(_lib.ZSTDB200_decompressBatch(self._dctx, n, sp, ss, dp, dc, res))
         outs = []
         for i in range(n):
-            if is_error(res[i]):
-                exc = ZstdException(error_code(res[i]), _lib.ZSTD_getErrorName(res[i]).decode())
+            code = int(ZSTD_ErrorCode.dstSize_tooSmall) if oversize[i] else (error_code(res[i]) if is_error(res[i]) else 0)
+            if code:
+                exc = ZstdException(code, _lib.ZSTD_getErrorName((1 << 64) - code).decode())
                 if raise_on_error:
                     raise exc
                 outs.append(exc)

@@ -431,9 +431,26 @@ __global__ void dec_scan_kernel(DecPass p, const DecItemInit* init)
     it.srcOff = in.srcOff; it.dstOff = in.dstOff; it.srcSize = in.srcSize; it.dstCap = in.dstCap;
     it.srcPos = 0; it.outPos = 0; it.frameStart = 0; it.status = kStRunning; it.errCode = 0; it.inFrame = 0;
     it.moreThan1Frame = 0; it.checksumFlag = 0; it.hasFcs = 0; it.fcs = 0; it.litEntropy = 0; it.fseEntropy = 0;
-    it.blkType = kBlkNone; it.prefix = 0;
+    it.blkType = kBlkNone; it.prefix = 0; it.hufX2 = 0;
     uint32_t const blocks = count_item_blocks(p.src + in.srcOff, in.srcSize);
     atomicMax(&p.counters[3], blocks);
+}
+
+// HUF_selectDecoder (HufDecompress.cs:1688; algoTime :1471-1681 = {tableTime, decode256Time} of the single- and the double-symbol
+// decoder per compression-ratio bucket).  Which of the two the reference runs does not change the bytes of a valid stream, only the
+// verdict on some damaged ones (huf_x2_replay below).
+__device__ __constant__ uint16_t c_hufAlgoTime[16][4] = {
+    {0, 0, 1, 1}, {0, 0, 1, 1}, {150, 216, 381, 119}, {170, 205, 514, 112}, {177, 199, 539, 110}, {197, 194, 644, 107},
+    {221, 192, 735, 107}, {256, 189, 881, 106}, {359, 188, 1167, 109}, {582, 187, 1570, 114}, {688, 187, 1712, 122},
+    {825, 186, 1965, 136}, {976, 185, 2131, 150}, {1180, 186, 2070, 175}, {1377, 185, 1731, 202}, {1412, 185, 1695, 202}};
+__device__ uint32_t huf_select_decoder(uint32_t dstSize, uint32_t cSrcSize)
+{
+    uint32_t const Q = cSrcSize >= dstSize ? 15u : cSrcSize * 16u / dstSize;
+    uint32_t const D256 = dstSize >> 8;
+    uint32_t const t0 = c_hufAlgoTime[Q][0] + c_hufAlgoTime[Q][1] * D256;
+    uint32_t t1 = c_hufAlgoTime[Q][2] + c_hufAlgoTime[Q][3] * D256;
+    t1 += t1 >> 5;
+    return t1 < t0 ? 1u : 0u;
 }
 
 // =====================================================================================================
@@ -548,6 +565,7 @@ __global__ void __launch_bounds__(kSetupWarps * 32) dec_setup_kernel(DecPass p)
                     if (di[2]) {
                         it.rep[0] = di[7]; it.rep[1] = di[8]; it.rep[2] = di[9]; it.litEntropy = 1; it.fseEntropy = 1;
                         it.hufLog = di[3]; it.llLog = di[4]; it.ofLog = di[5]; it.mlLog = di[6];
+                        it.hufX2 = 1;                                                            // HUF_readDTableX2_wksp, ZstdDecompress.cs:1786
                         s_dict[warp] = 1;
                     }
                 }
@@ -598,6 +616,7 @@ __global__ void __launch_bounds__(kSetupWarps * 32) dec_setup_kernel(DecPass p)
                     hSize = huf_read_stats(sc, &nbSym, &tlog, hsrc, litCSize);
                     if (hSize == 0 || hSize >= litCSize) { setup_fail(it, kCorruptionDetected); break; }
                     it.hufLog = tlog; s_huf[warp][0] = 1; s_huf[warp][1] = nbSym; s_huf[warp][2] = tlog;
+                    it.hufX2 = single ? 0u : huf_select_decoder(litSize, litCSize);      // ZstdDecompressBlock.cs:212-216
                 }
                 uint32_t const cOff = lhSize + hSize, cLen = litCSize - hSize;
                 it.litType = kLitHuf; it.litSize = litSize;
@@ -800,6 +819,110 @@ __device__ __forceinline__ uint32_t lds8u(uint32_t saddr) { uint16_t v; asm("ld.
 
 __device__ __forceinline__ uint32_t lit_segment_stride(uint32_t litSize) { uint32_t const seg = (litSize + 3) / 4; return (seg + 15) & ~15u; }
 
+// ---- Cold path: the reference's verdict on a DAMAGED literal section when it runs the double-symbol decoder ----
+// On valid streams HUF_decompress4X2 yields the bytes of the single-symbol decoder, so the hot loop below never builds the
+// double-symbol table.  On damaged streams the verdict can differ: HUF_decodeLastSymbolX2 (HufDecompress.cs:1022) clamps
+// bitsConsumed when a two-symbol cell is used for the last symbol (a stream whose last code runs past its start is ACCEPTED), and
+// the interleaved main loop of HUF_decompress4X2_usingDTable_internal_body (:1148) stops on stream 4 only, so streams 1-3 can
+// overshoot their segment (:1322-1335).  When the hot loop finds a stream that is not consumed exactly and the table is of the
+// double-symbol type, one thread replays the reference's control flow here (BIT_DStream_t of Bitstream.cs:172-425, cells derived
+// from the single-symbol table: a cell holds two symbols when the second one fits the remaining dtLog - l1 bits, :789-886).
+struct X2Bits {
+    const uint8_t* s; uint32_t len; int32_t ptr; uint64_t c; uint32_t consumed;
+    __device__ uint64_t rd(int32_t at) const { uint64_t v = 0; for (int i = 7; i >= 0; i--) v = (v << 8) | ((uint32_t)(at + i) < len ? s[at + i] : 0u); return v; }
+    __device__ void init(const uint8_t* b, uint32_t n) {          // n >= 1 and b[n-1] != 0 were checked by the hot loop's reader
+        s = b; len = n;
+        uint32_t const hb = highbit32(b[n - 1]);
+        if (n >= 8) { ptr = (int32_t)n - 8; c = rd(ptr); consumed = 8 - hb; }
+        else { ptr = 0; c = rd(0); consumed = 8 - hb + (8 - n) * 8; }
+    }
+    __device__ uint32_t look(uint32_t nb) const { return (uint32_t)((c << (consumed & 63)) >> (64 - nb)); }
+    __device__ int reloadFast() { if (ptr < 8) return 3; ptr -= (int32_t)(consumed >> 3); consumed &= 7; c = rd(ptr); return 0; }
+    __device__ int reload() {                                     // 0 unfinished, 1 endOfBuffer, 2 completed, 3 overflow
+        if (consumed > 64) return 3;
+        if (ptr >= 8) return reloadFast();
+        if (ptr == 0) return consumed < 64 ? 1 : 2;
+        uint32_t nb = consumed >> 3; int res = 0;
+        if ((int32_t)nb > ptr) { nb = (uint32_t)ptr; res = 1; }
+        ptr -= (int32_t)nb; consumed -= nb * 8; c = rd(ptr);
+        return res;
+    }
+    __device__ bool finished() const { return ptr == 0 && consumed == 64; }
+};
+struct X2Table {
+    const uint16_t* tab; uint32_t nativeLog, dtLog, minBits;
+    // cell of index val: returns length (1 or 2); sym = s1 | s2 << 8, nb = bits consumed
+    __device__ uint32_t cell(uint32_t val, uint32_t& sym, uint32_t& nb) const {
+        uint32_t const e1 = tab[val >> (dtLog - nativeLog)], l1 = e1 & 0xFF;
+        sym = e1 >> 8; nb = l1;
+        if (dtLog - l1 >= minBits) {
+            uint32_t const e2 = tab[((val << l1) & ((1u << dtLog) - 1u)) >> (dtLog - nativeLog)], l2 = e2 & 0xFF;
+            if (l2 <= dtLog - l1) { sym |= (e2 >> 8) << 8; nb = l1 + l2; return 2; }
+        }
+        return 1;
+    }
+};
+struct X2Out { uint8_t* p; uint32_t pos, end; };                   // pos may overshoot end inside the main loop; bytes beyond end are dropped
+__device__ void x2_symbol(X2Out& o, X2Bits& b, const X2Table& t)   // HUF_decodeSymbolX2 (:1012)
+{
+    uint32_t sym, nb; uint32_t const n = t.cell(b.look(t.dtLog), sym, nb);
+    if (o.pos < o.end) o.p[o.pos] = (uint8_t)sym;
+    if (n == 2 && o.pos + 1 < o.end) o.p[o.pos + 1] = (uint8_t)(sym >> 8);
+    b.consumed += nb; o.pos += n;
+}
+__device__ void x2_stream(X2Out& o, X2Bits& b, const X2Table& t)   // HUF_decodeStreamX2 (:1047)
+{
+    if (o.end - o.pos >= 8) {
+        if (t.dtLog <= 11) { while (b.reload() == 0 && o.pos + 9 < o.end) for (int k = 0; k < 5; k++) x2_symbol(o, b, t); }
+        else { while (b.reload() == 0 && o.pos + 7 < o.end) for (int k = 0; k < 4; k++) x2_symbol(o, b, t); }
+    } else b.reload();
+    if (o.end - o.pos >= 2) {
+        while (b.reload() == 0 && o.pos + 2 <= o.end) x2_symbol(o, b, t);
+        while (o.pos + 2 <= o.end) x2_symbol(o, b, t);
+    }
+    if (o.pos < o.end) {                                           // HUF_decodeLastSymbolX2 (:1022)
+        uint32_t sym, nb; uint32_t const n = t.cell(b.look(t.dtLog), sym, nb);
+        o.p[o.pos++] = (uint8_t)sym;
+        if (n == 1) b.consumed += nb;
+        else if (b.consumed < 64) { b.consumed += nb; if (b.consumed > 64) b.consumed = 64; }
+    }
+}
+// true = the reference accepts the literal section (and the literal buffer now holds what it decodes)
+__device__ __noinline__ bool huf_x2_replay(const DecPass& p, uint32_t item, const DecItem& it)
+{
+    X2Table t; t.tab = p.hufTable + (size_t)item * kHufTableEntries; t.nativeLog = it.hufLog; t.dtLog = it.hufLog <= 11 ? 11u : 12u;
+    t.minBits = t.tab[(1u << t.nativeLog) - 1u] & 0xFF;           // the last cells belong to the heaviest symbol = the shortest code
+    const uint8_t* const src = p.src + it.srcOff;
+    uint8_t* const lit = p.litBuf + (size_t)item * kLitStride;
+    uint32_t const litSize = it.litSize;
+    X2Bits b[4]; X2Out o[4];
+    if (it.nStreams == 1) {
+        b[0].init(src + it.streamOff[0], it.streamLen[0]);
+        o[0].p = lit; o[0].pos = 0; o[0].end = litSize;
+        x2_stream(o[0], b[0], t);
+        return b[0].finished();
+    }
+    uint32_t const seg = (litSize + 3) / 4, stride = lit_segment_stride(litSize);
+    for (int j = 0; j < 4; j++) {
+        b[j].init(src + it.streamOff[j], it.streamLen[j]);
+        o[j].p = lit + j * stride; o[j].pos = 0; o[j].end = j < 3 ? seg : litSize - 3 * seg;
+    }
+    if (o[3].end >= 8) {
+        uint32_t endSignal = 1;
+        while (endSignal && o[3].pos + 7 < o[3].end) {             // op4 < olimit
+            for (int k = 0; k < 4; k++) x2_symbol(o[0], b[0], t);
+            for (int k = 0; k < 4; k++) x2_symbol(o[1], b[1], t);
+            endSignal &= b[0].reloadFast() == 0; endSignal &= b[1].reloadFast() == 0;
+            for (int k = 0; k < 4; k++) x2_symbol(o[2], b[2], t);
+            for (int k = 0; k < 4; k++) x2_symbol(o[3], b[3], t);
+            endSignal &= b[2].reloadFast() == 0; endSignal &= b[3].reloadFast() == 0;
+        }
+    }
+    if (o[0].pos > o[0].end || o[1].pos > o[1].end || o[2].pos > o[2].end) return false;      // op1 > opStart2 ... (:1322-1335)
+    for (int j = 0; j < 4; j++) x2_stream(o[j], b[j], t);
+    return b[0].finished() && b[1].finished() && b[2].finished() && b[3].finished();
+}
+
 __global__ void __launch_bounds__(kHufThreads) dec_huf_kernel(DecPass p)
 {
     extern __shared__ __align__(256) uint8_t s_huf_raw[];    // [kHufThreads] rings of 128 B, then per item: u8 sym[2048] | u8 len[1024]
@@ -822,14 +945,15 @@ __global__ void __launch_bounds__(kHufThreads) dec_huf_kernel(DecPass p)
             len[u] = (uint8_t)(w & 0xFF);
         }
     }
+    __shared__ uint32_t s_inexact[kHufItemsPerCta];
+    if (threadIdx.x < kHufItemsPerCta) s_inexact[threadIdx.x] = 0;
     __syncthreads();
     uint32_t const slot = threadIdx.x >> 2, stream = threadIdx.x & 3;
-    if (slot >= nHere) return;
-    uint32_t const item = p.hufList[first + slot];
+    uint32_t const item = p.hufList[first + min(slot, nHere - 1)];
     DecItem& it = p.items[item];
-    if (it.status != kStRunning) return;
     uint32_t const nStreams = it.nStreams;
-    if (stream >= nStreams) return;
+    bool const active = slot < nHere && it.status == kStRunning && stream < nStreams;
+    if (active) {
     uint32_t const litSize = it.litSize, log = it.hufLog;
     uint32_t const seg = (litSize + 3) / 4;
     uint32_t count, outOff;
@@ -887,7 +1011,14 @@ __global__ void __launch_bounds__(kHufThreads) dec_huf_kernel(DecPass p)
         }
         ok = ((int32_t)G == gz) && (i == count);      // BIT_endOfDStream: the stream must be consumed exactly (:526-533)
     }
-    if (!ok) { it.errCode = kCorruptionDetected; it.status = kStError; }
+    if (!ok) s_inexact[slot] = G != 0 ? 1u : 2u;      // 2: BIT_initDStream itself fails (no end mark), whatever the decoder
+    }
+    __syncthreads();
+    if (stream == 0 && slot < nHere && it.status == kStRunning && s_inexact[slot]) {
+        // single-symbol decoder (HufDecompress.cs:526-533): corruption.  Double-symbol decoder: replay its control flow.
+        bool const accept = s_inexact[slot] == 1 && it.hufX2 && huf_x2_replay(p, item, it);
+        if (!accept) { it.errCode = kCorruptionDetected; it.status = kStError; }
+    }
 }
 
 // =====================================================================================================
@@ -1370,8 +1501,12 @@ __global__ void __launch_bounds__(kExecWarps * 32) dec_exec_kernel(DecPass p)
             uint32_t const farFast = farN <= 16 ? farN : 0u;             // longer far parts are copied in the rounds below
             {
                 uint32_t const d0 = fill + oStart;
-                uint32_t longMask = __ballot_sync(FULL, mine && ll > kExecLong);
-                uint32_t const myLL = (mine && ll <= kExecLong) ? ll : 0u;
+                // the per-lane path below handles a run that crosses at most ONE segment boundary: with four streams over fewer than
+                // 4 * kExecLong literals (legal, though the reference's encoder never emits it) a run can cross two, so those go the
+                // whole-warp way, which maps every byte through L.addr()
+                bool const llLong = ll > kExecLong || (ll && L.seg <= kExecLong);
+                uint32_t longMask = __ballot_sync(FULL, mine && llLong);
+                uint32_t const myLL = (mine && !llLong) ? ll : 0u;
                 if (L.type == kLitRle) {
                     Raw16 const fm = lane_ld16(dst + tileBase + srcRel, farFast);
                     for (uint32_t k = 0; k < myLL; k++) tile[d0 + k] = (uint8_t)L.rle;
@@ -1387,7 +1522,7 @@ __global__ void __launch_bounds__(kExecWarps * 32) dec_exec_kernel(DecPass p)
                     if (l16) lane_st16(tile + d0, lt, l16);
                     if (farFast) lane_st16(tile + mDst, fm, farFast);
                     if (n1 > 16) lane_copy_g2t(tile, d0 + 16, L.base + a + 16, n1 - 16);
-                    if (n1 < myLL) lane_copy_g2t(tile, d0 + n1, L.base + a + n1 + L.pad, myLL - n1);   // a run crosses at most one boundary (kExecLong < segment)
+                    if (n1 < myLL) lane_copy_g2t(tile, d0 + n1, L.base + a + n1 + L.pad, myLL - n1);   // at most one boundary: llLong above
                 }
                 while (longMask) {
                     uint32_t const j = (uint32_t)__ffs((int)longMask) - 1u; longMask &= longMask - 1;

@@ -48,7 +48,8 @@ struct __align__(16) DecItem {
     uint32_t moreThan1Frame;
     uint32_t checksumFlag;
     uint32_t hasFcs;
-    uint32_t _pad0;
+    uint32_t hufX2;         // the current Huffman table is the reference's double-symbol form (HUF_selectDecoder / dictionary): only the
+                            // verdict on damaged streams depends on it (dec_huf_kernel, huf_x2_replay)
     uint64_t fcs;
     uint32_t rep[3];
     uint32_t litEntropy;    // a Huffman table from an earlier block of this frame is available
