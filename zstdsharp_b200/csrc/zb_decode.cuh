@@ -111,16 +111,16 @@ __host__ __device__ inline uint32_t count_item_blocks(const uint8_t* src, uint32
         if (rem < 5) break;
         uint32_t const magic = le32(src + pos);
         if ((magic & kMagicSkippableMask) == kMagicSkippableStart) {
-            if (rem < 8) break;
+            if (rem < 8) { blocks++; break; }
             uint32_t const sz = le32(src + pos + 4);
-            if ((uint64_t)sz + 8 > rem) break;
+            if ((uint64_t)sz + 8 > rem) { blocks++; break; }
             pos += sz + 8; continue;
         }
-        if (magic != kMagic) break;
+        if (magic != kMagic) { blocks++; break; }                  // one more wave: dec_setup diagnoses what the walk stops at
         uint32_t const fhd = src[pos + 4];
         uint32_t const dictID = fhd & 3, single = (fhd >> 5) & 1, fcsId = fhd >> 6;
         uint32_t const hs = 5 + !single + (dictID == 3 ? 4 : dictID) + (fcsId == 0 ? 0 : (1u << fcsId)) + (single && !fcsId);
-        if (rem < hs + 3) break;
+        if (rem < hs + 3) { blocks++; break; }
         pos += hs;
         bool bad = false;
         for (;;) {
@@ -134,7 +134,7 @@ __host__ __device__ inline uint32_t count_item_blocks(const uint8_t* src, uint32
             pos += csz;
             if (h & 1) break;
         }
-        if (bad) break;
+        if (bad) { blocks++; break; }
         if (fhd & 4) { if (size - pos < 4) break; pos += 4; }
     }
     return blocks ? blocks : 1;
