@@ -2,7 +2,8 @@
 """Benchmark of the hot path: batch decompress (and level-1 compress) of independent 128 KiB zstd frames.
 
   python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path (one rank per GPU under torchrun)
-  python bench.py --impl reference --steps K --warmup W    # the reference's CPU algorithm (oracle port) on the host cores
+  python bench.py --impl reference --steps K --warmup W    # the reference's own native zstd 1.5.1 (oracle/_ref: its libzstd.dll
+                                                           # through the PE mapper), else the oracle port, on all host cores
 
 One JSON line on stdout (rank 0).  `value` = decompress GB/s of uncompressed bytes, whole job, frames resident in HBM
 (configs[1] of BASELINE.json: 1 GiB of 128 KiB level-1 frames per GPU, weak scaling); `e2e` = the same through the
@@ -181,31 +182,99 @@ def native_libzstd_decode_rate(frames, threads):
     return total / (time.perf_counter() - t0) / 1e9
 
 
+def ref_dll():
+    """The reference's own native library (src/Zstd.Extern/libzstd.dll, zstd 1.5.1) through oracle/_ref, or None.  ZstdSharp's
+    managed code is a translation of exactly this code; the reference's README.md:44-58 measures it 1.41x slower than this
+    binary, so timing the binary is the conservative stand-in for "ZstdSharp on .NET" (which this image cannot run)."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    try:
+        from _oracle import refdll, refdll_available
+        if refdll_available():
+            return refdll()
+    except Exception as e:                                   # noqa: BLE001
+        log("bench.py: oracle/_ref unavailable:", e)
+    return None
+
+
+class DllBatch:
+    """n frames decoded (or chunks compressed) by the DLL on `threads` host threads, one context per thread
+    (ZREF_decompressBatchMT / ZREF_compressBatchMT in oracle/ref_pe/peload.c; contexts as in ZstdNetTests.cs:498-522)."""
+
+    def __init__(self, r, srcs, dst_cap, threads):
+        self.r, self.n, self.threads = r, len(srcs), threads
+        self.srcs = srcs
+        vp, st = ctypes.c_void_p, ctypes.c_size_t
+        self.out = np.empty(self.n * dst_cap, dtype=np.uint8)
+        self.out[::4096] = 0                                  # touch the pages outside the timed region
+        self.sp = (vp * self.n)(*[s.ctypes.data for s in srcs])
+        self.ss = (st * self.n)(*[s.size for s in srcs])
+        self.dp = (vp * self.n)(*[self.out.ctypes.data + i * dst_cap for i in range(self.n)])
+        self.dc = (st * self.n)(*([dst_cap] * self.n))
+        self.res = (st * self.n)()
+        self.cap = dst_cap
+
+    def decompress(self):
+        self.r.lib.ZREF_decompressBatchMT(self.n, self.sp, self.ss, self.dp, self.dc, self.res, self.threads)
+
+    def compress(self, level):
+        self.r.lib.ZREF_compressBatchMT(self.n, self.sp, self.ss, self.dp, self.dc, self.res, level, self.threads)
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    o, chunks, frames, threads = cpu_frames(1, UNIQUE_FRAMES, "text")
-    for _ in range(args.warmup):
-        cpu_decode_pass(o, frames, threads)
-    t0 = time.perf_counter()
-    total = 0
-    for _ in range(args.steps):
-        b, _ = cpu_decode_pass(o, frames, threads)
-        total += b
-    dt = time.perf_counter() - t0
-    val = total / dt / 1e9
-    cb, ct = cpu_compress_pass(o, [c for c in dg.silesia_mix(128 * FRAME).reshape(-1, FRAME)], threads, 1)
-    sample = f"{UNIQUE_FRAMES} text-like 128 KiB level-1 frames ({UNIQUE_FRAMES * FRAME >> 20} MiB) per step, {threads} threads"
+    threads = os.cpu_count() or 1
+    r = ref_dll()
+    nframes = args.frames
+    uniq = min(UNIQUE_FRAMES, nframes)
+    o, chunks, frames, _ = cpu_frames(1, uniq, "text")      # frames: the oracle's = the DLL's bytes (tests/test_reference_pin.py)
+    port_b, port_t = cpu_decode_pass(o, frames[:256], threads, seconds_min=1.0)
+    port = port_b / port_t / 1e9
+    if r is None:                                            # no oracle/_ref on this box: the port is the arm
+        for _ in range(args.warmup):
+            cpu_decode_pass(o, frames, threads)
+        t0 = time.perf_counter(); total = 0
+        for _ in range(args.steps):
+            b, _ = cpu_decode_pass(o, frames, threads); total += b
+        dt = time.perf_counter() - t0
+        val, kind = total / dt / 1e9, "port"
+        sample = f"{uniq} text-like 128 KiB level-1 frames ({uniq * FRAME >> 20} MiB) per step, {threads} threads, oracle port of the C#"
+        comp_val = None
+    else:
+        srcs = [np.frombuffer(frames[i % uniq], dtype=np.uint8) for i in range(nframes)]
+        job = DllBatch(r, srcs, FRAME, threads)
+        for _ in range(max(1, args.warmup)):
+            job.decompress()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            job.decompress()
+        dt = time.perf_counter() - t0
+        assert all(x == FRAME for x in job.res), "the reference DLL failed to decode a frame"
+        want = np.concatenate(chunks).reshape(uniq, FRAME)
+        assert np.array_equal(job.out.reshape(nframes, FRAME)[:uniq], want), "reference DLL output differs from the corpus"
+        val, kind = nframes * FRAME * args.steps / dt / 1e9, "reference"
+        sample = (f"the whole configs[1] batch every step: {nframes} text-like 128 KiB level-1 frames ({nframes * FRAME >> 20} MiB out) decoded by the "
+                  f"reference's own libzstd.dll (zstd 1.5.1, oracle/_ref) on {threads} host threads, one ZSTD_DCtx per thread")
+        del job
+        sil = dg.silesia_mix(uniq * FRAME).reshape(uniq, FRAME)
+        cj = DllBatch(r, [sil[i % uniq] for i in range(nframes)], r.lib.ZREF_compressBound(FRAME), threads)
+        cj.compress(1)
+        t1 = time.perf_counter(); cj.compress(1); ct = time.perf_counter() - t1
+        comp_val = nframes * FRAME / ct / 1e9
+        del cj
     line = {
         "impl": "reference", "metric": METRIC, "value": round(val, 4), "unit": "GB/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": round(1e3 * dt / args.steps, 3), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-        "config": {"workload": "batch decompress of 128 KiB level-1 frames (configs[1]), bounded CPU sample", "frames_per_step": UNIQUE_FRAMES,
-                   "frame_bytes": FRAME, "note": "reference algorithm = C port of ZstdSharp's zstd 1.5.1 code (oracle/); .NET is not available in this image"},
-        "cpu_baseline": {"value": round(val, 4), "unit": "GB/s", "cores": threads, "kind": "port", "sample": sample},
-        "compress_l1": {"value": round(cb / ct / 1e9, 4), "unit": "GB/s", "sample": "128 Silesia-mix-like chunks, level 1"},
-        "native_libzstd_1_5_5_decompress_GBps": native_libzstd_decode_rate(frames, threads),
+        "config": {"workload": "batch decompress 1 GiB of 128 KiB level-1 frames, bit-exact (BASELINE.json configs[1])", "frames_per_gpu": nframes,
+                   "frame_bytes": FRAME, "corpus": f"text_like seed 0x{dg.SEED_TEXT:X}: {uniq} unique frames tiled to {nframes}",
+                   "note": "reference arm = the reference's own native zstd 1.5.1 binary (src/Zstd.Extern/libzstd.dll through oracle/ref_pe); ZstdSharp's "
+                           "managed translation of this code cannot run here (no .NET) and is 1.41x slower by the reference's README.md:44-58"},
+        "cpu_baseline": {"value": round(val, 4), "unit": "GB/s", "cores": threads, "kind": kind, "sample": sample},
+        "oracle_port_decompress_GBps": round(port, 4),
+        "compress_l1": None if comp_val is None else {"value": round(comp_val, 4), "unit": "GB/s", "sample": f"{nframes} Silesia-mix-like 128 KiB chunks, level 1, same DLL and threads"},
+        "native_libzstd_1_5_5_decompress_GBps": native_libzstd_decode_rate(frames[:256], threads),
         "e2e": {"value": round(val, 4), "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
@@ -230,6 +299,8 @@ def run_b200(args):
     if lib.ZSTDB200_deviceCount() == 0:
         raise SystemExit("bench.py: no CUDA device; zstdsharp_b200 has no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
+    # one process per GPU: keep this rank's threads and the pinned buffers it allocates on the CPUs next to its GPU's PCIe root
+    numa_rc = lib.ZSTDB200_bindThreadToDevice(local) if os.environ.get("ZSTDB200_NUMA_BIND", "1") != "0" else None
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
@@ -255,7 +326,7 @@ def run_b200(args):
     nframes = args.frames                                    # per GPU (weak scaling)
     # host scatter: the global frame list (world * nframes frames, index g -> unique frame g % UNIQUE) is cut into
     # contiguous ranges balanced by byte weight; this rank materialises its own range only.
-    uniq = min(UNIQUE_FRAMES, nframes)
+    uniq = min(args.unique, nframes)
     lo, hi = shard_bounds([FRAME] * (world * nframes), world)[rank]
     my_ids = np.arange(lo, hi) % uniq
     n = len(my_ids)
@@ -297,24 +368,44 @@ def run_b200(args):
 
     # ------------------------------------------------------------------ corpus + compressed frames (made by the GPU encoder)
     t_prep = time.perf_counter()
-    text = dg.text_like(uniq * FRAME)
-    sil = dg.silesia_mix(uniq * FRAME)
+    def corpus(fn, seed0):       # blocks of 512 frames with different seeds (--unique above 512: no tiling of the same 64 MiB)
+        parts = [fn(min(512, uniq - k) * FRAME, seed0 + k) if k else fn(min(512, uniq) * FRAME) for k in range(0, uniq, 512)]
+        return parts[0] if len(parts) == 1 else np.concatenate(parts)
+    text = corpus(dg.text_like, dg.SEED_TEXT)
+    sil = corpus(dg.silesia_mix, dg.SEED_SILESIA)
     d_text_u = torch.from_numpy(text).cuda()
     d_sil_u = torch.from_numpy(sil).cuda()
     bound = comp.GetCompressBound(FRAME)
     slot = (bound + 15) & ~15
 
-    def compress_unique(d_u):
-        d_out = torch.empty(uniq * slot, dtype=torch.uint8, device="cuda")
-        so = (u64 * uniq)(*[i * FRAME for i in range(uniq)]); ss = (st * uniq)(*([FRAME] * uniq))
-        do = (u64 * uniq)(*[i * slot for i in range(uniq)]); dc = (st * uniq)(*([bound] * uniq)); res = (st * uniq)()
-        dev_call(lib.ZSTDB200_compressBatchDevice, comp, uniq, 1, d_u.data_ptr(), so, ss, d_out.data_ptr(), do, dc, res)
+    def compress_unique(d_u, level=1):
+        m = d_u.numel() // FRAME
+        d_out = torch.empty(m * slot, dtype=torch.uint8, device="cuda")
+        so = (u64 * m)(*[i * FRAME for i in range(m)]); ss = (st * m)(*([FRAME] * m))
+        do = (u64 * m)(*[i * slot for i in range(m)]); dc = (st * m)(*([bound] * m)); res = (st * m)()
+        dev_call(lib.ZSTDB200_compressBatchDevice, comp, m, level, d_u.data_ptr(), so, ss, d_out.data_ptr(), do, dc, res)
         sizes = np.array(list(res), dtype=np.int64)
         assert (sizes > 0).all() and (sizes <= bound).all(), "GPU compressor reported an error"
         host = d_out.cpu().numpy()
-        return [host[i * slot:i * slot + sizes[i]].copy() for i in range(uniq)]
+        return [host[i * slot:i * slot + sizes[i]].copy() for i in range(m)]
 
     frames_u = compress_unique(d_text_u)
+    # parity gate outside every timed region (rank 0): the GPU encoder's frames of the bench corpus are the oracle's frames --
+    # byte for byte, levels 1 and 3, both corpora (the oracle is held to the reference's libzstd.dll by tests/test_reference_pin.py)
+    parity = None
+    if rank == 0 and not args.skip_cpu:
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        from _oracle import oracle as _oracle_fn
+        _o = _oracle_fn()
+        m_chk = min(uniq, 512)
+        with ThreadPoolExecutor(os.cpu_count() or 4) as ex:
+            for name, host_u, d_u in (("text", text, d_text_u), ("silesia", sil, d_sil_u)):
+                for level in (1, 3):
+                    got = frames_u if (name == "text" and level == 1) else compress_unique(d_u[:m_chk * FRAME], level)
+                    want = list(ex.map(lambda i: _o.compress(host_u[i * FRAME:(i + 1) * FRAME], level), range(m_chk)))
+                    bad = [i for i in range(m_chk) if got[i].tobytes() != want[i]]
+                    assert not bad, f"GPU level-{level} frames of the {name} corpus differ from the oracle at {bad[:5]}"
+        parity = {"frames_checked": 4 * m_chk, "against": "oracle (C restatement of the reference, pinned to its libzstd.dll 1.5.1)", "levels": [1, 3], "mismatches": 0}
     csz_u = np.array([f.size for f in frames_u], dtype=np.int64)
     # decode batch for this rank: compressed frames back to back (contiguous => one DMA in the e2e path)
     csz = csz_u[my_ids]
@@ -385,12 +476,81 @@ def run_b200(args):
     e2e_steps = max(1, min(args.steps, 5))
     _, e2e_wall_ms, _, e2e_slots = timed_steps(e2e_dec_step, min(args.warmup, 2), e2e_steps)
     assert all(r == FRAME for r in res)
-    assert np.array_equal(h_out.numpy()[:FRAME], text[int(my_ids[0]) * FRAME:(int(my_ids[0]) + 1) * FRAME])
+    want_out = text.reshape(uniq, FRAME)[my_ids]
+    assert np.array_equal(h_out.numpy().reshape(n, FRAME), want_out), "e2e output differs from the source corpus"      # the whole batch
     e2e_gbps = total_u * e2e_steps / (e2e_wall_ms * 1e-3) / 1e9
     e2e = {"value": round(e2e_gbps, 3), "unit": "GB/s", "h2d_bytes_per_step": int(total_c), "d2h_bytes_per_step": int(total_u),
            "ms_per_step": round(e2e_wall_ms / e2e_steps, 3), "api": "ZSTDB200_decompressBatch (host pointers, pinned, contiguous)",
            "phase_ms": {"h2d": round(float(e2e_slots[0]), 3), "kernels": round(float(e2e_slots[1]), 3), "d2h": round(float(e2e_slots[2]), 3)}}
+    # ---- what the copies alone cost (untimed probe, all ranks at once): the same pinned buffers, H2D of the compressed batch and
+    # D2H of the regenerated bytes issued together on two streams (PCIe is full duplex), no kernels.  e2e cannot beat this.
+    s_h2d, s_d2h = torch.cuda.Stream(), torch.cuda.Stream()
+    best = None
+    for _ in range(3):
+        barrier()
+        t0 = time.perf_counter()
+        with torch.cuda.stream(s_h2d):
+            d_comp.copy_(h_comp, non_blocking=True)
+        with torch.cuda.stream(s_d2h):
+            h_out.copy_(d_out, non_blocking=True)
+        s_h2d.synchronize(); s_d2h.synchronize()
+        dt = max_over_ranks((time.perf_counter() - t0) * 1e3)
+        best = dt if best is None else min(best, dt)
+    one_way = None
+    for _ in range(2):
+        barrier()
+        t0 = time.perf_counter()
+        with torch.cuda.stream(s_d2h):
+            h_out.copy_(d_out, non_blocking=True)
+        s_d2h.synchronize()
+        dt = max_over_ranks((time.perf_counter() - t0) * 1e3)
+        one_way = dt if one_way is None else min(one_way, dt)
+    e2e["copy_ceiling_gbs"] = round(total_u / (best * 1e-3) / 1e9, 3)
+    e2e["copy_ceiling_ms"] = round(best, 3)
+    e2e["d2h_only_ms"] = round(one_way, 3)
+    e2e["frac_of_ceiling"] = round(e2e_gbps / (total_u / (best * 1e-3) / 1e9), 4)
+    e2e["numa_bind_rc"] = numa_rc
     del h_out
+
+    # ---- the drop-in callers' memory: pageable, one separately allocated array per frame (Decompressor.Unwrap: `fixed` over a
+    # managed byte[] is GC pinning, not page locking; every Unwrap returns a `new byte[]`)
+    pg_src = [np.array(frames_u[int(i)]) for i in my_ids]
+    pg_dst = [np.empty(FRAME, dtype=np.uint8) for _ in range(n)]
+    for a in pg_dst:
+        a[::4096] = 0
+    psp = (vp * n)(*[a.ctypes.data for a in pg_src]); pdp = (vp * n)(*[a.ctypes.data for a in pg_dst])
+
+    def e2e_pageable_step():
+        dev_call(lib.ZSTDB200_decompressBatch, dec, n, psp, ss, pdp, dc, res)
+        return dec.launch_count(), np.array(dec.timings())
+    _, pg_wall_ms, _, _ = timed_steps(e2e_pageable_step, 1, 2)
+    assert all(r == FRAME for r in res)
+    for i in range(0, n, max(1, n // 61)):
+        assert np.array_equal(pg_dst[i], want_out[i]), "pageable e2e output differs"
+    e2e_pageable = {"value": round(total_u * 2 / (pg_wall_ms * 1e-3) / 1e9, 3), "unit": "GB/s", "ms_per_step": round(pg_wall_ms / 2, 3),
+                    "buffers": f"{n} separately allocated pageable arrays in, {n} out (numpy malloc), staged through the library's pinned ring by host threads",
+                    "frac_of_pinned": round((total_u * 2 / (pg_wall_ms * 1e-3) / 1e9) / e2e_gbps, 4)}
+    del pg_dst, pg_src
+
+    # ---- single-call latency of the zstd-named entry points on ONE 128 KiB frame (median), pageable buffers
+    single = None
+    if rank == 0:
+        f0 = np.array(frames_u[0]); o0 = np.empty(FRAME, dtype=np.uint8); c0 = np.empty(bound, dtype=np.uint8)
+        chunk0 = np.ascontiguousarray(text[:FRAME])
+        lat_d, lat_c = [], []
+        for k in range(60):
+            t0 = time.perf_counter()
+            r1 = lib.ZSTD_decompressDCtx(dec.handle, o0.ctypes.data, FRAME, f0.ctypes.data, f0.size)
+            lat_d.append(time.perf_counter() - t0)
+            assert r1 == FRAME
+        for k in range(30):
+            t0 = time.perf_counter()
+            r2 = lib.ZSTD_compressCCtx(comp.handle, c0.ctypes.data, bound, chunk0.ctypes.data, FRAME, 1)
+            lat_c.append(time.perf_counter() - t0)
+            assert r2 == f0.size
+        assert np.array_equal(o0, chunk0) and np.array_equal(c0[:r2], f0)
+        single = {"ZSTD_decompressDCtx_ms": round(1e3 * float(np.median(lat_d[5:])), 3), "ZSTD_compressCCtx_level1_ms": round(1e3 * float(np.median(lat_c[3:])), 3),
+                  "note": "one 128 KiB text-like frame per call, host to host; a single frame is a serial chain on the GPU (one lane per bit stream)"}
 
     # ------------------------------------------------------------------ level-1 compress (configs[2])
     compress = None
@@ -464,17 +624,67 @@ def run_b200(args):
             "decompress": {"value": round(total_u * 3 / (d3_dev_ms * 1e-3) / 1e9, 3), "unit": "GB/s", "ms_per_step": round(d3_dev_ms / 3, 3)},
             "ratio": round(n * FRAME * world / c3_total_c, 4)}
 
+    # ------------------------------------------------------------------ other decode workloads of BASELINE.json (device-resident)
+    workloads = None
+    if not args.skip_workloads:
+        workloads = {}
+        wu = min(uniq, 512)
+        for name in ("silesia", "literal_mix", "literal_heavy", "incompressible"):
+            host_u = sil[:wu * FRAME] if name == "silesia" else dg.WORKLOADS[name](wu * FRAME)
+            fr = compress_unique(torch.from_numpy(host_u).cuda(), 1)
+            wsz_u = np.array([f.size for f in fr], dtype=np.int64)
+            ids = np.arange(n) % wu
+            wsz = wsz_u[ids]; woff = np.concatenate([[0], np.cumsum(wsz)[:-1]]).astype(np.int64)
+            ub = np.concatenate(fr)
+            blob = np.concatenate([ub] * (n // wu) + ([np.concatenate(fr[:n % wu])] if n % wu else []))
+            d_w = torch.from_numpy(np.concatenate([blob, np.zeros(64, dtype=np.uint8)])).cuda()
+            wso = (u64 * n)(*woff.tolist()); wss = (st * n)(*wsz.tolist())
+
+            def w_step():
+                dev_call(lib.ZSTDB200_decompressBatchDevice, dec, n, d_w.data_ptr(), wso, wss, d_out.data_ptr(), do, dc, res)
+                return dec.launch_count(), np.array(dec.timings())
+            w_ms, _, _, w_slots = timed_steps(w_step, 1, 3)
+            assert all(r == FRAME for r in res)
+            refw = torch.from_numpy(host_u).cuda().view(wu, FRAME)
+            assert torch.equal(d_out.view(n, FRAME)[:wu], refw) and torch.equal(d_out.view(n, FRAME)[n - wu:], refw[torch.from_numpy((np.arange(n - wu, n) % wu)).cuda()])
+            wc = float(wsz.sum())
+            workloads[name] = {"decompress_GBps": round(total_u * 3 / (w_ms * 1e-3) / 1e9, 2), "ms_per_step": round(w_ms / 3, 3), "ratio": round(n * FRAME / wc, 3),
+                               "hbm_algorithmic_GBps_per_gpu": round((n * FRAME + wc) * 3 / (w_ms * 1e-3) / 1e9 / world, 1),
+                               "kernel_ms": {names[k]: round(float(w_slots[k]), 3) for k in names}}
+            del d_w, refw
+        workloads["note"] = "8192 x 128 KiB level-1 frames per GPU made by the GPU encoder from zstdsharp_b200.datagen workloads; incompressible = raw blocks (copy: 2 x bytes of HBM traffic)"
+
     # ------------------------------------------------------------------ CPU baseline (rank 0, N == 1 only)
     cpu = None
     if rank == 0 and world == 1 and not args.skip_cpu:
         o, chunks, frames, threads = cpu_frames(1, 256, "text")
         cpu_decode_pass(o, frames, threads)
-        b, t = cpu_decode_pass(o, frames, threads, seconds_min=2.0)
-        cpu = {"value": round(b / t / 1e9, 4), "unit": "GB/s", "cores": threads, "kind": "port",
-               "sample": f"256 text-like 128 KiB level-1 frames decoded repeatedly for {t:.1f} s on {threads} threads (oracle port of the reference's C# code)",
-               "native_libzstd_1_5_5_GBps": native_libzstd_decode_rate(frames, threads)}
-        cb, ct = cpu_compress_pass(o, [c for c in dg.silesia_mix(128 * FRAME).reshape(-1, FRAME)], threads, 1)
-        cpu["compress_l1_GBps"] = round(cb / ct / 1e9, 4)
+        b, t = cpu_decode_pass(o, frames, threads, seconds_min=1.0)
+        port_rate = b / t / 1e9
+        r = ref_dll()
+        if r is not None:
+            srcs = [np.frombuffer(frames[i % 256], dtype=np.uint8) for i in range(2048)]
+            job = DllBatch(r, srcs, FRAME, threads)
+            job.decompress()
+            t0 = time.perf_counter(); reps = 0
+            while time.perf_counter() - t0 < 2.0:
+                job.decompress(); reps += 1
+            t = time.perf_counter() - t0
+            assert all(x == FRAME for x in job.res)
+            cpu = {"value": round(2048 * FRAME * reps / t / 1e9, 4), "unit": "GB/s", "cores": threads, "kind": "reference",
+                   "sample": f"2048 text-like 128 KiB level-1 frames (256 MiB out) decoded {reps}x in {t:.1f} s by the reference's own libzstd.dll (zstd 1.5.1, oracle/_ref) on {threads} threads",
+                   "oracle_port_GBps": round(port_rate, 4)}
+            sil_c = dg.silesia_mix(256 * FRAME).reshape(256, FRAME)
+            cj = DllBatch(r, [sil_c[i % 256] for i in range(1024)], r.lib.ZREF_compressBound(FRAME), threads)
+            cj.compress(1); t1 = time.perf_counter(); cj.compress(1)
+            cpu["compress_l1_GBps"] = round(1024 * FRAME / (time.perf_counter() - t1) / 1e9, 4)
+            del job, cj
+        else:
+            cpu = {"value": round(port_rate, 4), "unit": "GB/s", "cores": threads, "kind": "port",
+                   "sample": f"256 text-like 128 KiB level-1 frames decoded repeatedly for {t:.1f} s on {threads} threads (oracle port of the reference's C# code)"}
+            cb, ct = cpu_compress_pass(o, [c for c in dg.silesia_mix(128 * FRAME).reshape(-1, FRAME)], threads, 1)
+            cpu["compress_l1_GBps"] = round(cb / ct / 1e9, 4)
+        cpu["native_libzstd_1_5_5_GBps"] = native_libzstd_decode_rate(frames, threads)
 
     if rank == 0:
         line = {
@@ -486,8 +696,8 @@ def run_b200(args):
                        "compressed_bytes_per_gpu": ctotal, "parallelism": f"host scatter, {world} rank(s), no collective",
                        "l2": "inputs larger than L2 (compressed batch %.0f MB + 1 GiB output per step)" % (ctotal / 1e6)},
             "wall_ms_per_step": round(wall_ms / args.steps, 4),
-            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
-            "cpu_baseline": cpu, "compress_l1": compress,
+            "clocks": clocks, "e2e": e2e, "e2e_pageable": e2e_pageable, "single_call": single, "gpu_launches": int(launches), "roofline": roofline,
+            "cpu_baseline": cpu, "compress_l1": compress, "workloads": workloads, "parity_gate": parity,
         }
         sys.stdout.flush()
         os.write(real_stdout, (json.dumps(line) + "\n").encode())
@@ -504,6 +714,8 @@ def main():
     ap.add_argument("--frames", type=int, default=8192, help="frames per GPU (8192 x 128 KiB = 1 GiB)")
     ap.add_argument("--skip-compress", action="store_true")
     ap.add_argument("--skip-cpu", action="store_true")
+    ap.add_argument("--skip-workloads", action="store_true")
+    ap.add_argument("--unique", type=int, default=UNIQUE_FRAMES, help="unique frames in the corpus (tiled up to --frames)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

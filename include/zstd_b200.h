@@ -111,6 +111,31 @@ ZSTDB200_API size_t ZSTDB200_compressBatchDevice(ZSTD_CCtx* cctx, size_t n, int 
                                                  void* d_dst, const uint64_t* dstOffset, const size_t* dstCapacity,
                                                  size_t* result);
 
+/* ---- multi-device scheduler (new): the host scatter of the batch across the GPUs of one box ----
+ * BASELINE.json north_star: "batches of independent frames are partitioned across the 8 GPUs of one box by a host scatter; no
+ * NCCL is used, because frames share no state".  The reference's closest notion is many contexts used at once
+ * (src/ZstdSharp.Test/ZstdNetTests.cs:498-522).  A Multi owns one decompression and one compression context per device;
+ * a batch call cuts the item list into contiguous ranges balanced by byte weight (ZSTDB200_shardBounds), runs every range on
+ * its device from its own host thread (bound to the CPUs local to that GPU's PCIe root unless ZSTDB200_NUMA_BIND=0), and
+ * writes result[] in the caller's order.  nDevices <= 0: every visible device. */
+typedef struct ZSTDB200_Multi_s ZSTDB200_Multi;
+ZSTDB200_API ZSTDB200_Multi* ZSTDB200_createMulti(int nDevices);
+ZSTDB200_API size_t ZSTDB200_freeMulti(ZSTDB200_Multi* m);
+ZSTDB200_API int    ZSTDB200_multiDeviceCount(const ZSTDB200_Multi* m);
+ZSTDB200_API size_t ZSTDB200_multiSetParameter(ZSTDB200_Multi* m, int param, int value);     /* ZSTD_CCtx_setParameter on every device's context */
+ZSTDB200_API size_t ZSTDB200_multiLoadDictionary(ZSTDB200_Multi* m, const void* dict, size_t dictSize);   /* ZSTD_DCtx_loadDictionary on every device */
+ZSTDB200_API size_t ZSTDB200_decompressBatchMulti(ZSTDB200_Multi* m, size_t n,
+                                                  const void* const* src, const size_t* srcSize,
+                                                  void* const* dst, const size_t* dstCapacity, size_t* result);
+ZSTDB200_API size_t ZSTDB200_compressBatchMulti(ZSTDB200_Multi* m, size_t n, int compressionLevel,
+                                                const void* const* src, const size_t* srcSize,
+                                                void* const* dst, const size_t* dstCapacity, size_t* result);
+/* bounds[0..parts]: item range [bounds[k], bounds[k+1]) goes to part k; contiguous, complete, balanced by weight */
+ZSTDB200_API void   ZSTDB200_shardBounds(size_t n, const size_t* weight, int parts, size_t* bounds);
+/* Pins the CALLING thread to the CPUs local to `device` (sysfs local_cpulist of its PCI function); pinned allocations made by the
+ * thread afterwards are then first-touched next to the GPU.  For one-process-per-GPU callers (bench.py); 0 = done, < 0 = not possible. */
+ZSTDB200_API int    ZSTDB200_bindThreadToDevice(int device);
+
 /* ---- instrumentation ---- */
 /* Milliseconds (CUDA events on the context's stream) of the last batch call: [0] host->device, [1] all kernels,
  * [2] device->host, [3..] per-kernel slots (decode: scan, setup, huf, seq, exec; encode: match, entropy). */

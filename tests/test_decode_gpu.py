@@ -335,3 +335,57 @@ def test_more_items_than_one_pass(dec):
         assert frames[i] == o.compress(srcs[i], 1), i
     outs = dec.UnwrapBatch(frames)
     assert outs == [s.tobytes() for s in srcs]
+
+
+def test_multi_device_scheduler_round_trip():
+    """ZSTDB200_compressBatchMulti / decompressBatchMulti: the in-library host scatter (one host thread + context per device,
+    ranges from ZSTDB200_shardBounds, results in caller order).  Runs on however many devices are visible (>= 1; 2+ on the
+    multi-GPU box): frames must equal the oracle's, decoded bytes the input, and a damaged item fails alone."""
+    from zstdsharp_b200 import MultiCodec, ZstdException
+    o = oracle()
+    data = dg.silesia_mix(40 * FRAME)
+    chunks = _chunks(data)[:37] + [dg.text_like(3 * FRAME + 17), np.zeros(0, dtype=np.uint8), dg.byte_ramp(5)]
+    with MultiCodec(0, level=1) as m:
+        assert m.DeviceCount >= 1
+        frames = m.WrapBatch(chunks)
+        for c, f in zip(chunks, frames):
+            assert f == o.compress(c, 1)
+        outs = m.UnwrapBatch(frames)
+        assert [bytes(x) for x in outs] == [c.tobytes() for c in chunks]
+        bad = list(frames)
+        g = bytearray(bad[5]); g[len(g) // 2] ^= 0x10; bad[5] = bytes(g)
+        res = m.UnwrapBatch(bad, raise_on_error=False)
+        rv, out = o.decompress_raw(bad[5], FRAME)
+        for i, r in enumerate(res):
+            if i == 5 and o.lib.zo_isError(rv):
+                assert isinstance(r, ZstdException) and r.Code == o.error_code(rv)
+            elif i != 5:
+                assert r == chunks[i].tobytes()
+    with MultiCodec(1, level=3) as m1:
+        assert m1.DeviceCount == 1
+        assert m1.WrapBatch(chunks[:4]) == [o.compress(c, 3) for c in chunks[:4]]
+
+
+def test_pageable_and_scattered_host_buffers(dec):
+    """What the drop-in callers hand over (Decompressor.cs:62-88: `fixed` over managed arrays = pageable, one array per frame):
+    the staging path (host threads <-> pinned ring) must give the same bytes as the pinned contiguous path."""
+    o = oracle()
+    data = dg.text_like(96 * FRAME)
+    chunks = _chunks(data)
+    frames = [o.compress(c, 1) for c in chunks]
+    outs = dec.UnwrapBatch(frames)                       # separate Python bytes objects: scattered pageable memory
+    assert b"".join(outs) == data.tobytes()
+    # contiguous pageable source and destination, through the C ABI directly
+    import ctypes
+    from zstdsharp_b200 import _native
+    blob = np.frombuffer(b"".join(frames), dtype=np.uint8).copy()
+    offs = np.concatenate([[0], np.cumsum([len(f) for f in frames])])
+    n = len(frames)
+    out = np.empty(n * FRAME, dtype=np.uint8)
+    sp = (ctypes.c_void_p * n)(*[blob.ctypes.data + int(x) for x in offs[:-1]])
+    ss = (ctypes.c_size_t * n)(*[len(f) for f in frames])
+    dp = (ctypes.c_void_p * n)(*[out.ctypes.data + i * FRAME for i in range(n)])
+    dc = (ctypes.c_size_t * n)(*[FRAME] * n)
+    res = (ctypes.c_size_t * n)()
+    assert _native.lib.ZSTDB200_decompressBatch(dec.handle, n, sp, ss, dp, dc, res) == 0
+    assert list(res) == [FRAME] * n and out.tobytes() == data.tobytes()

@@ -1,7 +1,7 @@
 import numpy as np
 
 from zstdsharp_b200 import datagen as dg
-from zstdsharp_b200.sharding import shard_bounds
+from zstdsharp_b200.sharding import shard_bounds, shard_bounds_native
 
 
 def test_datagen_is_deterministic_and_shaped():
@@ -23,6 +23,7 @@ def test_shard_bounds_cover_and_balance():
             assert len(b) == world and b[0][0] == 0 and b[-1][1] == n
             assert all(b[i][1] == b[i + 1][0] for i in range(world - 1))
             assert all(lo <= hi for lo, hi in b)
+            assert shard_bounds_native(w.tolist(), world) == b          # the C++ scheduler (ZSTDB200_*BatchMulti) cuts identically
             if n >= 8 * world:
                 sums = [int(w[lo:hi].sum()) for lo, hi in b]
                 assert max(sums) - min(sums) <= 2 * 131085

@@ -14,12 +14,13 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 def _worker(rank, world, port, q):
     sys.path.insert(0, ROOT)
-    from zstdsharp_b200.sharding import my_shard
+    from zstdsharp_b200.sharding import my_shard, shard_bounds_native
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     weights = (np.arange(1000) % 97 + 22).tolist()
     lo, hi = my_shard(weights, rank, world)
+    assert shard_bounds_native(weights, world)[rank] == (lo, hi)       # the in-library scatter (ZSTDB200_*BatchMulti) owns the same range
     mine = torch.zeros(1000, dtype=torch.int32)
     mine[lo:hi] = 1
     dist.all_reduce(mine, op=dist.ReduceOp.SUM)           # test-only collective: every frame owned exactly once

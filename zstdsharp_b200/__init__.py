@@ -3,7 +3,7 @@
 Importing the package loads ``_build/libzstdb200.so``; it fails loudly if the library has not been built.
 ``zstdsharp_b200.datagen`` (pure numpy) can be imported on its own without the native library.
 """
-__all__ = ["Compressor", "Decompressor", "ZstdException", "ZSTD_ErrorCode", "ZSTD_cParameter"]
+__all__ = ["Compressor", "Decompressor", "MultiCodec", "ZstdException", "ZSTD_ErrorCode", "ZSTD_cParameter"]
 
 
 def __getattr__(name):

@@ -23,6 +23,9 @@ EXPORTED_SYMBOLS = [
     "ZSTDB200_compressBatchDevice", "ZSTDB200_getLastTimings", "ZSTDB200_getLastLaunchCount",
     "ZSTDB200_lastErrorString", "ZSTDB200_deviceCount", "ZSTDB200_setStream", "ZSTD_DCtx_loadDictionary",
     "ZSTD_CCtx_getParameter", "ZSTD_DCtx_setParameter", "ZSTD_DCtx_getParameter",
+    "ZSTDB200_createMulti", "ZSTDB200_freeMulti", "ZSTDB200_multiDeviceCount", "ZSTDB200_multiSetParameter",
+    "ZSTDB200_multiLoadDictionary", "ZSTDB200_decompressBatchMulti", "ZSTDB200_compressBatchMulti",
+    "ZSTDB200_shardBounds", "ZSTDB200_bindThreadToDevice",
 ]
 
 
@@ -88,6 +91,24 @@ def _load() -> ctypes.CDLL:
     lib.ZSTDB200_deviceCount.restype = c_int
     lib.ZSTDB200_setStream.restype = c_size_t
     lib.ZSTDB200_setStream.argtypes = [c_void_p, c_void_p]
+    lib.ZSTDB200_createMulti.restype = c_void_p
+    lib.ZSTDB200_createMulti.argtypes = [c_int]
+    lib.ZSTDB200_freeMulti.restype = c_size_t
+    lib.ZSTDB200_freeMulti.argtypes = [c_void_p]
+    lib.ZSTDB200_multiDeviceCount.restype = c_int
+    lib.ZSTDB200_multiDeviceCount.argtypes = [c_void_p]
+    lib.ZSTDB200_multiSetParameter.restype = c_size_t
+    lib.ZSTDB200_multiSetParameter.argtypes = [c_void_p, c_int, c_int]
+    lib.ZSTDB200_multiLoadDictionary.restype = c_size_t
+    lib.ZSTDB200_multiLoadDictionary.argtypes = [c_void_p, c_void_p, c_size_t]
+    lib.ZSTDB200_decompressBatchMulti.restype = c_size_t
+    lib.ZSTDB200_decompressBatchMulti.argtypes = batch_host
+    lib.ZSTDB200_compressBatchMulti.restype = c_size_t
+    lib.ZSTDB200_compressBatchMulti.argtypes = [c_void_p, c_size_t, c_int, P(c_void_p), P(c_size_t), P(c_void_p), P(c_size_t), P(c_size_t)]
+    lib.ZSTDB200_shardBounds.restype = None
+    lib.ZSTDB200_shardBounds.argtypes = [c_size_t, P(c_size_t), c_int, P(c_size_t)]
+    lib.ZSTDB200_bindThreadToDevice.restype = c_int
+    lib.ZSTDB200_bindThreadToDevice.argtypes = [c_int]
     return lib
 
 

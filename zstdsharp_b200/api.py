@@ -351,3 +351,95 @@ class Decompressor:
     def _ensure(self) -> None:
         if not self._dctx:
             raise ObjectDisposedException("Decompressor")
+
+
+class MultiCodec:
+    """The batch scheduler across the GPUs of one box (BASELINE.json north_star: "partitioned across the 8 GPUs of one box by a
+    host scatter", no collective): ``WrapBatch`` / ``UnwrapBatch`` with the meaning they have on ``Compressor`` /
+    ``Decompressor``, every item handled by exactly one device, results in the caller's order (ZSTDB200_*BatchMulti)."""
+
+    def __init__(self, n_devices: int = 0, level: int = 1):
+        self._m = _lib.ZSTDB200_createMulti(int(n_devices))
+        if not self._m:
+            raise ZstdException(ZSTD_ErrorCode.GENERIC, "Failed to create the multi-device scheduler: " + _lib.ZSTDB200_lastErrorString().decode())
+        self.Level = level
+
+    @property
+    def DeviceCount(self) -> int:
+        return int(_lib.ZSTDB200_multiDeviceCount(self._m))
+
+    def SetParameter(self, parameter: int, value: int) -> None:
+        EnsureZstdSuccess(_lib.ZSTDB200_multiSetParameter(self._m, int(parameter), int(value)))
+
+    def LoadDictionary(self, dictionary) -> None:
+        if dictionary is None or len(dictionary) == 0:
+            EnsureZstdSuccess(_lib.ZSTDB200_multiLoadDictionary(self._m, 0, 0))
+            return
+        d = _as_u8(dictionary)
+        EnsureZstdSuccess(_lib.ZSTDB200_multiLoadDictionary(self._m, _ptr(d), d.size))
+
+    def WrapBatch(self, chunks: Sequence) -> List[bytes]:
+        srcs = [_as_u8(c) for c in chunks]
+        n = len(srcs)
+        if n == 0:
+            return []
+        caps = [Compressor.GetCompressBound(s.size) for s in srcs]
+        offs = np.concatenate([[0], np.cumsum(caps)]).astype(np.int64)
+        out = np.empty(int(offs[-1]), dtype=np.uint8)
+        sp = (ctypes.c_void_p * n)(*[_ptr(s) for s in srcs])
+        ss = (ctypes.c_size_t * n)(*[s.size for s in srcs])
+        dp = (ctypes.c_void_p * n)(*[out.ctypes.data + int(o) for o in offs[:-1]])
+        dc = (ctypes.c_size_t * n)(*caps)
+        res = (ctypes.c_size_t * n)()
+        level = 3 if self.Level == 0 else self.Level
+        EnsureZstdSuccess(_lib.ZSTDB200_compressBatchMulti(self._m, n, level, sp, ss, dp, dc, res))
+        frames = []
+        for i in range(n):
+            EnsureZstdSuccess(res[i])
+            frames.append(out[int(offs[i]):int(offs[i]) + res[i]].tobytes())
+        return frames
+
+    def UnwrapBatch(self, frames: Sequence, raise_on_error: bool = True):
+        srcs = [_as_u8(f) for f in frames]
+        n = len(srcs)
+        if n == 0:
+            return []
+        caps = []
+        for s in srcs:
+            b = int(_lib.ZSTD_decompressBound(_ptr(s), s.size))
+            caps.append(0 if b >= CONTENTSIZE_ERROR else b)
+        offs = np.concatenate([[0], np.cumsum(caps)]).astype(np.int64)
+        out = np.empty(max(int(offs[-1]), 1), dtype=np.uint8)
+        sp = (ctypes.c_void_p * n)(*[_ptr(s) for s in srcs])
+        ss = (ctypes.c_size_t * n)(*[s.size for s in srcs])
+        dp = (ctypes.c_void_p * n)(*[out.ctypes.data + int(o) for o in offs[:-1]])
+        dc = (ctypes.c_size_t * n)(*caps)
+        res = (ctypes.c_size_t * n)()
+        EnsureZstdSuccess(_lib.ZSTDB200_decompressBatchMulti(self._m, n, sp, ss, dp, dc, res))
+        outs = []
+        for i in range(n):
+            if is_error(res[i]):
+                exc = ZstdException(error_code(res[i]), _lib.ZSTD_getErrorName(res[i]).decode())
+                if raise_on_error:
+                    raise exc
+                outs.append(exc)
+            else:
+                outs.append(out[int(offs[i]):int(offs[i]) + res[i]].tobytes())
+        return outs
+
+    def Dispose(self) -> None:
+        if self._m:
+            _lib.ZSTDB200_freeMulti(self._m)
+            self._m = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.Dispose()
+
+    def __del__(self):
+        try:
+            self.Dispose()
+        except Exception:
+            pass

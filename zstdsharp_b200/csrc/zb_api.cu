@@ -15,6 +15,9 @@
 #include <string>
 #include <thread>
 #include <vector>
+#include <cctype>
+#include <cmath>
+#include <sched.h>
 
 #include "../../include/zstd_b200.h"
 #include "zb_decode.cuh"
@@ -93,6 +96,7 @@ struct DecArena {
 
 struct Engine {
     int device = -1;
+    int wantDevice = -1;                // >= 0: the device this context must live on (multi-device scheduler); else ZSTDB200_DEVICE / the caller's current device
     bool ready = false;
     cudaStream_t stream = nullptr;      // stream all work of this context is issued on
     cudaStream_t ownStream = nullptr;   // created by the context; replaced by ZSTDB200_setStream
@@ -126,7 +130,8 @@ struct Engine {
         cudaError_t e = cudaGetDeviceCount(&count);
         if (e != cudaSuccess || count == 0) { set_error(std::string("no CUDA device: ") + cudaGetErrorString(e)); return false; }
         int dev = 0;
-        if (const char* env = getenv("ZSTDB200_DEVICE")) dev = atoi(env);
+        if (wantDevice >= 0) dev = wantDevice;
+        else if (const char* env = getenv("ZSTDB200_DEVICE")) dev = atoi(env);
         else if (cudaGetDevice(&dev) != cudaSuccess) dev = 0;
         if (dev < 0 || dev >= count) { set_error("ZSTDB200_DEVICE out of range"); return false; }
         device = dev;
@@ -273,10 +278,22 @@ static void find_runs(std::vector<Run>& runs, size_t n, const void* const* ptr, 
     }
 }
 
+// true when `p` is ordinary pageable host memory (malloc / a managed byte[] that is only GC-pinned): a cudaMemcpyAsync from or to
+// it is staged by the driver in small synchronous pieces.  Such buffers go through the library's own pinned staging ring
+// instead, filled / drained by host threads while the DMA of the neighbouring sub-batch is in flight.
+static bool is_pageable(const void* p)
+{
+    if (!p) return false;
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { (void)cudaGetLastError(); return true; }
+    return a.type == cudaMemoryTypeUnregistered;
+}
+static int host_copy_threads() { static int v = env_int("ZSTDB200_HOST_THREADS", 16, 1, 64); return v; }
+
 static void parallel_for(size_t n, size_t grain, const std::function<void(size_t, size_t)>& fn)
 {
     unsigned hw = std::thread::hardware_concurrency(); if (hw == 0) hw = 4;
-    size_t const nt = std::min<size_t>(std::min<unsigned>(hw, 16), (n + grain - 1) / grain);
+    size_t const nt = std::min<size_t>(std::min<unsigned>(hw, (unsigned)host_copy_threads()), (n + grain - 1) / grain);
     if (nt <= 1) { fn(0, n); return; }
     std::vector<std::thread> th;
     size_t const per = (n + nt - 1) / nt;
@@ -378,8 +395,11 @@ static size_t decompress_batch_host(Engine& E, size_t n, const void* const* src,
     sTotal += 64;
     size_t const dstRuns = layout_dst(n, dst, dstCap, dOff, &dTotal, E.dict_headroom());
     if (!E.dSrc.ensure(sTotal) || !E.dDst.ensure(dTotal)) return (size_t)make_error(kMemoryAllocation);
-    bool const gather = runs.size() > 512;                     // many scattered buffers: stage through pinned memory
-    bool const scatter = dstRuns > 512;
+    // many scattered buffers, or pageable memory (what Unwrap's `fixed (byte* ...)` over a managed array hands over,
+    // Decompressor.cs:62-88): stage through pinned memory with host threads
+    static int const forceStage = env_int("ZSTDB200_FORCE_STAGING", 0, 0, 1);
+    bool const gather = runs.size() > 512 || forceStage || (n >= 64 && is_pageable(src[0]));
+    bool const scatter = dstRuns > 512 || forceStage || (n >= 64 && is_pageable(dst[0]));
     if (gather && !E.hStage.ensure(sTotal)) return (size_t)make_error(kMemoryAllocation);
     if (scatter && !E.hStageOut.ensure(dTotal)) return (size_t)make_error(kMemoryAllocation);
     // ---- sub-batches: sizes grow geometrically (n/16, n/8, n/4, ...) so that the first D2H starts early and the D2H
@@ -410,7 +430,7 @@ static size_t decompress_batch_host(Engine& E, size_t n, const void* const* src,
         size_t const a = sub[k], b = sub[k + 1];
         if (gather) {
             uint8_t* st = E.hStage.as<uint8_t>();
-            parallel_for(b - a, 256, [&](size_t x, size_t y) { for (size_t i = a + x; i < a + y; i++) memcpy(st + sOff[i], src[i], srcSize[i]); });
+            parallel_for(b - a, 32, [&](size_t x, size_t y) { for (size_t i = a + x; i < a + y; i++) memcpy(st + sOff[i], src[i], srcSize[i]); });
             size_t const lo = sOff[a], hi = sOff[b - 1] + srcSize[b - 1];
             if (hi > lo && cudaMemcpyAsync(E.dSrc.as<uint8_t>() + lo, st + lo, hi - lo, cudaMemcpyHostToDevice, E.sIn) != cudaSuccess) return fail(kGeneric);
         } else {
@@ -435,7 +455,7 @@ static size_t decompress_batch_host(Engine& E, size_t n, const void* const* src,
         size_t const a = sub[k], b = sub[k + 1];
         if (cudaEventSynchronize(evD2H[k]) != cudaSuccess) return false;
         const uint8_t* st = E.hStageOut.as<uint8_t>();
-        parallel_for(b - a, 256, [&](size_t x, size_t y) { for (size_t i = a + x; i < a + y; i++) if (!is_error(result[i])) memcpy(dst[i], st + dOff[i], result[i]); });
+        parallel_for(b - a, 32, [&](size_t x, size_t y) { for (size_t i = a + x; i < a + y; i++) if (!is_error(result[i])) memcpy(dst[i], st + dOff[i], result[i]); });
         return true;
     };
     auto finish = [&](size_t k) -> bool {
@@ -708,6 +728,55 @@ static unsigned long long decompress_bound_host(const void* srcV, size_t srcSize
     return bound;
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+//  Multi-device scheduler: the host scatter of BASELINE.json's north_star ("batches of independent frames are partitioned
+//  across the 8 GPUs of one box by a host scatter; no NCCL, frames share no state"; SURVEY.md section 8e: one host thread + one
+//  CUDA context / stream set per GPU, pinned-host scatter in, pinned-host gather out).
+// ---------------------------------------------------------------------------------------------------------------
+// Contiguous ranges balanced by byte weight (greedy on the prefix sum; the Python mirror is zstdsharp_b200/sharding.py).
+static void shard_bounds(size_t n, const size_t* weight, int parts, size_t* bounds /* [parts + 1] */)
+{
+    std::vector<unsigned long long> csum(n);
+    unsigned long long total = 0;
+    for (size_t i = 0; i < n; i++) { total += weight[i]; csum[i] = total; }
+    bounds[0] = 0;
+    for (int r = 1; r < parts; r++) {
+        double const target = (double)total * r / parts;
+        size_t cut = (size_t)(std::lower_bound(csum.begin(), csum.end(), target, [](unsigned long long c, double t) { return (double)c < t; }) - csum.begin()) + 1;
+        cut = std::min(std::max(cut, bounds[r - 1]), n);
+        if (cut >= 2 && cut - 1 > bounds[r - 1] && std::abs((double)csum[cut - 2] - target) <= std::abs((double)csum[cut - 1] - target)) cut--;
+        bounds[r] = cut;
+    }
+    bounds[parts] = n;
+}
+
+// Pins the calling thread to the CPUs that are local to `device` (its PCIe root's NUMA node, /sys/bus/pci/devices/<id>/local_cpulist):
+// the staging memcpy threads and the pinned allocations made afterwards then live next to the GPU.  Best effort: 0 = done.
+static int bind_thread_near_device(int device)
+{
+    char bus[32] = {0};
+    if (cudaDeviceGetPCIBusId(bus, sizeof(bus), device) != cudaSuccess) { (void)cudaGetLastError(); return -1; }
+    for (char* c = bus; *c; c++) *c = (char)tolower(*c);
+    std::string const path = std::string("/sys/bus/pci/devices/") + bus + "/local_cpulist";
+    FILE* f = fopen(path.c_str(), "r");
+    if (!f) return -2;
+    char line[4096] = {0};
+    char* const got = fgets(line, sizeof(line), f);
+    fclose(f);
+    if (!got) return -3;
+    cpu_set_t set; CPU_ZERO(&set);
+    int count = 0;
+    for (char* tok = strtok(line, ",\n"); tok; tok = strtok(nullptr, ",\n")) {
+        int a = 0, b = 0;
+        int const k = sscanf(tok, "%d-%d", &a, &b);
+        if (k == 1) b = a;
+        if (k < 1) continue;
+        for (int c = a; c <= b && c < CPU_SETSIZE; c++) { CPU_SET(c, &set); count++; }
+    }
+    if (count == 0) return -4;
+    return sched_setaffinity(0, sizeof(set), &set) == 0 ? 0 : -5;
+}
+
 static const char* error_name(uint32_t code)   // ErrorPrivate.cs:34-184
 {
     switch (code) {
@@ -914,5 +983,97 @@ size_t ZSTDB200_setStream(void* ctx, void* stream)
     return 0;
 }
 int ZSTDB200_deviceCount(void) { int c = 0; if (cudaGetDeviceCount(&c) != cudaSuccess) return 0; return c; }
+
+// ---- multi-device scheduler (include/zstd_b200.h) ----
+struct ZSTDB200_Multi_s {
+    std::vector<ZSTD_DCtx_s*> d; std::vector<ZSTD_CCtx_s*> c; std::vector<int> dev; int bindNuma = 1;
+};
+
+ZSTDB200_Multi* ZSTDB200_createMulti(int nDevices)
+{
+    int have = ZSTDB200_deviceCount();
+    if (have <= 0) { zb::set_error("no CUDA device"); return nullptr; }
+    if (nDevices <= 0 || nDevices > have) nDevices = have;
+    ZSTDB200_Multi_s* m = new (std::nothrow) ZSTDB200_Multi_s();
+    if (!m) return nullptr;
+    for (int k = 0; k < nDevices; k++) {
+        ZSTD_DCtx_s* d = new (std::nothrow) ZSTD_DCtx_s(); ZSTD_CCtx_s* c = new (std::nothrow) ZSTD_CCtx_s();
+        if (!d || !c) { delete d; delete c; ZSTDB200_freeMulti(m); return nullptr; }
+        d->E.wantDevice = k; c->E.wantDevice = k;
+        m->d.push_back(d); m->c.push_back(c); m->dev.push_back(k);
+    }
+    if (const char* e = getenv("ZSTDB200_NUMA_BIND")) m->bindNuma = atoi(e);
+    return m;
+}
+size_t ZSTDB200_freeMulti(ZSTDB200_Multi* m)
+{
+    if (!m) return 0;
+    for (auto* d : m->d) ZSTD_freeDCtx(d);
+    for (auto* c : m->c) ZSTD_freeCCtx(c);
+    delete m;
+    return 0;
+}
+int ZSTDB200_multiDeviceCount(const ZSTDB200_Multi* m) { return m ? (int)m->dev.size() : 0; }
+size_t ZSTDB200_multiSetParameter(ZSTDB200_Multi* m, int param, int value)
+{
+    if (!m) return (size_t)make_error(zb::kGeneric);
+    size_t r = 0;
+    for (auto* c : m->c) { size_t const x = ZSTD_CCtx_setParameter(c, param, value); if (zb::is_error(x)) r = x; }
+    return r;
+}
+void ZSTDB200_shardBounds(size_t n, const size_t* weight, int parts, size_t* bounds) { if (parts > 0) zb::shard_bounds(n, weight, parts, bounds); }
+int ZSTDB200_bindThreadToDevice(int device) { return zb::bind_thread_near_device(device); }
+
+}  // extern "C"
+// One host thread per device: thread k owns the contiguous item range [bounds[k], bounds[k+1]) (balanced by srcSize), runs the
+// single-device batch call on its context and writes result[] in the caller's order.  No data crosses between devices.
+template <typename Fn>
+static size_t multi_run(ZSTDB200_Multi* m, size_t n, const size_t* srcSize, size_t* bounds, Fn&& perDevice)
+{
+    int const parts = (int)m->dev.size();
+    zb::shard_bounds(n, srcSize, parts, bounds);
+    std::vector<size_t> rc((size_t)parts, 0);
+    std::vector<std::thread> th;
+    for (int k = 0; k < parts; k++) {
+        if (bounds[k] == bounds[k + 1]) continue;
+        th.emplace_back([&, k]() {
+            if (m->bindNuma) (void)zb::bind_thread_near_device(m->dev[(size_t)k]);
+            rc[(size_t)k] = perDevice(k, bounds[k], bounds[k + 1] - bounds[k]);
+        });
+    }
+    for (auto& t : th) t.join();
+    for (int k = 0; k < parts; k++) if (zb::is_error(rc[(size_t)k])) return rc[(size_t)k];
+    return 0;
+}
+extern "C" {
+
+size_t ZSTDB200_decompressBatchMulti(ZSTDB200_Multi* m, size_t n, const void* const* src, const size_t* srcSize,
+                                     void* const* dst, const size_t* dstCap, size_t* result)
+{
+    if (!m || m->dev.empty()) return (size_t)make_error(zb::kGeneric);
+    if (n == 0) return 0;
+    std::vector<size_t> bounds(m->dev.size() + 1);
+    // decode work follows the regenerated bytes more closely than the compressed ones
+    return multi_run(m, n, dstCap, bounds.data(), [&](int k, size_t a, size_t cnt) {
+        return ZSTDB200_decompressBatch(m->d[(size_t)k], cnt, src + a, srcSize + a, dst + a, dstCap + a, result + a);
+    });
+}
+size_t ZSTDB200_compressBatchMulti(ZSTDB200_Multi* m, size_t n, int level, const void* const* src, const size_t* srcSize,
+                                   void* const* dst, const size_t* dstCap, size_t* result)
+{
+    if (!m || m->dev.empty()) return (size_t)make_error(zb::kGeneric);
+    if (n == 0) return 0;
+    std::vector<size_t> bounds(m->dev.size() + 1);
+    return multi_run(m, n, srcSize, bounds.data(), [&](int k, size_t a, size_t cnt) {
+        return ZSTDB200_compressBatch(m->c[(size_t)k], cnt, level, src + a, srcSize + a, dst + a, dstCap + a, result + a);
+    });
+}
+size_t ZSTDB200_multiLoadDictionary(ZSTDB200_Multi* m, const void* dict, size_t dictSize)
+{
+    if (!m) return (size_t)make_error(zb::kGeneric);
+    size_t r = 0;
+    for (auto* d : m->d) { size_t const x = ZSTD_DCtx_loadDictionary(d, dict, dictSize); if (zb::is_error(x)) r = x; }
+    return r;
+}
 
 }  // extern "C"

@@ -36,3 +36,14 @@ def shard_bounds(weights: Sequence[int], world_size: int) -> List[Tuple[int, int
 
 def my_shard(weights: Sequence[int], rank: int, world_size: int) -> Tuple[int, int]:
     return shard_bounds(weights, world_size)[rank]
+
+
+def shard_bounds_native(weights: Sequence[int], world_size: int) -> List[Tuple[int, int]]:
+    """The C++ scheduler's split (ZSTDB200_shardBounds, what ZSTDB200_*BatchMulti use): must equal shard_bounds()."""
+    import ctypes
+    from . import _native
+    n = len(weights)
+    w = (ctypes.c_size_t * max(n, 1))(*[int(x) for x in weights])
+    b = (ctypes.c_size_t * (world_size + 1))()
+    _native.lib.ZSTDB200_shardBounds(n, w, world_size, b)
+    return [(int(b[i]), int(b[i + 1])) for i in range(world_size)]
