@@ -25,6 +25,8 @@
 
 namespace zb {
 
+void host_copy(void* dst, const void* src, size_t n);      // zb_hostcopy.cpp: staging copy with non-temporal stores
+
 static thread_local std::string t_lastError;
 static void set_error(const std::string& s) { t_lastError = s; }
 
@@ -404,7 +406,9 @@ static size_t decompress_batch_host(Engine& E, size_t n, const void* const* src,
     if (scatter && !E.hStageOut.ensure(dTotal)) return (size_t)make_error(kMemoryAllocation);
     // ---- sub-batches: sizes grow geometrically (n/16, n/8, n/4, ...) so that the first D2H starts early and the D2H
     // stream -- the slowest stage -- then never runs dry; no sub-batch exceeds the configured target ----
-    size_t const kPipe = (size_t)pipe_depth(), kPipeItems = pipe_items();
+    // staged output: the LAST sub-batch's copy-out by host threads is exposed, so sub-batches stay small there
+    static int const stageItems = env_int("ZSTDB200_STAGE_ITEMS", 1024, 16, 8192);
+    size_t const kPipe = (size_t)pipe_depth(), kPipeItems = scatter ? std::min<size_t>(pipe_items(), (size_t)stageItems) : pipe_items();
     std::vector<size_t> sub;                     // sub-batch k = items [sub[k], sub[k+1])
     {
         static int const firstDiv = env_int("ZSTDB200_PIPE_FIRST_DIV", 16, 2, 256);
@@ -424,16 +428,32 @@ static size_t decompress_batch_host(Engine& E, size_t n, const void* const* src,
     if (cudaEventRecord(E.evStart, E.stream) != cudaSuccess) return fail(kGeneric);   // order after the caller's stream
     cudaStreamWaitEvent(E.sIn, E.evStart, 0);
     cudaEventRecord(E.evIn[0], E.sIn);
-    // stage 1: all uploads are queued up front
-    size_t runIdx = 0;
-    for (size_t k = 0; k < nSub; k++) {
-        size_t const a = sub[k], b = sub[k + 1];
-        if (gather) {
+    // stage 1: all uploads are queued up front.  Staged input: a helper thread fills the pinned ring sub-batch by sub-batch (host
+    // threads) and queues each DMA, while this thread already launches kernels and drains results; `uploaded` counts the
+    // sub-batches whose H2D event has been recorded (a stream wait on an event that is not recorded yet would be a no-op).
+    std::atomic<size_t> uploaded{0}; std::atomic<bool> uploadFailed{false};
+    std::thread uploader;
+    struct Joiner { std::thread& t; ~Joiner() { if (t.joinable()) t.join(); } } joinUploader{uploader};
+    if (gather) {
+        int const dev = E.device;
+        uploader = std::thread([&, dev]() {
+            cudaSetDevice(dev);
             uint8_t* st = E.hStage.as<uint8_t>();
-            parallel_for(b - a, 32, [&](size_t x, size_t y) { for (size_t i = a + x; i < a + y; i++) memcpy(st + sOff[i], src[i], srcSize[i]); });
-            size_t const lo = sOff[a], hi = sOff[b - 1] + srcSize[b - 1];
-            if (hi > lo && cudaMemcpyAsync(E.dSrc.as<uint8_t>() + lo, st + lo, hi - lo, cudaMemcpyHostToDevice, E.sIn) != cudaSuccess) return fail(kGeneric);
-        } else {
+            for (size_t k = 0; k < nSub; k++) {
+                size_t const a = sub[k], b = sub[k + 1];
+                parallel_for(b - a, 32, [&](size_t x, size_t y) { for (size_t i = a + x; i < a + y; i++) host_copy(st + sOff[i], src[i], srcSize[i]); });
+                size_t const lo = sOff[a], hi = sOff[b - 1] + srcSize[b - 1];
+                if (hi > lo && cudaMemcpyAsync(E.dSrc.as<uint8_t>() + lo, st + lo, hi - lo, cudaMemcpyHostToDevice, E.sIn) != cudaSuccess) uploadFailed = true;
+                cudaEventRecord(evH2D[k], E.sIn);
+                if (k + 1 == nSub) cudaEventRecord(E.evIn[1], E.sIn);
+                uploaded.store(k + 1, std::memory_order_release);
+            }
+        });
+    }
+    size_t runIdx = 0;
+    for (size_t k = 0; k < nSub && !gather; k++) {
+        size_t const a = sub[k], b = sub[k + 1];
+        {
             // the pieces of the runs that intersect [a, b): one DMA each
             size_t i = a;
             while (i < b) {
@@ -446,18 +466,29 @@ static size_t decompress_batch_host(Engine& E, size_t n, const void* const* src,
         }
         cudaEventRecord(evH2D[k], E.sIn);
     }
-    cudaEventRecord(E.evIn[1], E.sIn);
+    if (!gather) { cudaEventRecord(E.evIn[1], E.sIn); uploaded.store(nSub); }
     // stage 2 + 3
     bool firstOut = true;
     // scattered destinations: the sub-batch's device region comes back with one DMA into pinned staging and is copied
     // out by host threads one sub-batch later (while the next DMA is in flight)
-    auto scatter_out = [&](size_t k) -> bool {
-        size_t const a = sub[k], b = sub[k + 1];
-        if (cudaEventSynchronize(evD2H[k]) != cudaSuccess) return false;
-        const uint8_t* st = E.hStageOut.as<uint8_t>();
-        parallel_for(b - a, 32, [&](size_t x, size_t y) { for (size_t i = a + x; i < a + y; i++) if (!is_error(result[i])) memcpy(dst[i], st + dOff[i], result[i]); });
-        return true;
-    };
+    // (a helper thread does the copy-out, so that this thread keeps launching kernels and queueing DMAs meanwhile)
+    std::atomic<size_t> d2hQueued{0}; std::atomic<bool> drainFailed{false}, drainStop{false};
+    std::thread drainer;
+    Joiner joinDrainer{drainer};
+    if (scatter) {
+        int const dev = E.device;
+        drainer = std::thread([&, dev]() {
+            cudaSetDevice(dev);
+            const uint8_t* st = E.hStageOut.as<uint8_t>();
+            for (size_t k = 0; k < nSub; k++) {
+                while (d2hQueued.load(std::memory_order_acquire) <= k) { if (drainStop.load()) return; std::this_thread::yield(); }
+                if (cudaEventSynchronize(evD2H[k]) != cudaSuccess) { drainFailed = true; return; }
+                size_t const a = sub[k], b = sub[k + 1];
+                parallel_for(b - a, 32, [&](size_t x, size_t y) { for (size_t i = a + x; i < a + y; i++) if (!is_error(result[i])) host_copy(dst[i], st + dOff[i], result[i]); });
+            }
+        });
+    }
+    struct Stopper { std::atomic<bool>& f; ~Stopper() { f = true; } } stopDrainer{drainStop};     // runs before joinDrainer (reverse order of construction)
     auto finish = [&](size_t k) -> bool {
         size_t const a = sub[k], b = sub[k + 1];
         if (cudaEventSynchronize(evDone[k]) != cudaSuccess) return false;
@@ -467,7 +498,8 @@ static size_t decompress_batch_host(Engine& E, size_t n, const void* const* src,
         size_t const lo = dOff[a], hi = dOff[b - 1] + dstCap[b - 1];
         if (hi > lo && cudaMemcpyAsync(E.hStageOut.as<uint8_t>() + lo, E.dDst.as<uint8_t>() + lo, hi - lo, cudaMemcpyDeviceToHost, E.sOut) != cudaSuccess) return false;
         cudaEventRecord(evD2H[k], E.sOut);
-        return k == 0 || scatter_out(k - 1);
+        d2hQueued.store(k + 1, std::memory_order_release);
+        return true;
     };
     for (size_t k = 0; k < nSub; k++) {
         size_t const a = sub[k], b = sub[k + 1];
@@ -475,6 +507,8 @@ static size_t decompress_batch_host(Engine& E, size_t n, const void* const* src,
         uint32_t waves = 1;
         for (size_t i = a; i < b; i++) waves = std::max(waves, count_item_blocks((const uint8_t*)src[i], (uint32_t)std::min<size_t>(srcSize[i], 0xFFFFFFF0u)));
         cudaStream_t const cs = E.sComp[k % kPipe];
+        while (uploaded.load(std::memory_order_acquire) <= k) std::this_thread::yield();
+        if (uploadFailed) return fail(kGeneric);
         cudaStreamWaitEvent(cs, evH2D[k], 0);
         cudaEventRecord(evBegin[k], cs);
         if (!decode_enqueue(E, E.dec[k % kPipe], cs, b - a, E.dSrc.as<uint8_t>(), sOff.data() + a, srcSize + a, E.dDst.as<uint8_t>(), dOff.data() + a, dstCap + a, waves, nullptr))
@@ -482,7 +516,7 @@ static size_t decompress_batch_host(Engine& E, size_t n, const void* const* src,
         cudaEventRecord(evDone[k], cs);
     }
     for (size_t k = nSub > kPipe ? nSub - kPipe : 0; k < nSub; k++) if (!finish(k)) return fail(kGeneric);
-    if (scatter && !scatter_out(nSub - 1)) return fail(kGeneric);
+    if (scatter) { drainer.join(); if (drainFailed) return fail(kGeneric); }
     cudaEventRecord(E.evOut[1], E.sOut);
     if (cudaStreamSynchronize(E.sOut) != cudaSuccess || cudaGetLastError() != cudaSuccess) return fail(kGeneric);
     // the stages overlap: [0] / [2] are the spans of the copy streams, [1] is the sum of the sub-batch kernel spans
