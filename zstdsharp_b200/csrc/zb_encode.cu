@@ -363,6 +363,14 @@ __device__ __forceinline__ uint32_t hash_val(uint64_t x, uint32_t hBits, uint32_
 //  instruction stream.  A 32-lane window wastes ~28 of its 32 probes on text (the first event sits within the first few
 //  probes): ncu showed 33 G warp instructions and 120 GB of DRAM reads per GiB; 8 lanes per chunk cut both.
 // ------------------------------------------------------------------------------------------------------------
+// Single-block frames (MB = false) never see a position above 2^17, so a table entry has room for a 14-bit tag of the four bytes
+// that sit at the position: entry = (position + 2) | tag << 18.  A probe whose tag differs cannot match (ZstdFast.cs:179-192 compares
+// MEM_read32(base + idx) with MEM_read32(ip)), so its candidate bytes are never fetched: 15 of the 16 candidate sectors of a window
+// stay in DRAM, and only likely hits pay the second dependent round trip.  The table still holds exactly the reference's positions.
+constexpr uint32_t kPosBits = 18, kPosMask = (1u << kPosBits) - 1u;
+__device__ __forceinline__ uint32_t tag4(uint32_t v) { return (v * 2654435761u) >> kPosBits; }
+template <bool TAG> __device__ __forceinline__ uint32_t tab_entry(uint32_t posPlus2, uint32_t first4) { return TAG ? (posPlus2 | (tag4(first4) << kPosBits)) : posPlus2; }
+
 template <int GS, bool MB>
 __global__ void __launch_bounds__(32 * kMatchWarps) enc_match_group_kernel(EncPass p, const uint32_t* __restrict__ workList, uint32_t nWork, uint32_t wave)
 {
@@ -401,8 +409,13 @@ __global__ void __launch_bounds__(32 * kMatchWarps) enc_match_group_kernel(EncPa
     while (__any_sync(FULL, active)) {
         // ---- positions of this lane's probe: iteration k of the window (ZstdFast.cs:147-230 schedule) ----
         int P = ip0, D = d, S = step, N = nextStep, pk = 0, dk = 0;
+        // right after a match (and for the first 100 bytes without one) the schedule is simply consecutive pairs: no step change inside the window
+        bool const simple = !active || (d == 2 && step == 2 && ip0 + 2 * NIT + 2 < nextStep);
+        if (__all_sync(FULL, simple)) { pk = ip0 + 2 * (int)k; dk = 2; P = ip0 + 2 * NIT; }
+        else {
 #pragma unroll
-        for (int j = 0; j < NIT; j++) { if (j == (int)k) { pk = P; dk = D; } P += D; int const ip2n = P + S; D = S; if (ip2n >= N) { S++; N += 128; } }
+            for (int j = 0; j < NIT; j++) { if (j == (int)k) { pk = P; dk = D; } P += D; int const ip2n = P + S; D = S; if (ip2n >= N) { S++; N += 128; } }
+        }
         bool const vk = active && (pk + dk + 1 < ilimit);          // loop condition ip3 < ilimit for this iteration
         uint32_t const validMask = gballot(vk);
         // ---- open rep2 loop first (:264-285): same answer in every lane of the group ----
@@ -416,12 +429,16 @@ __global__ void __launch_bounds__(32 * kMatchWarps) enc_match_group_kernel(EncPa
         if (vk && !odd && rep1) { int const r = pk + dk; repHit = rd32(src + r) == rd32(src + r - (int)rep1); }
         uint32_t const h = hash_val(x, hlog, mls);
         uint32_t const tv = vk ? __ldcg(T + h) : 0u;
+        constexpr bool TAG = !MB;
         uint32_t const peers = (__match_any_sync(FULL, vk ? (h | (g << 24)) : (0x80000000u | lane)) >> gbase) & LOW;
         uint32_t const lower = peers & ((1u << l) - 1u);
         int const cl = lower ? 31 - __clz((int)lower) : (int)l;
         int const cq = __shfl_sync(FULL, q, gbase + cl);
-        int const cand = lower ? cq : (int)tv - 2;                  // table stores position + 2, 0 = empty
-        bool const hit = vk && cand >= lowPos && rd32(src + cand) == cur4;   // idx >= prefixStartIndex
+        uint32_t const cq4 = __shfl_sync(FULL, cur4, gbase + cl);  // a candidate forwarded from a lower lane of the window: its bytes are in that lane's registers
+        int const cand = lower ? cq : (int)(TAG ? (tv & kPosMask) : tv) - 2;                  // table stores position + 2, 0 = empty
+        bool const maybe = vk && !lower && cand >= lowPos && (!TAG || (tv >> kPosBits) == tag4(cur4));   // idx >= prefixStartIndex
+        uint32_t const c4 = maybe ? rd32(src + cand) : 0u;
+        bool const hit = lower ? (vk && cq4 == cur4) : (maybe && c4 == cur4);
         uint32_t key = 0xFFFFFFFFu;                                 // 0: rep2 at ip0; 1 + 3k: repcode at ip2; 2 + 3k / 3 + 3k: hash hit at ip0 / ip1
         if (hit) key = 3 * k + 2 + odd;
         if (repHit) key = 3 * k + 1;
@@ -435,9 +452,9 @@ __global__ void __launch_bounds__(32 * kMatchWarps) enc_match_group_kernel(EncPa
         {
             uint32_t const lastLane = type < 0 ? (uint32_t)GS - 1 : 2 * ke + 1;
             uint32_t const peersC = peers & (lastLane >= 31 ? FULL : ((2u << lastLane) - 1u));
-            if (vk && type != 3 && l <= lastLane && ((peersC >> l) >> 1) == 0) T[h] = (uint32_t)q + 2;
+            if (vk && type != 3 && l <= lastLane && ((peersC >> l) >> 1) == 0) T[h] = tab_entry<TAG>((uint32_t)q + 2, cur4);
         }
-        if (type == 3 && l == 0) T[hash_val(rd64(src + ip0), hlog, mls)] = (uint32_t)ip0 + 2;     // :278
+        if (type == 3 && l == 0) { uint64_t const xi = rd64(src + ip0); T[hash_val(xi, hlog, mls)] = tab_entry<TAG>((uint32_t)ip0 + 2, (uint32_t)xi); }     // :278
         // ---- match geometry (group-uniform) ----
         int const pke = __shfl_sync(FULL, pk, gbase + 2 * ke), dke = __shfl_sync(FULL, dk, gbase + 2 * ke);
         uint32_t const evLane = 2 * ke + (type == 2 ? 1u : 0u);
@@ -483,10 +500,11 @@ __global__ void __launch_bounds__(32 * kMatchWarps) enc_match_group_kernel(EncPa
             nseq++;
             int const mend = mpos + mlen;
             if (l == 0) {
-                if (type == 2 && pke + dke < mend) { int const pp = pke + dke; T[hash_val(rd64(src + pp), hlog, mls)] = (uint32_t)pp + 2; }   // `if (ip1 < ip0) hashTable[hash1] = ip1`
+                if (type == 2 && pke + dke < mend) { int const pp = pke + dke; uint64_t const xp = rd64(src + pp); T[hash_val(xp, hlog, mls)] = tab_entry<TAG>((uint32_t)pp + 2, (uint32_t)xp); }   // `if (ip1 < ip0) hashTable[hash1] = ip1`
                 if (type != 3 && mend <= ilimit) {
-                    T[hash_val(rd64(src + current0 + 2), hlog, mls)] = (uint32_t)current0 + 2 + 2;
-                    T[hash_val(rd64(src + mend - 2), hlog, mls)] = (uint32_t)(mend - 2) + 2;
+                    uint64_t const xa = rd64(src + current0 + 2), xb = rd64(src + mend - 2);
+                    T[hash_val(xa, hlog, mls)] = tab_entry<TAG>((uint32_t)current0 + 2 + 2, (uint32_t)xa);
+                    T[hash_val(xb, hlog, mls)] = tab_entry<TAG>((uint32_t)(mend - 2) + 2, (uint32_t)xb);
                 }
             }
             ip0 = mend; anchor = mend;
@@ -1810,7 +1828,9 @@ bool enc_enqueue(EncArena& A, cudaStream_t stream, cudaStream_t copyStream, size
                 enc_entropy_kernel<true, 1><<<w.n[3], kEntThreads, 0, stream>>>(p, dw + w.off[3], wave);
             }
         } else {
-            if (w.n[0]) enc_match_group_kernel<16, false><<<(w.n[0] + 2 * kMatchWarps - 1) / (2 * kMatchWarps), 32 * kMatchWarps, 0, stream>>>(p, dw + w.off[0], w.n[0], 0u);
+            static int const gsFast = []() { const char* e = getenv("ZSTDB200_MATCH_GS"); return e ? atoi(e) : 16; }();      // developer knob
+            if (w.n[0] && gsFast == 8) enc_match_group_kernel<8, false><<<(w.n[0] + 4 * kMatchWarps - 1) / (4 * kMatchWarps), 32 * kMatchWarps, 0, stream>>>(p, dw + w.off[0], w.n[0], 0u);
+            else if (w.n[0]) enc_match_group_kernel<16, false><<<(w.n[0] + 2 * kMatchWarps - 1) / (2 * kMatchWarps), 32 * kMatchWarps, 0, stream>>>(p, dw + w.off[0], w.n[0], 0u);
             if (w.n[1]) enc_match_kernel<<<(w.n[1] + 31) / 32, 32, 0, stream>>>(p, dw + w.off[1], w.n[1], 0u);
             if (w.n[2]) enc_match_dfast_group_kernel<16, false><<<(w.n[2] + 2 * kMatchWarps - 1) / (2 * kMatchWarps), 32 * kMatchWarps, 0, stream>>>(p, dw + w.off[2], w.n[2], 0u);
             if (ev3) ENC_CUDA(cudaEventRecord(ev3[1], stream));
@@ -1840,6 +1860,7 @@ void enc_set_overlap_mode(bool overlap)
     int const x = overlap ? pct : (int)cudaSharedmemCarveoutDefault;
     auto const A = cudaFuncAttributePreferredSharedMemoryCarveout;
     cudaFuncSetAttribute(enc_match_group_kernel<16, false>, A, x);
+    cudaFuncSetAttribute(enc_match_group_kernel<8, false>, A, x);
     cudaFuncSetAttribute(enc_match_group_kernel<16, true>, A, x);
     cudaFuncSetAttribute(enc_match_dfast_group_kernel<16, false>, A, x);
     cudaFuncSetAttribute(enc_match_dfast_group_kernel<16, true>, A, x);
