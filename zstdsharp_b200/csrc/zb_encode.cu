@@ -563,6 +563,7 @@ __global__ void __launch_bounds__(32 * kMatchWarps) enc_match_dfast_group_kernel
     uint32_t nseq = 0;
     int step = 1, nextStep = ip + 256;
     bool afterMatch = false;
+    constexpr bool TAG = !MB;      // single-block frames: entries carry a 14-bit tag of the four bytes at the position (see enc_match_group_kernel)
     auto gballot = [&](bool pr) -> uint32_t { return (__ballot_sync(FULL, pr) >> gbase) & LOW; };
     auto hashL = [&](uint64_t x) { return (uint32_t)((x * 0xCF1BBCDCB7A56463ull) >> (64 - hBitsL)); };
     // common prefix of src[a..) and src[b..) by the group, lane l compares 4 bytes per round (ZSTD_count :264); valid in every lane
@@ -612,9 +613,15 @@ __global__ void __launch_bounds__(32 * kMatchWarps) enc_match_dfast_group_kernel
         uint32_t const lowL = peersL & ((1u << l) - 1u), lowS = peersS & ((1u << l) - 1u);
         int const fl = lowL ? 31 - __clz((int)lowL) : (int)l, fs = lowS ? 31 - __clz((int)lowS) : (int)l;
         int const pfl = __shfl_sync(FULL, pj, gbase + fl), pfs = __shfl_sync(FULL, pj, gbase + fs);
-        int const candL = lowL ? pfl : (int)tl - 2, candS = lowS ? pfs : (int)ts - 2;     // tables store position + 2; valid iff index > 2
-        bool const Lhit = rdok && candL > lowPos && rd64(src + candL) == x;          // idx > prefixLowestIndex
-        bool const Shit = probe && candS > lowPos && rd32(src + candS) == (uint32_t)x;
+        int const candL = lowL ? pfl : (int)(TAG ? (tl & kPosMask) : tl) - 2, candS = lowS ? pfs : (int)(TAG ? (ts & kPosMask) : ts) - 2;     // tables store position + 2; valid iff index > 2
+        // candidates forwarded from a lower lane of the window are compared in registers; table candidates are fetched only when the tag agrees
+        uint64_t const xfl = __shfl_sync(FULL, x, gbase + fl); uint32_t const xfs = (uint32_t)__shfl_sync(FULL, x, gbase + fs);
+        uint32_t const myTag = tag4((uint32_t)x);
+        bool const mayL = rdok && !lowL && candL > lowPos && (!TAG || (tl >> kPosBits) == myTag);          // idx > prefixLowestIndex
+        bool const mayS = probe && !lowS && candS > lowPos && (!TAG || (ts >> kPosBits) == myTag);
+        uint64_t const cL8 = mayL ? rd64(src + candL) : 0ull; uint32_t const cS4 = mayS ? rd32(src + candS) : 0u;
+        bool const Lhit = lowL ? (rdok && candL > lowPos && xfl == x) : (mayL && cL8 == x);
+        bool const Shit = lowS ? (probe && candS > lowPos && xfs == (uint32_t)x) : (mayS && cS4 == (uint32_t)x);
         uint32_t key = 0xFFFFFFFFu;                                 // 0: offset_2 repeat at ip; 1+3j: repcode at ip+1; 2+3j: long at ip; 3+3j: short at ip
         if (probe) { if (Shit) key = 3 * l + 3; if (Lhit) key = 3 * l + 2; if (repHit) key = 3 * l + 1; }
         if (r2hit) key = 0;
@@ -628,11 +635,11 @@ __global__ void __launch_bounds__(32 * kMatchWarps) enc_match_dfast_group_kernel
             uint32_t const lastLane = type < 0 ? (uint32_t)GS - 2 : je;
             uint32_t const keep = (2u << lastLane) - 1u;
             if (probe && type != 3 && l <= lastLane) {
-                if ((((peersL & keep) >> l) >> 1) == 0) TL[hl] = (uint32_t)pj + 2;
-                if ((((peersS & keep) >> l) >> 1) == 0) TS[hs] = (uint32_t)pj + 2;
+                if ((((peersL & keep) >> l) >> 1) == 0) TL[hl] = tab_entry<TAG>((uint32_t)pj + 2, (uint32_t)x);
+                if ((((peersS & keep) >> l) >> 1) == 0) TS[hs] = tab_entry<TAG>((uint32_t)pj + 2, (uint32_t)x);
             }
         }
-        if (type == 3 && l == 0) { uint64_t const xi = rd64(src + ip); TS[hash_val(xi, hBitsS, mls)] = (uint32_t)ip + 2; TL[hashL(xi)] = (uint32_t)ip + 2; }   // :237-238
+        if (type == 3 && l == 0) { uint64_t const xi = rd64(src + ip); TS[hash_val(xi, hBitsS, mls)] = tab_entry<TAG>((uint32_t)ip + 2, (uint32_t)xi); TL[hashL(xi)] = tab_entry<TAG>((uint32_t)ip + 2, (uint32_t)xi); }   // :237-238
         // ---- event data (group-uniform) ----
         int const pe = __shfl_sync(FULL, pj, gbase + je), se = __shfl_sync(FULL, sj, gbase + je);
         int const cLe = __shfl_sync(FULL, candL, gbase + je), cSe = __shfl_sync(FULL, candS, gbase + je);
@@ -640,6 +647,7 @@ __global__ void __launch_bounds__(32 * kMatchWarps) enc_match_dfast_group_kernel
         bool const nextLong = __shfl_sync(FULL, (int)Lhit, gbase + nx) != 0;       // long match at ip1 (:167-177); Lhit implies 8 readable bytes there
         int const cLn = __shfl_sync(FULL, candL, gbase + nx);
         uint32_t const hln = __shfl_sync(FULL, hl, gbase + nx);
+        uint32_t const x4n = (uint32_t)__shfl_sync(FULL, x, gbase + nx);
         int const p1e = pe + se;                                    // ip1 of the event position
         int mpos = 0, msrc = 0, mlen = 0, curr = pe; uint32_t offcode = 0; int base8 = 4;
         bool bext = false;
@@ -666,7 +674,7 @@ __global__ void __launch_bounds__(32 * kMatchWarps) enc_match_dfast_group_kernel
             if (type == 1 || type == 2) {
                 uint32_t const offset = (uint32_t)(mpos - msrc);
                 off2 = off1; off1 = offset; offcode = offset + 2;
-                if (l == 0 && se < 4 && p1e <= ilimit) TL[hln] = (uint32_t)p1e + 2;   // complementary insertion (:210-213): hashLong[hl1] = ip1
+                if (l == 0 && se < 4 && p1e <= ilimit) TL[hln] = tab_entry<TAG>((uint32_t)p1e + 2, x4n);   // complementary insertion (:210-213): hashLong[hl1] = ip1
             }
             if (l == 0) { oLL[nseq] = (uint32_t)(mpos - anchor); oOF[nseq] = offcode + 1; oML[nseq] = (uint32_t)mlen - 3; }
             nseq++;
@@ -674,10 +682,10 @@ __global__ void __launch_bounds__(32 * kMatchWarps) enc_match_dfast_group_kernel
             if (l == 0 && type != 3 && mend <= ilimit) {             // :221-229
                 int const ins = curr + 2;
                 uint64_t const xa = rd64(src + ins), xb = rd64(src + mend - 2), xc = rd64(src + mend - 1);
-                TL[hashL(xa)] = (uint32_t)ins + 2;
-                TL[hashL(xb)] = (uint32_t)(mend - 2) + 2;
-                TS[hash_val(xa, hBitsS, mls)] = (uint32_t)ins + 2;
-                TS[hash_val(xc, hBitsS, mls)] = (uint32_t)(mend - 1) + 2;
+                TL[hashL(xa)] = tab_entry<TAG>((uint32_t)ins + 2, (uint32_t)xa);
+                TL[hashL(xb)] = tab_entry<TAG>((uint32_t)(mend - 2) + 2, (uint32_t)xb);
+                TS[hash_val(xa, hBitsS, mls)] = tab_entry<TAG>((uint32_t)ins + 2, (uint32_t)xa);
+                TS[hash_val(xc, hBitsS, mls)] = tab_entry<TAG>((uint32_t)(mend - 1) + 2, (uint32_t)xc);
             }
             ip = mend; anchor = mend;
             afterMatch = true;
