@@ -80,16 +80,16 @@ static size_t pipe_items() { static int v = env_int("ZSTDB200_PIPE_ITEMS", 4096,
 
 // scratch of one decode pass (DecPass layout, zb_decode.cuh)
 struct DecArena {
-    DevBuf dItems, dInit, dHuf, dFse, dLit, dSeq, dHufList, dSeqList, dCounters, dResults;
+    DevBuf dItems, dInit, dHuf, dFse, dLit, dSeq, dHufList, dSeqList, dRawList, dCounters, dResults;
     PinBuf hInit, hCounters, hResults;
     bool ensure(size_t m) {
         return dItems.ensure(m * sizeof(DecItem)) && dInit.ensure(m * sizeof(DecItemInit)) && hInit.ensure(m * sizeof(DecItemInit)) &&
                dHuf.ensure(m * kHufTableEntries * 2) && dFse.ensure(m * kFseTableEntries * 4) && dLit.ensure(m * (size_t)kLitStride) &&
-               dSeq.ensure(m * (size_t)kSeqCap * 8) && dHufList.ensure(m * 4) && dSeqList.ensure(m * 4) &&
+               dSeq.ensure(m * (size_t)kSeqCap * 8) && dHufList.ensure(m * 4) && dSeqList.ensure(m * 4) && dRawList.ensure(m * 4) &&
                dCounters.ensure(64) && hCounters.ensure(64) && dResults.ensure(m * 8) && hResults.ensure(m * 8);
     }
     void release() {
-        DevBuf* d[] = {&dItems, &dInit, &dHuf, &dFse, &dLit, &dSeq, &dHufList, &dSeqList, &dCounters, &dResults};
+        DevBuf* d[] = {&dItems, &dInit, &dHuf, &dFse, &dLit, &dSeq, &dHufList, &dSeqList, &dRawList, &dCounters, &dResults};
         for (auto* b : d) b->release();
         PinBuf* h[] = {&hInit, &hCounters, &hResults};
         for (auto* b : h) b->release();
@@ -208,7 +208,7 @@ static bool decode_enqueue(Engine& E, DecArena& A, cudaStream_t stream, size_t m
     p.items = A.dItems.as<DecItem>(); p.nItems = (uint32_t)m; p.src = d_src; p.dst = d_dst;
     p.hufTable = A.dHuf.as<uint16_t>(); p.fseTable = A.dFse.as<uint32_t>(); p.litBuf = A.dLit.as<uint8_t>();
     p.seq = A.dSeq.as<uint2>();
-    p.defaultFse = E.dDefaultFse.as<uint32_t>(); p.hufList = A.dHufList.as<uint32_t>(); p.seqList = A.dSeqList.as<uint32_t>();
+    p.defaultFse = E.dDefaultFse.as<uint32_t>(); p.hufList = A.dHufList.as<uint32_t>(); p.seqList = A.dSeqList.as<uint32_t>(); p.rawList = A.dRawList.as<uint32_t>();
     p.counters = A.dCounters.as<uint32_t>(); p.results = A.hResults.as<uint64_t>();
     p.dictHuf = nullptr; p.dictFse = nullptr; p.dictBytes = nullptr; p.dictInfo = nullptr;
     if (E.dictLoaded) { p.dictHuf = E.dDictHuf.as<uint16_t>(); p.dictFse = E.dDictFse.as<uint32_t>(); p.dictBytes = E.dDict.as<uint8_t>(); p.dictInfo = E.dDictInfo.as<uint32_t>(); }
@@ -223,7 +223,7 @@ static bool decode_enqueue(Engine& E, DecArena& A, cudaStream_t stream, size_t m
     for (uint32_t w = 0; w < nWaves; w++) {
         if (timeEv && w == 0) dec_launch_wave_timed(p, stream, &timeEv[2]);   // records timeEv[2..6] between the kernels of the first wave
         else dec_launch_wave(p, stream);
-        E.launches += 5;
+        E.launches += 6;
     }
     dec_launch_finish(p, stream); E.launches++;
     if (timeEv) ZB_CUDA(cudaEventRecord(timeEv[1], stream));

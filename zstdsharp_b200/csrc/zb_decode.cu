@@ -14,6 +14,7 @@
 //   dec_exec_kernel      warp   / item   literal + match copies through a shared-memory output tile, raw/RLE blocks, XXH64 check
 //   dec_dict_kernel      thread          parses a loaded dictionary once (entropy tables, repcodes); dec_dict_prefill_kernel copies its
 //                                        content in front of every item's output slot
+#include <algorithm>
 #include "zb_decode.cuh"
 
 namespace zb {
@@ -585,6 +586,7 @@ __global__ void __launch_bounds__(kSetupWarps * 32) dec_setup_kernel(DecPass p)
             it.nbSeq = 0; it.blockOut = 0; it.seqLitEnd = 0;
             if (type != kBlkCompressed) {
                 if (cs > capLeft) setup_fail(it, kDstSizeTooSmall);     // ZSTD_copyRawBlock :1004 / ZSTD_setRleBlock :1029
+                else if (cs) { uint32_t const slot = atomicAdd(&p.counters[4], 1u); p.rawList[slot] = item; }
                 break;
             }
             // ---- compressed block: ZSTD_decompressBlock_internal, ZstdDecompressBlock.cs:3090 ----
@@ -1425,12 +1427,8 @@ __global__ void __launch_bounds__(kExecWarps * 32) dec_exec_kernel(DecPass p)
     uint32_t blockOut = 0;
     uint32_t const FULL = 0xFFFFFFFFu;
 
-    if (it.blkType == kBlkRaw) {
-        blockOut = it.blkSize;
-        warp_copy_g2g(dst + outBase, src + it.blkSrcOff, blockOut, lane);
-    } else if (it.blkType == kBlkRle) {
-        blockOut = it.blkSize;
-        warp_fill_g(dst + outBase, src[it.blkSrcOff], blockOut, lane);
+    if (it.blkType == kBlkRaw || it.blkType == kBlkRle) {
+        blockOut = it.blkSize;                       // the bytes were moved by dec_rawcopy_kernel, which runs before this kernel
     } else {
         uint8_t* const tileMem = s_exec + warp * kExecTileMem;
         uint32_t const litSize = it.litSize;
@@ -1634,6 +1632,70 @@ __global__ void __launch_bounds__(kExecWarps * 32) dec_exec_kernel(DecPass p)
     }
 }
 
+// =====================================================================================================
+//  Raw and RLE blocks (ZSTD_copyRawBlock / ZSTD_setRleBlock, ZstdDecompress.cs:1004, :1029): a streaming copy, the one part of the
+//  decoder that is bound by HBM bandwidth.  Persistent CTAs walk (block, 64 KiB half) units (smaller units spent more time on the dependent descriptor loads than on the copy).  Destination chunks are 16-byte
+//  aligned; the source is read as ALIGNED 16-byte words (the chunk and its successor, which the neighbouring thread also reads: an
+//  L1 hit) and shifted into place, four chunks per thread in flight.  cp.async.bulk (TMA) cannot do this copy: it needs both
+//  addresses 16-byte aligned, and a raw block sits 12 bytes into its frame while its destination is frame-aligned.
+// =====================================================================================================
+constexpr uint32_t kRawSeg = 65536, kRawSegsPerBlock = kBlockSizeMax / kRawSeg, kRawThreads = 256;
+__global__ void __launch_bounds__(kRawThreads) dec_rawcopy_kernel(DecPass p)
+{
+    uint32_t const nUnits = p.counters[4] * kRawSegsPerBlock;
+    for (uint32_t u = blockIdx.x; u < nUnits; u += gridDim.x) {
+        DecItem const& it = p.items[p.rawList[u / kRawSegsPerBlock]];
+        if (it.status != kStRunning) continue;
+        uint32_t const lo = (u % kRawSegsPerBlock) * kRawSeg, size = it.blkSize;
+        if (lo >= size) continue;
+        uint32_t n = min(kRawSeg, size - lo);
+        uint8_t* dst = p.dst + it.dstOff + it.outPos + lo;
+        uint32_t const t = threadIdx.x;
+        uint32_t const head = min(n, (uint32_t)((16 - ((uintptr_t)dst & 15)) & 15));
+        if (it.blkType == kBlkRle) {
+            uint32_t const byte = p.src[it.srcOff + it.blkSrcOff], w = byte * 0x01010101u;
+            if (t < head) dst[t] = (uint8_t)byte;
+            dst += head; n -= head;
+            uint32_t const nChunks = n >> 4;
+            for (uint32_t c = t; c < nChunks; c += kRawThreads) *(uint4*)(dst + 16 * (size_t)c) = make_uint4(w, w, w, w);
+            uint32_t const done = nChunks << 4;
+            if (t < n - done) dst[done + t] = (uint8_t)byte;
+            continue;
+        }
+        const uint8_t* src = p.src + it.srcOff + it.blkSrcOff + lo;
+        if (t < head) dst[t] = src[t];
+        dst += head; src += head; n -= head;
+        uint32_t const sh = (uint32_t)((uintptr_t)src & 15), w0 = sh >> 2, bsh = (sh & 3) * 8;
+        const uint4* const s4 = (const uint4*)(src - sh);
+        uint32_t const nChunks = n >> 4;
+        for (uint32_t c0 = t; c0 < nChunks; c0 += 4 * kRawThreads) {
+            uint4 a[4], b[4];
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                uint32_t const c = c0 + kRawThreads * k;
+                a[k] = c < nChunks ? __ldcs(s4 + c) : make_uint4(0, 0, 0, 0);
+                b[k] = (c < nChunks && sh) ? __ldcs(s4 + c + 1) : make_uint4(0, 0, 0, 0);
+            }
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                uint32_t const c = c0 + kRawThreads * k;
+                uint32_t v0, v1, v2, v3, v4;
+                switch (w0) {               // uniform for the unit
+                case 0: v0 = a[k].x; v1 = a[k].y; v2 = a[k].z; v3 = a[k].w; v4 = b[k].x; break;
+                case 1: v0 = a[k].y; v1 = a[k].z; v2 = a[k].w; v3 = b[k].x; v4 = b[k].y; break;
+                case 2: v0 = a[k].z; v1 = a[k].w; v2 = b[k].x; v3 = b[k].y; v4 = b[k].z; break;
+                default: v0 = a[k].w; v1 = b[k].x; v2 = b[k].y; v3 = b[k].z; v4 = b[k].w; break;
+                }
+                uint4 v;
+                v.x = __funnelshift_r(v0, v1, bsh); v.y = __funnelshift_r(v1, v2, bsh); v.z = __funnelshift_r(v2, v3, bsh); v.w = __funnelshift_r(v3, v4, bsh);
+                if (c < nChunks) __stcs((uint4*)(dst + 16 * (size_t)c), v);
+            }
+        }
+        uint32_t const done = nChunks << 4;
+        if (t < n - done) dst[done + t] = src[done + t];
+    }
+}
+
 __global__ void dec_finish_kernel(DecPass p)
 {
     uint32_t const i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1646,7 +1708,7 @@ __global__ void dec_finish_kernel(DecPass p)
     p.results[i] = r;
 }
 
-__global__ void dec_reset_counters_kernel(uint32_t* counters) { if (threadIdx.x < 3) counters[threadIdx.x] = 0; }
+__global__ void dec_reset_counters_kernel(uint32_t* counters) { if (threadIdx.x < 3) counters[threadIdx.x] = 0; if (threadIdx.x == 4) counters[4] = 0; }
 
 // opt-in shared memory sizes are a per-device function attribute: set them once per device
 static void dec_set_attrs()
@@ -1666,7 +1728,16 @@ static void dec_set_attrs()
     cudaFuncSetAttribute(dec_seq_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
     cudaFuncSetAttribute(dec_exec_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
     cudaFuncSetAttribute(dec_finish_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+    cudaFuncSetAttribute(dec_rawcopy_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
     done[dev] = true;
+}
+
+// persistent grid: 8 CTAs of 256 threads per SM at most, never more CTAs than there can be units
+static unsigned raw_grid(const DecPass& p)
+{
+    static int sms = 0;
+    if (!sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); if (sms <= 0) sms = 148; }
+    return (unsigned)std::min<uint64_t>((uint64_t)sms * 8, (uint64_t)p.nItems * kRawSegsPerBlock);
 }
 
 void dec_launch_wave(const DecPass& p, cudaStream_t s)
@@ -1676,6 +1747,7 @@ void dec_launch_wave(const DecPass& p, cudaStream_t s)
     dec_set_attrs();
     dec_huf_kernel<<<(p.nItems + kHufItemsPerCta - 1) / kHufItemsPerCta, kHufThreads, kHufSmemBytes, s>>>(p);
     dec_seq_kernel<<<(p.nItems + kSeqItemsPerCta - 1) / kSeqItemsPerCta, 32, kSeqSmemBytes, s>>>(p);
+    dec_rawcopy_kernel<<<raw_grid(p), kRawThreads, 0, s>>>(p);
     dec_exec_kernel<<<(p.nItems + kExecWarps - 1) / kExecWarps, kExecWarps * 32, kExecWarps * kExecTileMem, s>>>(p);
 }
 
@@ -1690,6 +1762,7 @@ void dec_launch_wave_timed(const DecPass& p, cudaStream_t s, cudaEvent_t* ev)
     cudaEventRecord(ev[2], s);
     dec_seq_kernel<<<(p.nItems + kSeqItemsPerCta - 1) / kSeqItemsPerCta, 32, kSeqSmemBytes, s>>>(p);
     cudaEventRecord(ev[3], s);
+    dec_rawcopy_kernel<<<raw_grid(p), kRawThreads, 0, s>>>(p);
     dec_exec_kernel<<<(p.nItems + kExecWarps - 1) / kExecWarps, kExecWarps * 32, kExecWarps * kExecTileMem, s>>>(p);
     cudaEventRecord(ev[4], s);
 }

@@ -93,7 +93,8 @@ struct DecPass {
     const uint32_t* defaultFse;  // predefined LL|ML|OF tables (ZstdDecompressBlock.cs:398/:857/:1092)
     uint32_t* hufList;      // item indices that need literal decoding this wave
     uint32_t* seqList;      // item indices that need sequence decoding this wave
-    uint32_t* counters;     // [0] hufCount [1] seqCount [2] running items after this wave [3] max blocks (scan)
+    uint32_t* rawList;      // item indices whose block of this wave is raw or RLE (copied / filled by dec_rawcopy_kernel)
+    uint32_t* counters;     // [0] hufCount [1] seqCount [2] running items after this wave [3] max blocks (scan) [4] rawCount
     uint64_t* results;      // per item: regenerated size or error code
     // dictionary (all null / 0 without one): tables in the layout of hufTable / fseTable, the raw dictionary bytes, info words
     const uint16_t* dictHuf; const uint32_t* dictFse; const uint8_t* dictBytes; const uint32_t* dictInfo;
