@@ -19,19 +19,19 @@
  * ===================================================================================== */
 typedef struct { U32 windowLog, chainLog, hashLog, searchLog, minMatch, targetLength; int strategy; } cParams_t;
 
-static const cParams_t zo_defaultCParameters[4][4] = {
+static const cParams_t zo_defaultCParameters[4][5] = {   /* rows 0..4; row 4 only where it is still ZSTD_dfast (else strategy 0 = not restated) */
     {   /* "default" - for any srcSize > 256 KB            Clevels.cs:13-43  */
         { 19, 12, 13, 1, 6, 1, ZSTD_fast }, { 19, 13, 14, 1, 7, 0, ZSTD_fast },
-        { 20, 15, 16, 1, 6, 0, ZSTD_fast }, { 21, 16, 17, 1, 5, 0, ZSTD_dfast } },
+        { 20, 15, 16, 1, 6, 0, ZSTD_fast }, { 21, 16, 17, 1, 5, 0, ZSTD_dfast }, { 21, 18, 18, 1, 5, 0, ZSTD_dfast } },
     {   /* for srcSize <= 256 KB                           Clevels.cs:246-276 */
         { 18, 12, 13, 1, 5, 1, ZSTD_fast }, { 18, 13, 14, 1, 6, 0, ZSTD_fast },
-        { 18, 14, 14, 1, 5, 0, ZSTD_dfast }, { 18, 16, 16, 1, 4, 0, ZSTD_dfast } },
+        { 18, 14, 14, 1, 5, 0, ZSTD_dfast }, { 18, 16, 16, 1, 4, 0, ZSTD_dfast }, { 18, 16, 17, 3, 5, 2, 0 /* ZSTD_greedy */ } },
     {   /* for srcSize <= 128 KB                           Clevels.cs:480-510 */
         { 17, 12, 12, 1, 5, 1, ZSTD_fast }, { 17, 12, 13, 1, 6, 0, ZSTD_fast },
-        { 17, 13, 15, 1, 5, 0, ZSTD_fast }, { 17, 15, 16, 2, 5, 0, ZSTD_dfast } },
+        { 17, 13, 15, 1, 5, 0, ZSTD_fast }, { 17, 15, 16, 2, 5, 0, ZSTD_dfast }, { 17, 17, 17, 2, 4, 0, ZSTD_dfast } },
     {   /* for srcSize <= 16 KB                            Clevels.cs:713-743 */
         { 14, 12, 13, 1, 5, 1, ZSTD_fast }, { 14, 14, 15, 1, 5, 0, ZSTD_fast },
-        { 14, 14, 15, 1, 4, 0, ZSTD_fast }, { 14, 14, 15, 2, 4, 0, ZSTD_dfast } },
+        { 14, 14, 15, 1, 4, 0, ZSTD_fast }, { 14, 14, 15, 2, 4, 0, ZSTD_dfast }, { 14, 14, 14, 4, 4, 2, 0 /* ZSTD_greedy */ } },
 };
 
 static cParams_t zo_adjustCParams(cParams_t cPar, U64 srcSize)   /* ZstdCompress.cs:2023, dictSize == 0, mode noAttachDict */
@@ -58,9 +58,17 @@ static int zo_getCParams_internal(cParams_t* out, int level, U64 srcSize)
     U32 const tableID = (rSize <= 256 * 1024) + (rSize <= 128 * 1024) + (rSize <= 16 * 1024);
     int row;
     if (level == 0) row = 3;                 /* ZSTD_CLEVEL_DEFAULT */
-    else if (level < 0 || level > 3) return -1;  /* outside the restated scope (levels 1..3) */
+    else if (level < 0) row = 0;             /* "entry 0 is baseline for fast mode" (ZstdCompress.cs:7901) */
+    else if (level > 4) return -1;           /* outside the restated scope (ZSTD_fast / ZSTD_dfast levels) */
     else row = level;
-    *out = zo_adjustCParams(zo_defaultCParameters[tableID][row], srcSize);
+    {   cParams_t cp = zo_defaultCParameters[tableID][row];
+        if (cp.strategy == 0) return -1;     /* level 4 is ZSTD_greedy for this size */
+        if (level < 0) {                     /* acceleration factor (:7918-7923); ZSTD_minCLevel() = -(1 << 17) */
+            int const clamped = level < -(1 << 17) ? -(1 << 17) : level;
+            cp.targetLength = (U32)(-clamped);
+        }
+        *out = zo_adjustCParams(cp, srcSize);
+    }
     /* ZSTD_getCParamsFromCCtxParams (:2156) re-applies ZSTD_adjustCParams_internal: idempotent */
     *out = zo_adjustCParams(*out, srcSize);
     return 0;
@@ -734,7 +742,7 @@ static size_t ZSTD_compressRleLiteralsBlock(void* dst, size_t dstCapacity, const
     ostart[flSize] = *(const BYTE*)src;
     return flSize + 1;
 }
-static size_t ZSTD_compressLiterals(const ZSTD_hufCTables_t* prevHuf, ZSTD_hufCTables_t* nextHuf, int strategy,
+static size_t ZSTD_compressLiterals(const ZSTD_hufCTables_t* prevHuf, ZSTD_hufCTables_t* nextHuf, int strategy, int disableLiteralCompression,
                                     void* dst, size_t dstCapacity, const void* src, size_t srcSize, unsigned suspectUncompressible)   /* :86 */
 {
     size_t const minGain = ZSTD_minGain(srcSize, strategy);
@@ -742,6 +750,7 @@ static size_t ZSTD_compressLiterals(const ZSTD_hufCTables_t* prevHuf, ZSTD_hufCT
     BYTE* const ostart = (BYTE*)dst; U32 singleStream = srcSize < 256;
     symbolEncodingType_e hType = set_compressed; size_t cLitSize;
     memcpy(nextHuf, prevHuf, sizeof(*prevHuf));
+    if (disableLiteralCompression) return ZSTD_noCompressLiterals(dst, dstCapacity, src, srcSize);      /* ZstdCompressLiterals.cs:100-101 */
     {   size_t const minLitSize = (prevHuf->repeatMode == HUF_repeat_valid) ? 6 : 63;
         if (srcSize <= minLitSize) return ZSTD_noCompressLiterals(dst, dstCapacity, src, srcSize); }
     if (dstCapacity < lhSize + 1) return ERROR(dstSize_tooSmall);
@@ -885,7 +894,7 @@ static size_t ZSTD_encodeSequences(void* dst, size_t dstCapacity, const FSE_CTab
 
 /* ZstdCompress.cs:3127 ZSTD_buildSequencesStatistics + :3236 ZSTD_entropyCompressSeqStore_internal */
 static size_t ZSTD_entropyCompressSeqStore_internal(seqStore_t* seqStorePtr, const ZSTD_entropyCTables_t* prevEntropy, ZSTD_entropyCTables_t* nextEntropy,
-                                                    int strategy, void* dst, size_t dstCapacity)
+                                                    int strategy, int disableLit, void* dst, size_t dstCapacity)
 {
     unsigned count[MaxSeq + 1];
     const zo_seqDef* const sequences = seqStorePtr->sequencesStart;
@@ -895,7 +904,7 @@ static size_t ZSTD_entropyCompressSeqStore_internal(seqStore_t* seqStorePtr, con
     {   const BYTE* const literals = seqStorePtr->litStart;
         size_t const numLiterals = (size_t)(seqStorePtr->lit - seqStorePtr->litStart);
         unsigned const suspectUncompressible = (nbSeq == 0) || (numLiterals / nbSeq >= 20);    /* SUSPECT_UNCOMPRESSIBLE_LITERAL_RATIO */
-        size_t const cSize = ZSTD_compressLiterals(&prevEntropy->huf, &nextEntropy->huf, strategy, op, dstCapacity, literals, numLiterals, suspectUncompressible);
+        size_t const cSize = ZSTD_compressLiterals(&prevEntropy->huf, &nextEntropy->huf, strategy, disableLit, op, dstCapacity, literals, numLiterals, suspectUncompressible);
         if (ERR_isError(cSize)) return cSize;
         op += cSize;
     }
@@ -947,9 +956,9 @@ static size_t ZSTD_entropyCompressSeqStore_internal(seqStore_t* seqStorePtr, con
 }
 
 static size_t ZSTD_entropyCompressSeqStore(seqStore_t* seqStorePtr, const ZSTD_entropyCTables_t* prevEntropy, ZSTD_entropyCTables_t* nextEntropy,
-                                           int strategy, void* dst, size_t dstCapacity, size_t srcSize)   /* :3357 */
+                                           int strategy, int disableLit, void* dst, size_t dstCapacity, size_t srcSize)   /* :3357 */
 {
-    size_t const cSize = ZSTD_entropyCompressSeqStore_internal(seqStorePtr, prevEntropy, nextEntropy, strategy, dst, dstCapacity);
+    size_t const cSize = ZSTD_entropyCompressSeqStore_internal(seqStorePtr, prevEntropy, nextEntropy, strategy, disableLit, dst, dstCapacity);
     if (cSize == 0) return 0;
     if ((cSize == ERROR(dstSize_tooSmall)) & (srcSize <= dstCapacity)) return 0;
     if (ERR_isError(cSize)) return cSize;
@@ -1232,7 +1241,9 @@ static size_t ZSTD_compressBlock_internal(zo_CCtx* zc, void* dst, size_t dstCapa
 {
     U32 const rleMaxLength = 25; size_t cSize; const BYTE* ip = (const BYTE*)src; BYTE* op = (BYTE*)dst;
     if (ZSTD_buildSeqStore(zc, src, srcSize)) { cSize = 0; goto out; }
-    cSize = ZSTD_entropyCompressSeqStore(&zc->seqStore, &zc->prevCBlock->entropy, &zc->nextCBlock->entropy, zc->cParams.strategy, dst, dstCapacity, srcSize);
+    /* ZSTD_literalsCompressionIsDisabled (ZstdCompressInternal.cs:483-498), ZSTD_ps_auto: fast strategy with an acceleration factor */
+    cSize = ZSTD_entropyCompressSeqStore(&zc->seqStore, &zc->prevCBlock->entropy, &zc->nextCBlock->entropy, zc->cParams.strategy,
+                                         zc->cParams.strategy == ZSTD_fast && zc->cParams.targetLength > 0, dst, dstCapacity, srcSize);
     if (frame && !zc->isFirstBlock && cSize < rleMaxLength && ZSTD_isRLE(ip, srcSize)) { cSize = 1; op[0] = ip[0]; }
 out:
     if (!ERR_isError(cSize) && cSize > 1) {   /* ZSTD_blockState_confirmRepcodesAndEntropyTables */
@@ -1309,8 +1320,8 @@ static size_t ZSTD_writeFrameHeader(void* dst, size_t dstCapacity, U32 windowLog
 
 /* Context buffers are sized once for the largest supported geometry (ZSTD_resetCCtx_internal :2548 reuses the
  * workspace the same way); the match-finder tables are re-zeroed for every frame (:2472, :2481-2484). */
-#define ZO_MAX_HASHLOG 17
-#define ZO_MAX_CHAINLOG 16
+#define ZO_MAX_HASHLOG 18
+#define ZO_MAX_CHAINLOG 18
 static size_t zo_ctx_buffers(zo_CCtx* c)
 {
     size_t const maxNbSeq = ZSTD_BLOCKSIZE_MAX / 3;

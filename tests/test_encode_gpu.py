@@ -264,3 +264,66 @@ def test_pipelined_host_path_byte_identical(comp, dec):
         want = o.compress(c, 1)
         assert f == want, _first_diff(f, want)
     assert dec.UnwrapBatch(frames) == [c.tobytes() for c in chunks]
+
+
+def test_more_than_32768_contiguous_small_items():
+    """one contiguous host run with more pieces than 4 pipelined sub-batches of 8192 can take (40000 x 4 KiB pages)
+    used to fail the whole call with ZSTD_error_GENERIC.  Every page must come back as the oracle's frame."""
+    import ctypes
+    from zstdsharp_b200 import Compressor, _native
+    lib = _native.lib
+    o = oracle()
+    n, page = 40000, 4096
+    data = np.tile(dg.text_like(64 * FRAME), 20)[:n * page].copy()
+    bound = Compressor.GetCompressBound(page)
+    out = np.empty(n * bound, dtype=np.uint8)
+    vp, st = ctypes.c_void_p, ctypes.c_size_t
+    sp = (vp * n)(*[data.ctypes.data + i * page for i in range(n)]); ss = (st * n)(*([page] * n))
+    dp = (vp * n)(*[out.ctypes.data + i * bound for i in range(n)]); dc = (st * n)(*([bound] * n)); res = (st * n)()
+    with Compressor(1) as c:
+        assert lib.ZSTDB200_compressBatch(c.handle, n, 1, sp, ss, dp, dc, res) == 0, lib.ZSTDB200_lastErrorString()
+    for i in list(range(0, n, 997)) + [n - 1, 32767, 32768, 32769]:
+        assert out[i * bound:i * bound + res[i]].tobytes() == o.compress(data[i * page:(i + 1) * page], 1), i
+
+
+def test_compressCCtx_ignores_context_parameters():
+    """ZSTD_compressCCtx derives everything from the level argument (ZstdCompress.cs:5772: contentSize 1, checksum 0), whatever
+    ZSTD_CCtx_setParameter stored; ZSTD_compress2 honours the stored parameters."""
+    from zstdsharp_b200 import Compressor, ZSTD_cParameter, _native
+    lib = _native.lib
+    o = oracle()
+    src = dg.text_like(FRAME)
+    cap = Compressor.GetCompressBound(FRAME)
+    out = np.empty(cap, dtype=np.uint8)
+    with Compressor(3) as c:
+        c.SetParameter(ZSTD_cParameter.ZSTD_c_checksumFlag, 1)
+        r = lib.ZSTD_compressCCtx(c.handle, out.ctypes.data, cap, src.ctypes.data, src.size, 1)
+        assert out[:r].tobytes() == o.compress(src, 1, checksum=0)
+        r = lib.ZSTD_compress2(c.handle, out.ctypes.data, cap, src.ctypes.data, src.size)
+        assert out[:r].tobytes() == o.compress(src, 3, checksum=1)
+
+
+@pytest.mark.parametrize("level", [-5, -4, -3, -2, -1, 4])
+def test_negative_levels_and_level4_byte_identical(level):
+    """Levels -5..-1 are ZSTD_fast with stepSize = targetLength + 1 and uncompressed literals (ZstdFast.cs:101, :334;
+    ZstdCompress.cs:7918-7923; the reference tests them: ZstdTest.cs:64-67); level 4 is ZSTD_dfast {17,17,17,2,4,0} for
+    16 KiB < n <= 128 KiB and {21,18,18,1,5,0} above 256 KiB (Clevels.cs row 4), ZSTD_greedy elsewhere -> parameter_unsupported."""
+    from zstdsharp_b200 import Compressor, ZstdException
+    o = oracle()
+    inputs = []
+    for wl in ("text", "silesia", "literal_mix", "incompressible"):
+        data = dg.WORKLOADS[wl](3 * FRAME)
+        inputs += [data[i * FRAME:(i + 1) * FRAME] for i in range(3)]
+    text = dg.text_like(4 * FRAME)
+    for n in (0, 1, 7, 8, 63, 64, 100, 1000, 4096, 16384, 16385, 20000, 65536, 100000, 131071, FRAME + 1, 200000, 300000, 3 * FRAME + 5):
+        inputs.append(text[:n])
+    ok = [a for a in inputs if not o.lib.zo_isError(o.compress_raw(a, level)[0])]
+    assert len(ok) >= (12 if level == 4 else len(inputs))
+    with Compressor(level) as c:
+        frames = c.WrapBatch(ok)
+        for a, f in zip(ok, frames):
+            assert f == o.compress(a, level), (level, a.size)
+        if level == 4:
+            with pytest.raises(ZstdException) as e:
+                c.Wrap(text[:1000])
+            assert int(e.value.Code) == 40

@@ -200,3 +200,31 @@ def test_handbuilt_tiny_four_stream_literals():
     o, r = oracle(), refdll()
     for f, expect in handbuilt_small_4stream_frames():
         assert o.decompress(f, len(expect)) == expect == r.decompress(f, len(expect))
+
+
+@pytest.mark.parametrize("level", [-5, -4, -3, -2, -1, -17, 4])
+def test_negative_levels_and_level4_match_the_dll(level):
+    """ZstdTest.cs:64-67 runs levels -5..-1 too; level 4 is restated only for the sizes where it is still ZSTD_dfast."""
+    from _cases import multiblock_inputs
+    o, r = oracle(), refdll()
+    n = 0
+    for wl in ("text", "silesia", "literal_mix", "incompressible"):
+        data = dg.WORKLOADS[wl](3 * FRAME)
+        for i in range(0, data.size, FRAME):
+            assert o.compress(data[i:i + FRAME], level) == r.compress(data[i:i + FRAME], level), (wl, i)
+            n += 1
+    text = dg.text_like(4 * FRAME)
+    for size in (0, 1, 7, 8, 63, 64, 100, 1000, 4096, 16384, 16385, 20000, 65536, 100000, 131071, FRAME + 1, 200000, 300000, 3 * FRAME + 5):
+        rv, _ = o.compress_raw(text[:size], level)
+        if o.lib.zo_isError(rv):
+            assert level == 4 and o.error_code(rv) == 40 and r.cparams(4, size)[6] > 2      # ZSTD_greedy and up: outside the restated scope
+            continue
+        if size:                                                   # ZSTD_getCParams reads a size hint of 0 as 'unknown'
+            assert o.cparams(level, size) == r.cparams(level, size)
+        assert o.compress(text[:size], level) == r.compress(text[:size], level), size
+        n += 1
+    for name, d in multiblock_inputs().items():
+        if not o.lib.zo_isError(o.compress_raw(d, level)[0]):
+            assert o.compress(d, level) == r.compress(d, level), name
+            n += 1
+    assert n >= 20

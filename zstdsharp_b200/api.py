@@ -107,8 +107,8 @@ def _ptr(a: np.ndarray) -> int:
 
 
 class Compressor:
-    MinCompressionLevel = 1                  # GPU path: ZSTD_fast/ZSTD_dfast levels only
-    MaxCompressionLevel = 3
+    MinCompressionLevel = -(1 << 17)         # Compressor.cs:12 ZSTD_minCLevel(): the negative levels are ZSTD_fast with an acceleration factor
+    MaxCompressionLevel = 4                  # GPU path: ZSTD_fast / ZSTD_dfast levels only (4 only for the input sizes where it is still ZSTD_dfast)
     DefaultCompressionLevel = 0              # Compressor.cs:10 (0 means level 3)
 
     def __init__(self, level: int = DefaultCompressionLevel):

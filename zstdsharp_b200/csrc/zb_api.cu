@@ -552,6 +552,21 @@ static size_t compress_batch_host(Engine& E, size_t n, int level, int checksum, 
     size_t np = 0;
     for (size_t i = 0; i < n; i++) { first[i] = np; np += !cut(srcSize[i]) ? 1 : (srcSize[i] + kBlockSizeMax - 1) / kBlockSizeMax; }
     first[n] = np;
+    // A pipelined pass takes at most kPipeMax sub-batches of 8192 pieces (one arena each): larger batches are run as consecutive slices
+    // of whole items (a single item with more pieces than that takes the non-pipelined path below, which loops over 8192-piece passes).
+    static int const encPipeCap = env_int("ZSTDB200_ENC_PIPE", 4, 1, kPipeMax);
+    size_t const sliceCap = (size_t)encPipeCap * kMaxItemsPerPass;
+    if (np > sliceCap && n > 1) {
+        size_t a = 0;
+        while (a < n) {
+            size_t b = a + 1;
+            while (b < n && first[b + 1] - first[a] <= sliceCap) b++;
+            size_t const rc = compress_batch_host(E, b - a, level, checksum, chunked, src + a, srcSize + a, dst + a, dstCap + a, result + a);
+            if (is_error(rc)) return rc;
+            a = b;
+        }
+        return 0;
+    }
     std::vector<Run> runs;
     find_runs(runs, n, src, srcSize);
     // One contiguous host buffer and enough pieces: sub-batches flow through H2D (sIn) -> kernels (sComp[k], one arena each)
@@ -559,7 +574,7 @@ static size_t compress_batch_host(Engine& E, size_t n, int level, int checksum, 
     // sub-batches are NOT run one after the other: their kernels overlap each other and the uploads that are still in flight.
     static int const encPipe = env_int("ZSTDB200_ENC_PIPE", 4, 1, kPipeMax);
     static int const encSub = env_int("ZSTDB200_ENC_SUB", 2048, 256, 8192);       // smallest sub-batch (pieces)
-    size_t const nSub = (runs.size() == 1 && np >= 4096) ? std::min<size_t>((size_t)encPipe, np / (size_t)encSub) : 1;
+    size_t const nSub = (runs.size() == 1 && np >= 4096 && np <= sliceCap) ? std::min<size_t>((size_t)encPipe, np / (size_t)encSub) : 1;
     std::vector<uint64_t> sOff(n); size_t sTotal = 16;
     if (nSub > 1) {
         size_t o = sTotal;
@@ -811,6 +826,17 @@ static int bind_thread_near_device(int device)
     return sched_setaffinity(0, sizeof(set), &set) == 0 ? 0 : -5;
 }
 
+// ZSTD_fast / ZSTD_dfast levels: the negative levels (ZSTD_fast with an acceleration factor), 0 (= 3), 1..3, and 4 for the input sizes where
+// it is still ZSTD_dfast (16 KiB < n <= 128 KiB and n > 256 KiB, Clevels.cs row 4; other sizes answer parameter_unsupported per item)
+static bool level_supported(int level) { return level >= -(1 << 17) && level <= 4; }
+
+// The entry points select the context's device (cudaSetDevice is per host thread); the caller's current device is put back on return.
+struct DeviceGuard {
+    int prev = -1;
+    DeviceGuard() { if (cudaGetDevice(&prev) != cudaSuccess) { prev = -1; (void)cudaGetLastError(); } }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
 static const char* error_name(uint32_t code)   // ErrorPrivate.cs:34-184
 {
     switch (code) {
@@ -868,7 +894,7 @@ size_t ZSTD_CCtx_setParameter(ZSTD_CCtx* cctx, int param, int value)
 {
     if (!cctx) return (size_t)make_error(zb::kGeneric);
     if (param == 100) {   // ZSTD_c_compressionLevel (ZSTD_cParameter.cs), bounds per ZSTD_cParam_getBounds (ZstdCompress.cs:444)
-        if (value < 0 || value > 3) return (size_t)make_error(zb::kParameterUnsupported);   // only fast/dfast levels are implemented on the GPU
+        if (!zb::level_supported(value)) return (size_t)make_error(zb::kParameterUnsupported);   // only fast/dfast levels are implemented on the GPU
         cctx->level = value; return 0;
     }
     if (param == 201) {   // ZSTD_c_checksumFlag
@@ -918,25 +944,34 @@ size_t ZSTD_DCtx_getParameter(const ZSTD_DCtx* dctx, int param, int* value)
 size_t ZSTDB200_compressBatch(ZSTD_CCtx* cctx, size_t n, int level, const void* const* src, const size_t* srcSize, void* const* dst, const size_t* dstCap, size_t* result)
 {
     if (!cctx) return (size_t)make_error(zb::kGeneric);
-    if (level < 0 || level > 3) { for (size_t i = 0; i < n; i++) result[i] = (size_t)make_error(zb::kParameterUnsupported); return 0; }
+    zb::DeviceGuard guard;
+    if (!zb::level_supported(level)) { for (size_t i = 0; i < n; i++) result[i] = (size_t)make_error(zb::kParameterUnsupported); return 0; }
     return zb::compress_batch_host(cctx->E, n, level, cctx->checksum, cctx->chunked, src, srcSize, dst, dstCap, result);
 }
 
+// ZSTD_compressCCtx (U/ZstdCompress.cs:5772): parameters derived from the level alone (contentSize 1, checksum 0), whatever was set
+// on the context with ZSTD_CCtx_setParameter; ZSTD_compress2 (:7138) is the entry point that honours the context's parameters.
 size_t ZSTD_compressCCtx(ZSTD_CCtx* cctx, void* dst, size_t dstCapacity, const void* src, size_t srcSize, int level)
 {
+    if (!cctx) return (size_t)make_error(zb::kGeneric);
+    if (!zb::level_supported(level)) return (size_t)make_error(zb::kParameterUnsupported);
+    zb::DeviceGuard guard;
     size_t r = 0; const void* s = src; void* d = dst;
-    size_t const rc = ZSTDB200_compressBatch(cctx, 1, level, &s, &srcSize, &d, &dstCapacity, &r);
+    size_t const rc = zb::compress_batch_host(cctx->E, 1, level, 0, 0, &s, &srcSize, &d, &dstCapacity, &r);
     return zb::is_error(rc) ? rc : r;
 }
 size_t ZSTD_compress2(ZSTD_CCtx* cctx, void* dst, size_t dstCapacity, const void* src, size_t srcSize)
 {
     if (!cctx) return (size_t)make_error(zb::kGeneric);
-    return ZSTD_compressCCtx(cctx, dst, dstCapacity, src, srcSize, cctx->level);
+    size_t r = 0; const void* s = src; void* d = dst;
+    size_t const rc = ZSTDB200_compressBatch(cctx, 1, cctx->level, &s, &srcSize, &d, &dstCapacity, &r);
+    return zb::is_error(rc) ? rc : r;
 }
 
 size_t ZSTDB200_decompressBatch(ZSTD_DCtx* dctx, size_t n, const void* const* src, const size_t* srcSize, void* const* dst, const size_t* dstCap, size_t* result)
 {
     if (!dctx) return (size_t)make_error(zb::kGeneric);
+    zb::DeviceGuard guard;
     return zb::decompress_batch_host(dctx->E, n, src, srcSize, dst, dstCap, result);
 }
 size_t ZSTD_decompressDCtx(ZSTD_DCtx* dctx, void* dst, size_t dstCapacity, const void* src, size_t srcSize)
@@ -949,6 +984,7 @@ size_t ZSTD_decompressDCtx(ZSTD_DCtx* dctx, void* dst, size_t dstCapacity, const
 size_t ZSTD_DCtx_loadDictionary(ZSTD_DCtx* dctx, const void* dict, size_t dictSize)
 {
     if (!dctx) return (size_t)make_error(zb::kGeneric);
+    zb::DeviceGuard guard;
     zb::Engine& E = dctx->E;
     if (!dict || dictSize == 0) { E.dictLoaded = false; return 0; }           // ZSTD_DCtx_loadDictionary(NULL, 0) clears (:2255)
     if (dictSize > 0x7FFFFFF0u) return (size_t)make_error(zb::kMemoryAllocation);
@@ -969,6 +1005,7 @@ size_t ZSTDB200_decompressBatchDevice(ZSTD_DCtx* dctx, size_t n, const void* d_s
                                       void* d_dst, const uint64_t* dstOffset, const size_t* dstCapacity, size_t* result)
 {
     if (!dctx) return (size_t)make_error(zb::kGeneric);
+    zb::DeviceGuard guard;
     zb::Engine& E = dctx->E;
     if (!E.init()) return (size_t)make_error(zb::kGeneric);
     if (E.dictLoaded) { zb::set_error("a dictionary is loaded: dictionary decoding lays the output out itself, use ZSTDB200_decompressBatch"); return (size_t)make_error(zb::kGeneric); }
@@ -983,11 +1020,12 @@ size_t ZSTDB200_compressBatchDevice(ZSTD_CCtx* cctx, size_t n, int level, const 
                                     void* d_dst, const uint64_t* dstOffset, const size_t* dstCapacity, size_t* result)
 {
     if (!cctx) return (size_t)make_error(zb::kGeneric);
+    zb::DeviceGuard guard;
     zb::Engine& E = cctx->E;
     if (!E.init() || !E.bind()) return (size_t)make_error(zb::kGeneric);
     E.launches = 0; memset(E.timings, 0, sizeof(E.timings));
     if (n == 0) return 0;
-    if (level < 0 || level > 3) { for (size_t i = 0; i < n; i++) result[i] = (size_t)make_error(zb::kParameterUnsupported); return 0; }
+    if (!zb::level_supported(level)) { for (size_t i = 0; i < n; i++) result[i] = (size_t)make_error(zb::kParameterUnsupported); return 0; }
     if (!zb::enc_compress_device(E.enc, E.stream, E.ev, n, level, cctx->checksum, (const uint8_t*)d_src, srcOffset, srcSize, (uint8_t*)d_dst, dstOffset, dstCapacity, result, E.timings, &E.launches))
         { zb::set_error(zb::enc_last_error()); return (size_t)make_error(zb::kGeneric); }
     return 0;

@@ -11,7 +11,6 @@
 // repcodes and Huffman table the blocks before it left behind):
 //   enc_match_group_kernel<16, MB>        16 lanes / block   exact ZSTD_fast parse (levels 1-2), speculative window of 8 reference iterations
 //   enc_match_dfast_group_kernel<16, MB>  16 lanes / block   exact ZSTD_dfast parse (level 3), 15 probe positions + 1 look-ahead per window
-//   enc_match_kernel                      lane / block       serial restatement, blocks below 64 bytes only
 //   enc_entropy_kernel<MB, 0>             CTA  / block       literal gather + histograms, Huffman table (new / repeated), parallel bit scatter of
 //                                                            the 4 Huffman streams, sequence codes + histograms, the three FSE tables and their descriptions
 //   enc_fse_chain_kernel<MB>              lane / FSE chain   the three FSE state chains of every block (3 x blocks lanes)
@@ -36,11 +35,11 @@ namespace zb {
 //  ZSTD_adjustCParams_internal (:2023).  Host-side integer logic, evaluated once per chunk.
 // ------------------------------------------------------------------------------------------------------------
 struct CParams { uint32_t windowLog, chainLog, hashLog, searchLog, minMatch, targetLength, strategy; };
-static const CParams kDefaultCParams[4][4] = {
-    {{19, 12, 13, 1, 6, 1, 1}, {19, 13, 14, 1, 7, 0, 1}, {20, 15, 16, 1, 6, 0, 1}, {21, 16, 17, 1, 5, 0, 2}},
-    {{18, 12, 13, 1, 5, 1, 1}, {18, 13, 14, 1, 6, 0, 1}, {18, 14, 14, 1, 5, 0, 2}, {18, 16, 16, 1, 4, 0, 2}},
-    {{17, 12, 12, 1, 5, 1, 1}, {17, 12, 13, 1, 6, 0, 1}, {17, 13, 15, 1, 5, 0, 1}, {17, 15, 16, 2, 5, 0, 2}},
-    {{14, 12, 13, 1, 5, 1, 1}, {14, 14, 15, 1, 5, 0, 1}, {14, 14, 15, 1, 4, 0, 1}, {14, 14, 15, 2, 4, 0, 2}},
+static const CParams kDefaultCParams[4][5] = {     // rows 0..4 (row 0 = base of the negative levels); strategy 0 = not a fast/dfast row (level 4 is ZSTD_greedy there)
+    {{19, 12, 13, 1, 6, 1, 1}, {19, 13, 14, 1, 7, 0, 1}, {20, 15, 16, 1, 6, 0, 1}, {21, 16, 17, 1, 5, 0, 2}, {21, 18, 18, 1, 5, 0, 2}},
+    {{18, 12, 13, 1, 5, 1, 1}, {18, 13, 14, 1, 6, 0, 1}, {18, 14, 14, 1, 5, 0, 2}, {18, 16, 16, 1, 4, 0, 2}, {18, 16, 17, 3, 5, 2, 0}},
+    {{17, 12, 12, 1, 5, 1, 1}, {17, 12, 13, 1, 6, 0, 1}, {17, 13, 15, 1, 5, 0, 1}, {17, 15, 16, 2, 5, 0, 2}, {17, 17, 17, 2, 4, 0, 2}},
+    {{14, 12, 13, 1, 5, 1, 1}, {14, 14, 15, 1, 5, 0, 1}, {14, 14, 15, 1, 4, 0, 1}, {14, 14, 15, 2, 4, 0, 2}, {14, 14, 14, 4, 4, 2, 0}},
 };
 static uint32_t h_highbit(uint32_t v) { return 31 - (uint32_t)__builtin_clz(v); }
 static CParams adjust_cparams(CParams c, uint64_t srcSize)
@@ -58,8 +57,11 @@ static CParams adjust_cparams(CParams c, uint64_t srcSize)
 static CParams get_cparams(int level, uint64_t srcSize)
 {
     uint32_t const tableID = (srcSize <= 256 * 1024) + (srcSize <= 128 * 1024) + (srcSize <= 16 * 1024);
-    int const row = level == 0 ? 3 : level;
-    return adjust_cparams(adjust_cparams(kDefaultCParams[tableID][row], srcSize), srcSize);
+    int const row = level == 0 ? 3 : (level < 0 ? 0 : level);      // negative levels: row 0 + acceleration (ZstdCompress.cs:7901-7923)
+    CParams c = kDefaultCParams[tableID][row];
+    if (c.strategy == 0) return c;                                  // caller reports parameter_unsupported
+    if (level < 0) c.targetLength = (uint32_t)(-(level < -(1 << 17) ? -(1 << 17) : level));     // ZSTD_minCLevel() = -(1 << 17)
+    return adjust_cparams(adjust_cparams(c, srcSize), srcSize);
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -85,7 +87,9 @@ struct __align__(16) EncItem {
     uint32_t outPos;        // bytes of the frame written so far
     uint32_t hufRepeat;     // prevCBlock->entropy.huf.repeatMode: 0 none, 1 check (valid needs a dictionary)
     uint32_t hufCur;        // which of the frame's two Huffman table slots holds prevCBlock's table
-    uint32_t _pad;
+    uint32_t stepSize;      // ZSTD_fast: distance between probe pairs (2, or targetLength + 1 for the negative levels)
+    uint32_t rawLits;       // literal compression disabled (negative levels)
+    uint32_t _pad[3];
 };
 
 // Geometry of block `wave` of a frame (ZSTD_compress_frameChunk :4690 + ZSTD_window_enforceMaxDist, ZstdCompressInternal.cs:630;
@@ -137,206 +141,6 @@ __device__ __forceinline__ uint64_t rd64(const uint8_t* p)
     if (sh == 0) return (uint64_t)w0 | ((uint64_t)w1 << 32);
     uint32_t const w2 = w[2];
     return (uint64_t)__funnelshift_r(w0, w1, sh) | ((uint64_t)__funnelshift_r(w1, w2, sh) << 32);
-}
-
-// ZSTD_hashPtr, ZstdCompressInternal.cs:340-437
-__device__ __forceinline__ uint32_t hash_ptr(const uint8_t* p, uint32_t hBits, uint32_t mls)
-{
-    switch (mls) {
-    default:
-    case 4: return (rd32(p) * 2654435761u) >> (32 - hBits);
-    case 5: return (uint32_t)(((rd64(p) << 24) * 889523592379ull) >> (64 - hBits));
-    case 6: return (uint32_t)(((rd64(p) << 16) * 227718039650203ull) >> (64 - hBits));
-    case 7: return (uint32_t)(((rd64(p) << 8) * 58295818150454627ull) >> (64 - hBits));
-    case 8: return (uint32_t)((rd64(p) * 0xCF1BBCDCB7A56463ull) >> (64 - hBits));
-    }
-}
-// ZSTD_count, ZstdCompressInternal.cs:264: common-prefix length bounded by pInLimit
-__device__ __forceinline__ uint32_t count_match(const uint8_t* pIn, const uint8_t* pMatch, const uint8_t* const pInLimit)
-{
-    const uint8_t* const pStart = pIn;
-    while (pIn + 4 <= pInLimit) {
-        uint32_t const diff = rd32(pIn) ^ rd32(pMatch);
-        if (diff) return (uint32_t)(pIn - pStart) + (__ffs((int)diff) - 1) / 8;
-        pIn += 4; pMatch += 4;
-    }
-    while (pIn < pInLimit && *pMatch == *pIn) { pIn++; pMatch++; }
-    return (uint32_t)(pIn - pStart);
-}
-
-struct SeqWriter {
-    uint32_t* ll; uint32_t* ml; uint32_t* of; uint32_t n;
-    __device__ __forceinline__ void store(uint32_t litLength, uint32_t offCode, uint32_t mlBase)   // ZSTD_storeSeq :204
-    { ll[n] = litLength; of[n] = offCode + 1; ml[n] = mlBase; n++; }
-};
-
-// ZSTD_compressBlock_fast_noDict_generic, ZstdFast.cs:96, on block g of the frame at `frame` (serial restatement)
-__device__ uint32_t match_fast(uint32_t* hashTable, uint32_t hlog, uint32_t mls, const uint8_t* frame, const BlkGeom& g, uint32_t rep[2], SeqWriter& sw)
-{
-    const uint8_t* const base = frame - 2;
-    uint32_t const prefixStartIndex = (uint32_t)g.lowPos + 2;
-    const uint8_t* const prefixStart = frame + g.lowPos;
-    const uint8_t* const istart = frame + g.B;
-    const uint8_t* const iend = frame + g.end; const uint8_t* const ilimit = iend - 8;
-    const uint8_t* anchor = istart; const uint8_t* ip0 = frame + g.ip0; const uint8_t* ip1; const uint8_t* ip2; const uint8_t* ip3;
-    uint32_t current0 = 0; uint32_t rep1 = rep[0], rep2 = rep[1], offsetSaved = 0;
-    uint32_t hash0, hash1, idx, mval, offcode; const uint8_t* match0; uint32_t mLength; uint32_t step; const uint8_t* nextStep;
-    if (rep2 > g.maxRep) { offsetSaved = rep2; rep2 = 0; }          // :131-145
-    if (rep1 > g.maxRep) { offsetSaved = rep1; rep1 = 0; }
-_start:
-    step = 2; nextStep = ip0 + 128;
-    ip1 = ip0 + 1; ip2 = ip0 + step; ip3 = ip2 + 1;
-    if (ip3 >= ilimit) goto _cleanup;
-    hash0 = hash_ptr(ip0, hlog, mls); hash1 = hash_ptr(ip1, hlog, mls);
-    idx = hashTable[hash0];
-    do {
-        uint32_t const rval = rep1 ? rd32(ip2 - rep1) : 0;
-        current0 = (uint32_t)(ip0 - base);
-        hashTable[hash0] = current0;
-        if ((rep1 > 0) && (rd32(ip2) == rval)) {
-            ip0 = ip2; match0 = ip0 - rep1;
-            mLength = ip0[-1] == match0[-1];
-            ip0 -= mLength; match0 -= mLength;
-            offcode = 0; mLength += 4;
-            goto _match;
-        }
-        mval = idx >= prefixStartIndex ? rd32(base + idx) : (rd32(ip0) ^ 1);
-        if (rd32(ip0) == mval) goto _offset;
-        idx = hashTable[hash1];
-        hash0 = hash1; hash1 = hash_ptr(ip2, hlog, mls);
-        ip0 = ip1; ip1 = ip2; ip2 = ip3;
-        current0 = (uint32_t)(ip0 - base);
-        hashTable[hash0] = current0;
-        mval = idx >= prefixStartIndex ? rd32(base + idx) : (rd32(ip0) ^ 1);
-        if (rd32(ip0) == mval) goto _offset;
-        idx = hashTable[hash1];
-        hash0 = hash1; hash1 = hash_ptr(ip2, hlog, mls);
-        ip0 = ip1; ip1 = ip2; ip2 = ip0 + step; ip3 = ip1 + step;
-        if (ip2 >= nextStep) { step++; nextStep += 128; }
-    } while (ip3 < ilimit);
-_cleanup:
-    rep[0] = rep1 ? rep1 : offsetSaved;                 // :232-233
-    rep[1] = rep2 ? rep2 : offsetSaved;
-    return (uint32_t)(iend - anchor);
-_offset:
-    match0 = base + idx;
-    rep2 = rep1; rep1 = (uint32_t)(ip0 - match0);
-    offcode = rep1 + 2;
-    mLength = 4;
-    while (((ip0 > anchor) & (match0 > prefixStart)) && (ip0[-1] == match0[-1])) { ip0--; match0--; mLength++; }
-_match:
-    mLength += count_match(ip0 + mLength, match0 + mLength, iend);
-    sw.store((uint32_t)(ip0 - anchor), offcode, mLength - 3);
-    ip0 += mLength; anchor = ip0;
-    if (ip1 < ip0) hashTable[hash1] = (uint32_t)(ip1 - base);
-    if (ip0 <= ilimit) {
-        hashTable[hash_ptr(base + current0 + 2, hlog, mls)] = current0 + 2;
-        hashTable[hash_ptr(ip0 - 2, hlog, mls)] = (uint32_t)(ip0 - 2 - base);
-        if (rep2 > 0) {
-            while ((ip0 <= ilimit) && (rd32(ip0) == rd32(ip0 - rep2))) {
-                uint32_t const rLength = count_match(ip0 + 4, ip0 + 4 - rep2, iend) + 4;
-                { uint32_t const t = rep2; rep2 = rep1; rep1 = t; }
-                hashTable[hash_ptr(ip0, hlog, mls)] = (uint32_t)(ip0 - base);
-                ip0 += rLength;
-                sw.store(0, 0, rLength - 3);
-                anchor = ip0;
-            }
-        }
-    }
-    goto _start;
-}
-
-// ZSTD_compressBlock_doubleFast_noDict_generic, ZstdDoubleFast.cs:51, on block g of the frame at `frame` (serial restatement)
-__device__ uint32_t match_dfast(uint32_t* hashLong, uint32_t hBitsL, uint32_t* hashSmall, uint32_t hBitsS, uint32_t mls,
-                                const uint8_t* frame, const BlkGeom& g, uint32_t rep[2], SeqWriter& sw)
-{
-    const uint8_t* const base = frame - 2;
-    uint32_t const prefixLowestIndex = (uint32_t)g.lowPos + 2;
-    const uint8_t* const prefixLowest = frame + g.lowPos;
-    const uint8_t* const istart = frame + g.B;
-    const uint8_t* const iend = frame + g.end; const uint8_t* const ilimit = iend - 8;
-    const uint8_t* anchor = istart;
-    uint32_t offset_1 = rep[0], offset_2 = rep[1], offsetSaved = 0;
-    uint32_t mLength, offset, curr = 0;
-    const uint8_t* nextStep; uint32_t step; uint32_t hl0, hl1 = 0; uint32_t idxl0, idxl1 = 0;
-    const uint8_t* matchl0; const uint8_t* matchs0; const uint8_t* matchl1 = istart;
-    const uint8_t* ip = frame + g.ip0; const uint8_t* ip1;
-    if (offset_2 > g.maxRep) { offsetSaved = offset_2; offset_2 = 0; }
-    if (offset_1 > g.maxRep) { offsetSaved = offset_1; offset_1 = 0; }
-    while (1) {
-        step = 1; nextStep = ip + 256; ip1 = ip + step;
-        if (ip1 > ilimit) goto _cleanup;
-        hl0 = hash_ptr(ip, hBitsL, 8);
-        idxl0 = hashLong[hl0]; matchl0 = base + idxl0;
-        do {
-            uint32_t const hs0 = hash_ptr(ip, hBitsS, mls);
-            uint32_t const idxs0 = hashSmall[hs0];
-            curr = (uint32_t)(ip - base);
-            matchs0 = base + idxs0;
-            hashLong[hl0] = hashSmall[hs0] = curr;
-            if ((offset_1 > 0) && (rd32(ip + 1 - offset_1) == rd32(ip + 1))) {
-                mLength = count_match(ip + 1 + 4, ip + 1 + 4 - offset_1, iend) + 4;
-                ip++;
-                sw.store((uint32_t)(ip - anchor), 0, mLength - 3);
-                goto _match_stored;
-            }
-            hl1 = hash_ptr(ip1, hBitsL, 8);
-            if (idxl0 > prefixLowestIndex) {
-                if (rd64(matchl0) == rd64(ip)) {
-                    mLength = count_match(ip + 8, matchl0 + 8, iend) + 8;
-                    offset = (uint32_t)(ip - matchl0);
-                    while (((ip > anchor) & (matchl0 > prefixLowest)) && (ip[-1] == matchl0[-1])) { ip--; matchl0--; mLength++; }
-                    goto _match_found;
-                }
-            }
-            idxl1 = hashLong[hl1]; matchl1 = base + idxl1;
-            if (idxs0 > prefixLowestIndex) {
-                if (rd32(matchs0) == rd32(ip)) goto _search_next_long;
-            }
-            if (ip1 >= nextStep) { step++; nextStep += 256; }
-            ip = ip1; ip1 += step;
-            hl0 = hl1; idxl0 = idxl1; matchl0 = matchl1;
-        } while (ip1 <= ilimit);
-_cleanup:
-        rep[0] = offset_1 ? offset_1 : offsetSaved;     // :215-216
-        rep[1] = offset_2 ? offset_2 : offsetSaved;
-        return (uint32_t)(iend - anchor);
-_search_next_long:
-        if (idxl1 > prefixLowestIndex) {
-            if (rd64(matchl1) == rd64(ip1)) {
-                ip = ip1;
-                mLength = count_match(ip + 8, matchl1 + 8, iend) + 8;
-                offset = (uint32_t)(ip - matchl1);
-                while (((ip > anchor) & (matchl1 > prefixLowest)) && (ip[-1] == matchl1[-1])) { ip--; matchl1--; mLength++; }
-                goto _match_found;
-            }
-        }
-        mLength = count_match(ip + 4, matchs0 + 4, iend) + 4;
-        offset = (uint32_t)(ip - matchs0);
-        while (((ip > anchor) & (matchs0 > prefixLowest)) && (ip[-1] == matchs0[-1])) { ip--; matchs0--; mLength++; }
-_match_found:
-        offset_2 = offset_1; offset_1 = offset;
-        if (step < 4) hashLong[hl1] = (uint32_t)(ip1 - base);
-        sw.store((uint32_t)(ip - anchor), offset + 2, mLength - 3);
-_match_stored:
-        ip += mLength; anchor = ip;
-        if (ip <= ilimit) {
-            {   uint32_t const indexToInsert = curr + 2;
-                hashLong[hash_ptr(base + indexToInsert, hBitsL, 8)] = indexToInsert;
-                hashLong[hash_ptr(ip - 2, hBitsL, 8)] = (uint32_t)(ip - 2 - base);
-                hashSmall[hash_ptr(base + indexToInsert, hBitsS, mls)] = indexToInsert;
-                hashSmall[hash_ptr(ip - 1, hBitsS, mls)] = (uint32_t)(ip - 1 - base);
-            }
-            while ((ip <= ilimit) && ((offset_2 > 0) && (rd32(ip) == rd32(ip - offset_2)))) {
-                uint32_t const rLength = count_match(ip + 4, ip + 4 - offset_2, iend) + 4;
-                uint32_t const t = offset_2; offset_2 = offset_1; offset_1 = t;
-                hashSmall[hash_ptr(ip, hBitsS, mls)] = (uint32_t)(ip - base);
-                hashLong[hash_ptr(ip, hBitsL, 8)] = (uint32_t)(ip - base);
-                sw.store(0, 0, rLength - 3);
-                ip += rLength; anchor = ip;
-            }
-        }
-    }
 }
 
 // ZSTD_hashPtr on 8 loaded bytes (ZstdCompressInternal.cs:340-437)
@@ -402,7 +206,8 @@ __global__ void __launch_bounds__(32 * kMatchWarps) enc_match_group_kernel(EncPa
     }
     int const ilimit = srcSize - 8;
     uint32_t nseq = 0;
-    int step = 2, nextStep = ip0 + 128, d = 2;       // _start
+    int const stepSize = active ? (int)it.stepSize : 2;
+    int step = stepSize, nextStep = ip0 + 128, d = stepSize;       // _start
     bool afterMatch = false;                         // the greedy rep2 loop (:264-285) is still open at ip0
     uint32_t const k = l >> 1, odd = l & 1;
     auto gballot = [&](bool pr) -> uint32_t { return (__ballot_sync(FULL, pr) >> gbase) & LOW; };
@@ -509,7 +314,7 @@ __global__ void __launch_bounds__(32 * kMatchWarps) enc_match_group_kernel(EncPa
             }
             ip0 = mend; anchor = mend;
             afterMatch = true;
-            step = 2; nextStep = ip0 + 128; d = 2;    // _start
+            step = stepSize; nextStep = ip0 + 128; d = stepSize;    // _start
         } else if (active) {
             if (validMask != LOW) active = false;     // the loop condition failed inside the window: _cleanup
             else { ip0 = P; d = D; step = S; nextStep = N; }
@@ -700,26 +505,6 @@ __global__ void __launch_bounds__(32 * kMatchWarps) enc_match_dfast_group_kernel
         it.nbSeq = nseq; it.lastLL = (uint32_t)(srcSize - anchor);
         if (MB) { it.repNext[0] = off1 ? off1 : offsetSaved; it.repNext[1] = off2 ? off2 : offsetSaved; }     // :215-216
     }
-}
-
-// Serial restatement (one lane per block): used for blocks below 64 bytes only; everything else goes to the group kernels.
-__global__ void __launch_bounds__(32) enc_match_kernel(EncPass p, const uint32_t* __restrict__ workList, uint32_t nWork, uint32_t wave)
-{
-    uint32_t const w = blockIdx.x * blockDim.x + threadIdx.x;
-    if (w >= nWork) return;
-    uint32_t const i = workList[w];
-    EncItem& it = p.items[i];
-    BlkGeom const bg = blk_geom(it.srcSize, it.windowLog, wave);
-    it.nbSeq = 0; it.lastLL = (uint32_t)(bg.end - bg.B);
-    if (bg.end - bg.B < 7) return;      // ZSTD_buildSeqStore: srcSize < MIN_CBLOCK_SIZE+blockHeader+1 -> noCompress (:3438)
-    SeqWriter sw{p.seqLL + (size_t)i * kEncSeqCap, p.seqML + (size_t)i * kEncSeqCap, p.seqOF + (size_t)i * kEncSeqCap, 0};
-    const uint8_t* const src = p.src + it.srcOff;
-    uint32_t* const tab = p.tables + it.tableOff;
-    uint32_t rep[2] = {it.rep[0], it.rep[1]};
-    uint32_t lastLL;
-    if (it.strategy == 1) lastLL = match_fast(tab, it.hashLog, it.minMatch, src, bg, rep, sw);
-    else lastLL = match_dfast(tab, it.hashLog, tab + (1u << it.hashLog), it.chainLog, it.minMatch, src, bg, rep, sw);
-    it.nbSeq = sw.n; it.lastLL = lastLL; it.repNext[0] = rep[0]; it.repNext[1] = rep[1];
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -1263,7 +1048,7 @@ __global__ void __launch_bounds__(kEntThreads, MB ? 8 : 15) enc_entropy_kernel(E
         uint32_t const singleStream = litSize < 256;
         uint32_t const seg = (litSize + 3) / 4;
         uint32_t litMode = 0;   // 0 raw, 1 rle, 2 huffman
-        if (litSize > 63) {
+        if (litSize > 63 && !it.rawLits) {       // rawLits: ZSTD_noCompressLiterals right away (ZstdCompressLiterals.cs:100-101)
             bool const suspect = (nbSeq == 0) || (litSize / nbSeq >= 20);       // ZstdCompress.cs:3262
             bool skip = false;
             if (suspect && litSize >= 40960) {                                   // HufCompress.cs:1412-1446
@@ -1761,6 +1546,11 @@ bool enc_enqueue(EncArena& A, cudaStream_t stream, cudaStream_t copyStream, size
         e.srcSize = (uint32_t)std::min<size_t>(ss, 0xFFFFFFF0u); e.dstCap = (uint32_t)std::min<size_t>(dstCap[i], 0xFFFFFFF0u);
         CParams const c = get_cparams(level, ss);
         e.windowLog = c.windowLog; e.hashLog = c.hashLog; e.chainLog = c.chainLog; e.minMatch = c.minMatch; e.strategy = c.strategy;
+        // ZSTD_fast with an acceleration factor: probe pairs `stepSize` apart (hasStep = targetLength > 1, ZstdFast.cs:101, :334) and
+        // leave the literals uncompressed (ZSTD_literalsCompressionIsDisabled, ZstdCompressInternal.cs:483-498)
+        e.stepSize = (c.strategy == 1 && c.targetLength > 1) ? c.targetLength + 1 : 2;
+        e.rawLits = (c.strategy == 1 && c.targetLength > 0) ? 1u : 0u;
+        if (c.strategy == 0) { nBlk[i] = 0; hr[i] = make_error(kParameterUnsupported); mb = true; continue; }   // level 4 outside its dfast sizes
         e.nbSeq = 0; e.lastLL = (uint32_t)std::min<size_t>(ss, kBlockSizeMax);
         e.rep[0] = 1; e.rep[1] = 4;                               // repStartValue (ZstdInternal.cs:13)
         if (ss > kEncMaxFrameBytes) { nBlk[i] = 0; hr[i] = make_error(kSrcSizeWrong); mb = true; continue; }   // positions are 31-bit
@@ -1772,7 +1562,7 @@ bool enc_enqueue(EncArena& A, cudaStream_t stream, cudaStream_t copyStream, size
         tableEntries += ((size_t)1 << c.hashLog) + (c.strategy == 2 ? ((size_t)1 << c.chainLog) : 0);
     }
     if (tableEntries >= 0xFFFFFFFFull) { t_encErr = "hash-table arena exceeds 32-bit indexing"; return false; }
-    // work lists: per wave [ZSTD_fast groups | serial | ZSTD_dfast groups | entropy]; blocks of 64 bytes and more take the group kernels
+    // work lists: per wave [ZSTD_fast groups | (unused) | ZSTD_dfast groups | entropy]
     struct WaveLists { size_t off[4]; uint32_t n[4]; };
     std::vector<WaveLists> waves(maxWaves);
     size_t const listCap = 2 * totalBlocks + 4;
@@ -1794,7 +1584,7 @@ bool enc_enqueue(EncArena& A, cudaStream_t stream, cudaStream_t copyStream, size
                 size_t const bs = std::min<size_t>(kBlockSizeMax, ss - b * (size_t)kBlockSizeMax);
                 tmp[3].push_back(i);
                 if (ss < 7 || bs < 7) continue;                   // ZSTD_buildSeqStore: noCompress (:3438)
-                if (bs >= 64) tmp[hi[i].strategy == 1 ? 0 : 2].push_back(i); else tmp[1].push_back(i);
+                tmp[hi[i].strategy == 1 ? 0 : 2].push_back(i);
             }
             alive.resize(keep);
             for (int k = 0; k < 4; k++) {
@@ -1827,7 +1617,6 @@ bool enc_enqueue(EncArena& A, cudaStream_t stream, cudaStream_t copyStream, size
         // lanes per chunk: 16 measured best for ZSTD_fast (8: 49/52 ms, 16: 42/49 ms, 32: 63/72 ms per GiB Silesia-mix / text)
         if (mb) {
             if (w.n[0]) enc_match_group_kernel<16, true><<<(w.n[0] + 2 * kMatchWarps - 1) / (2 * kMatchWarps), 32 * kMatchWarps, 0, stream>>>(p, dw + w.off[0], w.n[0], wave);
-            if (w.n[1]) enc_match_kernel<<<(w.n[1] + 31) / 32, 32, 0, stream>>>(p, dw + w.off[1], w.n[1], wave);
             if (w.n[2]) enc_match_dfast_group_kernel<16, true><<<(w.n[2] + 2 * kMatchWarps - 1) / (2 * kMatchWarps), 32 * kMatchWarps, 0, stream>>>(p, dw + w.off[2], w.n[2], wave);
             if (ev3 && b == 0) ENC_CUDA(cudaEventRecord(ev3[1], stream));
             if (w.n[3]) {
@@ -1839,7 +1628,6 @@ bool enc_enqueue(EncArena& A, cudaStream_t stream, cudaStream_t copyStream, size
             static int const gsFast = []() { const char* e = getenv("ZSTDB200_MATCH_GS"); return e ? atoi(e) : 16; }();      // developer knob
             if (w.n[0] && gsFast == 8) enc_match_group_kernel<8, false><<<(w.n[0] + 4 * kMatchWarps - 1) / (4 * kMatchWarps), 32 * kMatchWarps, 0, stream>>>(p, dw + w.off[0], w.n[0], 0u);
             else if (w.n[0]) enc_match_group_kernel<16, false><<<(w.n[0] + 2 * kMatchWarps - 1) / (2 * kMatchWarps), 32 * kMatchWarps, 0, stream>>>(p, dw + w.off[0], w.n[0], 0u);
-            if (w.n[1]) enc_match_kernel<<<(w.n[1] + 31) / 32, 32, 0, stream>>>(p, dw + w.off[1], w.n[1], 0u);
             if (w.n[2]) enc_match_dfast_group_kernel<16, false><<<(w.n[2] + 2 * kMatchWarps - 1) / (2 * kMatchWarps), 32 * kMatchWarps, 0, stream>>>(p, dw + w.off[2], w.n[2], 0u);
             if (ev3) ENC_CUDA(cudaEventRecord(ev3[1], stream));
             enc_entropy_kernel<false, 0><<<(unsigned)m, kEntThreads, 0, stream>>>(p, dw, 0u);
@@ -1872,7 +1660,6 @@ void enc_set_overlap_mode(bool overlap)
     cudaFuncSetAttribute(enc_match_group_kernel<16, true>, A, x);
     cudaFuncSetAttribute(enc_match_dfast_group_kernel<16, false>, A, x);
     cudaFuncSetAttribute(enc_match_dfast_group_kernel<16, true>, A, x);
-    cudaFuncSetAttribute(enc_match_kernel, A, x);
     cudaFuncSetAttribute(enc_entropy_kernel<false, 0>, A, x);
     cudaFuncSetAttribute(enc_entropy_kernel<false, 1>, A, x);
     cudaFuncSetAttribute(enc_entropy_kernel<true, 0>, A, x);
