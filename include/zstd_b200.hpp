@@ -20,6 +20,10 @@
 #include <stdexcept>
 #include <string>
 #include <vector>
+#include <istream>
+#include <ostream>
+#include <cstring>
+#include <algorithm>
 
 #include "zstd_b200.h"
 
@@ -98,7 +102,7 @@ inline std::vector<BatchResult> ToResults(const std::vector<size_t>& raw) {
 class Compressor {
 public:
     static constexpr int DefaultCompressionLevel = 0;                                  /* Compressor.cs:10 */
-    static constexpr int MinCompressionLevel = 0, MaxCompressionLevel = 3;             /* levels this library implements */
+    static constexpr int MinCompressionLevel = -(1 << 17), MaxCompressionLevel = 4;    /* ZSTD_fast / ZSTD_dfast levels (4: only where it is ZSTD_dfast) */
 
     explicit Compressor(int level = DefaultCompressionLevel) : cctx_(ZSTD_createCCtx()) {   /* Compressor.cs:58-65 */
         if (!cctx_) throw ZstdException(ZSTD_ErrorCode::GENERIC, "Failed to create cctx");
@@ -259,6 +263,168 @@ public:
 private:
     void EnsureNotDisposed() const { if (!dctx_) throw ObjectDisposedException("Decompressor"); }
     ZSTD_DCtx* dctx_;
+};
+
+/* The batch scheduler across the GPUs of one box (ZSTDB200_*BatchMulti, include/zstd_b200.h): WrapBatch / UnwrapBatch with the
+ * meaning they have on Compressor / Decompressor; every item is handled by exactly one device, results in the caller's order.
+ * Closest notion in the reference: many contexts used at once (ZstdNetTests.cs:498-522). */
+class MultiCodec {
+public:
+    explicit MultiCodec(int nDevices = 0, int level = 1) : m_(ZSTDB200_createMulti(nDevices)), level_(level) {
+        if (!m_) throw ZstdException(ZSTD_ErrorCode::GENERIC, std::string("Failed to create the multi-device scheduler: ") + ZSTDB200_lastErrorString());
+    }
+    ~MultiCodec() { Dispose(); }
+    MultiCodec(const MultiCodec&) = delete;
+    MultiCodec& operator=(const MultiCodec&) = delete;
+    int DeviceCount() const { return ZSTDB200_multiDeviceCount(m_); }
+    int Level() const { return level_; }
+    void Level(int value) { level_ = value; }
+    void SetParameter(ZSTD_cParameter parameter, int value) { ThrowHelper::EnsureZstdSuccess(ZSTDB200_multiSetParameter(m_, static_cast<int>(parameter), value)); }
+    void LoadDictionary(const void* dict, size_t dictLength) { ThrowHelper::EnsureZstdSuccess(ZSTDB200_multiLoadDictionary(m_, dict, dict ? dictLength : 0)); }
+    std::vector<BatchResult> WrapBatch(const std::vector<const void*>& src, const std::vector<size_t>& srcLength,
+                                       const std::vector<void*>& dest, const std::vector<size_t>& destLength) {
+        size_t n = src.size();
+        if (srcLength.size() != n || dest.size() != n || destLength.size() != n) throw std::invalid_argument("WrapBatch: array lengths differ");
+        std::vector<size_t> raw(n);
+        ThrowHelper::EnsureZstdSuccess(ZSTDB200_compressBatchMulti(m_, n, level_ == 0 ? 3 : level_, src.data(), srcLength.data(), dest.data(), destLength.data(), raw.data()));
+        return detail::ToResults(raw);
+    }
+    std::vector<BatchResult> UnwrapBatch(const std::vector<const void*>& src, const std::vector<size_t>& srcLength,
+                                         const std::vector<void*>& dest, const std::vector<size_t>& destLength) {
+        size_t n = src.size();
+        if (srcLength.size() != n || dest.size() != n || destLength.size() != n) throw std::invalid_argument("UnwrapBatch: array lengths differ");
+        std::vector<size_t> raw(n);
+        ThrowHelper::EnsureZstdSuccess(ZSTDB200_decompressBatchMulti(m_, n, src.data(), srcLength.data(), dest.data(), destLength.data(), raw.data()));
+        return detail::ToResults(raw);
+    }
+    void Dispose() { if (m_) { ZSTDB200_freeMulti(m_); m_ = nullptr; } }
+
+private:
+    ZSTDB200_Multi* m_;
+    int level_;
+};
+
+/* Stream adapters over the batch API.  The reference's CompressionStream / DecompressionStream
+ * (src/ZstdSharp/CompressionStream.cs:8-190, DecompressionStream.cs) drive zstd's serial streaming state machine; these keep the
+ * classes' shape (constructor over an inner stream, Write / Flush / Read / Dispose, SetParameter) but cut the data into independent
+ * frames of frameSize bytes and hand whole batches to WrapBatch / UnwrapBatch.  The output is format compatible: concatenated
+ * frames are one valid zstd stream (ZSTD_decompressMultiFrame, Unsafe/ZstdDecompress.cs:1216), and DecompressionStream accepts any
+ * concatenation of frames (from this class, the reference, the zstd CLI), cutting it at ZSTD_findFrameCompressedSize (:958). */
+class CompressionStream {
+public:
+    CompressionStream(std::ostream& stream, int level = Compressor::DefaultCompressionLevel, size_t frameSize = 128 * 1024, size_t batchFrames = 1024)
+        : inner_(stream), comp_(level), frame_(frameSize), batch_(batchFrames) {
+        if (frameSize == 0 || frameSize > 128 * 1024 || batchFrames == 0) throw std::invalid_argument("frameSize / batchFrames");
+    }
+    ~CompressionStream() { try { Dispose(); } catch (...) {} }
+    void SetParameter(ZSTD_cParameter parameter, int value) { EnsureNotDisposed(); comp_.SetParameter(parameter, value); }   /* CompressionStream.cs:46-50 */
+    void Write(const void* buffer, size_t count) {                                     /* CompressionStream.cs:130-150 */
+        EnsureNotDisposed();
+        const uint8_t* p = static_cast<const uint8_t*>(buffer);
+        buf_.insert(buf_.end(), p, p + count);
+        while (buf_.size() >= frame_ * batch_) Emit(frame_ * batch_);
+    }
+    void Flush() { EnsureNotDisposed(); Emit(buf_.size()); inner_.flush(); }           /* CompressionStream.cs:88-98: everything written so far becomes decodable */
+    void Dispose() { if (!done_) { Emit(buf_.size()); inner_.flush(); done_ = true; } }
+
+private:
+    void EnsureNotDisposed() const { if (done_) throw ObjectDisposedException("CompressionStream"); }
+    void Emit(size_t bytes) {
+        if (bytes == 0) return;
+        size_t const n = (bytes + frame_ - 1) / frame_;
+        std::vector<const void*> src(n); std::vector<size_t> len(n), cap(n); std::vector<void*> dst(n);
+        size_t total = 0;
+        for (size_t i = 0; i < n; i++) { len[i] = std::min(frame_, bytes - i * frame_); cap[i] = ZSTD_compressBound(len[i]); total += cap[i]; }
+        std::vector<uint8_t> out(total);
+        size_t o = 0;
+        for (size_t i = 0; i < n; i++) { src[i] = buf_.data() + i * frame_; dst[i] = out.data() + o; o += cap[i]; }
+        std::vector<BatchResult> r = comp_.WrapBatch(src, len, dst, cap);
+        for (size_t i = 0; i < n; i++) {
+            if (r[i].Code != ZSTD_ErrorCode::no_error) throw ZstdException(r[i].Code, "compression of a stream frame failed");
+            inner_.write(static_cast<const char*>(dst[i]), static_cast<std::streamsize>(r[i].Size));
+        }
+        buf_.erase(buf_.begin(), buf_.begin() + static_cast<std::ptrdiff_t>(bytes));
+    }
+    std::ostream& inner_;
+    Compressor comp_;
+    size_t frame_, batch_;
+    std::vector<uint8_t> buf_;
+    bool done_ = false;
+};
+
+class DecompressionStream {
+public:
+    explicit DecompressionStream(std::istream& stream, size_t batchBytes = size_t(64) << 20) : inner_(stream), batchBytes_(batchBytes) {}
+    void SetParameter(ZSTD_dParameter parameter, int value) { dec_.SetParameter(parameter, value); }            /* DecompressionStream.cs:47-51 */
+    void LoadDictionary(const void* dict, size_t dictLength) { dec_.LoadDictionary(dict, dictLength); }
+    /* int Read(byte[] buffer, int offset, int count)  (DecompressionStream.cs:74-120): 0 at the end of the stream; a stream that
+     * ends inside a frame throws (EndOfStreamException there, ZstdException(srcSize_wrong) here). */
+    size_t Read(void* buffer, size_t count) {
+        uint8_t* out = static_cast<uint8_t*>(buffer);
+        size_t got = 0;
+        while (got < count) {
+            if (pos_ == ready_.size()) { if (!Refill()) break; }
+            size_t const m = std::min(count - got, ready_.size() - pos_);
+            std::memcpy(out + got, ready_.data() + pos_, m);
+            pos_ += m; got += m;
+        }
+        return got;
+    }
+
+private:
+    bool Refill() {
+        ready_.clear(); pos_ = 0;
+        // pull compressed bytes until at least one whole frame is buffered (or the inner stream ends)
+        std::vector<size_t> cut;          // end offsets of whole frames inside pending_
+        size_t at = 0;
+        for (;;) {
+            while (at < pending_.size()) {
+                size_t const fs = ZSTD_findFrameCompressedSize(pending_.data() + at, pending_.size() - at);
+                if (ZSTD_isError(fs)) break;
+                at += fs; cut.push_back(at);
+            }
+            if (!cut.empty() && (at >= batchBytes_ || eof_)) break;
+            if (eof_) break;
+            size_t const old = pending_.size();
+            pending_.resize(old + (size_t(1) << 20));
+            inner_.read(reinterpret_cast<char*>(pending_.data() + old), static_cast<std::streamsize>(size_t(1) << 20));
+            size_t const n = static_cast<size_t>(inner_.gcount());
+            pending_.resize(old + n);
+            if (n == 0) eof_ = true;
+        }
+        if (cut.empty()) {
+            if (!pending_.empty()) {      // leftover bytes that are not a whole frame: report what ZSTD_findFrameCompressedSize says
+                size_t const fs = ZSTD_findFrameCompressedSize(pending_.data(), pending_.size());
+                pending_.clear();
+                ThrowHelper::EnsureZstdSuccess(fs);
+            }
+            return false;
+        }
+        size_t const n = cut.size();
+        std::vector<const void*> src(n); std::vector<size_t> len(n), cap(n); std::vector<void*> dst(n);
+        size_t total = 0, prev = 0;
+        for (size_t i = 0; i < n; i++) {
+            src[i] = pending_.data() + prev; len[i] = cut[i] - prev; prev = cut[i];
+            cap[i] = static_cast<size_t>(ThrowHelper::EnsureContentSizeOk(ZSTD_decompressBound(src[i], len[i])));
+            total += cap[i];
+        }
+        std::vector<uint8_t> out(total ? total : 1);
+        size_t o = 0;
+        for (size_t i = 0; i < n; i++) { dst[i] = out.data() + o; o += cap[i]; }
+        std::vector<BatchResult> r = dec_.UnwrapBatch(src, len, dst, cap);
+        for (size_t i = 0; i < n; i++) {
+            if (r[i].Code != ZSTD_ErrorCode::no_error) throw ZstdException(r[i].Code, "a frame of the stream failed to decode");
+            ready_.insert(ready_.end(), static_cast<uint8_t*>(dst[i]), static_cast<uint8_t*>(dst[i]) + r[i].Size);
+        }
+        pending_.erase(pending_.begin(), pending_.begin() + static_cast<std::ptrdiff_t>(cut.back()));
+        return true;
+    }
+    std::istream& inner_;
+    Decompressor dec_;
+    size_t batchBytes_;
+    std::vector<uint8_t> pending_, ready_;
+    size_t pos_ = 0;
+    bool eof_ = false;
 };
 
 }  // namespace ZstdSharp

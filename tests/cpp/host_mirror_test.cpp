@@ -12,6 +12,7 @@
 #include <string>
 #include <thread>
 #include <vector>
+#include <sstream>
 
 #include "zstd_b200.hpp"
 #include "zo.h"
@@ -246,6 +247,60 @@ static void gpu_all() {
             });
         for (auto& x : th) x.join();
         for (int t = 0; t < 4; ++t) CHECK(ok[t]);
+    }
+    // Stream adapters (CompressionStream.cs / DecompressionStream.cs shape; ZstdNetSteamingTests.cs round trips): every frame the
+    // adapter writes is the oracle's frame of that 128 KiB piece, the stream decodes back, foreign concatenations are accepted
+    {
+        Bytes data = text_like(5 * 131072 + 4321);
+        std::ostringstream os;
+        {
+            CompressionStream cs(os, 1);
+            cs.Write(data.data(), 100000);
+            cs.Flush();                                                  // a flush closes the frame(s) written so far
+            cs.Write(data.data() + 100000, data.size() - 100000);
+            cs.Dispose();
+            bool disposedThrows = false;
+            try { cs.Write(data.data(), 1); } catch (const ObjectDisposedException&) { disposedThrows = true; }
+            CHECK(disposedThrows);
+        }
+        std::string const z = os.str();
+        Bytes expect;
+        {
+            Bytes a(data.begin(), data.begin() + 100000); Bytes f = oracle_compress(a, 1); expect.insert(expect.end(), f.begin(), f.end());
+            for (size_t o = 100000; o < data.size(); o += 131072) {
+                Bytes b(data.begin() + o, data.begin() + std::min(data.size(), o + 131072)); Bytes g = oracle_compress(b, 1);
+                expect.insert(expect.end(), g.begin(), g.end());
+            }
+        }
+        CHECK(Bytes(z.begin(), z.end()) == expect);
+        std::istringstream is(z);
+        DecompressionStream ds(is);
+        Bytes back(data.size() + 100);
+        size_t got = 0, r;
+        while ((r = ds.Read(back.data() + got, std::min<size_t>(70001, back.size() - got))) != 0) got += r;
+        CHECK(got == data.size() && std::memcmp(back.data(), data.data(), got) == 0);
+        // a stream that ends inside a frame is an error (DecompressionStream.cs:108-113)
+        std::istringstream cutIs(z.substr(0, z.size() - 7));
+        DecompressionStream cutDs(cutIs);
+        CHECK(thrown_code([&] { Bytes tmp(data.size() + 100); size_t g = 0, q; while ((q = cutDs.Read(tmp.data() + g, tmp.size() - g)) != 0) g += q; }) == ZSTD_ErrorCode::srcSize_wrong);
+    }
+    // MultiCodec (ZSTDB200_*BatchMulti): however many devices are visible, the oracle's frames in the caller's order
+    {
+        MultiCodec m(0, 1);
+        CHECK(m.DeviceCount() >= 1);
+        size_t const n = 40;
+        std::vector<Bytes> in(n), comp(n), out(n);
+        std::vector<const void*> sp(n); std::vector<void*> dp(n); std::vector<size_t> ss(n), dsz(n);
+        for (size_t i = 0; i < n; ++i) {
+            in[i] = text_like(1000 + 3271 * i); comp[i].resize(ZSTD_compressBound(in[i].size()));
+            sp[i] = in[i].data(); ss[i] = in[i].size(); dp[i] = comp[i].data(); dsz[i] = comp[i].size();
+        }
+        std::vector<BatchResult> r = m.WrapBatch(sp, ss, dp, dsz);
+        for (size_t i = 0; i < n; ++i) { CHECK(r[i].Code == ZSTD_ErrorCode::no_error); comp[i].resize(r[i].Size); CHECK(comp[i] == oracle_compress(in[i], 1)); }
+        std::vector<const void*> csp(n); std::vector<void*> odp(n); std::vector<size_t> css(n), ods(n);
+        for (size_t i = 0; i < n; ++i) { out[i].resize(in[i].size()); csp[i] = comp[i].data(); css[i] = comp[i].size(); odp[i] = out[i].data(); ods[i] = out[i].size(); }
+        std::vector<BatchResult> u = m.UnwrapBatch(csp, css, odp, ods);
+        for (size_t i = 0; i < n; ++i) CHECK(u[i].Code == ZSTD_ErrorCode::no_error && u[i].Size == in[i].size() && out[i] == in[i]);
     }
 }
 
