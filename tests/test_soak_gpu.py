@@ -27,4 +27,4 @@ def test_soak_regression_seeds(codec, seed):
 def test_soak_fresh_seed(codec):
     seed = int(os.environ.get("ZSTDB200_SOAK_SEED", 0)) or int(time.time()) % 1_000_000_000
     print(f"ZSTDB200_SOAK_SEED={seed}")
-    assert run_soak(5000, seed, *codec) == 0, f"replay with ZSTDB200_SOAK_SEED={seed}"
+    assert run_soak(5000, seed, *codec, levels=(-5, -1, 1, 2, 3)) == 0, f"replay with ZSTDB200_SOAK_SEED={seed}"
