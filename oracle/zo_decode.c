@@ -609,6 +609,7 @@ typedef struct {
     HUF_DTable hufTable;
     U32 rep[3];
     int litEntropy, fseEntropy;
+    size_t seqOutLimit;      /* how far the sequences of the current block may write (zo_litBufferPlacement) */
     const BYTE* litPtr; size_t litSize;
     BYTE litBuffer[ZSTD_BLOCKSIZE_MAX + 32];
     const BYTE* prefixStart;
@@ -628,6 +629,18 @@ static void zo_decompressBegin(zo_DCtx* d)    /* ZstdDecompress.cs:1933 ZSTD_dec
 }
 
 /* ---- literals : ZstdDecompressBlock.cs:88 ZSTD_decodeLiteralsBlock ---- */
+/* ZSTD_allocateLiteralsBuffer (ZstdDecompressBlock.cs:44-73) + `oend` of ZSTD_decompressSequences_body (:2668).  The reference keeps the
+ * literals of a block inside dst when there is room (ZSTD_in_dst: at dst + ZSTD_BLOCKSIZE_MAX + WILDCOPY_OVERLENGTH); the sequences of
+ * the block may then only write up to that address, so a damaged block that regenerates more than 128 KiB + 32 bytes fails with
+ * dstSize_tooSmall before anything else is looked at.  On valid frames the placement is invisible.  This oracle keeps its literals in a
+ * buffer of its own and restates the limit.  NOT restated: the ZSTD_split placement (litSize > 64 KiB with a tight dst), whose
+ * "output caught up with the literal buffer" checks (:2139-2153) and literal clobbering only show on damaged frames. */
+static void zo_litBufferPlacement(zo_DCtx* dctx, size_t dstCapacity, size_t litSize, int directReference)
+{
+    if (!directReference && dstCapacity > ZSTD_BLOCKSIZE_MAX + 32 + litSize + 32) dctx->seqOutLimit = ZSTD_BLOCKSIZE_MAX + 32;   /* ZSTD_in_dst */
+    else dctx->seqOutLimit = dstCapacity;                                                                                          /* ZSTD_not_in_dst (and ZSTD_split) */
+}
+
 static size_t zo_decodeLiteralsBlock(zo_DCtx* dctx, const void* src, size_t srcSize, void* dst, size_t dstCapacity)
 {
     if (srcSize < MIN_CBLOCK_SIZE) return ERROR(corruption_detected);
@@ -654,6 +667,7 @@ static size_t zo_decodeLiteralsBlock(zo_DCtx* dctx, const void* src, size_t srcS
                 if (litSize > ZSTD_BLOCKSIZE_MAX) return ERROR(corruption_detected);
                 if (litCSize + lhSize > srcSize) return ERROR(corruption_detected);
                 if (expectedWriteSize < litSize) return ERROR(dstSize_tooSmall);
+                zo_litBufferPlacement(dctx, dstCapacity, litSize, 0);
                 if (litEncType == set_repeat) {
                     /* HUF_decompress{1,4}X_usingDTable_bmi2 (HufDecompress.cs:1759, :1786): by the type the table was built with */
                     int const x2 = dctx->hufTable.tableType != 0;
@@ -692,6 +706,7 @@ static size_t zo_decodeLiteralsBlock(zo_DCtx* dctx, const void* src, size_t srcS
                 }
                 if (litSize > 0 && dst == NULL) return ERROR(dstSize_tooSmall);
                 if (expectedWriteSize < litSize) return ERROR(dstSize_tooSmall);
+                zo_litBufferPlacement(dctx, dstCapacity, litSize, lhSize + litSize + 32 <= srcSize);     /* enough src behind them: referenced in place (:268-299) */
                 if (litSize + lhSize > srcSize) return ERROR(corruption_detected);
                 dctx->litPtr = istart + lhSize; dctx->litSize = litSize;
                 return lhSize + litSize;
@@ -708,6 +723,7 @@ static size_t zo_decodeLiteralsBlock(zo_DCtx* dctx, const void* src, size_t srcS
                 if (litSize > 0 && dst == NULL) return ERROR(dstSize_tooSmall);
                 if (litSize > ZSTD_BLOCKSIZE_MAX) return ERROR(corruption_detected);
                 if (expectedWriteSize < litSize) return ERROR(dstSize_tooSmall);
+                zo_litBufferPlacement(dctx, dstCapacity, litSize, 0);
                 memset(dctx->litBuffer, istart[lhSize], litSize);
                 dctx->litPtr = dctx->litBuffer; dctx->litSize = litSize;
                 return lhSize + 1;
@@ -873,7 +889,7 @@ typedef struct { uint32_t* triples; size_t cap; size_t n; } zo_seqTap;
 static size_t zo_decompressSequences(zo_DCtx* dctx, void* dst, size_t maxDstSize, const void* seqStart, size_t seqSize, int nbSeq, zo_seqTap* tap)
 {
     const BYTE* ip = (const BYTE*)seqStart; const BYTE* const iend = ip + seqSize;
-    BYTE* const ostart = (BYTE*)dst; BYTE* const oend = ostart + maxDstSize; BYTE* op = ostart;
+    BYTE* const ostart = (BYTE*)dst; BYTE* const oend = ostart + (maxDstSize < dctx->seqOutLimit ? maxDstSize : dctx->seqOutLimit); BYTE* op = ostart;
     const BYTE* litPtr = dctx->litPtr; const BYTE* const litEnd = litPtr + dctx->litSize;
     const BYTE* const prefixStart = dctx->prefixStart;
     if (nbSeq) {

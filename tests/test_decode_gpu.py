@@ -389,3 +389,20 @@ def test_pageable_and_scattered_host_buffers(dec):
     res = (ctypes.c_size_t * n)()
     assert _native.lib.ZSTDB200_decompressBatch(dec.handle, n, sp, ss, dp, dc, res) == 0
     assert list(res) == [FRAME] * n and out.tobytes() == data.tobytes()
+
+
+def test_error_codes_found_by_the_round2_soak(dec):
+    """tests/golden/soak_r02_frames.json: damaged frames on which round 2's 80 000-frame soak found an error-CODE difference (the verdict
+    class was right).  Expected codes come from the reference's libzstd.dll: dstSize_tooSmall when a block overruns the in-dst literal
+    buffer limit, corruption_detected when Huffman literals and the sequence section are both damaged."""
+    import json, os
+    from zstdsharp_b200 import ZstdException
+    o = oracle()
+    cases = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "soak_r02_frames.json")))["cases"]
+    for c in cases:
+        f = bytes.fromhex(c["frame_hex"])
+        rv, _ = o.decompress_raw(f, c["capacity"])
+        assert o.error_code(rv) == c["error_code"], c["name"]
+        got = dec.UnwrapBatch([f] * 3, raise_on_error=False, capacity=c["capacity"])
+        for g in got:
+            assert isinstance(g, ZstdException) and int(g.Code) == c["error_code"], (c["name"], g)

@@ -228,3 +228,12 @@ def test_negative_levels_and_level4_match_the_dll(level):
             assert o.compress(d, level) == r.compress(d, level), name
             n += 1
     assert n >= 20
+
+
+def test_error_codes_found_by_the_round2_soak():
+    """tests/golden/soak_r02_frames.json against the DLL itself (the fixture's codes were read off it) and the oracle."""
+    import json, os
+    o, r = oracle(), refdll()
+    for c in json.load(open(os.path.join(os.path.dirname(__file__), "golden", "soak_r02_frames.json")))["cases"]:
+        f = bytes.fromhex(c["frame_hex"])
+        assert r.error_code(r.decompress_raw(f, c["capacity"])[0]) == c["error_code"] == o.error_code(o.decompress_raw(f, c["capacity"])[0]), c["name"]

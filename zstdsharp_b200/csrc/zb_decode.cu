@@ -583,7 +583,7 @@ __global__ void __launch_bounds__(kSetupWarps * 32) dec_setup_kernel(DecPass p)
             if (cBlockSize > rem) { setup_fail(it, kSrcSizeWrong); break; }
             uint32_t const capLeft = it.dstCap - it.outPos;
             it.blkType = type; it.blkSrcOff = pos; it.blkSize = cs; it.srcPos = pos + cBlockSize;
-            it.nbSeq = 0; it.blockOut = 0; it.seqLitEnd = 0;
+            it.nbSeq = 0; it.blockOut = 0; it.seqLitEnd = 0; it.deferErr = 0; it.blkLimit = it.dstCap;
             if (type != kBlkCompressed) {
                 if (cs > capLeft) setup_fail(it, kDstSizeTooSmall);     // ZSTD_copyRawBlock :1004 / ZSTD_setRleBlock :1029
                 else if (cs) { uint32_t const slot = atomicAdd(&p.counters[4], 1u); p.rawList[slot] = item; }
@@ -662,20 +662,32 @@ __global__ void __launch_bounds__(kSetupWarps * 32) dec_setup_kernel(DecPass p)
                     litSectionSize = lhSize + 1;
                 }
             }
+            // literal buffer placement (ZSTD_allocateLiteralsBuffer :44-73): with room behind the block the reference stores the literals in
+            // dst at +128 KiB + 32 and the sequences may only write up to there; raw literals with 32 readable bytes behind them stay in src
+            {
+                bool const direct = it.litType == kLitRaw && (litSectionSize + 32 <= bsize);
+                if (!direct && capLeft > kBlockSizeMax + 32 + it.litSize + 32) it.blkLimit = it.outPos + kBlockSizeMax + 32;
+            }
+            // An error from here on sits BEHIND the literal section: the reference decodes Huffman literals first (corruption_detected if
+            // they are damaged) and only then parses the sequence section, so with Huffman literals the verdict is left to dec_huf
+            bool const hufFirst = it.litType == kLitHuf;
+            uint32_t late = 0;
             // sequences header
             uint32_t serr = 0;
             uint32_t const shs = setup_seq_headers(it, p, item, sc, b + litSectionSize, bsize - litSectionSize, &serr);
-            if (shs == 0xFFFFFFFFu) { setup_fail(it, serr); break; }
-            it.seqOff = pos + litSectionSize + shs; it.seqLen = bsize - litSectionSize - shs;
-            if (it.nbSeq) {
-                if (it.nbSeq > kSeqCap) { setup_fail(it, kCorruptionDetected); break; }
-                if (it.seqLen < 1) { setup_fail(it, kCorruptionDetected); break; }              // BIT_initDStream error -> corruption (:2697)
-                it.fseEntropy = 1;
-                uint32_t const slot = atomicAdd(&p.counters[1], 1u); p.seqList[slot] = item;
-            } else {
-                if (it.litSize > capLeft) { setup_fail(it, kDstSizeTooSmall); break; }           // last literals copy :2748
+            if (shs == 0xFFFFFFFFu) late = serr;
+            else {
+                it.seqOff = pos + litSectionSize + shs; it.seqLen = bsize - litSectionSize - shs;
+                if (it.nbSeq) {
+                    if (it.nbSeq > kSeqCap) late = kCorruptionDetected;
+                    else if (it.seqLen < 1) late = kCorruptionDetected;                          // BIT_initDStream error -> corruption (:2697)
+                    else it.fseEntropy = 1;
+                } else if (it.litSize > it.blkLimit - it.outPos) late = kDstSizeTooSmall;         // last literals copy :2748
             }
-            if (it.litType == kLitHuf) { uint32_t const slot = atomicAdd(&p.counters[0], 1u); p.hufList[slot] = item; }
+            if (late && !hufFirst) { setup_fail(it, late); break; }
+            if (late) { it.deferErr = late; it.nbSeq = 0; sc.tabAct[0] = sc.tabAct[1] = sc.tabAct[2] = 0; }
+            else if (it.nbSeq) { uint32_t const slot = atomicAdd(&p.counters[1], 1u); p.seqList[slot] = item; }
+            if (hufFirst) { uint32_t const slot = atomicAdd(&p.counters[0], 1u); p.hufList[slot] = item; }
         } while (0);
     }
     __syncwarp();
@@ -1021,6 +1033,7 @@ __global__ void __launch_bounds__(kHufThreads) dec_huf_kernel(DecPass p)
         bool const accept = s_inexact[slot] == 1 && it.hufX2 && huf_x2_replay(p, item, it);
         if (!accept) { it.errCode = kCorruptionDetected; it.status = kStError; }
     }
+    if (stream == 0 && slot < nHere && it.status == kStRunning && it.deferErr) { it.errCode = it.deferErr; it.status = kStError; }    // the literals were sound
 }
 
 // =====================================================================================================
@@ -1124,7 +1137,7 @@ __global__ void __launch_bounds__(32) dec_seq_kernel(DecPass p)
     br.settle();
     int32_t const gz = (int32_t)br.gZero;
     uint32_t rep0 = it.rep[0], rep1 = it.rep[1], rep2 = it.rep[2];
-    uint32_t outPos = it.outPos; uint32_t const outPos0 = outPos, dstCap = it.dstCap;
+    uint32_t outPos = it.outPos; uint32_t const outPos0 = outPos, dstCap = it.blkLimit;      // the block's write limit (<= the item's capacity)
     uint32_t const frameStart = it.frameStart - it.prefix;      // virtualStart: the dictionary content sits right in front of the frame (wraps below 0: unsigned differences stay right)
     uint32_t litPos = 0; uint32_t const litSize = it.litSize;
     uint32_t aL = kFseLLOff, aO = kFseOFOff, aM = kFseMLOff;

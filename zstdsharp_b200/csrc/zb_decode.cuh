@@ -73,7 +73,10 @@ struct __align__(16) DecItem {
     uint32_t blockOut;      // regenerated size of this block (literals-only part added by exec)
     uint32_t seqLitEnd;     // literals consumed by the sequences (set by seq_decode)
     uint32_t prefix;        // bytes of dictionary content that sit in front of the current frame's output (0 without a dictionary)
-    uint32_t _pad1[2];
+    uint32_t blkLimit;      // outPos up to which the sequences of this block may write: the reference keeps the block's literals inside
+                            // dst when there is room (ZSTD_in_dst, at +128 KiB + 32) and its sequences stop there (ZstdDecompressBlock.cs:44-73, :2668)
+    uint32_t deferErr;      // an error found behind a Huffman literal section: the reference decodes the literals first, so it only counts
+                            // if they turn out to be sound (dec_huf_kernel reports it)
 };
 
 // Dictionary of a decode context (ZSTD_decompress_insertDictionary, ZstdDecompress.cs:1880): parsed once on the device.
