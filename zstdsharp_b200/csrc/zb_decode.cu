@@ -1681,13 +1681,20 @@ __global__ void __launch_bounds__(kRawThreads) dec_rawcopy_kernel(DecPass p)
         uint32_t const sh = (uint32_t)((uintptr_t)src & 15), w0 = sh >> 2, bsh = (sh & 3) * 8;
         const uint4* const s4 = (const uint4*)(src - sh);
         uint32_t const nChunks = n >> 4;
-        for (uint32_t c0 = t; c0 < nChunks; c0 += 4 * kRawThreads) {
+        for (uint32_t base = 0; base < nChunks; base += 4 * kRawThreads) {     // uniform trip count: the shuffles below need the whole warp
+            uint32_t const c0 = base + t;
             uint4 a[4], b[4];
 #pragma unroll
             for (int k = 0; k < 4; k++) {
                 uint32_t const c = c0 + kRawThreads * k;
-                a[k] = c < nChunks ? __ldcs(s4 + c) : make_uint4(0, 0, 0, 0);
-                b[k] = (c < nChunks && sh) ? __ldcs(s4 + c + 1) : make_uint4(0, 0, 0, 0);
+                a[k] = (c < nChunks || (c == nChunks && sh)) ? __ldg(s4 + c) : make_uint4(0, 0, 0, 0);      // one chunk more: the last full chunk's successor
+                b[k] = (c < nChunks && sh && (t & 31) == 31) ? __ldg(s4 + c + 1) : make_uint4(0, 0, 0, 0);    // the successor chunk is the next lane's chunk
+            }
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                uint4 const nx = make_uint4(__shfl_down_sync(0xFFFFFFFFu, a[k].x, 1), __shfl_down_sync(0xFFFFFFFFu, a[k].y, 1),
+                                            __shfl_down_sync(0xFFFFFFFFu, a[k].z, 1), __shfl_down_sync(0xFFFFFFFFu, a[k].w, 1));
+                if ((t & 31) != 31) b[k] = nx;
             }
 #pragma unroll
             for (int k = 0; k < 4; k++) {
