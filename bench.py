@@ -33,7 +33,13 @@ from zstdsharp_b200.sharding import shard_bounds  # noqa: E402
 
 FRAME = dg.FRAME
 METRIC = "decompress & level-1 compress GB/s (128KB frames) at 1/2/4/8 B200 vs CPU"
-UNIQUE_FRAMES = 512          # 64 MiB of generated corpus, tiled up to the batch size (every frame is a genuine sample)
+UNIQUE_FRAMES = 4096         # 512 MiB of generated corpus (8 differently seeded 64 MiB blocks), tiled 2x up to the batch size
+
+
+def make_corpus(fn, seed0: int, uniq: int) -> np.ndarray:
+    """`uniq` frames of workload `fn`: blocks of 512 frames, block k generated with seed0 + 512 k (block 0 = the workload's default seed)."""
+    parts = [fn(min(512, uniq - k) * FRAME, seed0 + k) if k else fn(min(512, uniq) * FRAME) for k in range(0, uniq, 512)]
+    return parts[0] if len(parts) == 1 else np.concatenate(parts)
 
 
 def log(*a):
@@ -93,11 +99,11 @@ class ClockSampler:
 # ----------------------------------------------------------------------------------------------------------------
 #  CPU side (oracle port of the reference algorithm): --impl reference and the cpu_baseline leg
 # ----------------------------------------------------------------------------------------------------------------
-def cpu_frames(level: int = 1, nframes: int = UNIQUE_FRAMES, workload: str = "text"):
+def cpu_frames(level: int = 1, nframes: int = 512, workload: str = "text"):
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     from _oracle import oracle
     o = oracle()
-    data = dg.WORKLOADS[workload](nframes * FRAME)
+    data = make_corpus(dg.WORKLOADS[workload], dg.SEED_TEXT if workload == "text" else dg.SEED_SILESIA, nframes) if workload in ("text", "silesia") else dg.WORKLOADS[workload](nframes * FRAME)
     chunks = [data[i * FRAME:(i + 1) * FRAME] for i in range(nframes)]
     threads = os.cpu_count() or 1
     with ThreadPoolExecutor(threads) as ex:
@@ -227,7 +233,7 @@ def run_reference(args):
     threads = os.cpu_count() or 1
     r = ref_dll()
     nframes = args.frames
-    uniq = min(UNIQUE_FRAMES, nframes)
+    uniq = min(args.unique, nframes)
     o, chunks, frames, _ = cpu_frames(1, uniq, "text")      # frames: the oracle's = the DLL's bytes (tests/test_reference_pin.py)
     port_b, port_t = cpu_decode_pass(o, frames[:256], threads, seconds_min=1.0)
     port = port_b / port_t / 1e9
@@ -257,7 +263,7 @@ def run_reference(args):
         sample = (f"the whole configs[1] batch every step: {nframes} text-like 128 KiB level-1 frames ({nframes * FRAME >> 20} MiB out) decoded by the "
                   f"reference's own libzstd.dll (zstd 1.5.1, oracle/_ref) on {threads} host threads, one ZSTD_DCtx per thread")
         del job
-        sil = dg.silesia_mix(uniq * FRAME).reshape(uniq, FRAME)
+        sil = make_corpus(dg.silesia_mix, dg.SEED_SILESIA, uniq).reshape(uniq, FRAME)
         cj = DllBatch(r, [sil[i % uniq] for i in range(nframes)], r.lib.ZREF_compressBound(FRAME), threads)
         cj.compress(1)
         t1 = time.perf_counter(); cj.compress(1); ct = time.perf_counter() - t1
@@ -268,7 +274,7 @@ def run_reference(args):
         "warmup": args.warmup, "ms_per_step": round(1e3 * dt / args.steps, 3), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u8", "data": "synthetic",
         "config": {"workload": "batch decompress 1 GiB of 128 KiB level-1 frames, bit-exact (BASELINE.json configs[1])", "frames_per_gpu": nframes,
-                   "frame_bytes": FRAME, "corpus": f"text_like seed 0x{dg.SEED_TEXT:X}: {uniq} unique frames tiled to {nframes}",
+                   "frame_bytes": FRAME, "corpus": f"text_like seed 0x{dg.SEED_TEXT:X} (+512 per 64 MiB block): {uniq} unique frames tiled to {nframes}",
                    "note": "reference arm = the reference's own native zstd 1.5.1 binary (src/Zstd.Extern/libzstd.dll through oracle/ref_pe); ZstdSharp's "
                            "managed translation of this code cannot run here (no .NET) and is 1.41x slower by the reference's README.md:44-58"},
         "cpu_baseline": {"value": round(val, 4), "unit": "GB/s", "cores": threads, "kind": kind, "sample": sample},
@@ -368,11 +374,8 @@ def run_b200(args):
 
     # ------------------------------------------------------------------ corpus + compressed frames (made by the GPU encoder)
     t_prep = time.perf_counter()
-    def corpus(fn, seed0):       # blocks of 512 frames with different seeds (--unique above 512: no tiling of the same 64 MiB)
-        parts = [fn(min(512, uniq - k) * FRAME, seed0 + k) if k else fn(min(512, uniq) * FRAME) for k in range(0, uniq, 512)]
-        return parts[0] if len(parts) == 1 else np.concatenate(parts)
-    text = corpus(dg.text_like, dg.SEED_TEXT)
-    sil = corpus(dg.silesia_mix, dg.SEED_SILESIA)
+    text = make_corpus(dg.text_like, dg.SEED_TEXT, uniq)
+    sil = make_corpus(dg.silesia_mix, dg.SEED_SILESIA, uniq)
     d_text_u = torch.from_numpy(text).cuda()
     d_sil_u = torch.from_numpy(sil).cuda()
     bound = comp.GetCompressBound(FRAME)
@@ -692,7 +695,7 @@ def run_b200(args):
             "ms_per_step": round(dev_ms / args.steps, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u8", "data": "synthetic",
             "config": {"workload": "batch decompress 1 GiB of 128 KiB level-1 frames, bit-exact (BASELINE.json configs[1]); value = decompress, compress_l1 = configs[2]",
-                       "frames_per_gpu": nframes, "frame_bytes": FRAME, "corpus": f"text_like seed 0x{dg.SEED_TEXT:X}: {uniq} unique frames tiled to {nframes}",
+                       "frames_per_gpu": nframes, "frame_bytes": FRAME, "corpus": f"text_like seed 0x{dg.SEED_TEXT:X} (+512 per 64 MiB block): {uniq} unique frames tiled to {nframes}",
                        "compressed_bytes_per_gpu": ctotal, "parallelism": f"host scatter, {world} rank(s), no collective",
                        "l2": "inputs larger than L2 (compressed batch %.0f MB + 1 GiB output per step)" % (ctotal / 1e6)},
             "wall_ms_per_step": round(wall_ms / args.steps, 4),
