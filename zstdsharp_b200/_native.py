@@ -10,7 +10,8 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "_build", "libzstdb200.so")
+# ZSTDB200_LIB selects another build of the same library (the assertion build: make -C zstdsharp_b200/csrc debug)
+LIB_PATH = os.environ.get("ZSTDB200_LIB") or os.path.join(_HERE, "_build", "libzstdb200.so")
 
 TIMING_SLOTS = 12
 

@@ -6,7 +6,22 @@
 #pragma once
 #include <cstdint>
 #include <cstddef>
+#include <cstdio>
 #include <cuda_runtime.h>
+
+// Debug build (make -C zstdsharp_b200/csrc debug -> _build/libzstdb200_dbg.so, selected with ZSTDB200_LIB): index assertions on the
+// shared-memory tiles, staging blocks and per-item slots of every kernel.  compute-sanitizer is closed on this GPU pool, so this build,
+// run over the test suite and the randomised soak, is the memory-safety evidence (profiles/r02_notes.md).  Release builds compile it out.
+#ifndef ZB_DEBUG_MASK
+#define ZB_DEBUG_MASK 0xFFFF
+#endif
+#ifdef ZB_DEBUG_ASSERTS
+#define ZB_ASSERTK(k, cond) do { if (((ZB_DEBUG_MASK) >> (k)) & 1) ZB_ASSERT(cond); } while (0)
+#define ZB_ASSERT(cond) do { if (!(cond)) { printf("ZB_ASSERT failed %s:%d: %s (block %d thread %d)\n", __FILE__, __LINE__, #cond, (int)blockIdx.x, (int)threadIdx.x); __trap(); } } while (0)
+#else
+#define ZB_ASSERT(cond) do { } while (0)
+#define ZB_ASSERTK(k, cond) do { } while (0)
+#endif
 
 namespace zb {
 

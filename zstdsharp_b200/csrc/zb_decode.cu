@@ -739,8 +739,12 @@ __global__ void __launch_bounds__(kSetupWarps * 32) dec_setup_kernel(DecPass p)
 //  one funnel shift, with no branch: that keeps every lane of a warp on the same instruction stream, which is
 //  what bounds these latency-limited kernels (profiles/r01_notes.md).
 // =====================================================================================================
-__device__ __forceinline__ uint32_t lds32(uint32_t saddr) { uint32_t v; asm("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(saddr)); return v; }
-__device__ __forceinline__ uint32_t lds16(uint32_t saddr) { uint16_t v; asm("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(saddr)); return v; }
+// Shared-memory loads by 32-bit shared address.  `volatile` + "memory": the compiler must see them as memory reads, ordered after the
+// stores / cp.async waits that produce the data.  (Round 1 had plain `asm`: formally free to move across `cp.async.wait_group` and
+// `__syncwarp()`; it happened to work until the assertion build of round 2 perturbed the schedule and the last sequences of some frames
+// came out wrong, profiles/r02_notes.md.)
+__device__ __forceinline__ uint32_t lds32(uint32_t saddr) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(saddr) : "memory"); return v; }
+__device__ __forceinline__ uint32_t lds16(uint32_t saddr) { uint16_t v; asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(saddr) : "memory"); return v; }
 
 // top `nb` bits (0..31) of a left-justified word
 __device__ __forceinline__ uint32_t top_bits(uint32_t x, uint32_t nb) { return __funnelshift_l(x, 0u, nb); }   // one SHF: high word of (0:x) << nb
@@ -829,7 +833,7 @@ constexpr uint32_t kHufSmemLog = 11;
 constexpr uint32_t kHufSymBytes = 1u << kHufSmemLog, kHufLenBytes = 1u << (kHufSmemLog - 1), kHufItemBytes = kHufSymBytes + kHufLenBytes;
 constexpr uint32_t kHufChunk = 32;              // 4 x 32 B of ring per stream (8 symbols consume <= 12 bytes, a refill reads 12 more)
 constexpr uint32_t kHufSmemBytes = kHufThreads * 4 * kHufChunk + kHufItemsPerCta * kHufItemBytes;
-__device__ __forceinline__ uint32_t lds8u(uint32_t saddr) { uint16_t v; asm("ld.shared.u8 %0, [%1];" : "=h"(v) : "r"(saddr)); return v; }
+__device__ __forceinline__ uint32_t lds8u(uint32_t saddr) { uint16_t v; asm volatile("ld.shared.u8 %0, [%1];" : "=h"(v) : "r"(saddr) : "memory"); return v; }
 
 __device__ __forceinline__ uint32_t lit_segment_stride(uint32_t litSize) { uint32_t const seg = (litSize + 3) / 4; return (seg + 15) & ~15u; }
 
@@ -1006,6 +1010,7 @@ __global__ void __launch_bounds__(kHufThreads) dec_huf_kernel(DecPass p)
                     G -= used;
                     v[q] = acc;
                 }
+                ZB_ASSERTK(0, outOff + i + 16 <= kLitStride);
                 *(uint4*)(out + i) = make_uint4(v[0], v[1], v[2], v[3]);
             }
             for (; i < count && (int32_t)G >= gz; i++) {
@@ -1050,7 +1055,7 @@ constexpr uint32_t kSeqTab16Bytes = kFseTableEntries * 2, kSeqTab8Bytes = kFseTa
 constexpr uint32_t kSeqItemBytes = kSeqTab16Bytes + kSeqTab8Bytes;
 constexpr uint32_t kSeqFlush = 8;              // sequences per record flush
 constexpr uint32_t kSeqSmemBytes = kSeqItemsPerCta * (kSeqItemBytes + 4 * kSeqChunk) + kSeqFlush * kSeqItemsPerCta * 8;
-__device__ __forceinline__ uint32_t lds8(uint32_t saddr) { uint16_t v; asm("ld.shared.u8 %0, [%1];" : "=h"(v) : "r"(saddr)); return v; }
+__device__ __forceinline__ uint32_t lds8(uint32_t saddr) { uint16_t v; asm volatile("ld.shared.u8 %0, [%1];" : "=h"(v) : "r"(saddr) : "memory"); return v; }
 
 // BIT_readBits / BIT_readBitsFast exactly as the reference behaves near, at and beyond the START of a backward bit stream
 // (Bitstream.cs:189-264, 293-340, 381-424).  R = unread bits before the read.  While R >= 0 a read that runs past the start is filled
@@ -1059,34 +1064,35 @@ __device__ __forceinline__ uint32_t lds8(uint32_t saddr) { uint16_t v; asm("ld.s
 // eight bytes again.  The sequence decoder only checks the stream AFTER the last sequence (status >= completed,
 // ZstdDecompressBlock.cs:2730), so a corrupted stream that runs dry early is still decoded and executed if its lengths and offsets
 // happen to be valid; a valid stream gets here with its last few sequences (dec_seq_kernel's tail loop).
-__device__ __noinline__ uint32_t seq_bits_near_start(const uint8_t* s, uint32_t len, int32_t R, uint32_t nb)
-{
-    if (nb == 0) return 0;
-    uint64_t w = 0; uint32_t sh;
-    if (R <= 0) {                                                                                 // R == 0: bitsConsumed == 64, the shift count is already 0
-        for (int j = 7; j >= 0; j--) w = (w << 8) | ((uint32_t)j < len ? s[j] : 0u);              // the container at ptr == start
-        sh = (uint32_t)(-R) & 63u;
-    } else {
-        int32_t const hiB = (R - 1) >> 3;                                                         // byte that holds the next unread bit
-        for (int j = 0; j < 8; j++) { int32_t const b = hiB - j; w = (w << 8) | (b >= 0 ? s[b] : 0u); }
-        sh = 7u - ((uint32_t)(R - 1) & 7u);
+// The first 16 bytes of the stream held in registers (bytes past the stream's end read as zero): every read of the tail loop
+// (R < kSeqTailBits = 96 unread bits) and of a stream shorter than its three initial states comes out of these two words.
+struct NearStart {
+    uint64_t lo, hi;                                                                               // stream bytes 0..7, 8..15 (little endian)
+    __device__ __forceinline__ void load(const uint8_t* s, uint32_t len)
+    {
+        lo = hi = 0;
+#pragma unroll
+        for (int j = 7; j >= 0; j--) { lo = (lo << 8) | ((uint32_t)j < len ? s[j] : 0u); hi = (hi << 8) | ((uint32_t)(j + 8) < len ? s[j + 8] : 0u); }
     }
-    return (uint32_t)((w << sh) >> (64 - nb));
-}
-// BIT_readBits (Bitstream.cs:303-306, 329-336: BIT_getMiddleBits, used by FSE_initDState and by the FSE state updates) is NOT
-// BIT_readBitsFast near the stream start: container >> ((64 - bitsConsumed - nbBits) & 63), masked to nbBits.  A read that runs
-// past the start therefore returns bits from the TOP of the first eight bytes in its low positions instead of zero-filled real
-// bits.  (A read past the container only happens once the container sits at the stream start: before that a sequence consumes at
-// most 7 + 31 + 16 = 54 bits up to its mid reload and 7 + 30 + 26 = 63 without one.)  Found by the soak: 3 damaged frames of 80000
-// that the reference decodes were decoded to other bytes / rejected while every state update was read with the fast form.
-__device__ __noinline__ uint32_t seq_state_bits_near_start(const uint8_t* s, uint32_t len, int32_t R, uint32_t nb)
-{
-    if (nb == 0) return 0;
-    if (R >= (int32_t)nb) return seq_bits_near_start(s, len, R, nb);                              // inside the stream: an ordinary read
-    uint64_t w = 0;
-    for (int j = 7; j >= 0; j--) w = (w << 8) | ((uint32_t)j < len ? s[j] : 0u);                  // the container at ptr == start
-    return (uint32_t)(w >> ((uint32_t)(R - (int32_t)nb) & 63u)) & ((1u << nb) - 1u);
-}
+    // BIT_readBitsFast (also what BIT_readBits returns inside the stream): R <= 127
+    __device__ __forceinline__ uint32_t bits(int32_t R, uint32_t nb) const
+    {
+        if (nb == 0) return 0;
+        uint32_t const mask = (1u << nb) - 1u;                                                     // nb <= 31
+        if (R <= 0) return (uint32_t)((lo << ((uint32_t)(-R) & 63u)) >> (64 - nb));                // R == 0: bitsConsumed == 64, shift count 0
+        if (R < (int32_t)nb) return ((uint32_t)lo << (nb - (uint32_t)R)) & mask;                   // runs past the start: zero filled
+        uint32_t const sft = (uint32_t)R - nb;                                                     // 0..127
+        uint64_t const v = sft >= 64 ? hi >> (sft - 64) : (sft ? (lo >> sft) | (hi << (64 - sft)) : lo);
+        return (uint32_t)v & mask;
+    }
+    // BIT_readBits (BIT_getMiddleBits): a read past the start takes bits from the TOP of the first eight bytes
+    __device__ __forceinline__ uint32_t state_bits(int32_t R, uint32_t nb) const
+    {
+        if (nb == 0) return 0;
+        if (R >= (int32_t)nb) return bits(R, nb);
+        return (uint32_t)(lo >> ((uint32_t)(R - (int32_t)nb) & 63u)) & ((1u << nb) - 1u);
+    }
+};
 constexpr int32_t kSeqTailBits = 96;      // a sequence reads at most 31 + 16 + 16 extra bits and 9 + 9 + 8 state bits
 
 __global__ void __launch_bounds__(32) dec_seq_kernel(DecPass p)
@@ -1150,10 +1156,10 @@ __global__ void __launch_bounds__(32) dec_seq_kernel(DecPass p)
         aM = kFseMLOff + top_bits(x, mlLog);
         if ((int32_t)(G - (llLog + ofLog + mlLog)) < gz) {           // fewer bits than the three initial states need: the reference reads on
             int32_t const R = (int32_t)G - gz;
-            const uint8_t* const ss = p.src + it.srcOff + it.seqOff; uint32_t const sl = it.seqLen;
-            aL = kFseLLOff + seq_state_bits_near_start(ss, sl, R, llLog);
-            aO = kFseOFOff + seq_state_bits_near_start(ss, sl, R - (int32_t)llLog, ofLog);
-            aM = kFseMLOff + seq_state_bits_near_start(ss, sl, R - (int32_t)(llLog + ofLog), mlLog);
+            NearStart ns; ns.load(p.src + it.srcOff + it.seqOff, it.seqLen);
+            aL = kFseLLOff + ns.state_bits(R, llLog);
+            aO = kFseOFOff + ns.state_bits(R - (int32_t)llLog, ofLog);
+            aM = kFseMLOff + ns.state_bits(R - (int32_t)(llLog + ofLog), mlLog);
         }
         G -= llLog + ofLog + mlLog;
     }
@@ -1211,6 +1217,7 @@ __global__ void __launch_bounds__(32) dec_seq_kernel(DecPass p)
                 bool const e1 = seqLen > dstCap - outPos, e2 = ll > litSize - litPos, e3 = offset > (outPos + ll) - frameStart;
                 bool const e4 = (offset >> 30) != 0;                                             // offsets >= 1 GiB do not fit seq_pack
                 if (e1 | e2 | e3 | e4) err = e1 ? kDstSizeTooSmall : kCorruptionDetected;
+                ZB_ASSERTK(1, k * kSeqItemsPerCta + lane < kSeqFlush * kSeqItemsPerCta && n < kSeqCap);
                 s_stage[k * kSeqItemsPerCta + lane] = seq_pack(ll, ml, offset);
                 cnt = k + 1; nDone = n + 1;
                 outPos += seqLen; litPos += ll;
@@ -1229,7 +1236,7 @@ __global__ void __launch_bounds__(32) dec_seq_kernel(DecPass p)
     }
     // ---- tail: the sequences within kSeqTailBits of the stream start, bit reads as the reference does them there ----
     if (live && !err && nDone < nbSeq) {
-        const uint8_t* const ss = p.src + it.srcOff + it.seqOff; uint32_t const sl = it.seqLen;
+        NearStart ns; ns.load(p.src + it.srcOff + it.seqOff, it.seqLen);
         for (uint32_t n = nDone; n < nbSeq && !err; n++) {
             uint32_t const eL = lds16(t16 + 2 * aL), eO = lds16(t16 + 2 * aO), eM = lds16(t16 + 2 * aM);
             uint32_t const nL = lds8(t8 + aL), nO = lds8(t8 + aO), nM = lds8(t8 + aM);
@@ -1237,12 +1244,12 @@ __global__ void __launch_bounds__(32) dec_seq_kernel(DecPass p)
             uint32_t const nbL = eL & 15, nbM = eM & 15, nbO = eO & 15;
             uint32_t const llSym = (eL >> 9) & 63, mlSym = (eM >> 9) & 63;
             int32_t R = (int32_t)G - gz;
-            uint32_t const ofExtra = seq_bits_near_start(ss, sl, R, ofBits); R -= (int32_t)ofBits;
-            uint32_t const ml = lds32(mlBaseS + mlSym * 4) + seq_bits_near_start(ss, sl, R, mlBits); R -= (int32_t)mlBits;
-            uint32_t const ll = lds32(llBaseS + llSym * 4) + seq_bits_near_start(ss, sl, R, llBits); R -= (int32_t)llBits;
-            aL = kFseLLOff + (nL | ((eL >> 15) << 8)) + seq_state_bits_near_start(ss, sl, R, nbL); R -= (int32_t)nbL;
-            aM = kFseMLOff + (nM | ((eM >> 15) << 8)) + seq_state_bits_near_start(ss, sl, R, nbM); R -= (int32_t)nbM;
-            aO = kFseOFOff + (nO | ((eO >> 15) << 8)) + seq_state_bits_near_start(ss, sl, R, nbO); R -= (int32_t)nbO;
+            uint32_t const ofExtra = ns.bits(R, ofBits); R -= (int32_t)ofBits;
+            uint32_t const ml = lds32(mlBaseS + mlSym * 4) + ns.bits(R, mlBits); R -= (int32_t)mlBits;
+            uint32_t const ll = lds32(llBaseS + llSym * 4) + ns.bits(R, llBits); R -= (int32_t)llBits;
+            aL = kFseLLOff + (nL | ((eL >> 15) << 8)) + ns.state_bits(R, nbL); R -= (int32_t)nbL;
+            aM = kFseMLOff + (nM | ((eM >> 15) << 8)) + ns.state_bits(R, nbM); R -= (int32_t)nbM;
+            aO = kFseOFOff + (nO | ((eO >> 15) << 8)) + ns.state_bits(R, nbO); R -= (int32_t)nbO;
             G = (uint32_t)(R + gz);
             uint32_t offset;
             {   // ZSTD_decodeSequence offset rules (:2397-2445)
@@ -1262,6 +1269,7 @@ __global__ void __launch_bounds__(32) dec_seq_kernel(DecPass p)
             bool const e1 = seqLen > dstCap - outPos, e2 = ll > litSize - litPos, e3 = offset > (outPos + ll) - frameStart;
             bool const e4 = (offset >> 30) != 0;
             if (e1 | e2 | e3 | e4) err = e1 ? kDstSizeTooSmall : kCorruptionDetected;
+            ZB_ASSERTK(2, n < kSeqCap);
             p.seq[seqBase + n] = seq_pack(ll, ml, offset);
             outPos += seqLen; litPos += ll;
         }
@@ -1472,6 +1480,7 @@ __global__ void __launch_bounds__(kExecWarps * 32) dec_exec_kernel(DecPass p)
                 {
                     // nothing fits: flush what we have, or (tile already empty) execute this one sequence straight in HBM
                     if (fill) {
+                        ZB_ASSERTK(3, (uint64_t)tileBase + fill <= it.dstCap);
                         warp_flush_tile(dst + tileBase, tile, fill, lane);
                         tileBase += fill; fill = 0; tile = tileMem + ((uintptr_t)(dst + tileBase) & 15);
                         __syncwarp();
@@ -1500,6 +1509,8 @@ __global__ void __launch_bounds__(kExecWarps * 32) dec_exec_kernel(DecPass p)
                 }
             }
             bool const mine = lane < take;
+            ZB_ASSERTK(4, fill + __shfl_sync(FULL, oEnd, take - 1) <= kExecTile);                     // the batch fits the tile
+            ZB_ASSERTK(5, !mine || (litPos + lEnd <= litSize && (uint64_t)tileBase + fill + oEnd <= it.dstCap));   // dec_seq validated every sequence
             // prefetch the next batch of records while this one is executed
             uint2 recNext = make_uint2(0u, 0u);
             if (seqBase + take + lane < nbSeq) recNext = aSeq[seqBase + take + lane];
@@ -1510,6 +1521,7 @@ __global__ void __launch_bounds__(kExecWarps * 32) dec_exec_kernel(DecPass p)
             int32_t const srcRel = (int32_t)mDst - (int32_t)of;          // tile-relative source (negative: behind the tile, in HBM)
             uint32_t const farN = (mine && ml && ml <= kExecLong && srcRel < 0) ? min(ml, (uint32_t)(-srcRel)) : 0u;
             uint32_t const farFast = farN <= 16 ? farN : 0u;             // longer far parts are copied in the rounds below
+            ZB_ASSERTK(6, !(mine && ml) || (int64_t)tileBase + (int64_t)srcRel >= -(int64_t)it.prefix);   // a match never reaches in front of the frame (or its dictionary content)
             {
                 uint32_t const d0 = fill + oStart;
                 // the per-lane path below handles a run that crosses at most ONE segment boundary: with four streams over fewer than
@@ -1613,6 +1625,7 @@ __global__ void __launch_bounds__(kExecWarps * 32) dec_exec_kernel(DecPass p)
         }
         // flush, then the last literals go straight to HBM (ZstdDecompressBlock.cs:2748-2760)
         __syncwarp();
+        ZB_ASSERTK(7, (uint64_t)tileBase + fill + (litSize - litPos) <= it.dstCap && litPos <= litSize);
         if (fill) { warp_flush_tile(dst + tileBase, tile, fill, lane); tileBase += fill; }
         uint32_t const lastLL = litSize - litPos;
         L.to_global(dst + tileBase, litPos, lastLL, lane);
@@ -1662,6 +1675,7 @@ __global__ void __launch_bounds__(kRawThreads) dec_rawcopy_kernel(DecPass p)
         uint32_t const lo = (u % kRawSegsPerBlock) * kRawSeg, size = it.blkSize;
         if (lo >= size) continue;
         uint32_t n = min(kRawSeg, size - lo);
+        ZB_ASSERTK(8, (uint64_t)it.outPos + size <= it.dstCap && (it.blkType == kBlkRle || (uint64_t)it.blkSrcOff + size <= it.srcSize));
         uint8_t* dst = p.dst + it.dstOff + it.outPos + lo;
         uint32_t const t = threadIdx.x;
         uint32_t const head = min(n, (uint32_t)((16 - ((uintptr_t)dst & 15)) & 15));
@@ -1760,15 +1774,44 @@ static unsigned raw_grid(const DecPass& p)
     return (unsigned)std::min<uint64_t>((uint64_t)sms * 8, (uint64_t)p.nItems * kRawSegsPerBlock);
 }
 
+#ifdef ZB_DEBUG_ASSERTS
+// developer aid of the assertion build (ZSTDB200_DUMP_ITEM=<item>): the last literals and the last output bytes of one item between kernels
+__global__ void dec_debug_dump_kernel(DecPass p, uint32_t item, int stage)
+{
+    DecItem const& it = p.items[item];
+    uint32_t const litSize = it.litSize, seg = (litSize + 3) / 4, stride = lit_segment_stride(litSize);
+    const uint8_t* lb = p.litBuf + (size_t)item * kLitStride;
+    printf("dump stage %d item %u: status %u litType %u litSize %u nbSeq %u outPos %u | last literals:", stage, item, it.status, it.litType, litSize, it.nbSeq, it.outPos);
+    for (uint32_t i = litSize >= 12 ? litSize - 12 : 0; i < litSize; i++) { uint32_t const sgi = it.nStreams == 4 ? min(3u, i / seg) : 0u; printf(" %02x", lb[i + sgi * (stride - seg)]); }
+    if (stage >= 2) {
+        printf(" | last records:");
+        for (uint32_t n = it.nbSeq >= 4 ? it.nbSeq - 4 : 0; n < it.nbSeq; n++) { uint32_t ll, ml, of; seq_unpack(p.seq[(size_t)item * kSeqCap + n], ll, ml, of); printf(" (%u,%u,%u)", ll, ml, of); }
+    }
+    printf(" | dst tail:");
+    for (uint32_t i = it.dstCap >= 12 ? it.dstCap - 12 : 0; i < it.dstCap; i++) printf(" %02x", p.dst[it.dstOff + i]);
+    printf("\n");
+}
+static void debug_dump(const DecPass& p, cudaStream_t s, int stage)
+{
+    static int const item = []() { const char* e = getenv("ZSTDB200_DUMP_ITEM"); return e ? atoi(e) : -1; }();
+    if (item >= 0 && (uint32_t)item < p.nItems) dec_debug_dump_kernel<<<1, 1, 0, s>>>(p, (uint32_t)item, stage);
+}
+#else
+static inline void debug_dump(const DecPass&, cudaStream_t, int) {}
+#endif
+
 void dec_launch_wave(const DecPass& p, cudaStream_t s)
 {
     dec_reset_counters_kernel<<<1, 32, 0, s>>>(p.counters);
     dec_setup_kernel<<<(p.nItems + kSetupWarps - 1) / kSetupWarps, kSetupWarps * 32, 0, s>>>(p);
     dec_set_attrs();
     dec_huf_kernel<<<(p.nItems + kHufItemsPerCta - 1) / kHufItemsPerCta, kHufThreads, kHufSmemBytes, s>>>(p);
+    debug_dump(p, s, 1);
     dec_seq_kernel<<<(p.nItems + kSeqItemsPerCta - 1) / kSeqItemsPerCta, 32, kSeqSmemBytes, s>>>(p);
+    debug_dump(p, s, 2);
     dec_rawcopy_kernel<<<raw_grid(p), kRawThreads, 0, s>>>(p);
     dec_exec_kernel<<<(p.nItems + kExecWarps - 1) / kExecWarps, kExecWarps * 32, kExecWarps * kExecTileMem, s>>>(p);
+    debug_dump(p, s, 3);
 }
 
 void dec_launch_wave_timed(const DecPass& p, cudaStream_t s, cudaEvent_t* ev)

@@ -301,6 +301,7 @@ __global__ void __launch_bounds__(32 * kMatchWarps) enc_match_group_kernel(EncPa
         }
         // ---- sequence, post-match inserts (:251-263), next state ----
         if (ev) {
+            ZB_ASSERT(nseq < kEncSeqCap && mpos >= anchor && msrc >= lowPos && msrc < mpos && mpos + mlen <= srcSize);
             if (l == 0) { oLL[nseq] = (uint32_t)(mpos - anchor); oOF[nseq] = offcode + 1; oML[nseq] = (uint32_t)mlen - 3; }
             nseq++;
             int const mend = mpos + mlen;
@@ -481,6 +482,7 @@ __global__ void __launch_bounds__(32 * kMatchWarps) enc_match_dfast_group_kernel
                 off2 = off1; off1 = offset; offcode = offset + 2;
                 if (l == 0 && se < 4 && p1e <= ilimit) TL[hln] = tab_entry<TAG>((uint32_t)p1e + 2, x4n);   // complementary insertion (:210-213): hashLong[hl1] = ip1
             }
+            ZB_ASSERT(nseq < kEncSeqCap && mpos >= anchor && msrc >= lowPos && msrc < mpos && mpos + mlen <= srcSize);
             if (l == 0) { oLL[nseq] = (uint32_t)(mpos - anchor); oOF[nseq] = offcode + 1; oML[nseq] = (uint32_t)mlen - 3; }
             nseq++;
             int const mend = mpos + mlen;
@@ -1039,6 +1041,7 @@ __global__ void __launch_bounds__(kEntThreads, MB ? 8 : 15) enc_entropy_kernel(E
             uint32_t const lastLL = it.lastLL;
             for (uint32_t k = tid; k < lastLL; k += kEntThreads) lit[litPos + k] = src[srcSize - lastLL + k];
             litSize = litPos + lastLL;
+            ZB_ASSERT(litSize <= kBlockSizeMax);
         }
         for (uint32_t k = tid; k < 1024; k += kEntThreads) (&S.hist[0][0])[k] = 0;
         __syncthreads();
