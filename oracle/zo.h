@@ -35,6 +35,9 @@ size_t zo_compress_advanced(void* dst, size_t dstCapacity, const void* src, size
                             int level, int checksumFlag);
 
 /* Context-reusing variants (one context per thread, as the reference's tests do: ZstdNetTests.cs:498-522). */
+/* Compressor.LoadDictionary(dict) + Wrap(src): one frame by the CDict the first ZSTD_compress2 builds from the loaded bytes */
+size_t zo_compress_usingLoadedDict(void* dst, size_t dstCapacity, const void* src, size_t srcSize,
+                                   const void* dict, size_t dictSize, int level, int checksumFlag);
 void*  zo_createCCtx(void);
 void   zo_freeCCtx(void* cctx);
 size_t zo_compressCCtx(void* cctx, void* dst, size_t dstCapacity, const void* src, size_t srcSize, int level, int checksumFlag);

@@ -170,4 +170,8 @@ static inline U64 zo_xxh64(const void* src, size_t len, U64 seed)
     return h;
 }
 
+/* zo_decode.c: entropy-header readers also used by the encode side's dictionary loader */
+size_t zo_FSE_readNCount(S16* normalizedCounter, unsigned* maxSVPtr, unsigned* tableLogPtr, const void* headerBuffer, size_t hbSize);
+size_t zo_HUF_readStats(BYTE* huffWeight, size_t hwSize, U32* rankStats, U32* nbSymbolsPtr, U32* tableLogPtr, const void* src, size_t srcSize);
+
 #endif /* ZO_COMMON_H */

@@ -1303,3 +1303,9 @@ const char* zo_getErrorName(size_t code)
     default: return "Unspecified error code";
     }
 }
+
+/* entropy-header readers shared with the encode side's dictionary loader (zo_encode.c, ZSTD_loadCEntropy) */
+size_t zo_FSE_readNCount(S16* normalizedCounter, unsigned* maxSVPtr, unsigned* tableLogPtr, const void* headerBuffer, size_t hbSize)
+{ return FSE_readNCount(normalizedCounter, maxSVPtr, tableLogPtr, headerBuffer, hbSize); }
+size_t zo_HUF_readStats(BYTE* huffWeight, size_t hwSize, U32* rankStats, U32* nbSymbolsPtr, U32* tableLogPtr, const void* src, size_t srcSize)
+{ return HUF_readStats(huffWeight, hwSize, rankStats, nbSymbolsPtr, tableLogPtr, src, srcSize); }

@@ -1,8 +1,8 @@
 /*
  * zo_encode.c -- CPU ORACLE, encode side (test infrastructure only; see zo_common.h).
  *
- * Restates, in plain C, the reference's one-shot no-dictionary compressor for strategies ZSTD_fast and
- * ZSTD_dfast (levels 1..3):
+ * Restates, in plain C, the reference's one-shot compressor for strategies ZSTD_fast and ZSTD_dfast (levels 1..3, the
+ * negative levels, level 4 where it is still ZSTD_dfast), without and with a loaded dictionary:
  *   Compressor.Wrap -> ZSTD_compress2 -> ZSTD_compressEnd -> ZSTD_compress_frameChunk
  *     -> ZSTD_compressBlock_internal -> ZSTD_buildSeqStore (ZSTD_compressBlock_fast / _doubleFast)
  *        -> ZSTD_entropyCompressSeqStore (ZSTD_compressLiterals / HUF_*, ZSTD_buildSequencesStatistics / FSE_*,
@@ -971,7 +971,8 @@ static size_t ZSTD_entropyCompressSeqStore(seqStore_t* seqStorePtr, const ZSTD_e
  *  Match finders -- ZstdFast.cs:96, ZstdDoubleFast.cs:51, helpers ZstdCompressInternal.cs:204-437
  * ===================================================================================== */
 typedef struct { const BYTE* base; U32 dictLimit; U32 lowLimit; } ZSTD_window_t;
-typedef struct { ZSTD_window_t window; U32* hashTable; U32* chainTable; cParams_t cParams; } ZSTD_matchState_t;
+typedef struct ZSTD_matchState_s { ZSTD_window_t window; U32* hashTable; U32* chainTable; cParams_t cParams;
+                                   U32 loadedDictEnd; const struct ZSTD_matchState_s* dictMatchState; U32 dictEndIndex; } ZSTD_matchState_t;   /* dictEndIndex: dms->window.nextSrc - base */
 
 static const U32 prime4bytes = 2654435761U;
 static const U64 prime5bytes = 889523592379ULL;
@@ -1011,11 +1012,19 @@ static void ZSTD_storeSeq(seqStore_t* seqStorePtr, size_t litLength, const BYTE*
     seqStorePtr->sequences[0].matchLength = (U16)mlBase;
     seqStorePtr->sequences++;
 }
-static U32 ZSTD_getLowestPrefixIndex(const ZSTD_matchState_t* ms, U32 curr, unsigned windowLog)   /* :802 (no dictionary) */
+static U32 ZSTD_getLowestPrefixIndex(const ZSTD_matchState_t* ms, U32 curr, unsigned windowLog)   /* :802 */
 {
     U32 const maxDistance = 1U << windowLog;
     U32 const lowestValid = ms->window.dictLimit;
-    return (curr - lowestValid > maxDistance) ? curr - maxDistance : lowestValid;
+    U32 const withinWindow = (curr - lowestValid > maxDistance) ? curr - maxDistance : lowestValid;
+    return ms->loadedDictEnd != 0 ? lowestValid : withinWindow;
+}
+static U32 ZSTD_getLowestMatchIndex(const ZSTD_matchState_t* ms, U32 curr, unsigned windowLog)   /* :787 */
+{
+    U32 const maxDistance = 1U << windowLog;
+    U32 const lowestValid = ms->window.lowLimit;
+    U32 const withinWindow = (curr - lowestValid > maxDistance) ? curr - maxDistance : lowestValid;
+    return ms->loadedDictEnd != 0 ? lowestValid : withinWindow;
 }
 #define ZSTD_REP_MOVE 2
 
@@ -1202,6 +1211,327 @@ _match_stored:
     }   }   }
 }
 
+
+/* =====================================================================================
+ *  Match finders with a dictionary -- ZstdFast.cs:390 (dictMatchState), :583 (extDict), ZstdDoubleFast.cs:250, :590.
+ *  The oracle keeps the dictionary content and the input in ONE buffer (content directly in front of the input), so
+ *  `dictBase + index` and `base + index` are the same address and ZSTD_count_2segments (ZstdCompressInternal.cs:283) is a
+ *  plain ZSTD_count up to iend; everything else (which indices are eligible, where a backward extension stops, the 3-byte
+ *  guard in front of the prefix start) is restated as the reference has it.
+ * ===================================================================================== */
+static size_t ZSTD_compressBlock_fast_dictMatchState(ZSTD_matchState_t* ms, seqStore_t* seqStore, U32 rep[3], const void* src, size_t srcSize)   /* ZstdFast.cs:390 */
+{
+    const cParams_t* const cParams = &ms->cParams;
+    U32* const hashTable = ms->hashTable; U32 const hlog = cParams->hashLog; U32 const mls = cParams->minMatch;
+    U32 const stepSize = cParams->targetLength + !(cParams->targetLength);
+    const BYTE* const base = ms->window.base; const BYTE* const istart = (const BYTE*)src; const BYTE* ip = istart; const BYTE* anchor = istart;
+    U32 const prefixStartIndex = ms->window.dictLimit; const BYTE* const prefixStart = base + prefixStartIndex;
+    const BYTE* const iend = istart + srcSize; const BYTE* const ilimit = iend - 8;
+    U32 offset_1 = rep[0], offset_2 = rep[1]; U32 const offsetSaved = 0;
+    const ZSTD_matchState_t* const dms = ms->dictMatchState;
+    const U32* const dictHashTable = dms->hashTable; U32 const dictStartIndex = dms->window.dictLimit;
+    U32 const dictIndexDelta = prefixStartIndex - ms->dictEndIndex;                     /* dms index d is byte base[d + delta] */
+    const BYTE* const dictStart = base + dictStartIndex + dictIndexDelta;
+    U32 const dictAndPrefixLength = (U32)(ip - prefixStart) + (ms->dictEndIndex - dictStartIndex);
+    U32 const dictHLog = dms->cParams.hashLog;
+    ip += (dictAndPrefixLength == 0);
+    while (ip < ilimit) {
+        size_t mLength; size_t const h = ZSTD_hashPtr(ip, hlog, mls);
+        U32 const curr = (U32)(ip - base); U32 const matchIndex = hashTable[h]; const BYTE* match = base + matchIndex;
+        U32 const repIndex = curr + 1 - offset_1; const BYTE* const repMatch = base + repIndex;
+        hashTable[h] = curr;
+        if (((U32)((prefixStartIndex - 1) - repIndex) >= 3) && (MEM_read32(repMatch) == MEM_read32(ip + 1))) {
+            mLength = ZSTD_count(ip + 1 + 4, repMatch + 4, iend) + 4;
+            ip++;
+            ZSTD_storeSeq(seqStore, (size_t)(ip - anchor), anchor, 0, mLength - MINMATCH);
+        } else if (matchIndex <= prefixStartIndex) {
+            size_t const dictHash = ZSTD_hashPtr(ip, dictHLog, mls);
+            U32 const dictMatchIndex = dictHashTable[dictHash]; const BYTE* dictMatch = base + dictMatchIndex + dictIndexDelta;
+            if (dictMatchIndex <= dictStartIndex || MEM_read32(dictMatch) != MEM_read32(ip)) { ip += ((ip - anchor) >> 8) + stepSize; continue; }
+            {   U32 const offset = (U32)(curr - dictMatchIndex - dictIndexDelta);
+                mLength = ZSTD_count(ip + 4, dictMatch + 4, iend) + 4;
+                while (((ip > anchor) & (dictMatch > dictStart)) && (ip[-1] == dictMatch[-1])) { ip--; dictMatch--; mLength++; }
+                offset_2 = offset_1; offset_1 = offset;
+                ZSTD_storeSeq(seqStore, (size_t)(ip - anchor), anchor, offset + ZSTD_REP_MOVE, mLength - MINMATCH);
+            }
+        } else if (MEM_read32(match) != MEM_read32(ip)) { ip += ((ip - anchor) >> 8) + stepSize; continue; }
+        else {
+            U32 const offset = (U32)(ip - match);
+            mLength = ZSTD_count(ip + 4, match + 4, iend) + 4;
+            while (((ip > anchor) & (match > prefixStart)) && (ip[-1] == match[-1])) { ip--; match--; mLength++; }
+            offset_2 = offset_1; offset_1 = offset;
+            ZSTD_storeSeq(seqStore, (size_t)(ip - anchor), anchor, offset + ZSTD_REP_MOVE, mLength - MINMATCH);
+        }
+        ip += mLength; anchor = ip;
+        if (ip <= ilimit) {
+            hashTable[ZSTD_hashPtr(base + curr + 2, hlog, mls)] = curr + 2;
+            hashTable[ZSTD_hashPtr(ip - 2, hlog, mls)] = (U32)(ip - 2 - base);
+            while (ip <= ilimit) {
+                U32 const current2 = (U32)(ip - base); U32 const repIndex2 = current2 - offset_2; const BYTE* const repMatch2 = base + repIndex2;
+                if (((U32)((prefixStartIndex - 1) - repIndex2) >= 3) && (MEM_read32(repMatch2) == MEM_read32(ip))) {
+                    size_t const repLength2 = ZSTD_count(ip + 4, repMatch2 + 4, iend) + 4;
+                    U32 const tmpOffset = offset_2; offset_2 = offset_1; offset_1 = tmpOffset;
+                    ZSTD_storeSeq(seqStore, 0, anchor, 0, repLength2 - MINMATCH);
+                    hashTable[ZSTD_hashPtr(ip, hlog, mls)] = current2;
+                    ip += repLength2; anchor = ip;
+                    continue;
+                }
+                break;
+    }   }   }
+    rep[0] = offset_1 ? offset_1 : offsetSaved; rep[1] = offset_2 ? offset_2 : offsetSaved;
+    return (size_t)(iend - anchor);
+}
+
+static size_t ZSTD_compressBlock_fast_extDict(ZSTD_matchState_t* ms, seqStore_t* seqStore, U32 rep[3], const void* src, size_t srcSize)   /* ZstdFast.cs:583 */
+{
+    const cParams_t* const cParams = &ms->cParams;
+    U32* const hashTable = ms->hashTable; U32 const hlog = cParams->hashLog; U32 const mls = cParams->minMatch;
+    U32 const stepSize = cParams->targetLength + !(cParams->targetLength);
+    const BYTE* const base = ms->window.base; const BYTE* const istart = (const BYTE*)src; const BYTE* ip = istart; const BYTE* anchor = istart;
+    U32 const endIndex = (U32)((size_t)(istart - base) + srcSize);
+    U32 const lowLimit = ZSTD_getLowestMatchIndex(ms, endIndex, cParams->windowLog);
+    U32 const dictStartIndex = lowLimit; const BYTE* const dictStart = base + dictStartIndex;
+    U32 const dictLimit = ms->window.dictLimit; U32 const prefixStartIndex = dictLimit < lowLimit ? lowLimit : dictLimit;
+    const BYTE* const prefixStart = base + prefixStartIndex;
+    const BYTE* const iend = istart + srcSize; const BYTE* const ilimit = iend - 8;
+    U32 offset_1 = rep[0], offset_2 = rep[1];
+    if (prefixStartIndex == dictStartIndex) return ZSTD_compressBlock_fast(ms, seqStore, rep, src, srcSize);
+    while (ip < ilimit) {
+        size_t const h = ZSTD_hashPtr(ip, hlog, mls);
+        U32 const matchIndex = hashTable[h]; const BYTE* match = base + matchIndex;
+        U32 const curr = (U32)(ip - base); U32 const repIndex = curr + 1 - offset_1; const BYTE* const repMatch = base + repIndex;
+        hashTable[h] = curr;
+        if ((((U32)((prefixStartIndex - 1) - repIndex) >= 3) & (offset_1 <= curr + 1 - dictStartIndex)) && (MEM_read32(repMatch) == MEM_read32(ip + 1))) {
+            size_t const rLength = ZSTD_count(ip + 1 + 4, repMatch + 4, iend) + 4;
+            ip++;
+            ZSTD_storeSeq(seqStore, (size_t)(ip - anchor), anchor, 0, rLength - MINMATCH);
+            ip += rLength; anchor = ip;
+        } else {
+            if ((matchIndex < dictStartIndex) || (MEM_read32(match) != MEM_read32(ip))) { ip += ((ip - anchor) >> 8) + stepSize; continue; }
+            {   const BYTE* const lowMatchPtr = matchIndex < prefixStartIndex ? dictStart : prefixStart;
+                U32 const offset = curr - matchIndex;
+                size_t mLength = ZSTD_count(ip + 4, match + 4, iend) + 4;
+                while (((ip > anchor) & (match > lowMatchPtr)) && (ip[-1] == match[-1])) { ip--; match--; mLength++; }
+                offset_2 = offset_1; offset_1 = offset;
+                ZSTD_storeSeq(seqStore, (size_t)(ip - anchor), anchor, offset + ZSTD_REP_MOVE, mLength - MINMATCH);
+                ip += mLength; anchor = ip;
+        }   }
+        if (ip <= ilimit) {
+            hashTable[ZSTD_hashPtr(base + curr + 2, hlog, mls)] = curr + 2;
+            hashTable[ZSTD_hashPtr(ip - 2, hlog, mls)] = (U32)(ip - 2 - base);
+            while (ip <= ilimit) {
+                U32 const current2 = (U32)(ip - base); U32 const repIndex2 = current2 - offset_2; const BYTE* const repMatch2 = base + repIndex2;
+                if ((((U32)((prefixStartIndex - 1) - repIndex2) >= 3) & (offset_2 <= curr - dictStartIndex)) && (MEM_read32(repMatch2) == MEM_read32(ip))) {   /* `curr`, not current2: as the reference has it (:676) */
+                    size_t const repLength2 = ZSTD_count(ip + 4, repMatch2 + 4, iend) + 4;
+                    U32 const tmpOffset = offset_2; offset_2 = offset_1; offset_1 = tmpOffset;
+                    ZSTD_storeSeq(seqStore, 0, anchor, 0, repLength2 - MINMATCH);
+                    hashTable[ZSTD_hashPtr(ip, hlog, mls)] = current2;
+                    ip += repLength2; anchor = ip;
+                    continue;
+                }
+                break;
+    }   }   }
+    rep[0] = offset_1; rep[1] = offset_2;
+    return (size_t)(iend - anchor);
+}
+
+static size_t ZSTD_compressBlock_doubleFast_dictMatchState(ZSTD_matchState_t* ms, seqStore_t* seqStore, U32 rep[3], const void* src, size_t srcSize)   /* ZstdDoubleFast.cs:250 */
+{
+    const cParams_t* const cParams = &ms->cParams; U32 const mls = cParams->minMatch;
+    U32* const hashLong = ms->hashTable; U32 const hBitsL = cParams->hashLog;
+    U32* const hashSmall = ms->chainTable; U32 const hBitsS = cParams->chainLog;
+    const BYTE* const base = ms->window.base; const BYTE* const istart = (const BYTE*)src; const BYTE* ip = istart; const BYTE* anchor = istart;
+    U32 const endIndex = (U32)((size_t)(istart - base) + srcSize);
+    U32 const prefixLowestIndex = ZSTD_getLowestPrefixIndex(ms, endIndex, cParams->windowLog);
+    const BYTE* const prefixLowest = base + prefixLowestIndex;
+    const BYTE* const iend = istart + srcSize; const BYTE* const ilimit = iend - 8;
+    U32 offset_1 = rep[0], offset_2 = rep[1]; U32 const offsetSaved = 0;
+    const ZSTD_matchState_t* const dms = ms->dictMatchState;
+    const U32* const dictHashLong = dms->hashTable; const U32* const dictHashSmall = dms->chainTable;
+    U32 const dictStartIndex = dms->window.dictLimit;
+    U32 const dictIndexDelta = prefixLowestIndex - ms->dictEndIndex;
+    const BYTE* const dictStart = base + dictStartIndex + dictIndexDelta;
+    U32 const dictHBitsL = dms->cParams.hashLog; U32 const dictHBitsS = dms->cParams.chainLog;
+    U32 const dictAndPrefixLength = (U32)(ip - prefixLowest) + (ms->dictEndIndex - dictStartIndex);
+    ip += (dictAndPrefixLength == 0);
+    while (ip < ilimit) {
+        size_t mLength; U32 offset;
+        size_t const h2 = ZSTD_hashPtr(ip, hBitsL, 8); size_t const h = ZSTD_hashPtr(ip, hBitsS, mls);
+        size_t const dictHL = ZSTD_hashPtr(ip, dictHBitsL, 8); size_t const dictHS = ZSTD_hashPtr(ip, dictHBitsS, mls);
+        U32 const curr = (U32)(ip - base);
+        U32 const matchIndexL = hashLong[h2]; U32 matchIndexS = hashSmall[h];
+        const BYTE* matchLong = base + matchIndexL; const BYTE* match = base + matchIndexS;
+        U32 const repIndex = curr + 1 - offset_1; const BYTE* const repMatch = base + repIndex;
+        hashLong[h2] = hashSmall[h] = curr;
+        if (((U32)((prefixLowestIndex - 1) - repIndex) >= 3) && (MEM_read32(repMatch) == MEM_read32(ip + 1))) {
+            mLength = ZSTD_count(ip + 1 + 4, repMatch + 4, iend) + 4;
+            ip++;
+            ZSTD_storeSeq(seqStore, (size_t)(ip - anchor), anchor, 0, mLength - MINMATCH);
+            goto _match_stored;
+        }
+        if (matchIndexL > prefixLowestIndex) {
+            if (MEM_read64(matchLong) == MEM_read64(ip)) {
+                mLength = ZSTD_count(ip + 8, matchLong + 8, iend) + 8;
+                offset = (U32)(ip - matchLong);
+                while (((ip > anchor) & (matchLong > prefixLowest)) && (ip[-1] == matchLong[-1])) { ip--; matchLong--; mLength++; }
+                goto _match_found;
+            }
+        } else {
+            U32 const dictMatchIndexL = dictHashLong[dictHL]; const BYTE* dictMatchL = base + dictMatchIndexL + dictIndexDelta;
+            if (dictMatchL > dictStart && MEM_read64(dictMatchL) == MEM_read64(ip)) {
+                mLength = ZSTD_count(ip + 8, dictMatchL + 8, iend) + 8;
+                offset = (U32)(curr - dictMatchIndexL - dictIndexDelta);
+                while (((ip > anchor) & (dictMatchL > dictStart)) && (ip[-1] == dictMatchL[-1])) { ip--; dictMatchL--; mLength++; }
+                goto _match_found;
+        }   }
+        if (matchIndexS > prefixLowestIndex) {
+            if (MEM_read32(match) == MEM_read32(ip)) goto _search_next_long;
+        } else {
+            U32 const dictMatchIndexS = dictHashSmall[dictHS];
+            match = base + dictMatchIndexS + dictIndexDelta;
+            matchIndexS = dictMatchIndexS + dictIndexDelta;
+            if (match > dictStart && MEM_read32(match) == MEM_read32(ip)) goto _search_next_long;
+        }
+        ip += ((ip - anchor) >> 8) + 1;
+        continue;
+_search_next_long:
+        {   size_t const hl3 = ZSTD_hashPtr(ip + 1, hBitsL, 8); size_t const dictHLNext = ZSTD_hashPtr(ip + 1, dictHBitsL, 8);
+            U32 const matchIndexL3 = hashLong[hl3]; const BYTE* matchL3 = base + matchIndexL3;
+            hashLong[hl3] = curr + 1;
+            if (matchIndexL3 > prefixLowestIndex) {
+                if (MEM_read64(matchL3) == MEM_read64(ip + 1)) {
+                    mLength = ZSTD_count(ip + 9, matchL3 + 8, iend) + 8;
+                    ip++;
+                    offset = (U32)(ip - matchL3);
+                    while (((ip > anchor) & (matchL3 > prefixLowest)) && (ip[-1] == matchL3[-1])) { ip--; matchL3--; mLength++; }
+                    goto _match_found;
+                }
+            } else {
+                U32 const dictMatchIndexL3 = dictHashLong[dictHLNext]; const BYTE* dictMatchL3 = base + dictMatchIndexL3 + dictIndexDelta;
+                if (dictMatchL3 > dictStart && MEM_read64(dictMatchL3) == MEM_read64(ip + 1)) {
+                    mLength = ZSTD_count(ip + 1 + 8, dictMatchL3 + 8, iend) + 8;
+                    ip++;
+                    offset = (U32)(curr + 1 - dictMatchIndexL3 - dictIndexDelta);
+                    while (((ip > anchor) & (dictMatchL3 > dictStart)) && (ip[-1] == dictMatchL3[-1])) { ip--; dictMatchL3--; mLength++; }
+                    goto _match_found;
+        }   }   }
+        if (matchIndexS < prefixLowestIndex) {
+            mLength = ZSTD_count(ip + 4, match + 4, iend) + 4;
+            offset = (U32)(curr - matchIndexS);
+            while (((ip > anchor) & (match > dictStart)) && (ip[-1] == match[-1])) { ip--; match--; mLength++; }
+        } else {
+            mLength = ZSTD_count(ip + 4, match + 4, iend) + 4;
+            offset = (U32)(ip - match);
+            while (((ip > anchor) & (match > prefixLowest)) && (ip[-1] == match[-1])) { ip--; match--; mLength++; }
+        }
+_match_found:
+        offset_2 = offset_1; offset_1 = offset;
+        ZSTD_storeSeq(seqStore, (size_t)(ip - anchor), anchor, offset + ZSTD_REP_MOVE, mLength - MINMATCH);
+_match_stored:
+        ip += mLength; anchor = ip;
+        if (ip <= ilimit) {
+            {   U32 const indexToInsert = curr + 2;
+                hashLong[ZSTD_hashPtr(base + indexToInsert, hBitsL, 8)] = indexToInsert;
+                hashLong[ZSTD_hashPtr(ip - 2, hBitsL, 8)] = (U32)(ip - 2 - base);
+                hashSmall[ZSTD_hashPtr(base + indexToInsert, hBitsS, mls)] = indexToInsert;
+                hashSmall[ZSTD_hashPtr(ip - 1, hBitsS, mls)] = (U32)(ip - 1 - base);
+            }
+            while (ip <= ilimit) {
+                U32 const current2 = (U32)(ip - base); U32 const repIndex2 = current2 - offset_2; const BYTE* const repMatch2 = base + repIndex2;
+                if (((U32)((prefixLowestIndex - 1) - repIndex2) >= 3) && (MEM_read32(repMatch2) == MEM_read32(ip))) {
+                    size_t const repLength2 = ZSTD_count(ip + 4, repMatch2 + 4, iend) + 4;
+                    U32 const tmpOffset = offset_2; offset_2 = offset_1; offset_1 = tmpOffset;
+                    ZSTD_storeSeq(seqStore, 0, anchor, 0, repLength2 - MINMATCH);
+                    hashSmall[ZSTD_hashPtr(ip, hBitsS, mls)] = current2;
+                    hashLong[ZSTD_hashPtr(ip, hBitsL, 8)] = current2;
+                    ip += repLength2; anchor = ip;
+                    continue;
+                }
+                break;
+    }   }   }
+    rep[0] = offset_1 ? offset_1 : offsetSaved; rep[1] = offset_2 ? offset_2 : offsetSaved;
+    return (size_t)(iend - anchor);
+}
+
+static size_t ZSTD_compressBlock_doubleFast_extDict(ZSTD_matchState_t* ms, seqStore_t* seqStore, U32 rep[3], const void* src, size_t srcSize)   /* ZstdDoubleFast.cs:590 */
+{
+    const cParams_t* const cParams = &ms->cParams; U32 const mls = cParams->minMatch;
+    U32* const hashLong = ms->hashTable; U32 const hBitsL = cParams->hashLog;
+    U32* const hashSmall = ms->chainTable; U32 const hBitsS = cParams->chainLog;
+    const BYTE* const istart = (const BYTE*)src; const BYTE* ip = istart; const BYTE* anchor = istart;
+    const BYTE* const iend = istart + srcSize; const BYTE* const ilimit = iend - 8;
+    const BYTE* const base = ms->window.base;
+    U32 const endIndex = (U32)((size_t)(istart - base) + srcSize);
+    U32 const lowLimit = ZSTD_getLowestMatchIndex(ms, endIndex, cParams->windowLog);
+    U32 const dictStartIndex = lowLimit; U32 const dictLimit = ms->window.dictLimit;
+    U32 const prefixStartIndex = (dictLimit > lowLimit) ? dictLimit : lowLimit;
+    const BYTE* const prefixStart = base + prefixStartIndex; const BYTE* const dictStart = base + dictStartIndex;
+    U32 offset_1 = rep[0], offset_2 = rep[1];
+    if (prefixStartIndex == dictStartIndex) return ZSTD_compressBlock_doubleFast(ms, seqStore, rep, src, srcSize);
+    while (ip < ilimit) {
+        size_t const hSmall = ZSTD_hashPtr(ip, hBitsS, mls); U32 const matchIndex = hashSmall[hSmall]; const BYTE* match = base + matchIndex;
+        size_t const hLong = ZSTD_hashPtr(ip, hBitsL, 8); U32 const matchLongIndex = hashLong[hLong]; const BYTE* matchLong = base + matchLongIndex;
+        U32 const curr = (U32)(ip - base); U32 const repIndex = curr + 1 - offset_1; const BYTE* const repMatch = base + repIndex;
+        size_t mLength;
+        hashSmall[hSmall] = hashLong[hLong] = curr;
+        if ((((U32)((prefixStartIndex - 1) - repIndex) >= 3) & (offset_1 <= curr + 1 - dictStartIndex)) && (MEM_read32(repMatch) == MEM_read32(ip + 1))) {
+            mLength = ZSTD_count(ip + 1 + 4, repMatch + 4, iend) + 4;
+            ip++;
+            ZSTD_storeSeq(seqStore, (size_t)(ip - anchor), anchor, 0, mLength - MINMATCH);
+        } else {
+            if ((matchLongIndex > dictStartIndex) && (MEM_read64(matchLong) == MEM_read64(ip))) {
+                const BYTE* const lowMatchPtr = matchLongIndex < prefixStartIndex ? dictStart : prefixStart;
+                U32 offset;
+                mLength = ZSTD_count(ip + 8, matchLong + 8, iend) + 8;
+                offset = curr - matchLongIndex;
+                while (((ip > anchor) & (matchLong > lowMatchPtr)) && (ip[-1] == matchLong[-1])) { ip--; matchLong--; mLength++; }
+                offset_2 = offset_1; offset_1 = offset;
+                ZSTD_storeSeq(seqStore, (size_t)(ip - anchor), anchor, offset + ZSTD_REP_MOVE, mLength - MINMATCH);
+            } else if ((matchIndex > dictStartIndex) && (MEM_read32(match) == MEM_read32(ip))) {
+                size_t const h3 = ZSTD_hashPtr(ip + 1, hBitsL, 8); U32 const matchIndex3 = hashLong[h3]; const BYTE* match3 = base + matchIndex3;
+                U32 offset;
+                hashLong[h3] = curr + 1;
+                if ((matchIndex3 > dictStartIndex) && (MEM_read64(match3) == MEM_read64(ip + 1))) {
+                    const BYTE* const lowMatchPtr = matchIndex3 < prefixStartIndex ? dictStart : prefixStart;
+                    mLength = ZSTD_count(ip + 9, match3 + 8, iend) + 8;
+                    ip++;
+                    offset = curr + 1 - matchIndex3;
+                    while (((ip > anchor) & (match3 > lowMatchPtr)) && (ip[-1] == match3[-1])) { ip--; match3--; mLength++; }
+                } else {
+                    const BYTE* const lowMatchPtr = matchIndex < prefixStartIndex ? dictStart : prefixStart;
+                    mLength = ZSTD_count(ip + 4, match + 4, iend) + 4;
+                    offset = curr - matchIndex;
+                    while (((ip > anchor) & (match > lowMatchPtr)) && (ip[-1] == match[-1])) { ip--; match--; mLength++; }
+                }
+                offset_2 = offset_1; offset_1 = offset;
+                ZSTD_storeSeq(seqStore, (size_t)(ip - anchor), anchor, offset + ZSTD_REP_MOVE, mLength - MINMATCH);
+            } else { ip += ((ip - anchor) >> 8) + 1; continue; }
+        }
+        ip += mLength; anchor = ip;
+        if (ip <= ilimit) {
+            {   U32 const indexToInsert = curr + 2;
+                hashLong[ZSTD_hashPtr(base + indexToInsert, hBitsL, 8)] = indexToInsert;
+                hashLong[ZSTD_hashPtr(ip - 2, hBitsL, 8)] = (U32)(ip - 2 - base);
+                hashSmall[ZSTD_hashPtr(base + indexToInsert, hBitsS, mls)] = indexToInsert;
+                hashSmall[ZSTD_hashPtr(ip - 1, hBitsS, mls)] = (U32)(ip - 1 - base);
+            }
+            while (ip <= ilimit) {
+                U32 const current2 = (U32)(ip - base); U32 const repIndex2 = current2 - offset_2; const BYTE* const repMatch2 = base + repIndex2;
+                if ((((U32)((prefixStartIndex - 1) - repIndex2) >= 3) & (offset_2 <= current2 - dictStartIndex)) && (MEM_read32(repMatch2) == MEM_read32(ip))) {
+                    size_t const repLength2 = ZSTD_count(ip + 4, repMatch2 + 4, iend) + 4;
+                    U32 const tmpOffset = offset_2; offset_2 = offset_1; offset_1 = tmpOffset;
+                    ZSTD_storeSeq(seqStore, 0, anchor, 0, repLength2 - MINMATCH);
+                    hashSmall[ZSTD_hashPtr(ip, hBitsS, mls)] = current2;
+                    hashLong[ZSTD_hashPtr(ip, hBitsL, 8)] = current2;
+                    ip += repLength2; anchor = ip;
+                    continue;
+                }
+                break;
+    }   }   }
+    rep[0] = offset_1; rep[1] = offset_2;
+    return (size_t)(iend - anchor);
+}
+
 /* =====================================================================================
  *  Block / frame layer -- ZstdCompress.cs:3432, :4528, :4690, :4817, :5013, :5598, :5665, :7138
  * ===================================================================================== */
@@ -1227,9 +1557,17 @@ static size_t ZSTD_buildSeqStore(zo_CCtx* zc, const void* src, size_t srcSize)  
     if (srcSize < MIN_CBLOCK_SIZE + ZSTD_blockHeaderSize + 1) return 1;
     zc->seqStore.lit = zc->seqStore.litStart; zc->seqStore.sequences = zc->seqStore.sequencesStart; zc->seqStore.longLengthType = 0;
     {   int i; for (i = 0; i < 3; ++i) zc->nextCBlock->rep[i] = zc->prevCBlock->rep[i]; }
-    {   size_t const lastLLSize = (zc->cParams.strategy == ZSTD_fast)
-            ? ZSTD_compressBlock_fast(&zc->ms, &zc->seqStore, zc->nextCBlock->rep, src, srcSize)
-            : ZSTD_compressBlock_doubleFast(&zc->ms, &zc->seqStore, zc->nextCBlock->rep, src, srcSize);
+    {   /* ZSTD_matchState_dictMode (ZstdCompressInternal.cs:576) + ZSTD_selectBlockCompressor (ZstdCompress.cs:3398) */
+        int const extDict = zc->ms.window.lowLimit < zc->ms.window.dictLimit;
+        int const dms = !extDict && zc->ms.dictMatchState != NULL;
+        int const fast = (zc->cParams.strategy == ZSTD_fast);
+        size_t const lastLLSize =
+            extDict ? (fast ? ZSTD_compressBlock_fast_extDict(&zc->ms, &zc->seqStore, zc->nextCBlock->rep, src, srcSize)
+                            : ZSTD_compressBlock_doubleFast_extDict(&zc->ms, &zc->seqStore, zc->nextCBlock->rep, src, srcSize))
+          : dms     ? (fast ? ZSTD_compressBlock_fast_dictMatchState(&zc->ms, &zc->seqStore, zc->nextCBlock->rep, src, srcSize)
+                            : ZSTD_compressBlock_doubleFast_dictMatchState(&zc->ms, &zc->seqStore, zc->nextCBlock->rep, src, srcSize))
+          :           (fast ? ZSTD_compressBlock_fast(&zc->ms, &zc->seqStore, zc->nextCBlock->rep, src, srcSize)
+                            : ZSTD_compressBlock_doubleFast(&zc->ms, &zc->seqStore, zc->nextCBlock->rep, src, srcSize));
         const BYTE* const lastLiterals = (const BYTE*)src + srcSize - lastLLSize;
         memcpy(zc->seqStore.lit, lastLiterals, lastLLSize);   /* ZSTD_storeLastLiterals */
         zc->seqStore.lit += lastLLSize;
@@ -1272,12 +1610,17 @@ static size_t ZSTD_compress_frameChunk(zo_CCtx* cctx, void* dst, size_t dstCapac
         U32 const lastBlock = (blockSize >= remaining);
         if (dstCapacity < ZSTD_blockHeaderSize + MIN_CBLOCK_SIZE) return ERROR(dstSize_tooSmall);
         if (remaining < blockSize) blockSize = remaining;
-        {   /* ZSTD_window_enforceMaxDist(&ms->window, ip, maxDist, ...) : ZstdCompressInternal.cs:630 */
+        {   /* ZSTD_checkDictValidity(&ms->window, ip + blockSize, maxDist, ...) : ZstdCompressInternal.cs:697 */
+            U32 const blockEndIdx = (U32)((ip + blockSize) - ms->window.base);
+            if (blockEndIdx > ms->loadedDictEnd + maxDist) { ms->loadedDictEnd = 0; ms->dictMatchState = NULL; }
+        }
+        {   /* ZSTD_window_enforceMaxDist(&ms->window, ip, maxDist, ...) : ZstdCompressInternal.cs:659 */
             U32 const blockEndIdx = (U32)(ip - ms->window.base);
-            if (blockEndIdx > maxDist) {
+            if (blockEndIdx > maxDist + ms->loadedDictEnd) {
                 U32 const newLowLimit = blockEndIdx - maxDist;
                 if (ms->window.lowLimit < newLowLimit) ms->window.lowLimit = newLowLimit;
                 if (ms->window.dictLimit < ms->window.lowLimit) ms->window.dictLimit = ms->window.lowLimit;
+                ms->loadedDictEnd = 0; ms->dictMatchState = NULL;
         }   }
         {   size_t cSize = ZSTD_compressBlock_internal(cctx, op + ZSTD_blockHeaderSize, dstCapacity - ZSTD_blockHeaderSize, ip, blockSize, 1);
             if (ERR_isError(cSize)) return cSize;
@@ -1296,19 +1639,26 @@ static size_t ZSTD_compress_frameChunk(zo_CCtx* cctx, void* dst, size_t dstCapac
     return (size_t)(op - ostart);
 }
 
-static size_t ZSTD_writeFrameHeader(void* dst, size_t dstCapacity, U32 windowLog, int checksumFlag, U64 pledgedSrcSize)   /* :4817, contentSizeFlag=1, dictID=0 */
+static size_t ZSTD_writeFrameHeader(void* dst, size_t dstCapacity, U32 windowLog, int checksumFlag, U64 pledgedSrcSize, U32 dictID)   /* :4817, contentSizeFlag=1, noDictIDFlag=0 */
 {
     BYTE* const op = (BYTE*)dst;
+    U32 const dictIDSizeCode = (dictID > 0) + (dictID >= 256) + (dictID >= 65536);
     U32 const windowSize = 1U << windowLog;
     U32 const singleSegment = (windowSize >= pledgedSrcSize);
     BYTE const windowLogByte = (BYTE)((windowLog - 10) << 3);
     U32 const fcsCode = (pledgedSrcSize >= 256) + (pledgedSrcSize >= 65536 + 256) + (pledgedSrcSize >= 0xFFFFFFFFU);
-    BYTE const frameHeaderDescriptionByte = (BYTE)(0 + ((checksumFlag > 0) << 2) + (singleSegment << 5) + (fcsCode << 6));
+    BYTE const frameHeaderDescriptionByte = (BYTE)(dictIDSizeCode + ((checksumFlag > 0) << 2) + (singleSegment << 5) + (fcsCode << 6));
     size_t pos = 0;
     if (dstCapacity < 18) return ERROR(dstSize_tooSmall);
     MEM_write32(dst, ZSTD_MAGICNUMBER); pos = 4;
     op[pos++] = frameHeaderDescriptionByte;
     if (!singleSegment) op[pos++] = windowLogByte;
+    switch (dictIDSizeCode) {
+    default: case 0: break;
+    case 1: op[pos] = (BYTE)dictID; pos++; break;
+    case 2: MEM_write16(op + pos, (U16)dictID); pos += 2; break;
+    case 3: MEM_write32(op + pos, dictID); pos += 4; break;
+    }
     switch (fcsCode) {
     default: case 0: if (singleSegment) op[pos++] = (BYTE)pledgedSrcSize; break;
     case 1: MEM_write16(op + pos, (U16)(pledgedSrcSize - 256)); pos += 2; break;
@@ -1373,7 +1723,7 @@ size_t zo_compressCCtx(void* ctx, void* dst, size_t dstCapacity, const void* src
     /* window: byte 0 of src gets index 2 (ZSTD_window_init + first ZSTD_window_update, ZstdCompressInternal.cs:723-768) */
     c->ms.window.base = (const BYTE*)src - 2; c->ms.window.dictLimit = 2; c->ms.window.lowLimit = 2;
     /* ZSTD_compressContinue_internal :5013 */
-    {   size_t const fhSize = ZSTD_writeFrameHeader(op, dstCapacity, c->cParams.windowLog, checksumFlag, srcSize);
+    {   size_t const fhSize = ZSTD_writeFrameHeader(op, dstCapacity, c->cParams.windowLog, checksumFlag, srcSize, 0);
         if (ERR_isError(fhSize)) return fhSize;
         op += fhSize; dstCapacity -= fhSize; }
     if (srcSize) {
@@ -1406,6 +1756,270 @@ size_t zo_compress_advanced(void* dst, size_t dstCapacity, const void* src, size
 
 size_t zo_compress(void* dst, size_t dstCapacity, const void* src, size_t srcSize, int level)
 { return zo_compress_advanced(dst, dstCapacity, src, srcSize, level, 0); }
+
+/* =====================================================================================
+ *  Dictionary compression: Compressor.LoadDictionary (Compressor.cs:43-56) + Wrap.
+ *  ZSTD_CCtx_loadDictionary (ZstdCompress.cs:1683) only stores the bytes; the first ZSTD_compress2 digests them into a CDict
+ *  built with the context's level (ZSTD_initLocalDict :1581 -> ZSTD_createCDict_advanced2 :5933 -> ZSTD_initCDict_internal
+ *  :5826 -> ZSTD_compress_insertDictionary :5467, dtlm_full), and every frame starts from that CDict, either ATTACHED (small
+ *  inputs: the CDict's tables are searched in place, ZSTD_resetCCtx_byAttachingCDict :2746) or COPIED (its tables become the
+ *  working tables and the content an external dictionary segment, ZSTD_resetCCtx_byCopyingCDict :2803).
+ * ===================================================================================== */
+typedef enum { zo_cpm_noAttachDict = 0, zo_cpm_attachDict = 1, zo_cpm_createCDict = 2 } zo_cpm_e;
+
+static U32 zo_dictAndWindowLog(U32 windowLog, U64 srcSize, U64 dictSize)   /* :1985 */
+{
+    U64 const maxWindowSize = 1ULL << 31;
+    if (dictSize == 0) return windowLog;
+    {   U64 const windowSize = 1ULL << windowLog; U64 const dictAndWindowSize = dictSize + windowSize;
+        if (windowSize >= dictSize + srcSize) return windowLog;
+        if (dictAndWindowSize >= maxWindowSize) return 31;
+        return BIT_highbit32((U32)dictAndWindowSize - 1) + 1;
+    }
+}
+static cParams_t zo_adjustCParams_dict(cParams_t cPar, U64 srcSize, size_t dictSize, zo_cpm_e mode)   /* :2023 */
+{
+    U64 const minSrcSize = 513; U64 const maxWindowResize = 1ULL << 30;
+    if (mode == zo_cpm_createCDict) { if (dictSize && srcSize == ZSTD_CONTENTSIZE_UNKNOWN) srcSize = minSrcSize; }
+    else if (mode == zo_cpm_attachDict) dictSize = 0;
+    if ((srcSize < maxWindowResize) && (dictSize < maxWindowResize)) {
+        U32 const tSize = (U32)(srcSize + dictSize); U32 const hashSizeMin = 1 << 6;
+        U32 const srcLog = (tSize < hashSizeMin) ? 6 : BIT_highbit32(tSize - 1) + 1;
+        if (cPar.windowLog > srcLog) cPar.windowLog = srcLog;
+    }
+    if (srcSize != ZSTD_CONTENTSIZE_UNKNOWN) {
+        U32 const dictAndWindowLog = zo_dictAndWindowLog(cPar.windowLog, srcSize, dictSize);
+        U32 const cycleLog = cPar.chainLog;                    /* ZSTD_cycleLog: strategy < btlazy2 */
+        if (cPar.hashLog > dictAndWindowLog + 1) cPar.hashLog = dictAndWindowLog + 1;
+        if (cycleLog > dictAndWindowLog) cPar.chainLog -= (cycleLog - dictAndWindowLog);
+    }
+    if (cPar.windowLog < 10) cPar.windowLog = 10;
+    return cPar;
+}
+/* ZSTD_getCParamsFromCCtxParams :2156 = ZSTD_getCParams_internal :7891 (row size :7852) + a second adjust */
+static int zo_getCParams_dict(cParams_t* out, int level, U64 srcSizeHint, size_t dictSize, zo_cpm_e mode)
+{
+    size_t const rowDict = (mode == zo_cpm_attachDict) ? 0 : dictSize;
+    int const unknown = (srcSizeHint == ZSTD_CONTENTSIZE_UNKNOWN);
+    size_t const addedSize = unknown && rowDict > 0 ? 500 : 0;
+    U64 const rSize = unknown && rowDict == 0 ? ZSTD_CONTENTSIZE_UNKNOWN : srcSizeHint + rowDict + addedSize;   /* wraps for `unknown` with a dictionary, as in the reference */
+    U32 const tableID = (rSize <= 256 * 1024) + (rSize <= 128 * 1024) + (rSize <= 16 * 1024);
+    int row;
+    if (level == 0) row = 3; else if (level < 0) row = 0; else if (level > 4) return -1; else row = level;
+    {   cParams_t cp = zo_defaultCParameters[tableID][row];
+        if (cp.strategy == 0) return -1;
+        if (level < 0) { int const clamped = level < -(1 << 17) ? -(1 << 17) : level; cp.targetLength = (U32)(-clamped); }
+        *out = zo_adjustCParams_dict(cp, srcSizeHint, dictSize, mode);
+    }
+    *out = zo_adjustCParams_dict(*out, srcSizeHint, dictSize, mode);
+    return 0;
+}
+
+/* HufCompress.cs:249 HUF_readCTable */
+static size_t zo_HUF_readCTable(HUF_CTable* CTable, unsigned* maxSymbolValuePtr, const void* src, size_t srcSize, unsigned* hasZeroWeights)
+{
+    BYTE huffWeight[HUF_SYMBOLVALUE_MAX + 1]; U32 rankVal[HUF_TABLELOG_MAX + 2]; U32 tableLog = 0, nbSymbols = 0;
+    size_t const readSize = zo_HUF_readStats(huffWeight, HUF_SYMBOLVALUE_MAX + 1, rankVal, &nbSymbols, &tableLog, src, srcSize);
+    if (ERR_isError(readSize)) return readSize;
+    *hasZeroWeights = (rankVal[0] > 0);
+    if (tableLog > HUF_TABLELOG_MAX) return ERROR(tableLog_tooLarge);
+    if (nbSymbols > *maxSymbolValuePtr + 1) return ERROR(maxSymbolValue_tooSmall);
+    memset(CTable, 0, sizeof(*CTable));
+    CTable->tableLog = tableLog;
+    {   U32 n; for (n = 0; n < nbSymbols; n++) { U32 const w = huffWeight[n]; CTable->nbBits[n] = (BYTE)(w ? tableLog + 1 - w : 0); } }
+    {   U16 nbPerRank[HUF_TABLELOG_MAX + 2] = { 0 }; U16 valPerRank[HUF_TABLELOG_MAX + 2] = { 0 };
+        {   U32 n; for (n = 0; n < nbSymbols; n++) nbPerRank[CTable->nbBits[n]]++; }
+        valPerRank[tableLog + 1] = 0;
+        {   U16 min = 0; U32 n; for (n = tableLog; n > 0; n--) { valPerRank[n] = min; min = (U16)(min + nbPerRank[n]); min >>= 1; } }
+        {   U32 n; for (n = 0; n < nbSymbols; n++) CTable->value[n] = valPerRank[CTable->nbBits[n]]++; }
+    }
+    *maxSymbolValuePtr = nbSymbols - 1;
+    return readSize;
+}
+
+static FSE_repeat ZSTD_dictNCountRepeat(const S16* normalizedCounter, unsigned dictMaxSymbolValue, unsigned maxSymbolValue)   /* :5239 */
+{
+    U32 s;
+    if (dictMaxSymbolValue < maxSymbolValue) return FSE_repeat_check;
+    for (s = 0; s <= maxSymbolValue; ++s) if (normalizedCounter[s] == 0) return FSE_repeat_check;
+    return FSE_repeat_valid;
+}
+
+/* ZstdCompress.cs:5264 ZSTD_loadCEntropy: header size, or an error */
+static size_t ZSTD_loadCEntropy(ZSTD_compressedBlockState_t* bs, const void* const dict, size_t dictSize)
+{
+    S16 offcodeNCount[MaxOff + 1]; unsigned offcodeMaxValue = MaxOff;
+    const BYTE* dictPtr = (const BYTE*)dict; const BYTE* const dictEnd = dictPtr + dictSize;
+    dictPtr += 8;
+    bs->entropy.huf.repeatMode = HUF_repeat_check;
+    {   unsigned maxSymbolValue = 255; unsigned hasZeroWeights = 1;
+        size_t const hufHeaderSize = zo_HUF_readCTable(&bs->entropy.huf.CTable, &maxSymbolValue, dictPtr, (size_t)(dictEnd - dictPtr), &hasZeroWeights);
+        if (!hasZeroWeights) bs->entropy.huf.repeatMode = HUF_repeat_valid;
+        if (ERR_isError(hufHeaderSize)) return ERROR(dictionary_corrupted);
+        if (maxSymbolValue < 255) return ERROR(dictionary_corrupted);
+        dictPtr += hufHeaderSize;
+    }
+    {   unsigned offcodeLog;
+        size_t const offcodeHeaderSize = zo_FSE_readNCount(offcodeNCount, &offcodeMaxValue, &offcodeLog, dictPtr, (size_t)(dictEnd - dictPtr));
+        if (ERR_isError(offcodeHeaderSize)) return ERROR(dictionary_corrupted);
+        if (offcodeLog > OffFSELog) return ERROR(dictionary_corrupted);
+        if (ERR_isError(FSE_buildCTable(&bs->entropy.fse.offcodeCTable, offcodeNCount, MaxOff, offcodeLog))) return ERROR(dictionary_corrupted);
+        dictPtr += offcodeHeaderSize;
+    }
+    {   S16 matchlengthNCount[MaxML + 1]; unsigned matchlengthMaxValue = MaxML, matchlengthLog;
+        size_t const h = zo_FSE_readNCount(matchlengthNCount, &matchlengthMaxValue, &matchlengthLog, dictPtr, (size_t)(dictEnd - dictPtr));
+        if (ERR_isError(h)) return ERROR(dictionary_corrupted);
+        if (matchlengthLog > MLFSELog) return ERROR(dictionary_corrupted);
+        if (ERR_isError(FSE_buildCTable(&bs->entropy.fse.matchlengthCTable, matchlengthNCount, matchlengthMaxValue, matchlengthLog))) return ERROR(dictionary_corrupted);
+        bs->entropy.fse.matchlength_repeatMode = ZSTD_dictNCountRepeat(matchlengthNCount, matchlengthMaxValue, MaxML);
+        dictPtr += h;
+    }
+    {   S16 litlengthNCount[MaxLL + 1]; unsigned litlengthMaxValue = MaxLL, litlengthLog;
+        size_t const h = zo_FSE_readNCount(litlengthNCount, &litlengthMaxValue, &litlengthLog, dictPtr, (size_t)(dictEnd - dictPtr));
+        if (ERR_isError(h)) return ERROR(dictionary_corrupted);
+        if (litlengthLog > LLFSELog) return ERROR(dictionary_corrupted);
+        if (ERR_isError(FSE_buildCTable(&bs->entropy.fse.litlengthCTable, litlengthNCount, litlengthMaxValue, litlengthLog))) return ERROR(dictionary_corrupted);
+        bs->entropy.fse.litlength_repeatMode = ZSTD_dictNCountRepeat(litlengthNCount, litlengthMaxValue, MaxLL);
+        dictPtr += h;
+    }
+    if (dictPtr + 12 > dictEnd) return ERROR(dictionary_corrupted);
+    bs->rep[0] = MEM_read32(dictPtr + 0); bs->rep[1] = MEM_read32(dictPtr + 4); bs->rep[2] = MEM_read32(dictPtr + 8);
+    dictPtr += 12;
+    {   size_t const dictContentSize = (size_t)(dictEnd - dictPtr); U32 offcodeMax = MaxOff;
+        if (dictContentSize <= ((U32)-1) - 128 * 1024) { U32 const maxOffset = (U32)dictContentSize + 128 * 1024; offcodeMax = BIT_highbit32(maxOffset); }
+        bs->entropy.fse.offcode_repeatMode = ZSTD_dictNCountRepeat(offcodeNCount, offcodeMaxValue, offcodeMax < MaxOff ? offcodeMax : MaxOff);
+        {   U32 u; for (u = 0; u < 3; u++) { if (bs->rep[u] == 0) return ERROR(dictionary_corrupted); if (bs->rep[u] > dictContentSize) return ERROR(dictionary_corrupted); } }
+    }
+    return (size_t)(dictPtr - (const BYTE*)dict);
+}
+
+/* ZstdFast.cs:9 ZSTD_fillHashTable / ZstdDoubleFast.cs:9 ZSTD_fillDoubleHashTable, dtlm_full, from index `from` to `end` */
+static void ZSTD_fillHashTable_full(ZSTD_matchState_t* ms, U32 from, const BYTE* end)
+{
+    U32* const hashTable = ms->hashTable; U32 const hBits = ms->cParams.hashLog; U32 const mls = ms->cParams.minMatch;
+    const BYTE* const base = ms->window.base; const BYTE* ip = base + from; const BYTE* const iend = end - 8;
+    U32 const fastHashFillStep = 3;
+    for (; ip + fastHashFillStep < iend + 2; ip += fastHashFillStep) {
+        U32 const curr = (U32)(ip - base); U32 p;
+        hashTable[ZSTD_hashPtr(ip, hBits, mls)] = curr;
+        for (p = 1; p < fastHashFillStep; ++p) { size_t const hash = ZSTD_hashPtr(ip + p, hBits, mls); if (hashTable[hash] == 0) hashTable[hash] = curr + p; }
+    }
+}
+static void ZSTD_fillDoubleHashTable_full(ZSTD_matchState_t* ms, U32 from, const BYTE* end)
+{
+    U32* const hashLarge = ms->hashTable; U32 const hBitsL = ms->cParams.hashLog; U32 const mls = ms->cParams.minMatch;
+    U32* const hashSmall = ms->chainTable; U32 const hBitsS = ms->cParams.chainLog;
+    const BYTE* const base = ms->window.base; const BYTE* ip = base + from; const BYTE* const iend = end - 8;
+    U32 const fastHashFillStep = 3;
+    for (; ip + fastHashFillStep - 1 <= iend; ip += fastHashFillStep) {
+        U32 const curr = (U32)(ip - base); U32 i;
+        for (i = 0; i < fastHashFillStep; ++i) {
+            size_t const smHash = ZSTD_hashPtr(ip + i, hBitsS, mls); size_t const lgHash = ZSTD_hashPtr(ip + i, hBitsL, 8);
+            if (i == 0) hashSmall[smHash] = curr + i;
+            if (i == 0 || hashLarge[lgHash] == 0) hashLarge[lgHash] = curr + i;
+        }
+    }
+}
+
+static const size_t zo_attachDictSizeCutoffs[3] = { 8 * 1024, 8 * 1024, 16 * 1024 };   /* :2725, index = strategy (fast 1, dfast 2) */
+
+/* One frame with a loaded dictionary. */
+static size_t zo_compress_dict_internal(void* dst, size_t dstCapacity, const void* src, size_t srcSize, const void* dict, size_t dictSize,
+                                        int level, int checksumFlag)
+{
+    zo_CCtx* const c = (zo_CCtx*)calloc(1, sizeof(zo_CCtx));
+    ZSTD_matchState_t cdictMs; cParams_t cdictCP, reqCP, workCP;
+    ZSTD_compressedBlockState_t cdictBs; U32 dictID = 0;
+    const BYTE* content = (const BYTE*)dict; size_t contentLen = dictSize;
+    BYTE* V = NULL; U32* cdictHash = NULL; U32* cdictChain = NULL; size_t result;
+    BYTE* const ostart = (BYTE*)dst; BYTE* op = ostart;
+    if (!c) return ERROR(memory_allocation);
+    memset(&cdictMs, 0, sizeof(cdictMs));
+#define ZO_DICT_FAIL(e) do { result = (e); goto _cleanup; } while (0)
+    /* ---- the CDict: parameters for an unknown source size (ZSTD_cpm_createCDict) ---- */
+    if (zo_getCParams_dict(&cdictCP, level, ZSTD_CONTENTSIZE_UNKNOWN, dictSize, zo_cpm_createCDict)) ZO_DICT_FAIL(ERROR(parameter_unsupported));
+    ZSTD_reset_compressedBlockState(&cdictBs);
+    if (dictSize >= 8 && MEM_read32(dict) == 0xEC30A437U) {      /* ZSTD_loadZstdDictionary :5424 */
+        size_t const eSize = ZSTD_loadCEntropy(&cdictBs, dict, dictSize);
+        if (ERR_isError(eSize)) ZO_DICT_FAIL(eSize);
+        dictID = MEM_read32((const BYTE*)dict + 4);
+        content = (const BYTE*)dict + eSize; contentLen = dictSize - eSize;
+    } else if (dictSize < 8) contentLen = 0;                     /* ZSTD_compress_insertDictionary :5467: nothing is loaded */
+    V = (BYTE*)malloc(contentLen + srcSize + 32);
+    cdictHash = (U32*)calloc((size_t)1 << cdictCP.hashLog, sizeof(U32));
+    cdictChain = (U32*)calloc((size_t)1 << cdictCP.chainLog, sizeof(U32));
+    if (!V || !cdictHash || !cdictChain) ZO_DICT_FAIL(ERROR(memory_allocation));
+    memcpy(V, content, contentLen); memcpy(V + contentLen, src, srcSize); memset(V + contentLen + srcSize, 0, 32);
+    cdictMs.cParams = cdictCP; cdictMs.hashTable = cdictHash; cdictMs.chainTable = cdictChain;
+    cdictMs.window.base = V - 2; cdictMs.window.dictLimit = 2; cdictMs.window.lowLimit = 2;      /* ZSTD_window_init + first update */
+    cdictMs.loadedDictEnd = contentLen ? (U32)(2 + contentLen) : 0;                               /* ZSTD_loadDictionaryContent :5126 */
+    if (contentLen > 8) {
+        if (cdictCP.strategy == ZSTD_fast) ZSTD_fillHashTable_full(&cdictMs, 2, V + contentLen);
+        else ZSTD_fillDoubleHashTable_full(&cdictMs, 2, V + contentLen);
+    }
+    /* ---- the frame: ZSTD_CCtx_init_compressStream2 :6949, ZSTD_compressBegin_internal :5505 (cdict->compressionLevel == 0: always by CDict) ---- */
+    {   int const attach = srcSize <= zo_attachDictSizeCutoffs[cdictCP.strategy];                 /* ZSTD_shouldAttachDict :2738 */
+        U32 const cdictEnd = (U32)(2 + contentLen);
+        if (zo_getCParams_dict(&reqCP, level, srcSize, dictSize, attach ? zo_cpm_attachDict : zo_cpm_noAttachDict)) ZO_DICT_FAIL(ERROR(parameter_unsupported));
+        if (attach) { workCP = zo_adjustCParams_dict(cdictCP, srcSize, dictSize, zo_cpm_attachDict); workCP.windowLog = reqCP.windowLog; }
+        else { workCP = cdictCP; workCP.windowLog = reqCP.windowLog; }
+        c->cParams = workCP;
+        CHECK_F(zo_ctx_buffers(c));
+        {   size_t const windowSize = (size_t)1 << workCP.windowLog;
+            size_t ws = windowSize < srcSize ? windowSize : srcSize; if (ws < 1) ws = 1;
+            c->blockSize = ws < ZSTD_BLOCKSIZE_MAX ? ws : ZSTD_BLOCKSIZE_MAX; }
+        c->seqStore.maxNbSeq = c->blockSize / ((workCP.minMatch == 3) ? 3 : 4); c->seqStore.maxNbLit = c->blockSize;
+        c->ms.cParams = workCP;
+        c->prevCBlock = &c->blockStateA; c->nextCBlock = &c->blockStateB;
+        memcpy(c->prevCBlock, &cdictBs, sizeof(cdictBs));
+        c->isFirstBlock = 1;
+        if (attach) {
+            memset(c->ms.hashTable, 0, ((size_t)1 << workCP.hashLog) * sizeof(U32));
+            if (workCP.strategy != ZSTD_fast) memset(c->ms.chainTable, 0, ((size_t)1 << workCP.chainLog) * sizeof(U32));
+            if (contentLen == 0) {                                                                  /* cdictLen == 0: nothing to attach */
+                c->ms.window.base = V - 2; c->ms.window.dictLimit = 2; c->ms.window.lowLimit = 2;
+            } else {
+                c->ms.dictMatchState = &cdictMs; c->ms.dictEndIndex = cdictEnd;
+                c->ms.window.base = V - 2; c->ms.window.dictLimit = cdictEnd; c->ms.window.lowLimit = cdictEnd;   /* ZSTD_window_clear, then the update */
+                c->ms.loadedDictEnd = cdictEnd;
+            }
+        } else {
+            memcpy(c->ms.hashTable, cdictHash, ((size_t)1 << workCP.hashLog) * sizeof(U32));
+            if (workCP.strategy != ZSTD_fast) memcpy(c->ms.chainTable, cdictChain, ((size_t)1 << workCP.chainLog) * sizeof(U32));
+            c->ms.loadedDictEnd = cdictMs.loadedDictEnd;
+            /* window copied from the CDict, then ZSTD_window_update with the (non contiguous) source: the content becomes the extDict */
+            c->ms.window.base = V - 2; c->ms.window.lowLimit = 2; c->ms.window.dictLimit = cdictEnd;
+            if (c->ms.window.dictLimit - c->ms.window.lowLimit < 8) c->ms.window.lowLimit = c->ms.window.dictLimit;
+        }
+    }
+    {   size_t const fhSize = ZSTD_writeFrameHeader(op, dstCapacity, workCP.windowLog, checksumFlag, srcSize, dictID);
+        if (ERR_isError(fhSize)) ZO_DICT_FAIL(fhSize);
+        op += fhSize; dstCapacity -= fhSize; }
+    if (srcSize) {
+        size_t const cSize = ZSTD_compress_frameChunk(c, op, dstCapacity, V + contentLen, srcSize);
+        if (ERR_isError(cSize)) ZO_DICT_FAIL(cSize);
+        op += cSize; dstCapacity -= cSize;
+    } else {
+        if (dstCapacity < 4) ZO_DICT_FAIL(ERROR(dstSize_tooSmall));
+        MEM_writeLE24(op, 1 + (((U32)bt_raw) << 1)); op += ZSTD_blockHeaderSize; dstCapacity -= ZSTD_blockHeaderSize;
+    }
+    if (checksumFlag) {
+        if (dstCapacity < 4) ZO_DICT_FAIL(ERROR(dstSize_tooSmall));
+        MEM_write32(op, (U32)zo_xxh64(src, srcSize, 0)); op += 4;
+    }
+    result = (size_t)(op - ostart);
+_cleanup:
+    free(V); free(cdictHash); free(cdictChain);
+    zo_ctx_free(c); free(c);
+    return result;
+#undef ZO_DICT_FAIL
+}
+
+size_t zo_compress_usingLoadedDict(void* dst, size_t dstCapacity, const void* src, size_t srcSize, const void* dict, size_t dictSize, int level, int checksumFlag)
+{
+    if (dict == NULL || dictSize == 0) return zo_compress_advanced(dst, dstCapacity, src, srcSize, level, checksumFlag);   /* ZSTD_CCtx_loadDictionary(NULL, 0) clears the dictionary */
+    return zo_compress_dict_internal(dst, dstCapacity, src, srcSize, dict, dictSize, level, checksumFlag);
+}
 
 size_t zo_matchfinder_block(int level, const void* src, size_t srcSize, zo_seqDef* seqs, uint8_t* lits, size_t* litSize,
                             uint32_t longLength[2], uint32_t repOut[3])

@@ -53,6 +53,7 @@ class Oracle:
         _sig(L.zo_getCParams, None, [ci, st, ctypes.POINTER(ctypes.c_uint)])
         _sig(L.zo_matchfinder_block, st, [ci, vp, st, vp, vp, ctypes.POINTER(st), ctypes.POINTER(ctypes.c_uint32), ctypes.POINTER(ctypes.c_uint32)])
         _sig(L.zo_decode_first_block_stages, st, [vp, st, vp, st, ctypes.POINTER(st), vp, st])
+        _sig(L.zo_compress_usingLoadedDict, st, [vp, st, vp, st, vp, st, ci, ci])
 
     @staticmethod
     def _buf(data):
@@ -68,6 +69,20 @@ class Oracle:
 
     def compress(self, data, level: int, checksum: int = 0) -> bytes:
         r, out = self.compress_raw(data, level, checksum=checksum)
+        assert not self.lib.zo_isError(r), self.lib.zo_getErrorName(r)
+        return out[:r].tobytes()
+
+    def compress_loaded_dict_raw(self, data, level: int, dictionary, checksum: int = 0):
+        """Compressor.LoadDictionary(dictionary) + Wrap(data) (Compressor.cs:43-56, 86-97)."""
+        a, p = self._buf(data)
+        d, dp = self._buf(dictionary)
+        cap = self.lib.zo_compressBound(a.size)
+        out = np.empty(max(cap, 1), dtype=np.uint8)
+        r = self.lib.zo_compress_usingLoadedDict(out.ctypes.data, cap, p, a.size, dp, d.size, level, checksum)
+        return r, out
+
+    def compress_loaded_dict(self, data, level: int, dictionary, checksum: int = 0) -> bytes:
+        r, out = self.compress_loaded_dict_raw(data, level, dictionary, checksum)
         assert not self.lib.zo_isError(r), self.lib.zo_getErrorName(r)
         return out[:r].tobytes()
 

@@ -193,6 +193,34 @@ def test_dictionary_frames_of_the_dll_decode_in_the_oracle():
     assert o.error_code(ro) == r.error_code(rr) == 32
 
 
+def test_dictionary_compression_matches_the_dll():
+    """SURVEY 8f.4, encode side: Compressor.LoadDictionary + Wrap (ZSTD_CCtx_loadDictionary, then ZSTD_compress2 digests the bytes
+    into a CDict at the context's level: ZstdCompress.cs:1581, :5933, :5826; attach below 8 / 16 KiB, copy above: :2738-2881;
+    match finders ZstdFast.cs:390 / :583, ZstdDoubleFast.cs:250 / :590; entropy tables and repcodes of the dictionary with
+    their repeat modes: :5264).  The oracle writes the DLL's bytes for zstd-format and raw dictionaries of 7 bytes .. 300 KB,
+    inputs of 0 bytes .. 600 KB around every cut-off, levels -3, 1, 2, 3, with and without checksum; the DLL decodes them."""
+    from _dict_cases import compress_dictionaries, compress_payloads
+    from _oracle import libzstd
+    o, r = oracle(), refdll()
+    dicts = compress_dictionaries(libzstd())
+    pays = compress_payloads()
+    n = 0
+    for di, (name, d) in enumerate(dicts.items()):
+        for pi, src in enumerate(pays):
+            level = (1, 2, 3, -3)[(di + pi) % 4]
+            want = r.compress_loaded_dict(src, level, d, checksum=(pi & 1))
+            assert o.compress_loaded_dict(src, level, d, checksum=(pi & 1)) == want, (name, level, src.size)
+            if pi % 5 == 0:
+                rr, outr = r.decompress_using_dict_raw(want, src.size, d)
+                assert rr == src.size and outr[:rr].tobytes() == src.tobytes()
+            n += 1
+    # every level on one dictionary / payload each side of the cut-offs
+    for level in (-5, -1, 1, 2, 3):
+        for src in (pays[3], pays[8], pays[10]):
+            assert o.compress_loaded_dict(src, level, dicts["zdict_32k"]) == r.compress_loaded_dict(src, level, dicts["zdict_32k"]), (level, src.size)
+    assert n >= 300
+
+
 def test_handbuilt_tiny_four_stream_literals():
     """tests/_cases.py::handbuilt_small_4stream_frames: legal frames no zstd encoder writes (four Huffman streams over < 256
     literals), decoded by the oracle and by the DLL to the bytes the construction implies."""
