@@ -66,6 +66,14 @@ ZSTDB200_API size_t     ZSTD_CCtx_setParameter(ZSTD_CCtx* cctx, int param, int v
 /* Compressor.GetParameter (Compressor.cs:35-41 -> U/ZstdCompress.cs:1289): reads back the parameters listed above; the level
  * reads 3 after 0 was set (ZSTD_CLEVEL_DEFAULT), as in the reference. */
 ZSTDB200_API size_t     ZSTD_CCtx_getParameter(const ZSTD_CCtx* cctx, int param, int* value);
+/* Compressor.LoadDictionary (Compressor.cs:43-56 -> U/ZstdCompress.cs:1683 ZSTD_CCtx_loadDictionary): the dictionary is copied and
+ * applies to every ZSTD_compress2 / ZSTDB200_compressBatch[Device] call of the context (ZSTD_compressCCtx ignores it, as in the
+ * reference); NULL / 0 removes it.  A zstd-format dictionary (magic 0xEC30A437: entropy tables, repcodes, content, dictionary id
+ * written into every frame header) or raw content.  As in the reference the dictionary is digested by the FIRST compression that
+ * follows, at that call's level (ZSTD_initLocalDict, U/ZstdCompress.cs:1581), and the digest is kept until the dictionary is
+ * replaced; a dictionary that cannot be digested makes those compressions fail with ZSTD_error_memory_allocation, the code the
+ * reference reports (:1604).  Frames are byte-identical to the reference's (levels as for ZSTD_compress2). */
+ZSTDB200_API size_t     ZSTD_CCtx_loadDictionary(ZSTD_CCtx* cctx, const void* dict, size_t dictSize);
 /* Decompressor.SetParameter / GetParameter (Decompressor.cs:22-34 -> U/ZstdDecompress.cs:2532, 2477).  ZSTD_d_windowLogMax = 100:
  * bounds 10..31, 0 = default 27, else ZSTD_error_parameter_outOfBound; it limits the streaming decoder only, exactly as in the
  * reference (the one-shot ZSTD_decompressDCtx path never reads it).  Other parameters -> ZSTD_error_parameter_unsupported. */
@@ -123,7 +131,7 @@ ZSTDB200_API ZSTDB200_Multi* ZSTDB200_createMulti(int nDevices);
 ZSTDB200_API size_t ZSTDB200_freeMulti(ZSTDB200_Multi* m);
 ZSTDB200_API int    ZSTDB200_multiDeviceCount(const ZSTDB200_Multi* m);
 ZSTDB200_API size_t ZSTDB200_multiSetParameter(ZSTDB200_Multi* m, int param, int value);     /* ZSTD_CCtx_setParameter on every device's context */
-ZSTDB200_API size_t ZSTDB200_multiLoadDictionary(ZSTDB200_Multi* m, const void* dict, size_t dictSize);   /* ZSTD_DCtx_loadDictionary on every device */
+ZSTDB200_API size_t ZSTDB200_multiLoadDictionary(ZSTDB200_Multi* m, const void* dict, size_t dictSize);   /* ZSTD_DCtx_loadDictionary and ZSTD_CCtx_loadDictionary on every device */
 ZSTDB200_API size_t ZSTDB200_decompressBatchMulti(ZSTDB200_Multi* m, size_t n,
                                                   const void* const* src, const size_t* srcSize,
                                                   void* const* dst, const size_t* dstCapacity, size_t* result);

@@ -124,6 +124,11 @@ public:
         ThrowHelper::EnsureZstdSuccess(ZSTD_CCtx_setParameter(cctx_, static_cast<int>(parameter), value));
     }
 
+    /* LoadDictionary(byte[] dict): null / empty drops the dictionary  (Compressor.cs:43-56). */
+    void LoadDictionary(const void* dict, size_t dictLength) {
+        EnsureNotDisposed();
+        ThrowHelper::EnsureZstdSuccess(ZSTD_CCtx_loadDictionary(cctx_, dict, dict ? dictLength : 0));
+    }
     int GetParameter(ZSTD_cParameter parameter) const {                                /* Compressor.cs:35-41 */
         EnsureNotDisposed();
         int value = 0;

@@ -327,3 +327,38 @@ def test_negative_levels_and_level4_byte_identical(level):
             with pytest.raises(ZstdException) as e:
                 c.Wrap(text[:1000])
             assert int(e.value.Code) == 40
+
+
+@pytest.mark.parametrize("level", [1, 2, 3, -3])
+def test_dictionary_compression_byte_identical(dec, level):
+    """SURVEY 8f.4, encode side: Compressor.LoadDictionary + Wrap / WrapBatch (Compressor.cs:43-56 -> ZSTD_CCtx_loadDictionary, the CDict
+    built by the first compression at the context's level, attached below 8 / 16 KiB and copied above, dictionary entropy tables
+    and repcodes, dictionary id in the frame header).  Frames equal the oracle's (pinned to the reference DLL's
+    ZSTD_CCtx_loadDictionary + ZSTD_compress2 bytes: tests/test_reference_pin.py) for zstd-format and raw dictionaries of 7 bytes
+    .. 300 KB and inputs of 0 bytes .. 600 KB around every cut-off; they decode with the same dictionary on the GPU; a fresh
+    context is used per (dictionary, level) like the reference's tests (ZstdNetTests.cs:19-39)."""
+    from zstdsharp_b200 import Compressor
+    from _dict_cases import compress_dictionaries, compress_payloads
+    o = oracle()
+    dicts = compress_dictionaries(libzstd())
+    pays = compress_payloads()
+    for name, d in dicts.items():
+        c = Compressor(level)
+        try:
+            c.LoadDictionary(d)
+            frames = c.WrapBatch(pays)
+            assert c.launch_count() > 0
+            for src, f in zip(pays, frames):
+                want = o.compress_loaded_dict(src, level, d)
+                assert f == want, (name, level, src.size, _first_diff(f, want))
+            one = c.Wrap(pays[3])                                   # single-call path (ZSTD_compress2)
+            assert bytes(one) == o.compress_loaded_dict(pays[3], level, d)
+            c.LoadDictionary(None)                                  # back to no dictionary (ZSTD_CCtx_loadDictionary(NULL, 0))
+            assert bytes(c.Wrap(pays[3])) == o.compress(pays[3], level)
+        finally:
+            c.Dispose()
+        dec.LoadDictionary(d)
+        try:
+            assert dec.UnwrapBatch(frames) == [p.tobytes() for p in pays], name
+        finally:
+            dec.LoadDictionary(None)

@@ -22,7 +22,7 @@ EXPORTED_SYMBOLS = [
     "ZSTD_getErrorName", "ZSTD_versionNumber", "ZSTD_versionString", "ZSTD_findFrameCompressedSize",
     "ZSTDB200_decompressBatch", "ZSTDB200_compressBatch", "ZSTDB200_decompressBatchDevice",
     "ZSTDB200_compressBatchDevice", "ZSTDB200_getLastTimings", "ZSTDB200_getLastLaunchCount",
-    "ZSTDB200_lastErrorString", "ZSTDB200_deviceCount", "ZSTDB200_setStream", "ZSTD_DCtx_loadDictionary",
+    "ZSTDB200_lastErrorString", "ZSTDB200_deviceCount", "ZSTDB200_setStream", "ZSTD_DCtx_loadDictionary", "ZSTD_CCtx_loadDictionary",
     "ZSTD_CCtx_getParameter", "ZSTD_DCtx_setParameter", "ZSTD_DCtx_getParameter",
     "ZSTDB200_createMulti", "ZSTDB200_freeMulti", "ZSTDB200_multiDeviceCount", "ZSTDB200_multiSetParameter",
     "ZSTDB200_multiLoadDictionary", "ZSTDB200_decompressBatchMulti", "ZSTDB200_compressBatchMulti",
@@ -54,6 +54,8 @@ def _load() -> ctypes.CDLL:
     lib.ZSTD_decompressDCtx.argtypes = [c_void_p, c_void_p, c_size_t, c_void_p, c_size_t]
     lib.ZSTD_DCtx_loadDictionary.restype = c_size_t
     lib.ZSTD_DCtx_loadDictionary.argtypes = [c_void_p, c_void_p, c_size_t]
+    lib.ZSTD_CCtx_loadDictionary.restype = c_size_t
+    lib.ZSTD_CCtx_loadDictionary.argtypes = [c_void_p, c_void_p, c_size_t]
     lib.ZSTD_findFrameCompressedSize.restype = c_size_t
     lib.ZSTD_findFrameCompressedSize.argtypes = [c_void_p, c_size_t]
     lib.ZSTD_compressBound.restype = c_size_t

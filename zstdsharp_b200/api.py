@@ -133,6 +133,14 @@ class Compressor:
         self._ensure()
         EnsureZstdSuccess(_lib.ZSTD_CCtx_setParameter(self._cctx, int(parameter), int(value)))
 
+    def LoadDictionary(self, dictionary) -> None:    # Compressor.cs:43-56: null / empty removes the dictionary
+        self._ensure()
+        if dictionary is None or len(dictionary) == 0:
+            EnsureZstdSuccess(_lib.ZSTD_CCtx_loadDictionary(self._cctx, 0, 0))
+            return
+        d = _as_u8(dictionary)
+        EnsureZstdSuccess(_lib.ZSTD_CCtx_loadDictionary(self._cctx, _ptr(d), d.size))
+
     def GetParameter(self, parameter: int) -> int:   # Compressor.cs:35-41
         self._ensure()
         value = ctypes.c_int(0)

@@ -541,7 +541,8 @@ static size_t decompress_batch_host(Engine& E, size_t n, const void* const* src,
 // are compressed as independent frames and written back to back: a valid zstd stream for any decoder
 // (ZSTD_decompressMultiFrame, ZstdDecompress.cs:1216) whose ZSTD_decompressBound is the item size, all pieces in
 // parallel, but NOT the reference's bytes -- see DESIGN.md, deviations.
-static size_t compress_batch_host(Engine& E, size_t n, int level, int checksum, int chunked, const void* const* src, const size_t* srcSize, void* const* dst, const size_t* dstCap, size_t* result)
+static size_t compress_batch_host(Engine& E, size_t n, int level, int checksum, int chunked, const void* const* src, const size_t* srcSize, void* const* dst, const size_t* dstCap, size_t* result,
+                                  const EncDict* dict = nullptr)
 {
     auto cut = [&](size_t ss) { return ss > kBlockSizeMax && (chunked || ss > enc_max_frame_bytes()); };
     if (!E.init() || !E.bind()) return (size_t)make_error(kGeneric);
@@ -561,7 +562,7 @@ static size_t compress_batch_host(Engine& E, size_t n, int level, int checksum, 
         while (a < n) {
             size_t b = a + 1;
             while (b < n && first[b + 1] - first[a] <= sliceCap) b++;
-            size_t const rc = compress_batch_host(E, b - a, level, checksum, chunked, src + a, srcSize + a, dst + a, dstCap + a, result + a);
+            size_t const rc = compress_batch_host(E, b - a, level, checksum, chunked, src + a, srcSize + a, dst + a, dstCap + a, result + a, dict);
             if (is_error(rc)) return rc;
             a = b;
         }
@@ -621,7 +622,7 @@ static size_t compress_batch_host(Engine& E, size_t n, int level, int checksum, 
             size_t const lo = pSrcOff[a], hi = pSrcOff[b - 1] + pSize[b - 1];
             if (hi > lo && cudaMemcpyAsync(E.dSrc.as<uint8_t>() + lo, hostBase + (lo - sOff[0]), hi - lo, cudaMemcpyHostToDevice, E.sIn) != cudaSuccess) return fail(kGeneric);
             if (!enc_enqueue(E.encPipe[k], E.sEnc[k], E.sIn, b - a, level, checksum, E.dSrc.as<uint8_t>(), pSrcOff.data() + a, pSize.data() + a,
-                             E.dDst.as<uint8_t>(), pDstOff.data() + a, slotCap.data() + a, evK + 3 * k, &E.launches)) { set_error(enc_last_error()); return fail(kGeneric); }
+                             E.dDst.as<uint8_t>(), pDstOff.data() + a, slotCap.data() + a, evK + 3 * k, &E.launches, dict)) { set_error(enc_last_error()); return fail(kGeneric); }
         }
         cudaEventRecord(E.evIn[1], E.sIn);
         size_t stageBase = 0, itemNext = 0;
@@ -681,7 +682,7 @@ static size_t compress_batch_host(Engine& E, size_t n, int level, int checksum, 
         }
         return 0;
     } else {
-        if (!enc_compress_device(E.enc, E.stream, E.ev, np, level, checksum, E.dSrc.as<uint8_t>(), pSrcOff.data(), pSize.data(), E.dDst.as<uint8_t>(), pDstOff.data(), slotCap.data(), r.data(), E.timings, &E.launches))
+        if (!enc_compress_device(E.enc, E.stream, E.ev, np, level, checksum, E.dSrc.as<uint8_t>(), pSrcOff.data(), pSize.data(), E.dDst.as<uint8_t>(), pDstOff.data(), slotCap.data(), r.data(), E.timings, &E.launches, dict))
             { set_error(enc_last_error()); return (size_t)make_error(kGeneric); }
         cudaEventRecord(E.ev[12], E.stream);
     }
@@ -876,7 +877,24 @@ static const char* error_name(uint32_t code)   // ErrorPrivate.cs:34-184
 // =================================================================================================================
 //  extern "C" surface
 // =================================================================================================================
-struct ZSTD_CCtx_s { zb::Engine E; int level = 3; int checksum = 0; int chunked = 0; };
+struct ZSTD_CCtx_s {
+    zb::Engine E; int level = 3; int checksum = 0; int chunked = 0;
+    // Compressor.LoadDictionary (Compressor.cs:43-56): the bytes ZSTD_CCtx_loadDictionary stores, and their digest for the level of the first
+    // compression that follows (ZSTD_initLocalDict, ZstdCompress.cs:1581: built once, kept until the dictionary is replaced)
+    std::vector<uint8_t> dictBytes; zb::EncDict encDict;
+};
+// The digest of the loaded dictionary (built on first use); *err receives the zstd error code when it cannot be built.
+static const zb::EncDict* cctx_dict(ZSTD_CCtx_s* c, int level, size_t* err)
+{
+    *err = 0;
+    if (c->dictBytes.empty()) return nullptr;
+    if (!c->encDict.ready) {
+        if (!c->E.init() || !c->E.bind()) { *err = (size_t)zb::make_error(zb::kGeneric); return nullptr; }
+        size_t const rc = zb::enc_dict_digest(c->encDict, c->E.stream, c->dictBytes.data(), c->dictBytes.size(), level);
+        if (zb::is_error(rc)) { *err = rc; return nullptr; }
+    }
+    return &c->encDict;
+}
 struct ZSTD_DCtx_s { zb::Engine E; int windowLogMax = 27; };
 
 using zb::make_error;
@@ -884,7 +902,7 @@ using zb::make_error;
 extern "C" {
 
 ZSTD_CCtx* ZSTD_createCCtx(void) { return new (std::nothrow) ZSTD_CCtx_s(); }
-size_t ZSTD_freeCCtx(ZSTD_CCtx* c) { if (c) { c->E.destroy(); delete c; } return 0; }
+size_t ZSTD_freeCCtx(ZSTD_CCtx* c) { if (c) { zb::DeviceGuard guard; if (c->E.device >= 0) cudaSetDevice(c->E.device); c->encDict.release(); c->E.destroy(); delete c; } return 0; }
 ZSTD_DCtx* ZSTD_createDCtx(void) { return new (std::nothrow) ZSTD_DCtx_s(); }
 size_t ZSTD_freeDCtx(ZSTD_DCtx* d) { if (d) { d->E.destroy(); delete d; } return 0; }
 
@@ -946,7 +964,23 @@ size_t ZSTDB200_compressBatch(ZSTD_CCtx* cctx, size_t n, int level, const void* 
     if (!cctx) return (size_t)make_error(zb::kGeneric);
     zb::DeviceGuard guard;
     if (!zb::level_supported(level)) { for (size_t i = 0; i < n; i++) result[i] = (size_t)make_error(zb::kParameterUnsupported); return 0; }
-    return zb::compress_batch_host(cctx->E, n, level, cctx->checksum, cctx->chunked, src, srcSize, dst, dstCap, result);
+    size_t derr = 0;
+    const zb::EncDict* const dict = cctx_dict(cctx, level, &derr);
+    if (derr) { for (size_t i = 0; i < n; i++) result[i] = derr; return 0; }
+    return zb::compress_batch_host(cctx->E, n, level, cctx->checksum, cctx->chunked, src, srcSize, dst, dstCap, result, dict);
+}
+
+// Compressor.LoadDictionary (Compressor.cs:43-56) -> ZSTD_CCtx_loadDictionary (U/ZstdCompress.cs:1683): the bytes are copied and kept; NULL / 0
+// returns the context to no-dictionary mode.  The dictionary is digested by the first compression that follows.
+size_t ZSTD_CCtx_loadDictionary(ZSTD_CCtx* cctx, const void* dict, size_t dictSize)
+{
+    if (!cctx) return (size_t)make_error(zb::kGeneric);
+    zb::DeviceGuard guard;
+    if (cctx->E.device >= 0) cudaSetDevice(cctx->E.device);
+    cctx->encDict.release();
+    cctx->dictBytes.clear();
+    if (dict && dictSize) cctx->dictBytes.assign((const uint8_t*)dict, (const uint8_t*)dict + dictSize);
+    return 0;
 }
 
 // ZSTD_compressCCtx (U/ZstdCompress.cs:5772): parameters derived from the level alone (contentSize 1, checksum 0), whatever was set
@@ -1026,7 +1060,10 @@ size_t ZSTDB200_compressBatchDevice(ZSTD_CCtx* cctx, size_t n, int level, const 
     E.launches = 0; memset(E.timings, 0, sizeof(E.timings));
     if (n == 0) return 0;
     if (!zb::level_supported(level)) { for (size_t i = 0; i < n; i++) result[i] = (size_t)make_error(zb::kParameterUnsupported); return 0; }
-    if (!zb::enc_compress_device(E.enc, E.stream, E.ev, n, level, cctx->checksum, (const uint8_t*)d_src, srcOffset, srcSize, (uint8_t*)d_dst, dstOffset, dstCapacity, result, E.timings, &E.launches))
+    size_t derr = 0;
+    const zb::EncDict* const dict = cctx_dict(cctx, level, &derr);
+    if (derr) { for (size_t i = 0; i < n; i++) result[i] = derr; return 0; }
+    if (!zb::enc_compress_device(E.enc, E.stream, E.ev, n, level, cctx->checksum, (const uint8_t*)d_src, srcOffset, srcSize, (uint8_t*)d_dst, dstOffset, dstCapacity, result, E.timings, &E.launches, dict))
         { zb::set_error(zb::enc_last_error()); return (size_t)make_error(zb::kGeneric); }
     return 0;
 }
@@ -1145,6 +1182,7 @@ size_t ZSTDB200_multiLoadDictionary(ZSTDB200_Multi* m, const void* dict, size_t 
     if (!m) return (size_t)make_error(zb::kGeneric);
     size_t r = 0;
     for (auto* d : m->d) { size_t const x = ZSTD_DCtx_loadDictionary(d, dict, dictSize); if (zb::is_error(x)) r = x; }
+    for (auto* c : m->c) { size_t const x = ZSTD_CCtx_loadDictionary(c, dict, dictSize); if (zb::is_error(x)) r = x; }
     return r;
 }
 

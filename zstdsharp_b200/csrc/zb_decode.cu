@@ -329,7 +329,9 @@ void dec_build_default_tables(uint32_t* d, cudaStream_t s) { dec_default_tables_
 // ZSTD_decompress_insertDictionary / ZSTD_loadDEntropy (ZstdDecompress.cs:1880, :1770), one thread, once per loaded dictionary.
 // A dictionary without the magic number is pure content.  The Huffman table is stored in the single-symbol form the literal
 // kernel reads (the reference builds the double-symbol form of the same code).
-__global__ void dec_dict_kernel(const uint8_t* dict, uint32_t dictSize, uint16_t* hufOut, uint32_t* fseOut, uint32_t* info)
+// encStats (optional, for the encode side's CDict: enc_dict_build_kernel): [0..255] Huffman weights | [256] Huffman tableLog | [257] nbSymbols |
+// then for OF, ML, LL: 64 normalized counts (sign-extended), maxSymbolValue, tableLog (kEncDictStatsWords words).
+__global__ void dec_dict_kernel(const uint8_t* dict, uint32_t dictSize, uint16_t* hufOut, uint32_t* fseOut, uint32_t* info, uint32_t* encStats)
 {
     __shared__ SetupScratch sc;
     if (threadIdx.x != 0) return;
@@ -349,6 +351,7 @@ __global__ void dec_dict_kernel(const uint8_t* dict, uint32_t dictSize, uint16_t
                 for (uint32_t u = 0; u < len; u++) hufOut[st + u] = (uint16_t)((s << 8) | (tlog + 1 - w));
             }
             info[3] = tlog; pos += hs;
+            if (encStats) { for (uint32_t q = 0; q < 256; q++) encStats[q] = q < nbSym ? sc.weights[q] : 0u; encStats[256] = tlog; encStats[257] = nbSym; }
             int const kinds[3] = {2, 1, 0};                         // stored in the order OF, ML, LL
             for (int q = 0; q < 3 && status == 1; q++) {
                 int const kind = kinds[q];
@@ -356,6 +359,7 @@ __global__ void dec_dict_kernel(const uint8_t* dict, uint32_t dictSize, uint16_t
                 uint32_t maxSV = maxSym, tableLog = 0;
                 uint32_t const h = fse_read_ncount(sc.norm, &maxSV, &tableLog, dict + pos, dictSize - pos);
                 if (h == 0 || maxSV > maxSym || tableLog > maxLog) { status = 2; break; }
+                if (encStats) { uint32_t* const e = encStats + 258 + q * 66; for (uint32_t u = 0; u < 64; u++) e[u] = (uint32_t)(int32_t)(u <= maxSym ? sc.norm[u] : (int16_t)0); e[64] = maxSV; e[65] = tableLog; }
                 build_seq_table(fseOut + (kind == 0 ? kFseLLOff : (kind == 1 ? kFseMLOff : kFseOFOff)), sc, maxSV, tableLog, kind);
                 info[kind == 0 ? 4 : (kind == 1 ? 6 : 5)] = tableLog;
                 pos += h;
@@ -374,8 +378,8 @@ __global__ void dec_dict_kernel(const uint8_t* dict, uint32_t dictSize, uint16_t
     info[10] = pos; info[11] = status == 1 ? dictSize - pos : 0;
     info[0] = status;
 }
-void dec_launch_dict_setup(const uint8_t* d_dict, uint32_t dictSize, uint16_t* d_huf, uint32_t* d_fse, uint32_t* d_info, cudaStream_t s)
-{ dec_dict_kernel<<<1, 32, 0, s>>>(d_dict, dictSize, d_huf, d_fse, d_info); }
+void dec_launch_dict_setup(const uint8_t* d_dict, uint32_t dictSize, uint16_t* d_huf, uint32_t* d_fse, uint32_t* d_info, cudaStream_t s, uint32_t* d_encStats)
+{ dec_dict_kernel<<<1, 32, 0, s>>>(d_dict, dictSize, d_huf, d_fse, d_info, d_encStats); }
 
 __global__ void dec_dict_prefill_kernel(DecPass p, uint32_t contentOff, uint32_t contentSize)
 {

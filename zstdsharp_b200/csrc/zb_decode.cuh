@@ -152,7 +152,8 @@ void dec_launch_wave(const DecPass& p, cudaStream_t s);
 void dec_launch_wave_timed(const DecPass& p, cudaStream_t s, cudaEvent_t* ev5);
 void dec_launch_finish(const DecPass& p, cudaStream_t s);
 // parses a dictionary that already sits in device memory (one thread; a one-off per ZSTD_DCtx_loadDictionary)
-void dec_launch_dict_setup(const uint8_t* d_dict, uint32_t dictSize, uint16_t* d_huf, uint32_t* d_fse, uint32_t* d_info, cudaStream_t s);
+constexpr uint32_t kEncDictStatsWords = 258 + 3 * 66;     // what the encode side's CDict needs from the parse (dec_dict_kernel)
+void dec_launch_dict_setup(const uint8_t* d_dict, uint32_t dictSize, uint16_t* d_huf, uint32_t* d_fse, uint32_t* d_info, cudaStream_t s, uint32_t* d_encStats = nullptr);
 // copies the dictionary content in front of every item's output slot (the caller left p.dictInfo[11] bytes of headroom there)
 void dec_launch_dict_prefill(const DecPass& p, uint32_t contentOff, uint32_t contentSize, cudaStream_t s);
 

@@ -27,6 +27,7 @@
 #include <string>
 #include <vector>
 #include "zb_encode.cuh"
+#include "zb_decode.cuh"      // the dictionary header is parsed by the decode side's dec_dict_kernel
 
 namespace zb {
 
@@ -64,6 +65,47 @@ static CParams get_cparams(int level, uint64_t srcSize)
     return adjust_cparams(adjust_cparams(c, srcSize), srcSize);
 }
 
+// With a dictionary (ZSTD_getCParamsFromCCtxParams :2156 = ZSTD_getCParams_internal :7891 + ZSTD_adjustCParams_internal :2023 twice;
+// row size :7852, ZSTD_dictAndWindowLog :1985).  mode: 0 noAttachDict, 1 attachDict, 2 createCDict.
+constexpr uint64_t kSrcSizeUnknown = ~0ull;
+static uint32_t dict_and_window_log(uint32_t windowLog, uint64_t srcSize, uint64_t dictSize)
+{
+    if (dictSize == 0) return windowLog;
+    uint64_t const windowSize = 1ull << windowLog, dictAndWindowSize = dictSize + windowSize;
+    if (windowSize >= dictSize + srcSize) return windowLog;
+    if (dictAndWindowSize >= (1ull << 31)) return 31;
+    return h_highbit((uint32_t)dictAndWindowSize - 1) + 1;
+}
+static CParams adjust_cparams_dict(CParams c, uint64_t srcSize, uint64_t dictSize, int mode)
+{
+    if (mode == 2) { if (dictSize && srcSize == kSrcSizeUnknown) srcSize = 513; }
+    else if (mode == 1) dictSize = 0;
+    if (srcSize < (1ull << 30) && dictSize < (1ull << 30)) {
+        uint32_t const t = (uint32_t)(srcSize + dictSize);
+        uint32_t const srcLog = t < 64 ? 6 : h_highbit(t - 1) + 1;
+        if (c.windowLog > srcLog) c.windowLog = srcLog;
+    }
+    if (srcSize != kSrcSizeUnknown) {
+        uint32_t const dawl = dict_and_window_log(c.windowLog, srcSize, dictSize);
+        if (c.hashLog > dawl + 1) c.hashLog = dawl + 1;
+        if (c.chainLog > dawl) c.chainLog -= (c.chainLog - dawl);
+    }
+    if (c.windowLog < 10) c.windowLog = 10;
+    return c;
+}
+static CParams get_cparams_dict(int level, uint64_t srcSizeHint, uint64_t dictSize, int mode)
+{
+    uint64_t const rowDict = mode == 1 ? 0 : dictSize;
+    bool const unknown = srcSizeHint == kSrcSizeUnknown;
+    uint64_t const rSize = (unknown && rowDict == 0) ? kSrcSizeUnknown : srcSizeHint + rowDict + ((unknown && rowDict > 0) ? 500 : 0);   // wraps for `unknown` with a dictionary, as in the reference
+    uint32_t const tableID = (rSize <= 256 * 1024) + (rSize <= 128 * 1024) + (rSize <= 16 * 1024);
+    int const row = level == 0 ? 3 : (level < 0 ? 0 : level);
+    CParams c = kDefaultCParams[tableID][row];
+    if (c.strategy == 0) return c;
+    if (level < 0) c.targetLength = (uint32_t)(-(level < -(1 << 17) ? -(1 << 17) : level));
+    return adjust_cparams_dict(adjust_cparams_dict(c, srcSizeHint, dictSize, mode), srcSizeHint, dictSize, mode);
+}
+
 // ------------------------------------------------------------------------------------------------------------
 //  Device-side layout
 // ------------------------------------------------------------------------------------------------------------
@@ -89,8 +131,16 @@ struct __align__(16) EncItem {
     uint32_t hufCur;        // which of the frame's two Huffman table slots holds prevCBlock's table
     uint32_t stepSize;      // ZSTD_fast: distance between probe pairs (2, or targetLength + 1 for the negative levels)
     uint32_t rawLits;       // literal compression disabled (negative levels)
-    uint32_t _pad[3];
+    // ---- frames compressed with a loaded dictionary (enc_match_dict_kernel); all 0 otherwise ----
+    uint32_t dMode;         // 0 no dictionary, 1 the CDict is attached (ZSTD_resetCCtx_byAttachingCDict :2746), 2 copied (:2803)
+    uint32_t dPrefix;       // the reference's index of src[0]: 2 + dictionary content length
+    uint32_t dStep;         // stepSize of the dictionary variants: targetLength + !targetLength (ZstdFast.cs:395, :588)
+    uint32_t wLow, wDictLimit, loadedDictEnd, dms;   // ms->window.lowLimit / .dictLimit, ms->loadedDictEnd, ms->dictMatchState != NULL: advanced block by block
+    uint32_t fseValid;      // prevCBlock->entropy.fse.*_repeatMode == FSE_repeat_valid: 1 LL, 2 OF, 4 ML (only a dictionary makes them valid)
+    uint32_t fseValidNext;  // nextCBlock's, confirmed with the block
+    uint32_t _pad[2];
 };
+static_assert(sizeof(EncItem) % 16 == 0, "EncItem is copied and indexed as 16-byte units");
 
 // Geometry of block `wave` of a frame (ZSTD_compress_frameChunk :4690 + ZSTD_window_enforceMaxDist, ZstdCompressInternal.cs:630;
 // ZSTD_getLowestPrefixIndex :802).  Positions are byte offsets from the frame start; the reference's index of a position is +2.
@@ -112,6 +162,14 @@ __device__ __forceinline__ BlkGeom blk_geom(uint32_t frameSize, uint32_t windowL
 }
 
 struct FseGTable; struct EntCarry;
+// The digested dictionary of a pass (ZSTD_CDict_s: content, match-finder tables filled with dtlm_full, entropy tables); content == nullptr: none
+struct EncDictDev {
+    const uint8_t* content; uint32_t contentLen; uint32_t dictID;
+    const uint32_t* tables;         // ZSTD_fast: hashTable[1 << hashLog]; ZSTD_dfast: hashLong[1 << hashLog] | hashSmall[1 << chainLog]
+    uint32_t hashLog, chainLog;
+    const uint8_t* huf;             // {u8 nbBits[256]; u16 value[256]}: the dictionary's Huffman CTable (HUF_readCTable)
+    const FseGTable* fse;           // [3] LL, OF, ML
+};
 struct EncPass {
     EncItem* items; uint32_t nItems;
     const uint8_t* src; uint8_t* dst;
@@ -124,6 +182,7 @@ struct EncPass {
     EntCarry* carry;        // [item]
     uint8_t* hufState;      // multi-block frames: 2 slots of {u8 nbBits[256]; u16 value[256]} per frame (prev / next Huffman CTable)
     uint32_t checksumFlag;  // ZSTD_c_checksumFlag: append the low 32 bits of XXH64(src) to every frame
+    EncDictDev dict;
 };
 constexpr uint32_t kHufStateSlot = 768;
 
@@ -152,6 +211,7 @@ __device__ __forceinline__ uint32_t hash_val(uint64_t x, uint32_t hBits, uint32_
     case 5: return (uint32_t)(((x << 24) * 889523592379ull) >> (64 - hBits));
     case 6: return (uint32_t)(((x << 16) * 227718039650203ull) >> (64 - hBits));
     case 7: return (uint32_t)(((x << 8) * 58295818150454627ull) >> (64 - hBits));
+    case 8: return (uint32_t)((x * 0xCF1BBCDCB7A56463ull) >> (64 - hBits));
     }
 }
 
@@ -933,13 +993,15 @@ __device__ uint32_t huf_write_ctable(EntShared& S, uint32_t maxSymbolValue, uint
     return ((maxSymbolValue + 1) / 2) + 1;
 }
 
-// ZSTD_selectEncodingType (ZstdCompressSequences.cs:400), strategy < ZSTD_lazy, first block (no repeat mode)
-__device__ uint32_t select_encoding_type(uint32_t mostFrequent, uint32_t nbSeq, uint32_t defaultNormLog, bool isDefaultAllowed, uint32_t strategy)
+// ZSTD_selectEncodingType (ZstdCompressSequences.cs:400), strategy < ZSTD_lazy.  `valid`: the previous table's repeat mode is
+// FSE_repeat_valid (only a dictionary's tables are); every outcome but set_repeat (3) leaves the mode `none` or `check`.
+__device__ uint32_t select_encoding_type(uint32_t mostFrequent, uint32_t nbSeq, uint32_t defaultNormLog, bool isDefaultAllowed, uint32_t strategy, bool valid = false)
 {
     if (mostFrequent == nbSeq) { if (isDefaultAllowed && nbSeq <= 2) return 0; return 1; }
     if (isDefaultAllowed) {
         uint32_t const mult = 10 - strategy;
         uint32_t const dynamicFse_nbSeq_min = ((1u << defaultNormLog) * mult) >> 3;
+        if (valid && nbSeq < 1000) return 3;                                              // staticFse_nbSeq_max (:420)
         if ((nbSeq < dynamicFse_nbSeq_min) || (mostFrequent < (nbSeq >> (defaultNormLog - 1)))) return 0;
     }
     return 2;
@@ -955,6 +1017,652 @@ __device__ __forceinline__ void put_bits(uint32_t* w, uint64_t bit, uint32_t v, 
     uint32_t const sh = (uint32_t)(bit & 31); uint64_t const x = (uint64_t)(nb < 32 ? (v & ((1u << nb) - 1)) : v) << sh;
     atomicOr(&w[bit >> 5], (uint32_t)x);
     if (sh + nb > 32) atomicOr(&w[(bit >> 5) + 1], (uint32_t)(x >> 32));
+}
+
+// ------------------------------------------------------------------------------------------------------------
+//  Dictionary compression (Compressor.LoadDictionary + Wrap): serial match finders, one THREAD per frame.
+//  ZstdFast.cs:390 (dictMatchState), :583 (extDict), ZstdDoubleFast.cs:250, :590, and the no-dictionary forms (ZstdFast.cs:96,
+//  ZstdDoubleFast.cs:51) for the blocks behind an invalidated dictionary.  The dictionary content is one shared device buffer;
+//  a frame's bytes are its source: `dictBase + index` / `base + index` are the reference's two segments, and a match may run
+//  from the first into the second (ZSTD_count_2segments, ZstdCompressInternal.cs:283).  This is the first, correct form of the
+//  path: 32 independent parses per warp, no speculation (the batch is the parallelism); the group kernels above remain the
+//  no-dictionary path.
+// ------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t hash_ptr(const uint8_t* p, uint32_t hBits, uint32_t mls) { return hash_val(rd64(p), hBits, mls); }
+// ZSTD_count, ZstdCompressInternal.cs:264
+__device__ uint32_t count_match(const uint8_t* pIn, const uint8_t* pMatch, const uint8_t* const pInLimit)
+{
+    const uint8_t* const pStart = pIn;
+    while (pIn + 4 <= pInLimit) {
+        uint32_t const diff = rd32(pIn) ^ rd32(pMatch);
+        if (diff) return (uint32_t)(pIn - pStart) + (__ffs((int)diff) - 1) / 8;
+        pIn += 4; pMatch += 4;
+    }
+    while (pIn < pInLimit && *pMatch == *pIn) { pIn++; pMatch++; }
+    return (uint32_t)(pIn - pStart);
+}
+// ZSTD_count_2segments, ZstdCompressInternal.cs:283
+__device__ uint32_t count_2segments(const uint8_t* ip, const uint8_t* match, const uint8_t* iEnd, const uint8_t* mEnd, const uint8_t* iStart)
+{
+    const uint8_t* const vEnd = (ip + (mEnd - match)) < iEnd ? ip + (mEnd - match) : iEnd;
+    uint32_t const matchLength = count_match(ip, match, vEnd);
+    if (match + matchLength != mEnd) return matchLength;
+    return matchLength + count_match(ip + matchLength, iStart, iEnd);
+}
+struct SeqWriter {
+    uint32_t* ll; uint32_t* ml; uint32_t* of; uint32_t n;
+    __device__ __forceinline__ void store(uint32_t litLength, uint32_t offCode, uint32_t mlBase)   // ZSTD_storeSeq :204
+    { ZB_ASSERT(n < kEncSeqCap); ll[n] = litLength; of[n] = offCode + 1; ml[n] = mlBase; n++; }
+};
+// what the serial parsers share: the two segments and the block
+struct DictBlk {
+    const uint8_t* base; const uint8_t* dictBase;     // index -> byte, in the prefix (>= prefixStartIndex) / in the dictionary segment
+    const uint8_t* istart; const uint8_t* iend;
+    uint32_t prefixStartIndex, dictStartIndex;        // extDict / dictMatchState: dictionary segment = [dictStartIndex, prefixStartIndex)
+    uint32_t mls, dStep;
+};
+
+// ZstdFast.cs:390 ZSTD_compressBlock_fast_dictMatchState_generic
+__device__ uint32_t dict_fast_dms(uint32_t* hashTable, uint32_t hlog, const uint32_t* dictHashTable, uint32_t dictHLog, const DictBlk& b, uint32_t rep[2], SeqWriter& sw)
+{
+    const uint8_t* const base = b.base; const uint8_t* const dictBase = b.dictBase; uint32_t const mls = b.mls, stepSize = b.dStep;
+    uint32_t const prefixStartIndex = b.prefixStartIndex, dictStartIndex = b.dictStartIndex;
+    const uint8_t* const prefixStart = base + prefixStartIndex; const uint8_t* const dictStart = dictBase + dictStartIndex; const uint8_t* const dictEnd = dictBase + prefixStartIndex;
+    const uint8_t* ip = b.istart; const uint8_t* anchor = b.istart; const uint8_t* const iend = b.iend; const uint8_t* const ilimit = iend - 8;
+    uint32_t offset_1 = rep[0], offset_2 = rep[1];
+    uint32_t const dictAndPrefixLength = (uint32_t)(ip - prefixStart) + (prefixStartIndex - dictStartIndex);
+    ip += (dictAndPrefixLength == 0);
+    while (ip < ilimit) {
+        uint32_t mLength; uint32_t const h = hash_ptr(ip, hlog, mls);
+        uint32_t const curr = (uint32_t)(ip - base), matchIndex = hashTable[h]; const uint8_t* match = base + matchIndex;
+        uint32_t const repIndex = curr + 1 - offset_1; const uint8_t* const repMatch = repIndex < prefixStartIndex ? dictBase + repIndex : base + repIndex;
+        hashTable[h] = curr;
+        if (((uint32_t)((prefixStartIndex - 1) - repIndex) >= 3) && (rd32(repMatch) == rd32(ip + 1))) {
+            const uint8_t* const repMatchEnd = repIndex < prefixStartIndex ? dictEnd : iend;
+            mLength = count_2segments(ip + 1 + 4, repMatch + 4, iend, repMatchEnd, prefixStart) + 4;
+            ip++;
+            sw.store((uint32_t)(ip - anchor), 0, mLength - 3);
+        } else if (matchIndex <= prefixStartIndex) {
+            uint32_t const dictMatchIndex = dictHashTable[hash_ptr(ip, dictHLog, mls)]; const uint8_t* dictMatch = dictBase + dictMatchIndex;
+            if (dictMatchIndex <= dictStartIndex || rd32(dictMatch) != rd32(ip)) { ip += ((ip - anchor) >> 8) + stepSize; continue; }
+            uint32_t const offset = curr - dictMatchIndex;
+            mLength = count_2segments(ip + 4, dictMatch + 4, iend, dictEnd, prefixStart) + 4;
+            while (((ip > anchor) & (dictMatch > dictStart)) && (ip[-1] == dictMatch[-1])) { ip--; dictMatch--; mLength++; }
+            offset_2 = offset_1; offset_1 = offset;
+            sw.store((uint32_t)(ip - anchor), offset + 2, mLength - 3);
+        } else if (rd32(match) != rd32(ip)) { ip += ((ip - anchor) >> 8) + stepSize; continue; }
+        else {
+            uint32_t const offset = (uint32_t)(ip - match);
+            mLength = count_match(ip + 4, match + 4, iend) + 4;
+            while (((ip > anchor) & (match > prefixStart)) && (ip[-1] == match[-1])) { ip--; match--; mLength++; }
+            offset_2 = offset_1; offset_1 = offset;
+            sw.store((uint32_t)(ip - anchor), offset + 2, mLength - 3);
+        }
+        ip += mLength; anchor = ip;
+        if (ip <= ilimit) {
+            hashTable[hash_ptr(base + curr + 2, hlog, mls)] = curr + 2;
+            hashTable[hash_ptr(ip - 2, hlog, mls)] = (uint32_t)(ip - 2 - base);
+            while (ip <= ilimit) {
+                uint32_t const current2 = (uint32_t)(ip - base), repIndex2 = current2 - offset_2;
+                const uint8_t* const repMatch2 = repIndex2 < prefixStartIndex ? dictBase + repIndex2 : base + repIndex2;
+                if (((uint32_t)((prefixStartIndex - 1) - repIndex2) >= 3) && (rd32(repMatch2) == rd32(ip))) {
+                    const uint8_t* const repEnd2 = repIndex2 < prefixStartIndex ? dictEnd : iend;
+                    uint32_t const repLength2 = count_2segments(ip + 4, repMatch2 + 4, iend, repEnd2, prefixStart) + 4;
+                    uint32_t const t = offset_2; offset_2 = offset_1; offset_1 = t;
+                    sw.store(0, 0, repLength2 - 3);
+                    hashTable[hash_ptr(ip, hlog, mls)] = current2;
+                    ip += repLength2; anchor = ip;
+                    continue;
+                }
+                break;
+    }   }   }
+    rep[0] = offset_1; rep[1] = offset_2;         // offsetSaved is 0 and the offsets never are (:520-521)
+    return (uint32_t)(iend - anchor);
+}
+
+// ZstdFast.cs:583 ZSTD_compressBlock_fast_extDict_generic (the caller has already ruled out prefixStartIndex == dictStartIndex)
+__device__ uint32_t dict_fast_ext(uint32_t* hashTable, uint32_t hlog, const DictBlk& b, uint32_t rep[2], SeqWriter& sw)
+{
+    const uint8_t* const base = b.base; const uint8_t* const dictBase = b.dictBase; uint32_t const mls = b.mls, stepSize = b.dStep;
+    uint32_t const prefixStartIndex = b.prefixStartIndex, dictStartIndex = b.dictStartIndex;
+    const uint8_t* const prefixStart = base + prefixStartIndex; const uint8_t* const dictStart = dictBase + dictStartIndex; const uint8_t* const dictEnd = dictBase + prefixStartIndex;
+    const uint8_t* ip = b.istart; const uint8_t* anchor = b.istart; const uint8_t* const iend = b.iend; const uint8_t* const ilimit = iend - 8;
+    uint32_t offset_1 = rep[0], offset_2 = rep[1];
+    while (ip < ilimit) {
+        uint32_t const h = hash_ptr(ip, hlog, mls);
+        uint32_t const matchIndex = hashTable[h]; const uint8_t* match = (matchIndex < prefixStartIndex ? dictBase : base) + matchIndex;
+        uint32_t const curr = (uint32_t)(ip - base), repIndex = curr + 1 - offset_1;
+        const uint8_t* const repMatch = (repIndex < prefixStartIndex ? dictBase : base) + repIndex;
+        hashTable[h] = curr;
+        if ((((uint32_t)((prefixStartIndex - 1) - repIndex) >= 3) & (offset_1 <= curr + 1 - dictStartIndex)) && (rd32(repMatch) == rd32(ip + 1))) {
+            const uint8_t* const repMatchEnd = repIndex < prefixStartIndex ? dictEnd : iend;
+            uint32_t const rLength = count_2segments(ip + 1 + 4, repMatch + 4, iend, repMatchEnd, prefixStart) + 4;
+            ip++;
+            sw.store((uint32_t)(ip - anchor), 0, rLength - 3);
+            ip += rLength; anchor = ip;
+        } else {
+            if ((matchIndex < dictStartIndex) || (rd32(match) != rd32(ip))) { ip += ((ip - anchor) >> 8) + stepSize; continue; }
+            const uint8_t* const matchEnd = matchIndex < prefixStartIndex ? dictEnd : iend;
+            const uint8_t* const lowMatchPtr = matchIndex < prefixStartIndex ? dictStart : prefixStart;
+            uint32_t const offset = curr - matchIndex;
+            uint32_t mLength = count_2segments(ip + 4, match + 4, iend, matchEnd, prefixStart) + 4;
+            while (((ip > anchor) & (match > lowMatchPtr)) && (ip[-1] == match[-1])) { ip--; match--; mLength++; }
+            offset_2 = offset_1; offset_1 = offset;
+            sw.store((uint32_t)(ip - anchor), offset + 2, mLength - 3);
+            ip += mLength; anchor = ip;
+        }
+        if (ip <= ilimit) {
+            hashTable[hash_ptr(base + curr + 2, hlog, mls)] = curr + 2;
+            hashTable[hash_ptr(ip - 2, hlog, mls)] = (uint32_t)(ip - 2 - base);
+            while (ip <= ilimit) {
+                uint32_t const current2 = (uint32_t)(ip - base), repIndex2 = current2 - offset_2;
+                const uint8_t* const repMatch2 = (repIndex2 < prefixStartIndex ? dictBase : base) + repIndex2;
+                if ((((uint32_t)((prefixStartIndex - 1) - repIndex2) >= 3) & (offset_2 <= curr - dictStartIndex)) && (rd32(repMatch2) == rd32(ip))) {     // `curr`, as the reference has it (:676)
+                    const uint8_t* const repEnd2 = repIndex2 < prefixStartIndex ? dictEnd : iend;
+                    uint32_t const repLength2 = count_2segments(ip + 4, repMatch2 + 4, iend, repEnd2, prefixStart) + 4;
+                    uint32_t const t = offset_2; offset_2 = offset_1; offset_1 = t;
+                    sw.store(0, 0, repLength2 - 3);
+                    hashTable[hash_ptr(ip, hlog, mls)] = current2;
+                    ip += repLength2; anchor = ip;
+                    continue;
+                }
+                break;
+    }   }   }
+    rep[0] = offset_1; rep[1] = offset_2;
+    return (uint32_t)(iend - anchor);
+}
+
+// ZstdDoubleFast.cs:250 ZSTD_compressBlock_doubleFast_dictMatchState_generic
+__device__ uint32_t dict_dfast_dms(uint32_t* hashLong, uint32_t hBitsL, uint32_t* hashSmall, uint32_t hBitsS,
+                                   const uint32_t* dictHashLong, uint32_t dictHBitsL, const uint32_t* dictHashSmall, uint32_t dictHBitsS,
+                                   const DictBlk& b, uint32_t rep[2], SeqWriter& sw)
+{
+    const uint8_t* const base = b.base; const uint8_t* const dictBase = b.dictBase; uint32_t const mls = b.mls;
+    uint32_t const prefixLowestIndex = b.prefixStartIndex, dictStartIndex = b.dictStartIndex;
+    const uint8_t* const prefixLowest = base + prefixLowestIndex; const uint8_t* const dictStart = dictBase + dictStartIndex; const uint8_t* const dictEnd = dictBase + prefixLowestIndex;
+    const uint8_t* ip = b.istart; const uint8_t* anchor = b.istart; const uint8_t* const iend = b.iend; const uint8_t* const ilimit = iend - 8;
+    uint32_t offset_1 = rep[0], offset_2 = rep[1];
+    uint32_t const dictAndPrefixLength = (uint32_t)(ip - prefixLowest) + (prefixLowestIndex - dictStartIndex);
+    ip += (dictAndPrefixLength == 0);
+    while (ip < ilimit) {
+        uint32_t mLength, offset;
+        uint64_t const x = rd64(ip);
+        uint32_t const h2 = hash_val(x, hBitsL, 8), h = hash_val(x, hBitsS, mls), dictHL = hash_val(x, dictHBitsL, 8), dictHS = hash_val(x, dictHBitsS, mls);
+        uint32_t const curr = (uint32_t)(ip - base);
+        uint32_t const matchIndexL = hashLong[h2]; uint32_t matchIndexS = hashSmall[h];
+        const uint8_t* matchLong = base + matchIndexL; const uint8_t* match = base + matchIndexS;
+        uint32_t const repIndex = curr + 1 - offset_1; const uint8_t* const repMatch = repIndex < prefixLowestIndex ? dictBase + repIndex : base + repIndex;
+        hashLong[h2] = hashSmall[h] = curr;
+        if (((uint32_t)((prefixLowestIndex - 1) - repIndex) >= 3) && (rd32(repMatch) == rd32(ip + 1))) {
+            const uint8_t* const repMatchEnd = repIndex < prefixLowestIndex ? dictEnd : iend;
+            mLength = count_2segments(ip + 1 + 4, repMatch + 4, iend, repMatchEnd, prefixLowest) + 4;
+            ip++;
+            sw.store((uint32_t)(ip - anchor), 0, mLength - 3);
+            goto _match_stored;
+        }
+        if (matchIndexL > prefixLowestIndex) {
+            if (rd64(matchLong) == x) {
+                mLength = count_match(ip + 8, matchLong + 8, iend) + 8;
+                offset = (uint32_t)(ip - matchLong);
+                while (((ip > anchor) & (matchLong > prefixLowest)) && (ip[-1] == matchLong[-1])) { ip--; matchLong--; mLength++; }
+                goto _match_found;
+            }
+        } else {
+            uint32_t const dictMatchIndexL = dictHashLong[dictHL]; const uint8_t* dictMatchL = dictBase + dictMatchIndexL;
+            if (dictMatchL > dictStart && rd64(dictMatchL) == x) {
+                mLength = count_2segments(ip + 8, dictMatchL + 8, iend, dictEnd, prefixLowest) + 8;
+                offset = curr - dictMatchIndexL;
+                while (((ip > anchor) & (dictMatchL > dictStart)) && (ip[-1] == dictMatchL[-1])) { ip--; dictMatchL--; mLength++; }
+                goto _match_found;
+        }   }
+        if (matchIndexS > prefixLowestIndex) {
+            if (rd32(match) == (uint32_t)x) goto _search_next_long;
+        } else {
+            uint32_t const dictMatchIndexS = dictHashSmall[dictHS];
+            match = dictBase + dictMatchIndexS; matchIndexS = dictMatchIndexS;
+            if (match > dictStart && rd32(match) == (uint32_t)x) goto _search_next_long;
+        }
+        ip += ((ip - anchor) >> 8) + 1;
+        continue;
+_search_next_long:
+        {   uint64_t const x1 = rd64(ip + 1);
+            uint32_t const hl3 = hash_val(x1, hBitsL, 8), dictHLNext = hash_val(x1, dictHBitsL, 8);
+            uint32_t const matchIndexL3 = hashLong[hl3]; const uint8_t* matchL3 = base + matchIndexL3;
+            hashLong[hl3] = curr + 1;
+            if (matchIndexL3 > prefixLowestIndex) {
+                if (rd64(matchL3) == x1) {
+                    mLength = count_match(ip + 9, matchL3 + 8, iend) + 8;
+                    ip++;
+                    offset = (uint32_t)(ip - matchL3);
+                    while (((ip > anchor) & (matchL3 > prefixLowest)) && (ip[-1] == matchL3[-1])) { ip--; matchL3--; mLength++; }
+                    goto _match_found;
+                }
+            } else {
+                uint32_t const dictMatchIndexL3 = dictHashLong[dictHLNext]; const uint8_t* dictMatchL3 = dictBase + dictMatchIndexL3;
+                if (dictMatchL3 > dictStart && rd64(dictMatchL3) == x1) {
+                    mLength = count_2segments(ip + 1 + 8, dictMatchL3 + 8, iend, dictEnd, prefixLowest) + 8;
+                    ip++;
+                    offset = curr + 1 - dictMatchIndexL3;
+                    while (((ip > anchor) & (dictMatchL3 > dictStart)) && (ip[-1] == dictMatchL3[-1])) { ip--; dictMatchL3--; mLength++; }
+                    goto _match_found;
+        }   }   }
+        if (matchIndexS < prefixLowestIndex) {
+            mLength = count_2segments(ip + 4, match + 4, iend, dictEnd, prefixLowest) + 4;
+            offset = curr - matchIndexS;
+            while (((ip > anchor) & (match > dictStart)) && (ip[-1] == match[-1])) { ip--; match--; mLength++; }
+        } else {
+            mLength = count_match(ip + 4, match + 4, iend) + 4;
+            offset = (uint32_t)(ip - match);
+            while (((ip > anchor) & (match > prefixLowest)) && (ip[-1] == match[-1])) { ip--; match--; mLength++; }
+        }
+_match_found:
+        offset_2 = offset_1; offset_1 = offset;
+        sw.store((uint32_t)(ip - anchor), offset + 2, mLength - 3);
+_match_stored:
+        ip += mLength; anchor = ip;
+        if (ip <= ilimit) {
+            {   uint32_t const indexToInsert = curr + 2;
+                hashLong[hash_ptr(base + indexToInsert, hBitsL, 8)] = indexToInsert;
+                hashLong[hash_ptr(ip - 2, hBitsL, 8)] = (uint32_t)(ip - 2 - base);
+                hashSmall[hash_ptr(base + indexToInsert, hBitsS, mls)] = indexToInsert;
+                hashSmall[hash_ptr(ip - 1, hBitsS, mls)] = (uint32_t)(ip - 1 - base);
+            }
+            while (ip <= ilimit) {
+                uint32_t const current2 = (uint32_t)(ip - base), repIndex2 = current2 - offset_2;
+                const uint8_t* const repMatch2 = repIndex2 < prefixLowestIndex ? dictBase + repIndex2 : base + repIndex2;
+                if (((uint32_t)((prefixLowestIndex - 1) - repIndex2) >= 3) && (rd32(repMatch2) == rd32(ip))) {
+                    const uint8_t* const repEnd2 = repIndex2 < prefixLowestIndex ? dictEnd : iend;
+                    uint32_t const repLength2 = count_2segments(ip + 4, repMatch2 + 4, iend, repEnd2, prefixLowest) + 4;
+                    uint32_t const t = offset_2; offset_2 = offset_1; offset_1 = t;
+                    sw.store(0, 0, repLength2 - 3);
+                    hashSmall[hash_ptr(ip, hBitsS, mls)] = current2;
+                    hashLong[hash_ptr(ip, hBitsL, 8)] = current2;
+                    ip += repLength2; anchor = ip;
+                    continue;
+                }
+                break;
+    }   }   }
+    rep[0] = offset_1; rep[1] = offset_2;
+    return (uint32_t)(iend - anchor);
+}
+
+// ZstdDoubleFast.cs:590 ZSTD_compressBlock_doubleFast_extDict_generic
+__device__ uint32_t dict_dfast_ext(uint32_t* hashLong, uint32_t hBitsL, uint32_t* hashSmall, uint32_t hBitsS, const DictBlk& b, uint32_t rep[2], SeqWriter& sw)
+{
+    const uint8_t* const base = b.base; const uint8_t* const dictBase = b.dictBase; uint32_t const mls = b.mls;
+    uint32_t const prefixStartIndex = b.prefixStartIndex, dictStartIndex = b.dictStartIndex;
+    const uint8_t* const prefixStart = base + prefixStartIndex; const uint8_t* const dictStart = dictBase + dictStartIndex; const uint8_t* const dictEnd = dictBase + prefixStartIndex;
+    const uint8_t* ip = b.istart; const uint8_t* anchor = b.istart; const uint8_t* const iend = b.iend; const uint8_t* const ilimit = iend - 8;
+    uint32_t offset_1 = rep[0], offset_2 = rep[1];
+    auto seg = [&](uint32_t idx) { return (idx < prefixStartIndex ? dictBase : base) + idx; };
+    while (ip < ilimit) {
+        uint64_t const x = rd64(ip);
+        uint32_t const hSmall = hash_val(x, hBitsS, mls); uint32_t const matchIndex = hashSmall[hSmall]; const uint8_t* match = seg(matchIndex);
+        uint32_t const hLong = hash_val(x, hBitsL, 8); uint32_t const matchLongIndex = hashLong[hLong]; const uint8_t* matchLong = seg(matchLongIndex);
+        uint32_t const curr = (uint32_t)(ip - base), repIndex = curr + 1 - offset_1; const uint8_t* const repMatch = seg(repIndex);
+        uint32_t mLength;
+        hashSmall[hSmall] = hashLong[hLong] = curr;
+        if ((((uint32_t)((prefixStartIndex - 1) - repIndex) >= 3) & (offset_1 <= curr + 1 - dictStartIndex)) && (rd32(repMatch) == rd32(ip + 1))) {
+            const uint8_t* const repMatchEnd = repIndex < prefixStartIndex ? dictEnd : iend;
+            mLength = count_2segments(ip + 1 + 4, repMatch + 4, iend, repMatchEnd, prefixStart) + 4;
+            ip++;
+            sw.store((uint32_t)(ip - anchor), 0, mLength - 3);
+        } else {
+            if ((matchLongIndex > dictStartIndex) && (rd64(matchLong) == x)) {
+                const uint8_t* const matchEnd = matchLongIndex < prefixStartIndex ? dictEnd : iend;
+                const uint8_t* const lowMatchPtr = matchLongIndex < prefixStartIndex ? dictStart : prefixStart;
+                mLength = count_2segments(ip + 8, matchLong + 8, iend, matchEnd, prefixStart) + 8;
+                uint32_t const offset = curr - matchLongIndex;
+                while (((ip > anchor) & (matchLong > lowMatchPtr)) && (ip[-1] == matchLong[-1])) { ip--; matchLong--; mLength++; }
+                offset_2 = offset_1; offset_1 = offset;
+                sw.store((uint32_t)(ip - anchor), offset + 2, mLength - 3);
+            } else if ((matchIndex > dictStartIndex) && (rd32(match) == (uint32_t)x)) {
+                uint64_t const x1 = rd64(ip + 1);
+                uint32_t const h3 = hash_val(x1, hBitsL, 8); uint32_t const matchIndex3 = hashLong[h3]; const uint8_t* match3 = seg(matchIndex3);
+                uint32_t offset;
+                hashLong[h3] = curr + 1;
+                if ((matchIndex3 > dictStartIndex) && (rd64(match3) == x1)) {
+                    const uint8_t* const matchEnd = matchIndex3 < prefixStartIndex ? dictEnd : iend;
+                    const uint8_t* const lowMatchPtr = matchIndex3 < prefixStartIndex ? dictStart : prefixStart;
+                    mLength = count_2segments(ip + 9, match3 + 8, iend, matchEnd, prefixStart) + 8;
+                    ip++;
+                    offset = curr + 1 - matchIndex3;
+                    while (((ip > anchor) & (match3 > lowMatchPtr)) && (ip[-1] == match3[-1])) { ip--; match3--; mLength++; }
+                } else {
+                    const uint8_t* const matchEnd = matchIndex < prefixStartIndex ? dictEnd : iend;
+                    const uint8_t* const lowMatchPtr = matchIndex < prefixStartIndex ? dictStart : prefixStart;
+                    mLength = count_2segments(ip + 4, match + 4, iend, matchEnd, prefixStart) + 4;
+                    offset = curr - matchIndex;
+                    while (((ip > anchor) & (match > lowMatchPtr)) && (ip[-1] == match[-1])) { ip--; match--; mLength++; }
+                }
+                offset_2 = offset_1; offset_1 = offset;
+                sw.store((uint32_t)(ip - anchor), offset + 2, mLength - 3);
+            } else { ip += ((ip - anchor) >> 8) + 1; continue; }
+        }
+        ip += mLength; anchor = ip;
+        if (ip <= ilimit) {
+            {   uint32_t const indexToInsert = curr + 2;
+                hashLong[hash_ptr(base + indexToInsert, hBitsL, 8)] = indexToInsert;
+                hashLong[hash_ptr(ip - 2, hBitsL, 8)] = (uint32_t)(ip - 2 - base);
+                hashSmall[hash_ptr(base + indexToInsert, hBitsS, mls)] = indexToInsert;
+                hashSmall[hash_ptr(ip - 1, hBitsS, mls)] = (uint32_t)(ip - 1 - base);
+            }
+            while (ip <= ilimit) {
+                uint32_t const current2 = (uint32_t)(ip - base), repIndex2 = current2 - offset_2; const uint8_t* const repMatch2 = seg(repIndex2);
+                if ((((uint32_t)((prefixStartIndex - 1) - repIndex2) >= 3) & (offset_2 <= current2 - dictStartIndex)) && (rd32(repMatch2) == rd32(ip))) {
+                    const uint8_t* const repEnd2 = repIndex2 < prefixStartIndex ? dictEnd : iend;
+                    uint32_t const repLength2 = count_2segments(ip + 4, repMatch2 + 4, iend, repEnd2, prefixStart) + 4;
+                    uint32_t const t = offset_2; offset_2 = offset_1; offset_1 = t;
+                    sw.store(0, 0, repLength2 - 3);
+                    hashSmall[hash_ptr(ip, hBitsS, mls)] = current2;
+                    hashLong[hash_ptr(ip, hBitsL, 8)] = current2;
+                    ip += repLength2; anchor = ip;
+                    continue;
+                }
+                break;
+    }   }   }
+    rep[0] = offset_1; rep[1] = offset_2;
+    return (uint32_t)(iend - anchor);
+}
+
+// ZstdFast.cs:96 ZSTD_compressBlock_fast_noDict_generic, serial (blocks of a dictionary frame that no longer see the dictionary)
+__device__ uint32_t nodict_fast(uint32_t* hashTable, uint32_t hlog, const DictBlk& b, uint32_t stepSize, uint32_t maxRep, uint32_t rep[2], SeqWriter& sw)
+{
+    const uint8_t* const base = b.base; uint32_t const mls = b.mls; uint32_t const prefixStartIndex = b.prefixStartIndex;
+    const uint8_t* const prefixStart = base + prefixStartIndex;
+    const uint8_t* const iend = b.iend; const uint8_t* const ilimit = iend - 8;
+    const uint8_t* anchor = b.istart; const uint8_t* ip0 = b.istart; const uint8_t* ip1; const uint8_t* ip2; const uint8_t* ip3;
+    uint32_t current0 = 0; uint32_t rep1 = rep[0], rep2 = rep[1], offsetSaved = 0;
+    uint32_t hash0, hash1, idx, mval, offcode; const uint8_t* match0; uint32_t mLength; uint32_t step; const uint8_t* nextStep;
+    ip0 += (ip0 == prefixStart);
+    if (rep2 > maxRep) { offsetSaved = rep2; rep2 = 0; }          // :131-145
+    if (rep1 > maxRep) { offsetSaved = rep1; rep1 = 0; }
+_start:
+    step = stepSize; nextStep = ip0 + 128;
+    ip1 = ip0 + 1; ip2 = ip0 + step; ip3 = ip2 + 1;
+    if (ip3 >= ilimit) goto _cleanup;
+    hash0 = hash_ptr(ip0, hlog, mls); hash1 = hash_ptr(ip1, hlog, mls);
+    idx = hashTable[hash0];
+    do {
+        uint32_t const rval = rep1 ? rd32(ip2 - rep1) : 0;
+        current0 = (uint32_t)(ip0 - base);
+        hashTable[hash0] = current0;
+        if ((rep1 > 0) && (rd32(ip2) == rval)) {
+            ip0 = ip2; match0 = ip0 - rep1;
+            mLength = ip0[-1] == match0[-1];
+            ip0 -= mLength; match0 -= mLength;
+            offcode = 0; mLength += 4;
+            goto _match;
+        }
+        mval = idx >= prefixStartIndex ? rd32(base + idx) : (rd32(ip0) ^ 1);
+        if (rd32(ip0) == mval) goto _offset;
+        idx = hashTable[hash1];
+        hash0 = hash1; hash1 = hash_ptr(ip2, hlog, mls);
+        ip0 = ip1; ip1 = ip2; ip2 = ip3;
+        current0 = (uint32_t)(ip0 - base);
+        hashTable[hash0] = current0;
+        mval = idx >= prefixStartIndex ? rd32(base + idx) : (rd32(ip0) ^ 1);
+        if (rd32(ip0) == mval) goto _offset;
+        idx = hashTable[hash1];
+        hash0 = hash1; hash1 = hash_ptr(ip2, hlog, mls);
+        ip0 = ip1; ip1 = ip2; ip2 = ip0 + step; ip3 = ip1 + step;
+        if (ip2 >= nextStep) { step++; nextStep += 128; }
+    } while (ip3 < ilimit);
+_cleanup:
+    rep[0] = rep1 ? rep1 : offsetSaved;                 // :232-233
+    rep[1] = rep2 ? rep2 : offsetSaved;
+    return (uint32_t)(iend - anchor);
+_offset:
+    match0 = base + idx;
+    rep2 = rep1; rep1 = (uint32_t)(ip0 - match0);
+    offcode = rep1 + 2;
+    mLength = 4;
+    while (((ip0 > anchor) & (match0 > prefixStart)) && (ip0[-1] == match0[-1])) { ip0--; match0--; mLength++; }
+_match:
+    mLength += count_match(ip0 + mLength, match0 + mLength, iend);
+    sw.store((uint32_t)(ip0 - anchor), offcode, mLength - 3);
+    ip0 += mLength; anchor = ip0;
+    if (ip1 < ip0) hashTable[hash1] = (uint32_t)(ip1 - base);
+    if (ip0 <= ilimit) {
+        hashTable[hash_ptr(base + current0 + 2, hlog, mls)] = current0 + 2;
+        hashTable[hash_ptr(ip0 - 2, hlog, mls)] = (uint32_t)(ip0 - 2 - base);
+        if (rep2 > 0) {
+            while ((ip0 <= ilimit) && (rd32(ip0) == rd32(ip0 - rep2))) {
+                uint32_t const rLength = count_match(ip0 + 4, ip0 + 4 - rep2, iend) + 4;
+                { uint32_t const t = rep2; rep2 = rep1; rep1 = t; }
+                hashTable[hash_ptr(ip0, hlog, mls)] = (uint32_t)(ip0 - base);
+                ip0 += rLength;
+                sw.store(0, 0, rLength - 3);
+                anchor = ip0;
+            }
+        }
+    }
+    goto _start;
+}
+
+// ZstdDoubleFast.cs:51 ZSTD_compressBlock_doubleFast_noDict_generic, serial
+__device__ uint32_t nodict_dfast(uint32_t* hashLong, uint32_t hBitsL, uint32_t* hashSmall, uint32_t hBitsS, const DictBlk& b, uint32_t maxRep, uint32_t rep[2], SeqWriter& sw)
+{
+    const uint8_t* const base = b.base; uint32_t const mls = b.mls; uint32_t const prefixLowestIndex = b.prefixStartIndex;
+    const uint8_t* const prefixLowest = base + prefixLowestIndex;
+    const uint8_t* const istart = b.istart; const uint8_t* const iend = b.iend; const uint8_t* const ilimit = iend - 8;
+    const uint8_t* anchor = istart;
+    uint32_t offset_1 = rep[0], offset_2 = rep[1], offsetSaved = 0;
+    uint32_t mLength, offset, curr = 0;
+    const uint8_t* nextStep; uint32_t step; uint32_t hl0, hl1 = 0; uint32_t idxl0, idxl1 = 0;
+    const uint8_t* matchl0; const uint8_t* matchs0; const uint8_t* matchl1 = istart;
+    const uint8_t* ip = istart; const uint8_t* ip1;
+    ip += ((ip - prefixLowest) == 0);
+    if (offset_2 > maxRep) { offsetSaved = offset_2; offset_2 = 0; }
+    if (offset_1 > maxRep) { offsetSaved = offset_1; offset_1 = 0; }
+    while (1) {
+        step = 1; nextStep = ip + 256; ip1 = ip + step;
+        if (ip1 > ilimit) goto _cleanup;
+        hl0 = hash_ptr(ip, hBitsL, 8);
+        idxl0 = hashLong[hl0]; matchl0 = base + idxl0;
+        do {
+            uint32_t const hs0 = hash_ptr(ip, hBitsS, mls);
+            uint32_t const idxs0 = hashSmall[hs0];
+            curr = (uint32_t)(ip - base);
+            matchs0 = base + idxs0;
+            hashLong[hl0] = hashSmall[hs0] = curr;
+            if ((offset_1 > 0) && (rd32(ip + 1 - offset_1) == rd32(ip + 1))) {
+                mLength = count_match(ip + 1 + 4, ip + 1 + 4 - offset_1, iend) + 4;
+                ip++;
+                sw.store((uint32_t)(ip - anchor), 0, mLength - 3);
+                goto _match_stored;
+            }
+            hl1 = hash_ptr(ip1, hBitsL, 8);
+            if (idxl0 > prefixLowestIndex) {
+                if (rd64(matchl0) == rd64(ip)) {
+                    mLength = count_match(ip + 8, matchl0 + 8, iend) + 8;
+                    offset = (uint32_t)(ip - matchl0);
+                    while (((ip > anchor) & (matchl0 > prefixLowest)) && (ip[-1] == matchl0[-1])) { ip--; matchl0--; mLength++; }
+                    goto _match_found;
+                }
+            }
+            idxl1 = hashLong[hl1]; matchl1 = base + idxl1;
+            if (idxs0 > prefixLowestIndex) {
+                if (rd32(matchs0) == rd32(ip)) goto _search_next_long;
+            }
+            if (ip1 >= nextStep) { step++; nextStep += 256; }
+            ip = ip1; ip1 += step;
+            hl0 = hl1; idxl0 = idxl1; matchl0 = matchl1;
+        } while (ip1 <= ilimit);
+_cleanup:
+        rep[0] = offset_1 ? offset_1 : offsetSaved;     // :215-216
+        rep[1] = offset_2 ? offset_2 : offsetSaved;
+        return (uint32_t)(iend - anchor);
+_search_next_long:
+        if (idxl1 > prefixLowestIndex) {
+            if (rd64(matchl1) == rd64(ip1)) {
+                ip = ip1;
+                mLength = count_match(ip + 8, matchl1 + 8, iend) + 8;
+                offset = (uint32_t)(ip - matchl1);
+                while (((ip > anchor) & (matchl1 > prefixLowest)) && (ip[-1] == matchl1[-1])) { ip--; matchl1--; mLength++; }
+                goto _match_found;
+            }
+        }
+        mLength = count_match(ip + 4, matchs0 + 4, iend) + 4;
+        offset = (uint32_t)(ip - matchs0);
+        while (((ip > anchor) & (matchs0 > prefixLowest)) && (ip[-1] == matchs0[-1])) { ip--; matchs0--; mLength++; }
+_match_found:
+        offset_2 = offset_1; offset_1 = offset;
+        if (step < 4) hashLong[hl1] = (uint32_t)(ip1 - base);
+        sw.store((uint32_t)(ip - anchor), offset + 2, mLength - 3);
+_match_stored:
+        ip += mLength; anchor = ip;
+        if (ip <= ilimit) {
+            {   uint32_t const indexToInsert = curr + 2;
+                hashLong[hash_ptr(base + indexToInsert, hBitsL, 8)] = indexToInsert;
+                hashLong[hash_ptr(ip - 2, hBitsL, 8)] = (uint32_t)(ip - 2 - base);
+                hashSmall[hash_ptr(base + indexToInsert, hBitsS, mls)] = indexToInsert;
+                hashSmall[hash_ptr(ip - 1, hBitsS, mls)] = (uint32_t)(ip - 1 - base);
+            }
+            while ((ip <= ilimit) && ((offset_2 > 0) && (rd32(ip) == rd32(ip - offset_2)))) {
+                uint32_t const rLength = count_match(ip + 4, ip + 4 - offset_2, iend) + 4;
+                uint32_t const t = offset_2; offset_2 = offset_1; offset_1 = t;
+                hashSmall[hash_ptr(ip, hBitsS, mls)] = (uint32_t)(ip - base);
+                hashLong[hash_ptr(ip, hBitsL, 8)] = (uint32_t)(ip - base);
+                sw.store(0, 0, rLength - 3);
+                ip += rLength; anchor = ip;
+            }
+        }
+    }
+}
+
+// One thread per frame: block `wave` of a frame compressed with a loaded dictionary.  The window bookkeeping of
+// ZSTD_compress_frameChunk (:4690: ZSTD_checkDictValidity, ZSTD_window_enforceMaxDist) runs here, per block, and picks the
+// variant the way ZSTD_matchState_dictMode / ZSTD_selectBlockCompressor do (ZstdCompressInternal.cs:576, ZstdCompress.cs:3398).
+__global__ void __launch_bounds__(32) enc_match_dict_kernel(EncPass p, const uint32_t* __restrict__ workList, uint32_t nWork, uint32_t wave)
+{
+    uint32_t const wi = blockIdx.x * 32 + threadIdx.x;
+    if (wi >= nWork) return;
+    uint32_t const item = workList[wi];
+    EncItem& it = p.items[item];
+    const uint8_t* const src = p.src + it.srcOff;
+    uint32_t const blkStart = wave * kBlockSizeMax, blkSize = min(kBlockSizeMax, it.srcSize - blkStart);
+    uint32_t const srcIdx0 = it.dPrefix;                             // index of src[0]: 2 + dictionary content length (2 when nothing was attached)
+    const uint8_t* const base = src - srcIdx0;
+    uint32_t const maxDist = 1u << it.windowLog;
+    uint32_t lowLimit = it.wLow, dictLimit = it.wDictLimit, loadedDictEnd = it.loadedDictEnd, dms = it.dms;
+    {   // ZSTD_checkDictValidity (ZstdCompressInternal.cs:697) on the block's end, ZSTD_window_enforceMaxDist (:659) on its start
+        uint32_t const endIdx = srcIdx0 + blkStart + blkSize, startIdx = srcIdx0 + blkStart;
+        if (endIdx > loadedDictEnd + maxDist) { loadedDictEnd = 0; dms = 0; }
+        if (startIdx > maxDist + loadedDictEnd) {
+            uint32_t const newLowLimit = startIdx - maxDist;
+            if (lowLimit < newLowLimit) lowLimit = newLowLimit;
+            if (dictLimit < lowLimit) dictLimit = lowLimit;
+            loadedDictEnd = 0; dms = 0;
+        }
+        it.wLow = lowLimit; it.wDictLimit = dictLimit; it.loadedDictEnd = loadedDictEnd; it.dms = dms;
+    }
+    SeqWriter sw{p.seqLL + (size_t)item * kEncSeqCap, p.seqML + (size_t)item * kEncSeqCap, p.seqOF + (size_t)item * kEncSeqCap, 0};
+    uint32_t rep[2] = {it.rep[0], it.rep[1]};
+    uint32_t* const T = p.tables + it.tableOff;
+    uint32_t* const TS = T + ((size_t)1 << it.hashLog);              // ZSTD_dfast: the small table (chainTable) follows the long one
+    bool const fast = it.strategy == 1;
+    DictBlk b;
+    b.base = base; b.dictBase = p.dict.content - 2; b.istart = src + blkStart; b.iend = src + blkStart + blkSize; b.mls = it.minMatch; b.dStep = it.dStep;
+    uint32_t const endIndex = srcIdx0 + blkStart + blkSize;
+    auto lowest = [&](uint32_t lowestValid, uint32_t curr) { return loadedDictEnd != 0 ? lowestValid : ((curr - lowestValid > maxDist) ? curr - maxDist : lowestValid); };   // ZSTD_getLowestMatchIndex / ..PrefixIndex (:787, :802)
+    uint32_t lastLL;
+    bool const extDict = lowLimit < dictLimit;
+    uint32_t const extLow = lowest(lowLimit, endIndex), extPrefix = dictLimit < extLow ? extLow : dictLimit;
+    if (extDict && extPrefix != extLow) {
+        b.dictStartIndex = extLow; b.prefixStartIndex = extPrefix;
+        lastLL = fast ? dict_fast_ext(T, it.hashLog, b, rep, sw) : dict_dfast_ext(T, it.hashLog, TS, it.chainLog, b, rep, sw);
+    } else if (!extDict && dms) {
+        b.dictStartIndex = 2; b.prefixStartIndex = fast ? dictLimit : lowest(dictLimit, endIndex);
+        lastLL = fast ? dict_fast_dms(T, it.hashLog, p.dict.tables, p.dict.hashLog, b, rep, sw)
+                      : dict_dfast_dms(T, it.hashLog, TS, it.chainLog, p.dict.tables, p.dict.hashLog, p.dict.tables + ((size_t)1 << p.dict.hashLog), p.dict.chainLog, b, rep, sw);
+    } else {
+        b.prefixStartIndex = lowest(dictLimit, endIndex); b.dictStartIndex = b.prefixStartIndex;
+        uint32_t const curr0 = srcIdx0 + blkStart + ((srcIdx0 + blkStart) == b.prefixStartIndex);
+        uint32_t const maxRep = curr0 - lowest(dictLimit, curr0);
+        lastLL = fast ? nodict_fast(T, it.hashLog, b, it.stepSize, maxRep, rep, sw) : nodict_dfast(T, it.hashLog, TS, it.chainLog, b, maxRep, rep, sw);
+    }
+    it.nbSeq = sw.n; it.lastLL = lastLL; it.repNext[0] = rep[0]; it.repNext[1] = rep[1];
+}
+
+// Start state of a frame that uses the CDict: prevCBlock's Huffman table is the dictionary's (both :2746 and :2803 copy cdict->cBlockState),
+// and a frame that COPIES the CDict (ZSTD_resetCCtx_byCopyingCDict :2803) starts with the CDict's match-finder tables as its own.
+__global__ void enc_dict_init_kernel(EncPass p, uint32_t nItems, uint32_t entries)
+{
+    uint32_t const item = blockIdx.y;
+    if (item >= nItems) return;
+    EncItem const& it = p.items[item];
+    if (it.dMode == 0) return;
+    if (blockIdx.x == 0 && it.hufRepeat) {
+        uint32_t* const d = (uint32_t*)(p.hufState + (size_t)item * 2 * kHufStateSlot); const uint32_t* const s = (const uint32_t*)p.dict.huf;
+        for (uint32_t k = threadIdx.x; k < kHufStateSlot / 4; k += blockDim.x) d[k] = s[k];
+    }
+    if (it.dMode != 2 || it.srcSize < 7) return;                     // attached frames search the CDict's tables in place
+    uint4* const d = (uint4*)(p.tables + it.tableOff); const uint4* const s = (const uint4*)p.dict.tables;
+    for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < entries / 4; k += gridDim.x * blockDim.x) d[k] = s[k];
+}
+
+// ZSTD_initCDict_internal (:5826) on the device, one thread, once per (dictionary, level): ZSTD_loadCEntropy (:5264: HUF_readCTable
+// HufCompress.cs:249, three FSE_buildCTable_wksp, ZSTD_dictNCountRepeat :5239) from the statistics dec_dict_kernel has already
+// parsed and validated, then ZSTD_fillHashTable / ZSTD_fillDoubleHashTable with dtlm_full (ZstdFast.cs:9, ZstdDoubleFast.cs:9) over
+// the content.  out[]: [0] 1 ok / 2 corrupted | [1] Huffman repeat mode (0 none, 1 check, 2 valid) | [2] FSE `valid` bits (1 LL, 2 OF, 4 ML).
+__global__ void enc_dict_build_kernel(const uint32_t* __restrict__ stats, const uint32_t* __restrict__ info, const uint8_t* content, uint32_t contentLen,
+                                      uint32_t strategy, uint32_t hashLog, uint32_t chainLog, uint32_t mls,
+                                      uint32_t* tables, uint8_t* hufSlot, FseGTable* fse, uint32_t* out)
+{
+    __shared__ FseCTable ct; __shared__ uint16_t cumul[64]; __shared__ uint8_t tableSymbol[512]; __shared__ int16_t norm[64];
+    if (threadIdx.x != 0) return;
+    out[0] = 1; out[1] = 0; out[2] = 0;
+    if (info[2]) {                                                   // a zstd-format dictionary: entropy tables
+        uint32_t const tableLog = stats[256], nbSymbols = stats[257];
+        if (nbSymbols < 256) { out[0] = 2; return; }                 // maxSymbolValue < 255: dictionary_corrupted (:5283)
+        uint16_t* const val = (uint16_t*)(hufSlot + 256);
+        uint32_t nbPerRank[14], valPerRank[14]; bool hasZero = false;
+        for (int r = 0; r < 14; r++) nbPerRank[r] = valPerRank[r] = 0;
+        for (uint32_t n = 0; n < 256; n++) { uint32_t const w = stats[n]; uint32_t const nb = w ? tableLog + 1 - w : 0; hufSlot[n] = (uint8_t)nb; nbPerRank[nb]++; hasZero |= (w == 0); }
+        {   uint32_t mn = 0; for (uint32_t n = tableLog; n > 0; n--) { valPerRank[n] = mn; mn += nbPerRank[n]; mn >>= 1; } }
+        for (uint32_t n = 0; n < 256; n++) val[n] = (uint16_t)(valPerRank[hufSlot[n]]++);
+        out[1] = hasZero ? 1 : 2;
+        uint32_t validBits = 0;
+        for (int q = 0; q < 3; q++) {                                // stats order: OF, ML, LL; fse[] order: LL, OF, ML
+            const uint32_t* const s = stats + 258 + q * 66;
+            uint32_t const maxSV = s[64], tlog = s[65];
+            for (int u = 0; u < 64; u++) norm[u] = (int16_t)(int32_t)s[u];
+            uint32_t const full = q == 0 ? kMaxOff : (q == 1 ? kMaxML : kMaxLL);
+            fse_build_ctable(ct, cumul, tableSymbol, norm, q == 0 ? kMaxOff : maxSV, tlog);      // the offset table is built over all 32 codes (:5297)
+            FseGTable& g = fse[q == 0 ? 1 : (q == 1 ? 2 : 0)];
+            for (uint32_t u = 0; u < 53; u++) g.tt[u] = ct.tt[u];
+            g.tableLog = tlog; g._pad = 0;
+            for (uint32_t u = 0; u < (1u << tlog); u++) g.stateTable[u] = ct.stateTable[u];
+            uint32_t need = full;
+            if (q == 0) { uint32_t const maxOffset = contentLen + 128 * 1024; uint32_t const offcodeMax = contentLen <= 0xFFFFFFFFu - 128 * 1024 ? highbit32(maxOffset) : kMaxOff; need = offcodeMax < kMaxOff ? offcodeMax : kMaxOff; }
+            bool valid = maxSV >= need;                               // ZSTD_dictNCountRepeat
+            for (uint32_t u = 0; valid && u <= need; u++) if (norm[u] == 0) valid = false;
+            if (valid) validBits |= q == 0 ? 2u : (q == 1 ? 4u : 1u);
+        }
+        out[2] = validBits;
+    }
+    if (contentLen > 8) {
+        const uint8_t* const base = content - 2; const uint8_t* ip = content; const uint8_t* const iend = content + contentLen - 8;
+        if (strategy == 1) {
+            for (; ip + 3 < iend + 2; ip += 3) {
+                uint32_t const curr = (uint32_t)(ip - base);
+                tables[hash_ptr(ip, hashLog, mls)] = curr;
+                for (uint32_t q = 1; q < 3; ++q) { uint32_t const h = hash_ptr(ip + q, hashLog, mls); if (tables[h] == 0) tables[h] = curr + q; }
+            }
+        } else {
+            uint32_t* const hashLarge = tables; uint32_t* const hashSmall = tables + ((size_t)1 << hashLog);
+            for (; ip + 3 - 1 <= iend; ip += 3) {
+                uint32_t const curr = (uint32_t)(ip - base);
+                for (uint32_t i = 0; i < 3; ++i) {
+                    uint64_t const x = rd64(ip + i);
+                    uint32_t const smHash = hash_val(x, chainLog, mls), lgHash = hash_val(x, hashLog, 8);
+                    if (i == 0) hashSmall[smHash] = curr + i;
+                    if (i == 0 || hashLarge[lgHash] == 0) hashLarge[lgHash] = curr + i;
+                }
+            }
+        }
+    }
 }
 
 // MB = false: every frame is one block (srcSize <= 128 KiB), one CTA per frame, no state.  MB = true: the CTA handles block
@@ -980,17 +1688,20 @@ __global__ void __launch_bounds__(kEntThreads, MB ? 8 : 15) enc_entropy_kernel(E
     uint32_t const srcSize = MB ? min(kBlockSizeMax, frameSize - blkStart) : frameSize;     // block size
     bool const firstBlock = !MB || wave == 0, lastBlock = !MB || blkStart + srcSize == frameSize;
     if (!MB && srcSize > kBlockSizeMax) { if (tid == 0) { p.results[item] = make_error(kSrcSizeWrong); p.carry[item].flags = 0; } return; }
-    // ---- frame header: ZSTD_writeFrameHeader (ZstdCompress.cs:4817), contentSizeFlag = 1, no dictID ----
+    // ---- frame header: ZSTD_writeFrameHeader (ZstdCompress.cs:4817), contentSizeFlag = 1, the dictionary's id when one is loaded ----
     uint32_t fhSize = 0;
     if (firstBlock) {
         uint32_t const fcsCode = (frameSize >= 256) + (frameSize >= 65536 + 256);
         bool const singleSegment = !MB || ((1u << it.windowLog) >= frameSize);     // windowSize >= pledgedSrcSize (:4823); always for one-block frames
-        fhSize = 4 + 1 + (singleSegment ? 0 : 1) + (fcsCode == 0 ? (singleSegment ? 1 : 0) : (fcsCode == 1 ? 2 : 4));
+        uint32_t const dictID = (MB && it.dMode) ? p.dict.dictID : 0u;
+        uint32_t const dictIDSizeCode = (dictID > 0) + (dictID >= 256) + (dictID >= 65536);
+        fhSize = 4 + 1 + (singleSegment ? 0 : 1) + (dictIDSizeCode == 3 ? 4 : dictIDSizeCode) + (fcsCode == 0 ? (singleSegment ? 1 : 0) : (fcsCode == 1 ? 2 : 4));
         if (tid == 0 && PHASE == 0) {
             dst[0] = 0x28; dst[1] = 0xB5; dst[2] = 0x2F; dst[3] = 0xFD;
-            dst[4] = (uint8_t)((p.checksumFlag ? 4u : 0u) + ((singleSegment ? 1u : 0u) << 5) + (fcsCode << 6));   // FHD: checksum bit 2, singleSegment bit 5, fcsID bits 6-7 (:4823-4829)
+            dst[4] = (uint8_t)(dictIDSizeCode + (p.checksumFlag ? 4u : 0u) + ((singleSegment ? 1u : 0u) << 5) + (fcsCode << 6));   // FHD: dictID size bits 0-1, checksum bit 2, singleSegment bit 5, fcsID bits 6-7 (:4823-4829)
             uint32_t pos = 5;
             if (!singleSegment) dst[pos++] = (uint8_t)((it.windowLog - 10) << 3);
+            if (MB) { uint32_t const nDid = dictIDSizeCode == 3 ? 4u : dictIDSizeCode; for (uint32_t q = 0; q < nDid; q++) dst[pos++] = (uint8_t)(dictID >> (8 * q)); }
             if (fcsCode == 0) { if (singleSegment) dst[pos++] = (uint8_t)frameSize; }
             else if (fcsCode == 1) { uint32_t const v = frameSize - 256; dst[pos] = (uint8_t)v; dst[pos + 1] = (uint8_t)(v >> 8); }
             else { dst[pos] = (uint8_t)frameSize; dst[pos + 1] = (uint8_t)(frameSize >> 8); dst[pos + 2] = (uint8_t)(frameSize >> 16); dst[pos + 3] = (uint8_t)(frameSize >> 24); }
@@ -1048,13 +1759,18 @@ __global__ void __launch_bounds__(kEntThreads, MB ? 8 : 15) enc_entropy_kernel(E
         // ---- 2. literals section: ZSTD_compressLiterals (ZstdCompressLiterals.cs:86) ----
         uint32_t const minGainLit = (litSize >> 6) + 2;
         uint32_t const lhSize = 3 + (litSize >= 1024) + (litSize >= 16384);
-        uint32_t const singleStream = litSize < 256;
+        // prevHuf->repeatMode == HUF_repeat_valid (a dictionary's table that codes every byte value): literals from 7 bytes up are
+        // compressed, below 1 KiB as one stream (ZstdCompressLiterals.cs:103-120), and up to 1 KiB the old table is used without
+        // looking at the literals at all (preferRepeat, HufCompress.cs:1404-1410)
+        bool const hufValid = MB && it.hufRepeat == 2u;
+        bool const direct = hufValid && litSize <= 1024;
+        uint32_t const singleStream = litSize < 256 || (hufValid && lhSize == 3);
         uint32_t const seg = (litSize + 3) / 4;
         uint32_t litMode = 0;   // 0 raw, 1 rle, 2 huffman
-        if (litSize > 63 && !it.rawLits) {       // rawLits: ZSTD_noCompressLiterals right away (ZstdCompressLiterals.cs:100-101)
+        if (litSize > (hufValid ? 6u : 63u) && !it.rawLits) {       // rawLits: ZSTD_noCompressLiterals right away (ZstdCompressLiterals.cs:100-101)
             bool const suspect = (nbSeq == 0) || (litSize / nbSeq >= 20);       // ZstdCompress.cs:3262
             bool skip = false;
-            if (suspect && litSize >= 40960) {                                   // HufCompress.cs:1412-1446
+            if (!direct && suspect && litSize >= 40960) {                        // HufCompress.cs:1412-1446
                 for (uint32_t k = tid; k < 4096; k += kEntThreads) { atomicAdd(&S.hist[0][lit[k]], 1u); atomicAdd(&S.hist[1][lit[litSize - 4096 + k]], 1u); }
                 __syncthreads();
                 uint32_t m0 = 0, m1 = 0;
@@ -1087,8 +1803,8 @@ __global__ void __launch_bounds__(kEntThreads, MB ? 8 : 15) enc_entropy_kernel(E
                 uint32_t largest = 0, maxSym = 0;
                 for (int k = 0; k < kEntThreads / 32; k++) { largest = max(largest, S.scanA[k]); maxSym = max(maxSym, S.scanB[k]); }
                 __syncthreads();
-                if (largest == litSize) litMode = 1;                              // all same byte -> rle (HufCompress.cs:1458)
-                else if (largest <= (litSize >> 7) + 4) litMode = 0;              // not compressible enough (:1463)
+                if (!direct && largest == litSize) litMode = 1;                   // all same byte -> rle (HufCompress.cs:1458)
+                else if (!direct && largest <= (litSize >> 7) + 4) litMode = 0;   // not compressible enough (:1463)
                 else {
                     // HUF_repeat (HufCompress.cs:1475-1530): the previous block's table may be reused (literals header type set_repeat, no
                     // table description).  repeatMode is `check` after any block that shipped a new table; `valid` needs a dictionary.
@@ -1096,7 +1812,7 @@ __global__ void __launch_bounds__(kEntThreads, MB ? 8 : 15) enc_entropy_kernel(E
                     uint32_t repeat = MB ? it.hufRepeat : 0u;
                     const uint8_t* const oldNb = p.hufState + ((size_t)item * 2 + (MB ? it.hufCur : 0u)) * kHufStateSlot;
                     if (MB && repeat) {
-                        int bad = 0;                                               // HUF_validateCTable: every present symbol has a code
+                        int bad = 0;                                               // HUF_validateCTable (only in `check` mode; a valid table codes every symbol)
                         for (uint32_t q = tid; q <= maxSym; q += kEntThreads) bad |= (S.count[q] != 0) & (oldNb[q] == 0);
                         if (__syncthreads_or(bad)) repeat = 0;
                         if (repeat && litSize <= 1024) useOld = true;              // preferRepeat (ZstdCompressLiterals.cs:121)
@@ -1142,6 +1858,7 @@ __global__ void __launch_bounds__(kEntThreads, MB ? 8 : 15) enc_entropy_kernel(E
                         if (!singleStream && litSize < 12) bad = true;
                         if (bad || total >= litSize - 1) litMode = 0;              // HUF_compressCTable_internal :1333-1356
                         else if (total >= litSize - minGainLit) litMode = 0;       // ZstdCompressLiterals.cs:133
+                        else if (total == 1) litMode = 1;                          // cLitSize == 1 -> ZSTD_compressRleLiteralsBlock (:139): one byte value, 7 times a 1-bit code
                         else {
                             litMode = 2;
                             // zero the stream area, then scatter every symbol's code (symbols are appended last-to-first)
@@ -1248,7 +1965,8 @@ __global__ void __launch_bounds__(kEntThreads, MB ? 8 : 15) enc_entropy_kernel(E
                 uint32_t mostFrequent = 0; for (uint32_t q = 0; q <= max; q++) if (count[q] > mostFrequent) mostFrequent = count[q];
                 uint32_t const defLog = k == 1 ? kOFDefaultNormLog : kLLDefaultNormLog;
                 bool const defAllowed = k == 1 ? (max <= (uint32_t)kDefaultMaxOff) : true;
-                uint32_t const type = select_encoding_type(mostFrequent, nbSeq, defLog, defAllowed, strategy);
+                bool const valid = MB && ((it.fseValid >> (k == 0 ? 0 : (k == 1 ? 1 : 2))) & 1u);      // bits: 1 LL, 2 OF, 4 ML
+                uint32_t const type = select_encoding_type(mostFrequent, nbSeq, defLog, defAllowed, strategy, valid);
                 uint32_t const lastCode = codes[(size_t)(nbSeq - 1) * 4];
                 uint32_t countSize = 0;
                 FseCTable& ct = S.ct[k];
@@ -1256,6 +1974,11 @@ __global__ void __launch_bounds__(kEntThreads, MB ? 8 : 15) enc_entropy_kernel(E
                     ct.tableLog = 0; ct.stateTable[0] = 0; ct.stateTable[1] = 0; ct.tt[max].deltaNbBits = 0; ct.tt[max].deltaFindState = 0;
                     S.hdr3[k][0] = (uint8_t)codes[0];   // the reference writes codeTable[0], the code of the FIRST sequence (all codes are equal here)
                     countSize = 1;
+                } else if (type == 3) {     // set_repeat: the dictionary's table, no description (ZstdCompressSequences.cs:494)
+                    const FseGTable& dg = p.dict.fse[k];
+                    ct.tableLog = dg.tableLog;
+                    for (uint32_t q = 0; q < 53; q++) ct.tt[q] = dg.tt[q];
+                    for (uint32_t q = 0; q < (1u << dg.tableLog); q++) ct.stateTable[q] = dg.stateTable[q];
                 } else if (type == 0) {     // set_basic
                     uint32_t const dmax = k == 0 ? kMaxLL : (k == 1 ? kDefaultMaxOff : kMaxML);
                     for (uint32_t q = 0; q <= dmax; q++) norm[q] = k == 0 ? c_LL_defaultNorm[q] : (k == 1 ? c_OF_defaultNorm[q] : c_ML_defaultNorm[q]);
@@ -1281,6 +2004,7 @@ __global__ void __launch_bounds__(kEntThreads, MB ? 8 : 15) enc_entropy_kernel(E
             }
             __syncthreads();
             if (tid == 0) dst[seqHead] = (uint8_t)((types[0] << 6) + (types[1] << 4) + (types[2] << 2));
+            if (MB && tid == 0) it.fseValidNext = (types[0] == 3 ? 1u : 0u) | (types[1] == 3 ? 2u : 0u) | (types[2] == 3 ? 4u : 0u);    // any other type leaves `none` or `check`
             // ---- hand the three tables to the state-chain kernel ----
             for (int k = 0; k < 3; k++) {
                 const FseCTable& ct = S.ct[k]; FseGTable& g = gt[k];
@@ -1292,6 +2016,7 @@ __global__ void __launch_bounds__(kEntThreads, MB ? 8 : 15) enc_entropy_kernel(E
             }
         }
         if (tid == 0) { cy.op = op; cy.lastCountSize = lastCountSize; cy.flags = (nbSeq > 0 ? 1u : 0u) | (newHuf ? 2u : 0u); }
+        if (MB && tid == 0 && nbSeq == 0) it.fseValidNext = it.fseValid;        // no sequences: the FSE state is carried over as it is (:3283)
         return;
       }
         // ================= PHASE 1: after the state chains =================
@@ -1396,7 +2121,9 @@ __global__ void __launch_bounds__(kEntThreads, MB ? 8 : 15) enc_entropy_kernel(E
         if (!raw && !rle) {
             it.rep[0] = it.repNext[0]; it.rep[1] = it.repNext[1];
             if (newHuf) { it.hufCur ^= 1u; it.hufRepeat = 1u; }
+            it.fseValid = it.fseValidNext;
         }
+        it.fseValid &= ~2u;             // the dictionary's offset table is only trusted for the first block (:4582-4589)
         it.outPos = total;
     }
     if (!lastBlock) return;
@@ -1504,6 +2231,56 @@ struct EncArenaImpl {
 };
 static thread_local std::string t_encErr;
 const char* enc_last_error() { return t_encErr.c_str(); }
+
+// ---- digested dictionary (ZSTD_CDict_s): built on the device once per (dictionary, level) ----
+struct EncDictImpl {
+    DBuf raw, decHuf, decFse, info, stats, tables, huf, fse, out;
+    uint32_t dictSize = 0, contentOff = 0, contentLen = 0, dictID = 0, hufRepeat = 0, fseValid = 0, rep[2] = {1, 4};
+    CParams cp{};               // the CDict's parameters (ZSTD_cpm_createCDict: unknown source size)
+    size_t tableEntries = 0;
+};
+void EncDict::release()
+{
+    if (!impl) return;
+    DBuf* d[] = {&impl->raw, &impl->decHuf, &impl->decFse, &impl->info, &impl->stats, &impl->tables, &impl->huf, &impl->fse, &impl->out};
+    for (auto* b : d) b->release();
+    delete impl; impl = nullptr; level = 0; ready = false;
+}
+// ZSTD_initLocalDict (:1581) -> ZSTD_createCDict_advanced2 (:5933) -> ZSTD_initCDict_internal (:5826).  Returns 0 or a zstd error code.
+size_t enc_dict_digest(EncDict& D, cudaStream_t stream, const void* dict, size_t dictSize, int level)
+{
+    D.release();
+    if (dictSize > 0x7FFFFF00u) return (size_t)make_error(kMemoryAllocation);
+    CParams const cp = get_cparams_dict(level, kSrcSizeUnknown, dictSize, 2);
+    if (cp.strategy == 0) return (size_t)make_error(kParameterUnsupported);       // a level outside ZSTD_fast / ZSTD_dfast for this dictionary size
+    D.impl = new EncDictImpl();
+    EncDictImpl& I = *D.impl;
+    I.cp = cp; I.dictSize = (uint32_t)dictSize;
+    I.tableEntries = ((size_t)1 << cp.hashLog) + (cp.strategy == 2 ? ((size_t)1 << cp.chainLog) : 0);
+    auto fail = [&](ErrorCode e) { D.release(); return (size_t)make_error(e); };
+    if (!I.raw.ensure(dictSize + 64) || !I.decHuf.ensure(kHufTableEntries * 2) || !I.decFse.ensure(kFseTableEntries * 4) || !I.info.ensure(kDictInfoWords * 4) ||
+        !I.stats.ensure(kEncDictStatsWords * 4) || !I.tables.ensure(I.tableEntries * 4 + 16) || !I.huf.ensure(kHufStateSlot) || !I.fse.ensure(3 * sizeof(FseGTable)) || !I.out.ensure(16))
+        return fail(kMemoryAllocation);
+    uint32_t info[kDictInfoWords] = {}, out[4] = {};
+    if (cudaMemsetAsync(I.raw.p, 0, dictSize + 64, stream) != cudaSuccess || cudaMemcpyAsync(I.raw.p, dict, dictSize, cudaMemcpyHostToDevice, stream) != cudaSuccess) return fail(kGeneric);
+    cudaMemsetAsync(I.tables.p, 0, I.tableEntries * 4 + 16, stream); cudaMemsetAsync(I.huf.p, 0, kHufStateSlot, stream); cudaMemsetAsync(I.fse.p, 0, 3 * sizeof(FseGTable), stream);
+    cudaMemsetAsync(I.stats.p, 0, kEncDictStatsWords * 4, stream);
+    dec_launch_dict_setup((const uint8_t*)I.raw.p, (uint32_t)dictSize, (uint16_t*)I.decHuf.p, (uint32_t*)I.decFse.p, (uint32_t*)I.info.p, stream, (uint32_t*)I.stats.p);
+    if (cudaMemcpyAsync(info, I.info.p, sizeof(info), cudaMemcpyDeviceToHost, stream) != cudaSuccess || cudaStreamSynchronize(stream) != cudaSuccess) return fail(kGeneric);
+    // a dictionary the reference cannot digest: ZSTD_createCDict_advanced2 returns NULL and ZSTD_initLocalDict reports memory_allocation (:1604-1607)
+    if (info[0] != 1) return fail(kMemoryAllocation);
+    I.contentOff = dictSize < 8 ? 0 : info[10];
+    I.contentLen = dictSize < 8 ? 0 : info[11];                  // ZSTD_compress_insertDictionary (:5467): below 8 bytes nothing is loaded
+    I.dictID = info[2] ? info[1] : 0;
+    if (info[2]) { I.rep[0] = info[7]; I.rep[1] = info[8]; }
+    enc_dict_build_kernel<<<1, 32, 0, stream>>>((const uint32_t*)I.stats.p, (const uint32_t*)I.info.p, (const uint8_t*)I.raw.p + I.contentOff, I.contentLen,
+                                                 cp.strategy, cp.hashLog, cp.chainLog, cp.minMatch, (uint32_t*)I.tables.p, (uint8_t*)I.huf.p, (FseGTable*)I.fse.p, (uint32_t*)I.out.p);
+    if (cudaMemcpyAsync(out, I.out.p, sizeof(out), cudaMemcpyDeviceToHost, stream) != cudaSuccess || cudaStreamSynchronize(stream) != cudaSuccess || cudaGetLastError() != cudaSuccess) return fail(kGeneric);
+    if (out[0] != 1) return fail(kMemoryAllocation);
+    I.hufRepeat = out[1]; I.fseValid = out[2];
+    D.level = level; D.ready = true;
+    return 0;
+}
 size_t enc_max_frame_bytes() { return kEncMaxFrameBytes; }
 void EncArena::release()
 {
@@ -1530,8 +2307,9 @@ constexpr size_t kEncMaxItemsPerPass = 8192;
 // ev3 (optional): [0] before the match finder, [1] after it (first wave), [2] after the last entropy stage.
 bool enc_enqueue(EncArena& A, cudaStream_t stream, cudaStream_t copyStream, size_t m, int level, int checksumFlag,
                  const uint8_t* d_src, const uint64_t* srcOff, const size_t* srcSize,
-                 uint8_t* d_dst, const uint64_t* dstOff, const size_t* dstCap, cudaEvent_t* ev3, unsigned* launches)
+                 uint8_t* d_dst, const uint64_t* dstOff, const size_t* dstCap, cudaEvent_t* ev3, unsigned* launches, const EncDict* dict)
 {
+    const EncDictImpl* const DI = (dict && dict->ready) ? dict->impl : nullptr;
     if (!A.impl) A.impl = new EncArenaImpl();
     EncArenaImpl& I = *A.impl;
     if (m > kEncMaxItemsPerPass) { t_encErr = "pass too large"; return false; }
@@ -1547,7 +2325,26 @@ bool enc_enqueue(EncArena& A, cudaStream_t stream, cudaStream_t copyStream, size
         memset(&e, 0, sizeof(e));
         e.srcOff = srcOff[i]; e.dstOff = dstOff[i];
         e.srcSize = (uint32_t)std::min<size_t>(ss, 0xFFFFFFF0u); e.dstCap = (uint32_t)std::min<size_t>(dstCap[i], 0xFFFFFFF0u);
-        CParams const c = get_cparams(level, ss);
+        CParams c = get_cparams(level, ss);
+        if (DI) {
+            // ZSTD_CCtx_init_compressStream2 (:6949) + ZSTD_resetCCtx_usingCDict (:2881): the frame's window comes from the level, the
+            // source and the dictionary size; everything else from the CDict -- as it is when the CDict is copied, re-adjusted for
+            // the source size when it is attached (small inputs: ZSTD_shouldAttachDict :2738, 8 KiB for ZSTD_fast, 16 KiB for ZSTD_dfast)
+            bool const attach = ss <= (DI->cp.strategy == 1 ? 8u * 1024 : 16u * 1024);
+            CParams const req = get_cparams_dict(level, ss, DI->dictSize, attach ? 1 : 0);
+            c = attach ? adjust_cparams_dict(DI->cp, ss, DI->dictSize, 1) : DI->cp;
+            if (req.strategy == 0) c.strategy = 0; else c.windowLog = req.windowLog;
+            uint32_t const L = DI->contentLen, cdictEnd = 2 + L;
+            e.dMode = attach ? 1u : 2u; e.dStep = c.targetLength + !c.targetLength;
+            if (attach) {
+                if (L == 0) { e.dPrefix = 2; e.wLow = e.wDictLimit = 2; }                        // cdictLen == 0: nothing to attach (:2779)
+                else { e.dPrefix = cdictEnd; e.wLow = e.wDictLimit = cdictEnd; e.loadedDictEnd = cdictEnd; e.dms = 1; }
+            } else {
+                e.dPrefix = cdictEnd; e.wLow = 2; e.wDictLimit = cdictEnd; e.loadedDictEnd = L ? cdictEnd : 0;
+                if (e.wDictLimit - e.wLow < 8) e.wLow = e.wDictLimit;                             // ZSTD_window_update (ZstdCompressInternal.cs:742)
+            }
+            e.hufRepeat = DI->hufRepeat; e.fseValid = DI->fseValid;
+        }
         e.windowLog = c.windowLog; e.hashLog = c.hashLog; e.chainLog = c.chainLog; e.minMatch = c.minMatch; e.strategy = c.strategy;
         // ZSTD_fast with an acceleration factor: probe pairs `stepSize` apart (hasStep = targetLength > 1, ZstdFast.cs:101, :334) and
         // leave the literals uncompressed (ZSTD_literalsCompressionIsDisabled, ZstdCompressInternal.cs:483-498)
@@ -1556,6 +2353,7 @@ bool enc_enqueue(EncArena& A, cudaStream_t stream, cudaStream_t copyStream, size
         if (c.strategy == 0) { nBlk[i] = 0; hr[i] = make_error(kParameterUnsupported); mb = true; continue; }   // level 4 outside its dfast sizes
         e.nbSeq = 0; e.lastLL = (uint32_t)std::min<size_t>(ss, kBlockSizeMax);
         e.rep[0] = 1; e.rep[1] = 4;                               // repStartValue (ZstdInternal.cs:13)
+        if (DI) { e.rep[0] = DI->rep[0]; e.rep[1] = DI->rep[1]; mb = true; }     // the dictionary's repcodes; dictionary frames always run as block waves (entropy state)
         if (ss > kEncMaxFrameBytes) { nBlk[i] = 0; hr[i] = make_error(kSrcSizeWrong); mb = true; continue; }   // positions are 31-bit
         nBlk[i] = ss <= kBlockSizeMax ? 1u : (uint32_t)((ss + kBlockSizeMax - 1) / kBlockSizeMax);
         if (nBlk[i] > 1) mb = true;
@@ -1565,7 +2363,7 @@ bool enc_enqueue(EncArena& A, cudaStream_t stream, cudaStream_t copyStream, size
         tableEntries += ((size_t)1 << c.hashLog) + (c.strategy == 2 ? ((size_t)1 << c.chainLog) : 0);
     }
     if (tableEntries >= 0xFFFFFFFFull) { t_encErr = "hash-table arena exceeds 32-bit indexing"; return false; }
-    // work lists: per wave [ZSTD_fast groups | (unused) | ZSTD_dfast groups | entropy]
+    // work lists: per wave [ZSTD_fast groups | frames with a dictionary (serial kernel) | ZSTD_dfast groups | entropy]
     struct WaveLists { size_t off[4]; uint32_t n[4]; };
     std::vector<WaveLists> waves(maxWaves);
     size_t const listCap = 2 * totalBlocks + 4;
@@ -1587,7 +2385,7 @@ bool enc_enqueue(EncArena& A, cudaStream_t stream, cudaStream_t copyStream, size
                 size_t const bs = std::min<size_t>(kBlockSizeMax, ss - b * (size_t)kBlockSizeMax);
                 tmp[3].push_back(i);
                 if (ss < 7 || bs < 7) continue;                   // ZSTD_buildSeqStore: noCompress (:3438)
-                tmp[hi[i].strategy == 1 ? 0 : 2].push_back(i);
+                tmp[DI ? 1 : (hi[i].strategy == 1 ? 0 : 2)].push_back(i);
             }
             alive.resize(keep);
             for (int k = 0; k < 4; k++) {
@@ -1612,6 +2410,15 @@ bool enc_enqueue(EncArena& A, cudaStream_t stream, cudaStream_t copyStream, size
     p.items = (EncItem*)I.items.p; p.nItems = (uint32_t)m; p.src = d_src; p.dst = d_dst; p.tables = (uint32_t*)I.tables.p;
     p.seqLL = (uint32_t*)I.seqLL.p; p.seqML = (uint32_t*)I.seqML.p; p.seqOF = (uint32_t*)I.seqOF.p; p.litBuf = (uint8_t*)I.lit.p;
     p.stateBits = (uint64_t*)I.stateBits.p; p.results = hr; p.hufState = (uint8_t*)I.hufState.p; p.fseTabs = (FseGTable*)I.fseTabs.p; p.carry = (EntCarry*)I.carry.p; p.checksumFlag = checksumFlag ? 1u : 0u;
+    memset(&p.dict, 0, sizeof(p.dict));
+    if (DI) {
+        p.dict.content = (const uint8_t*)DI->raw.p + DI->contentOff; p.dict.contentLen = DI->contentLen; p.dict.dictID = DI->dictID;
+        p.dict.tables = (const uint32_t*)DI->tables.p; p.dict.hashLog = DI->cp.hashLog; p.dict.chainLog = DI->cp.chainLog;
+        p.dict.huf = (const uint8_t*)DI->huf.p; p.dict.fse = (const FseGTable*)DI->fse.p;
+        uint32_t const entries = (uint32_t)DI->tableEntries;
+        enc_dict_init_kernel<<<dim3(std::max(1u, std::min(64u, entries / 1024)), (unsigned)m), 256, 0, stream>>>(p, (uint32_t)m, entries);
+        *launches += 1;
+    }
     const uint32_t* const dw = (const uint32_t*)I.workLists.p;
     *launches += tableEntries ? 1 : 0;
     for (size_t b = 0; b < maxWaves; b++) {
@@ -1620,6 +2427,7 @@ bool enc_enqueue(EncArena& A, cudaStream_t stream, cudaStream_t copyStream, size
         // lanes per chunk: 16 measured best for ZSTD_fast (8: 49/52 ms, 16: 42/49 ms, 32: 63/72 ms per GiB Silesia-mix / text)
         if (mb) {
             if (w.n[0]) enc_match_group_kernel<16, true><<<(w.n[0] + 2 * kMatchWarps - 1) / (2 * kMatchWarps), 32 * kMatchWarps, 0, stream>>>(p, dw + w.off[0], w.n[0], wave);
+            if (w.n[1]) enc_match_dict_kernel<<<(w.n[1] + 31) / 32, 32, 0, stream>>>(p, dw + w.off[1], w.n[1], wave);
             if (w.n[2]) enc_match_dfast_group_kernel<16, true><<<(w.n[2] + 2 * kMatchWarps - 1) / (2 * kMatchWarps), 32 * kMatchWarps, 0, stream>>>(p, dw + w.off[2], w.n[2], wave);
             if (ev3 && b == 0) ENC_CUDA(cudaEventRecord(ev3[1], stream));
             if (w.n[3]) {
@@ -1678,13 +2486,13 @@ const uint64_t* enc_results(const EncArena& A) { return A.impl ? (const uint64_t
 bool enc_compress_device(EncArena& A, cudaStream_t stream, cudaEvent_t* ev, size_t n, int level, int checksumFlag,
                          const uint8_t* d_src, const uint64_t* srcOff, const size_t* srcSize,
                          uint8_t* d_dst, const uint64_t* dstOff, const size_t* dstCap, size_t* result,
-                         float* timings, unsigned* launches)
+                         float* timings, unsigned* launches, const EncDict* dict)
 {
     float msAll = 0, msMatch = 0, msEnt = 0;
     enc_set_overlap_mode(false);                 // one pass at a time on one stream: every kernel keeps its own L1 / shared-memory split
     for (size_t base = 0; base < n; base += kEncMaxItemsPerPass) {
         size_t const m = std::min(kEncMaxItemsPerPass, n - base);
-        if (!enc_enqueue(A, stream, stream, m, level, checksumFlag, d_src, srcOff + base, srcSize + base, d_dst, dstOff + base, dstCap + base, &ev[14], launches)) return false;
+        if (!enc_enqueue(A, stream, stream, m, level, checksumFlag, d_src, srcOff + base, srcSize + base, d_dst, dstOff + base, dstCap + base, &ev[14], launches, dict)) return false;
         ENC_CUDA(cudaStreamSynchronize(stream));
         ENC_CUDA(cudaGetLastError());
         float t;

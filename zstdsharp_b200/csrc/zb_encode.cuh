@@ -11,6 +11,16 @@ struct EncArena {
     const uint8_t* compactBuf() const;
 };
 
+// A loaded compression dictionary, digested on the device for one level (Compressor.LoadDictionary, Compressor.cs:43-56: ZSTD_CCtx_loadDictionary
+// stores the bytes, the first ZSTD_compress2 builds the CDict with the level the context has then: ZstdCompress.cs:1581).
+struct EncDictImpl;
+struct EncDict {
+    EncDictImpl* impl = nullptr; int level = 0; bool ready = false;
+    void release();
+};
+// Returns 0 or a zstd error code (memory_allocation for a dictionary the reference cannot digest either, parameter_unsupported for a level outside ZSTD_fast / ZSTD_dfast).
+size_t enc_dict_digest(EncDict& D, cudaStream_t stream, const void* dict, size_t dictSize, int level);
+
 // ZSTD_compressBound, ZstdCompress.cs:19-22
 inline size_t enc_compress_bound(size_t srcSize)
 { return srcSize + (srcSize >> 8) + ((srcSize < (128u << 10)) ? (((128u << 10) - srcSize) >> 11) : 0); }
@@ -23,12 +33,12 @@ size_t enc_max_frame_bytes();
 bool enc_compress_device(EncArena& A, cudaStream_t stream, cudaEvent_t* ev, size_t n, int level, int checksumFlag,
                          const uint8_t* d_src, const uint64_t* srcOff, const size_t* srcSize,
                          uint8_t* d_dst, const uint64_t* dstOff, const size_t* dstCap, size_t* result,
-                         float* timings, unsigned* launches);
+                         float* timings, unsigned* launches, const EncDict* dict = nullptr);
 // Queues one pass (m <= 8192 chunks) on `stream` without waiting; descriptors are copied on `copyStream`; results land in
 // pinned host memory (enc_results) once `stream` has drained.  ev3 (optional): events before/after match, after entropy.
 bool enc_enqueue(EncArena& A, cudaStream_t stream, cudaStream_t copyStream, size_t m, int level, int checksumFlag,
                  const uint8_t* d_src, const uint64_t* srcOff, const size_t* srcSize,
-                 uint8_t* d_dst, const uint64_t* dstOff, const size_t* dstCap, cudaEvent_t* ev3, unsigned* launches);
+                 uint8_t* d_dst, const uint64_t* dstOff, const size_t* dstCap, cudaEvent_t* ev3, unsigned* launches, const EncDict* dict = nullptr);
 const uint64_t* enc_results(const EncArena& A);
 // Gathers the n variable-size frames into one dense device buffer (A.compactBuf()) at offsets cOff.
 bool enc_compact_device(EncArena& A, cudaStream_t stream, size_t n, const uint8_t* d_dst, const uint64_t* dstOff,
