@@ -1941,7 +1941,7 @@ static size_t zo_compress_dict_internal(void* dst, size_t dstCapacity, const voi
     ZSTD_reset_compressedBlockState(&cdictBs);
     if (dictSize >= 8 && MEM_read32(dict) == 0xEC30A437U) {      /* ZSTD_loadZstdDictionary :5424 */
         size_t const eSize = ZSTD_loadCEntropy(&cdictBs, dict, dictSize);
-        if (ERR_isError(eSize)) ZO_DICT_FAIL(eSize);
+        if (ERR_isError(eSize)) ZO_DICT_FAIL(ERROR(memory_allocation));   /* ZSTD_createCDict_advanced2 returns NULL and ZSTD_initLocalDict (:1604) reports memory_allocation */
         dictID = MEM_read32((const BYTE*)dict + 4);
         content = (const BYTE*)dict + eSize; contentLen = dictSize - eSize;
     } else if (dictSize < 8) contentLen = 0;                     /* ZSTD_compress_insertDictionary :5467: nothing is loaded */

@@ -284,6 +284,28 @@ static void gpu_all() {
         DecompressionStream cutDs(cutIs);
         CHECK(thrown_code([&] { Bytes tmp(data.size() + 100); size_t g = 0, q; while ((q = cutDs.Read(tmp.data() + g, tmp.size() - g)) != 0) g += q; }) == ZSTD_ErrorCode::srcSize_wrong);
     }
+    // Compressor.LoadDictionary / Decompressor.LoadDictionary with a raw-content dictionary (ZstdNetTests.cs:19-39, 95-134): the oracle's
+    // bytes (Compressor.LoadDictionary + Wrap), the round trip, and the two failures the reference tests
+    {
+        Bytes const dict = text_like(20000), data = text_like(90000);
+        Bytes expect(zo_compressBound(data.size()));
+        size_t const er = zo_compress_usingLoadedDict(expect.data(), expect.size(), data.data(), data.size(), dict.data(), dict.size(), 3, 0);
+        CHECK(!zo_isError(er)); expect.resize(er);
+        Compressor c(3);
+        c.LoadDictionary(dict.data(), dict.size());
+        Bytes const f = c.Wrap(data);
+        CHECK(f == expect);
+        c.LoadDictionary(nullptr, 0);
+        CHECK(c.Wrap(data) == oracle_compress(data, 3));
+        Decompressor d;
+        d.LoadDictionary(dict.data(), dict.size());
+        CHECK(d.Unwrap(f) == data);
+        d.LoadDictionary(nullptr, 0);
+        CHECK(thrown_code([&] { d.Unwrap(f); }) != ZSTD_ErrorCode::no_error);             // DecompressWithoutDictionary_throwsZstdException_onDataCompressedWithIt
+        std::string const other = "zstd supports raw-content dictionaries";
+        d.LoadDictionary(other.data(), other.size());
+        CHECK(thrown_code([&] { d.Unwrap(f); }) != ZSTD_ErrorCode::no_error);             // DecompressWithAnotherDictionary_throwsZstdException
+    }
     // MultiCodec (ZSTDB200_*BatchMulti): however many devices are visible, the oracle's frames in the caller's order
     {
         MultiCodec m(0, 1);

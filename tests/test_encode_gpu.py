@@ -362,3 +362,35 @@ def test_dictionary_compression_byte_identical(dec, level):
             assert dec.UnwrapBatch(frames) == [p.tobytes() for p in pays], name
         finally:
             dec.LoadDictionary(None)
+
+
+def test_dictionary_tests_of_the_reference(dec):
+    """ZstdNetTests.cs:19-39 (CompressAndDecompress_workCorrectly with a dictionary at the minimum / default / maximum level),
+    :95-134 (decoding without the dictionary, or with another one, throws), plus the reference's verdict on a dictionary it
+    cannot digest: LoadDictionary succeeds, every Wrap reports memory_allocation (ZstdCompress.cs:1604-1607; pinned on the DLL
+    in tests/test_reference_pin.py)."""
+    from zstdsharp_b200 import Compressor, Decompressor, ZstdException
+    from _dict_cases import dictionaries
+    dicts = dictionaries(libzstd())
+    d = dicts["zdict_32k"]
+    data = dg.text_like(3 * FRAME)[FRAME // 2:FRAME // 2 + 90_000]
+    for level in (Compressor.MinCompressionLevel, Compressor.DefaultCompressionLevel, 3):
+        c = Compressor(level); c.LoadDictionary(d)
+        f = bytes(c.Wrap(data)); c.Dispose()
+        dec.LoadDictionary(d)
+        assert bytes(dec.Unwrap(f)) == data.tobytes()
+        dec.LoadDictionary(None)
+        with pytest.raises(ZstdException):                       # DecompressWithoutDictionary_throwsZstdException_onDataCompressedWithIt
+            dec.Unwrap(f)
+        dec.LoadDictionary(b"zstd supports raw-content dictionaries")
+        with pytest.raises(ZstdException):                       # DecompressWithAnotherDictionary_throwsZstdException
+            dec.Unwrap(f)
+        dec.LoadDictionary(None)
+    bad = bytearray(dicts["zdict_4k"]); bad[9] ^= 0xFF; bad[10] ^= 0x55; bad[12] ^= 0xFF
+    c = Compressor(1); c.LoadDictionary(bytes(bad))
+    with pytest.raises(ZstdException) as e:
+        c.Wrap(data)
+    assert int(e.value.Code) == 64
+    c.LoadDictionary(dicts["zdict_4k"])                          # a good dictionary afterwards works
+    assert bytes(c.Wrap(data)) == oracle().compress_loaded_dict(data, 1, dicts["zdict_4k"])
+    c.Dispose()

@@ -219,6 +219,17 @@ def test_dictionary_compression_matches_the_dll():
         for src in (pays[3], pays[8], pays[10]):
             assert o.compress_loaded_dict(src, level, dicts["zdict_32k"]) == r.compress_loaded_dict(src, level, dicts["zdict_32k"]), (level, src.size)
     assert n >= 300
+    # a dictionary whose entropy header is damaged: loading succeeds, every compression reports memory_allocation (64),
+    # because ZSTD_createCDict_advanced2 returns NULL (ZstdCompress.cs:1604-1607)
+    bad = bytearray(dicts["zdict_4k"]); bad[9] ^= 0xFF; bad[10] ^= 0x55; bad[12] ^= 0xFF
+    L = r.lib
+    c = L.ZREF_createCCtx(); L.ZREF_CCtx_setParameter(c, 100, 1)
+    db = np.frombuffer(bytes(bad), dtype=np.uint8); out = np.empty(70000, dtype=np.uint8)
+    assert not L.ZREF_isError(L.ZREF_CCtx_loadDictionary(c, db.ctypes.data, db.size))
+    rv = L.ZREF_compress2(c, out.ctypes.data, out.size, pays[3].ctypes.data, pays[3].size)
+    L.ZREF_freeCCtx(c)
+    ro, _ = o.compress_loaded_dict_raw(pays[3], 1, bytes(bad))
+    assert r.error_code(rv) == o.error_code(ro) == 64
 
 
 def test_handbuilt_tiny_four_stream_literals():
