@@ -2,8 +2,9 @@
 libzstd.dll -- shared by tests/test_soak_gpu.py (-m gpu) and scripts/soak_gpu.py (longer runs, fresh seeds).
 
 Every input is compressed on the GPU at levels 1..3 and must be byte-identical to the oracle's frame; every GPU frame and a
-libzstd frame of a random higher level must decode on the GPU to the input; a mutated copy of every frame must give the
-oracle's answer: the same bytes, or the same error code.  Failing cases are written to gpurun_out/soakfail_* so that they replay
+libzstd frame of a random higher level must decode on the GPU to the input; a quarter of the inputs is compressed and decoded again
+with a raw-content and with a trained dictionary; a mutated copy of every frame must give the oracle's answer: the same bytes,
+or the same error code.  Failing cases are written to gpurun_out/soakfail_* so that they replay
 on the CPU.  The fixed test set missed two decoder defects with a rate of about 1 in 30 000 inputs in round 1; this is the net.
 """
 import os
@@ -79,7 +80,7 @@ def gen_one(rng):
 
 
 
-def run_soak(n_inputs, seed, comp, dec, log=print, levels=(1, 2, 3)):
+def run_soak(n_inputs, seed, comp, dec, log=print, levels=(1, 2, 3), dict_phase=True):
     """Returns the number of disagreements (0 = clean)."""
     rng = np.random.default_rng(seed)
     t0 = time.time()
@@ -137,6 +138,49 @@ def run_soak(n_inputs, seed, comp, dec, log=print, levels=(1, 2, 3)):
                 dump(f"decode_{name.replace(' ', '_').replace('.', '')}_{i}", frames[i], a.tobytes())
         bad += nb
         log(f"decode {name}: {nb} mismatches of {n_inputs}")
+    # dictionaries (Compressor.LoadDictionary / Decompressor.LoadDictionary): a raw-content dictionary cut from this run's own data at
+    # a random size and a trained zstd-format one, a quarter of the inputs each, one ZSTD_fast and one ZSTD_dfast level
+    if dict_phase:
+        pool = _pool()
+        raw_src = pool[list(pool)[int(rng.integers(0, len(pool)))]]
+        raw_len = int(rng.integers(8, 200_000)); raw_off = int(rng.integers(0, raw_src.size - raw_len))
+        samples = [pool["text"][i * 3000:(i + 1) * 3000].tobytes() for i in range(200)]
+        dicts = [("raw", raw_src[raw_off:raw_off + raw_len].tobytes()), ("zdict", z.train_dictionary(samples, int(rng.integers(2000, 60000))))]
+        sub = inputs[::4]
+        for dname, d in dicts:
+            for level in (levels[0], levels[-1]):
+                comp.Level = level
+                comp.LoadDictionary(d)
+                try:
+                    frames = comp.WrapBatch(sub)
+                finally:
+                    comp.LoadDictionary(None)
+                with ThreadPoolExecutor(16) as ex:
+                    want = list(ex.map(lambda a: o.compress_loaded_dict(a, level, d), sub))
+                nb = 0
+                for i, (f, w) in enumerate(zip(frames, want)):
+                    if f != w:
+                        nb += 1
+                        if nb <= 3:
+                            log(f"  MISMATCH dictionary {dname} ({len(d)} bytes) level {level} input {4 * i} size {sub[i].size}: gpu {len(f)} oracle {len(w)}")
+                            dump(f"dict_{dname}_L{level}_{4 * i}", sub[i].tobytes(), w, f)
+                if r is not None:
+                    for i in range(0, len(sub), max(1, len(sub) // 60)):
+                        if want[i] != r.compress_loaded_dict(sub[i], level, d):
+                            nb += 1
+                            log(f"  ORACLE != reference DLL, dictionary {dname} level {level} input {4 * i} size {sub[i].size}")
+                dec.LoadDictionary(d)
+                try:
+                    outs = dec.UnwrapBatch(frames, raise_on_error=False)
+                finally:
+                    dec.LoadDictionary(None)
+                for i, (x, a) in enumerate(zip(outs, sub)):
+                    if x != a.tobytes():
+                        nb += 1
+                        if nb <= 3:
+                            log(f"  DECODE FAILURE with dictionary {dname} level {level} input {4 * i} size {a.size}")
+                bad += nb
+                log(f"dictionary {dname} ({len(d)} bytes) level {level}: {nb} mismatches of {len(sub)}")
     # damaged frames: the oracle's answer, error code included (the oracle is held to the reference binary on the same kind of
     # damage by tests/test_reference_pin.py; a sample of this run is checked against it here too)
     mut = []

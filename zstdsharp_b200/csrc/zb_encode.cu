@@ -1534,10 +1534,12 @@ _match_stored:
 // One thread per frame: block `wave` of a frame compressed with a loaded dictionary.  The window bookkeeping of
 // ZSTD_compress_frameChunk (:4690: ZSTD_checkDictValidity, ZSTD_window_enforceMaxDist) runs here, per block, and picks the
 // variant the way ZSTD_matchState_dictMode / ZSTD_selectBlockCompressor do (ZstdCompressInternal.cs:576, ZstdCompress.cs:3398).
-__global__ void __launch_bounds__(32) enc_match_dict_kernel(EncPass p, const uint32_t* __restrict__ workList, uint32_t nWork, uint32_t wave)
+// `shift`: a frame gets 1 << shift consecutive threads, of which the first one works.  Few large frames: one frame per warp (shift 5: every
+// parse has its own instruction stream, nothing waits for a divergent neighbour); many small records: one per thread (shift 0).
+__global__ void __launch_bounds__(128) enc_match_dict_kernel(EncPass p, const uint32_t* __restrict__ workList, uint32_t nWork, uint32_t wave, uint32_t shift)
 {
-    uint32_t const wi = blockIdx.x * 32 + threadIdx.x;
-    if (wi >= nWork) return;
+    uint32_t const gt = blockIdx.x * blockDim.x + threadIdx.x, wi = gt >> shift;
+    if (wi >= nWork || (gt & ((1u << shift) - 1u)) != 0) return;
     uint32_t const item = workList[wi];
     EncItem& it = p.items[item];
     const uint8_t* const src = p.src + it.srcOff;
@@ -2427,7 +2429,12 @@ bool enc_enqueue(EncArena& A, cudaStream_t stream, cudaStream_t copyStream, size
         // lanes per chunk: 16 measured best for ZSTD_fast (8: 49/52 ms, 16: 42/49 ms, 32: 63/72 ms per GiB Silesia-mix / text)
         if (mb) {
             if (w.n[0]) enc_match_group_kernel<16, true><<<(w.n[0] + 2 * kMatchWarps - 1) / (2 * kMatchWarps), 32 * kMatchWarps, 0, stream>>>(p, dw + w.off[0], w.n[0], wave);
-            if (w.n[1]) enc_match_dict_kernel<<<(w.n[1] + 31) / 32, 32, 0, stream>>>(p, dw + w.off[1], w.n[1], wave);
+            if (w.n[1]) {
+                static int const forced = []() { const char* e = getenv("ZSTDB200_DICT_SHIFT"); return e ? atoi(e) : -1; }();      // developer knob
+                uint32_t const shift = forced >= 0 ? (uint32_t)std::min(forced, 5) : (w.n[1] >= 131072 ? 0u : (w.n[1] >= 32768 ? 2u : 5u));
+                uint64_t const threads = (uint64_t)w.n[1] << shift;
+                enc_match_dict_kernel<<<(unsigned)((threads + 127) / 128), 128, 0, stream>>>(p, dw + w.off[1], w.n[1], wave, shift);
+            }
             if (w.n[2]) enc_match_dfast_group_kernel<16, true><<<(w.n[2] + 2 * kMatchWarps - 1) / (2 * kMatchWarps), 32 * kMatchWarps, 0, stream>>>(p, dw + w.off[2], w.n[2], wave);
             if (ev3 && b == 0) ENC_CUDA(cudaEventRecord(ev3[1], stream));
             if (w.n[3]) {
