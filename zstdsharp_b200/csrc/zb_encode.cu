@@ -138,7 +138,8 @@ struct __align__(16) EncItem {
     uint32_t wLow, wDictLimit, loadedDictEnd, dms;   // ms->window.lowLimit / .dictLimit, ms->loadedDictEnd, ms->dictMatchState != NULL: advanced block by block
     uint32_t fseValid;      // prevCBlock->entropy.fse.*_repeatMode == FSE_repeat_valid: 1 LL, 2 OF, 4 ML (only a dictionary makes them valid)
     uint32_t fseValidNext;  // nextCBlock's, confirmed with the block
-    uint32_t _pad[2];
+    uint32_t dBlkMode, dBlkLow, dBlkPrefix;   // the current block's variant (0 none, 1 dictMatchState, 2 extDict; | kDictSerial) and its dictStartIndex / prefixStartIndex (dict_block_mode)
+    uint32_t _pad[3];
 };
 static_assert(sizeof(EncItem) % 16 == 0, "EncItem is copied and indexed as 16-byte units");
 
@@ -1531,9 +1532,211 @@ _match_stored:
     }
 }
 
-// One thread per frame: block `wave` of a frame compressed with a loaded dictionary.  The window bookkeeping of
-// ZSTD_compress_frameChunk (:4690: ZSTD_checkDictValidity, ZSTD_window_enforceMaxDist) runs here, per block, and picks the
-// variant the way ZSTD_matchState_dictMode / ZSTD_selectBlockCompressor do (ZstdCompressInternal.cs:576, ZstdCompress.cs:3398).
+// Window state of block `wave` of a dictionary frame: ZSTD_checkDictValidity (ZstdCompressInternal.cs:697) on the block's end, ZSTD_window_enforceMaxDist
+// (:659) on its start, then the variant ZSTD_matchState_dictMode / ZSTD_selectBlockCompressor pick (:576, ZstdCompress.cs:3398) and its two limits.
+struct DictBlkMode { uint32_t lowLimit, dictLimit, loadedDictEnd, dms, mode /* 0 no dictionary, 1 dictMatchState, 2 extDict */, dictStartIndex, prefixStartIndex; };
+__device__ __forceinline__ DictBlkMode dict_block_mode(const EncItem& it, uint32_t wave)
+{
+    DictBlkMode m;
+    uint32_t const blkStart = wave * kBlockSizeMax, blkSize = min(kBlockSizeMax, it.srcSize - blkStart), maxDist = 1u << it.windowLog;
+    uint32_t const startIdx = it.dPrefix + blkStart, endIdx = startIdx + blkSize;
+    m.lowLimit = it.wLow; m.dictLimit = it.wDictLimit; m.loadedDictEnd = it.loadedDictEnd; m.dms = it.dms;
+    if (endIdx > m.loadedDictEnd + maxDist) { m.loadedDictEnd = 0; m.dms = 0; }
+    if (startIdx > maxDist + m.loadedDictEnd) {
+        uint32_t const newLowLimit = startIdx - maxDist;
+        if (m.lowLimit < newLowLimit) m.lowLimit = newLowLimit;
+        if (m.dictLimit < m.lowLimit) m.dictLimit = m.lowLimit;
+        m.loadedDictEnd = 0; m.dms = 0;
+    }
+    auto lowest = [&](uint32_t lowestValid, uint32_t curr) { return m.loadedDictEnd != 0 ? lowestValid : ((curr - lowestValid > maxDist) ? curr - maxDist : lowestValid); };   // ZSTD_getLowestMatchIndex / ..PrefixIndex (:787, :802)
+    bool const extDict = m.lowLimit < m.dictLimit;
+    uint32_t const extLow = lowest(m.lowLimit, endIdx), extPrefix = m.dictLimit < extLow ? extLow : m.dictLimit;
+    if (extDict && extPrefix != extLow) { m.mode = 2; m.dictStartIndex = extLow; m.prefixStartIndex = extPrefix; }
+    else if (!extDict && m.dms) { m.mode = 1; m.dictStartIndex = 2; m.prefixStartIndex = m.dictLimit; }     // loadedDictEnd != 0 here: ZSTD_getLowestPrefixIndex is dictLimit
+    else { m.mode = 0; m.prefixStartIndex = lowest(m.dictLimit, endIdx); m.dictStartIndex = m.prefixStartIndex; }
+    return m;
+}
+constexpr uint32_t kDictSerial = 8;     // EncItem::dBlkMode bit: this block is left to the serial kernel
+
+// ------------------------------------------------------------------------------------------------------------
+//  Group-per-frame ZSTD_fast parse with a dictionary (ZstdFast.cs:390 dictMatchState, :583 extDict): the same construction as
+//  enc_match_group_kernel, over the classic loop of the dictionary variants.  That loop visits one position per step,
+//  ip += ((ip - anchor) >> 8) + stepSize, until the repcode at ip + 1 or the table candidate at ip matches, so lane l of a group
+//  evaluates the l-th position of the schedule speculatively: it sees the window's earlier positions through __match_any_sync and
+//  older ones through the table, the first event in the reference's order wins and only the writes up to it are committed.
+//  Positions are the reference's indices: index < prefixStartIndex lives in the dictionary content (`dictBase + index`), the rest
+//  in the frame (`base + index`), and a match runs from the first segment into the second as if they were adjacent
+//  (ZSTD_count_2segments, ZstdCompressInternal.cs:283).  Blocks that no longer see the dictionary, and ZSTD_dfast frames, are
+//  handed to the serial kernel (enc_match_dict_kernel) through EncItem::dBlkMode.
+// ------------------------------------------------------------------------------------------------------------
+template <int GS>
+__global__ void __launch_bounds__(32 * kMatchWarps) enc_match_dict_fast_group_kernel(EncPass p, const uint32_t* __restrict__ workList, uint32_t nWork, uint32_t wave, uint32_t forceSerial)
+{
+    constexpr uint32_t FULL = 0xFFFFFFFFu;
+    constexpr int NG = 32 / GS;
+    constexpr uint32_t LOW = GS == 32 ? FULL : ((1u << (GS & 31)) - 1u);
+    uint32_t const lane = threadIdx.x & 31, g = lane / GS, l = lane % GS, gbase = g * GS;
+    uint32_t const gmask = LOW << gbase;
+    uint32_t const wi = (blockIdx.x * kMatchWarps + (threadIdx.x >> 5)) * NG + g;
+    bool active = wi < nWork;
+    uint32_t const item = workList[active ? wi : 0];
+    EncItem& it = p.items[item];
+    DictBlkMode const bm = dict_block_mode(it, wave);
+    bool const serial = forceSerial || bm.mode == 0 || it.strategy != 1;
+    __syncwarp();                                      // every lane has read the window state before lane 0 of its group advances it
+    if (active && l == 0) {
+        it.wLow = bm.lowLimit; it.wDictLimit = bm.dictLimit; it.loadedDictEnd = bm.loadedDictEnd; it.dms = bm.dms;
+        it.dBlkMode = bm.mode | (serial ? kDictSerial : 0u); it.dBlkLow = bm.dictStartIndex; it.dBlkPrefix = bm.prefixStartIndex;
+    }
+    active = active && !serial;
+    bool const isDms = bm.mode == 1;
+    uint32_t const hlog = it.hashLog, mls = it.minMatch, dictHLog = p.dict.hashLog;
+    const uint8_t* const src = p.src + it.srcOff;
+    uint32_t const dP = it.dPrefix;                    // index of src[0]
+    const uint8_t* const base = src - dP; const uint8_t* const dictBase = p.dict.content - 2;
+    uint32_t const prefixStartIndex = bm.prefixStartIndex, dictStartIndex = bm.dictStartIndex;
+    uint32_t* const T = p.tables + it.tableOff; const uint32_t* const DT = p.dict.tables;
+    uint32_t* const oLL = p.seqLL + (size_t)item * kEncSeqCap;
+    uint32_t* const oML = p.seqML + (size_t)item * kEncSeqCap;
+    uint32_t* const oOF = p.seqOF + (size_t)item * kEncSeqCap;
+    int const blkStart = (int)(wave * kBlockSizeMax), blkEnd = active ? blkStart + (int)min(kBlockSizeMax, it.srcSize - (uint32_t)blkStart) : blkStart + 64;
+    int const ilimit = blkEnd - 8;
+    int const stepSize = active ? (int)it.dStep : 1;
+    int ip = blkStart, anchor = blkStart;
+    if (isDms && ((uint32_t)blkStart + dP - prefixStartIndex) + (prefixStartIndex - dictStartIndex) == 0) ip++;      // ip += (dictAndPrefixLength == 0)
+    uint32_t offset_1 = it.rep[0], offset_2 = it.rep[1], nseq = 0, currPrev = 0;
+    bool afterMatch = false;                           // the repcode loop behind a match (:499-520, :670-690) is still open at ip
+    auto gballot = [&](bool pr) -> uint32_t { return (__ballot_sync(FULL, pr) >> gbase) & LOW; };
+    auto ptrOf = [&](uint32_t idx) -> const uint8_t* { return idx < prefixStartIndex ? dictBase + idx : base + idx; };
+    auto rd32x = [&](uint32_t idx) -> uint32_t {       // four bytes at an index, also across the segment boundary
+        if (idx + 4 <= prefixStartIndex || idx >= prefixStartIndex) return rd32(ptrOf(idx));
+        uint32_t v = 0;
+        for (int j = 0; j < 4; j++) v |= (uint32_t)*ptrOf(idx + j) << (8 * j);
+        return v;
+    };
+    // the guard in front of both repcode tests: not inside the last three bytes of the dictionary segment; extDict: inside the window
+    auto repOk = [&](uint32_t repIndex, uint32_t off, uint32_t span) { return ((uint32_t)((prefixStartIndex - 1) - repIndex) >= 3) && (isDms || off <= span); };
+    while (__any_sync(FULL, active)) {
+        // ---- this lane's position: the l-th of the schedule ----
+        int pl, P;
+        {
+            int const s0 = ((ip - anchor) >> 8) + stepSize;
+            bool const simple = !active || (((ip + GS * s0 - anchor) >> 8) == ((ip - anchor) >> 8));
+            if (__all_sync(FULL, simple)) { pl = ip + (int)l * s0; P = ip + GS * s0; }
+            else {
+                P = ip; pl = ip;
+#pragma unroll
+                for (int j = 0; j < GS; j++) { if (j == (int)l) pl = P; P += ((P - anchor) >> 8) + stepSize; }
+            }
+        }
+        bool const vk = active && pl < ilimit;
+        uint32_t const validMask = gballot(vk);
+        // ---- the open repcode loop at ip (same answer in every lane of the group) ----
+        bool r2hit = false; uint32_t repIndex2 = 0;
+        if (active && afterMatch && ip <= ilimit) {
+            uint32_t const current2 = (uint32_t)ip + dP;
+            repIndex2 = current2 - offset_2;
+            r2hit = repOk(repIndex2, offset_2, currPrev - dictStartIndex) && rd32(ptrOf(repIndex2)) == rd32(src + ip);       // `curr` of the last search, as the reference has it (:676)
+        }
+        // ---- probes ----
+        uint64_t const x = vk ? rd64(src + pl) : 0ull;
+        uint32_t const cur4 = (uint32_t)x, next4 = (uint32_t)(x >> 8);
+        uint32_t const curr = (uint32_t)pl + dP;
+        uint32_t const repIndex = curr + 1 - offset_1;
+        bool const repHit = vk && repOk(repIndex, offset_1, curr + 1 - dictStartIndex) && rd32(ptrOf(repIndex)) == next4;
+        uint32_t const h = hash_val(x, hlog, mls);
+        uint32_t const tv = vk ? __ldcg(T + h) : 0u;
+        uint32_t const peers = (__match_any_sync(FULL, vk ? (h | (g << 24)) : (0x80000000u | lane)) >> gbase) & LOW;
+        uint32_t const lower = peers & ((1u << l) - 1u);
+        int const cl = lower ? 31 - __clz((int)lower) : (int)l;
+        uint32_t const cqIdx = __shfl_sync(FULL, curr, gbase + cl);
+        uint32_t const cq4 = __shfl_sync(FULL, cur4, gbase + cl);      // a candidate forwarded from a lower lane of the window: its bytes are in that lane's registers
+        uint32_t cand = lower ? cqIdx : tv;
+        bool hit;
+        if (lower) hit = vk && cq4 == cur4;                            // a position of this block: always inside the prefix
+        else if (isDms) {
+            if (cand <= prefixStartIndex) {                            // nothing usable in the frame's own table: the dictionary's (:441-449)
+                cand = vk ? __ldg(DT + hash_val(x, dictHLog, mls)) : 0u;
+                hit = vk && cand > dictStartIndex && rd32(dictBase + cand) == cur4;
+            } else hit = vk && rd32(base + cand) == cur4;
+        } else hit = vk && cand >= dictStartIndex && rd32(ptrOf(cand)) == cur4;
+        uint32_t key = 0xFFFFFFFFu;                                    // 0: repcode loop at ip; 1 + 2l: repcode at position l + 1; 2 + 2l: table candidate at position l
+        if (hit) key = 2 * l + 2;
+        if (repHit) key = 2 * l + 1;
+        if (r2hit) key = 0;
+        uint32_t const best = __reduce_min_sync(gmask, key);
+        bool const ev = active && best != 0xFFFFFFFFu;
+        int const type = !ev ? -1 : (best == 0 ? 3 : (int)((best - 1) & 1u));       // 0 repcode, 1 table candidate, 3 repcode loop
+        uint32_t const le = (ev && best) ? (best - 1) >> 1 : 0u;
+        if (active && type != 3) afterMatch = false;
+        // ---- table writes of the positions visited up to the event (`hashTable[h] = curr` precedes both tests); the latest position of a bucket wins ----
+        {
+            uint32_t const lastLane = type < 0 ? (uint32_t)GS - 1 : le;
+            uint32_t const peersC = peers & (lastLane >= 31 ? FULL : ((2u << lastLane) - 1u));
+            if (vk && type != 3 && l <= lastLane && ((peersC >> l) >> 1) == 0) T[h] = curr;
+        }
+        if (type == 3 && l == 0) T[hash_val(rd64(src + ip), hlog, mls)] = (uint32_t)ip + dP;
+        // ---- match geometry (group-uniform): position in the frame, index of its source ----
+        int const pe = __shfl_sync(FULL, pl, gbase + le);
+        uint32_t const ce = __shfl_sync(FULL, cand, gbase + le), re = __shfl_sync(FULL, repIndex, gbase + le);
+        int mpos = 0, mlen = 0; uint32_t msrc = 0, offcode = 0;
+        if (type == 3) { mpos = ip; msrc = repIndex2; mlen = 4; uint32_t const t = offset_2; offset_2 = offset_1; offset_1 = t; }
+        else if (type == 0) { mpos = pe + 1; msrc = re; mlen = 4; currPrev = (uint32_t)pe + dP; }
+        else if (type == 1) { mpos = pe; msrc = ce; mlen = 4; currPrev = (uint32_t)pe + dP; offset_2 = offset_1; offset_1 = currPrev - ce; offcode = offset_1 + 2; }
+        // backward extension of table matches (:462-467, :648-653): not below the anchor, not below the start of the source's segment
+        {
+            bool ext = type == 1;
+            uint32_t const lowIdx = msrc < prefixStartIndex ? dictStartIndex : prefixStartIndex;
+            while (__any_sync(FULL, ext)) {
+                int const a = mpos - 1 - (int)l; uint32_t const b = msrc - 1 - l;
+                bool const ok = ext && a >= anchor && msrc >= lowIdx + 1 + l && src[a] == *ptrOf(b);
+                uint32_t const okm = gballot(ok);
+                uint32_t const n = okm == LOW ? (uint32_t)GS : (uint32_t)__ffs((int)~okm) - 1u;
+                if (ext) { mpos -= (int)n; msrc -= n; mlen += (int)n; ext = n == (uint32_t)GS; }
+            }
+        }
+        // forward extension (ZSTD_count_2segments): lane l compares 4 bytes, 4*GS bytes per round; the source is read by index
+        {
+            bool cnt = ev;
+            while (__any_sync(FULL, cnt)) {
+                int const pa = mpos + mlen + 4 * (int)l; uint32_t const ib = msrc + (uint32_t)mlen + 4 * l;
+                int const rem = blkEnd - pa;
+                uint32_t n = 4;
+                if (cnt) {
+                    if (rem >= 4) { uint32_t const diff = rd32(src + pa) ^ rd32x(ib); n = diff ? (uint32_t)(__ffs((int)diff) - 1) >> 3 : 4u; }
+                    else { n = 0; for (int j = 0; j < rem; j++) { if (src[pa + j] == *ptrOf(ib + j)) n++; else break; } }
+                }
+                uint32_t const notFull = gballot(cnt && n != 4);
+                uint32_t const f = notFull ? (uint32_t)__ffs((int)notFull) - 1u : 0u;
+                uint32_t const nf = __shfl_sync(FULL, n, gbase + f);
+                if (cnt) { if (notFull) { mlen += 4 * (int)f + (int)nf; cnt = false; } else mlen += 4 * GS; }
+            }
+        }
+        // ---- sequence, post-match inserts (:490-498, :662-669), next state ----
+        if (ev) {
+            ZB_ASSERT(nseq < kEncSeqCap && mpos >= anchor && msrc < (uint32_t)mpos + dP && mpos + mlen <= blkEnd);
+            if (l == 0) { oLL[nseq] = (uint32_t)(mpos - anchor); oOF[nseq] = offcode + 1; oML[nseq] = (uint32_t)mlen - 3; }
+            nseq++;
+            int const mend = mpos + mlen;
+            if (l == 0 && type != 3 && mend <= ilimit) {
+                int const c2 = (int)(currPrev - dP) + 2;
+                T[hash_val(rd64(src + c2), hlog, mls)] = currPrev + 2;
+                T[hash_val(rd64(src + mend - 2), hlog, mls)] = (uint32_t)(mend - 2) + dP;
+            }
+            ip = mend; anchor = mend;
+            afterMatch = mend <= ilimit;               // the repcode loop only opens `if (ip <= ilimit)`
+        } else if (active) {
+            if (validMask != LOW) active = false;      // the loop condition failed inside the window
+            else ip = P;
+        }
+        __syncwarp();
+    }
+    if (wi < nWork && !serial && l == 0) { it.nbSeq = nseq; it.lastLL = (uint32_t)(blkEnd - anchor); it.repNext[0] = offset_1; it.repNext[1] = offset_2; }
+}
+
+// One thread per frame: block `wave` of a frame compressed with a loaded dictionary, for the blocks enc_match_dict_fast_group_kernel
+// (which runs first and does the window bookkeeping of the block: dict_block_mode) leaves to it: ZSTD_dfast frames and blocks that no
+// longer see the dictionary.
 // `shift`: a frame gets 1 << shift consecutive threads, of which the first one works.  Few large frames: one frame per warp (shift 5: every
 // parse has its own instruction stream, nothing waits for a divergent neighbour); many small records: one per thread (shift 0).
 __global__ void __launch_bounds__(128) enc_match_dict_kernel(EncPass p, const uint32_t* __restrict__ workList, uint32_t nWork, uint32_t wave, uint32_t shift)
@@ -1542,23 +1745,13 @@ __global__ void __launch_bounds__(128) enc_match_dict_kernel(EncPass p, const ui
     if (wi >= nWork || (gt & ((1u << shift) - 1u)) != 0) return;
     uint32_t const item = workList[wi];
     EncItem& it = p.items[item];
+    if (!(it.dBlkMode & kDictSerial)) return;
+    uint32_t const mode = it.dBlkMode & 3u;
     const uint8_t* const src = p.src + it.srcOff;
     uint32_t const blkStart = wave * kBlockSizeMax, blkSize = min(kBlockSizeMax, it.srcSize - blkStart);
     uint32_t const srcIdx0 = it.dPrefix;                             // index of src[0]: 2 + dictionary content length (2 when nothing was attached)
     const uint8_t* const base = src - srcIdx0;
-    uint32_t const maxDist = 1u << it.windowLog;
-    uint32_t lowLimit = it.wLow, dictLimit = it.wDictLimit, loadedDictEnd = it.loadedDictEnd, dms = it.dms;
-    {   // ZSTD_checkDictValidity (ZstdCompressInternal.cs:697) on the block's end, ZSTD_window_enforceMaxDist (:659) on its start
-        uint32_t const endIdx = srcIdx0 + blkStart + blkSize, startIdx = srcIdx0 + blkStart;
-        if (endIdx > loadedDictEnd + maxDist) { loadedDictEnd = 0; dms = 0; }
-        if (startIdx > maxDist + loadedDictEnd) {
-            uint32_t const newLowLimit = startIdx - maxDist;
-            if (lowLimit < newLowLimit) lowLimit = newLowLimit;
-            if (dictLimit < lowLimit) dictLimit = lowLimit;
-            loadedDictEnd = 0; dms = 0;
-        }
-        it.wLow = lowLimit; it.wDictLimit = dictLimit; it.loadedDictEnd = loadedDictEnd; it.dms = dms;
-    }
+    uint32_t const maxDist = 1u << it.windowLog, dictLimit = it.wDictLimit, loadedDictEnd = it.loadedDictEnd;
     SeqWriter sw{p.seqLL + (size_t)item * kEncSeqCap, p.seqML + (size_t)item * kEncSeqCap, p.seqOF + (size_t)item * kEncSeqCap, 0};
     uint32_t rep[2] = {it.rep[0], it.rep[1]};
     uint32_t* const T = p.tables + it.tableOff;
@@ -1566,20 +1759,14 @@ __global__ void __launch_bounds__(128) enc_match_dict_kernel(EncPass p, const ui
     bool const fast = it.strategy == 1;
     DictBlk b;
     b.base = base; b.dictBase = p.dict.content - 2; b.istart = src + blkStart; b.iend = src + blkStart + blkSize; b.mls = it.minMatch; b.dStep = it.dStep;
-    uint32_t const endIndex = srcIdx0 + blkStart + blkSize;
-    auto lowest = [&](uint32_t lowestValid, uint32_t curr) { return loadedDictEnd != 0 ? lowestValid : ((curr - lowestValid > maxDist) ? curr - maxDist : lowestValid); };   // ZSTD_getLowestMatchIndex / ..PrefixIndex (:787, :802)
+    b.dictStartIndex = it.dBlkLow; b.prefixStartIndex = it.dBlkPrefix;
     uint32_t lastLL;
-    bool const extDict = lowLimit < dictLimit;
-    uint32_t const extLow = lowest(lowLimit, endIndex), extPrefix = dictLimit < extLow ? extLow : dictLimit;
-    if (extDict && extPrefix != extLow) {
-        b.dictStartIndex = extLow; b.prefixStartIndex = extPrefix;
-        lastLL = fast ? dict_fast_ext(T, it.hashLog, b, rep, sw) : dict_dfast_ext(T, it.hashLog, TS, it.chainLog, b, rep, sw);
-    } else if (!extDict && dms) {
-        b.dictStartIndex = 2; b.prefixStartIndex = fast ? dictLimit : lowest(dictLimit, endIndex);
+    if (mode == 2) lastLL = fast ? dict_fast_ext(T, it.hashLog, b, rep, sw) : dict_dfast_ext(T, it.hashLog, TS, it.chainLog, b, rep, sw);
+    else if (mode == 1)
         lastLL = fast ? dict_fast_dms(T, it.hashLog, p.dict.tables, p.dict.hashLog, b, rep, sw)
                       : dict_dfast_dms(T, it.hashLog, TS, it.chainLog, p.dict.tables, p.dict.hashLog, p.dict.tables + ((size_t)1 << p.dict.hashLog), p.dict.chainLog, b, rep, sw);
-    } else {
-        b.prefixStartIndex = lowest(dictLimit, endIndex); b.dictStartIndex = b.prefixStartIndex;
+    else {
+        auto lowest = [&](uint32_t lowestValid, uint32_t curr) { return loadedDictEnd != 0 ? lowestValid : ((curr - lowestValid > maxDist) ? curr - maxDist : lowestValid); };
         uint32_t const curr0 = srcIdx0 + blkStart + ((srcIdx0 + blkStart) == b.prefixStartIndex);
         uint32_t const maxRep = curr0 - lowest(dictLimit, curr0);
         lastLL = fast ? nodict_fast(T, it.hashLog, b, it.stepSize, maxRep, rep, sw) : nodict_dfast(T, it.hashLog, TS, it.chainLog, b, maxRep, rep, sw);
@@ -2430,6 +2617,8 @@ bool enc_enqueue(EncArena& A, cudaStream_t stream, cudaStream_t copyStream, size
         if (mb) {
             if (w.n[0]) enc_match_group_kernel<16, true><<<(w.n[0] + 2 * kMatchWarps - 1) / (2 * kMatchWarps), 32 * kMatchWarps, 0, stream>>>(p, dw + w.off[0], w.n[0], wave);
             if (w.n[1]) {
+                static int const forceSerial = []() { const char* e = getenv("ZSTDB200_DICT_SERIAL"); return e ? atoi(e) : 0; }();   // developer knob: everything through the serial kernel
+                enc_match_dict_fast_group_kernel<16><<<(w.n[1] + 2 * kMatchWarps - 1) / (2 * kMatchWarps), 32 * kMatchWarps, 0, stream>>>(p, dw + w.off[1], w.n[1], wave, (uint32_t)forceSerial);
                 static int const forced = []() { const char* e = getenv("ZSTDB200_DICT_SHIFT"); return e ? atoi(e) : -1; }();      // developer knob
                 uint32_t const shift = forced >= 0 ? (uint32_t)std::min(forced, 5) : (w.n[1] >= 131072 ? 0u : (w.n[1] >= 32768 ? 2u : 5u));
                 uint64_t const threads = (uint64_t)w.n[1] << shift;
@@ -2452,7 +2641,7 @@ bool enc_enqueue(EncArena& A, cudaStream_t stream, cudaStream_t copyStream, size
             enc_fse_chain_kernel<false><<<(unsigned)(3 * m + 31) / 32, 32, 32 * kChainTabStride, stream>>>(p, dw, (uint32_t)m);
             enc_entropy_kernel<false, 1><<<(unsigned)m, kEntThreads, 0, stream>>>(p, dw, 0u);
         }
-        *launches += (w.n[0] ? 1 : 0) + (w.n[1] ? 1 : 0) + (w.n[2] ? 1 : 0) + ((mb ? w.n[3] : 1) ? 3 : 0);
+        *launches += (w.n[0] ? 1 : 0) + (w.n[1] ? 2 : 0) + (w.n[2] ? 1 : 0) + ((mb ? w.n[3] : 1) ? 3 : 0);
     }
     if (ev3) ENC_CUDA(cudaEventRecord(ev3[2], stream));
     ENC_CUDA(cudaGetLastError());
@@ -2478,6 +2667,8 @@ void enc_set_overlap_mode(bool overlap)
     cudaFuncSetAttribute(enc_match_group_kernel<16, true>, A, x);
     cudaFuncSetAttribute(enc_match_dfast_group_kernel<16, false>, A, x);
     cudaFuncSetAttribute(enc_match_dfast_group_kernel<16, true>, A, x);
+    cudaFuncSetAttribute(enc_match_dict_fast_group_kernel<16>, A, x);
+    cudaFuncSetAttribute(enc_match_dict_kernel, A, x);
     cudaFuncSetAttribute(enc_entropy_kernel<false, 0>, A, x);
     cudaFuncSetAttribute(enc_entropy_kernel<false, 1>, A, x);
     cudaFuncSetAttribute(enc_entropy_kernel<true, 0>, A, x);
