@@ -1556,7 +1556,8 @@ __device__ __forceinline__ DictBlkMode dict_block_mode(const EncItem& it, uint32
     else { m.mode = 0; m.prefixStartIndex = lowest(m.dictLimit, endIdx); m.dictStartIndex = m.prefixStartIndex; }
     return m;
 }
-constexpr uint32_t kDictSerial = 8;     // EncItem::dBlkMode bit: this block is left to the serial kernel
+constexpr uint32_t kDictSerial = 8;     // EncItem::dBlkMode bit: this block is left to a later kernel (ZSTD_dfast group kernel, serial kernel)
+constexpr uint32_t kDictForced = 16;    // developer knob ZSTDB200_DICT_SERIAL: the serial kernel takes everything
 
 // ------------------------------------------------------------------------------------------------------------
 //  Group-per-frame ZSTD_fast parse with a dictionary (ZstdFast.cs:390 dictMatchState, :583 extDict): the same construction as
@@ -1566,8 +1567,9 @@ constexpr uint32_t kDictSerial = 8;     // EncItem::dBlkMode bit: this block is 
 //  older ones through the table, the first event in the reference's order wins and only the writes up to it are committed.
 //  Positions are the reference's indices: index < prefixStartIndex lives in the dictionary content (`dictBase + index`), the rest
 //  in the frame (`base + index`), and a match runs from the first segment into the second as if they were adjacent
-//  (ZSTD_count_2segments, ZstdCompressInternal.cs:283).  Blocks that no longer see the dictionary, and ZSTD_dfast frames, are
-//  handed to the serial kernel (enc_match_dict_kernel) through EncItem::dBlkMode.
+//  (ZSTD_count_2segments, ZstdCompressInternal.cs:283).  This kernel also does the window bookkeeping of the block for every dictionary
+//  frame of the pass; ZSTD_dfast frames go on to enc_match_dict_dfast_group_kernel, blocks that no longer see the dictionary to the
+//  serial kernel (enc_match_dict_kernel), through EncItem::dBlkMode.
 // ------------------------------------------------------------------------------------------------------------
 template <int GS>
 __global__ void __launch_bounds__(32 * kMatchWarps) enc_match_dict_fast_group_kernel(EncPass p, const uint32_t* __restrict__ workList, uint32_t nWork, uint32_t wave, uint32_t forceSerial)
@@ -1586,7 +1588,7 @@ __global__ void __launch_bounds__(32 * kMatchWarps) enc_match_dict_fast_group_ke
     __syncwarp();                                      // every lane has read the window state before lane 0 of its group advances it
     if (active && l == 0) {
         it.wLow = bm.lowLimit; it.wDictLimit = bm.dictLimit; it.loadedDictEnd = bm.loadedDictEnd; it.dms = bm.dms;
-        it.dBlkMode = bm.mode | (serial ? kDictSerial : 0u); it.dBlkLow = bm.dictStartIndex; it.dBlkPrefix = bm.prefixStartIndex;
+        it.dBlkMode = bm.mode | (serial ? kDictSerial : 0u) | (forceSerial ? kDictForced : 0u); it.dBlkLow = bm.dictStartIndex; it.dBlkPrefix = bm.prefixStartIndex;
     }
     active = active && !serial;
     bool const isDms = bm.mode == 1;
@@ -1732,6 +1734,200 @@ __global__ void __launch_bounds__(32 * kMatchWarps) enc_match_dict_fast_group_ke
         __syncwarp();
     }
     if (wi < nWork && !serial && l == 0) { it.nbSeq = nseq; it.lastLL = (uint32_t)(blkEnd - anchor); it.repNext[0] = offset_1; it.repNext[1] = offset_2; }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+//  Group-per-frame ZSTD_dfast parse with a dictionary (ZstdDoubleFast.cs:250 dictMatchState, :590 extDict): as above, with the two
+//  tables.  Order of the tests at a position: repcode at ip + 1, long table (8 bytes) at ip, short table (4 bytes) at ip -- and a short
+//  hit first looks the long table up at ip + 1 (`_search_next_long`), which only the winning position does, after the window's
+//  writes up to it have been committed.
+// ------------------------------------------------------------------------------------------------------------
+template <int GS>
+__global__ void __launch_bounds__(32 * kMatchWarps) enc_match_dict_dfast_group_kernel(EncPass p, const uint32_t* __restrict__ workList, uint32_t nWork, uint32_t wave)
+{
+    constexpr uint32_t FULL = 0xFFFFFFFFu;
+    constexpr int NG = 32 / GS;
+    constexpr uint32_t LOW = GS == 32 ? FULL : ((1u << (GS & 31)) - 1u);
+    uint32_t const lane = threadIdx.x & 31, g = lane / GS, l = lane % GS, gbase = g * GS;
+    uint32_t const gmask = LOW << gbase;
+    uint32_t const wi = (blockIdx.x * kMatchWarps + (threadIdx.x >> 5)) * NG + g;
+    bool active = wi < nWork;
+    uint32_t const item = workList[active ? wi : 0];
+    EncItem& it = p.items[item];
+    // the window bookkeeping of the block was done by enc_match_dict_fast_group_kernel; this kernel takes the ZSTD_dfast blocks that still see the dictionary
+    uint32_t const mode = it.dBlkMode & 3u;
+    bool const mine = active && it.strategy == 2 && mode != 0 && (it.dBlkMode & kDictSerial) && !(it.dBlkMode & kDictForced);
+    active = mine;
+    __syncwarp();
+    if (mine && l == 0) it.dBlkMode &= ~kDictSerial;                 // taken here: the serial kernel skips it
+    bool const isDms = mode == 1;
+    uint32_t const hBitsL = it.hashLog, hBitsS = it.chainLog, mls = it.minMatch, dictHBitsL = p.dict.hashLog, dictHBitsS = p.dict.chainLog;
+    const uint8_t* const src = p.src + it.srcOff;
+    uint32_t const dP = it.dPrefix;
+    const uint8_t* const base = src - dP; const uint8_t* const dictBase = p.dict.content - 2;
+    uint32_t const prefixStartIndex = it.dBlkPrefix, dictStartIndex = it.dBlkLow;
+    uint32_t* const TL = p.tables + it.tableOff; uint32_t* const TS = TL + ((size_t)1 << hBitsL);
+    const uint32_t* const DTL = p.dict.tables; const uint32_t* const DTS = DTL + ((size_t)1 << dictHBitsL);
+    uint32_t* const oLL = p.seqLL + (size_t)item * kEncSeqCap;
+    uint32_t* const oML = p.seqML + (size_t)item * kEncSeqCap;
+    uint32_t* const oOF = p.seqOF + (size_t)item * kEncSeqCap;
+    int const blkStart = (int)(wave * kBlockSizeMax), blkEnd = active ? blkStart + (int)min(kBlockSizeMax, it.srcSize - (uint32_t)blkStart) : blkStart + 64;
+    int const ilimit = blkEnd - 8;
+    int ip = blkStart, anchor = blkStart;
+    if (isDms && ((uint32_t)blkStart + dP - prefixStartIndex) + (prefixStartIndex - dictStartIndex) == 0) ip++;
+    uint32_t offset_1 = it.rep[0], offset_2 = it.rep[1], nseq = 0, currPrev = 0;
+    bool afterMatch = false;
+    auto gballot = [&](bool pr) -> uint32_t { return (__ballot_sync(FULL, pr) >> gbase) & LOW; };
+    auto ptrOf = [&](uint32_t idx) -> const uint8_t* { return idx < prefixStartIndex ? dictBase + idx : base + idx; };
+    auto rd32x = [&](uint32_t idx) -> uint32_t {
+        if (idx + 4 <= prefixStartIndex || idx >= prefixStartIndex) return rd32(ptrOf(idx));
+        uint32_t v = 0;
+        for (int j = 0; j < 4; j++) v |= (uint32_t)*ptrOf(idx + j) << (8 * j);
+        return v;
+    };
+    auto repOk = [&](uint32_t repIndex, uint32_t off, uint32_t span) { return ((uint32_t)((prefixStartIndex - 1) - repIndex) >= 3) && (isDms || off <= span); };
+    auto hashL = [&](uint64_t v, uint32_t bits) { return (uint32_t)((v * 0xCF1BBCDCB7A56463ull) >> (64 - bits)); };
+    // a long-table candidate for the 8 bytes v: (dms) outside the frame's own range the dictionary's table answers (:296-330, :367-399)
+    auto longHit = [&](uint32_t& cand, uint64_t v) -> bool {
+        if (isDms) {
+            if (cand > prefixStartIndex) return rd64(base + cand) == v;
+            cand = __ldg(DTL + hashL(v, dictHBitsL));
+            return cand > dictStartIndex && rd64(dictBase + cand) == v;
+        }
+        return cand > dictStartIndex && rd64(ptrOf(cand)) == v;
+    };
+    while (__any_sync(FULL, active)) {
+        int pl, P;
+        {
+            int const s0 = ((ip - anchor) >> 8) + 1;
+            bool const simple = !active || (((ip + GS * s0 - anchor) >> 8) == ((ip - anchor) >> 8));
+            if (__all_sync(FULL, simple)) { pl = ip + (int)l * s0; P = ip + GS * s0; }
+            else {
+                P = ip; pl = ip;
+#pragma unroll
+                for (int j = 0; j < GS; j++) { if (j == (int)l) pl = P; P += ((P - anchor) >> 8) + 1; }
+            }
+        }
+        bool const vk = active && pl < ilimit;
+        uint32_t const validMask = gballot(vk);
+        bool r2hit = false; uint32_t repIndex2 = 0;
+        if (active && afterMatch && ip <= ilimit) {
+            uint32_t const current2 = (uint32_t)ip + dP;
+            repIndex2 = current2 - offset_2;
+            r2hit = repOk(repIndex2, offset_2, current2 - dictStartIndex) && rd32(ptrOf(repIndex2)) == rd32(src + ip);      // current2 here (:739), unlike ZSTD_fast
+        }
+        // ---- probes: both tables, each with the window's earlier positions forwarded ----
+        uint64_t const x = vk ? rd64(src + pl) : 0ull;
+        uint32_t const cur4 = (uint32_t)x, next4 = (uint32_t)(x >> 8);
+        uint32_t const curr = (uint32_t)pl + dP;
+        uint32_t const repIndex = curr + 1 - offset_1;
+        bool const repHit = vk && repOk(repIndex, offset_1, curr + 1 - dictStartIndex) && rd32(ptrOf(repIndex)) == next4;
+        uint32_t const hL = hashL(x, hBitsL), hS = hash_val(x, hBitsS, mls);
+        uint32_t const tL = vk ? __ldcg(TL + hL) : 0u, tS = vk ? __ldcg(TS + hS) : 0u;
+        uint32_t const peersL = (__match_any_sync(FULL, vk ? (hL | (g << 24)) : (0x80000000u | lane)) >> gbase) & LOW;
+        uint32_t const peersS = (__match_any_sync(FULL, vk ? (hS | (g << 24)) : (0x80000000u | lane)) >> gbase) & LOW;
+        uint32_t const lowerL = peersL & ((1u << l) - 1u), lowerS = peersS & ((1u << l) - 1u);
+        int const clL = lowerL ? 31 - __clz((int)lowerL) : (int)l, clS = lowerS ? 31 - __clz((int)lowerS) : (int)l;
+        uint32_t const fL = __shfl_sync(FULL, curr, gbase + clL), fS = __shfl_sync(FULL, curr, gbase + clS);
+        uint32_t const fxLo = __shfl_sync(FULL, cur4, gbase + clL), fxHi = __shfl_sync(FULL, (uint32_t)(x >> 32), gbase + clL);
+        uint32_t const fS4 = __shfl_sync(FULL, cur4, gbase + clS);
+        uint32_t candL = lowerL ? fL : tL, candS = lowerS ? fS : tS;
+        bool hitL, hitS;
+        if (lowerL) hitL = vk && fxLo == cur4 && fxHi == (uint32_t)(x >> 32);
+        else hitL = vk && longHit(candL, x);
+        if (lowerS) hitS = vk && fS4 == cur4;
+        else if (isDms) {
+            if (candS > prefixStartIndex) hitS = vk && rd32(base + candS) == cur4;
+            else { candS = vk ? __ldg(DTS + hash_val(x, dictHBitsS, mls)) : 0u; hitS = vk && candS > dictStartIndex && rd32(dictBase + candS) == cur4; }
+        } else hitS = vk && candS > dictStartIndex && rd32(ptrOf(candS)) == cur4;
+        uint32_t key = 0xFFFFFFFFu;                                    // 0: repcode loop; 1 + 3l repcode at l + 1; 2 + 3l long at l; 3 + 3l short at l
+        if (hitS) key = 3 * l + 3;
+        if (hitL) key = 3 * l + 2;
+        if (repHit) key = 3 * l + 1;
+        if (r2hit) key = 0;
+        uint32_t const best = __reduce_min_sync(gmask, key);
+        bool const ev = active && best != 0xFFFFFFFFu;
+        int type = !ev ? -1 : (best == 0 ? 3 : (int)((best - 1) % 3));   // 0 repcode, 1 long, 2 short, 3 repcode loop
+        uint32_t const le = (ev && best) ? (best - 1) / 3 : 0u;
+        if (active && type != 3) afterMatch = false;
+        {
+            uint32_t const lastLane = type < 0 ? (uint32_t)GS - 1 : le;
+            uint32_t const upTo = lastLane >= 31 ? FULL : ((2u << lastLane) - 1u);
+            if (vk && type != 3 && l <= lastLane) {
+                if ((((peersL & upTo) >> l) >> 1) == 0) TL[hL] = curr;
+                if ((((peersS & upTo) >> l) >> 1) == 0) TS[hS] = curr;
+            }
+        }
+        if (type == 3 && l == 0) { uint64_t const xi = rd64(src + ip); TS[hash_val(xi, hBitsS, mls)] = (uint32_t)ip + dP; TL[hashL(xi, hBitsL)] = (uint32_t)ip + dP; }
+        __syncwarp();
+        int const pe = __shfl_sync(FULL, pl, gbase + le);
+        uint32_t const cLe = __shfl_sync(FULL, candL, gbase + le), cSe = __shfl_sync(FULL, candS, gbase + le), re = __shfl_sync(FULL, repIndex, gbase + le);
+        int mpos = 0, mlen = 0; uint32_t msrc = 0, offcode = 0;
+        bool back = false;
+        if (type == 3) { mpos = ip; msrc = repIndex2; mlen = 4; uint32_t const t = offset_2; offset_2 = offset_1; offset_1 = t; }
+        else if (type == 0) { mpos = pe + 1; msrc = re; mlen = 4; currPrev = (uint32_t)pe + dP; }
+        else if (type == 1) { mpos = pe; msrc = cLe; mlen = 8; currPrev = (uint32_t)pe + dP; back = true; }
+        else if (type == 2) {
+            // _search_next_long: the long table at ip + 1, read after the writes of the positions up to ip, then written (:340-399, :642-660)
+            currPrev = (uint32_t)pe + dP;
+            uint64_t const x1 = rd64(src + pe + 1);
+            uint32_t const h3 = hashL(x1, hBitsL);
+            uint32_t m3 = __ldcg(TL + h3);
+            if (l == 0) TL[h3] = currPrev + 1;
+            if (longHit(m3, x1)) { mpos = pe + 1; msrc = m3; mlen = 8; }
+            else { mpos = pe; msrc = cSe; mlen = 4; }
+            back = true;
+        }
+        if (back) { offset_2 = offset_1; offset_1 = ((uint32_t)mpos + dP) - msrc; offcode = offset_1 + 2; }
+        {
+            bool ext = back;
+            uint32_t const lowIdx = msrc < prefixStartIndex ? dictStartIndex : prefixStartIndex;
+            while (__any_sync(FULL, ext)) {
+                int const a = mpos - 1 - (int)l; uint32_t const b = msrc - 1 - l;
+                bool const ok = ext && a >= anchor && msrc >= lowIdx + 1 + l && src[a] == *ptrOf(b);
+                uint32_t const okm = gballot(ok);
+                uint32_t const n = okm == LOW ? (uint32_t)GS : (uint32_t)__ffs((int)~okm) - 1u;
+                if (ext) { mpos -= (int)n; msrc -= n; mlen += (int)n; ext = n == (uint32_t)GS; }
+            }
+        }
+        {
+            bool cnt = ev;
+            while (__any_sync(FULL, cnt)) {
+                int const pa = mpos + mlen + 4 * (int)l; uint32_t const ib = msrc + (uint32_t)mlen + 4 * l;
+                int const rem = blkEnd - pa;
+                uint32_t n = 4;
+                if (cnt) {
+                    if (rem >= 4) { uint32_t const diff = rd32(src + pa) ^ rd32x(ib); n = diff ? (uint32_t)(__ffs((int)diff) - 1) >> 3 : 4u; }
+                    else { n = 0; for (int j = 0; j < rem; j++) { if (src[pa + j] == *ptrOf(ib + j)) n++; else break; } }
+                }
+                uint32_t const notFull = gballot(cnt && n != 4);
+                uint32_t const f = notFull ? (uint32_t)__ffs((int)notFull) - 1u : 0u;
+                uint32_t const nf = __shfl_sync(FULL, n, gbase + f);
+                if (cnt) { if (notFull) { mlen += 4 * (int)f + (int)nf; cnt = false; } else mlen += 4 * GS; }
+            }
+        }
+        if (ev) {
+            ZB_ASSERT(nseq < kEncSeqCap && mpos >= anchor && msrc < (uint32_t)mpos + dP && mpos + mlen <= blkEnd);
+            if (l == 0) { oLL[nseq] = (uint32_t)(mpos - anchor); oOF[nseq] = offcode + 1; oML[nseq] = (uint32_t)mlen - 3; }
+            nseq++;
+            int const mend = mpos + mlen;
+            if (l == 0 && type != 3 && mend <= ilimit) {
+                int const c2 = (int)(currPrev - dP) + 2;
+                uint64_t const xa = rd64(src + c2), xb = rd64(src + mend - 2), xc = rd64(src + mend - 1);
+                TL[hashL(xa, hBitsL)] = currPrev + 2;
+                TL[hashL(xb, hBitsL)] = (uint32_t)(mend - 2) + dP;
+                TS[hash_val(xa, hBitsS, mls)] = currPrev + 2;
+                TS[hash_val(xc, hBitsS, mls)] = (uint32_t)(mend - 1) + dP;
+            }
+            ip = mend; anchor = mend;
+            afterMatch = mend <= ilimit;
+        } else if (active) {
+            if (validMask != LOW) active = false;
+            else ip = P;
+        }
+        __syncwarp();
+    }
+    if (mine && l == 0) { it.nbSeq = nseq; it.lastLL = (uint32_t)(blkEnd - anchor); it.repNext[0] = offset_1; it.repNext[1] = offset_2; }
 }
 
 // One thread per frame: block `wave` of a frame compressed with a loaded dictionary, for the blocks enc_match_dict_fast_group_kernel
@@ -2619,6 +2815,7 @@ bool enc_enqueue(EncArena& A, cudaStream_t stream, cudaStream_t copyStream, size
             if (w.n[1]) {
                 static int const forceSerial = []() { const char* e = getenv("ZSTDB200_DICT_SERIAL"); return e ? atoi(e) : 0; }();   // developer knob: everything through the serial kernel
                 enc_match_dict_fast_group_kernel<16><<<(w.n[1] + 2 * kMatchWarps - 1) / (2 * kMatchWarps), 32 * kMatchWarps, 0, stream>>>(p, dw + w.off[1], w.n[1], wave, (uint32_t)forceSerial);
+                enc_match_dict_dfast_group_kernel<16><<<(w.n[1] + 2 * kMatchWarps - 1) / (2 * kMatchWarps), 32 * kMatchWarps, 0, stream>>>(p, dw + w.off[1], w.n[1], wave);
                 static int const forced = []() { const char* e = getenv("ZSTDB200_DICT_SHIFT"); return e ? atoi(e) : -1; }();      // developer knob
                 uint32_t const shift = forced >= 0 ? (uint32_t)std::min(forced, 5) : (w.n[1] >= 131072 ? 0u : (w.n[1] >= 32768 ? 2u : 5u));
                 uint64_t const threads = (uint64_t)w.n[1] << shift;
@@ -2641,7 +2838,7 @@ bool enc_enqueue(EncArena& A, cudaStream_t stream, cudaStream_t copyStream, size
             enc_fse_chain_kernel<false><<<(unsigned)(3 * m + 31) / 32, 32, 32 * kChainTabStride, stream>>>(p, dw, (uint32_t)m);
             enc_entropy_kernel<false, 1><<<(unsigned)m, kEntThreads, 0, stream>>>(p, dw, 0u);
         }
-        *launches += (w.n[0] ? 1 : 0) + (w.n[1] ? 2 : 0) + (w.n[2] ? 1 : 0) + ((mb ? w.n[3] : 1) ? 3 : 0);
+        *launches += (w.n[0] ? 1 : 0) + (w.n[1] ? 3 : 0) + (w.n[2] ? 1 : 0) + ((mb ? w.n[3] : 1) ? 3 : 0);
     }
     if (ev3) ENC_CUDA(cudaEventRecord(ev3[2], stream));
     ENC_CUDA(cudaGetLastError());
@@ -2668,6 +2865,7 @@ void enc_set_overlap_mode(bool overlap)
     cudaFuncSetAttribute(enc_match_dfast_group_kernel<16, false>, A, x);
     cudaFuncSetAttribute(enc_match_dfast_group_kernel<16, true>, A, x);
     cudaFuncSetAttribute(enc_match_dict_fast_group_kernel<16>, A, x);
+    cudaFuncSetAttribute(enc_match_dict_dfast_group_kernel<16>, A, x);
     cudaFuncSetAttribute(enc_match_dict_kernel, A, x);
     cudaFuncSetAttribute(enc_entropy_kernel<false, 0>, A, x);
     cudaFuncSetAttribute(enc_entropy_kernel<false, 1>, A, x);
