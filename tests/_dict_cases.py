@@ -47,4 +47,10 @@ def compress_payloads(seed=5, n_random=24):
         off = int(rng.integers(0, srcsel.size - n - 1))
         out.append(np.ascontiguousarray(srcsel[off:off + n]))
     out.append(np.ascontiguousarray(text[2_010_000:2_040_000]))              # inside raw_50k: matches reach deep into the dictionary
+    # inputs that repeat their FIRST bytes: with an attached dictionary a candidate at the first position of the input counts as an empty
+    # cell (`matchIndex <= prefixStartIndex`, ZstdFast.cs:441) -- the soak found the group kernels matching against it (seed 991177)
+    out.append(np.resize(text[5000:5037], 4095).copy())
+    out.append(np.resize(np.arange(7, dtype=np.uint8), 3000).copy())
+    out.append(np.resize(sil[100:164], 12000).copy())
+    out.append(np.resize(text[7000:7300], 40000).copy())
     return out

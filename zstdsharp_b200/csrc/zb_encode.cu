@@ -1655,7 +1655,9 @@ __global__ void __launch_bounds__(32 * kMatchWarps) enc_match_dict_fast_group_ke
         uint32_t const cq4 = __shfl_sync(FULL, cur4, gbase + cl);      // a candidate forwarded from a lower lane of the window: its bytes are in that lane's registers
         uint32_t cand = lower ? cqIdx : tv;
         bool hit;
-        if (lower) hit = vk && cq4 == cur4;                            // a position of this block: always inside the prefix
+        // a forwarded candidate is a position of this block, inside the prefix -- but dictMatchState treats the prefix's FIRST position like an
+        // empty cell (`matchIndex <= prefixStartIndex`, :441) and asks the dictionary instead (found by the soak: inputs that repeat their first bytes)
+        if (lower && !(isDms && cand <= prefixStartIndex)) hit = vk && cq4 == cur4;
         else if (isDms) {
             if (cand <= prefixStartIndex) {                            // nothing usable in the frame's own table: the dictionary's (:441-449)
                 cand = vk ? __ldg(DT + hash_val(x, dictHLog, mls)) : 0u;
@@ -1833,9 +1835,10 @@ __global__ void __launch_bounds__(32 * kMatchWarps) enc_match_dict_dfast_group_k
         uint32_t const fS4 = __shfl_sync(FULL, cur4, gbase + clS);
         uint32_t candL = lowerL ? fL : tL, candS = lowerS ? fS : tS;
         bool hitL, hitS;
-        if (lowerL) hitL = vk && fxLo == cur4 && fxHi == (uint32_t)(x >> 32);
+        // (dictMatchState: a candidate at the prefix's first position counts as an empty cell, `matchIndex > prefixLowestIndex` :296, :333)
+        if (lowerL && !(isDms && candL <= prefixStartIndex)) hitL = vk && fxLo == cur4 && fxHi == (uint32_t)(x >> 32);
         else hitL = vk && longHit(candL, x);
-        if (lowerS) hitS = vk && fS4 == cur4;
+        if (lowerS && !(isDms && candS <= prefixStartIndex)) hitS = vk && fS4 == cur4;
         else if (isDms) {
             if (candS > prefixStartIndex) hitS = vk && rd32(base + candS) == cur4;
             else { candS = vk ? __ldg(DTS + hash_val(x, dictHBitsS, mls)) : 0u; hitS = vk && candS > dictStartIndex && rd32(dictBase + candS) == cur4; }
