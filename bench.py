@@ -655,6 +655,48 @@ def run_b200(args):
                                "hbm_algorithmic_GBps_per_gpu": round((n * FRAME + wc) * 3 / (w_ms * 1e-3) / 1e9 / world, 1),
                                "kernel_ms": {names[k]: round(float(w_slots[k]), 3) for k in names}}
             del d_w, refw
+        # ---- dictionary records: what Compressor.LoadDictionary is for -- many small records sharing one dictionary ----
+        # 65536 text-like records of 4 KiB, a 32 KiB raw-content dictionary cut from the same generator, device-resident compression at
+        # levels 1 and 3 with and without the dictionary; the frames with the dictionary are decoded again through the host API
+        # (dictionary decoding lays its output out itself).  The frames are the reference's bytes (tests/test_encode_gpu.py, soak).
+        try:
+            rec, nrec = 4096, 65536
+            dtext = dg.text_like((nrec + 64) * rec)
+            dictionary = np.ascontiguousarray(dtext[:32768])
+            d_rec = torch.from_numpy(np.concatenate([dtext[64 * rec:(64 + nrec) * rec], np.zeros(64, dtype=np.uint8)])).cuda()
+            rslot = (int(lib.ZSTD_compressBound(rec)) + 15) & ~15
+            d_rout = torch.empty(nrec * rslot + 64, dtype=torch.uint8, device="cuda")
+            rso = (u64 * nrec)(*[i * rec for i in range(nrec)]); rss = (st * nrec)(*([rec] * nrec))
+            rdo2 = (u64 * nrec)(*[i * rslot for i in range(nrec)]); rdc2 = (st * nrec)(*([rslot] * nrec)); rres = (st * nrec)()
+            drec = {"workload": f"{nrec} text-like records of {rec} B per GPU, 32 KiB raw-content dictionary (ZSTD_CCtx_loadDictionary), device-resident"}
+            for lvl in (1, 3):
+                for use_dict in (False, True):
+                    cd = api.Compressor(lvl)
+                    if use_dict:
+                        cd.LoadDictionary(dictionary)
+
+                    def r_step():
+                        dev_call(lib.ZSTDB200_compressBatchDevice, cd, nrec, lvl, d_rec.data_ptr(), rso, rss, d_rout.data_ptr(), rdo2, rdc2, rres)
+                        return cd.launch_count(), np.array(cd.timings())
+                    r_ms, _, _, r_slots = timed_steps(r_step, 1, 2)
+                    rsz = np.array(list(rres), dtype=np.int64)
+                    assert (rsz > 0).all() and (rsz <= rslot).all()
+                    drec[f"level{lvl}_{'dict' if use_dict else 'nodict'}"] = {
+                        "compress_GBps": round(nrec * rec * world * 2 / (r_ms * 1e-3) / 1e9, 3), "ms_per_step": round(r_ms / 2, 3),
+                        "ratio": round(nrec * rec / float(rsz.sum()), 3),
+                        "kernel_ms": {"enc_match": round(float(r_slots[8]) / 2, 3), "enc_entropy": round(float(r_slots[9]) / 2, 3)}}
+                    if use_dict and lvl == 1:              # round trip of a sample through the decoder with the same dictionary
+                        hb = d_rout.cpu().numpy()
+                        fr = [hb[i * rslot:i * rslot + rsz[i]].tobytes() for i in range(0, nrec, 64)]
+                        dd = api.Decompressor(); dd.LoadDictionary(dictionary)
+                        back = dd.UnwrapBatch(fr); dd.Dispose()
+                        hsrc = d_rec.cpu().numpy()
+                        assert all(b == hsrc[i * rec:(i + 1) * rec].tobytes() for b, i in zip(back, range(0, nrec, 64))), "dictionary round trip failed"
+                    cd.Dispose()
+            workloads["dictionary_records"] = drec
+            del d_rec, d_rout
+        except Exception as e:                                   # noqa: BLE001  (a probe must not take the headline down with it)
+            workloads["dictionary_records"] = {"error": repr(e)}
         workloads["note"] = "8192 x 128 KiB level-1 frames per GPU made by the GPU encoder from zstdsharp_b200.datagen workloads; incompressible = raw blocks (copy: 2 x bytes of HBM traffic)"
 
     # ------------------------------------------------------------------ CPU baseline (rank 0, N == 1 only)
