@@ -682,7 +682,7 @@ static size_t compress_batch_host(Engine& E, size_t n, int level, int checksum, 
         }
         return 0;
     } else {
-        if (!enc_compress_device(E.enc, E.stream, E.ev, np, level, checksum, E.dSrc.as<uint8_t>(), pSrcOff.data(), pSize.data(), E.dDst.as<uint8_t>(), pDstOff.data(), slotCap.data(), r.data(), E.timings, &E.launches, dict))
+        if (!enc_compress_device(E.enc, E.stream, E.ev, np, level, checksum, E.dSrc.as<uint8_t>(), pSrcOff.data(), pSize.data(), E.dDst.as<uint8_t>(), pDstOff.data(), slotCap.data(), r.data(), E.timings, &E.launches, dict, &E.encPipe[0]))
             { set_error(enc_last_error()); return (size_t)make_error(kGeneric); }
         cudaEventRecord(E.ev[12], E.stream);
     }
@@ -1063,7 +1063,7 @@ size_t ZSTDB200_compressBatchDevice(ZSTD_CCtx* cctx, size_t n, int level, const 
     size_t derr = 0;
     const zb::EncDict* const dict = cctx_dict(cctx, level, &derr);
     if (derr) { for (size_t i = 0; i < n; i++) result[i] = derr; return 0; }
-    if (!zb::enc_compress_device(E.enc, E.stream, E.ev, n, level, cctx->checksum, (const uint8_t*)d_src, srcOffset, srcSize, (uint8_t*)d_dst, dstOffset, dstCapacity, result, E.timings, &E.launches, dict))
+    if (!zb::enc_compress_device(E.enc, E.stream, E.ev, n, level, cctx->checksum, (const uint8_t*)d_src, srcOffset, srcSize, (uint8_t*)d_dst, dstOffset, dstCapacity, result, E.timings, &E.launches, dict, &E.encPipe[0]))
         { zb::set_error(zb::enc_last_error()); return (size_t)make_error(zb::kGeneric); }
     return 0;
 }

@@ -2614,8 +2614,9 @@ struct EncArenaImpl {
     DBuf items, tables, seqLL, seqML, seqOF, lit, stateBits, results, compact, cSrcOff, cSizes, cDstOff, workLists, hufState, fseTabs, carry;
     HBuf hItems, hResults, hC, hWork;
     cudaEvent_t copied = nullptr;
-    EncArenaImpl() { cudaEventCreateWithFlags(&copied, cudaEventDisableTiming); }
-    ~EncArenaImpl() { if (copied) cudaEventDestroy(copied); }
+    cudaEvent_t tev[3] = {nullptr, nullptr, nullptr};       // enc_compress_device: before the match finder / after it / after the entropy stage of this arena's pass
+    EncArenaImpl() { cudaEventCreateWithFlags(&copied, cudaEventDisableTiming); for (auto& e : tev) cudaEventCreate(&e); }
+    ~EncArenaImpl() { if (copied) cudaEventDestroy(copied); for (auto& e : tev) if (e) cudaEventDestroy(e); }
 };
 static thread_local std::string t_encErr;
 const char* enc_last_error() { return t_encErr.c_str(); }
@@ -2882,28 +2883,47 @@ void enc_set_overlap_mode(bool overlap)
 }
 const uint64_t* enc_results(const EncArena& A) { return A.impl ? (const uint64_t*)A.impl->hResults.p : nullptr; }
 
+// More than one pass (n > 8192): with a second arena B the passes alternate between the two, so that the host's preparation of a pass
+// (descriptors, work lists) and the read-back of the one before overlap the kernels -- many small records are otherwise bound by that.
 bool enc_compress_device(EncArena& A, cudaStream_t stream, cudaEvent_t* ev, size_t n, int level, int checksumFlag,
                          const uint8_t* d_src, const uint64_t* srcOff, const size_t* srcSize,
                          uint8_t* d_dst, const uint64_t* dstOff, const size_t* dstCap, size_t* result,
-                         float* timings, unsigned* launches, const EncDict* dict)
+                         float* timings, unsigned* launches, const EncDict* dict, EncArena* B)
 {
+    (void)ev;
     float msAll = 0, msMatch = 0, msEnt = 0;
-    enc_set_overlap_mode(false);                 // one pass at a time on one stream: every kernel keeps its own L1 / shared-memory split
-    for (size_t base = 0; base < n; base += kEncMaxItemsPerPass) {
-        size_t const m = std::min(kEncMaxItemsPerPass, n - base);
-        if (!enc_enqueue(A, stream, stream, m, level, checksumFlag, d_src, srcOff + base, srcSize + base, d_dst, dstOff + base, dstCap + base, &ev[14], launches, dict)) return false;
-        ENC_CUDA(cudaStreamSynchronize(stream));
-        ENC_CUDA(cudaGetLastError());
+    enc_set_overlap_mode(false);                 // the passes run one after the other on one stream: every kernel keeps its own L1 / shared-memory split
+    EncArena* const ar[2] = {&A, (B && n > kEncMaxItemsPerPass) ? B : &A};
+    int const nAr = ar[1] != ar[0] ? 2 : 1;
+    struct Pending { bool on = false; size_t base = 0, m = 0; } pend[2];
+    for (auto* a : ar) if (!a->impl) a->impl = new EncArenaImpl();
+    auto finish = [&](int k) -> bool {
+        Pending& pd = pend[k];
+        if (!pd.on) return true;
+        EncArenaImpl& I = *ar[k]->impl;
+        ENC_CUDA(cudaEventSynchronize(I.tev[2]));
         float t;
-        cudaEventElapsedTime(&t, ev[14], ev[16]); msAll += t;
-        cudaEventElapsedTime(&t, ev[14], ev[15]); msMatch += t;
-        cudaEventElapsedTime(&t, ev[15], ev[16]); msEnt += t;
-        const uint64_t* hr = enc_results(A);
-        for (size_t i = 0; i < m; i++) {
-            size_t const ss = srcSize[base + i];
-            result[base + i] = ss > kEncMaxFrameBytes ? (size_t)make_error(kSrcSizeWrong) : (size_t)hr[i];
+        cudaEventElapsedTime(&t, I.tev[0], I.tev[2]); msAll += t;
+        cudaEventElapsedTime(&t, I.tev[0], I.tev[1]); msMatch += t;
+        cudaEventElapsedTime(&t, I.tev[1], I.tev[2]); msEnt += t;
+        const uint64_t* hr = enc_results(*ar[k]);
+        for (size_t i = 0; i < pd.m; i++) {
+            size_t const ss = srcSize[pd.base + i];
+            result[pd.base + i] = ss > kEncMaxFrameBytes ? (size_t)make_error(kSrcSizeWrong) : (size_t)hr[i];
         }
+        pd.on = false;
+        return true;
+    };
+    int k = 0;
+    for (size_t base = 0; base < n; base += kEncMaxItemsPerPass, k = (k + 1) % nAr) {
+        size_t const m = std::min(kEncMaxItemsPerPass, n - base);
+        if (!finish(k)) return false;
+        if (!enc_enqueue(*ar[k], stream, stream, m, level, checksumFlag, d_src, srcOff + base, srcSize + base, d_dst, dstOff + base, dstCap + base, ar[k]->impl->tev, launches, dict)) return false;
+        pend[k].on = true; pend[k].base = base; pend[k].m = m;
     }
+    for (int q = 0; q < nAr; q++, k = (k + 1) % nAr) if (!finish(k)) return false;
+    ENC_CUDA(cudaStreamSynchronize(stream));
+    ENC_CUDA(cudaGetLastError());
     timings[1] = msAll; timings[8] = msMatch; timings[9] = msEnt;
     return true;
 }

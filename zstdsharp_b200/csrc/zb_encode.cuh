@@ -33,7 +33,7 @@ size_t enc_max_frame_bytes();
 bool enc_compress_device(EncArena& A, cudaStream_t stream, cudaEvent_t* ev, size_t n, int level, int checksumFlag,
                          const uint8_t* d_src, const uint64_t* srcOff, const size_t* srcSize,
                          uint8_t* d_dst, const uint64_t* dstOff, const size_t* dstCap, size_t* result,
-                         float* timings, unsigned* launches, const EncDict* dict = nullptr);
+                         float* timings, unsigned* launches, const EncDict* dict = nullptr, EncArena* second = nullptr);
 // Queues one pass (m <= 8192 chunks) on `stream` without waiting; descriptors are copied on `copyStream`; results land in
 // pinned host memory (enc_results) once `stream` has drained.  ev3 (optional): events before/after match, after entropy.
 bool enc_enqueue(EncArena& A, cudaStream_t stream, cudaStream_t copyStream, size_t m, int level, int checksumFlag,
