@@ -307,8 +307,17 @@ def run_b200(args):
     torch.cuda.set_device(local)
     # one process per GPU: keep this rank's threads and the pinned buffers it allocates on the CPUs next to its GPU's PCIe root
     numa_rc = lib.ZSTDB200_bindThreadToDevice(local) if os.environ.get("ZSTDB200_NUMA_BIND", "1") != "0" else None
+    # The ranks exchange nothing on the data path (frames share no state): the process group only carries the barrier and three
+    # scalars (max step time, byte totals), so it is a CPU group (gloo over loopback); NCCL only if gloo cannot come up here.
+    coll_device = "cpu"
     if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        os.environ.setdefault("GLOO_SOCKET_IFNAME", "lo")
+        try:
+            dist.init_process_group("gloo")
+        except Exception as e:                                   # noqa: BLE001
+            log("bench.py: gloo group failed (%r), using nccl for the bookkeeping" % (e,))
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+            coll_device = "cuda"
 
     def barrier():
         torch.cuda.synchronize()
@@ -318,14 +327,14 @@ def run_b200(args):
     def max_over_ranks(x: float) -> float:
         if world == 1:
             return x
-        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        t = torch.tensor([x], dtype=torch.float64, device=coll_device)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
     def sum_over_ranks(x: float) -> float:
         if world == 1:
             return x
-        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        t = torch.tensor([x], dtype=torch.float64, device=coll_device)
         dist.all_reduce(t, op=dist.ReduceOp.SUM)
         return float(t.item())
 
