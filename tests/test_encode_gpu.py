@@ -394,3 +394,55 @@ def test_dictionary_tests_of_the_reference(dec):
     c.LoadDictionary(dicts["zdict_4k"])                          # a good dictionary afterwards works
     assert bytes(c.Wrap(data)) == oracle().compress_loaded_dict(data, 1, dicts["zdict_4k"])
     c.Dispose()
+
+
+def test_dictionary_digest_keeps_its_level_like_the_reference():
+    """ZSTD_initLocalDict (ZstdCompress.cs:1581) builds the CDict once, with the level of the first compression after LoadDictionary; a later
+    level change only moves the window (ZSTD_CCtx_init_compressStream2 :6949), the match finder keeps the CDict's parameters.  The same call
+    sequence on one context of the reference DLL and on one GPU context gives the same bytes."""
+    from _oracle import refdll, refdll_available
+    if not refdll_available():
+        pytest.skip("oracle/_ref not built")
+    from zstdsharp_b200 import Compressor
+    from _dict_cases import dictionaries
+    r = refdll(); L = r.lib
+    d = dictionaries(libzstd())["zdict_32k"]
+    text = dg.text_like(4 * FRAME)
+    inputs = [np.ascontiguousarray(text[1000:1000 + 6000]), np.ascontiguousarray(text[50_000:50_000 + 90_000]), np.ascontiguousarray(text[200_000:200_000 + 12_000])]
+    for first, second in ((1, 3), (3, 1), (2, -3)):
+        c = Compressor(first); c.LoadDictionary(d)
+        rc = L.ZREF_createCCtx(); L.ZREF_CCtx_setParameter(rc, 100, first)
+        db = np.frombuffer(d, dtype=np.uint8)
+        assert not L.ZREF_isError(L.ZREF_CCtx_loadDictionary(rc, db.ctypes.data, db.size))
+        out = np.empty(200_000, dtype=np.uint8)
+        try:
+            for k, level in enumerate((first, second, second, first)):
+                src = inputs[k % len(inputs)]
+                c.Level = level
+                L.ZREF_CCtx_setParameter(rc, 100, level)
+                n = L.ZREF_compress2(rc, out.ctypes.data, out.size, src.ctypes.data, src.size)
+                assert not L.ZREF_isError(n)
+                assert bytes(c.Wrap(src)) == out[:n].tobytes(), (first, second, k, level, src.size)
+        finally:
+            L.ZREF_freeCCtx(rc); c.Dispose()
+
+
+def test_multi_device_codec_with_a_dictionary():
+    """ZSTDB200_multiLoadDictionary loads the dictionary into every device's compression and decompression context: one WrapBatch /
+    UnwrapBatch over all visible devices gives the oracle's frames in the caller's order and the inputs back."""
+    from zstdsharp_b200 import MultiCodec
+    from _dict_cases import dictionaries, compress_payloads
+    o = oracle()
+    d = dictionaries(libzstd())["zdict_4k"]
+    pays = compress_payloads(n_random=8)
+    m = MultiCodec(0, 3)
+    try:
+        m.LoadDictionary(d)
+        frames = m.WrapBatch(pays)
+        for src, f in zip(pays, frames):
+            assert f == o.compress_loaded_dict(src, 3, d), src.size
+        assert m.UnwrapBatch(frames) == [p.tobytes() for p in pays]
+        m.LoadDictionary(None)
+        assert m.WrapBatch(pays[:4]) == [o.compress(p, 3) for p in pays[:4]]
+    finally:
+        m.Dispose()
