@@ -323,6 +323,7 @@ public:
     }
     ~CompressionStream() { try { Dispose(); } catch (...) {} }
     void SetParameter(ZSTD_cParameter parameter, int value) { EnsureNotDisposed(); comp_.SetParameter(parameter, value); }   /* CompressionStream.cs:46-50 */
+    void LoadDictionary(const void* dict, size_t dictLength) { EnsureNotDisposed(); comp_.LoadDictionary(dict, dictLength); }  /* CompressionStream.cs:58-62 */
     void Write(const void* buffer, size_t count) {                                     /* CompressionStream.cs:130-150 */
         EnsureNotDisposed();
         const uint8_t* p = static_cast<const uint8_t*>(buffer);

@@ -54,3 +54,28 @@ def test_stream_round_trip_and_interop():
     foreign = b"".join(z.compress(np.frombuffer(data[i:i + FRAME], dtype=np.uint8), lvl, checksum=lvl & 1)
                        for i, lvl in zip(range(0, 4 * FRAME, FRAME), (1, 3, 9, 19)))
     assert DecompressionStream(io.BytesIO(foreign)).readall() == data[:4 * FRAME]
+
+
+@pytest.mark.gpu
+def test_stream_round_trip_with_a_dictionary():
+    """CompressionStream.LoadDictionary / DecompressionStream.LoadDictionary (CompressionStream.cs:58-62, DecompressionStream.cs:58-62;
+    ZstdNetSteamingTests: the dictionary variants of the round trips): every frame of the stream is the oracle's dictionary frame of its
+    piece, the stream reads back with the dictionary and fails without it."""
+    from zstdsharp_b200.streams import CompressionStream, DecompressionStream
+    from zstdsharp_b200 import ZstdException
+    from _dict_cases import dictionaries
+    o = oracle()
+    d = dictionaries(libzstd())["zdict_32k"]
+    data = dg.text_like(4 * FRAME)[FRAME // 3: FRAME // 3 + 2 * FRAME + 777].tobytes()
+    sink = io.BytesIO()
+    with CompressionStream(sink, level=3, batch_frames=2, leaveOpen=True) as cs:
+        cs.LoadDictionary(d)
+        cs.Write(data)
+    z = sink.getvalue()
+    expect = b"".join(o.compress_loaded_dict(np.frombuffer(data[i:i + FRAME], dtype=np.uint8), 3, d) for i in range(0, len(data), FRAME))
+    assert z == expect
+    ds = DecompressionStream(io.BytesIO(z))
+    ds.LoadDictionary(d)
+    assert ds.read() == data
+    with pytest.raises(ZstdException):
+        DecompressionStream(io.BytesIO(z)).read()

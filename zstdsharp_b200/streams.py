@@ -52,6 +52,10 @@ class CompressionStream(io.RawIOBase):
         self._ensure()
         self._comp.SetParameter(parameter, value)
 
+    def LoadDictionary(self, dictionary) -> None:     # CompressionStream.cs:58-62: every frame of the stream is compressed with it
+        self._ensure()
+        self._comp.LoadDictionary(dictionary)
+
     def writable(self) -> bool:
         return True
 
@@ -146,6 +150,9 @@ class DecompressionStream(io.RawIOBase):
         self._out = bytearray()       # decoded bytes not yet handed out
         self._eof = False
         self._done = False
+
+    def LoadDictionary(self, dictionary) -> None:     # DecompressionStream.cs:58-62
+        self._dec.LoadDictionary(dictionary)
 
     def readable(self) -> bool:
         return True
