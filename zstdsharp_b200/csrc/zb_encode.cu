@@ -21,6 +21,7 @@
 // dependent memory round trips per sequence, and only concurrency across frames hides it (profiles/r01_notes.md).
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -183,6 +184,8 @@ struct EncPass {
     EntCarry* carry;        // [item]
     uint8_t* hufState;      // multi-block frames: 2 slots of {u8 nbBits[256]; u16 value[256]} per frame (prev / next Huffman CTable)
     uint32_t checksumFlag;  // ZSTD_c_checksumFlag: append the low 32 bits of XXH64(src) to every frame
+    uint32_t seqStride;     // entries per frame in seqLL / seqML / seqOF / stateBits: largest block of the pass / 4 + 1 (maxNbSeq, ZstdCompress.cs:2570), at most kEncSeqCap
+    uint32_t litStride;     // bytes per frame in litBuf: largest block of the pass + 64
     EncDictDev dict;
 };
 constexpr uint32_t kHufStateSlot = 768;
@@ -251,9 +254,9 @@ __global__ void __launch_bounds__(32 * kMatchWarps) enc_match_group_kernel(EncPa
     uint32_t const hlog = it.hashLog, mls = it.minMatch;
     const uint8_t* const src = p.src + it.srcOff;    // frame start; every position below is an offset from it
     uint32_t* const T = p.tables + it.tableOff;      // zero-initialised per frame, HBM/L2-resident; entries hold position + 2 (the reference's index)
-    uint32_t* const oLL = p.seqLL + (size_t)item * kEncSeqCap;
-    uint32_t* const oML = p.seqML + (size_t)item * kEncSeqCap;
-    uint32_t* const oOF = p.seqOF + (size_t)item * kEncSeqCap;
+    uint32_t* const oLL = p.seqLL + (size_t)item * p.seqStride;
+    uint32_t* const oML = p.seqML + (size_t)item * p.seqStride;
+    uint32_t* const oOF = p.seqOF + (size_t)item * p.seqStride;
     // block geometry: first block of a frame unless MB (then block `wave`, with the window and repcodes of the blocks before it)
     int srcSize = active ? (int)it.srcSize : 64;     // end of the block
     int ip0 = 1, anchor = 0, lowPos = 0;             // first position of a frame is skipped (:129)
@@ -362,7 +365,7 @@ __global__ void __launch_bounds__(32 * kMatchWarps) enc_match_group_kernel(EncPa
         }
         // ---- sequence, post-match inserts (:251-263), next state ----
         if (ev) {
-            ZB_ASSERT(nseq < kEncSeqCap && mpos >= anchor && msrc >= lowPos && msrc < mpos && mpos + mlen <= srcSize);
+            ZB_ASSERT(nseq < p.seqStride && mpos >= anchor && msrc >= lowPos && msrc < mpos && mpos + mlen <= srcSize);
             if (l == 0) { oLL[nseq] = (uint32_t)(mpos - anchor); oOF[nseq] = offcode + 1; oML[nseq] = (uint32_t)mlen - 3; }
             nseq++;
             int const mend = mpos + mlen;
@@ -413,9 +416,9 @@ __global__ void __launch_bounds__(32 * kMatchWarps) enc_match_dfast_group_kernel
     const uint8_t* const src = p.src + it.srcOff;                 // frame start
     uint32_t* const TL = p.tables + it.tableOff;                  // long table (hash8), then short table (hash mls)
     uint32_t* const TS = TL + (1u << hBitsL);
-    uint32_t* const oLL = p.seqLL + (size_t)item * kEncSeqCap;
-    uint32_t* const oML = p.seqML + (size_t)item * kEncSeqCap;
-    uint32_t* const oOF = p.seqOF + (size_t)item * kEncSeqCap;
+    uint32_t* const oLL = p.seqLL + (size_t)item * p.seqStride;
+    uint32_t* const oML = p.seqML + (size_t)item * p.seqStride;
+    uint32_t* const oOF = p.seqOF + (size_t)item * p.seqStride;
     int srcSize = active ? (int)it.srcSize : 64;     // end of the block
     int ip = 1, anchor = 0, lowPos = 0;              // first position of a frame is skipped (:84)
     uint32_t off1 = 1, off2 = 0, offsetSaved = 4;    // offset_2 = 4 exceeds the history at frame start
@@ -543,7 +546,7 @@ __global__ void __launch_bounds__(32 * kMatchWarps) enc_match_dfast_group_kernel
                 off2 = off1; off1 = offset; offcode = offset + 2;
                 if (l == 0 && se < 4 && p1e <= ilimit) TL[hln] = tab_entry<TAG>((uint32_t)p1e + 2, x4n);   // complementary insertion (:210-213): hashLong[hl1] = ip1
             }
-            ZB_ASSERT(nseq < kEncSeqCap && mpos >= anchor && msrc >= lowPos && msrc < mpos && mpos + mlen <= srcSize);
+            ZB_ASSERT(nseq < p.seqStride && mpos >= anchor && msrc >= lowPos && msrc < mpos && mpos + mlen <= srcSize);
             if (l == 0) { oLL[nseq] = (uint32_t)(mpos - anchor); oOF[nseq] = offcode + 1; oML[nseq] = (uint32_t)mlen - 3; }
             nseq++;
             int const mend = mpos + mlen;
@@ -1051,9 +1054,9 @@ __device__ uint32_t count_2segments(const uint8_t* ip, const uint8_t* match, con
     return matchLength + count_match(ip + matchLength, iStart, iEnd);
 }
 struct SeqWriter {
-    uint32_t* ll; uint32_t* ml; uint32_t* of; uint32_t n;
+    uint32_t* ll; uint32_t* ml; uint32_t* of; uint32_t n; uint32_t cap;
     __device__ __forceinline__ void store(uint32_t litLength, uint32_t offCode, uint32_t mlBase)   // ZSTD_storeSeq :204
-    { ZB_ASSERT(n < kEncSeqCap); ll[n] = litLength; of[n] = offCode + 1; ml[n] = mlBase; n++; }
+    { ZB_ASSERT(n < cap); ll[n] = litLength; of[n] = offCode + 1; ml[n] = mlBase; n++; }
 };
 // what the serial parsers share: the two segments and the block
 struct DictBlk {
@@ -1598,9 +1601,9 @@ __global__ void __launch_bounds__(32 * kMatchWarps) enc_match_dict_fast_group_ke
     const uint8_t* const base = src - dP; const uint8_t* const dictBase = p.dict.content - 2;
     uint32_t const prefixStartIndex = bm.prefixStartIndex, dictStartIndex = bm.dictStartIndex;
     uint32_t* const T = p.tables + it.tableOff; const uint32_t* const DT = p.dict.tables;
-    uint32_t* const oLL = p.seqLL + (size_t)item * kEncSeqCap;
-    uint32_t* const oML = p.seqML + (size_t)item * kEncSeqCap;
-    uint32_t* const oOF = p.seqOF + (size_t)item * kEncSeqCap;
+    uint32_t* const oLL = p.seqLL + (size_t)item * p.seqStride;
+    uint32_t* const oML = p.seqML + (size_t)item * p.seqStride;
+    uint32_t* const oOF = p.seqOF + (size_t)item * p.seqStride;
     int const blkStart = (int)(wave * kBlockSizeMax), blkEnd = active ? blkStart + (int)min(kBlockSizeMax, it.srcSize - (uint32_t)blkStart) : blkStart + 64;
     int const ilimit = blkEnd - 8;
     int const stepSize = active ? (int)it.dStep : 1;
@@ -1718,7 +1721,7 @@ __global__ void __launch_bounds__(32 * kMatchWarps) enc_match_dict_fast_group_ke
         }
         // ---- sequence, post-match inserts (:490-498, :662-669), next state ----
         if (ev) {
-            ZB_ASSERT(nseq < kEncSeqCap && mpos >= anchor && msrc < (uint32_t)mpos + dP && mpos + mlen <= blkEnd);
+            ZB_ASSERT(nseq < p.seqStride && mpos >= anchor && msrc < (uint32_t)mpos + dP && mpos + mlen <= blkEnd);
             if (l == 0) { oLL[nseq] = (uint32_t)(mpos - anchor); oOF[nseq] = offcode + 1; oML[nseq] = (uint32_t)mlen - 3; }
             nseq++;
             int const mend = mpos + mlen;
@@ -1770,9 +1773,9 @@ __global__ void __launch_bounds__(32 * kMatchWarps) enc_match_dict_dfast_group_k
     uint32_t const prefixStartIndex = it.dBlkPrefix, dictStartIndex = it.dBlkLow;
     uint32_t* const TL = p.tables + it.tableOff; uint32_t* const TS = TL + ((size_t)1 << hBitsL);
     const uint32_t* const DTL = p.dict.tables; const uint32_t* const DTS = DTL + ((size_t)1 << dictHBitsL);
-    uint32_t* const oLL = p.seqLL + (size_t)item * kEncSeqCap;
-    uint32_t* const oML = p.seqML + (size_t)item * kEncSeqCap;
-    uint32_t* const oOF = p.seqOF + (size_t)item * kEncSeqCap;
+    uint32_t* const oLL = p.seqLL + (size_t)item * p.seqStride;
+    uint32_t* const oML = p.seqML + (size_t)item * p.seqStride;
+    uint32_t* const oOF = p.seqOF + (size_t)item * p.seqStride;
     int const blkStart = (int)(wave * kBlockSizeMax), blkEnd = active ? blkStart + (int)min(kBlockSizeMax, it.srcSize - (uint32_t)blkStart) : blkStart + 64;
     int const ilimit = blkEnd - 8;
     int ip = blkStart, anchor = blkStart;
@@ -1910,7 +1913,7 @@ __global__ void __launch_bounds__(32 * kMatchWarps) enc_match_dict_dfast_group_k
             }
         }
         if (ev) {
-            ZB_ASSERT(nseq < kEncSeqCap && mpos >= anchor && msrc < (uint32_t)mpos + dP && mpos + mlen <= blkEnd);
+            ZB_ASSERT(nseq < p.seqStride && mpos >= anchor && msrc < (uint32_t)mpos + dP && mpos + mlen <= blkEnd);
             if (l == 0) { oLL[nseq] = (uint32_t)(mpos - anchor); oOF[nseq] = offcode + 1; oML[nseq] = (uint32_t)mlen - 3; }
             nseq++;
             int const mend = mpos + mlen;
@@ -1951,7 +1954,7 @@ __global__ void __launch_bounds__(128) enc_match_dict_kernel(EncPass p, const ui
     uint32_t const srcIdx0 = it.dPrefix;                             // index of src[0]: 2 + dictionary content length (2 when nothing was attached)
     const uint8_t* const base = src - srcIdx0;
     uint32_t const maxDist = 1u << it.windowLog, dictLimit = it.wDictLimit, loadedDictEnd = it.loadedDictEnd;
-    SeqWriter sw{p.seqLL + (size_t)item * kEncSeqCap, p.seqML + (size_t)item * kEncSeqCap, p.seqOF + (size_t)item * kEncSeqCap, 0};
+    SeqWriter sw{p.seqLL + (size_t)item * p.seqStride, p.seqML + (size_t)item * p.seqStride, p.seqOF + (size_t)item * p.seqStride, 0, p.seqStride};
     uint32_t rep[2] = {it.rep[0], it.rep[1]};
     uint32_t* const T = p.tables + it.tableOff;
     uint32_t* const TS = T + ((size_t)1 << it.hashLog);              // ZSTD_dfast: the small table (chainTable) follows the long one
@@ -1977,17 +1980,17 @@ __global__ void __launch_bounds__(128) enc_match_dict_kernel(EncPass p, const ui
 // and a frame that COPIES the CDict (ZSTD_resetCCtx_byCopyingCDict :2803) starts with the CDict's match-finder tables as its own.
 __global__ void enc_dict_init_kernel(EncPass p, uint32_t nItems, uint32_t entries)
 {
-    uint32_t const item = blockIdx.y;
+    uint32_t const item = blockIdx.x, part = blockIdx.y, parts = gridDim.y;      // frames along x: a pass of small records has more than 65535 of them
     if (item >= nItems) return;
     EncItem const& it = p.items[item];
     if (it.dMode == 0) return;
-    if (blockIdx.x == 0 && it.hufRepeat) {
+    if (part == 0 && it.hufRepeat) {
         uint32_t* const d = (uint32_t*)(p.hufState + (size_t)item * 2 * kHufStateSlot); const uint32_t* const s = (const uint32_t*)p.dict.huf;
         for (uint32_t k = threadIdx.x; k < kHufStateSlot / 4; k += blockDim.x) d[k] = s[k];
     }
     if (it.dMode != 2 || it.srcSize < 7) return;                     // attached frames search the CDict's tables in place
     uint4* const d = (uint4*)(p.tables + it.tableOff); const uint4* const s = (const uint4*)p.dict.tables;
-    for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < entries / 4; k += gridDim.x * blockDim.x) d[k] = s[k];
+    for (uint32_t k = part * blockDim.x + threadIdx.x; k < entries / 4; k += parts * blockDim.x) d[k] = s[k];
 }
 
 // ZSTD_initCDict_internal (:5826) on the device, one thread, once per (dictionary, level): ZSTD_loadCEntropy (:5264: HUF_readCTable
@@ -2115,13 +2118,13 @@ __global__ void __launch_bounds__(kEntThreads, MB ? 8 : 15) enc_entropy_kernel(E
     uint32_t const nbSeq = it.nbSeq;
     if (srcSize < 7) { raw = true; if (PHASE == 0) { if (tid == 0) cy.flags = 0; return; } }
     if (!raw) {
-        const uint32_t* const aLL = p.seqLL + (size_t)item * kEncSeqCap;
-        const uint32_t* const aML = p.seqML + (size_t)item * kEncSeqCap;
-        const uint32_t* const aOF = p.seqOF + (size_t)item * kEncSeqCap;
-        uint64_t* const sb = p.stateBits + (size_t)item * kEncSeqCap;
+        const uint32_t* const aLL = p.seqLL + (size_t)item * p.seqStride;
+        const uint32_t* const aML = p.seqML + (size_t)item * p.seqStride;
+        const uint32_t* const aOF = p.seqOF + (size_t)item * p.seqStride;
+        uint64_t* const sb = p.stateBits + (size_t)item * p.seqStride;
         uint32_t op = 0, lastCountSize = 0;
       if (PHASE == 0) {
-        uint8_t* const lit = p.litBuf + (size_t)item * kEncLitStride;
+        uint8_t* const lit = p.litBuf + (size_t)item * p.litStride;
         // ---- 1. gather literals (ZSTD_storeSeq copies + ZSTD_storeLastLiterals) ----
         uint32_t litSize;
         {
@@ -2559,7 +2562,7 @@ __global__ void __launch_bounds__(32) enc_fse_chain_kernel(EncPass p, const uint
     const uint2* const gtt = (const uint2*)g.tt;                    // {deltaFindState, deltaNbBits}
     const uint16_t* const st = (const uint16_t*)(s_chain + lane * kChainTabStride);
     uint32_t const nbSeq = p.items[item].nbSeq;
-    uint16_t* const out16 = (uint16_t*)(p.stateBits + (size_t)item * kEncSeqCap) + k;     // 4 x u16 per sequence
+    uint16_t* const out16 = (uint16_t*)(p.stateBits + (size_t)item * p.seqStride) + k;     // 4 x u16 per sequence
     uint32_t state;
     {   // FSE_initCState2 (Fse.cs:38) on the last sequence's symbol
         uint2 const tt = __ldg(gtt + out16[(size_t)(nbSeq - 1) * 4]);
@@ -2684,6 +2687,13 @@ const uint8_t* EncArena::compactBuf() const { return impl ? (const uint8_t*)impl
 #define ENC_CUDA(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { t_encErr = std::string(#call) + ": " + cudaGetErrorString(e_); fprintf(stderr, "[zstdb200] CUDA failure: %s\n", t_encErr.c_str()); return false; } } while (0)
 
 constexpr size_t kEncMaxItemsPerPass = 8192;
+// Frames one pass can hold: 8192 blocks of 128 KiB fill the arenas (0.9 MB of sequence / literal / state scratch per block); passes of smaller
+// records hold proportionally more, up to 65536 (one launch overhead and one host round trip per pass is what small records are bound by)
+size_t enc_pass_capacity(size_t maxBlockBytes)
+{
+    size_t const blk = std::max<size_t>(std::min<size_t>(maxBlockBytes, kBlockSizeMax), 16384);
+    return std::min<size_t>(65536, kEncMaxItemsPerPass * (kBlockSizeMax / blk));
+}
 
 // Queues one pass (m <= kEncMaxItemsPerPass frames) without waiting: the frame descriptors and work lists are copied on
 // `copyStream` (pass the stream that carries the bulk H2D of the same frames, so that the small copies do not queue
@@ -2699,58 +2709,78 @@ bool enc_enqueue(EncArena& A, cudaStream_t stream, cudaStream_t copyStream, size
                  uint8_t* d_dst, const uint64_t* dstOff, const size_t* dstCap, cudaEvent_t* ev3, unsigned* launches, const EncDict* dict)
 {
     const EncDictImpl* const DI = (dict && dict->ready) ? dict->impl : nullptr;
+    static bool const trace = getenv("ZSTDB200_TRACE_ENQ") != nullptr;       // developer aid: host time of the stages of this function
+    auto const tq0 = std::chrono::steady_clock::now();
+    auto lap = [&](const char* what) { if (trace) fprintf(stderr, "[zstdb200] enqueue %-10s %.3f ms since entry\n", what, std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tq0).count()); };
     if (!A.impl) A.impl = new EncArenaImpl();
     EncArenaImpl& I = *A.impl;
-    if (m > kEncMaxItemsPerPass) { t_encErr = "pass too large"; return false; }
+    size_t maxBlk = 0;
+    for (size_t i = 0; i < m; i++) maxBlk = std::max(maxBlk, std::min<size_t>(srcSize[i], kBlockSizeMax));
+    if (m > enc_pass_capacity(maxBlk)) { t_encErr = "pass too large"; return false; }
+    // per-frame strides of the sequence / literal arenas follow the largest block of the pass: a pass of small records holds more of them
+    uint32_t const seqStride = (uint32_t)((maxBlk / 4 + 1 + 3) & ~(size_t)3), litStride = (uint32_t)((maxBlk + 64 + 15) & ~(size_t)15);
     if (!I.hItems.ensure(m * sizeof(EncItem)) || !I.items.ensure(m * sizeof(EncItem)) || !I.hResults.ensure(m * 8)) { t_encErr = "out of memory (items)"; return false; }
     EncItem* hi = (EncItem*)I.hItems.p;
     uint64_t* const hr = (uint64_t*)I.hResults.p;
     size_t tableEntries = 0, maxWaves = 1, totalBlocks = 0;
     bool mb = false;
     std::vector<uint32_t> nBlk(m);
+    // Everything but the offsets depends on the size alone: records of equal size (the usual batch) share one prepared descriptor
+    EncItem proto; size_t protoSS = ~(size_t)0, protoTable = 0; uint32_t protoBlk = 0; uint64_t protoErr = 0;
     for (size_t i = 0; i < m; i++) {
         size_t const ss = srcSize[i];
-        EncItem& e = hi[i];
-        memset(&e, 0, sizeof(e));
-        e.srcOff = srcOff[i]; e.dstOff = dstOff[i];
-        e.srcSize = (uint32_t)std::min<size_t>(ss, 0xFFFFFFF0u); e.dstCap = (uint32_t)std::min<size_t>(dstCap[i], 0xFFFFFFF0u);
-        CParams c = get_cparams(level, ss);
-        if (DI) {
-            // ZSTD_CCtx_init_compressStream2 (:6949) + ZSTD_resetCCtx_usingCDict (:2881): the frame's window comes from the level, the
-            // source and the dictionary size; everything else from the CDict -- as it is when the CDict is copied, re-adjusted for
-            // the source size when it is attached (small inputs: ZSTD_shouldAttachDict :2738, 8 KiB for ZSTD_fast, 16 KiB for ZSTD_dfast)
-            bool const attach = ss <= (DI->cp.strategy == 1 ? 8u * 1024 : 16u * 1024);
-            CParams const req = get_cparams_dict(level, ss, DI->dictSize, attach ? 1 : 0);
-            c = attach ? adjust_cparams_dict(DI->cp, ss, DI->dictSize, 1) : DI->cp;
-            if (req.strategy == 0) c.strategy = 0; else c.windowLog = req.windowLog;
-            uint32_t const L = DI->contentLen, cdictEnd = 2 + L;
-            e.dMode = attach ? 1u : 2u; e.dStep = c.targetLength + !c.targetLength;
-            if (attach) {
-                if (L == 0) { e.dPrefix = 2; e.wLow = e.wDictLimit = 2; }                        // cdictLen == 0: nothing to attach (:2779)
-                else { e.dPrefix = cdictEnd; e.wLow = e.wDictLimit = cdictEnd; e.loadedDictEnd = cdictEnd; e.dms = 1; }
-            } else {
-                e.dPrefix = cdictEnd; e.wLow = 2; e.wDictLimit = cdictEnd; e.loadedDictEnd = L ? cdictEnd : 0;
-                if (e.wDictLimit - e.wLow < 8) e.wLow = e.wDictLimit;                             // ZSTD_window_update (ZstdCompressInternal.cs:742)
+        if (ss != protoSS) {
+            EncItem& e = proto;
+            memset(&e, 0, sizeof(e));
+            protoSS = ss; protoTable = 0; protoBlk = 0; protoErr = 0;
+            e.srcSize = (uint32_t)std::min<size_t>(ss, 0xFFFFFFF0u);
+            CParams c = get_cparams(level, ss);
+            if (DI) {
+                // ZSTD_CCtx_init_compressStream2 (:6949) + ZSTD_resetCCtx_usingCDict (:2881): the frame's window comes from the level, the
+                // source and the dictionary size; everything else from the CDict -- as it is when the CDict is copied, re-adjusted for
+                // the source size when it is attached (small inputs: ZSTD_shouldAttachDict :2738, 8 KiB for ZSTD_fast, 16 KiB for ZSTD_dfast)
+                bool const attach = ss <= (DI->cp.strategy == 1 ? 8u * 1024 : 16u * 1024);
+                CParams const req = get_cparams_dict(level, ss, DI->dictSize, attach ? 1 : 0);
+                c = attach ? adjust_cparams_dict(DI->cp, ss, DI->dictSize, 1) : DI->cp;
+                if (req.strategy == 0) c.strategy = 0; else c.windowLog = req.windowLog;
+                uint32_t const L = DI->contentLen, cdictEnd = 2 + L;
+                e.dMode = attach ? 1u : 2u; e.dStep = c.targetLength + !c.targetLength;
+                if (attach) {
+                    if (L == 0) { e.dPrefix = 2; e.wLow = e.wDictLimit = 2; }                        // cdictLen == 0: nothing to attach (:2779)
+                    else { e.dPrefix = cdictEnd; e.wLow = e.wDictLimit = cdictEnd; e.loadedDictEnd = cdictEnd; e.dms = 1; }
+                } else {
+                    e.dPrefix = cdictEnd; e.wLow = 2; e.wDictLimit = cdictEnd; e.loadedDictEnd = L ? cdictEnd : 0;
+                    if (e.wDictLimit - e.wLow < 8) e.wLow = e.wDictLimit;                             // ZSTD_window_update (ZstdCompressInternal.cs:742)
+                }
+                e.hufRepeat = DI->hufRepeat; e.fseValid = DI->fseValid;
             }
-            e.hufRepeat = DI->hufRepeat; e.fseValid = DI->fseValid;
+            e.windowLog = c.windowLog; e.hashLog = c.hashLog; e.chainLog = c.chainLog; e.minMatch = c.minMatch; e.strategy = c.strategy;
+            // ZSTD_fast with an acceleration factor: probe pairs `stepSize` apart (hasStep = targetLength > 1, ZstdFast.cs:101, :334) and
+            // leave the literals uncompressed (ZSTD_literalsCompressionIsDisabled, ZstdCompressInternal.cs:483-498)
+            e.stepSize = (c.strategy == 1 && c.targetLength > 1) ? c.targetLength + 1 : 2;
+            e.rawLits = (c.strategy == 1 && c.targetLength > 0) ? 1u : 0u;
+            e.nbSeq = 0; e.lastLL = (uint32_t)std::min<size_t>(ss, kBlockSizeMax);
+            e.rep[0] = 1; e.rep[1] = 4;                               // repStartValue (ZstdInternal.cs:13)
+            if (DI) { e.rep[0] = DI->rep[0]; e.rep[1] = DI->rep[1]; }   // the dictionary's repcodes
+            if (c.strategy == 0) protoErr = make_error(kParameterUnsupported);                   // level 4 outside its dfast sizes
+            else if (ss > kEncMaxFrameBytes) protoErr = make_error(kSrcSizeWrong);                // positions are 31-bit
+            else {
+                protoBlk = ss <= kBlockSizeMax ? 1u : (uint32_t)((ss + kBlockSizeMax - 1) / kBlockSizeMax);
+                if (ss >= 7) protoTable = ((size_t)1 << c.hashLog) + (c.strategy == 2 ? ((size_t)1 << c.chainLog) : 0);   // below: raw block, no match finding, no table
+            }
         }
-        e.windowLog = c.windowLog; e.hashLog = c.hashLog; e.chainLog = c.chainLog; e.minMatch = c.minMatch; e.strategy = c.strategy;
-        // ZSTD_fast with an acceleration factor: probe pairs `stepSize` apart (hasStep = targetLength > 1, ZstdFast.cs:101, :334) and
-        // leave the literals uncompressed (ZSTD_literalsCompressionIsDisabled, ZstdCompressInternal.cs:483-498)
-        e.stepSize = (c.strategy == 1 && c.targetLength > 1) ? c.targetLength + 1 : 2;
-        e.rawLits = (c.strategy == 1 && c.targetLength > 0) ? 1u : 0u;
-        if (c.strategy == 0) { nBlk[i] = 0; hr[i] = make_error(kParameterUnsupported); mb = true; continue; }   // level 4 outside its dfast sizes
-        e.nbSeq = 0; e.lastLL = (uint32_t)std::min<size_t>(ss, kBlockSizeMax);
-        e.rep[0] = 1; e.rep[1] = 4;                               // repStartValue (ZstdInternal.cs:13)
-        if (DI) { e.rep[0] = DI->rep[0]; e.rep[1] = DI->rep[1]; mb = true; }     // the dictionary's repcodes; dictionary frames always run as block waves (entropy state)
-        if (ss > kEncMaxFrameBytes) { nBlk[i] = 0; hr[i] = make_error(kSrcSizeWrong); mb = true; continue; }   // positions are 31-bit
-        nBlk[i] = ss <= kBlockSizeMax ? 1u : (uint32_t)((ss + kBlockSizeMax - 1) / kBlockSizeMax);
-        if (nBlk[i] > 1) mb = true;
-        maxWaves = std::max<size_t>(maxWaves, nBlk[i]); totalBlocks += nBlk[i];
-        if (ss < 7) continue;                                     // raw block: no match finding, no table
+        EncItem& e = hi[i];
+        e = proto;
+        e.srcOff = srcOff[i]; e.dstOff = dstOff[i]; e.dstCap = (uint32_t)std::min<size_t>(dstCap[i], 0xFFFFFFF0u);
+        if (DI) mb = true;                                            // dictionary frames always run as block waves (entropy state)
+        nBlk[i] = protoBlk;
+        if (protoErr) { hr[i] = protoErr; mb = true; continue; }
+        if (protoBlk > 1) mb = true;
+        maxWaves = std::max<size_t>(maxWaves, protoBlk); totalBlocks += protoBlk;
         e.tableOff = (uint32_t)tableEntries;
-        tableEntries += ((size_t)1 << c.hashLog) + (c.strategy == 2 ? ((size_t)1 << c.chainLog) : 0);
+        tableEntries += protoTable;
     }
+    lap("items");
     if (tableEntries >= 0xFFFFFFFFull) { t_encErr = "hash-table arena exceeds 32-bit indexing"; return false; }
     // work lists: per wave [ZSTD_fast groups | frames with a dictionary (serial kernel) | ZSTD_dfast groups | entropy]
     struct WaveLists { size_t off[4]; uint32_t n[4]; };
@@ -2784,9 +2814,10 @@ bool enc_enqueue(EncArena& A, cudaStream_t stream, cudaStream_t copyStream, size
             }
         }
     }
-    if (!I.tables.ensure(tableEntries * 4 + 16) || !I.seqLL.ensure(m * (size_t)kEncSeqCap * 4) || !I.seqML.ensure(m * (size_t)kEncSeqCap * 4) ||
-        !I.seqOF.ensure(m * (size_t)kEncSeqCap * 4) || !I.lit.ensure(m * (size_t)kEncLitStride) || !I.stateBits.ensure(m * (size_t)kEncSeqCap * 8) ||
+    if (!I.tables.ensure(tableEntries * 4 + 16) || !I.seqLL.ensure(m * (size_t)seqStride * 4) || !I.seqML.ensure(m * (size_t)seqStride * 4) ||
+        !I.seqOF.ensure(m * (size_t)seqStride * 4) || !I.lit.ensure(m * (size_t)litStride) || !I.stateBits.ensure(m * (size_t)seqStride * 8) ||
         (mb && !I.hufState.ensure(m * 2 * (size_t)kHufStateSlot)) || !I.fseTabs.ensure(m * 3 * sizeof(FseGTable)) || !I.carry.ensure(m * sizeof(EntCarry))) { t_encErr = "out of memory (arena)"; return false; }
+    lap("lists+mem");
     ENC_CUDA(cudaMemcpyAsync(I.items.p, hi, m * sizeof(EncItem), cudaMemcpyHostToDevice, copyStream));
     ENC_CUDA(cudaMemcpyAsync(I.workLists.p, I.hWork.p, listCap * 4, cudaMemcpyHostToDevice, copyStream));
     if (copyStream != stream) {                                   // order the kernels after the two small copies
@@ -2799,13 +2830,14 @@ bool enc_enqueue(EncArena& A, cudaStream_t stream, cudaStream_t copyStream, size
     p.items = (EncItem*)I.items.p; p.nItems = (uint32_t)m; p.src = d_src; p.dst = d_dst; p.tables = (uint32_t*)I.tables.p;
     p.seqLL = (uint32_t*)I.seqLL.p; p.seqML = (uint32_t*)I.seqML.p; p.seqOF = (uint32_t*)I.seqOF.p; p.litBuf = (uint8_t*)I.lit.p;
     p.stateBits = (uint64_t*)I.stateBits.p; p.results = hr; p.hufState = (uint8_t*)I.hufState.p; p.fseTabs = (FseGTable*)I.fseTabs.p; p.carry = (EntCarry*)I.carry.p; p.checksumFlag = checksumFlag ? 1u : 0u;
+    p.seqStride = seqStride; p.litStride = litStride;
     memset(&p.dict, 0, sizeof(p.dict));
     if (DI) {
         p.dict.content = (const uint8_t*)DI->raw.p + DI->contentOff; p.dict.contentLen = DI->contentLen; p.dict.dictID = DI->dictID;
         p.dict.tables = (const uint32_t*)DI->tables.p; p.dict.hashLog = DI->cp.hashLog; p.dict.chainLog = DI->cp.chainLog;
         p.dict.huf = (const uint8_t*)DI->huf.p; p.dict.fse = (const FseGTable*)DI->fse.p;
         uint32_t const entries = (uint32_t)DI->tableEntries;
-        enc_dict_init_kernel<<<dim3(std::max(1u, std::min(64u, entries / 1024)), (unsigned)m), 256, 0, stream>>>(p, (uint32_t)m, entries);
+        enc_dict_init_kernel<<<dim3((unsigned)m, std::max(1u, std::min(64u, entries / 1024))), 256, 0, stream>>>(p, (uint32_t)m, entries);
         *launches += 1;
     }
     const uint32_t* const dw = (const uint32_t*)I.workLists.p;
@@ -2846,6 +2878,7 @@ bool enc_enqueue(EncArena& A, cudaStream_t stream, cudaStream_t copyStream, size
     }
     if (ev3) ENC_CUDA(cudaEventRecord(ev3[2], stream));
     ENC_CUDA(cudaGetLastError());
+    lap("launched");
     return true;
 }
 // Shared-memory carve-out of the encoder's kernels.  An SM keeps ONE L1 / shared-memory split while it has resident CTAs, and a CTA of a
@@ -2893,7 +2926,10 @@ bool enc_compress_device(EncArena& A, cudaStream_t stream, cudaEvent_t* ev, size
     (void)ev;
     float msAll = 0, msMatch = 0, msEnt = 0;
     enc_set_overlap_mode(false);                 // the passes run one after the other on one stream: every kernel keeps its own L1 / shared-memory split
-    EncArena* const ar[2] = {&A, (B && n > kEncMaxItemsPerPass) ? B : &A};
+    size_t maxBlkAll = 0;
+    for (size_t i = 0; i < n; i++) maxBlkAll = std::max(maxBlkAll, std::min<size_t>(srcSize[i], kBlockSizeMax));
+    size_t const passCap = enc_pass_capacity(maxBlkAll);
+    EncArena* const ar[2] = {&A, (B && n > passCap) ? B : &A};
     int const nAr = ar[1] != ar[0] ? 2 : 1;
     struct Pending { bool on = false; size_t base = 0, m = 0; } pend[2];
     for (auto* a : ar) if (!a->impl) a->impl = new EncArenaImpl();
@@ -2915,8 +2951,8 @@ bool enc_compress_device(EncArena& A, cudaStream_t stream, cudaEvent_t* ev, size
         return true;
     };
     int k = 0;
-    for (size_t base = 0; base < n; base += kEncMaxItemsPerPass, k = (k + 1) % nAr) {
-        size_t const m = std::min(kEncMaxItemsPerPass, n - base);
+    for (size_t base = 0; base < n; base += passCap, k = (k + 1) % nAr) {
+        size_t const m = std::min(passCap, n - base);
         if (!finish(k)) return false;
         if (!enc_enqueue(*ar[k], stream, stream, m, level, checksumFlag, d_src, srcOff + base, srcSize + base, d_dst, dstOff + base, dstCap + base, ar[k]->impl->tev, launches, dict)) return false;
         pend[k].on = true; pend[k].base = base; pend[k].m = m;

@@ -40,6 +40,8 @@ bool enc_enqueue(EncArena& A, cudaStream_t stream, cudaStream_t copyStream, size
                  const uint8_t* d_src, const uint64_t* srcOff, const size_t* srcSize,
                  uint8_t* d_dst, const uint64_t* dstOff, const size_t* dstCap, cudaEvent_t* ev3, unsigned* launches, const EncDict* dict = nullptr);
 const uint64_t* enc_results(const EncArena& A);
+// Frames one enc_enqueue pass can hold when its largest block has maxBlockBytes: 8192 at 128 KiB, more for smaller records (up to 65536).
+size_t enc_pass_capacity(size_t maxBlockBytes);
 // Gathers the n variable-size frames into one dense device buffer (A.compactBuf()) at offsets cOff.
 bool enc_compact_device(EncArena& A, cudaStream_t stream, size_t n, const uint8_t* d_dst, const uint64_t* dstOff,
                         const size_t* sizes, const uint64_t* cOff, size_t total, unsigned* launches);
