@@ -2642,7 +2642,7 @@ void EncDict::release()
 size_t enc_dict_digest(EncDict& D, cudaStream_t stream, const void* dict, size_t dictSize, int level)
 {
     D.release();
-    if (dictSize > 0x7FFFFF00u) return (size_t)make_error(kMemoryAllocation);
+    if (dictSize > (1u << 30)) return (size_t)make_error(kMemoryAllocation);     // indices are position + 2 + content length in 32 bits; the reference trims such dictionaries (:5133-5147), this library refuses them
     CParams const cp = get_cparams_dict(level, kSrcSizeUnknown, dictSize, 2);
     if (cp.strategy == 0) return (size_t)make_error(kParameterUnsupported);       // a level outside ZSTD_fast / ZSTD_dfast for this dictionary size
     D.impl = new EncDictImpl();
