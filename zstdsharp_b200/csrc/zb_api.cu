@@ -75,7 +75,7 @@ constexpr int kEvents = 24;
 constexpr int kPipeMax = 8;                    // upper bound of sub-batches in flight in the host-pointer path (one scratch arena + compute stream each)
 static int env_int(const char* name, int def, int lo, int hi) { const char* e = getenv(name); if (!e) return def; int v = atoi(e); return v < lo ? lo : (v > hi ? hi : v); }
 // sub-batches in flight / target sub-batch size (items); tunable for experiments, defaults chosen on B200 (profiles/r01_notes.md)
-static int pipe_depth() { static int v = env_int("ZSTDB200_PIPE", 3, 1, kPipeMax); return v; }
+static int pipe_depth() { static int v = env_int("ZSTDB200_PIPE", 4, 1, kPipeMax); return v; }      // 3 -> 4 with first sub-batch n/32: 24.5 -> 23.8 ms per GiB host to host (profiles/r02_notes.md)
 static size_t pipe_items() { static int v = env_int("ZSTDB200_PIPE_ITEMS", 4096, 16, 8192); return (size_t)v; }
 
 // scratch of one decode pass (DecPass layout, zb_decode.cuh)
@@ -411,7 +411,7 @@ static size_t decompress_batch_host(Engine& E, size_t n, const void* const* src,
     size_t const kPipe = (size_t)pipe_depth(), kPipeItems = scatter ? std::min<size_t>(pipe_items(), (size_t)stageItems) : pipe_items();
     std::vector<size_t> sub;                     // sub-batch k = items [sub[k], sub[k+1])
     {
-        static int const firstDiv = env_int("ZSTDB200_PIPE_FIRST_DIV", 16, 2, 256);
+        static int const firstDiv = env_int("ZSTDB200_PIPE_FIRST_DIV", 32, 2, 256);
         size_t pos = 0, sz = std::max<size_t>(64, std::min(kPipeItems, n / (size_t)firstDiv));
         while (pos < n) {
             size_t take = std::min(sz, n - pos);
