@@ -408,11 +408,15 @@ static size_t decompress_batch_host(Engine& E, size_t n, const void* const* src,
     // stream -- the slowest stage -- then never runs dry; no sub-batch exceeds the configured target ----
     // staged output: the LAST sub-batch's copy-out by host threads is exposed, so sub-batches stay small there
     static int const stageItems = env_int("ZSTDB200_STAGE_ITEMS", 1024, 16, 8192);
-    size_t const kPipe = (size_t)pipe_depth(), kPipeItems = scatter ? std::min<size_t>(pipe_items(), (size_t)stageItems) : pipe_items();
+    // pinned, contiguous buffers: 4 sub-batches in flight, first one n/32; staged (pageable / scattered) buffers keep 3 and n/16, the setting their
+    // host-thread copies were tuned with (an explicit ZSTDB200_PIPE / ZSTDB200_PIPE_FIRST_DIV applies to both)
+    bool const staged = scatter || gather;
+    size_t const kPipe = (staged && !getenv("ZSTDB200_PIPE")) ? 3 : (size_t)pipe_depth(), kPipeItems = scatter ? std::min<size_t>(pipe_items(), (size_t)stageItems) : pipe_items();
     std::vector<size_t> sub;                     // sub-batch k = items [sub[k], sub[k+1])
     {
         static int const firstDiv = env_int("ZSTDB200_PIPE_FIRST_DIV", 32, 2, 256);
-        size_t pos = 0, sz = std::max<size_t>(64, std::min(kPipeItems, n / (size_t)firstDiv));
+        size_t const div = (staged && !getenv("ZSTDB200_PIPE_FIRST_DIV")) ? 16 : (size_t)firstDiv;
+        size_t pos = 0, sz = std::max<size_t>(64, std::min(kPipeItems, n / div));
         while (pos < n) {
             size_t take = std::min(sz, n - pos);
             if (n - pos - take < take / 2) take = n - pos;      // fold a small remainder into the last sub-batch
