@@ -78,3 +78,27 @@ def handbuilt_small_4stream_frames():
         frame = bytes.fromhex("28b52ffd") + bytes([0x20, len(expect)]) + hdr + block
         out.append((frame, bytes(expect)))
     return out
+
+
+def dfast_last_window_case():
+    """A two-block input for ZSTD_dfast (levels 2 / 3 at this size) found by the round-2 soak (seed 993001): the first block is incompressible, so
+    the search step has grown to ~440 bytes at its end; the last position the reference's loop still visits (130562) and the first one that
+    fails the loop condition but still has 8 readable bytes (131005) hold the same 8 bytes.  The reference writes 130562 into the long table;
+    a window-parallel match finder must not let the unvisited position shadow that write.  The second block repeats those bytes behind a decoy
+    that owns the short-table bucket, so only the long table finds the 24-byte match."""
+    rng = np.random.default_rng(20261019)
+    B = 131072
+    a = rng.integers(0, 256, size=B + 400, dtype=np.uint8)
+    ip, step, next_step, last = 1, 1, 1 + 256, None                  # ZstdDoubleFast.cs:100-165: positions of an all-literal block
+    while ip + step <= B - 8:
+        last = ip
+        ip1 = ip + step
+        if ip1 >= next_step:
+            step += 1; next_step += 256
+        ip = ip1
+    assert last == 130562 and ip == 131005
+    marker = a[last:last + 24].copy()
+    a[ip:ip + 16] = marker[:16]
+    a[B + 40:B + 46] = marker[:6]                                     # decoy: same first bytes, different continuation
+    a[B + 86:B + 110] = marker
+    return a

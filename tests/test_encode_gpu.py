@@ -446,3 +446,14 @@ def test_multi_device_codec_with_a_dictionary():
         assert m.WrapBatch(pays[:4]) == [o.compress(p, 3) for p in pays[:4]]
     finally:
         m.Dispose()
+
+
+def test_dfast_write_of_the_last_visited_position(comp):
+    """tests/_cases.py::dfast_last_window_case (found by the soak, seed 993001): the long-table write of the last visited position of a block
+    must survive an unvisited position with the same 8 bytes in the same window."""
+    from _cases import dfast_last_window_case
+    o = oracle()
+    a = dfast_last_window_case()
+    for level in (1, 2, 3):
+        comp.Level = level
+        assert bytes(comp.Wrap(a)) == o.compress(a, level), level

@@ -504,7 +504,10 @@ __global__ void __launch_bounds__(32 * kMatchWarps) enc_match_dfast_group_kernel
         // ---- both tables are written at every position up to the event (:122); the latest position of a bucket wins ----
         {
             uint32_t const lastLane = type < 0 ? (uint32_t)GS - 2 : je;
-            uint32_t const keep = (2u << lastLane) - 1u;
+            // only positions that are visited write: a lane whose loop condition failed but which still had 8 readable bytes takes part in
+            // peersL (its look-up may be the `ip1` of the lane below) and must not shadow a lower lane's write (soak seed 993001: the last
+            // visited position of an incompressible block and the unvisited one behind it held the same 8 bytes)
+            uint32_t const keep = ((2u << lastLane) - 1u) & gballot(probe);
             if (probe && type != 3 && l <= lastLane) {
                 if ((((peersL & keep) >> l) >> 1) == 0) TL[hl] = tab_entry<TAG>((uint32_t)pj + 2, (uint32_t)x);
                 if ((((peersS & keep) >> l) >> 1) == 0) TS[hs] = tab_entry<TAG>((uint32_t)pj + 2, (uint32_t)x);
