@@ -1,4 +1,4 @@
-// zb_encode.cu -- batch Zstandard frame encoder for sm_100a, levels 1..3 (product code; no CPU fallback).
+// zb_encode.cu -- batch Zstandard frame encoder for sm_100a: ZSTD_fast / ZSTD_dfast levels (-131072..-1, 0..3, 4 where it is dfast), with or without a loaded dictionary (product code; no CPU fallback).
 //
 // Replaces, for batches of independent inputs (one frame each: one block up to 128 KiB, a multi-block frame above), the reference's
 //   ZSTD_compress2 -> ZSTD_compressEnd -> ZSTD_compress_frameChunk -> ZSTD_compressBlock_internal   (ZstdCompress.cs:7138,5665,4690,4528)
@@ -17,6 +17,14 @@
 //   enc_entropy_kernel<MB, 1>             CTA  / block       parallel bit scatter of the sequence bitstream, block/frame assembly with the
 //                                                            reference's accept/reject gates (raw / RLE / compressed), state confirmation, XXH64 trailer
 //   enc_compact_kernel                    CTA  / frame       packs the frames densely before D2H
+// With a loaded dictionary (Compressor.LoadDictionary; ZstdCompress.cs:1581-1700, 2725-2900, 5126-5500, 5826-6010):
+//   enc_dict_build_kernel                 thread             the CDict on the device, once per dictionary and level: compression forms of the entropy tables, repeat
+//                                                            modes, match-finder tables filled over the content (dtlm_full)
+//   enc_dict_init_kernel                  grid over frames   per pass: the dictionary's Huffman table into every frame's `prev` slot, the CDict's tables into frames that copy it
+//   enc_match_dict_fast_group_kernel<16>  16 lanes / frame   ZSTD_fast with a dictionary (dictMatchState / extDict), speculative window over the classic loop; block bookkeeping
+//   enc_match_dict_dfast_group_kernel<16> 16 lanes / frame   ZSTD_dfast with a dictionary, two tables, long-table look-up at ip + 1 by the winning position
+//   enc_match_dict_kernel                 warp / frame       serial restatement of the six variants: blocks behind an invalidated dictionary; cross-check of the two above
+// The entropy kernels start such frames from the dictionary's state (Huffman valid / check, set_repeat FSE tables, repcodes, dictionary id in the header).
 // All hash tables live in HBM/L2 (zeroed per frame) and every block of a wave is in flight at once: the parse is a chain of
 // dependent memory round trips per sequence, and only concurrency across frames hides it (profiles/r01_notes.md).
 #include <algorithm>
