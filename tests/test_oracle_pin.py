@@ -204,3 +204,28 @@ def test_streams_that_run_dry_match_libzstd():
         got = o.decompress(f, c["size"])
         assert len(got) == c["size"] and hashlib.sha256(got).hexdigest() == c["sha256"], c["name"]
         assert z.decompress(f, c["size"]) == got
+
+
+def test_dictionary_golden_vectors():
+    """tests/golden/dict_golden.json (written by the reference's libzstd.dll: ZSTD_CCtx_loadDictionary + ZSTD_compress2, see
+    make_dict_golden.py): the oracle's Compressor.LoadDictionary + Wrap frames have the recorded length and SHA-256 -- the pin of
+    SURVEY 8f.4's encode side that travels to machines without the reference tree."""
+    import hashlib
+    from _dict_cases import compress_dictionaries, compress_payloads
+    with open(os.path.join(HERE, "golden", "dict_golden.json")) as f:
+        gold = json.load(f)
+    o = oracle()
+    dicts = compress_dictionaries(libzstd())
+    pays = compress_payloads()
+    usable = {k for k, v in dicts.items() if hashlib.sha256(v).hexdigest() == gold["dictionaries"].get(k)}
+    assert {"raw_50k", "raw_7", "raw_8", "raw_9", "raw_110k", "raw_300k"} <= usable          # the trained ones depend on the trainer's version
+    n = 0
+    for v in gold["vectors"]:
+        if v["dict"] not in usable:
+            continue
+        src = pays[v["payload"]]
+        assert src.size == v["size"]
+        f = o.compress_loaded_dict(src, v["level"], dicts[v["dict"]], checksum=v["checksum"])
+        assert len(f) == v["frame_len"] and hashlib.sha256(f).hexdigest() == v["frame_sha256"], (v["dict"], v["payload"], v["level"])
+        n += 1
+    assert n >= 400

@@ -232,6 +232,16 @@ def test_dictionary_compression_matches_the_dll():
     assert r.error_code(rv) == o.error_code(ro) == 64
 
 
+def test_constructed_encoder_cases_match_the_dll():
+    """tests/_cases.py::dfast_last_window_case (the input behind the round-2 fix of enc_match_dfast_group_kernel): the oracle writes the
+    DLL's bytes for it at every restated level, so the GPU test that uses it is held to the reference."""
+    from _cases import dfast_last_window_case
+    o, r = oracle(), refdll()
+    a = dfast_last_window_case()
+    for level in (-5, 1, 2, 3, 4):
+        assert o.compress(a, level) == r.compress(a, level), level
+
+
 def test_handbuilt_tiny_four_stream_literals():
     """tests/_cases.py::handbuilt_small_4stream_frames: legal frames no zstd encoder writes (four Huffman streams over < 256
     literals), decoded by the oracle and by the DLL to the bytes the construction implies."""
