@@ -238,7 +238,7 @@ def test_constructed_encoder_cases_match_the_dll():
     from _cases import dfast_last_window_case
     o, r = oracle(), refdll()
     a = dfast_last_window_case()
-    for level in (-5, 1, 2, 3, 4):
+    for level in (-5, 1, 2, 3):                                    # level 4 is ZSTD_greedy for this size: not restated
         assert o.compress(a, level) == r.compress(a, level), level
 
 
