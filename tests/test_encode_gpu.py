@@ -223,8 +223,8 @@ def test_independent_chunks_parameter(comp, dec):
 
 
 def test_golden_vectors_on_gpu(comp):
-    """The committed golden vectors (tests/golden/golden_vectors.json, written by libzstd 1.5.5; inputs regenerated by
-    make_golden.inputs()) against the GPU compressor directly, without the oracle in between."""
+    """The committed golden vectors (tests/golden/golden_vectors.json, written by the reference's own libzstd.dll 1.5.1 through oracle/ref_pe;
+    inputs regenerated by make_golden.inputs()) against the GPU compressor directly, without the oracle in between."""
     import hashlib, importlib.util, json, os
     here = os.path.dirname(os.path.abspath(__file__))
     spec = importlib.util.spec_from_file_location("make_golden", os.path.join(here, "golden", "make_golden.py"))
@@ -457,3 +457,4 @@ def test_dfast_write_of_the_last_visited_position(comp):
     for level in (1, 2, 3):
         comp.Level = level
         assert bytes(comp.Wrap(a)) == o.compress(a, level), level
+
